@@ -1,0 +1,58 @@
+"""Build the CUDA C-ABI library in-tree for sm_100a (B200).
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels
+to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libhycom_tsadvc_b200.so")
+SOURCES = ["tsadvc_kernels.cu", "halo.cu", "tsadvc_abi.cu", "synth.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",            # keep the Fortran operation order: no FMA contraction
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fopenmp",
+    "-shared",
+]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps += [os.path.join(HERE, "..", "include", f) for f in os.listdir(os.path.join(HERE, "..", "include"))]
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libhycom_tsadvc_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    # the image exports CC/CXX=/opt/gcc/bin/* (no libgomp.spec); use the distro g++
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

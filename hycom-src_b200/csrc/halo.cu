@@ -1,0 +1,80 @@
+// Halo update of the device mirrors: the device-side xctilr.
+//
+// Single tile (mod_xc_sm.h:1337-1428): closed edges receive vland (0.0),
+// periodic edges wrap.  North/south lines are filled first over i=1..ii, then
+// east/west columns over j=1-nhl..jj+nhl, so corners come from the second pass
+// applied to the lines written by the first.
+#include <cuda_runtime.h>
+
+#include "tsadvc_launch.h"
+
+namespace tsadvc {
+
+// a(i,j) of the Fortran array <-> base[(j-1+nb)*pitch + (i-1+nb)]
+__device__ __forceinline__ long fidx(int i, int j, int nb, int pitch) {
+  return (long)(j - 1 + nb) * pitch + (i - 1 + nb);
+}
+
+__global__ void k_halo_ns(double* __restrict__ base, long slab, int nslab, int pitch, int nb,
+                          int ii, int jj, int nhl, int periodic_j) {
+  const long per = (long)nhl * ii;
+  const long total = per * nslab;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / per);
+    const long q = t - (long)s * per;
+    const int j = (int)(q / ii) + 1;
+    const int i = (int)(q % ii) + 1;
+    double* a = base + slab * s;
+    double vs = 0.0, vn = 0.0;  // vland
+    if (periodic_j) {
+      vs = a[fidx(i, jj + 1 - j, nb, pitch)];
+      vn = a[fidx(i, j, nb, pitch)];
+    }
+    a[fidx(i, 1 - j, nb, pitch)] = vs;
+    a[fidx(i, jj + j, nb, pitch)] = vn;
+  }
+}
+
+__global__ void k_halo_ew(double* __restrict__ base, long slab, int nslab, int pitch, int nb,
+                          int ii, int jj, int mhl, int nhl, int periodic_i) {
+  const int nj = jj + 2 * nhl;
+  const long per = (long)nj * mhl;
+  const long total = per * nslab;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / per);
+    const long q = t - (long)s * per;
+    const int j = (int)(q / mhl) + 1 - nhl;
+    const int i = (int)(q % mhl) + 1;
+    double* a = base + slab * s;
+    double vw = 0.0, ve = 0.0;
+    if (periodic_i) {
+      vw = a[fidx(ii + 1 - i, j, nb, pitch)];
+      ve = a[fidx(i, j, nb, pitch)];
+    }
+    a[fidx(1 - i, j, nb, pitch)] = vw;
+    a[fidx(ii + i, j, nb, pitch)] = ve;
+  }
+}
+
+int launch_halo_local(double* base, long slab, int nslab, int pitch, int nbdy, int ii, int jj,
+                      int mh, int nh, int periodic_i, int periodic_j, cudaStream_t stream) {
+  const int mhl = max(0, min(mh, nbdy)), nhl = max(0, min(nh, nbdy));
+  const int threads = 256;
+  if (nhl > 0) {
+    const long total = (long)nhl * ii * nslab;
+    const int blocks = (int)min((total + threads - 1) / threads, (long)148 * 16);
+    k_halo_ns<<<blocks, threads, 0, stream>>>(base, slab, nslab, pitch, nbdy, ii, jj, nhl,
+                                              periodic_j);
+  }
+  if (mhl > 0) {
+    const long total = (long)(jj + 2 * nhl) * mhl * nslab;
+    const int blocks = (int)min((total + threads - 1) / threads, (long)148 * 16);
+    k_halo_ew<<<blocks, threads, 0, stream>>>(base, slab, nslab, pitch, nbdy, ii, jj, mhl, nhl,
+                                              periodic_i);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tsadvc

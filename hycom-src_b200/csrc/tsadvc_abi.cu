@@ -1,0 +1,510 @@
+// C ABI of the B200 tsadvc path: device mirrors of the mod_cb_arrays fields,
+// host<->device copies, and the tsadvc(m,n) driver (mod_tsadvc.F90:1708-2132)
+// around the marching kernels.  See include/hycom_tsadvc_b200.h.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/hycom_tsadvc_b200.h"
+#include "tsadvc_dev.h"
+#include "tsadvc_handle.h"
+#include "tsadvc_launch.h"
+
+using namespace tsadvc;
+
+namespace {
+
+char g_err[512] = "";
+
+}  // namespace
+
+namespace {
+
+int fail(hycom_tsadvc_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  snprintf(g_err, sizeof g_err, "%s", buf);
+  if (h) snprintf(h->err, sizeof h->err, "%s", buf);
+  return code;
+}
+
+#define CU(h, call)                                                                        \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(h, HYCOM_TSADVC_ECUDA, "%s failed: %s (%s:%d)", #call,                   \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                             \
+  } while (0)
+
+int dalloc(hycom_tsadvc_handle* h, void** p, size_t nbytes, bool zero) {
+  CU(h, cudaSetDevice(h->d.device));
+  cudaError_t e = cudaMalloc(p, nbytes);
+  if (e != cudaSuccess)
+    return fail(h, HYCOM_TSADVC_ENOMEM, "cudaMalloc(%zu) failed: %s", nbytes,
+                cudaGetErrorString(e));
+  h->bytes += (int64_t)nbytes;
+  if (zero) CU(h, cudaMemsetAsync(*p, 0, nbytes, h->stream));
+  return 0;
+}
+
+Mirror* mirror_of(hycom_tsadvc_handle* h, int field, int ktr) {
+  switch (field) {
+    case HYCOM_F_TEMP: return &h->temp;
+    case HYCOM_F_SALN: return &h->saln;
+    case HYCOM_F_TH3D: return &h->th3d;
+    case HYCOM_F_DP: return &h->dp;
+    case HYCOM_F_UFLX: return &h->uflx;
+    case HYCOM_F_VFLX: return &h->vflx;
+    case HYCOM_F_TRACER:
+      if (ktr >= 1 && ktr <= h->d.ntracr) return &h->tracer[ktr - 1];
+      return nullptr;
+  }
+  return nullptr;
+}
+bool is3d(int field) { return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX; }
+
+// device pointer of slot tlev (1,2) of a mirror, allocated on first use
+int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
+  Mirror* mi = mirror_of(h, field, ktr);
+  if (!mi) return fail(h, HYCOM_TSADVC_EINVAL, "bad field %d / ktr %d", field, ktr);
+  const int s = is3d(field) ? 0 : tlev - 1;
+  if (s < 0 || s > 1) return fail(h, HYCOM_TSADVC_EINVAL, "bad time slot %d", tlev);
+  if (!mi->lev[s]) {
+    int rc = dalloc(h, (void**)&mi->lev[s], sizeof(double) * (size_t)h->slab * h->d.kdm, true);
+    if (rc) return rc;
+  }
+  *out = mi->lev[s];
+  return 0;
+}
+
+int spare_of(hycom_tsadvc_handle* h, Mirror* mi, double** out) {
+  if (!mi->spare) {
+    int rc = dalloc(h, (void**)&mi->spare, sizeof(double) * (size_t)h->slab * h->d.kdm, true);
+    if (rc) return rc;
+  }
+  *out = mi->spare;
+  return 0;
+}
+
+int up2d(hycom_tsadvc_handle* h, double** dst, const double* src) {
+  if (!*dst) {
+    int rc = dalloc(h, (void**)dst, sizeof(double) * (size_t)h->slab, true);
+    if (rc) return rc;
+  }
+  CU(h, cudaMemcpy2DAsync(*dst, sizeof(double) * h->pitch, src, sizeof(double) * h->ncols,
+                          sizeof(double) * h->ncols, h->nrows, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+// per-layer salinity range over sea cells with dp > onemm (mod_tsadvc.F90:2065-2084)
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) > v) {
+    const unsigned long long assumed = old;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    if (old == assumed) break;
+  }
+}
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) < v) {
+    const unsigned long long assumed = old;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    if (old == assumed) break;
+  }
+}
+
+__global__ void k_minmax_init(double* mm, int kk) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < kk) {
+    mm[k] = 999.;        // :2069
+    mm[kk + k] = -999.;  // :2070
+  }
+}
+
+__global__ void k_saln_minmax(const double* __restrict__ saln, const double* __restrict__ dp,
+                              const uint8_t* __restrict__ mask, long slab, int pitch, int nrows,
+                              double onemm, double* mm, int kk) {
+  const int k = blockIdx.y;
+  const double* s = saln + slab * k;
+  const double* d = dp + slab * k;
+  double lo = 999., hi = -999.;
+  const long n = (long)pitch * nrows;
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+       q += (long)gridDim.x * blockDim.x) {
+    if ((mask[q] & M_OUT) && d[q] > onemm) {
+      const double v = s[q];
+      lo = lo < v ? lo : v;
+      hi = hi > v ? hi : v;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double l2 = __shfl_xor_sync(0xffffffffu, lo, o);
+    const double h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = lo < l2 ? lo : l2;
+    hi = hi > h2 ? hi : h2;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_f64(&mm[k], lo);
+    atomic_max_f64(&mm[kk + k], hi);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int hycom_tsadvc_abi_version(void) { return HYCOM_TSADVC_ABI_VERSION; }
+
+const char* hycom_tsadvc_last_error(const hycom_tsadvc_handle* h) { return h ? h->err : g_err; }
+
+int hycom_tsadvc_create(const hycom_tsadvc_dims* dims, hycom_tsadvc_handle** out) {
+  if (!dims || !out) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null argument");
+  const hycom_tsadvc_dims& d = *dims;
+  if (d.idm < 1 || d.jdm < 1 || d.kdm < 1 || d.nbdy < 0 || d.ii < 1 || d.jj < 1 ||
+      d.ii > d.idm || d.jj > d.jdm || d.ntracr < 0 || d.ntracr > HYCOM_TSADVC_MXTRCR)
+    return fail(nullptr, HYCOM_TSADVC_EINVAL, "bad dimensions idm=%d jdm=%d kdm=%d nbdy=%d ii=%d jj=%d ntracr=%d",
+                d.idm, d.jdm, d.kdm, d.nbdy, d.ii, d.jj, d.ntracr);
+  if (d.nreg == 2) return fail(nullptr, HYCOM_TSADVC_EUNSUPPORTED, "nreg=2 (arctic tripole) not supported");
+  if (d.nreg < 0 || d.nreg > 4) return fail(nullptr, HYCOM_TSADVC_EINVAL, "bad nreg %d", d.nreg);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(nullptr, HYCOM_TSADVC_ECUDA, "no CUDA device: %s (this library has no CPU path)",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (d.device < 0 || d.device >= ndev)
+    return fail(nullptr, HYCOM_TSADVC_EINVAL, "device %d out of range (%d devices)", d.device, ndev);
+  hycom_tsadvc_handle* h = new (std::nothrow) hycom_tsadvc_handle();
+  if (!h) return fail(nullptr, HYCOM_TSADVC_ENOMEM, "out of host memory");
+  h->d = d;
+  h->err[0] = 0;
+  h->ncols = d.idm + 2 * d.nbdy;
+  h->nrows = d.jdm + 2 * d.nbdy;
+  h->pitch = (h->ncols + 1) & ~1;
+  h->slab = (long)h->pitch * h->nrows;
+  CU(h, cudaSetDevice(d.device));
+  CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  *out = h;
+  return 0;
+}
+
+int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->d.device);
+  cudaDeviceSynchronize();
+  auto rel = [](Mirror& m) { cudaFree(m.lev[0]); cudaFree(m.lev[1]); cudaFree(m.spare); };
+  rel(h->temp); rel(h->saln); rel(h->th3d); rel(h->dp); rel(h->uflx); rel(h->vflx);
+  for (auto& t : h->tracer) rel(t);
+  cudaFree(h->mask); cudaFree(h->scp2); cudaFree(h->scp2i); cudaFree(h->scuy); cudaFree(h->scvx);
+  cudaFree(h->aspux); cudaFree(h->aspvy); cudaFree(h->d_minmax); cudaFree(h->d_sea);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int hycom_tsadvc_set_stream(hycom_tsadvc_handle* h, void* cuda_stream) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  if (h->own_stream && h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  if (cuda_stream) {
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+  } else {
+    CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  return 0;
+}
+
+int hycom_tsadvc_synchronize(hycom_tsadvc_handle* h) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t hycom_tsadvc_device_bytes(const hycom_tsadvc_handle* h) { return h ? h->bytes : 0; }
+int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle* h) { return h ? h->launches : 0; }
+
+int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const double* scp2i,
+                            const double* scuy, const double* scvx, const double* aspux,
+                            const double* aspvy, const int32_t* ip, const int32_t* iu,
+                            const int32_t* iv) {
+  if (!h || !scp2 || !scp2i || !ip || !iu || !iv)
+    return fail(h, HYCOM_TSADVC_EINVAL, "set_static: scp2, scp2i, ip, iu, iv are required");
+  CU(h, cudaSetDevice(h->d.device));
+  int rc;
+  if ((rc = up2d(h, &h->scp2, scp2))) return rc;
+  if ((rc = up2d(h, &h->scp2i, scp2i))) return rc;
+  if (scuy && (rc = up2d(h, &h->scuy, scuy))) return rc;
+  if (scvx && (rc = up2d(h, &h->scvx, scvx))) return rc;
+  if (aspux && (rc = up2d(h, &h->aspux, aspux))) return rc;
+  if (aspvy && (rc = up2d(h, &h->aspvy, aspvy))) return rc;
+  // pack ip/iu/iv and the sea-only neighbour flags (ipim1.. of bigrid.F90:316-341)
+  // into one byte per cell
+  const int nc = h->ncols, nr = h->nrows, nb = h->d.nbdy;
+  std::vector<uint8_t> m((size_t)h->slab, 0);
+  for (int r = 0; r < nr; ++r)
+    for (int c = 0; c < nc; ++c) {
+      const size_t q = (size_t)r * nc + c;
+      unsigned b = 0;
+      if (ip[q] != 0) b |= M_IP;
+      if (iu[q] != 0) b |= M_IU;
+      if (iv[q] != 0) b |= M_IV;
+      if (c > 0 && ip[q - 1] != 0) b |= M_PW;
+      if (c < nc - 1 && ip[q + 1] != 0) b |= M_PE;
+      if (r > 0 && ip[q - nc] != 0) b |= M_PS;
+      if (r < nr - 1 && ip[q + nc] != 0) b |= M_PN;
+      const int i = c + 1 - nb, j = r + 1 - nb;
+      if (ip[q] != 0 && i >= 1 && i <= h->d.ii && j >= 1 && j <= h->d.jj) b |= M_OUT;
+      m[(size_t)r * h->pitch + c] = (uint8_t)b;
+    }
+  if (!h->mask && (rc = dalloc(h, (void**)&h->mask, (size_t)h->slab, true))) return rc;
+  CU(h, cudaMemcpyAsync(h->mask, m.data(), (size_t)h->slab, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->have_static = true;
+  return 0;
+}
+
+int hycom_tsadvc_upload(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
+                        int32_t k0, int32_t nk, const double* host) {
+  if (!h || !host) return fail(h, HYCOM_TSADVC_EINVAL, "upload: null argument");
+  if (k0 < 1 || nk < 1 || k0 + nk - 1 > h->d.kdm)
+    return fail(h, HYCOM_TSADVC_EINVAL, "upload: layers %d..%d out of 1..%d", k0, k0 + nk - 1, h->d.kdm);
+  double* base;
+  int rc = slot(h, field, ktr, tlev, &base);
+  if (rc) return rc;
+  CU(h, cudaMemcpy2DAsync(base + h->slab * (k0 - 1), sizeof(double) * h->pitch, host,
+                          sizeof(double) * h->ncols, sizeof(double) * h->ncols,
+                          (size_t)h->nrows * nk, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int hycom_tsadvc_download(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
+                          int32_t k0, int32_t nk, double* host) {
+  if (!h || !host) return fail(h, HYCOM_TSADVC_EINVAL, "download: null argument");
+  if (k0 < 1 || nk < 1 || k0 + nk - 1 > h->d.kdm)
+    return fail(h, HYCOM_TSADVC_EINVAL, "download: layers %d..%d out of 1..%d", k0, k0 + nk - 1, h->d.kdm);
+  double* base;
+  int rc = slot(h, field, ktr, tlev, &base);
+  if (rc) return rc;
+  CU(h, cudaMemcpy2DAsync(host, sizeof(double) * h->ncols, base + h->slab * (k0 - 1),
+                          sizeof(double) * h->pitch, sizeof(double) * h->ncols,
+                          (size_t)h->nrows * nk, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int hycom_tsadvc_device_slab(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
+                             int32_t k, void** dev_ptr, int64_t* pitch) {
+  if (!h || !dev_ptr) return fail(h, HYCOM_TSADVC_EINVAL, "device_slab: null argument");
+  if (k < 1 || k > h->d.kdm) return fail(h, HYCOM_TSADVC_EINVAL, "device_slab: bad layer %d", k);
+  double* base;
+  int rc = slot(h, field, ktr, tlev, &base);
+  if (rc) return rc;
+  *dev_ptr = base + h->slab * (k - 1);
+  if (pitch) *pitch = h->pitch;
+  return 0;
+}
+
+int hycom_tsadvc_halo_local(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
+                            int32_t mh, int32_t nh) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  const int nreg = h->d.nreg;
+  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
+  const int t0 = is3d(field) ? 1 : (tlev == 0 ? 1 : tlev);
+  const int t1 = is3d(field) ? 1 : (tlev == 0 ? 2 : tlev);
+  for (int t = t0; t <= t1; ++t) {
+    double* base;
+    int rc = slot(h, field, ktr, t, &base);
+    if (rc) return rc;
+    rc = launch_halo_local(base, h->slab, h->d.kdm, h->pitch, h->d.nbdy, h->d.ii, h->d.jj, mh, nh,
+                           per_i, per_j, h->stream);
+    h->launches += 2;
+    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s",
+                        cudaGetErrorString((cudaError_t)rc));
+  }
+  return 0;
+}
+
+int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params* prm, double* xmin, double* xmax) {
+  if (!h || !prm) return fail(h, HYCOM_TSADVC_EINVAL, "step: null argument");
+  if (!h->have_static) return fail(h, HYCOM_TSADVC_EINVAL, "step: set_static has not been called");
+  if (m < 1 || m > 2 || n < 1 || n > 2 || m == n)
+    return fail(h, HYCOM_TSADVC_EINVAL, "step: bad leapfrog slots m=%d n=%d", m, n);
+  const hycom_tsadvc_params& p = *prm;
+  const int aadv = abs(p.advtyp);
+  // mod_tsadvc.F90:24-29, :159-166
+  if (!(aadv == 0 || aadv == 1 || aadv == 2 || aadv == 4))
+    return fail(h, HYCOM_TSADVC_EADVTYP, "error: advem called with advtyp =%4d", p.advtyp);
+  const int mbdy = (aadv == 0) ? 2 : 5;
+  // :1817-1825
+  if (h->d.nbdy < mbdy)
+    return fail(h, HYCOM_TSADVC_ENBDY,
+                "error: nbdy (dimensions.h) must be at least%3d for the advection scheme indicated by advtyp",
+                mbdy);
+  if (aadv == 0 || aadv == 4)
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "advtyp=%d (PCM/FCT4) is not built yet", p.advtyp);
+  if (p.btrmas) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "btrmas (advem_fct2c) is not built yet");
+  if (p.isopyc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc (k=1 flux smoothing) is not built yet");
+  if (p.mxlmy) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "mxlmy (q2,q2l advection) is not built yet");
+  if (p.temdf2 > 0.0) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "temdf2>0 (tsdff_1x/2x) is not built yet");
+  CU(h, cudaSetDevice(h->d.device));
+
+  const int kk = h->d.kdm;
+  const int nhyb = p.nhybrd < 0 ? 0 : (p.nhybrd > kk ? kk : p.nhybrd);
+  // fields to advect, :1855-1857, :1969-2034 (hybrid coordinates)
+  struct Adv { int field, ktr; double posdef; int nlay; };
+  std::vector<Adv> adv;
+  if (p.advflg == 0) { if (nhyb > 0) adv.push_back({HYCOM_F_TEMP, 0, 256.0, nhyb}); }
+  else               { if (nhyb > 0) adv.push_back({HYCOM_F_TH3D, 0, 32.0, nhyb}); }
+  adv.push_back({HYCOM_F_SALN, 0, 0.0, kk});
+  for (int t = 1; t <= h->d.ntracr; ++t)
+    adv.push_back({HYCOM_F_TRACER, t, p.trcflg[t - 1] == 2 ? 256.0 : 0.0, kk});
+  if ((int)adv.size() > kMaxFields) return fail(h, HYCOM_TSADVC_EINVAL, "too many advected fields");
+
+  int rc;
+  // :1827-1836  xctilr of the advected fields (both slots) and the mass fluxes;
+  // "dp halo is up to date".  Multi-tile handles are exchanged by the caller.
+  if (h->d.ipr * h->d.jpr == 1) {
+    for (const Adv& a : adv)
+      if ((rc = hycom_tsadvc_halo_local(h, a.field, a.ktr, 0, mbdy, mbdy))) return rc;
+    if (p.advflg == 0 && h->th3d.lev[0] && h->th3d.lev[1])
+      if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TH3D, 0, 0, mbdy, mbdy))) return rc;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_UFLX, 0, 1, mbdy, mbdy))) return rc;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy))) return rc;
+  }
+
+  MarchParams P;
+  memset(&P, 0, sizeof P);
+  P.nfld = (int)adv.size();
+  P.kk = kk;
+  for (int f = 0; f < P.nfld; ++f) {
+    double *in, *ctr, *out;
+    if ((rc = slot(h, adv[f].field, adv[f].ktr, n, &in))) return rc;
+    if ((rc = slot(h, adv[f].field, adv[f].ktr, m, &ctr))) return rc;
+    if ((rc = spare_of(h, mirror_of(h, adv[f].field, adv[f].ktr), &out))) return rc;
+    P.fld[f].fld = in;
+    P.fld[f].fldc = ctr;
+    P.fld[f].out = out;
+    P.fld[f].posdef = adv[f].posdef;
+    P.fld[f].nlay = adv[f].nlay;
+  }
+  double *u, *v, *dpn;
+  if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &u))) return rc;
+  if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &v))) return rc;
+  if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
+  P.u = u; P.v = v; P.dp = dpn;
+  P.slab = h->slab;
+  P.njobs = P.nfld * kk;
+  P.g.pitch = h->pitch; P.g.ncols = h->ncols; P.g.nrows = h->nrows; P.g.nbdy = h->d.nbdy;
+  P.g.ii = h->d.ii; P.g.jj = h->d.jj;
+  P.g.mask = h->mask; P.g.scp2 = h->scp2; P.g.scp2i = h->scp2i;
+  P.g.delt1 = p.delt1; P.g.onemm = p.onemm;
+  P.nstrips = (h->pitch + 1 + kUse - 1) / kUse;
+  const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
+  P.chunk_rows = ce ? atoi(ce) : 128;
+  if (P.chunk_rows < 8) P.chunk_rows = 8;
+  P.nchunks = (h->nrows + P.chunk_rows - 1) / P.chunk_rows;
+  P.nunits = (long)P.njobs * P.nstrips * P.nchunks;
+  rc = launch_march(aadv, P, h->stream);
+  h->launches += 1;
+  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "march kernel launch failed: %s",
+                      rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "bad scheme");
+
+  // slot n now lives in the ping-pong buffer
+  for (int f = 0; f < P.nfld; ++f) {
+    Mirror* mi = mirror_of(h, adv[f].field, adv[f].ktr);
+    if (adv[f].nlay < kk)  // layers that were not advected keep their values (:2008-2014)
+      CU(h, cudaMemcpyAsync(mi->spare + h->slab * adv[f].nlay, mi->lev[n - 1] + h->slab * adv[f].nlay,
+                            sizeof(double) * (size_t)h->slab * (kk - adv[f].nlay),
+                            cudaMemcpyDeviceToDevice, h->stream));
+    double* t = mi->lev[n - 1];
+    mi->lev[n - 1] = mi->spare;
+    mi->spare = t;
+  }
+
+  // :2065-2094 salinity range, every third step or when diagno
+  if (xmin && xmax && ((p.nstep % 3 == 0) || p.diagno)) {
+    if (!h->d_minmax && (rc = dalloc(h, (void**)&h->d_minmax, sizeof(double) * 2 * kk, false))) return rc;
+    k_minmax_init<<<(kk + 127) / 128, 128, 0, h->stream>>>(h->d_minmax, kk);
+    dim3 grid(148 * 2, kk);
+    k_saln_minmax<<<grid, 256, 0, h->stream>>>(h->saln.lev[n - 1], dpn, h->mask, h->slab, h->pitch,
+                                               h->nrows, p.onemm, h->d_minmax, kk);
+    h->launches += 2;
+    std::vector<double> mm(2 * kk);
+    CU(h, cudaMemcpyAsync(mm.data(), h->d_minmax, sizeof(double) * 2 * kk, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < kk; ++k) { xmin[k] = mm[k]; xmax[k] = mm[kk + k]; }
+  }
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                      double* temp, double* saln, double* th3d, double* tracer, const double* dp,
+                      const double* uflx, const double* vflx, const double* oneta, double* xmin,
+                      double* xmax) {
+  (void)oneta;  // only read when btrmas or temdf2>0 (:1804-1810, :2276), neither built yet
+  if (!h || !prm) return fail(h, HYCOM_TSADVC_EINVAL, "step: null argument");
+  if (m < 1 || m > 2 || n < 1 || n > 2 || m == n)
+    return fail(h, HYCOM_TSADVC_EINVAL, "step: bad leapfrog slots m=%d n=%d", m, n);
+  const int kk = h->d.kdm;
+  const size_t fs = (size_t)h->ncols * h->nrows;  // Fortran slab
+  const bool adv_th3d = prm->advflg != 0;
+  double* first = adv_th3d ? th3d : temp;
+  if (!first || !saln || !dp || !uflx || !vflx || (h->d.ntracr > 0 && !tracer))
+    return fail(h, HYCOM_TSADVC_EINVAL, "step: a required array is NULL");
+  int rc;
+  const int ffield = adv_th3d ? HYCOM_F_TH3D : HYCOM_F_TEMP;
+  for (int t = 1; t <= 2; ++t) {
+    if ((rc = hycom_tsadvc_upload(h, ffield, 0, t, 1, kk, first + fs * kk * (t - 1)))) return rc;
+    if ((rc = hycom_tsadvc_upload(h, HYCOM_F_SALN, 0, t, 1, kk, saln + fs * kk * (t - 1)))) return rc;
+    for (int q = 1; q <= h->d.ntracr; ++q)
+      if ((rc = hycom_tsadvc_upload(h, HYCOM_F_TRACER, q, t, 1, kk,
+                                    tracer + fs * kk * (2 * (size_t)(q - 1) + (t - 1)))))
+        return rc;
+  }
+  if ((rc = hycom_tsadvc_upload(h, HYCOM_F_DP, 0, n, 1, kk, dp + fs * kk * (n - 1)))) return rc;
+  if ((rc = hycom_tsadvc_upload(h, HYCOM_F_UFLX, 0, 1, 1, kk, uflx))) return rc;
+  if ((rc = hycom_tsadvc_upload(h, HYCOM_F_VFLX, 0, 1, 1, kk, vflx))) return rc;
+  if ((rc = hycom_tsadvc_step_device(h, m, n, prm, xmin, xmax))) return rc;
+  // copy back slot n of the advected fields on 1:ii,1:jj ("valid halo 0 wide", :104)
+  auto back = [&](int field, int ktr, double* host_n) -> int {
+    double* base;
+    int r2 = slot(h, field, ktr, n, &base);
+    if (r2) return r2;
+    const int nb = h->d.nbdy;
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr(base, sizeof(double) * h->pitch, h->pitch, h->nrows);
+    cp.dstPtr = make_cudaPitchedPtr(host_n, sizeof(double) * h->ncols, h->ncols, h->nrows);
+    cp.srcPos = make_cudaPos(sizeof(double) * nb, nb, 0);
+    cp.dstPos = make_cudaPos(sizeof(double) * nb, nb, 0);
+    cp.extent = make_cudaExtent(sizeof(double) * h->d.ii, h->d.jj, kk);
+    cp.kind = cudaMemcpyDeviceToHost;
+    CU(h, cudaMemcpy3DAsync(&cp, h->stream));
+    return 0;
+  };
+  if ((rc = back(ffield, 0, first + fs * kk * (n - 1)))) return rc;
+  if ((rc = back(HYCOM_F_SALN, 0, saln + fs * kk * (n - 1)))) return rc;
+  for (int q = 1; q <= h->d.ntracr; ++q)
+    if ((rc = back(HYCOM_F_TRACER, q, tracer + fs * kk * (2 * (size_t)(q - 1) + (n - 1))))) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // extern "C"

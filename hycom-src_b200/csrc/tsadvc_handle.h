@@ -1,0 +1,33 @@
+// private: the handle behind hycom_tsadvc_handle* (shared by tsadvc_abi.cu and synth.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/hycom_tsadvc_b200.h"
+
+namespace tsadvc {
+struct Mirror {
+  double* lev[2] = {nullptr, nullptr};  // time slots 1,2 (3-D fields: lev[0] only)
+  double* spare = nullptr;              // ping-pong target of the next step
+};
+}  // namespace tsadvc
+
+struct hycom_tsadvc_handle {
+  hycom_tsadvc_dims d;
+  int pitch, ncols, nrows;
+  long slab;  // doubles per slab on the device
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t bytes = 0;
+  int64_t launches = 0;
+  bool have_static = false;
+  uint8_t* mask = nullptr;
+  double *scp2 = nullptr, *scp2i = nullptr, *scuy = nullptr, *scvx = nullptr, *aspux = nullptr,
+         *aspvy = nullptr;
+  tsadvc::Mirror temp, saln, th3d, dp, uflx, vflx;
+  tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
+  double* d_minmax = nullptr;  // 2*kdm
+  uint8_t* d_sea = nullptr;    // synthetic generator: global sea mask
+  char err[512];
+};

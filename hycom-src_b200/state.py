@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference interface of the path: mod_cb_arrays state
+(``CbArrays``) and ``tsadvc(m, n)`` (``Tsadvc``), on top of the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import cabi
+from .cabi import Dims, Params, check, load_library
+from .geometry import TileGeom
+
+ONEM = 9806.0  # mod_cb_arrays.F90:842-846
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "arrays must be contiguous in the Fortran (i fastest) layout"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class CbArrays:
+    """The mod_cb_arrays / blkdat fields tsadvc(m,n) reads and writes.
+
+    Shapes (i fastest == Fortran layout): 2-D (nrows, ncols); uflx, vflx
+    (kdm, nrows, ncols); temp, saln, th3d, dp (2, kdm, nrows, ncols); tracer
+    (ntracr, 2, kdm, nrows, ncols); oneta (2, nrows, ncols).
+    """
+    geom: TileGeom
+    ntracr: int = 0
+    # masks / metrics
+    ip: np.ndarray = None
+    iu: np.ndarray = None
+    iv: np.ndarray = None
+    scp2: np.ndarray = None
+    scp2i: np.ndarray = None
+    scuy: np.ndarray = None
+    scvx: np.ndarray = None
+    aspux: np.ndarray = None
+    aspvy: np.ndarray = None
+    # state
+    temp: np.ndarray = None
+    saln: np.ndarray = None
+    th3d: np.ndarray = None
+    dp: np.ndarray = None
+    tracer: np.ndarray = None
+    uflx: np.ndarray = None
+    vflx: np.ndarray = None
+    oneta: np.ndarray = None
+    # blkdat scalars (defaults = the benchmark configuration: FCT2, T&S, hybrid)
+    advtyp: int = 2
+    advflg: int = 0
+    btrmas: bool = False
+    nhybrd: int = -1          # -1: kdm
+    hybrid: bool = True
+    isopyc: bool = False
+    mxlmy: bool = False
+    nstep: int = 1
+    diagno: bool = False
+    trcflg: list = field(default_factory=list)
+    delt1: float = 480.0
+    temdf2: float = 0.0
+    temdfc: float = 1.0
+    thbase: float = 34.0
+    onemm: float = ONEM * 0.001
+
+    def params(self) -> Params:
+        p = Params()
+        p.advtyp, p.advflg, p.btrmas = self.advtyp, self.advflg, int(self.btrmas)
+        p.nhybrd = self.geom.kdm if self.nhybrd < 0 else self.nhybrd
+        p.hybrid, p.isopyc, p.mxlmy = int(self.hybrid), int(self.isopyc), int(self.mxlmy)
+        p.nstep, p.diagno = self.nstep, int(self.diagno)
+        for q in range(cabi.MXTRCR):
+            p.trcflg[q] = self.trcflg[q] if q < len(self.trcflg) else 0
+        p.delt1, p.temdf2, p.temdfc = self.delt1, self.temdf2, self.temdfc
+        p.thbase, p.onemm = self.thbase, self.onemm
+        return p
+
+
+class Tsadvc:
+    """``tsadvc(m, n)`` of mod_tsadvc.F90 on a B200.
+
+    ``Tsadvc(cb).tsadvc(m, n)`` is the drop-in call: same argument meaning as the
+    reference (m, n = 1-based leapfrog slots; slot n holds t-1 on entry and t+1 on
+    exit), operands taken from ``cb`` the way the Fortran takes them from
+    mod_cb_arrays, XcStop raised where the reference calls xcstop.
+    ``tsadvc_device`` is the same step on the device-resident mirrors.
+    """
+
+    def __init__(self, cb: CbArrays, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        self.cb = cb
+        g = cb.geom
+        d = Dims(idm=g.idm, jdm=g.jdm, kdm=g.kdm, nbdy=g.nbdy, ii=g.ii, jj=g.jj, i0=g.i0, j0=g.j0,
+                 itdm=g.itdm, jtdm=g.jtdm, nreg=g.nreg, ipr=g.ipr, jpr=g.jpr, mproc=g.mproc,
+                 nproc=g.nproc, ntracr=cb.ntracr, device=device)
+        self.dims = d
+        h = C.c_void_p()
+        check(self.lib, None, self.lib.hycom_tsadvc_create(C.byref(d), C.byref(h)))
+        self.h = h
+        if stream is not None:
+            self.set_stream(stream)
+        self.xmin = np.full(g.kdm, np.nan)
+        self.xmax = np.full(g.kdm, np.nan)
+        if cb.ip is not None:
+            self.set_static()
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hycom_tsadvc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        check(self.lib, self.h, rc)
+
+    # -- plumbing ---------------------------------------------------------
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.lib.hycom_tsadvc_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.lib.hycom_tsadvc_synchronize(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.hycom_tsadvc_device_bytes(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.hycom_tsadvc_launch_count(self.h))
+
+    def set_static(self):
+        cb = self.cb
+        self._ck(self.lib.hycom_tsadvc_set_static(
+            self.h, _ptr(cb.scp2), _ptr(cb.scp2i), _ptr(cb.scuy), _ptr(cb.scvx), _ptr(cb.aspux),
+            _ptr(cb.aspvy), _ptr(cb.ip), _ptr(cb.iu), _ptr(cb.iv)))
+
+    def upload(self, fld: int, host: np.ndarray, tlev: int = 1, ktr: int = 0, k0: int = 1):
+        nk = host.shape[0] if host.ndim == 3 else 1
+        self._ck(self.lib.hycom_tsadvc_upload(self.h, fld, ktr, tlev, k0, nk, _ptr(host)))
+
+    def download(self, fld: int, tlev: int = 1, ktr: int = 0, k0: int = 1, nk: Optional[int] = None):
+        g = self.cb.geom
+        nk = g.kdm - k0 + 1 if nk is None else nk
+        out = np.empty((nk, g.nrows, g.ncols))
+        self._ck(self.lib.hycom_tsadvc_download(self.h, fld, ktr, tlev, k0, nk, _ptr(out)))
+        return out
+
+    def upload_state(self, m: int, n: int):
+        """push every operand of tsadvc(m,n) to the device mirrors"""
+        cb = self.cb
+        first, ff = (cb.th3d, cabi.F_TH3D) if cb.advflg else (cb.temp, cabi.F_TEMP)
+        for t in (1, 2):
+            self.upload(ff, first[t - 1], t)
+            self.upload(cabi.F_SALN, cb.saln[t - 1], t)
+            for q in range(cb.ntracr):
+                self.upload(cabi.F_TRACER, cb.tracer[q, t - 1], t, ktr=q + 1)
+        self.upload(cabi.F_DP, cb.dp[n - 1], n)
+        self.upload(cabi.F_UFLX, cb.uflx, 1)
+        self.upload(cabi.F_VFLX, cb.vflx, 1)
+
+    # -- the path ---------------------------------------------------------
+    def tsadvc(self, m: int, n: int):
+        """tsadvc(m,n) on the host arrays of ``cb`` (copies in, computes, copies out)."""
+        cb = self.cb
+        p = cb.params()
+        self._ck(self.lib.hycom_tsadvc_step(
+            self.h, m, n, C.byref(p), _ptr(cb.temp), _ptr(cb.saln), _ptr(cb.th3d), _ptr(cb.tracer),
+            _ptr(cb.dp), _ptr(cb.uflx), _ptr(cb.vflx), _ptr(cb.oneta), _ptr(self.xmin),
+            _ptr(self.xmax)))
+
+    def tsadvc_device(self, m: int, n: int, diag: bool = True):
+        """tsadvc(m,n) on the device mirrors (no host<->device traffic)."""
+        p = self.cb.params()
+        xm = _ptr(self.xmin) if diag else None
+        xx = _ptr(self.xmax) if diag else None
+        self._ck(self.lib.hycom_tsadvc_step_device(self.h, m, n, C.byref(p), xm, xx))

@@ -1,0 +1,153 @@
+/*
+ * hycom_tsadvc_b200.h -- C ABI of the B200-native tsadvc(m,n) hot path.
+ *
+ * The reference (HYCOM-src) has no plugin / FFI interface: the boundary of this
+ * path is the Fortran module procedure `mod_tsadvc::tsadvc(m,n)`
+ * (mod_tsadvc.F90:21-22,1708-1712), called once per baroclinic step from
+ * HYCOM_Run (mod_hycom.F90:2535-2537), which finds all of its operands in
+ * mod_cb_arrays / mod_dimensions / mod_xc.  A drop-in therefore replaces the
+ * file mod_tsadvc.F90 by a thin ISO_C_BINDING shim (fortran/mod_tsadvc_b200.F90,
+ * shown in INTEGRATION.md) that hands `c_loc` of those arrays to the entry
+ * points below.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Array arguments are pointers to the FIRST element of the full Fortran array
+ * (c_loc(temp) == &temp(1-nbdy,1-nbdy,1,1)), column-major, reals are
+ * real(8) (-fdefault-real-8, config/generic-gnu-relo_one:22), integers int32:
+ *   2-D  a(1-nbdy:idm+nbdy, 1-nbdy:jdm+nbdy)
+ *   3-D  a(.., .., kdm)            uflx, vflx      (mod_cb_arrays.F90:147-174)
+ *   4-D  a(.., .., kdm, 2)         temp, saln, th3d, dp  (mod_cb_arrays.F90:14-33)
+ *   5-D  tracer(.., .., kdm, 2, ntracr)
+ *   (.., .., 2)                    oneta           (mod_cb_arrays.F90:135-137)
+ * m and n are the 1-based leapfrog slots of tsadvc(m,n): (:,:,:,n) holds time
+ * level t-1 on entry and t+1 on exit, (:,:,:,m) holds t (mod_tsadvc.F90:1717-1728).
+ *
+ * Every function returns 0 on success or a HYCOM_TSADVC_E* code; the message is
+ * available from hycom_tsadvc_last_error().  The reference's error behaviour
+ * (print on mnproc==1, then `call xcstop('tsadvc')`, mod_tsadvc.F90:1817-1825
+ * and :159-166) is reproduced by the shim from the non-zero return.
+ * Like the reference routine, calls are collective over all tiles and not
+ * re-entrant for one handle.
+ */
+#ifndef HYCOM_TSADVC_B200_H
+#define HYCOM_TSADVC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYCOM_TSADVC_ABI_VERSION 1
+#define HYCOM_TSADVC_MXTRCR 16
+
+enum {
+  HYCOM_TSADVC_OK = 0,
+  HYCOM_TSADVC_EINVAL = 1,       /* bad argument */
+  HYCOM_TSADVC_ECUDA = 2,        /* CUDA runtime error or no usable device */
+  HYCOM_TSADVC_EUNSUPPORTED = 3, /* valid in the reference, not built here yet */
+  HYCOM_TSADVC_ENBDY = 4,        /* nbdy < mbdy_advtyp: xcstop('tsadvc') :1817-1825 */
+  HYCOM_TSADVC_EADVTYP = 5,      /* advem called with bad advtyp: xcstop('advem') :159-166 */
+  HYCOM_TSADVC_ENOMEM = 6
+};
+
+/* fields of mod_cb_arrays mirrored on the device */
+enum {
+  HYCOM_F_TEMP = 0,
+  HYCOM_F_SALN = 1,
+  HYCOM_F_TH3D = 2,
+  HYCOM_F_DP = 3,
+  HYCOM_F_UFLX = 4,   /* 3-D: tlev ignored */
+  HYCOM_F_VFLX = 5,   /* 3-D: tlev ignored */
+  HYCOM_F_TRACER = 6  /* with ktr = 1..ntracr */
+};
+
+/* mod_dimensions.F90:33,45-49 + mod_xc tile geometry (mod_xc_mp.h:2317-3288) */
+typedef struct hycom_tsadvc_dims {
+  int32_t idm, jdm, kdm, nbdy;  /* array extents of this tile, halo width (6) */
+  int32_t ii, jj;               /* tile extents actually used (<= idm, jdm) */
+  int32_t i0, j0;               /* offset of the tile in the global grid */
+  int32_t itdm, jtdm;           /* global extents */
+  int32_t nreg;                 /* mod_xc.F90:25-31: 0 closed, 1 periodic in i,
+                                   3 periodic in i and j (f-plane), 4 closed f-plane */
+  int32_t ipr, jpr;             /* number of tiles in i and j */
+  int32_t mproc, nproc;         /* 1-based tile coordinates */
+  int32_t ntracr;               /* number of tracers (<= HYCOM_TSADVC_MXTRCR) */
+  int32_t device;               /* CUDA device ordinal */
+} hycom_tsadvc_dims;
+
+/* run-time scalars tsadvc reads (blkdat.F90; mod_cb_arrays.F90:358-365,813-833) */
+typedef struct hycom_tsadvc_params {
+  int32_t advtyp;  /* 0 PCM, 1 MPDATA, 2 FCT2, 4 FCT4 */
+  int32_t advflg;  /* 0 advect T&S, 1 advect th3d&S */
+  int32_t btrmas, nhybrd, hybrid, isopyc, mxlmy;
+  int32_t nstep, diagno;
+  int32_t trcflg[HYCOM_TSADVC_MXTRCR];
+  double delt1;    /* dt2 of advem */
+  double temdf2, temdfc, thbase, onemm;
+} hycom_tsadvc_params;
+
+typedef struct hycom_tsadvc_handle hycom_tsadvc_handle;
+
+int hycom_tsadvc_abi_version(void);
+const char *hycom_tsadvc_last_error(const hycom_tsadvc_handle *h);
+
+/* device mirrors + scratch are owned by the handle (the analogue of the lazily
+ * allocated module scratch, mod_tsadvc.F90:110-147); allocation is lazy */
+int hycom_tsadvc_create(const hycom_tsadvc_dims *dims, hycom_tsadvc_handle **out);
+int hycom_tsadvc_destroy(hycom_tsadvc_handle *h);
+/* run all work of this handle on a caller-owned cudaStream_t (NULL: own stream) */
+int hycom_tsadvc_set_stream(hycom_tsadvc_handle *h, void *cuda_stream);
+int hycom_tsadvc_synchronize(hycom_tsadvc_handle *h);
+/* bytes of device memory currently held (the mem_stat_add ledger,
+ * mod_tsadvc.F90:129) */
+int64_t hycom_tsadvc_device_bytes(const hycom_tsadvc_handle *h);
+
+/* grid metrics and land/sea masks: scp2, scp2i (geopar.F90:311-340), ip, iu, iv
+ * (bigrid.F90:193-297), host pointers, halos valid.  scuy..aspvy (diffusion)
+ * may be NULL. */
+int hycom_tsadvc_set_static(hycom_tsadvc_handle *h, const double *scp2,
+                            const double *scp2i, const double *scuy,
+                            const double *scvx, const double *aspux,
+                            const double *aspvy, const int32_t *ip,
+                            const int32_t *iu, const int32_t *iv);
+
+/* THE drop-in entry: tsadvc(m,n) on host arrays (mod_tsadvc.F90:1708).
+ * Copies temp/saln(/th3d/tracer) both time levels, dp(:,:,:,n), uflx, vflx to
+ * the device, refreshes the halos, advects, and copies (:,:,:,n) of the advected
+ * fields back on 1:ii,1:jj.  xmin/xmax (kdm reals, may be NULL) receive the
+ * per-layer salinity range when mod(nstep,3)==0 or diagno (:2065-2094). */
+int hycom_tsadvc_step(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                      const hycom_tsadvc_params *prm, double *temp,
+                      double *saln, double *th3d, double *tracer,
+                      const double *dp, const double *uflx, const double *vflx,
+                      const double *oneta, double *xmin, double *xmax);
+
+/* device-resident variant: operands already in the handle's device mirrors */
+int hycom_tsadvc_step_device(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params *prm, double *xmin,
+                             double *xmax);
+
+/* host <-> device mirror copies of nk layers starting at layer k0 (1-based) of
+ * time slot tlev (1 or 2).  `host` points at nk consecutive Fortran slabs. */
+int hycom_tsadvc_upload(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
+                        int32_t tlev, int32_t k0, int32_t nk, const double *host);
+int hycom_tsadvc_download(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
+                          int32_t tlev, int32_t k0, int32_t nk, double *host);
+/* device address of one slab of a mirror and its row pitch in doubles */
+int hycom_tsadvc_device_slab(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
+                             int32_t tlev, int32_t k, void **dev_ptr,
+                             int64_t *pitch);
+
+/* xctilr(a,1,ld,mh,nh,halo_ps) for one mirror on a single tile (closed: vland,
+ * periodic: wrap; mod_xc_sm.h:1337-1428).  step/step_device call this
+ * themselves when ipr*jpr == 1. */
+int hycom_tsadvc_halo_local(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
+                            int32_t tlev_or_0_for_both, int32_t mh, int32_t nh);
+
+/* number of kernels this library launched on the handle since creation */
+int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,126 @@
+/*
+ * oracle/tsadvc_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C99) of HYCOM's tsadvc(m,n) path:
+ *   mod_tsadvc.F90 (tsadvc, advem, advem_pcm, advem_mpdata, advem_fct2,
+ *   advem_fct4, tsdff_1x/2x), bigrid.F90 (masks, sea-only neighbours, segment
+ *   tables), mod_xc_sm.h / mod_xc_mp.h (xctilr), geopar.F90:311-340 (metrics).
+ *
+ * PARITY UNPINNED: the reference ships no golden vectors, no tests and no input
+ * decks, and no Fortran compiler exists in this image, so this restatement
+ * cannot be checked against the reference binary.  Its fidelity is argued by
+ * construction (same sweeps, same margins, same operation order, same scratch
+ * arrays, each function citing the Fortran lines it follows), by an independent
+ * second restatement in numpy (oracle/np_restatement.py) that must agree with
+ * it bit-for-bit, and by the invariants the reference itself relies on
+ * (SURVEY.md section 4).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.
+ */
+#ifndef TSADVC_ORACLE_H
+#define TSADVC_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MXTRCR 16
+
+/* One tile's view of mod_dimensions + mod_xc + mod_cb_arrays + the module-level
+ * scratch of mod_tsadvc.  2-D slabs are (idm+2*nbdy)*(jdm+2*nbdy), Fortran
+ * column-major with lower bounds 1-nbdy (mod_dimensions.F90:62-84). */
+typedef struct orc_tile {
+  /* mod_dimensions.F90:33,45-49 */
+  int idm, jdm, kdm, nbdy, ms;
+  int ii, jj, kk, i0, j0, itdm, jtdm;
+  /* mod_xc.F90:25-31 */
+  int nreg, mnproc;
+  /* masks, sea-only neighbour indices, segment tables (bigrid.F90) */
+  int *ip, *iu, *iv, *iq;
+  int *ipim1, *ipip1, *ipjm1, *ipjp1;
+  int *ifp, *ilp, *isp, *jfp, *jlp, *jsp;
+  /* metrics (geopar.F90:311-340) */
+  double *scp2, *scp2i, *scuy, *scvx, *aspux, *aspvy;
+  /* prognostic state (mod_cb_arrays.F90:14-33,118,135-137,147-174) */
+  double *temp, *saln, *th3d, *dp;   /* (P,kdm,2) */
+  double *tracer;                    /* (P,kdm,2,ntracr) */
+  double *uflx, *vflx;               /* (P,kdm) */
+  double *oneta, *onetamas;          /* (P,2) */
+  double *uflux, *vflux, *uflux2, *vflux2, *util1, *util2; /* (P) */
+  /* run-time scalars (blkdat) */
+  int advtyp, advflg, btrmas, nhybrd, hybrid, isopyc, mxlmy, ntracr, nstep,
+      diagno;
+  int trcflg[ORC_MXTRCR];
+  double delt1, temdf2, temdfc, thbase, onemm;
+  /* mod_tsadvc.F90:38-51 scratch */
+  double *fmx, *fmn, *flx, *fly, *fldlo, *fmxlo, *fmnlo, *fax, *fay, *rp, *rm,
+      *flxdiv, *tx1, *ty1, *fldao, *fldan;
+  /* diagnostics (mod_tsadvc.F90:2065-2084) */
+  double *xmin, *xmax;               /* (kdm) */
+  int xminmax_valid;
+  /* OpenMP threads used by the sweeps (0 = runtime default) */
+  int nthreads;
+} orc_tile;
+
+orc_tile *orc_tile_create(int idm, int jdm, int kdm, int nbdy, int ii, int jj,
+                          int i0, int j0, int itdm, int jtdm, int nreg,
+                          int ntracr);
+void orc_tile_destroy(orc_tile *t);
+/* field access by mod_cb_arrays name ("temp", "ip", "fldlo", ...) */
+double *orc_f64(orc_tile *t, const char *name);
+int *orc_i32(orc_tile *t, const char *name);
+int64_t orc_slab(const orc_tile *t); /* P */
+/* run-time scalars by blkdat name ("advtyp", "delt1", ...) */
+int orc_set_i(orc_tile *t, const char *name, int v);
+int orc_get_i(const orc_tile *t, const char *name);
+int orc_set_d(orc_tile *t, const char *name, double v);
+
+/* mod_xc_sm.h:1337-1428  single-tile halo update (closed: vland=0, periodic) */
+void orc_xctilr(const orc_tile *t, double *a, int l1, int ld, int mh, int nh);
+/* mod_xc_mp.h:4664-4987 emulated over an ipr x jpr array of tiles living in one
+ * address space: a[m + ipr*n] is the same field on tile (m,n), 0-based. */
+void orc_world_xctilr(int ipr, int jpr, orc_tile *const *tiles,
+                      double *const *a, int l1, int ld, int mh, int nh);
+
+/* bigrid.F90:116-386; depth is a P-sized slab whose interior 1..ii,1..jj is set.
+ * stage1: halo of depth must be current; builds ip and interior iu/iv/iq and
+ *         leaves iu/iv/iq as reals in util1/util2/uflux for the halo update.
+ * stage2: after the halo update of those three; finishes masks, neighbours,
+ *         segment tables.  orc_bigrid = single-tile driver doing both. */
+int orc_bigrid_stage1(orc_tile *t, double *depth);
+int orc_bigrid_stage2(orc_tile *t);
+int orc_bigrid(orc_tile *t, double *depth);
+
+/* geopar.F90:311-340 : scp2, scp2i, aspux, aspvy from scpx,scpy,scux,scuy,
+ * scvx,scvy (all P-sized, halos valid). */
+void orc_geopar_metrics(orc_tile *t, const double *scpx, const double *scpy,
+                        const double *scux, const double *scuy,
+                        const double *scvx, const double *scvy);
+
+/* mod_tsadvc.F90:69-205 */
+int orc_advem(orc_tile *t, int advtyp, double *fld, const double *fldc,
+              const double *u, const double *v, const double *fco,
+              const double *fcn, double posdef, const double *scal,
+              const double *scali, double dt2, int btrmas);
+
+/* mod_tsadvc.F90:1708-2258.  m,n are the 1-based leapfrog slots.
+ * do_halo=1: call the single-tile xctilr exactly where the reference does;
+ * do_halo=0: the caller has already refreshed the halos (multi-tile emulation,
+ *            orc_tsadvc_halo_list + orc_world_xctilr). Returns 0 or an error. */
+int orc_tsadvc(orc_tile *t, int m, int n, int do_halo);
+
+/* intermediate taps: the places the reference put pipe_compare_sym* hooks
+ * (mod_tsadvc.F90:286-294,358-362,798-802,983-987).  When a tap buffer is set,
+ * the named scratch slab is copied into it each time that hook is passed. */
+void orc_set_tap(const char *tag, double *buf);
+void orc_clear_taps(void);
+
+const char *orc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
