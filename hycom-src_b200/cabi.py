@@ -80,6 +80,8 @@ PROTOTYPES = {
                                            C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "hycom_tsadvc_halo_local": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "hycom_tsadvc_launch_count": (C.c_int64, [_vp]),
+    "hycom_tsadvc_set_timing": (C.c_int, [_vp, C.c_int32]),
+    "hycom_tsadvc_get_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "hycom_synth_sea_mask": (C.c_int, [C.POINTER(SynthCfg), _vp]),
     "hycom_synth_fill_host": (C.c_int, [C.POINTER(SynthCfg), C.POINTER(SynthTile), _vp,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

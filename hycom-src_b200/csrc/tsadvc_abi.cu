@@ -208,6 +208,8 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   for (auto& t : h->tracer) rel(t);
   cudaFree(h->mask); cudaFree(h->scp2); cudaFree(h->scp2i); cudaFree(h->scuy); cudaFree(h->scvx);
   cudaFree(h->aspux); cudaFree(h->aspvy); cudaFree(h->d_minmax); cudaFree(h->d_sea);
+  for (auto* v : {&h->ev_pending, &h->ev_free})
+    for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -236,6 +238,31 @@ int hycom_tsadvc_synchronize(hycom_tsadvc_handle* h) {
 }
 
 int64_t hycom_tsadvc_device_bytes(const hycom_tsadvc_handle* h) { return h ? h->bytes : 0; }
+
+int hycom_tsadvc_set_timing(hycom_tsadvc_handle* h, int32_t enable) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  h->timing = enable != 0;
+  return 0;
+}
+
+int hycom_tsadvc_get_timing(hycom_tsadvc_handle* h, double* march_ms, int64_t* march_launches,
+                            int32_t reset) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  CU(h, cudaSetDevice(h->d.device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (auto& ev : h->ev_pending) {
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, ev.first, ev.second));
+    h->march_ms += ms;
+    h->march_n += 1;
+    h->ev_free.push_back(ev);
+  }
+  h->ev_pending.clear();
+  if (march_ms) *march_ms = h->march_ms;
+  if (march_launches) *march_launches = h->march_n;
+  if (reset) { h->march_ms = 0.0; h->march_n = 0; }
+  return 0;
+}
 int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle* h) { return h ? h->launches : 0; }
 
 int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const double* scp2i,
@@ -420,8 +447,18 @@ int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   if (P.chunk_rows < 8) P.chunk_rows = 8;
   P.nchunks = (h->nrows + P.chunk_rows - 1) / P.chunk_rows;
   P.nunits = (long)P.njobs * P.nstrips * P.nchunks;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (h->timing) {
+    if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
+    else { CU(h, cudaEventCreate(&ev.first)); CU(h, cudaEventCreate(&ev.second)); }
+    CU(h, cudaEventRecord(ev.first, h->stream));
+  }
   rc = launch_march(aadv, P, h->stream);
   h->launches += 1;
+  if (h->timing) {
+    CU(h, cudaEventRecord(ev.second, h->stream));
+    h->ev_pending.push_back(ev);
+  }
   if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "march kernel launch failed: %s",
                       rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "bad scheme");
 

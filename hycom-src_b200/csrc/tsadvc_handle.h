@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <utility>
+#include <vector>
 
 #include "../../include/hycom_tsadvc_b200.h"
 
@@ -29,5 +31,10 @@ struct hycom_tsadvc_handle {
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
   double* d_minmax = nullptr;  // 2*kdm
   uint8_t* d_sea = nullptr;    // synthetic generator: global sea mask
+  // optional per-launch timing of the marching kernel (hycom_tsadvc_set_timing)
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+  double march_ms = 0.0;
+  int64_t march_n = 0;
   char err[512];
 };

@@ -139,6 +139,15 @@ class Tsadvc:
     def launch_count(self) -> int:
         return int(self.lib.hycom_tsadvc_launch_count(self.h))
 
+    def set_timing(self, enable: bool = True):
+        self._ck(self.lib.hycom_tsadvc_set_timing(self.h, int(enable)))
+
+    def get_timing(self, reset: bool = False):
+        """(accumulated device ms of the marching kernel, launches) since the last reset"""
+        ms, nl = C.c_double(0.0), C.c_int64(0)
+        self._ck(self.lib.hycom_tsadvc_get_timing(self.h, C.byref(ms), C.byref(nl), int(reset)))
+        return ms.value, nl.value
+
     def set_static(self):
         cb = self.cb
         self._ck(self.lib.hycom_tsadvc_set_static(

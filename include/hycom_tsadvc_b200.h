@@ -147,6 +147,16 @@ int hycom_tsadvc_halo_local(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
 /* number of kernels this library launched on the handle since creation */
 int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle *h);
 
+/* the analogue of the reference's xctmr0/xctmr1 accumulators (timer 41 = tsadvc,
+ * mod_hycom.F90:2535-2537; mod_xc_sm.h:1431-1538), at kernel granularity: when
+ * enabled, every launch of the marching kernel is bracketed by CUDA events on the
+ * handle's stream.  hycom_tsadvc_get_timing synchronises the stream and returns
+ * the accumulated device time (ms) and the number of launches since the last
+ * reset; reset != 0 clears the accumulators. */
+int hycom_tsadvc_set_timing(hycom_tsadvc_handle *h, int32_t enable);
+int hycom_tsadvc_get_timing(hycom_tsadvc_handle *h, double *march_ms,
+                            int64_t *march_launches, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,233 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Bar (BASELINE.json north_star): <= 1e-12 relative
+max error per field and layer, land cells bit-unchanged.  The kernels keep the
+reference's operation order without FMA contraction, so the tests additionally demand
+bit equality with the unfused oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from util import pkg, syn, cabi, REL_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(cb, g, got, ref, n, names, exact=True):
+    msk = util.interior_sea(cb)
+    land = ~msk
+    worst = 0.0
+    for name in names:
+        a, b = got[name], ref[name]
+        for k in range(g.kdm):
+            e = util.rel_err(a[n - 1, k], b[n - 1, k], msk)
+            worst = max(worst, e)
+            assert e <= REL_TOL, (name, k, e)
+            if exact:
+                assert np.array_equal(a[n - 1, k][msk], b[n - 1, k][msk]), (name, k, "not bit-exact")
+    return worst
+
+
+def _run_host_path(cb, m, n):
+    """the drop-in call on host arrays; returns the updated arrays"""
+    ts = pkg.Tsadvc(cb)
+    before = {k: getattr(cb, k).copy() for k in ("temp", "saln", "th3d")}
+    if cb.ntracr:
+        before["tracer"] = cb.tracer.copy()
+    ts.tsadvc(m, n)
+    got = dict(temp=cb.temp, saln=cb.saln, th3d=cb.th3d, tracer=cb.tracer, xmin=ts.xmin.copy(),
+               xmax=ts.xmax.copy())
+    launches = ts.launch_count
+    ts.close()
+    return got, before, launches
+
+
+CASES = [
+    # itdm, jtdm, kdm, nreg, ntracr, advtyp, extra
+    (150, 150, 22, 0, 0, 2, {}),                 # BASELINE configs[0]: box basin, FCT2 T+S
+    (150, 150, 22, 0, 2, 1, {"trcflg": [0, 2]}), # MPDATA + tracers
+    (131, 77, 3, 3, 1, 2, {}),                   # doubly periodic f-plane, odd row length
+    (64, 203, 2, 1, 0, 2, {}),                   # periodic in i only, many rows (chunk seams)
+    (200, 60, 2, 4, 0, 1, {}),                   # closed f-plane (periodic in j), strip seams
+    (9, 8, 2, 0, 0, 2, {}),                      # tiny
+    (58, 31, 4, 0, 1, 2, {"nhybrd": 2}),         # temp only in the top nhybrd layers
+    (70, 45, 3, 0, 0, 2, {"advflg": 1}),         # advect th3d & S
+    (70, 45, 3, 0, 0, 1, {"advflg": 1}),
+]
+
+
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,ntracr,advtyp,extra", CASES)
+def test_tsadvc_host_path_matches_oracle(oracle, itdm, jtdm, kdm, nreg, ntracr, advtyp, extra):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=13, m=m, n=n,
+                                     advtyp=advtyp, nstep=3, **extra)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    got, before, launches = _run_host_path(cb, m, n)
+    assert launches > 0
+    names = ["saln"] + (["th3d"] if cb.advflg else ["temp"])
+    _compare(cb, g, got, ref, n, names)
+    for q in range(ntracr):
+        _compare(cb, g, {"t": got["tracer"][q]}, {"t": ref["tracer"][q]}, n, ["t"])
+    msk = util.interior_sea(cb)
+    # land cells and the centre time level keep their bits; NaN halos of the host arrays too
+    for name in names:
+        a, b = got[name], before[name]
+        assert np.array_equal(a[m - 1], b[m - 1], equal_nan=True), (name, "slot m modified")
+        assert np.array_equal(a[n - 1][:, ~msk], b[n - 1][:, ~msk], equal_nan=True), (name, "land/halo modified")
+    # fields that are not advected are untouched
+    idle = "temp" if cb.advflg else "th3d"
+    assert np.array_equal(got[idle], before[idle], equal_nan=True)
+    # diagnostics (:2065-2094)
+    assert np.array_equal(got["xmin"], ref["xmin"])
+    assert np.array_equal(got["xmax"], ref["xmax"])
+    # something moved
+    assert not np.array_equal(got["saln"][n - 1, 0][msk], before["saln"][n - 1, 0][msk])
+
+
+@pytest.mark.parametrize("m,n", [(1, 2), (2, 1)])
+def test_leapfrog_slots_and_two_steps(oracle, m, n):
+    """two consecutive calls with swapped slots, as HYCOM_Run does (mod_hycom.F90:2254-2257)"""
+    cfg, sea, g, cb = util.make_case(90, 70, 3, nreg=0, seed=21, m=m, n=n, advtyp=2)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_state(m, n)
+    ts.upload(cabi.F_DP, cb.dp[m - 1], m)
+    ot.tsadvc(m, n, 1)
+    ts.tsadvc_device(m, n)
+    ot.tsadvc(n, m, 1)
+    ts.tsadvc_device(n, m)
+    msk = util.interior_sea(cb)
+    for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+        for slot in (1, 2):
+            dev = ts.download(fld, slot)
+            ref = ot.f64(name)[slot - 1]
+            for k in range(g.kdm):
+                assert np.array_equal(dev[k][msk], ref[k][msk]), (name, slot, k)
+    ts.close()
+    ot.close()
+
+
+def test_device_generator_matches_host_generator():
+    cfg, sea, g, cb = util.make_case(83, 61, 3, nreg=1, ntracr=1, seed=17)
+    ts = pkg.Tsadvc(cb)
+    syn.fill_device(ts, cfg, sea, 1, 2)
+    for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+        for slot in (1, 2):
+            assert np.array_equal(ts.download(fld, slot), getattr(cb, name)[slot - 1], equal_nan=True)
+    assert np.array_equal(ts.download(cabi.F_DP, 2), cb.dp[1], equal_nan=True)
+    assert np.array_equal(ts.download(cabi.F_UFLX, 1), cb.uflx, equal_nan=True)
+    assert np.array_equal(ts.download(cabi.F_VFLX, 1), cb.vflx, equal_nan=True)
+    assert np.array_equal(ts.download(cabi.F_TRACER, 1, ktr=1), cb.tracer[0, 0], equal_nan=True)
+    ts.close()
+
+
+def test_device_halo_matches_xctilr(oracle):
+    """hycom_tsadvc_halo_local == xctilr of mod_xc_sm.h:1337-1428, closed and periodic"""
+    for nreg in (0, 1, 3, 4):
+        cfg, sea, g, cb = util.make_case(37, 29, 2, nreg=nreg, seed=3)
+        ot = util.oracle_tile_from_cb(oracle, cb, sea)
+        ts = pkg.Tsadvc(cb)
+        ts.upload(cabi.F_SALN, cb.saln[0], 1)
+        ts.upload(cabi.F_SALN, cb.saln[1], 2)
+        ts._ck(ts.lib.hycom_tsadvc_halo_local(ts.h, cabi.F_SALN, 0, 0, 5, 5))
+        a = ot.f64("saln")
+        ot.xctilr(a, 1, 2 * g.kdm, 5, 5)
+        for slot in (1, 2):
+            assert np.array_equal(ts.download(cabi.F_SALN, slot), a[slot - 1], equal_nan=True), nreg
+        ts.close()
+        ot.close()
+
+
+def test_error_behaviour_mirrors_xcstop():
+    cfg, sea, g, cb = util.make_case(30, 30, 1, seed=1, advtyp=3)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_state(1, 2)
+    with pytest.raises(cabi.XcStop, match="advem called with advtyp"):
+        ts.tsadvc_device(1, 2)
+    cb.advtyp = 2
+    with pytest.raises(cabi.TsadvcError):
+        ts.tsadvc_device(1, 1)  # m == n
+    ts.close()
+    # nbdy < mbdy_advtyp -> xcstop('tsadvc') (mod_tsadvc.F90:1817-1825)
+    g4 = pkg.partition(30, 30, 1, 1, 1, 0, nbdy=4)[0]
+    cb4 = syn.build_cb_arrays(cfg, g4, sea, 1, 2, advtyp=2)
+    ts = pkg.Tsadvc(cb4)
+    ts.upload_state(1, 2)
+    with pytest.raises(cabi.XcStop, match="nbdy"):
+        ts.tsadvc_device(1, 2)
+    ts.close()
+
+
+@pytest.mark.parametrize("advtyp", [1, 2])
+def test_temperature_tracer_equals_temp_on_device(advtyp):
+    """PIPE_TRACER invariant (mod_pipe.F90:1517-1542) through the CUDA path"""
+    cfg, sea, g, cb = util.make_case(120, 90, 4, nreg=0, ntracr=1, seed=4, advtyp=advtyp, trcflg=[2])
+    cb.tracer[0] = cb.temp
+    got, before, _ = _run_host_path(cb, 1, 2)
+    msk = util.interior_sea(cb)
+    assert np.array_equal(got["tracer"][0, 1][:, msk], got["temp"][1][:, msk])
+
+
+def test_constant_field_preserved_on_device():
+    cfg, sea, g, cb = util.make_case(100, 80, 2, nreg=0, seed=2, advtyp=2)
+    cb.saln[:] = np.where(cb.ip != 0, 35.25, cb.saln)
+    got, before, _ = _run_host_path(cb, 1, 2)
+    msk = util.interior_sea(cb)
+    assert (got["saln"][1][:, msk] == 35.25).all()
+
+
+@pytest.mark.parametrize("advtyp,ntracr", [(2, 0), (1, 1)])
+def test_full_size_glb_layers_match_oracle(oracle, advtyp, ntracr):
+    """BASELINE configs[1]/[2] at the full GLBb0.08 horizontal size (4500x3298) on the
+    device-resident path; two of the layers are checked against the oracle (each layer
+    is independent of the others, mod_tsadvc.F90:1842), the rest through the
+    size-independent properties: land untouched, finite on sea, tracer bounds."""
+    itdm, jtdm, kdm = 4500, 3298, 6
+    m, n = 1, 2
+    cfg = syn.make_cfg(itdm, jtdm, kdm, nreg=0, ntracr=ntracr, seed=1, dx0=8900.0, delt1=480.0)
+    sea = syn.sea_mask(cfg)
+    g = pkg.partition(itdm, jtdm, kdm, 1, 1, 0)[0]
+    cb = syn.build_cb_arrays(cfg, g, sea, m, n, with_state=False, advtyp=advtyp)
+    ts = pkg.Tsadvc(cb)
+    syn.fill_device(ts, cfg, sea, m, n)
+    ts.tsadvc_device(m, n, diag=False)
+    ts.synchronize()
+    # oracle on layers k0..k0+1 only: a 2-layer tile filled with the same global function
+    k0, nk = 3, 2
+    g2 = pkg.partition(itdm, jtdm, nk, 1, 1, 0)[0]
+    cb2 = syn.build_cb_arrays(cfg, g2, sea, m, n, with_state=False, advtyp=advtyp)
+    cb2.ntracr = ntracr
+
+    def f4(fld, ktr=0, halo_mode=0):
+        a = np.empty((2, nk, g.nrows, g.ncols))
+        for slot in (1, 2):
+            a[slot - 1] = syn.fill_host(cfg, g, sea, fld, ktr, 0 if slot == n else 1, k0, nk, halo_mode)
+        return a
+    cb2.temp, cb2.saln = f4(cabi.F_TEMP), f4(cabi.F_SALN)
+    cb2.th3d = np.zeros_like(cb2.temp)
+    cb2.dp = f4(cabi.F_DP, halo_mode=1)
+    cb2.uflx = syn.fill_host(cfg, g, sea, cabi.F_UFLX, 0, 0, k0, nk, 0)
+    cb2.vflx = syn.fill_host(cfg, g, sea, cabi.F_VFLX, 0, 0, k0, nk, 0)
+    cb2.oneta = np.ones((2, g.nrows, g.ncols))
+    if ntracr:
+        cb2.tracer = np.stack([f4(cabi.F_TRACER, ktr=q + 1) for q in range(ntracr)])
+    ref = util.run_oracle(oracle, cb2, sea, m, n)
+    msk = util.interior_sea(cb)
+    for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+        dev = ts.download(fld, n, k0=k0, nk=nk)
+        for k in range(nk):
+            e = util.rel_err(dev[k], ref[name][n - 1, k], msk)
+            assert e <= REL_TOL, (name, k, e)
+            assert np.array_equal(dev[k][msk], ref[name][n - 1, k][msk]), (name, k)
+            assert np.array_equal(dev[k][~msk], cb2.__dict__[name][n - 1, k][~msk], equal_nan=True)
+    if ntracr:
+        dev = ts.download(cabi.F_TRACER, n, ktr=1, k0=k0, nk=nk)
+        for k in range(nk):
+            assert np.array_equal(dev[k][msk], ref["tracer"][0, n - 1, k][msk])
+    # remaining layers: properties
+    for k in (1, kdm):
+        s = ts.download(cabi.F_SALN, n, k0=k, nk=1)[0]
+        assert np.isfinite(s[msk]).all()
+        assert 25.0 < s[msk].min() and s[msk].max() < 45.0
+    ts.close()

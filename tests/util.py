@@ -1,0 +1,73 @@
+"""Shared helpers of the test-suite (TEST INFRASTRUCTURE).
+
+`make_case` builds a synthetic single-tile CbArrays (product-side host generator,
+identical bits on host and device), `run_oracle` runs the CPU oracle on a copy of it.
+"""
+from __future__ import annotations
+
+import importlib
+
+import numpy as np
+
+pkg = importlib.import_module("hycom-src_b200")
+syn = pkg.synthetic
+cabi = importlib.import_module("hycom-src_b200.cabi")
+
+REL_TOL = 1.0e-12  # BASELINE.json north_star: "within 1e-12 relative max error"
+
+
+def make_cfg(itdm, jtdm, kdm, nreg=0, ntracr=0, seed=1, dx0=20000.0, delt1=3600.0):
+    return syn.make_cfg(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=seed, dx0=dx0, delt1=delt1)
+
+
+def make_case(itdm, jtdm, kdm, nreg=0, ntracr=0, seed=1, m=1, n=2, **scalars):
+    cfg = make_cfg(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=seed)
+    sea = syn.sea_mask(cfg)
+    g = pkg.partition(itdm, jtdm, kdm, 1, 1, nreg)[0]
+    cb = syn.build_cb_arrays(cfg, g, sea, m, n, **scalars)
+    return cfg, sea, g, cb
+
+
+def oracle_tile_from_cb(oracle, cb, sea=None):
+    """an oracle tile loaded with the product-side CbArrays; masks come from the
+    oracle's own bigrid restatement when `sea` is given (checked against cb)"""
+    g = cb.geom
+    ot = oracle.tile(g, cb.ntracr)
+    if sea is not None:
+        depth = np.zeros((g.nrows, g.ncols))
+        nb = g.nbdy
+        depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(
+            sea[g.j0:g.j0 + g.jj, g.i0:g.i0 + g.ii] != 0, 100.0, 0.0)
+        ot.bigrid(depth)
+    else:
+        raise ValueError("sea map required")
+    ot.load_cb(cb)
+    return ot
+
+
+def run_oracle(oracle, cb, sea, m, n):
+    """CPU oracle tsadvc(m,n) on a private copy of cb; returns dict of slot-n results"""
+    ot = oracle_tile_from_cb(oracle, cb, sea)
+    ot.tsadvc(m, n, 1)
+    out = dict(temp=ot.f64("temp").copy(), saln=ot.f64("saln").copy(), th3d=ot.f64("th3d").copy(),
+               xmin=ot.f64("xmin").copy(), xmax=ot.f64("xmax").copy())
+    if cb.ntracr:
+        out["tracer"] = ot.f64("tracer").copy()
+    ot.close()
+    return out
+
+
+def rel_err(a, b, mask):
+    """max_sea|a-b| / max_sea|b| over mask"""
+    d = np.abs(np.where(mask, a - b, 0.0))
+    ref = np.abs(np.where(mask, b, 0.0))
+    den = ref.max()
+    return 0.0 if den == 0 else float(d.max() / den)
+
+
+def interior_sea(cb):
+    g = cb.geom
+    nb = g.nbdy
+    m = np.zeros((g.nrows, g.ncols), dtype=bool)
+    m[nb:nb + g.jj, nb:nb + g.ii] = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
+    return m
