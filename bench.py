@@ -203,6 +203,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ipr, jpr = TILINGS[world]
     idm, jdm, kdm, baclin, dx = syn.SHAPES[args.workload]
+    if args.kdm:            # profiling aid only (ncu replays): NOT the named config
+        kdm = args.kdm
     cfg = syn.make_cfg(idm, jdm, kdm, nreg=0, ntracr=args.ntracr, seed=1, dx0=dx, delt1=2.0 * baclin)
     sea = syn.sea_mask(cfg)
     tiles = pkg.partition(idm, jdm, kdm, ipr, jpr, 0)
@@ -299,7 +301,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {idm}x{jdm}x{kdm} T+S advtyp={args.advtyp} ntracr={args.ntracr}",
+            "config": {"workload": f"{args.workload} {idm}x{jdm}x{kdm} T+S advtyp={args.advtyp} ntracr={args.ntracr}"
+                                   + (" (REDUCED kdm: profiling run, not a bench value)" if args.kdm else ""),
                        "tiling": f"{ipr}x{jpr}", "tile": f"{g.ii}x{g.jj}", "nreg": 0,
                        "l2": "inputs per step (%.1f GB) exceed L2 (126 MB); no flush" % (alg / 1e9),
                        "diag": "salinity min/max every 3rd step as mod_tsadvc.F90:2065"},
@@ -385,6 +388,7 @@ def main():
     ap.add_argument("--workload", default="GLBb0.08")
     ap.add_argument("--advtyp", type=int, default=2)
     ap.add_argument("--ntracr", type=int, default=0)
+    ap.add_argument("--kdm", type=int, default=0, help="override the layer count (profiling runs only)")
     ap.add_argument("--cpu-layers", type=int, default=2)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

@@ -58,6 +58,38 @@ __global__ void k_halo_ew(double* __restrict__ base, long slab, int nslab, int p
   }
 }
 
+// Cells beyond the refreshed halo (rings mh+1..nbdy, and the unused part of a ragged
+// tile) are never read by the reference and may hold r_init
+// NaNs.  The marching kernels recompute an apron that touches them (results discarded),
+// so they are set to vland here: finite operands keep every lane on the fast division
+// path.  Nothing observable depends on these cells.
+__global__ void k_halo_outer(double* __restrict__ base, long slab, int nslab, int pitch, int nrows,
+                             int nb, int ii, int jj, int mhl, int nhl) {
+  const int c_lo = nb - mhl, c_hi = nb + ii + mhl;   // refreshed columns [c_lo, c_hi)
+  const int r_lo = nb - nhl, r_hi = nb + jj + nhl;   // refreshed rows    [r_lo, r_hi)
+  const int nfull = r_lo + (nrows - r_hi);           // rows zeroed over their whole width
+  const int wside = c_lo + (pitch - c_hi);           // columns zeroed in the other rows
+  const long per = (long)nfull * pitch + (long)(r_hi - r_lo) * wside;
+  const long total = per * nslab;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long)gridDim.x * blockDim.x) {
+    const long sl = t / per;
+    long q = t - sl * per;
+    int r, c;
+    if (q < (long)nfull * pitch) {
+      r = (int)(q / pitch);
+      c = (int)(q - (long)r * pitch);
+      if (r >= r_lo) r += r_hi - r_lo;
+    } else {
+      q -= (long)nfull * pitch;
+      r = r_lo + (int)(q / wside);
+      c = (int)(q % wside);
+      if (c >= c_lo) c += c_hi - c_lo;
+    }
+    base[slab * sl + (long)r * pitch + c] = 0.0;
+  }
+}
+
 int launch_halo_local(double* base, long slab, int nslab, int pitch, int nbdy, int ii, int jj,
                       int mh, int nh, int periodic_i, int periodic_j, cudaStream_t stream) {
   const int mhl = max(0, min(mh, nbdy)), nhl = max(0, min(nh, nbdy));
@@ -74,6 +106,16 @@ int launch_halo_local(double* base, long slab, int nslab, int pitch, int nbdy, i
     k_halo_ew<<<blocks, threads, 0, stream>>>(base, slab, nslab, pitch, nbdy, ii, jj, mhl, nhl,
                                               periodic_i);
   }
+  return (int)cudaGetLastError();
+}
+
+int launch_halo_outer(double* base, long slab, int nslab, int pitch, int nrows, int nbdy, int ii,
+                      int jj, int mh, int nh, cudaStream_t stream) {
+  const int mhl = max(0, min(mh, nbdy)), nhl = max(0, min(nh, nbdy));
+  if (mhl >= nbdy && nhl >= nbdy) {
+    // nothing beyond the refreshed halo unless the tile is ragged (ii < idm)
+  }
+  k_halo_outer<<<148 * 4, 256, 0, stream>>>(base, slab, nslab, pitch, nrows, nbdy, ii, jj, mhl, nhl);
   return (int)cudaGetLastError();
 }
 

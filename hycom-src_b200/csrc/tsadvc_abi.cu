@@ -359,7 +359,10 @@ int hycom_tsadvc_halo_local(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, 
     if (rc) return rc;
     rc = launch_halo_local(base, h->slab, h->d.kdm, h->pitch, h->d.nbdy, h->d.ii, h->d.jj, mh, nh,
                            per_i, per_j, h->stream);
-    h->launches += 2;
+    if (!rc)
+      rc = launch_halo_outer(base, h->slab, h->d.kdm, h->pitch, h->nrows, h->d.nbdy, h->d.ii, h->d.jj,
+                             mh, nh, h->stream);
+    h->launches += 3;
     if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s",
                         cudaGetErrorString((cudaError_t)rc));
   }
@@ -441,9 +444,13 @@ int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   P.g.ii = h->d.ii; P.g.jj = h->d.jj;
   P.g.mask = h->mask; P.g.scp2 = h->scp2; P.g.scp2i = h->scp2i;
   P.g.delt1 = p.delt1; P.g.onemm = p.onemm;
-  P.nstrips = (h->pitch + 1 + kUse - 1) / kUse;
+  const char* cn = getenv("HYCOM_TSADVC_NC");
+  P.nc = (aadv == 2 && !(cn && atoi(cn) == 2)) ? 1 : 2;
+  const char* cb = getenv("HYCOM_TSADVC_MINB");
+  P.minb = cb ? atoi(cb) : 3;
+  P.nstrips = strip_count(h->pitch, P.nc);
   const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
-  P.chunk_rows = ce ? atoi(ce) : 128;
+  P.chunk_rows = ce ? atoi(ce) : 512;
   if (P.chunk_rows < 8) P.chunk_rows = 8;
   P.nchunks = (h->nrows + P.chunk_rows - 1) / P.chunk_rows;
   P.nunits = (long)P.njobs * P.nstrips * P.nchunks;

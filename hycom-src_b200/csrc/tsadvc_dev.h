@@ -60,9 +60,15 @@ struct Geo {
   double onemm;
 };
 
-// strips/chunks of the marching decomposition
-constexpr int kWin = 64;             // columns staged per warp (2 per lane)
-constexpr int kApron = 3;            // true dependency radius of FCT2/MPDATA/FCT4
-constexpr int kUse = kWin - 2 * kApron;  // 58 output columns per warp strip
+// strips/chunks of the marching decomposition: a warp stages 32*nc columns (nc adjacent
+// cells per lane) and yields all but the apron of 3 on each side, the true dependency
+// radius of FCT2/MPDATA (the reference's margins 4,3,3,2,1,0 are wider than needed)
+constexpr int kApron = 3;
+__host__ __device__ constexpr int strip_use(int nc) { return 32 * nc - 2 * kApron; }
+// first column of strip s is s*strip_use - strip_lead (even for nc=2: 16-byte vector loads)
+__host__ __device__ constexpr int strip_lead(int nc) { return nc == 2 ? 4 : 3; }
+__host__ __device__ constexpr int strip_count(int pitch, int nc) {
+  return (pitch + (nc == 2 ? 1 : 0) + strip_use(nc) - 1) / strip_use(nc);
+}
 
 }  // namespace tsadvc
