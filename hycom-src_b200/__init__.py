@@ -33,10 +33,11 @@ from .geometry import (  # noqa: F401
     partition,
 )
 from .state import CbArrays, Tsadvc  # noqa: F401
+from .xc import XcExchange, neighbors, halo_counts  # noqa: F401
 from . import synthetic  # noqa: F401
 
 __all__ = [
     "Dims", "Params", "SynthCfg", "SynthTile", "TsadvcError", "XcStop",
     "lib_path", "load_library", "TileGeom", "bigrid_masks", "geopar_metrics",
-    "partition", "CbArrays", "Tsadvc", "synthetic",
+    "partition", "CbArrays", "Tsadvc", "synthetic", "XcExchange", "neighbors", "halo_counts",
 ]

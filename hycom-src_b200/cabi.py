@@ -17,6 +17,8 @@ F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER = range(7)
 S_SCPX, S_SCPY, S_SCUX, S_SCUY, S_SCVX, S_SCVY, S_ONETA = range(10, 17)
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENBDY, EADVTYP, ENOMEM = range(7)
+PART_ALL, PART_INTERIOR, PART_FRAME = range(3)
+DIRS = ("W", "E", "S", "N", "SW", "SE", "NW", "NE")
 
 
 class TsadvcError(RuntimeError):
@@ -80,6 +82,15 @@ PROTOTYPES = {
                                            C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "hycom_tsadvc_halo_local": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "hycom_tsadvc_launch_count": (C.c_int64, [_vp]),
+    "hycom_tsadvc_halo_neighbors": (C.c_int, [_vp, C.POINTER(C.c_int32 * 8)]),
+    "hycom_tsadvc_halo_counts": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params),
+                                           C.POINTER(C.c_int64 * 8)]),
+    "hycom_tsadvc_halo_pack": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params),
+                                         C.POINTER(_vp * 8), _vp]),
+    "hycom_tsadvc_halo_unpack": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params),
+                                           C.POINTER(_vp * 8), _vp]),
+    "hycom_tsadvc_step_device_part": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params),
+                                                C.c_int32, _vp, _vp]),
     "hycom_tsadvc_set_timing": (C.c_int, [_vp, C.c_int32]),
     "hycom_tsadvc_get_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "hycom_synth_sea_mask": (C.c_int, [C.POINTER(SynthCfg), _vp]),

@@ -120,3 +120,93 @@ int launch_halo_outer(double* base, long slab, int nslab, int pitch, int nrows, 
 }
 
 }  // namespace tsadvc
+
+// ---------------------------------------------------------------------------------------
+// Multi-tile exchange (mod_xc_mp.h:4664-4987).  The reference packs north/south lines,
+// exchanges, then packs east/west columns INCLUDING the fresh north/south halo lines so
+// that corners propagate in two hops.  Here the eight neighbours are addressed directly in
+// one round (a corner comes from the diagonal tile, which is what the two hops deliver);
+// directions without a neighbour (closed edge) receive vland = 0.0 like mod_xc_sm.h.
+// One kernel packs every array, layer and direction of a call; one kernel unpacks.
+// ---------------------------------------------------------------------------------------
+namespace tsadvc {
+
+template <bool PACK>
+__global__ void k_halo_xfer(HaloArrays a, HaloBufs b) {
+  long total = 0;
+  long first[9];
+  int w[8], h[8], c0[8], r0[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    first[d] = total;
+    halo_region(a, d, !PACK, w[d], h[d], c0[d], r0[d]);
+    const bool on = PACK ? (b.buf[d] != nullptr) : true;
+    total += on ? (long)w[d] * h[d] * a.narr * a.kk : 0;
+  }
+  first[8] = total;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long)gridDim.x * blockDim.x) {
+    int d = 0;
+#pragma unroll
+    for (int q = 1; q < 8; ++q) d += (t >= first[q]) ? 1 : 0;
+    // segments of skipped directions are empty, so d lands on the owning direction
+    const long q = t - first[d];
+    const long per = (long)w[d] * h[d];
+    const int s = (int)(q / per);
+    const long e = q - (long)s * per;
+    const int r = (int)(e / w[d]), c = (int)(e - (long)r * w[d]);
+    double* cell = a.base[s / a.kk] + a.slab * (s % a.kk) + (long)(r0[d] + r) * a.pitch + (c0[d] + c);
+    if (PACK) b.buf[d][q] = *cell;
+    else *cell = b.buf[d] ? b.buf[d][q] : 0.0;  // vland
+  }
+}
+
+__global__ void k_halo_outer_multi(HaloArrays a) {
+  const int nb = a.nbdy;
+  const int c_lo = nb - a.mh, c_hi = nb + a.ii + a.mh;
+  const int r_lo = nb - a.nh, r_hi = nb + a.jj + a.nh;
+  const int nfull = r_lo + (a.nrows - r_hi);
+  const int wside = c_lo + (a.pitch - c_hi);
+  const long per = (long)nfull * a.pitch + (long)(r_hi - r_lo) * wside;
+  const long total = per * a.narr * a.kk;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long)gridDim.x * blockDim.x) {
+    const int s = (int)(t / per);
+    long q = t - (long)s * per;
+    int r, c;
+    if (q < (long)nfull * a.pitch) {
+      r = (int)(q / a.pitch);
+      c = (int)(q - (long)r * a.pitch);
+      if (r >= r_lo) r += r_hi - r_lo;
+    } else {
+      q -= (long)nfull * a.pitch;
+      r = r_lo + (int)(q / wside);
+      c = (int)(q % wside);
+      if (c >= c_lo) c += c_hi - c_lo;
+    }
+    a.base[s / a.kk][a.slab * (s % a.kk) + (long)r * a.pitch + c] = 0.0;
+  }
+}
+
+static int halo_blocks(const HaloArrays& a) {
+  const long cells = ((long)2 * a.mh * (a.jj + 2 * a.nh) + (long)2 * a.nh * a.ii) * a.narr * a.kk;
+  long blocks = (cells + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int launch_halo_pack(const HaloArrays& a, const HaloBufs& b, cudaStream_t stream) {
+  k_halo_xfer<true><<<halo_blocks(a), 256, 0, stream>>>(a, b);
+  return (int)cudaGetLastError();
+}
+int launch_halo_unpack(const HaloArrays& a, const HaloBufs& b, cudaStream_t stream) {
+  k_halo_xfer<false><<<halo_blocks(a), 256, 0, stream>>>(a, b);
+  return (int)cudaGetLastError();
+}
+int launch_halo_outer_multi(const HaloArrays& a, cudaStream_t stream) {
+  k_halo_outer_multi<<<148 * 4, 256, 0, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tsadvc

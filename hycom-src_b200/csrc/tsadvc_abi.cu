@@ -369,19 +369,25 @@ int hycom_tsadvc_halo_local(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, 
   return 0;
 }
 
-int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
-                             const hycom_tsadvc_params* prm, double* xmin, double* xmax) {
+}  // extern "C"
+
+namespace {
+
+struct Adv { int field, ktr; double posdef; int nlay; };
+
+// argument checks of tsadvc/advem (mod_tsadvc.F90:1815-1825, :159-166) and the list of
+// advected fields (:1855-1857, :1969-2034)
+int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+              std::vector<Adv>& adv, int& mbdy) {
   if (!h || !prm) return fail(h, HYCOM_TSADVC_EINVAL, "step: null argument");
   if (!h->have_static) return fail(h, HYCOM_TSADVC_EINVAL, "step: set_static has not been called");
   if (m < 1 || m > 2 || n < 1 || n > 2 || m == n)
     return fail(h, HYCOM_TSADVC_EINVAL, "step: bad leapfrog slots m=%d n=%d", m, n);
   const hycom_tsadvc_params& p = *prm;
   const int aadv = abs(p.advtyp);
-  // mod_tsadvc.F90:24-29, :159-166
   if (!(aadv == 0 || aadv == 1 || aadv == 2 || aadv == 4))
     return fail(h, HYCOM_TSADVC_EADVTYP, "error: advem called with advtyp =%4d", p.advtyp);
-  const int mbdy = (aadv == 0) ? 2 : 5;
-  // :1817-1825
+  mbdy = (aadv == 0) ? 2 : 5;
   if (h->d.nbdy < mbdy)
     return fail(h, HYCOM_TSADVC_ENBDY,
                 "error: nbdy (dimensions.h) must be at least%3d for the advection scheme indicated by advtyp",
@@ -392,32 +398,49 @@ int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   if (p.isopyc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc (k=1 flux smoothing) is not built yet");
   if (p.mxlmy) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "mxlmy (q2,q2l advection) is not built yet");
   if (p.temdf2 > 0.0) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "temdf2>0 (tsdff_1x/2x) is not built yet");
-  CU(h, cudaSetDevice(h->d.device));
-
   const int kk = h->d.kdm;
   const int nhyb = p.nhybrd < 0 ? 0 : (p.nhybrd > kk ? kk : p.nhybrd);
-  // fields to advect, :1855-1857, :1969-2034 (hybrid coordinates)
-  struct Adv { int field, ktr; double posdef; int nlay; };
-  std::vector<Adv> adv;
+  adv.clear();
   if (p.advflg == 0) { if (nhyb > 0) adv.push_back({HYCOM_F_TEMP, 0, 256.0, nhyb}); }
   else               { if (nhyb > 0) adv.push_back({HYCOM_F_TH3D, 0, 32.0, nhyb}); }
   adv.push_back({HYCOM_F_SALN, 0, 0.0, kk});
   for (int t = 1; t <= h->d.ntracr; ++t)
     adv.push_back({HYCOM_F_TRACER, t, p.trcflg[t - 1] == 2 ? 256.0 : 0.0, kk});
   if ((int)adv.size() > kMaxFields) return fail(h, HYCOM_TSADVC_EINVAL, "too many advected fields");
+  return 0;
+}
 
+// the arrays xctilr is called on at mod_tsadvc.F90:1829-1836 (th3d is exchanged by the
+// reference too but not read when advflg=0 and temdf2=0: left out of the multi-tile messages)
+int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, HaloArrays& a) {
+  memset(&a, 0, sizeof a);
   int rc;
-  // :1827-1836  xctilr of the advected fields (both slots) and the mass fluxes;
-  // "dp halo is up to date".  Multi-tile handles are exchanged by the caller.
-  if (h->d.ipr * h->d.jpr == 1) {
-    for (const Adv& a : adv)
-      if ((rc = hycom_tsadvc_halo_local(h, a.field, a.ktr, 0, mbdy, mbdy))) return rc;
-    if (p.advflg == 0 && h->th3d.lev[0] && h->th3d.lev[1])
-      if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TH3D, 0, 0, mbdy, mbdy))) return rc;
-    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_UFLX, 0, 1, mbdy, mbdy))) return rc;
-    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy))) return rc;
-  }
+  for (const Adv& f : adv)
+    for (int t = 1; t <= 2; ++t)
+      if ((rc = slot(h, f.field, f.ktr, t, &a.base[a.narr++]))) return rc;
+  if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &a.base[a.narr++]))) return rc;
+  if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &a.base[a.narr++]))) return rc;
+  a.kk = h->d.kdm; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+  a.ii = h->d.ii; a.jj = h->d.jj; a.mh = mbdy; a.nh = mbdy;
+  return 0;
+}
 
+// 0-based tile index of the neighbour in direction d, -1 at a closed edge
+// (mod_xc.F90:25-31: nreg 1,3 periodic in i; nreg 3,4 periodic in j)
+int neighbour(const hycom_tsadvc_dims& d, int dir) {
+  static const int dx[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+  static const int dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+  const bool per_i = !(d.nreg == 0 || d.nreg == 4), per_j = d.nreg > 2;
+  int mp = d.mproc - 1 + dx[dir], np = d.nproc - 1 + dy[dir];
+  if (mp < 0 || mp >= d.ipr) { if (!per_i) return -1; mp = (mp + d.ipr) % d.ipr; }
+  if (np < 0 || np >= d.jpr) { if (!per_j) return -1; np = (np + d.jpr) % d.jpr; }
+  return mp + d.ipr * np;
+}
+
+int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
+              const std::vector<Adv>& adv, int part) {
+  const int kk = h->d.kdm, aadv = abs(p.advtyp);
+  int rc;
   MarchParams P;
   memset(&P, 0, sizeof P);
   P.nfld = (int)adv.size();
@@ -448,12 +471,39 @@ int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   P.nc = (aadv == 2 && !(cn && atoi(cn) == 2)) ? 1 : 2;
   const char* cb = getenv("HYCOM_TSADVC_MINB");
   P.minb = cb ? atoi(cb) : 3;
-  P.nstrips = strip_count(h->pitch, P.nc);
   const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
   P.chunk_rows = ce ? atoi(ce) : 512;
   if (P.chunk_rows < 8) P.chunk_rows = 8;
-  P.nchunks = (h->nrows + P.chunk_rows - 1) / P.chunk_rows;
-  P.nunits = (long)P.njobs * P.nstrips * P.nchunks;
+
+  // (strip,row) rectangles of this part.  Interior = units whose staged window (apron and
+  // prefetched row included) lies inside 1..ii x 1..jj, i.e. reads no halo cell.
+  const int nstrips = strip_count(h->pitch, P.nc);
+  const int nb = h->d.nbdy, use = strip_use(P.nc), lead = strip_lead(P.nc), wid = 32 * P.nc;
+  int s_lo = 0, s_hi = nstrips;           // interior strips [s_lo, s_hi)
+  while (s_lo < nstrips && s_lo * use - lead < nb) ++s_lo;
+  while (s_hi > s_lo && (s_hi - 1) * use - lead + wid > nb + h->d.ii) --s_hi;
+  int r_lo = nb + 3, r_hi = nb + h->d.jj - 4;  // interior rows [r_lo, r_hi)
+  if (s_lo >= s_hi || r_lo >= r_hi) { s_lo = s_hi = 0; r_lo = r_hi = 0; }
+  auto add = [&](int strip0, int ns, int row0, int row1) {
+    if (ns <= 0 || row1 <= row0) return;
+    MarchRect& R = P.rect[P.nrect++];
+    R.strip0 = strip0; R.nstrips = ns; R.row0 = row0; R.row1 = row1;
+    R.nchunks = (row1 - row0 + P.chunk_rows - 1) / P.chunk_rows;
+    R.unit0 = P.nunits;
+    P.nunits += (long)P.njobs * ns * R.nchunks;
+  };
+  const bool empty_interior = (s_lo >= s_hi);
+  if (part == HYCOM_TSADVC_PART_ALL || (part == HYCOM_TSADVC_PART_FRAME && empty_interior)) {
+    add(0, nstrips, 0, h->nrows);
+  } else if (part == HYCOM_TSADVC_PART_INTERIOR) {
+    add(s_lo, s_hi - s_lo, r_lo, r_hi);
+  } else {
+    add(0, s_lo, 0, h->nrows);
+    add(s_hi, nstrips - s_hi, 0, h->nrows);
+    add(s_lo, s_hi - s_lo, 0, r_lo);
+    add(s_lo, s_hi - s_lo, r_hi, h->nrows);
+  }
+  if (P.nunits == 0) return 0;
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
   if (h->timing) {
     if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
@@ -468,21 +518,27 @@ int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   }
   if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "march kernel launch failed: %s",
                       rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "bad scheme");
+  return 0;
+}
 
-  // slot n now lives in the ping-pong buffer
-  for (int f = 0; f < P.nfld; ++f) {
-    Mirror* mi = mirror_of(h, adv[f].field, adv[f].ktr);
-    if (adv[f].nlay < kk)  // layers that were not advected keep their values (:2008-2014)
-      CU(h, cudaMemcpyAsync(mi->spare + h->slab * adv[f].nlay, mi->lev[n - 1] + h->slab * adv[f].nlay,
-                            sizeof(double) * (size_t)h->slab * (kk - adv[f].nlay),
+// slot n moves to the ping-pong buffer; salinity range diagnostics (:2065-2094)
+int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
+                const std::vector<Adv>& adv, double* xmin, double* xmax) {
+  const int kk = h->d.kdm;
+  int rc;
+  for (const Adv& f : adv) {
+    Mirror* mi = mirror_of(h, f.field, f.ktr);
+    if (f.nlay < kk)  // layers that were not advected keep their values (:2008-2014)
+      CU(h, cudaMemcpyAsync(mi->spare + h->slab * f.nlay, mi->lev[n - 1] + h->slab * f.nlay,
+                            sizeof(double) * (size_t)h->slab * (kk - f.nlay),
                             cudaMemcpyDeviceToDevice, h->stream));
     double* t = mi->lev[n - 1];
     mi->lev[n - 1] = mi->spare;
     mi->spare = t;
   }
-
-  // :2065-2094 salinity range, every third step or when diagno
   if (xmin && xmax && ((p.nstep % 3 == 0) || p.diagno)) {
+    double* dpn;
+    if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
     if (!h->d_minmax && (rc = dalloc(h, (void**)&h->d_minmax, sizeof(double) * 2 * kk, false))) return rc;
     k_minmax_init<<<(kk + 127) / 128, 128, 0, h->stream>>>(h->d_minmax, kk);
     dim3 grid(148 * 2, kk);
@@ -496,6 +552,94 @@ int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   }
   CU(h, cudaGetLastError());
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hycom_tsadvc_step_device_part(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                                  const hycom_tsadvc_params* prm, int32_t part, double* xmin,
+                                  double* xmax) {
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  if (part < HYCOM_TSADVC_PART_ALL || part > HYCOM_TSADVC_PART_FRAME)
+    return fail(h, HYCOM_TSADVC_EINVAL, "step: bad part %d", part);
+  CU(h, cudaSetDevice(h->d.device));
+  // :1827-1836  xctilr of the advected fields (both slots) and the mass fluxes; "dp halo is
+  // up to date".  Single tile: done here.  Multi-tile: hycom_tsadvc_halo_pack/unpack around
+  // the caller's transport, before PART_ALL / PART_FRAME.
+  if (h->d.ipr * h->d.jpr == 1 && part != HYCOM_TSADVC_PART_FRAME) {
+    for (const Adv& a : adv)
+      if ((rc = hycom_tsadvc_halo_local(h, a.field, a.ktr, 0, mbdy, mbdy))) return rc;
+    if (prm->advflg == 0 && h->th3d.lev[0] && h->th3d.lev[1])
+      if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TH3D, 0, 0, mbdy, mbdy))) return rc;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_UFLX, 0, 1, mbdy, mbdy))) return rc;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy))) return rc;
+  }
+  if ((rc = run_march(h, m, n, *prm, adv, part))) return rc;
+  if (part == HYCOM_TSADVC_PART_INTERIOR) return 0;
+  return finish_step(h, n, *prm, adv, xmin, xmax);
+}
+
+int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params* prm, double* xmin, double* xmax) {
+  return hycom_tsadvc_step_device_part(h, m, n, prm, HYCOM_TSADVC_PART_ALL, xmin, xmax);
+}
+
+int hycom_tsadvc_halo_neighbors(const hycom_tsadvc_handle* h, int32_t nbr[8]) {
+  if (!h || !nbr) return fail(nullptr, HYCOM_TSADVC_EINVAL, "halo_neighbors: null argument");
+  for (int d = 0; d < 8; ++d) nbr[d] = neighbour(h->d, d);
+  return 0;
+}
+
+int hycom_tsadvc_halo_counts(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params* prm, int64_t count[8]) {
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if (!count) return fail(h, HYCOM_TSADVC_EINVAL, "halo_counts: null argument");
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  HaloArrays a;
+  if ((rc = halo_arrays(h, adv, mbdy, a))) return rc;
+  for (int d = 0; d < 8; ++d) {
+    int w, hh, c0, r0;
+    halo_region(a, d, false, w, hh, c0, r0);
+    count[d] = (int64_t)w * hh * a.narr * a.kk;
+  }
+  return 0;
+}
+
+static int halo_xfer(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                     double* const buf[8], void* cuda_stream, bool pack) {
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if (!buf) return fail(h, HYCOM_TSADVC_EINVAL, "halo: null buffer table");
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  CU(h, cudaSetDevice(h->d.device));
+  HaloArrays a;
+  if ((rc = halo_arrays(h, adv, mbdy, a))) return rc;
+  HaloBufs b;
+  for (int d = 0; d < 8; ++d) { b.buf[d] = buf[d]; b.count[d] = 0; }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  rc = pack ? launch_halo_pack(a, b, st) : launch_halo_unpack(a, b, st);
+  h->launches += 1;
+  if (!rc && !pack) { rc = launch_halo_outer_multi(a, st); h->launches += 1; }
+  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s",
+                      cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
+int hycom_tsadvc_halo_pack(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                           const hycom_tsadvc_params* prm, double* const sendbuf[8],
+                           void* cuda_stream) {
+  return halo_xfer(h, m, n, prm, sendbuf, cuda_stream, true);
+}
+
+int hycom_tsadvc_halo_unpack(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params* prm, double* const recvbuf[8],
+                             void* cuda_stream) {
+  return halo_xfer(h, m, n, prm, recvbuf, cuda_stream, false);
 }
 
 int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,

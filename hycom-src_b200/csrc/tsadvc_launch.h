@@ -8,6 +8,14 @@ namespace tsadvc {
 
 constexpr int kWarpsPerBlock = 4;
 
+struct MarchRect {
+  int strip0, nstrips;   // strips strip0 .. strip0+nstrips-1
+  int row0, row1;        // rows [row0, row1) are stored
+  int nchunks;           // ceil((row1-row0)/chunk_rows)
+  int pad;
+  long unit0;            // first unit: unit = unit0 + job + njobs*(strip + nstrips*chunk)
+};
+
 struct MarchParams {
   FieldDesc fld[kMaxFields];
   int nfld;
@@ -20,10 +28,13 @@ struct MarchParams {
   Geo g;
   int nc;           // cells per lane (1 or 2)
   int minb;         // resident blocks per SM the variant is compiled for
-  int nstrips;      // strip_count(pitch, nc)
-  int nchunks;      // ceil(nrows/chunk_rows)
   int chunk_rows;
-  long nunits;      // njobs*nstrips*nchunks; unit = job + njobs*(strip + nstrips*chunk)
+  // the launch covers up to four rectangles of (strip, row) space: one for a whole slab or
+  // for the interior of a tile, four for the frame that depends on halo cells
+  // (interior/frame split: the frame waits for the halo exchange, the interior overlaps it)
+  int nrect;
+  MarchRect rect[4];
+  long nunits;      // sum over rectangles of njobs*nstrips*nchunks
 };
 
 // scheme: 1 = MPDATA, 2 = FCT2 (advtyp of blkdat.input, mod_tsadvc.F90:87-90)
@@ -35,5 +46,46 @@ int launch_halo_local(double* base, long slab, int nslab, int pitch, int nbdy, i
 
 int launch_halo_outer(double* base, long slab, int nslab, int pitch, int nrows, int nbdy, int ii,
                       int jj, int mh, int nh, cudaStream_t stream);
+
+}  // namespace tsadvc
+
+// ---- multi-tile halo exchange building blocks (halo.cu) ---------------------------------
+namespace tsadvc {
+
+constexpr int kMaxHaloArrays = 2 * kMaxFields + 4;
+
+// the 3-D arrays one tsadvc(m,n) call exchanges (mod_tsadvc.F90:1829-1836): every entry is
+// `kk` consecutive slabs; the message of one direction is [array][k][row][col] contiguous
+struct HaloArrays {
+  double* base[kMaxHaloArrays];
+  int narr;
+  int kk;
+  long slab;
+  int pitch, nrows, nbdy, ii, jj, mh, nh;
+};
+struct HaloBufs {
+  double* buf[8];     // per direction (W,E,S,N,SW,SE,NW,NE); nullptr: skip (pack) / vland (unpack)
+  long count[8];      // doubles per direction (0: no message)
+};
+
+// (width, height) of the strip exchanged with direction d and its first (column,row) in the
+// slab: `recv` selects the halo cells that are filled, else the interior cells that are sent
+__host__ __device__ inline void halo_region(const HaloArrays& a, int d, bool recv, int& w, int& h,
+                                            int& c0, int& r0) {
+  const int nb = a.nbdy;
+  // x extent
+  const int xs = (d == 0 || d == 4 || d == 6) ? -1 : (d == 1 || d == 5 || d == 7) ? 1 : 0;
+  const int ys = (d == 2 || d == 4 || d == 5) ? -1 : (d == 3 || d == 6 || d == 7) ? 1 : 0;
+  if (xs == 0) { w = a.ii; c0 = nb; }
+  else if (xs < 0) { w = a.mh; c0 = recv ? nb - a.mh : nb; }
+  else { w = a.mh; c0 = recv ? nb + a.ii : nb + a.ii - a.mh; }
+  if (ys == 0) { h = a.jj; r0 = nb; }
+  else if (ys < 0) { h = a.nh; r0 = recv ? nb - a.nh : nb; }
+  else { h = a.nh; r0 = recv ? nb + a.jj : nb + a.jj - a.nh; }
+}
+
+int launch_halo_pack(const HaloArrays& a, const HaloBufs& b, cudaStream_t stream);
+int launch_halo_unpack(const HaloArrays& a, const HaloBufs& b, cudaStream_t stream);
+int launch_halo_outer_multi(const HaloArrays& a, cudaStream_t stream);
 
 }  // namespace tsadvc

@@ -1,0 +1,225 @@
+"""Multi-tile halo exchange of the tsadvc path: the host side of ``xctilr``.
+
+mod_xc (mod_xc_mp.h:4664-4987) owns the communicator and moves the packed edge strips with
+MPI/SHMEM.  Here one process drives one GPU (= one tile, placed exactly as mod_xc places
+tiles: ``geometry.partition``), the edge strips are packed and unpacked on the device by the
+C library (``hycom_tsadvc_halo_pack/unpack``) and travel between GPUs as NCCL send/recv over
+NVLink (``torch.distributed`` is the plumbing).  All eight neighbours are addressed in one
+round, and the exchange overlaps the interior of the tile:
+
+    comm stream   : pack -> send/recv -> unpack
+    compute stream: march(PART_INTERIOR) ................ wait -> march(PART_FRAME)
+
+``XcExchange`` holds the schedule (who sends what to whom, in which order); the byte moving
+is behind a small backend so that the schedule is also exercised on CPU ranks (gloo) by the
+test-suite with a numpy backend.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+from . import cabi
+from .geometry import TileGeom
+
+# direction d -> (dx, dy); opposite direction
+DIR_DXY = ((-1, 0), (1, 0), (0, -1), (0, 1), (-1, -1), (1, -1), (-1, 1), (1, 1))
+OPP = (1, 0, 3, 2, 7, 6, 5, 4)
+
+
+def neighbors(g: TileGeom) -> List[int]:
+    """0-based tile index (mproc-1 + ipr*(nproc-1)) of the eight neighbours, -1 at a closed
+    edge (mod_xc.F90:25-31: nreg 1,3 periodic in i; nreg 3,4 periodic in j)."""
+    out = []
+    for dx, dy in DIR_DXY:
+        mp, np_ = g.mproc - 1 + dx, g.nproc - 1 + dy
+        if not 0 <= mp < g.ipr:
+            if not g.periodic_i:
+                out.append(-1)
+                continue
+            mp %= g.ipr
+        if not 0 <= np_ < g.jpr:
+            if not g.periodic_j:
+                out.append(-1)
+                continue
+            np_ %= g.jpr
+        out.append(mp + g.ipr * np_)
+    return out
+
+
+def halo_counts(g: TileGeom, nslab: int, mh: int = 5, nh: int = 5) -> List[int]:
+    """doubles per direction of one message of ``nslab`` slabs"""
+    out = []
+    for dx, dy in DIR_DXY:
+        w = g.ii if dx == 0 else mh
+        h = g.jj if dy == 0 else nh
+        out.append(w * h * nslab)
+    return out
+
+
+class DeviceHaloBackend:
+    """pack/unpack on the GPU through the C ABI; buffers are torch CUDA tensors"""
+    device = True
+
+    def __init__(self, ts):
+        import torch
+        self.torch = torch
+        self.ts = ts
+        self.dev = torch.device("cuda", ts.dims.device)
+
+    def counts(self, m, n):
+        cnt = (C.c_int64 * 8)()
+        p = self.ts.cb.params()
+        self.ts._ck(self.ts.lib.hycom_tsadvc_halo_counts(self.ts.h, m, n, C.byref(p), C.byref(cnt)))
+        return [int(c) for c in cnt]
+
+    def alloc(self, n):
+        return self.torch.empty(n, dtype=self.torch.float64, device=self.dev)
+
+    def _table(self, bufs):
+        t = (C.c_void_p * 8)()
+        for d in range(8):
+            t[d] = None if bufs[d] is None else bufs[d].data_ptr()
+        return t
+
+    def pack(self, m, n, send, stream=None):
+        p = self.ts.cb.params()
+        t = self._table(send)
+        self.ts._ck(self.ts.lib.hycom_tsadvc_halo_pack(self.ts.h, m, n, C.byref(p), C.byref(t),
+                                                      C.c_void_p(stream) if stream else None))
+
+    def unpack(self, m, n, recv, stream=None):
+        p = self.ts.cb.params()
+        t = self._table(recv)
+        self.ts._ck(self.ts.lib.hycom_tsadvc_halo_unpack(self.ts.h, m, n, C.byref(p), C.byref(t),
+                                                        C.c_void_p(stream) if stream else None))
+
+
+class XcExchange:
+    """``xctilr`` of the arrays tsadvc(m,n) exchanges (mod_tsadvc.F90:1829-1836) for one tile
+    per rank of a ``torch.distributed`` group, plus the overlapped ``tsadvc_device``."""
+
+    def __init__(self, ts, dist, backend=None, group=None, rank: Optional[int] = None,
+                 compute_stream=None):
+        self.ts, self.dist, self.group = ts, dist, group
+        self.backend = backend if backend is not None else DeviceHaloBackend(ts)
+        g = ts.cb.geom if ts is not None else backend.geom
+        self.geom = g
+        self.rank = dist.get_rank(group) if rank is None else rank
+        me = g.mproc - 1 + g.ipr * (g.nproc - 1)
+        if me != self.rank:
+            raise ValueError(f"rank {self.rank} holds tile {me}: tiles are placed row-major, rank = mproc-1 + ipr*(nproc-1)")
+        self.nbr = neighbors(g)
+        if ts is not None and hasattr(ts, "lib"):
+            nb = (C.c_int32 * 8)()
+            ts._ck(ts.lib.hycom_tsadvc_halo_neighbors(ts.h, C.byref(nb)))
+            assert list(nb) == self.nbr, (list(nb), self.nbr)
+        self._bufs = {}
+        self.comm_stream = None
+        import torch
+        self.torch = torch
+        if getattr(self.backend, "device", False):
+            self.comm_stream = torch.cuda.Stream(device=self.backend.dev)
+            self.compute_stream = compute_stream
+
+    # -- buffers ----------------------------------------------------------------------
+    def _buffers(self, m, n):
+        key = tuple(self.backend.counts(m, n))
+        if key not in self._bufs:
+            send = [self.backend.alloc(c) if self.nbr[d] >= 0 else None for d, c in enumerate(key)]
+            recv: List = [None] * 8
+            for d, c in enumerate(key):
+                if self.nbr[d] < 0:
+                    continue
+                # a periodic edge that wraps onto this tile: what leaves in the opposite
+                # direction is what arrives here
+                recv[d] = send[OPP[d]] if self.nbr[d] == self.rank else self.backend.alloc(c)
+            self._bufs[key] = (send, recv)
+        return self._bufs[key]
+
+    def ops(self, send, recv):
+        """the P2P operations of one exchange, ordered so that the k-th send of rank A to
+        rank B meets the k-th receive B posts for A (NCCL matches by order, not by tag)"""
+        P2POp, dist = self.dist.P2POp, self.dist
+        ops = []
+        for d in range(8):
+            peer = self.nbr[d]
+            if peer >= 0 and peer != self.rank:
+                ops.append(P2POp(dist.isend, send[d], self._global(peer), group=self.group, tag=d))
+        for d in range(8):
+            e = OPP[d]          # the peer sent this message in ITS direction d
+            peer = self.nbr[e]
+            if peer >= 0 and peer != self.rank:
+                ops.append(P2POp(dist.irecv, recv[e], self._global(peer), group=self.group, tag=d))
+        return ops
+
+    def _global(self, peer):
+        return peer if self.group is None else self.dist.get_global_rank(self.group, peer)
+
+    # -- the exchange -------------------------------------------------------------------
+    def start(self, m, n):
+        send, recv = self._buffers(m, n)
+        cs = self.comm_stream
+        if cs is not None:
+            cs.wait_stream(self._compute())
+            with self.torch.cuda.stream(cs):
+                self.backend.pack(m, n, send, cs.cuda_stream)
+                ops = self.ops(send, recv)
+                works = self.dist.batch_isend_irecv(ops) if ops else []
+        else:
+            self.backend.pack(m, n, send)
+            ops = self.ops(send, recv)
+            works = self.dist.batch_isend_irecv(ops) if ops else []
+        return works, recv
+
+    def finish(self, m, n, pending):
+        works, recv = pending
+        cs = self.comm_stream
+        if cs is not None:
+            with self.torch.cuda.stream(cs):
+                for w in works:
+                    w.wait()
+                self.backend.unpack(m, n, recv, cs.cuda_stream)
+            self._compute().wait_stream(cs)
+        else:
+            for w in works:
+                w.wait()
+            self.backend.unpack(m, n, recv)
+
+    def xctilr(self, m, n):
+        """blocking form: halos of every exchanged array valid to width 5 on return"""
+        self.finish(m, n, self.start(m, n))
+
+    def _compute(self):
+        if self.compute_stream is None:
+            raise RuntimeError("XcExchange.compute_stream is not set (the torch stream the handle runs on)")
+        return self.compute_stream
+
+    # -- tsadvc(m,n) with the exchange overlapped with the interior ----------------------
+    def tsadvc_device(self, m, n, diag: bool = True, overlap: bool = True):
+        ts = self.ts
+        p = ts.cb.params()
+        xm = ts.xmin.ctypes.data_as(C.c_void_p) if diag else None
+        xx = ts.xmax.ctypes.data_as(C.c_void_p) if diag else None
+        pending = self.start(m, n)
+        if overlap:
+            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_INTERIOR, None, None))
+            self.finish(m, n, pending)
+            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_FRAME, xm, xx))
+        else:
+            self.finish(m, n, pending)
+            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, xm, xx))
+        if diag and (ts.cb.nstep % 3 == 0 or ts.cb.diagno):
+            self.xcminmax(ts.xmin, ts.xmax)
+
+    def xcminmax(self, xmin, xmax):
+        """xcminr / xcmaxr of the per-layer salinity range (mod_tsadvc.F90:2093-2094):
+        element-wise min/max over all tiles, in place"""
+        torch = self.torch
+        dev = self.backend.dev if self.comm_stream is not None else "cpu"
+        lo = torch.from_numpy(xmin).to(dev)
+        hi = torch.from_numpy(xmax).to(dev)
+        self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.group)
+        self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.group)
+        xmin[:] = lo.cpu().numpy()
+        xmax[:] = hi.cpu().numpy()

@@ -144,6 +144,47 @@ int hycom_tsadvc_device_slab(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
 int hycom_tsadvc_halo_local(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
                             int32_t tlev_or_0_for_both, int32_t mh, int32_t nh);
 
+/* ---- multi-tile runs (ipr*jpr > 1): the device side of xctilr --------------------------
+ * mod_xc_mp.h:4664-4987 packs the mh x nh wide edge strips of a (..,..,ld) array, moves them
+ * with MPI/SHMEM and unpacks them into the neighbour's halo.  Here the library packs and
+ * unpacks on the device; the TRANSPORT between tiles stays with the host program, as it
+ * does in the reference (mod_xc owns the communicator): NCCL send/recv or CUDA-aware MPI on
+ * the device buffers, torch.distributed in this repository's Python host.
+ * Directions: 0 W, 1 E, 2 S, 3 N, 4 SW, 5 SE, 6 NW, 7 NE.  All eight neighbours are
+ * addressed in one round; a corner message comes from the diagonal tile (the reference
+ * gets the same values in two hops, N/S then E/W including the fresh N/S lines).
+ * A message is [array][k][row][col] over the arrays tsadvc(m,n) exchanges at
+ * mod_tsadvc.F90:1829-1836 (advected fields, both time slots; uflx; vflx), halo width
+ * mbdy_advtyp (5). */
+enum {
+  HYCOM_TSADVC_PART_ALL = 0,      /* the whole tile */
+  HYCOM_TSADVC_PART_INTERIOR = 1, /* cells that read no halo: may overlap the exchange */
+  HYCOM_TSADVC_PART_FRAME = 2     /* the rest, after unpack; completes the step */
+};
+/* 0-based index (mproc-1 + ipr*(nproc-1)) of the neighbour tile per direction, -1 at a
+ * closed edge; periodic edges wrap (possibly onto the tile itself) */
+int hycom_tsadvc_halo_neighbors(const hycom_tsadvc_handle *h, int32_t nbr[8]);
+/* doubles per direction of one message (send and receive sizes are equal for the uniform
+ * tilings of hycom-src_b200/geometry.py: tiles of one row share jj, of one column ii) */
+int hycom_tsadvc_halo_counts(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params *prm, int64_t count[8]);
+/* pack the edge strips into sendbuf[d] (device pointers; NULL: direction skipped) /
+ * unpack recvbuf[d] into the halo (NULL: closed edge, halo := vland = 0.0 as
+ * mod_xc_sm.h:1377-1422) on cuda_stream (NULL: the handle's stream) */
+int hycom_tsadvc_halo_pack(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                           const hycom_tsadvc_params *prm, double *const sendbuf[8],
+                           void *cuda_stream);
+int hycom_tsadvc_halo_unpack(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params *prm, double *const recvbuf[8],
+                             void *cuda_stream);
+/* tsadvc(m,n) on the device mirrors in two parts so that PART_INTERIOR runs while the halo
+ * messages are in flight; PART_FRAME (or PART_ALL) finishes the call (leapfrog slot n is
+ * switched to the new time level, diagnostics).  On a multi-tile handle no part touches
+ * the halos: pack / transport / unpack come first. */
+int hycom_tsadvc_step_device_part(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                                  const hycom_tsadvc_params *prm, int32_t part,
+                                  double *xmin, double *xmax);
+
 /* number of kernels this library launched on the handle since creation */
 int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle *h);
 

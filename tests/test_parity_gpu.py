@@ -243,3 +243,79 @@ def test_full_size_glb_layers_match_oracle(oracle, advtyp, ntracr):
         assert np.isfinite(s[msk]).all()
         assert 25.0 < s[msk].min() and s[msk].max() < 45.0
     ts.close()
+
+
+# ---------------------------------------------------------------------------------------
+# multi-tile: the reference's own test idea (mod_pipe.F90:26-127: 1 tile vs N tiles, exact)
+# ---------------------------------------------------------------------------------------
+def _exchange_in_process(tss, m, n):
+    """xctilr between the tiles of one process: every tile packs on the device, a message
+    leaving tile A in direction d is unpacked by tile nbr_A[d] as arriving from OPP[d]."""
+    import torch
+    xc = __import__("importlib").import_module("hycom-src_b200.xc")
+    sends, nbrs = [], []
+    for ts in tss:
+        be = xc.DeviceHaloBackend(ts)
+        nbr = xc.neighbors(ts.cb.geom)
+        cnt = be.counts(m, n)
+        assert cnt == xc.halo_counts(ts.cb.geom, (2 * (2 + ts.cb.ntracr) + 2) * ts.cb.geom.kdm)
+        send = [be.alloc(c) if nbr[d] >= 0 else None for d, c in enumerate(cnt)]
+        be.pack(m, n, send)
+        sends.append(send)
+        nbrs.append(nbr)
+        ts.synchronize()
+    for t, ts in enumerate(tss):
+        recv = [sends[nbrs[t][d]][xc.OPP[d]] if nbrs[t][d] >= 0 else None for d in range(8)]
+        xc.DeviceHaloBackend(ts).unpack(m, n, recv)
+        ts.synchronize()
+
+
+TILINGS = [
+    # itdm, jtdm, kdm, ipr, jpr, nreg, ntracr, advtyp, split
+    (150, 150, 3, 2, 1, 0, 0, 2, True),    # BASELINE configs[3] tilings on the box basin
+    (150, 150, 3, 2, 2, 0, 1, 2, True),
+    (150, 150, 2, 4, 2, 0, 0, 2, False),
+    (131, 97, 2, 2, 2, 3, 0, 2, True),     # doubly periodic, ragged splits
+    (120, 90, 2, 1, 2, 1, 1, 1, True),     # MPDATA, periodic in i wrapping onto the tile itself
+    (300, 64, 2, 2, 1, 0, 0, 2, True),     # tiles wide enough to have interior strips
+]
+
+
+@pytest.mark.parametrize("itdm,jtdm,kdm,ipr,jpr,nreg,ntracr,advtyp,split", TILINGS)
+def test_tiling_invariance_on_device(oracle, itdm, jtdm, kdm, ipr, jpr, nreg, ntracr, advtyp, split):
+    """N tiles (device pack/unpack, interior/frame split) == the oracle on 1 tile, bit for bit"""
+    m, n = 1, 2
+    cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=5, m=m, n=n,
+                                       advtyp=advtyp, nstep=3)
+    ref = util.run_oracle(oracle, cb1, sea, m, n)
+    tiles = pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)
+    tss = []
+    for g in tiles:
+        cb = syn.build_cb_arrays(cfg, g, sea, m, n, advtyp=advtyp, nstep=3)
+        ts = pkg.Tsadvc(cb)
+        ts.upload_state(m, n)
+        tss.append(ts)
+    _exchange_in_process(tss, m, n)
+    xmin = np.full(kdm, 999.0)
+    xmax = np.full(kdm, -999.0)
+    for ts in tss:
+        p = ts.cb.params()
+        xm, xx = ts.xmin.ctypes.data_as(C.c_void_p), ts.xmax.ctypes.data_as(C.c_void_p)
+        if split:
+            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_INTERIOR, None, None))
+            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_FRAME, xm, xx))
+        else:
+            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, xm, xx))
+        xmin, xmax = np.minimum(xmin, ts.xmin), np.maximum(xmax, ts.xmax)   # xcminr/xcmaxr
+    nb = g1.nbdy
+    for ts in tss:
+        g = ts.cb.geom
+        sea_t = ts.cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
+        glob = (slice(None), slice(nb + g.j0, nb + g.j0 + g.jj), slice(nb + g.i0, nb + g.i0 + g.ii))
+        pairs = [(cabi.F_TEMP, 0, ref["temp"][n - 1]), (cabi.F_SALN, 0, ref["saln"][n - 1])]
+        pairs += [(cabi.F_TRACER, q + 1, ref["tracer"][q, n - 1]) for q in range(ntracr)]
+        for fld, ktr, r in pairs:
+            dev = ts.download(fld, n, ktr=ktr)[:, nb:nb + g.jj, nb:nb + g.ii]
+            assert np.array_equal(dev[:, sea_t], r[glob][:, sea_t]), (g.mproc, g.nproc, fld)
+        ts.close()
+    assert np.array_equal(xmin, ref["xmin"]) and np.array_equal(xmax, ref["xmax"])

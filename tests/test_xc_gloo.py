@@ -1,0 +1,121 @@
+"""The N>1 path on CPU: the product's exchange schedule (hycom-src_b200/xc.py) driven over
+torch.distributed/gloo with world_size 2 and 4, numpy doing the pack/unpack.  The data are a
+function of the GLOBAL (i,j,k) - the reference's own way of checking decompositions
+(mod_pipe.F90:26-127) - so after xctilr every halo cell must hold the value of the global
+cell it images (periodic wrap) or vland = 0 beyond a closed edge (mod_xc_sm.h:1377-1422)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import util
+from util import pkg
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _field(ig, jg, k, a):
+    return 1000.0 * a + 100.0 * k + ig + 0.001 * jg
+
+
+def _expected(g, a, kk, mh=5, nh=5):
+    """what xctilr must leave in the tile (interior + halo of width 5; NaN elsewhere)"""
+    nb = g.nbdy
+    out = np.full((kk, g.nrows, g.ncols), np.nan)
+    for r in range(nb - nh, nb + g.jj + nh):
+        for c in range(nb - mh, nb + g.ii + mh):
+            ig, jg = g.i0 + c + 1 - nb, g.j0 + r + 1 - nb
+            if g.periodic_i:
+                ig = (ig - 1) % g.itdm + 1
+            if g.periodic_j:
+                jg = (jg - 1) % g.jtdm + 1
+            inside = 1 <= ig <= g.itdm and 1 <= jg <= g.jtdm
+            for k in range(kk):
+                out[k, r, c] = _field(ig, jg, k, a) if inside else 0.0
+    return out
+
+
+def _worker(rank, world, port, itdm, jtdm, ipr, jpr, nreg, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import np_halo
+        kk, narr = 2, 3
+        g = pkg.partition(itdm, jtdm, kk, ipr, jpr, nreg)[rank]
+        nb = g.nbdy
+        arrays = []
+        for a in range(narr):
+            arr = np.full((kk, g.nrows, g.ncols), np.nan)
+            for k in range(kk):
+                jj_, ii_ = np.meshgrid(np.arange(1, g.jj + 1), np.arange(1, g.ii + 1), indexing="ij")
+                arr[k, nb:nb + g.jj, nb:nb + g.ii] = _field(g.i0 + ii_, g.j0 + jj_, k, a)
+            arrays.append(arr)
+        be = np_halo.NumpyHaloBackend(g, arrays)
+        ex = pkg.XcExchange(None, dist, backend=be)
+        for _ in range(2):               # twice: buffers are reused
+            ex.xctilr(1, 2)
+        ok = True
+        for a in range(narr):
+            exp = _expected(g, a, kk)
+            live = ~np.isnan(exp)
+            ok = ok and np.array_equal(arrays[a][live], exp[live])
+            # the sixth halo line is not touched by a width-5 exchange
+            ok = ok and np.isnan(arrays[a][~live]).all()
+        # xcminr/xcmaxr
+        lo, hi = np.array([float(rank), 5.0]), np.array([float(rank), 5.0])
+        ex.xcminmax(lo, hi)
+        ok = ok and lo[0] == 0.0 and hi[0] == world - 1
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = [
+    (2, 57, 41, 2, 1, 0),   # BASELINE configs[3] at 2 GPUs: 2x1 tiles, closed basin, ragged split
+    (2, 40, 37, 1, 2, 1),   # 1x2 tiles, periodic in i: E/W wrap onto the tile itself
+    (2, 44, 36, 2, 1, 3),   # 2x1 doubly periodic: both E and W neighbour are the other rank
+    (4, 45, 38, 2, 2, 3),   # 2x2 doubly periodic: every neighbour pair exchanges 4 messages
+    (4, 61, 33, 4, 1, 0),   # 4x1 closed
+]
+
+
+@pytest.mark.parametrize("world,itdm,jtdm,ipr,jpr,nreg", CASES)
+def test_xctilr_over_gloo(world, itdm, jtdm, ipr, jpr, nreg):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, itdm, jtdm, ipr, jpr, nreg, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res.values()), res
+
+
+def test_neighbour_tables():
+    xc = __import__("importlib").import_module("hycom-src_b200.xc")
+    tiles = pkg.partition(100, 80, 1, 4, 2, 0)
+    t = tiles[0]                      # SW corner of a closed basin
+    assert xc.neighbors(t) == [-1, 1, -1, 4, -1, -1, -1, 5]
+    t = tiles[5]                      # interior column, top row
+    assert xc.neighbors(t) == [4, 6, 1, -1, 0, 2, -1, -1]
+    tiles = pkg.partition(100, 80, 1, 4, 2, 1)   # periodic in i
+    assert xc.neighbors(tiles[0]) == [3, 1, -1, 4, -1, -1, 7, 5]
+    # message sizes: send size of a tile == receive size of its neighbour
+    tiles = pkg.partition(103, 81, 1, 4, 2, 3)
+    for t in tiles:
+        cnt, nbr = xc.halo_counts(t, 7), xc.neighbors(t)
+        for d in range(8):
+            assert cnt[d] == xc.halo_counts(tiles[nbr[d]], 7)[xc.OPP[d]]

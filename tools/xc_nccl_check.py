@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Parity of the multi-GPU path under real NCCL (run with torchrun, one rank per GPU):
+tsadvc(m,n) on ipr x jpr tiles with XcExchange (pack -> NCCL send/recv -> unpack overlapped
+with the tile interior) against the CPU oracle on ONE tile, bit for bit, two leapfrog steps.
+The oracle is test infrastructure: this script is a checker, not a product path."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import oracle_binding
+    import util
+    pkg, syn, cabi = util.pkg, util.syn, util.cabi
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ipr, jpr = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
+    ok_all = True
+    for (itdm, jtdm, kdm, nreg, ntracr, advtyp) in [(150, 150, 4, 0, 0, 2), (301, 203, 3, 3, 1, 2), (180, 120, 2, 1, 1, 1)]:
+        m, n = 1, 2
+        cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=9, m=m, n=n, advtyp=advtyp)
+        orc = oracle_binding.Oracle(os.path.join(ROOT, "oracle", "_build", "liboracle.so"))
+        ot = util.oracle_tile_from_cb(orc, cb1, sea)
+        g = pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)[rank]
+        cb = syn.build_cb_arrays(cfg, g, sea, m, n, advtyp=advtyp)
+        stream = torch.cuda.Stream()
+        ts = pkg.Tsadvc(cb, device=local, stream=stream.cuda_stream)
+        ts.upload_state(m, n)
+        ts.upload(cabi.F_DP, cb.dp[m - 1], m)
+        xc = pkg.XcExchange(ts, dist, compute_stream=stream)
+        nb = g.nbdy
+        for step, (mm, nn) in enumerate([(m, n), (n, m)]):
+            cb.nstep = 3 * (step + 1)
+            ot.set_i("nstep", cb.nstep) if hasattr(ot, "set_i") else None
+            ot.tsadvc(mm, nn, 1)
+            with torch.cuda.stream(stream):
+                xc.tsadvc_device(mm, nn, diag=True, overlap=(step == 0))
+            ts.synchronize()
+            sea_t = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
+            glob = (slice(None), slice(nb + g.j0, nb + g.j0 + g.jj), slice(nb + g.i0, nb + g.i0 + g.ii))
+            for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+                dev = ts.download(fld, nn)[:, nb:nb + g.jj, nb:nb + g.ii]
+                ref = ot.f64(name)[nn - 1][glob]
+                ok = np.array_equal(dev[:, sea_t], ref[:, sea_t])
+                ok_all = ok_all and ok
+                if not ok:
+                    print(f"rank {rank}: MISMATCH {name} step {step} case {(itdm, jtdm, nreg, advtyp)}", flush=True)
+        ts.close()
+        ot.close()
+    t = torch.tensor([1 if ok_all else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("xc_nccl_check:", "PASS" if int(t.item()) == 1 else "FAIL", f"(world {world}, tiles {ipr}x{jpr})", flush=True)
+    dist.destroy_process_group()
+    return 0 if int(t.item()) == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
