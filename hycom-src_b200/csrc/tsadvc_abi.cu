@@ -472,8 +472,8 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   const char* cb = getenv("HYCOM_TSADVC_MINB");
   P.minb = cb ? atoi(cb) : 3;
   const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
-  P.chunk_rows = ce ? atoi(ce) : 512;
-  if (P.chunk_rows < 8) P.chunk_rows = 8;
+  int chunk_rows = ce ? atoi(ce) : 512;
+  if (chunk_rows < 8) chunk_rows = 8;
 
   // (strip,row) rectangles of this part.  Interior = units whose staged window (apron and
   // prefetched row included) lies inside 1..ii x 1..jj, i.e. reads no halo cell.
@@ -484,24 +484,28 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   while (s_hi > s_lo && (s_hi - 1) * use - lead + wid > nb + h->d.ii) --s_hi;
   int r_lo = nb + 3, r_hi = nb + h->d.jj - 4;  // interior rows [r_lo, r_hi)
   if (s_lo >= s_hi || r_lo >= r_hi) { s_lo = s_hi = 0; r_lo = r_hi = 0; }
-  auto add = [&](int strip0, int ns, int row0, int row1) {
+  // the two side columns of the frame are only a few strips wide: short chunks give the
+  // launch enough warps to fill the machine
+  auto add = [&](int strip0, int ns, int row0, int row1, int crows) {
     if (ns <= 0 || row1 <= row0) return;
     MarchRect& R = P.rect[P.nrect++];
     R.strip0 = strip0; R.nstrips = ns; R.row0 = row0; R.row1 = row1;
-    R.nchunks = (row1 - row0 + P.chunk_rows - 1) / P.chunk_rows;
+    R.chunk_rows = crows;
+    R.nchunks = (row1 - row0 + crows - 1) / crows;
     R.unit0 = P.nunits;
     P.nunits += (long)P.njobs * ns * R.nchunks;
   };
   const bool empty_interior = (s_lo >= s_hi);
   if (part == HYCOM_TSADVC_PART_ALL || (part == HYCOM_TSADVC_PART_FRAME && empty_interior)) {
-    add(0, nstrips, 0, h->nrows);
+    add(0, nstrips, 0, h->nrows, chunk_rows);
   } else if (part == HYCOM_TSADVC_PART_INTERIOR) {
-    add(s_lo, s_hi - s_lo, r_lo, r_hi);
+    add(s_lo, s_hi - s_lo, r_lo, r_hi, chunk_rows);
   } else {
-    add(0, s_lo, 0, h->nrows);
-    add(s_hi, nstrips - s_hi, 0, h->nrows);
-    add(s_lo, s_hi - s_lo, 0, r_lo);
-    add(s_lo, s_hi - s_lo, r_hi, h->nrows);
+    const int side = chunk_rows < 48 ? chunk_rows : 48;
+    add(0, s_lo, 0, h->nrows, side);
+    add(s_hi, nstrips - s_hi, 0, h->nrows, side);
+    add(s_lo, s_hi - s_lo, 0, r_lo, chunk_rows);
+    add(s_lo, s_hi - s_lo, r_hi, h->nrows, chunk_rows);
   }
   if (P.nunits == 0) return 0;
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};

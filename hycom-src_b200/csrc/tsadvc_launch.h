@@ -12,7 +12,7 @@ struct MarchRect {
   int strip0, nstrips;   // strips strip0 .. strip0+nstrips-1
   int row0, row1;        // rows [row0, row1) are stored
   int nchunks;           // ceil((row1-row0)/chunk_rows)
-  int pad;
+  int chunk_rows;        // rows one warp marches (plus 6 rows of pipeline fill)
   long unit0;            // first unit: unit = unit0 + job + njobs*(strip + nstrips*chunk)
 };
 
@@ -28,7 +28,6 @@ struct MarchParams {
   Geo g;
   int nc;           // cells per lane (1 or 2)
   int minb;         // resident blocks per SM the variant is compiled for
-  int chunk_rows;
   // the launch covers up to four rectangles of (strip, row) space: one for a whole slab or
   // for the interior of a tile, four for the frame that depends on halo cells
   // (interior/frame split: the frame waits for the halo exchange, the interior overlaps it)
