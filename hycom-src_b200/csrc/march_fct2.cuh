@@ -154,6 +154,27 @@ __device__ __forceinline__ void maxmin_if(double& mx, double& mn, double xa, dou
       : "+d"(mx), "+d"(mn) : "d"(xa), "d"(xb), "r"(mword), "r"(bit));
 }
 
+// first step of a masked extremum: mx = (sea && xa > cmx) ? xa : cmx, mn likewise, into fresh
+// registers (the in-place form above would first have to copy the centre value)
+__device__ __forceinline__ void maxmin_first(double& mx, double& mn, double cmx, double cmn,
+                                             double xa, double xb, unsigned mword, unsigned bit) {
+  asm("{\n\t.reg .pred e, p, q;\n\t.reg .b32 t;\n\t"
+      "and.b32 t, %6, %7;\n\tsetp.ne.u32 e, t, 0;\n\t"
+      "setp.gt.and.f64 p, %4, %2, e;\n\t"
+      "setp.lt.and.f64 q, %5, %3, e;\n\t"
+      "selp.f64 %0, %4, %2, p;\n\t"
+      "selp.f64 %1, %5, %3, q;\n\t}"
+      : "=d"(mx), "=d"(mn) : "d"(cmx), "d"(cmn), "d"(xa), "d"(xb), "r"(mword), "r"(bit));
+}
+// min(x, 1.0) as one compare and one select (the ?: form is pattern-matched into a
+// NaN-propagating minimum that costs an extra fix-up instruction)
+__device__ __forceinline__ double min_one(double x) {
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, 0d3FF0000000000000;\n\t"
+      "selp.f64 %0, %1, 0d3FF0000000000000, p;\n\t}" : "=d"(r) : "d"(x));
+  return r;
+}
+
 template <int NC, int PH, bool SAFE>
 __device__ __forceinline__ void fct2_step(Fct2State<NC>& s, const MarchCtx& x, const int r, bool& bad) {
   constexpr int p2 = PH & 1, q2 = p2 ^ 1;                          // rows r (r-2), r-1 (r-3)

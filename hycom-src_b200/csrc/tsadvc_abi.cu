@@ -14,6 +14,7 @@
 #include "tsadvc_dev.h"
 #include "tsadvc_handle.h"
 #include "tsadvc_launch.h"
+#include "tma_maps.h"
 
 using namespace tsadvc;
 
@@ -78,8 +79,18 @@ int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
   const int s = is3d(field) ? 0 : tlev - 1;
   if (s < 0 || s > 1) return fail(h, HYCOM_TSADVC_EINVAL, "bad time slot %d", tlev);
   if (!mi->lev[s]) {
-    int rc = dalloc(h, (void**)&mi->lev[s], sizeof(double) * (size_t)h->slab * h->d.kdm, true);
-    if (rc) return rc;
+    if (field == HYCOM_F_DP || field == HYCOM_F_UFLX || field == HYCOM_F_VFLX) {
+      const size_t K = (size_t)h->slab * h->d.kdm;
+      int rc = dalloc(h, (void**)&h->flux_block, sizeof(double) * 4 * K, true);
+      if (rc) return rc;
+      h->dp.lev[0] = h->flux_block;
+      h->uflx.lev[0] = h->flux_block + K;
+      h->vflx.lev[0] = h->flux_block + 2 * K;
+      h->dp.lev[1] = h->flux_block + 3 * K;
+    } else {
+      int rc = dalloc(h, (void**)&mi->lev[s], sizeof(double) * (size_t)h->slab * h->d.kdm, true);
+      if (rc) return rc;
+    }
   }
   *out = mi->lev[s];
   return 0;
@@ -190,7 +201,7 @@ int hycom_tsadvc_create(const hycom_tsadvc_dims* dims, hycom_tsadvc_handle** out
   h->err[0] = 0;
   h->ncols = d.idm + 2 * d.nbdy;
   h->nrows = d.jdm + 2 * d.nbdy;
-  h->pitch = (h->ncols + 1) & ~1;
+  h->pitch = (h->ncols + 15) & ~15;  // rows 128-byte aligned; byte planes 16-byte (TMA strides)
   h->slab = (long)h->pitch * h->nrows;
   CU(h, cudaSetDevice(d.device));
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -204,9 +215,11 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   cudaSetDevice(h->d.device);
   cudaDeviceSynchronize();
   auto rel = [](Mirror& m) { cudaFree(m.lev[0]); cudaFree(m.lev[1]); cudaFree(m.spare); };
-  rel(h->temp); rel(h->saln); rel(h->th3d); rel(h->dp); rel(h->uflx); rel(h->vflx);
+  rel(h->temp); rel(h->saln); rel(h->th3d);
+  cudaFree(h->flux_block);    // dp, uflx, vflx
+  cudaFree(h->static_block);  // scp2i, scp2, mask plane
   for (auto& t : h->tracer) rel(t);
-  cudaFree(h->mask); cudaFree(h->scp2); cudaFree(h->scp2i); cudaFree(h->scuy); cudaFree(h->scvx);
+  cudaFree(h->mask); cudaFree(h->scuy); cudaFree(h->scvx);
   cudaFree(h->aspux); cudaFree(h->aspvy); cudaFree(h->d_minmax); cudaFree(h->d_sea);
   for (auto* v : {&h->ev_pending, &h->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -273,6 +286,11 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const do
     return fail(h, HYCOM_TSADVC_EINVAL, "set_static: scp2, scp2i, ip, iu, iv are required");
   CU(h, cudaSetDevice(h->d.device));
   int rc;
+  if (!h->static_block) {
+    if ((rc = dalloc(h, (void**)&h->static_block, sizeof(double) * 3 * (size_t)h->slab, true))) return rc;
+    h->scp2i = h->static_block;
+    h->scp2 = h->static_block + h->slab;
+  }
   if ((rc = up2d(h, &h->scp2, scp2))) return rc;
   if ((rc = up2d(h, &h->scp2i, scp2i))) return rc;
   if (scuy && (rc = up2d(h, &h->scuy, scuy))) return rc;
@@ -300,6 +318,13 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const do
     }
   if (!h->mask && (rc = dalloc(h, (void**)&h->mask, (size_t)h->slab, true))) return rc;
   CU(h, cudaMemcpyAsync(h->mask, m.data(), (size_t)h->slab, cudaMemcpyHostToDevice, h->stream));
+  {  // third plane of the static block: the mask byte in the low bits of a 64-bit word
+    std::vector<uint64_t> m64((size_t)h->slab);
+    for (size_t q = 0; q < m64.size(); ++q) m64[q] = m[q];
+    CU(h, cudaMemcpyAsync(h->static_block + 2 * h->slab, m64.data(), sizeof(uint64_t) * m64.size(),
+                          cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
   CU(h, cudaStreamSynchronize(h->stream));
   h->have_static = true;
   return 0;
@@ -437,6 +462,24 @@ int neighbour(const hycom_tsadvc_dims& d, int dir) {
   return mp + d.ipr * np;
 }
 
+// cached TMA descriptor of a mirror buffer; kind 0: (pitch,nrows,kdm) field, 1: flux block,
+// 2: static block
+int tmap_of(hycom_tsadvc_handle* h, const double* base, int kind, int nc, CUtensorMap* out) {
+  const auto key = std::make_pair((const void*)base, kind * 4 + nc);
+  auto it = h->tmaps.find(key);
+  if (it == h->tmaps.end()) {
+    CUtensorMap mp;
+    int rc;
+    if (kind == 0) rc = make_map_f64(&mp, base, h->pitch, h->nrows, h->d.kdm, 32 * nc, 1);
+    else if (kind == 1) rc = make_map_f64_4d(&mp, base, h->pitch, h->nrows, h->d.kdm, 4, 32 * nc, 3);
+    else rc = make_map_f64(&mp, base, h->pitch, h->nrows, 3, 32 * nc, 3);
+    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d, kind %d)", rc, kind);
+    it = h->tmaps.emplace(key, mp).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
 int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
               const std::vector<Adv>& adv, int part) {
   const int kk = h->d.kdm, aadv = abs(p.advtyp);
@@ -514,7 +557,23 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     else { CU(h, cudaEventCreate(&ev.first)); CU(h, cudaEventCreate(&ev.second)); }
     CU(h, cudaEventRecord(ev.first, h->stream));
   }
-  rc = launch_march(aadv, P, h->stream);
+  const char* ct = getenv("HYCOM_TSADVC_TMA");
+  const bool use_tma = (aadv == 2) && !(ct && atoi(ct) == 0);
+  if (use_tma) {
+    // raw rows staged through shared memory by the TMA engine (march_fct2_tma.cuh)
+    static thread_local TmaMaps T;
+    for (int f = 0; f < P.nfld; ++f) {
+      if ((rc = tmap_of(h, P.fld[f].fld, 0, P.nc, &T.fld[f]))) return rc;
+      if ((rc = tmap_of(h, P.fld[f].fldc, 0, P.nc, &T.fldc[f]))) return rc;
+    }
+    if ((rc = tmap_of(h, h->flux_block, 1, P.nc, &T.flux))) return rc;
+    if ((rc = tmap_of(h, h->static_block, 2, P.nc, &T.stat))) return rc;
+    P.dp_first = (n == 1) ? 1 : 0;
+    if (!cb) P.minb = (P.nc == 2) ? 2 : 4;
+    rc = launch_march_tma(T, P, h->stream);
+  } else {
+    rc = launch_march(aadv, P, h->stream);
+  }
   h->launches += 1;
   if (h->timing) {
     CU(h, cudaEventRecord(ev.second, h->stream));

@@ -4,7 +4,9 @@
 
 #include <cstdint>
 #include <utility>
+#include <map>
 #include <vector>
+#include <cuda.h>
 
 #include "../../include/hycom_tsadvc_b200.h"
 
@@ -29,6 +31,12 @@ struct hycom_tsadvc_handle {
          *aspvy = nullptr;
   tsadvc::Mirror temp, saln, th3d, dp, uflx, vflx;
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
+  // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)] so that a single 4-D TMA request
+  // fetches a row of uflx, vflx and dp(:,:,:,n) (planes 0..2 for n=1, 1..3 for n=2)
+  double* flux_block = nullptr;
+  // one allocation [scp2i | scp2 | mask as the low bits of a double] for the same reason
+  double* static_block = nullptr;
+  std::map<std::pair<const void*, int>, CUtensorMap> tmaps;  // (buffer, kind*4+nc) -> descriptor
   double* d_minmax = nullptr;  // 2*kdm
   uint8_t* d_sea = nullptr;    // synthetic generator: global sea mask
   // optional per-launch timing of the marching kernel (hycom_tsadvc_set_timing)
