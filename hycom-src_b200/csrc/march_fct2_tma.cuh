@@ -3,28 +3,28 @@
 // Same row pipeline as march_fct2.cuh (stage A row r, B row r-1, C/D row r-2, E row r-3) but
 // the RAW rows (fld, fldc, uflx, vflx, dp, scp2i, scp2, masks) are not carried in registers:
 // each warp owns a ring of six row slots in shared memory that the TMA engine fills
-// (cp.async.bulk.tensor, one request per array and row, completion on one mbarrier per
-// slot).  Row r+3 is requested at the end of iteration r, into the slot of row r-3 that
+// (cp.async.bulk global->shared, SASS UBLKCP: one 256*NC-byte request per array and row,
+// completion counted in bytes on one mbarrier per slot).  Row r+3 is requested at the end of iteration r, into the slot of row r-3 that
 // iteration r has just finished with, so three rows are always in flight and the prefetch
 // distance does not depend on the instruction scheduler.  i-neighbours of raw data are
-// plain shared-memory reads at lane-1 / lane+1; j-neighbours are older slots.  Out-of-range
-// rows and columns (apron of the first/last chunk and strip) are zero-filled by the TMA unit,
-// masks included, so no load is predicated.  Only computed intermediates stay in the
-// register rings, which frees about 40 registers against march_fct2.cuh.
+// plain shared-memory reads at lane-1 / lane+1; j-neighbours are older slots.  Rows outside
+// the slab (apron of the first/last chunk) are clamped to the nearest row; the window of the
+// first/last strip may start 4 columns before / end after its row, i.e. in the neighbouring
+// row or in the guard row every buffer is allocated with: real, finite data that only ever
+// feeds apron lanes (dependency radius 3 < nbdy).  Nothing is predicated.  Only computed
+// intermediates stay in the register rings (about 40 registers less than march_fct2.cuh).
+// (The tensor-map form cp.async.bulk.tensor / UTMALDG raises "illegal instruction" on this
+// pool's B200 boxes even for the CUDA programming guide's own example - tools/probe/ -
+// so the rows are fetched with the descriptor-less bulk copy.)
 #pragma once
-#include <cuda.h>
-
 #include "march_common.cuh"
 #include "march_fct2.cuh"
 #include "tsadvc_launch.h"
 
 namespace tsadvc {
 
-// One row slot = eight staged rows of 32*NC doubles, filled by FOUR requests:
-//   fld(n) | fld(m) | three planes of the flux block | three planes of the static block
-// The flux block is [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)] (tsadvc_handle.h): planes 0..2
-// when n=1 (DF: dp first), planes 1..3 when n=2 (dp last).  The static block is
-// [scp2i | scp2 | mask word].
+// One row slot = eight staged rows of 32*NC doubles: fld(n), fld(m), uflx, vflx, dp(n),
+// scp2i, scp2 and the mask word plane of the static block.
 template <int NC>
 struct Ring {
   static constexpr int RB = 256 * NC;   // bytes of one staged row of doubles (32*NC columns)
@@ -32,14 +32,9 @@ struct Ring {
   static constexpr int SLOT = NARR * RB;
   static constexpr int NSLOT = 6;
   static constexpr int BYTES = NSLOT * SLOT;           // per warp
-  static constexpr int TX = SLOT;                      // bytes one row request group delivers
-  enum { F = 0, C = 1, X = 2, SCI = 5, SC = 6, MSK = 7 };
+  static constexpr int TX = SLOT;                      // bytes the requests of one row deliver
+  enum { F = 0, C = 1, U = 2, V = 3, D = 4, SCI = 5, SC = 6, MSK = 7 };
 };
-template <bool DF> struct FluxOrder {
-  static constexpr int D = DF ? 2 : 4, U = DF ? 3 : 2, V = DF ? 4 : 3;
-};
-
-
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -75,33 +70,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (int spin = 0; !mbar_try(bar, parity); ++spin)
     if (spin > (1 << 16)) __trap();
 }
-__device__ __forceinline__ void tma_row3d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0,
-                                          int c1, int c2) {
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned),
+// completion on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_row4d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0,
-                                          int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
 
 struct TmaCtx {
-  const CUtensorMap *fld, *fldc, *flux, *stat;
-  int plane0;            // first plane of the flux block: 0 (n=1) or 1 (n=2)
+  // slabs of this (field, layer): element (row 0, column w0) of each staged array
+  const double *fld, *fldc, *u, *v, *dp, *sci, *sc, *msk;
   double* __restrict__ out;
   unsigned char* ring;   // this warp's ring (generic pointer into shared memory)
   uint32_t ring_s;       // same, shared-window address
   uint32_t bar_s;        // six mbarriers of this warp
-  int pitch;
-  int w0, k0;            // first staged column, layer (slab) index
+  int pitch, nrows;
+  int w0;                // first staged column (even: 16-byte aligned requests)
   int lane;
   int j0, j1;
   double dt2, qdt2x2;
@@ -113,11 +99,16 @@ __device__ __forceinline__ void issue_row(const TmaCtx& x, int r, int slot) {
   typedef Ring<NC> R;
   const uint32_t bar = x.bar_s + 8u * slot;
   const uint32_t dst = x.ring_s + (uint32_t)(slot * R::SLOT);
+  const long off = (long)max(0, min(r, x.nrows - 1)) * x.pitch;
   mbar_expect_tx(bar, R::TX);
-  tma_row3d(x.fld, dst + R::F * R::RB, bar, x.w0, r, x.k0);
-  tma_row3d(x.fldc, dst + R::C * R::RB, bar, x.w0, r, x.k0);
-  tma_row4d(x.flux, dst + R::X * R::RB, bar, x.w0, r, x.k0, x.plane0);
-  tma_row3d(x.stat, dst + R::SCI * R::RB, bar, x.w0, r, 0);
+  bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
+  bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
+  bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
+  bulk_g2s(dst + R::V * R::RB, x.v + off, R::RB, bar);
+  bulk_g2s(dst + R::D * R::RB, x.dp + off, R::RB, bar);
+  bulk_g2s(dst + R::SCI * R::RB, x.sci + off, R::RB, bar);
+  bulk_g2s(dst + R::SC * R::RB, x.sc + off, R::RB, bar);
+  bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);
 }
 
 template <int NC>
@@ -172,12 +163,11 @@ __device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, int slot) {
   return m;
 }
 
-template <int NC, bool DF, int PH, bool SAFE>
+template <int NC, int PH, bool SAFE>
 __device__ __forceinline__ void fct2t_step(Fct2T<NC>& s, const TmaCtx& x, const RingPtr& p,
                                            const int r, const bool more, const uint32_t parity,
                                            bool& bad) {
   typedef Ring<NC> R;
-  typedef FluxOrder<DF> X;
   constexpr int p2 = PH & 1, q2 = p2 ^ 1;
   constexpr int a3 = PH % 3, b3 = (PH + 2) % 3, c3 = (PH + 1) % 3;
   constexpr int s0 = PH % 6, s1 = (PH + 5) % 6, s2 = (PH + 4) % 6, s3 = (PH + 3) % 6;  // rows r..r-3
@@ -193,11 +183,11 @@ __device__ __forceinline__ void fct2t_step(Fct2T<NC>& s, const TmaCtx& x, const 
   ld_own<NC, R::C>(p, s1, C1);
   const unsigned m0 = ld_mask_s<NC>(p, s0);
   double V0[NC];
-  ld_own<NC, X::V>(p, s0, V0);
+  ld_own<NC, R::V>(p, s0, V0);
   {
     double C0[NC], U0[NC], FW[NC], CW[NC], flx[NC];
     ld_own<NC, R::C>(p, s0, C0);
-    ld_own<NC, X::U>(p, s0, U0);
+    ld_own<NC, R::U>(p, s0, U0);
     ld_west<NC, R::F>(p, s0, F0, FW);
     ld_west<NC, R::C>(p, s0, C0, CW);
 #pragma unroll
@@ -224,10 +214,10 @@ __device__ __forceinline__ void fct2t_step(Fct2T<NC>& s, const TmaCtx& x, const 
     ld_west<NC, R::F>(p, s1, F1, Fw);
     ld_east<NC, R::F>(p, s1, F1, Fe);
     ld_own<NC, R::F>(p, s2, F2);
-    ld_own<NC, X::U>(p, s1, U1);
-    ld_east<NC, X::U>(p, s1, U1, UE);
-    ld_own<NC, X::V>(p, s1, V1);
-    ld_own<NC, X::D>(p, s1, D1);
+    ld_own<NC, R::U>(p, s1, U1);
+    ld_east<NC, R::U>(p, s1, U1, UE);
+    ld_own<NC, R::V>(p, s1, V1);
+    ld_own<NC, R::D>(p, s1, D1);
     ld_own<NC, R::SCI>(p, s1, SCI1);
     double q[NC], b[NC], y[NC], fmx[NC], fmn[NC];
 #pragma unroll
@@ -358,7 +348,7 @@ __device__ __forceinline__ void fct2t_step(Fct2T<NC>& s, const TmaCtx& x, const 
   if (more && elect_one()) issue_row<NC>(x, r + 3, s3);
 }
 
-template <int NC, bool DF, bool SAFE>
+template <int NC, bool SAFE>
 __device__ __forceinline__ bool march_fct2_tma_pass(const TmaCtx& x, const RingPtr& p, uint32_t& round) {
   Fct2T<NC> s;
 #pragma unroll
@@ -394,23 +384,23 @@ __device__ __forceinline__ bool march_fct2_tma_pass(const TmaCtx& x, const RingP
   for (int t = 0; t < niter; t += 6) {
     const int r = r0 + t;
     const uint32_t par = round & 1u;
-    fct2t_step<NC, DF, 0, SAFE>(s, x, p, r, t + 3 < niter, par, bad);
-    fct2t_step<NC, DF, 1, SAFE>(s, x, p, r + 1, t + 4 < niter, par, bad);
-    fct2t_step<NC, DF, 2, SAFE>(s, x, p, r + 2, t + 5 < niter, par, bad);
-    fct2t_step<NC, DF, 3, SAFE>(s, x, p, r + 3, t + 6 < niter, par, bad);
-    fct2t_step<NC, DF, 4, SAFE>(s, x, p, r + 4, t + 7 < niter, par, bad);
-    fct2t_step<NC, DF, 5, SAFE>(s, x, p, r + 5, t + 8 < niter, par, bad);
+    fct2t_step<NC, 0, SAFE>(s, x, p, r, t + 3 < niter, par, bad);
+    fct2t_step<NC, 1, SAFE>(s, x, p, r + 1, t + 4 < niter, par, bad);
+    fct2t_step<NC, 2, SAFE>(s, x, p, r + 2, t + 5 < niter, par, bad);
+    fct2t_step<NC, 3, SAFE>(s, x, p, r + 3, t + 6 < niter, par, bad);
+    fct2t_step<NC, 4, SAFE>(s, x, p, r + 4, t + 7 < niter, par, bad);
+    fct2t_step<NC, 5, SAFE>(s, x, p, r + 5, t + 8 < niter, par, bad);
     ++round;
   }
   return bad;
 }
 
-template <int NC, bool DF>
+template <int NC>
 __device__ __noinline__ void march_fct2_tma_safe(const TmaCtx x, const RingPtr p, uint32_t round) {
-  march_fct2_tma_pass<NC, DF, true>(x, p, round);
+  march_fct2_tma_pass<NC, true>(x, p, round);
 }
 
-template <int NC, bool DF>
+template <int NC>
 __device__ void march_fct2_tma(const TmaCtx& x) {
   typedef Ring<NC> R;
   RingPtr p;
@@ -425,8 +415,8 @@ __device__ void march_fct2_tma(const TmaCtx& x) {
   }
   __syncwarp();
   uint32_t round = 0;
-  const bool bad = march_fct2_tma_pass<NC, DF, false>(x, p, round);
-  if (__any_sync(TSADVC_FULLMASK, bad)) march_fct2_tma_safe<NC, DF>(x, p, round);
+  const bool bad = march_fct2_tma_pass<NC, false>(x, p, round);
+  if (__any_sync(TSADVC_FULLMASK, bad)) march_fct2_tma_safe<NC>(x, p, round);
 }
 
 }  // namespace tsadvc

@@ -14,7 +14,6 @@
 #include "tsadvc_dev.h"
 #include "tsadvc_handle.h"
 #include "tsadvc_launch.h"
-#include "tma_maps.h"
 
 using namespace tsadvc;
 
@@ -56,6 +55,17 @@ int dalloc(hycom_tsadvc_handle* h, void** p, size_t nbytes, bool zero) {
   return 0;
 }
 
+// field buffers: one zeroed guard row on each side (see tsadvc_handle.h)
+int dalloc_field(hycom_tsadvc_handle* h, double** p, size_t ndoubles) {
+  void* raw = nullptr;
+  const size_t g = (size_t)h->pitch;
+  int rc = dalloc(h, &raw, sizeof(double) * (ndoubles + 2 * g), true);
+  if (rc) return rc;
+  h->raw_allocs.push_back(raw);
+  *p = (double*)raw + g;
+  return 0;
+}
+
 Mirror* mirror_of(hycom_tsadvc_handle* h, int field, int ktr) {
   switch (field) {
     case HYCOM_F_TEMP: return &h->temp;
@@ -81,14 +91,14 @@ int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
   if (!mi->lev[s]) {
     if (field == HYCOM_F_DP || field == HYCOM_F_UFLX || field == HYCOM_F_VFLX) {
       const size_t K = (size_t)h->slab * h->d.kdm;
-      int rc = dalloc(h, (void**)&h->flux_block, sizeof(double) * 4 * K, true);
+      int rc = dalloc_field(h, &h->flux_block, 4 * K);
       if (rc) return rc;
       h->dp.lev[0] = h->flux_block;
       h->uflx.lev[0] = h->flux_block + K;
       h->vflx.lev[0] = h->flux_block + 2 * K;
       h->dp.lev[1] = h->flux_block + 3 * K;
     } else {
-      int rc = dalloc(h, (void**)&mi->lev[s], sizeof(double) * (size_t)h->slab * h->d.kdm, true);
+      int rc = dalloc_field(h, &mi->lev[s], (size_t)h->slab * h->d.kdm);
       if (rc) return rc;
     }
   }
@@ -98,7 +108,7 @@ int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
 
 int spare_of(hycom_tsadvc_handle* h, Mirror* mi, double** out) {
   if (!mi->spare) {
-    int rc = dalloc(h, (void**)&mi->spare, sizeof(double) * (size_t)h->slab * h->d.kdm, true);
+    int rc = dalloc_field(h, &mi->spare, (size_t)h->slab * h->d.kdm);
     if (rc) return rc;
   }
   *out = mi->spare;
@@ -214,11 +224,7 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->d.device);
   cudaDeviceSynchronize();
-  auto rel = [](Mirror& m) { cudaFree(m.lev[0]); cudaFree(m.lev[1]); cudaFree(m.spare); };
-  rel(h->temp); rel(h->saln); rel(h->th3d);
-  cudaFree(h->flux_block);    // dp, uflx, vflx
-  cudaFree(h->static_block);  // scp2i, scp2, mask plane
-  for (auto& t : h->tracer) rel(t);
+  for (void* raw : h->raw_allocs) cudaFree(raw);  // field mirrors, flux block, static block
   cudaFree(h->mask); cudaFree(h->scuy); cudaFree(h->scvx);
   cudaFree(h->aspux); cudaFree(h->aspvy); cudaFree(h->d_minmax); cudaFree(h->d_sea);
   for (auto* v : {&h->ev_pending, &h->ev_free})
@@ -287,7 +293,7 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const do
   CU(h, cudaSetDevice(h->d.device));
   int rc;
   if (!h->static_block) {
-    if ((rc = dalloc(h, (void**)&h->static_block, sizeof(double) * 3 * (size_t)h->slab, true))) return rc;
+    if ((rc = dalloc_field(h, &h->static_block, 3 * (size_t)h->slab))) return rc;
     h->scp2i = h->static_block;
     h->scp2 = h->static_block + h->slab;
   }
@@ -462,24 +468,6 @@ int neighbour(const hycom_tsadvc_dims& d, int dir) {
   return mp + d.ipr * np;
 }
 
-// cached TMA descriptor of a mirror buffer; kind 0: (pitch,nrows,kdm) field, 1: flux block,
-// 2: static block
-int tmap_of(hycom_tsadvc_handle* h, const double* base, int kind, int nc, CUtensorMap* out) {
-  const auto key = std::make_pair((const void*)base, kind * 4 + nc);
-  auto it = h->tmaps.find(key);
-  if (it == h->tmaps.end()) {
-    CUtensorMap mp;
-    int rc;
-    if (kind == 0) rc = make_map_f64(&mp, base, h->pitch, h->nrows, h->d.kdm, 32 * nc, 1);
-    else if (kind == 1) rc = make_map_f64_4d(&mp, base, h->pitch, h->nrows, h->d.kdm, 4, 32 * nc, 3);
-    else rc = make_map_f64(&mp, base, h->pitch, h->nrows, 3, 32 * nc, 3);
-    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d, kind %d)", rc, kind);
-    it = h->tmaps.emplace(key, mp).first;
-  }
-  *out = it->second;
-  return 0;
-}
-
 int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
               const std::vector<Adv>& adv, int part) {
   const int kk = h->d.kdm, aadv = abs(p.advtyp);
@@ -509,6 +497,7 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   P.g.pitch = h->pitch; P.g.ncols = h->ncols; P.g.nrows = h->nrows; P.g.nbdy = h->d.nbdy;
   P.g.ii = h->d.ii; P.g.jj = h->d.jj;
   P.g.mask = h->mask; P.g.scp2 = h->scp2; P.g.scp2i = h->scp2i;
+  P.g.mask64 = h->static_block + 2 * h->slab;
   P.g.delt1 = p.delt1; P.g.onemm = p.onemm;
   const char* cn = getenv("HYCOM_TSADVC_NC");
   P.nc = (aadv == 2 && !(cn && atoi(cn) == 2)) ? 1 : 2;
@@ -561,16 +550,8 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   const bool use_tma = (aadv == 2) && !(ct && atoi(ct) == 0);
   if (use_tma) {
     // raw rows staged through shared memory by the TMA engine (march_fct2_tma.cuh)
-    static thread_local TmaMaps T;
-    for (int f = 0; f < P.nfld; ++f) {
-      if ((rc = tmap_of(h, P.fld[f].fld, 0, P.nc, &T.fld[f]))) return rc;
-      if ((rc = tmap_of(h, P.fld[f].fldc, 0, P.nc, &T.fldc[f]))) return rc;
-    }
-    if ((rc = tmap_of(h, h->flux_block, 1, P.nc, &T.flux))) return rc;
-    if ((rc = tmap_of(h, h->static_block, 2, P.nc, &T.stat))) return rc;
-    P.dp_first = (n == 1) ? 1 : 0;
-    if (!cb) P.minb = (P.nc == 2) ? 2 : 4;
-    rc = launch_march_tma(T, P, h->stream);
+    if (!cb) P.minb = (P.nc == 2) ? 2 : 3;
+    rc = launch_march_tma(P, h->stream);
   } else {
     rc = launch_march(aadv, P, h->stream);
   }

@@ -54,6 +54,7 @@ struct Geo {
   int nbdy;
   int ii, jj;  // tile extent
   const uint8_t* mask;  // nrows x pitch bytes, MaskBits
+  const double* mask64; // the same byte in the low bits of a 64-bit word (TMA-staged path)
   const double* scp2;   // scal
   const double* scp2i;  // scali
   double delt1;         // dt2
@@ -65,10 +66,12 @@ struct Geo {
 // radius of FCT2/MPDATA (the reference's margins 4,3,3,2,1,0 are wider than needed)
 constexpr int kApron = 3;
 __host__ __device__ constexpr int strip_use(int nc) { return 32 * nc - 2 * kApron; }
-// first column of strip s is s*strip_use - strip_lead (even for nc=2: 16-byte vector loads)
-__host__ __device__ constexpr int strip_lead(int nc) { return nc == 2 ? 4 : 3; }
+// first column of strip s is s*strip_use - strip_lead: even, so that vector loads and the
+// bulk copies of the TMA path are 16-byte aligned; the strip yields columns
+// s*strip_use - 1 .. (s+1)*strip_use - 2
+__host__ __device__ constexpr int strip_lead(int) { return 4; }
 __host__ __device__ constexpr int strip_count(int pitch, int nc) {
-  return (pitch + (nc == 2 ? 1 : 0) + strip_use(nc) - 1) / strip_use(nc);
+  return (pitch + 1 + strip_use(nc) - 1) / strip_use(nc);
 }
 
 }  // namespace tsadvc

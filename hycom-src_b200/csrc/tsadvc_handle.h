@@ -4,9 +4,7 @@
 
 #include <cstdint>
 #include <utility>
-#include <map>
 #include <vector>
-#include <cuda.h>
 
 #include "../../include/hycom_tsadvc_b200.h"
 
@@ -31,12 +29,13 @@ struct hycom_tsadvc_handle {
          *aspvy = nullptr;
   tsadvc::Mirror temp, saln, th3d, dp, uflx, vflx;
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
-  // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)] so that a single 4-D TMA request
-  // fetches a row of uflx, vflx and dp(:,:,:,n) (planes 0..2 for n=1, 1..3 for n=2)
+  // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)]
   double* flux_block = nullptr;
-  // one allocation [scp2i | scp2 | mask as the low bits of a double] for the same reason
+  // one allocation [scp2i | scp2 | mask byte in the low bits of a 64-bit word]
   double* static_block = nullptr;
-  std::map<std::pair<const void*, int>, CUtensorMap> tmaps;  // (buffer, kind*4+nc) -> descriptor
+  // every field buffer is allocated with one guard row in front and behind (the bulk copies
+  // of the first/last strip start 4 columns before / end after their row); freed from here
+  std::vector<void*> raw_allocs;
   double* d_minmax = nullptr;  // 2*kdm
   uint8_t* d_sea = nullptr;    // synthetic generator: global sea mask
   // optional per-launch timing of the marching kernel (hycom_tsadvc_set_timing)

@@ -1,6 +1,5 @@
 // host <-> kernel launch contract of the marching kernels
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "tsadvc_dev.h"
@@ -27,7 +26,6 @@ struct MarchParams {
   long slab;         // doubles per 2-D slab (pitch*nrows)
   int njobs;         // nfld*kk; job = field + nfld*(k-1): T and S of a layer adjacent
   Geo g;
-  int dp_first;     // TMA path: dp(:,:,:,n) is plane 0 of the flux block (n=1), else plane 3
   int nc;           // cells per lane (1 or 2)
   int minb;         // resident blocks per SM the variant is compiled for
   // the launch covers up to four rectangles of (strip, row) space: one for a whole slab or
@@ -41,15 +39,8 @@ struct MarchParams {
 // scheme: 1 = MPDATA, 2 = FCT2 (advtyp of blkdat.input, mod_tsadvc.F90:87-90)
 int launch_march(int scheme, const MarchParams& P, cudaStream_t stream);
 
-// TMA-staged FCT2 launch (tsadvc_kernels.cu): the tensor maps of one launch
-// (kernel parameter, __grid_constant__)
-struct TmaMaps {
-  CUtensorMap fld[kMaxFields];    // (pitch, nrows, kdm)
-  CUtensorMap fldc[kMaxFields];
-  CUtensorMap flux;               // (pitch, nrows, kdm, 4): dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)
-  CUtensorMap stat;               // (pitch, nrows, 3):      scp2i | scp2 | mask word
-};
-int launch_march_tma(const TmaMaps& T, const MarchParams& P, cudaStream_t stream);
+// TMA-staged FCT2 launch (tsadvc_kernels.cu, march_fct2_tma.cuh)
+int launch_march_tma(const MarchParams& P, cudaStream_t stream);
 
 // aux kernels (halo.cu)
 int launch_halo_local(double* base, long slab, int nslab, int pitch, int nbdy, int ii, int jj,
