@@ -1,115 +1,30 @@
-// advem_fct2 (mod_tsadvc.F90:645-997) + tsadvc prolog (:1905-1942), TMA-staged marching.
+// advem_fct2 (mod_tsadvc.F90:645-997) + tsadvc prolog (:1905-1942) as a scheme of the
+// TMA-staged march (march_tma_common.cuh).
 //
-// Same row pipeline as march_fct2.cuh (stage A row r, B row r-1, C/D row r-2, E row r-3) but
-// the RAW rows (fld, fldc, uflx, vflx, dp, scp2i, scp2, masks) are not carried in registers:
-// each warp owns a ring of six row slots in shared memory that the TMA engine fills
-// (cp.async.bulk global->shared, SASS UBLKCP: one 256*NC-byte request per array and row,
-// completion counted in bytes on one mbarrier per slot).  Row r+3 is requested at the end of iteration r, into the slot of row r-3 that
-// iteration r has just finished with, so three rows are always in flight and the prefetch
-// distance does not depend on the instruction scheduler.  i-neighbours of raw data are
-// plain shared-memory reads at lane-1 / lane+1; j-neighbours are older slots.  Rows outside
-// the slab (apron of the first/last chunk) are clamped to the nearest row; the window of the
-// first/last strip may start 4 columns before / end after its row, i.e. in the neighbouring
-// row or in the guard row every buffer is allocated with: real, finite data that only ever
-// feeds apron lanes (dependency radius 3 < nbdy).  Nothing is predicated.  Only computed
-// intermediates stay in the register rings (about 40 registers less than march_fct2.cuh).
-// (The tensor-map form cp.async.bulk.tensor / UTMALDG raises "illegal instruction" on this
-// pool's B200 boxes even for the CUDA programming guide's own example - tools/probe/ -
-// so the rows are fetched with the descriptor-less bulk copy.)
+//   stage A, row r   : S1 upwind fluxes flx,fly (:692-707) and S3 antidiffusive fluxes
+//                      fax,fay (:823-830); coast zeroing (:738-758, :835-855) by select
+//   stage B, row r-1 : prolog fco,fcn (:1934-1938), S1 extrema (:708-717), S2 low-order
+//                      solution fldlo and fmxlo,fmnlo (:786-795)
+//   stage C, row r-2 : S4 Zalesak ratios rp,rm and fmx,fmn (:869-906)
+//   stage D, row r-2 : S5 flux limiting (:926-945)
+//   stage E, row r-3 : S6 update (:968-980) and store
+//
+// Instruction diet (the kernel is issue-bound, not HBM-bound: DESIGN.md section 4):
+//   * sea-only neighbour selection (ipim1.. of bigrid.F90:316-341) is folded into the
+//     predicate input of the DSETP of each max/min step instead of a 64-bit select;
+//   * max(0,x), min(0,x) of S4 are formed as (x+|x|), (x-|x|) = twice the exact parts,
+//     the factor 2 is carried through famax/famin and 2*qdt2 and cancels in the quotient
+//     (scaling by 2 is exact, so every rounding is the reference's);
+//   * rp/rm are min(1, q/fa) evaluated with the reference's guard fa > 0; where fa == 0
+//     the reference stores 0 but that value only ever multiplies fluxes that are zero,
+//     so any finite stand-in gives identical results (and saves two selects);
+//   * comparisons against zero use the sign bit on the integer pipe;
+//   * one reciprocal of (fcn+onemu) serves the divisions of S2 and S6;
+//   * divisions are branch-free with a sticky flag and a whole-chunk redo (march_common.cuh).
 #pragma once
-#include "march_common.cuh"
-#include "march_fct2.cuh"
-#include "tsadvc_launch.h"
+#include "march_tma_common.cuh"
 
 namespace tsadvc {
-
-// One row slot = eight staged rows of 32*NC doubles: fld(n), fld(m), uflx, vflx, dp(n),
-// scp2i, scp2 and the mask word plane of the static block.
-template <int NC>
-struct Ring {
-  static constexpr int RB = 256 * NC;   // bytes of one staged row of doubles (32*NC columns)
-  static constexpr int NARR = 8;
-  static constexpr int SLOT = NARR * RB;
-  static constexpr int NSLOT = 6;
-  static constexpr int BYTES = NSLOT * SLOT;           // per warp
-  static constexpr int TX = SLOT;                      // bytes the requests of one row deliver
-  enum { F = 0, C = 1, U = 2, V = 3, D = 4, SCI = 5, SC = 6, MSK = 7 };
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-// one lane of the (converged) warp; the compiler recognises elect.sync as the guard of a
-// uniform-datapath instruction and emits UTMALDG without a per-thread serialisation loop
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}"
-               : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// wait for the row in a slot; a request that never completes (bad descriptor) traps instead
-// of hanging the device
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  for (int spin = 0; !mbar_try(bar, parity); ++spin)
-    if (spin > (1 << 16)) __trap();
-}
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned),
-// completion on the mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-
-struct TmaCtx {
-  // slabs of this (field, layer): element (row 0, column w0) of each staged array
-  const double *fld, *fldc, *u, *v, *dp, *sci, *sc, *msk;
-  double* __restrict__ out;
-  unsigned char* ring;   // this warp's ring (generic pointer into shared memory)
-  uint32_t ring_s;       // same, shared-window address
-  uint32_t bar_s;        // six mbarriers of this warp
-  int pitch, nrows;
-  int w0;                // first staged column (even: 16-byte aligned requests)
-  int lane;
-  int j0, j1;
-  double dt2, qdt2x2;
-};
-
-// request row r of every staged array into slot `slot` (one lane)
-template <int NC>
-__device__ __forceinline__ void issue_row(const TmaCtx& x, int r, int slot) {
-  typedef Ring<NC> R;
-  const uint32_t bar = x.bar_s + 8u * slot;
-  const uint32_t dst = x.ring_s + (uint32_t)(slot * R::SLOT);
-  const long off = (long)max(0, min(r, x.nrows - 1)) * x.pitch;
-  mbar_expect_tx(bar, R::TX);
-  bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
-  bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
-  bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
-  bulk_g2s(dst + R::V * R::RB, x.v + off, R::RB, bar);
-  bulk_g2s(dst + R::D * R::RB, x.dp + off, R::RB, bar);
-  bulk_g2s(dst + R::SCI * R::RB, x.sci + off, R::RB, bar);
-  bulk_g2s(dst + R::SC * R::RB, x.sc + off, R::RB, bar);
-  bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);
-}
 
 template <int NC>
 struct Fct2T {                                       // computed intermediates only
@@ -123,58 +38,37 @@ struct Fct2T {                                       // computed intermediates o
   unsigned m1, m2, m3;                               // masks of rows r-1, r-2, r-3
 };
 
-// per-lane views of the ring: own columns, west neighbour of the first own column, east
-// neighbour of the last own column (clamped inside the row: the clamped lanes are apron)
-struct RingPtr {
-  const unsigned char *c, *w, *e;
-};
-
-template <int NC, int ARR>
-__device__ __forceinline__ void ld_own(const RingPtr& p, int slot, double (&x)[NC]) {
-  typedef Ring<NC> R;
-  const unsigned char* a = p.c + slot * R::SLOT + ARR * R::RB;
-  if (NC == 2) {
-    const double2 v = *reinterpret_cast<const double2*>(a);
-    x[0] = v.x; x[NC - 1] = v.y;
-  } else {
-    x[0] = *reinterpret_cast<const double*>(a);
-  }
-}
-template <int NC, int ARR>
-__device__ __forceinline__ void ld_west(const RingPtr& p, int slot, const double (&own)[NC],
-                                        double (&w)[NC]) {
-  typedef Ring<NC> R;
-  w[0] = *reinterpret_cast<const double*>(p.w + slot * R::SLOT + ARR * R::RB);
-  if (NC == 2) w[NC - 1] = own[0];
-}
-template <int NC, int ARR>
-__device__ __forceinline__ void ld_east(const RingPtr& p, int slot, const double (&own)[NC],
-                                        double (&e)[NC]) {
-  typedef Ring<NC> R;
-  e[NC - 1] = *reinterpret_cast<const double*>(p.e + slot * R::SLOT + ARR * R::RB);
-  if (NC == 2) e[0] = own[NC - 1];
-}
 template <int NC>
-__device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, int slot) {
-  typedef Ring<NC> R;
-  const unsigned char* a = p.c + slot * R::SLOT + R::MSK * R::RB;   // low word of the mask plane
-  unsigned m = *reinterpret_cast<const unsigned*>(a);
-  if (NC == 2) m |= *reinterpret_cast<const unsigned*>(a + 8) << 8;
-  return m;
-}
+struct Fct2Scheme {
+  typedef Fct2T<NC> State;
+  static constexpr bool kNeedC = true;
 
-template <int NC, int PH, bool SAFE>
-__device__ __forceinline__ void fct2t_step(Fct2T<NC>& s, const TmaCtx& x, const RingPtr& p,
-                                           const int r, const bool more, const uint32_t parity,
-                                           bool& bad) {
+  static __device__ __forceinline__ void init(State& s) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        s.FAX[q][c] = 0.0; s.FAY[q][c] = 0.0; s.LO[q][c] = 0.0; s.FCN[q][c] = 0.0;
+        s.Y[q][c] = 1.0; s.MXL[q][c] = 0.0; s.MNL[q][c] = 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        s.DFLX[q][c] = 0.0; s.FLY[q][c] = 0.0; s.RP[q][c] = 0.0; s.RM[q][c] = 0.0;
+        s.QMX[q][c] = 0.0; s.QMN[q][c] = 0.0; s.DFAXL[q][c] = 0.0; s.FAYL[q][c] = 0.0;
+      }
+    }
+    s.m1 = s.m2 = s.m3 = 0u;
+  }
+
+  template <int PH, bool SAFE>
+  static __device__ __forceinline__ void step(State& s, const TmaCtx& x, const RingPtr& p, const int r,
+                                              bool& bad) {
   typedef Ring<NC> R;
   constexpr int p2 = PH & 1, q2 = p2 ^ 1;
   constexpr int a3 = PH % 3, b3 = (PH + 2) % 3, c3 = (PH + 1) % 3;
   constexpr int s0 = PH % 6, s1 = (PH + 5) % 6, s2 = (PH + 4) % 6, s3 = (PH + 3) % 6;  // rows r..r-3
   const double onemu = 9806.e-12;  // :671
   const double dt2 = x.dt2;
-
-  mbar_wait(x.bar_s + 8u * s0, parity);   // row r has landed
 
   // ---- stage A: row r
   double F0[NC], F1[NC], C1[NC];
@@ -301,7 +195,7 @@ __device__ __forceinline__ void fct2t_step(Fct2T<NC>& s, const TmaCtx& x, const 
       rr[i] = div_flag<SAFE>(qq[i], bb[i], SAFE ? 0.0 : rcp_nr(bb[i]), bad);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      // :884-903: rp = famax>0 ? (qp<famax ? qp/famax : 1) : 0 ; see march_fct2.cuh for fa==0
+      // :884-903: rp = famax>0 ? (qp<famax ? qp/famax : 1) : 0 ; see the header note for fa==0
       s.RP[p2][c] = min_one(rr[2 * c]);
       s.RM[p2][c] = min_one(rr[2 * c + 1]);
     }
@@ -342,81 +236,9 @@ __device__ __forceinline__ void fct2t_step(Fct2T<NC>& s, const TmaCtx& x, const 
     }
   }
   s.m3 = s.m2; s.m2 = s.m1; s.m1 = m0;
+  }
 
-  // slot s3 (row r-3) is free now: request row r+3 into it
-  __syncwarp();
-  if (more && elect_one()) issue_row<NC>(x, r + 3, s3);
-}
 
-template <int NC, bool SAFE>
-__device__ __forceinline__ bool march_fct2_tma_pass(const TmaCtx& x, const RingPtr& p, uint32_t& round) {
-  Fct2T<NC> s;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      s.FAX[q][c] = 0.0; s.FAY[q][c] = 0.0; s.LO[q][c] = 0.0; s.FCN[q][c] = 0.0;
-      s.Y[q][c] = 1.0; s.MXL[q][c] = 0.0; s.MNL[q][c] = 0.0;
-    }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      s.DFLX[q][c] = 0.0; s.FLY[q][c] = 0.0; s.RP[q][c] = 0.0; s.RM[q][c] = 0.0;
-      s.QMX[q][c] = 0.0; s.QMN[q][c] = 0.0; s.DFAXL[q][c] = 0.0; s.FAYL[q][c] = 0.0;
-    }
-  }
-  s.m1 = s.m2 = s.m3 = 0u;
-  bool bad = false;
-  const int r0 = x.j0 - 3;
-  const int niter = ((x.j1 - x.j0) + 6 + 5) / 6 * 6;   // rows j0-3 .. j1+2, whole rounds of six
-  // rows r0-3..r0-1 are "below the chunk": zeros with an all-land mask (never stored)
-  {
-    typedef Ring<NC> R;
-    double* z = reinterpret_cast<double*>(x.ring + 3 * R::SLOT);
-    for (int i = x.lane; i < 3 * R::SLOT / 8; i += 32) z[i] = 0.0;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-  }
-  if (elect_one()) {
-    issue_row<NC>(x, r0, 0);
-    issue_row<NC>(x, r0 + 1, 1);
-    issue_row<NC>(x, r0 + 2, 2);
-  }
-  for (int t = 0; t < niter; t += 6) {
-    const int r = r0 + t;
-    const uint32_t par = round & 1u;
-    fct2t_step<NC, 0, SAFE>(s, x, p, r, t + 3 < niter, par, bad);
-    fct2t_step<NC, 1, SAFE>(s, x, p, r + 1, t + 4 < niter, par, bad);
-    fct2t_step<NC, 2, SAFE>(s, x, p, r + 2, t + 5 < niter, par, bad);
-    fct2t_step<NC, 3, SAFE>(s, x, p, r + 3, t + 6 < niter, par, bad);
-    fct2t_step<NC, 4, SAFE>(s, x, p, r + 4, t + 7 < niter, par, bad);
-    fct2t_step<NC, 5, SAFE>(s, x, p, r + 5, t + 8 < niter, par, bad);
-    ++round;
-  }
-  return bad;
-}
-
-template <int NC>
-__device__ __noinline__ void march_fct2_tma_safe(const TmaCtx x, const RingPtr p, uint32_t round) {
-  march_fct2_tma_pass<NC, true>(x, p, round);
-}
-
-template <int NC>
-__device__ void march_fct2_tma(const TmaCtx& x) {
-  typedef Ring<NC> R;
-  RingPtr p;
-  const int l0 = x.lane * NC;
-  p.c = x.ring + 8 * l0;
-  p.w = x.ring + 8 * max(l0 - 1, 0);
-  p.e = x.ring + 8 * min(l0 + NC, 32 * NC - 1);
-  if (x.lane == 0) {
-#pragma unroll
-    for (int q = 0; q < R::NSLOT; ++q) mbar_init(x.bar_s + 8u * q, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint32_t round = 0;
-  const bool bad = march_fct2_tma_pass<NC, false>(x, p, round);
-  if (__any_sync(TSADVC_FULLMASK, bad)) march_fct2_tma_safe<NC>(x, p, round);
-}
+};
 
 }  // namespace tsadvc

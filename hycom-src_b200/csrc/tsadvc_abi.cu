@@ -500,7 +500,9 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   P.g.mask64 = h->static_block + 2 * h->slab;
   P.g.delt1 = p.delt1; P.g.onemm = p.onemm;
   const char* cn = getenv("HYCOM_TSADVC_NC");
-  P.nc = (aadv == 2 && !(cn && atoi(cn) == 2)) ? 1 : 2;
+  // cells per lane (tuning knobs HYCOM_TSADVC_NC / _MINB / _CHUNK_ROWS; defaults measured on
+  // B200: FCT2 1 cell per lane at 4 blocks per SM, MPDATA 2 cells per lane at 2 blocks)
+  P.nc = cn ? (atoi(cn) == 2 ? 2 : 1) : (aadv == 1 ? 2 : 1);
   const char* cb = getenv("HYCOM_TSADVC_MINB");
   P.minb = cb ? atoi(cb) : 3;
   const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
@@ -546,15 +548,8 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     else { CU(h, cudaEventCreate(&ev.first)); CU(h, cudaEventCreate(&ev.second)); }
     CU(h, cudaEventRecord(ev.first, h->stream));
   }
-  const char* ct = getenv("HYCOM_TSADVC_TMA");
-  const bool use_tma = (aadv == 2) && !(ct && atoi(ct) == 0);
-  if (use_tma) {
-    // raw rows staged through shared memory by the TMA engine (march_fct2_tma.cuh)
-    if (!cb) P.minb = (P.nc == 2) ? 2 : 3;
-    rc = launch_march_tma(P, h->stream);
-  } else {
-    rc = launch_march(aadv, P, h->stream);
-  }
+  if (!cb) P.minb = (P.nc == 2) ? 2 : 3;
+  rc = launch_march_tma(aadv, P, h->stream);
   h->launches += 1;
   if (h->timing) {
     CU(h, cudaEventRecord(ev.second, h->stream));

@@ -37,10 +37,8 @@ struct MarchParams {
 };
 
 // scheme: 1 = MPDATA, 2 = FCT2 (advtyp of blkdat.input, mod_tsadvc.F90:87-90)
-int launch_march(int scheme, const MarchParams& P, cudaStream_t stream);
 
-// TMA-staged FCT2 launch (tsadvc_kernels.cu, march_fct2_tma.cuh)
-int launch_march_tma(const MarchParams& P, cudaStream_t stream);
+int launch_march_tma(int scheme, const MarchParams& P, cudaStream_t stream);
 
 // aux kernels (halo.cu)
 int launch_halo_local(double* base, long slab, int nslab, int pitch, int nbdy, int ii, int jj,
