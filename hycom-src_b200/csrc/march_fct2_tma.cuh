@@ -1,5 +1,8 @@
-// advem_fct2 (mod_tsadvc.F90:645-997) + tsadvc prolog (:1905-1942) as a scheme of the
-// TMA-staged march (march_tma_common.cuh).
+// advem_fct2 (mod_tsadvc.F90:645-997) and advem_fct4 (:1370-1706) + tsadvc prolog
+// (:1905-1942) as a scheme of the TMA-staged march (march_tma_common.cuh).  The two differ
+// in the high-order flux of S3 only: fct4 uses the 4-point formula 7/12, -1/12 (:1534-1554)
+// unless a neighbouring face is land, and therefore forms fax,fay one row later (row r-1,
+// when fldc of row r is staged).
 //
 //   stage A, row r   : S1 upwind fluxes flx,fly (:692-707) and S3 antidiffusive fluxes
 //                      fax,fay (:823-830); coast zeroing (:738-758, :835-855) by select
@@ -35,10 +38,11 @@ struct Fct2T {                                       // computed intermediates o
   double RP[2][NC], RM[2][NC];                       //                                   [row&1]
   double QMX[2][NC], QMN[2][NC];                     // fmx, fmn of S4                    [row&1]
   double DFAXL[2][NC], FAYL[2][NC];                  // limited fluxes                    [row&1]
+  double FLXR[2][NC];                                // flx itself (fct4 only)            [row&1]
   unsigned m1, m2, m3;                               // masks of rows r-1, r-2, r-3
 };
 
-template <int NC>
+template <int NC, int ORDER = 2>
 struct Fct2Scheme {
   typedef Fct2T<NC> State;
   static constexpr bool kNeedC = true;
@@ -55,6 +59,7 @@ struct Fct2Scheme {
       for (int q = 0; q < 2; ++q) {
         s.DFLX[q][c] = 0.0; s.FLY[q][c] = 0.0; s.RP[q][c] = 0.0; s.RM[q][c] = 0.0;
         s.QMX[q][c] = 0.0; s.QMN[q][c] = 0.0; s.DFAXL[q][c] = 0.0; s.FAYL[q][c] = 0.0;
+        s.FLXR[q][c] = 0.0;
       }
     }
     s.m1 = s.m2 = s.m3 = 0u;
@@ -92,13 +97,51 @@ struct Fct2Scheme {
       const double qy = signbit_set(V) ? F : F1[c];               // :700-704
       flx[c] = (mc & M_IU) ? U * qx : 0.0;
       const double fly = (mc & M_IV) ? V * qy : 0.0;
-      const double fhx = U * 0.5 * (C + CW[c]);                   // :824
-      const double fhy = V * 0.5 * (C + C1[c]);                   // :828
-      s.FAX[a3][c] = (mc & M_IU) ? fhx - flx[c] : 0.0;
-      s.FAY[a3][c] = (mc & M_IV) ? fhy - fly : 0.0;
+      if (ORDER == 2) {
+        const double fhx = U * 0.5 * (C + CW[c]);                   // :824
+        const double fhy = V * 0.5 * (C + C1[c]);                   // :828
+        s.FAX[a3][c] = (mc & M_IU) ? fhx - flx[c] : 0.0;
+        s.FAY[a3][c] = (mc & M_IV) ? fhy - fly : 0.0;
+      } else {
+        s.FLXR[p2][c] = flx[c];
+      }
       s.FLY[p2][c] = fly;
     }
     ediff<NC>(flx, s.DFLX[p2]);
+  }
+  if (ORDER == 4) {
+    // ---- S3 of advem_fct4 for row r-1 (:1528-1558): fldc of rows r-3..r and columns i-2..i+1
+    const unsigned m1 = s.m1;
+    double Cc[NC], Cw[NC], Cww[NC], Ce[NC], Cn[NC], Cs[NC], Css[NC], U1[NC], V1[NC];
+    ld_own<NC, R::C>(p, s1, Cc);
+    ld_own<NC, R::C>(p, s0, Cn);
+    ld_own<NC, R::C>(p, s2, Cs);
+    ld_own<NC, R::C>(p, s3, Css);
+    ld_own<NC, R::U>(p, s1, U1);
+    ld_own<NC, R::V>(p, s1, V1);
+    ld_west<NC, R::C>(p, s1, Cc, Cw);
+    ld_east<NC, R::C>(p, s1, Cc, Ce);
+    unsigned mw[NC], me[NC];
+    Cww[0] = ld_at<NC, R::C>(p.w2, s1);
+    mw[0] = ld_mask_at<NC>(p.w, s1);
+    me[NC - 1] = ld_mask_at<NC>(p.e, s1);
+    if (NC == 2) { Cww[NC - 1] = Cw[0]; mw[NC - 1] = mk(m1, 0); me[0] = mk(m1, 1); }
+    const double ft14 = 7.0 / 12.0, ft24 = -1.0 / 12.0;              // :1398-1399
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const unsigned mc = mk(m1, c);
+      const double U = U1[c], V = V1[c];
+      const bool lowx = !(mw[c] & M_IU) || !(me[c] & M_IU);         // iu(i-1)==0 .or. iu(i+1)==0
+      const bool lowy = !(mk(s.m2, c) & M_IV) || !(mk(m0, c) & M_IV);
+      const double fhx2 = U * 0.5 * (Cc[c] + Cw[c]);
+      const double fhx4 = U * (ft14 * (Cc[c] + Cw[c]) + ft24 * (Ce[c] + Cww[c]));
+      const double fhy2 = V * 0.5 * (Cc[c] + Cs[c]);
+      const double fhy4 = V * (ft14 * (Cc[c] + Cs[c]) + ft24 * (Cn[c] + Css[c]));
+      const double fhx = lowx ? fhx2 : fhx4;
+      const double fhy = lowy ? fhy2 : fhy4;
+      s.FAX[b3][c] = (mc & M_IU) ? fhx - s.FLXR[q2][c] : 0.0;
+      s.FAY[b3][c] = (mc & M_IV) ? fhy - s.FLY[q2][c] : 0.0;
+    }
   }
 
   // ---- stage B: row r-1

@@ -117,6 +117,7 @@ __device__ __forceinline__ void issue_row(const TmaCtx& x, int r, int slot) {
 // neighbour of the last own column (clamped inside the row: the clamped lanes are apron)
 struct RingPtr {
   const unsigned char *c, *w, *e;
+  const unsigned char* w2;   // two columns west of the first own column (advem_fct4)
 };
 
 template <int NC, int ARR>
@@ -143,6 +144,17 @@ __device__ __forceinline__ void ld_east(const RingPtr& p, int slot, const double
   typedef Ring<NC> R;
   e[NC - 1] = *reinterpret_cast<const double*>(p.e + slot * R::SLOT + ARR * R::RB);
   if (NC == 2) e[0] = own[NC - 1];
+}
+// value of array ARR / mask byte at the column a per-lane pointer (p.w, p.e, p.w2) addresses
+template <int NC, int ARR>
+__device__ __forceinline__ double ld_at(const unsigned char* q, int slot) {
+  typedef Ring<NC> R;
+  return *reinterpret_cast<const double*>(q + slot * R::SLOT + ARR * R::RB);
+}
+template <int NC>
+__device__ __forceinline__ unsigned ld_mask_at(const unsigned char* q, int slot) {
+  typedef Ring<NC> R;
+  return *reinterpret_cast<const unsigned*>(q + slot * R::SLOT + R::MSK * R::RB);
 }
 template <int NC>
 __device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, int slot) {
@@ -213,6 +225,7 @@ __device__ void march_tma(const TmaCtx& x) {
   p.c = x.ring + 8 * l0;
   p.w = x.ring + 8 * max(l0 - 1, 0);
   p.e = x.ring + 8 * min(l0 + NC, 32 * NC - 1);
+  p.w2 = x.ring + 8 * max(l0 - 2, 0);
   if (x.lane == 0) {
 #pragma unroll
     for (int q = 0; q < R::NSLOT; ++q) mbar_init(x.bar_s + 8u * q, 1);

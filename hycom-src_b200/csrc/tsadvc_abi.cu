@@ -153,20 +153,33 @@ __global__ void k_minmax_init(double* mm, int kk) {
   }
 }
 
-__global__ void k_saln_minmax(const double* __restrict__ saln, const double* __restrict__ dp,
-                              const uint8_t* __restrict__ mask, long slab, int pitch, int nrows,
-                              double onemm, double* mm, int kk) {
+// two cells per thread (16-byte loads), 8 independent loads in flight per thread
+__global__ void __launch_bounds__(256) k_saln_minmax(const double* __restrict__ saln,
+                                                      const double* __restrict__ dp,
+                                                      const uint8_t* __restrict__ mask, long slab,
+                                                      double onemm, double* mm, int kk) {
   const int k = blockIdx.y;
-  const double* s = saln + slab * k;
-  const double* d = dp + slab * k;
+  const double2* s = reinterpret_cast<const double2*>(saln + slab * k);
+  const double2* d = reinterpret_cast<const double2*>(dp + slab * k);
+  const uchar2* mk2 = reinterpret_cast<const uchar2*>(mask);
   double lo = 999., hi = -999.;
-  const long n = (long)pitch * nrows;
-  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n;
-       q += (long)gridDim.x * blockDim.x) {
-    if ((mask[q] & M_OUT) && d[q] > onemm) {
-      const double v = s[q];
-      lo = lo < v ? lo : v;
-      hi = hi > v ? hi : v;
+  const long n2 = slab / 2;   // pitch is even
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long q0 = (long)blockIdx.x * blockDim.x + threadIdx.x; q0 < n2; q0 += 4 * stride) {
+    double2 sv[4], dv[4];
+    uchar2 mv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long q = q0 + u * stride;
+      const bool ok = q < n2;
+      mv[u] = ok ? __ldg(mk2 + q) : make_uchar2(0, 0);
+      sv[u] = ok ? __ldg(s + q) : make_double2(0., 0.);
+      dv[u] = ok ? __ldg(d + q) : make_double2(0., 0.);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if ((mv[u].x & M_OUT) && dv[u].x > onemm) { lo = lo < sv[u].x ? lo : sv[u].x; hi = hi > sv[u].x ? hi : sv[u].x; }
+      if ((mv[u].y & M_OUT) && dv[u].y > onemm) { lo = lo < sv[u].y ? lo : sv[u].y; hi = hi > sv[u].y ? hi : sv[u].y; }
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -423,8 +436,6 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     return fail(h, HYCOM_TSADVC_ENBDY,
                 "error: nbdy (dimensions.h) must be at least%3d for the advection scheme indicated by advtyp",
                 mbdy);
-  if (aadv == 0 || aadv == 4)
-    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "advtyp=%d (PCM/FCT4) is not built yet", p.advtyp);
   if (p.btrmas) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "btrmas (advem_fct2c) is not built yet");
   if (p.isopyc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc (k=1 flux smoothing) is not built yet");
   if (p.mxlmy) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "mxlmy (q2,q2l advection) is not built yet");
@@ -502,7 +513,7 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   const char* cn = getenv("HYCOM_TSADVC_NC");
   // cells per lane (tuning knobs HYCOM_TSADVC_NC / _MINB / _CHUNK_ROWS; defaults measured on
   // B200: FCT2 1 cell per lane at 4 blocks per SM, MPDATA 2 cells per lane at 2 blocks)
-  P.nc = cn ? (atoi(cn) == 2 ? 2 : 1) : (aadv == 1 ? 2 : 1);
+  P.nc = (aadv == 0 || aadv == 4) ? 1 : cn ? (atoi(cn) == 2 ? 2 : 1) : (aadv == 1 ? 2 : 1);
   const char* cb = getenv("HYCOM_TSADVC_MINB");
   P.minb = cb ? atoi(cb) : 3;
   const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
@@ -580,9 +591,9 @@ int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
     if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
     if (!h->d_minmax && (rc = dalloc(h, (void**)&h->d_minmax, sizeof(double) * 2 * kk, false))) return rc;
     k_minmax_init<<<(kk + 127) / 128, 128, 0, h->stream>>>(h->d_minmax, kk);
-    dim3 grid(148 * 2, kk);
-    k_saln_minmax<<<grid, 256, 0, h->stream>>>(h->saln.lev[n - 1], dpn, h->mask, h->slab, h->pitch,
-                                               h->nrows, p.onemm, h->d_minmax, kk);
+    dim3 grid(148, kk);
+    k_saln_minmax<<<grid, 256, 0, h->stream>>>(h->saln.lev[n - 1], dpn, h->mask, h->slab, p.onemm,
+                                               h->d_minmax, kk);
     h->launches += 2;
     std::vector<double> mm(2 * kk);
     CU(h, cudaMemcpyAsync(mm.data(), h->d_minmax, sizeof(double) * 2 * kk, cudaMemcpyDeviceToHost, h->stream));

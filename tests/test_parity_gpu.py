@@ -54,6 +54,10 @@ CASES = [
     (58, 31, 4, 0, 1, 2, {"nhybrd": 2}),         # temp only in the top nhybrd layers
     (70, 45, 3, 0, 0, 2, {"advflg": 1}),         # advect th3d & S
     (70, 45, 3, 0, 0, 1, {"advflg": 1}),
+    (150, 150, 5, 0, 1, 4, {}),                  # advem_fct4 (4th-order high-order flux)
+    (97, 83, 3, 3, 0, 4, {}),                    # fct4, doubly periodic
+    (150, 150, 5, 0, 1, 0, {}),                  # advem_pcm (donor cell), halo width 2
+    (64, 90, 2, 1, 0, 0, {}),
 ]
 
 
@@ -258,7 +262,8 @@ def _exchange_in_process(tss, m, n):
         be = xc.DeviceHaloBackend(ts)
         nbr = xc.neighbors(ts.cb.geom)
         cnt = be.counts(m, n)
-        assert cnt == xc.halo_counts(ts.cb.geom, (2 * (2 + ts.cb.ntracr) + 2) * ts.cb.geom.kdm)
+        mb = 2 if ts.cb.advtyp == 0 else 5      # mbdy_advtyp (mod_tsadvc.F90:24-29)
+        assert cnt == xc.halo_counts(ts.cb.geom, (2 * (2 + ts.cb.ntracr) + 2) * ts.cb.geom.kdm, mb, mb)
         send = [be.alloc(c) if nbr[d] >= 0 else None for d, c in enumerate(cnt)]
         be.pack(m, n, send)
         sends.append(send)
@@ -278,6 +283,8 @@ TILINGS = [
     (131, 97, 2, 2, 2, 3, 0, 2, True),     # doubly periodic, ragged splits
     (120, 90, 2, 1, 2, 1, 1, 1, True),     # MPDATA, periodic in i wrapping onto the tile itself
     (300, 64, 2, 2, 1, 0, 0, 2, True),     # tiles wide enough to have interior strips
+    (150, 150, 2, 2, 2, 0, 0, 4, True),    # advem_fct4 on 2x2 tiles
+    (150, 150, 2, 2, 2, 0, 1, 0, True),    # advem_pcm on 2x2 tiles (halo width 2)
 ]
 
 
