@@ -26,6 +26,7 @@ c
         integer(c_int32_t) :: advtyp,advflg,btrmas,nhybrd,hybrid,
      &                        isopyc,mxlmy, nstep,diagno
         integer(c_int32_t) :: trcflg(mxtrcr_c)
+        integer(c_int32_t) :: sigver
         real(c_double)     :: delt1,temdf2,temdfc,thbase,onemm
       end type
 c
@@ -52,6 +53,12 @@ c
           type(tsadvc_params), intent(in) :: prm
           type(c_ptr), value :: temp,saln,th3d,tracer,dp,uflx,vflx,
      &                          oneta,xmin,xmax
+        end function
+        integer(c_int) function hycom_tsadvc_upload(h,field,ktr,
+     &           tlev,k0,nk,host) bind(c,name='hycom_tsadvc_upload')
+          import
+          type(c_ptr), value        :: h, host
+          integer(c_int32_t), value :: field,ktr,tlev,k0,nk
         end function
         function hycom_tsadvc_last_error(h)
      &           bind(c,name='hycom_tsadvc_last_error')
@@ -95,6 +102,12 @@ c ---   allocation of the module scratch in the reference advem)
      &         c_loc(aspux),c_loc(aspvy),c_loc(ip),c_loc(iu),c_loc(iv))
         if (rc.ne.0) call b200_stop(rc)
         allocate( xmin(kdm),xmax(kdm) )
+c ---   theta (isopycnic target densities) is constant in time and only
+c ---   read by the diffusion part in exactly-isopycnal layers (k>nhybrd)
+        if     (temdf2.gt.0.0 .and. nhybrd.lt.kdm) then
+          rc = hycom_tsadvc_upload(handle,8,0,1,1,kdm,c_loc(theta))
+          if (rc.ne.0) call b200_stop(rc)
+        endif
       endif
 c
       p%advtyp=advtyp; p%advflg=advflg
@@ -108,6 +121,7 @@ c
       enddo
       p%delt1=delt1; p%temdf2=temdf2; p%temdfc=temdfc
       p%thbase=thbase; p%onemm=onemm
+      p%sigver=sigver     ! stmt_fns.h: the EOS this executable was built with
 c
 c --- multi-tile host-array mode: keep the reference's xctilr calls on the
 c --- HOST arrays here (halo width 5 of temp,saln,tracer both slots, uflx,

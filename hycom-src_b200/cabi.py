@@ -13,7 +13,7 @@ _LIB_NAME = "libhycom_tsadvc_b200.so"
 
 MXTRCR = 16
 
-F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER = range(7)
+F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER, F_ONETA, F_THETA = range(9)
 S_SCPX, S_SCPY, S_SCUX, S_SCUY, S_SCVX, S_SCVY, S_ONETA = range(10, 17)
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENBDY, EADVTYP, ENOMEM = range(7)
@@ -42,7 +42,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "advtyp", "advflg", "btrmas", "nhybrd", "hybrid", "isopyc", "mxlmy",
         "nstep", "diagno")] + [
-        ("trcflg", C.c_int32 * MXTRCR),
+        ("trcflg", C.c_int32 * MXTRCR), ("sigver", C.c_int32),
         ("delt1", C.c_double), ("temdf2", C.c_double), ("temdfc", C.c_double),
         ("thbase", C.c_double), ("onemm", C.c_double)]
 
@@ -91,6 +91,10 @@ PROTOTYPES = {
                                            C.POINTER(_vp * 8), _vp]),
     "hycom_tsadvc_step_device_part": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params),
                                                 C.c_int32, _vp, _vp]),
+    "hycom_tsadvc_diff_halo_counts": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(C.c_int64 * 8)]),
+    "hycom_tsadvc_diff_halo_pack": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(_vp * 8), _vp]),
+    "hycom_tsadvc_diff_halo_unpack": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(_vp * 8), _vp]),
+    "hycom_tsadvc_diffuse_device": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params)]),
     "hycom_tsadvc_set_timing": (C.c_int, [_vp, C.c_int32]),
     "hycom_tsadvc_get_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "hycom_synth_sea_mask": (C.c_int, [C.POINTER(SynthCfg), _vp]),

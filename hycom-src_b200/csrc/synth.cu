@@ -141,13 +141,15 @@ int hycom_tsadvc_synth_fill(hycom_tsadvc_handle* h, const hycom_synth_cfg* cfg, 
   if (!h || !cfg || !h->d_sea) return HYCOM_TSADVC_EINVAL;
   void* base;
   int64_t pitch;
-  int rc = hycom_tsadvc_device_slab(h, field, ktr, tlev, 1, &base, &pitch);
+  // the generator's oneta id (HYCOM_SYNTH_ONETA) fills the one-slab-per-slot oneta mirror
+  const bool is_oneta = field == HYCOM_SYNTH_ONETA;
+  int rc = hycom_tsadvc_device_slab(h, is_oneta ? HYCOM_F_ONETA : field, ktr, tlev, 1, &base, &pitch);
   if (rc) return rc;
   const synth::Cfg c = to_cfg(*cfg);
   synth::Tile t;
   t.idm = h->d.idm; t.jdm = h->d.jdm; t.nbdy = h->d.nbdy; t.ii = h->d.ii; t.jj = h->d.jj;
   t.i0 = h->d.i0; t.j0 = h->d.j0; t.pad = 0;
-  k_synth_fill<<<148 * 8, 256, 0, h->stream>>>(c, t, h->d_sea, field, ktr, lev, 1, h->d.kdm,
+  k_synth_fill<<<148 * 8, 256, 0, h->stream>>>(c, t, h->d_sea, field, ktr, lev, 1, is_oneta ? 1 : h->d.kdm,
                                                 halo_mode, fill, (double*)base, (int)pitch, h->slab);
   h->launches += 1;
   if (cudaGetLastError() != cudaSuccess) return HYCOM_TSADVC_ECUDA;

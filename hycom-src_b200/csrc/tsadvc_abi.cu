@@ -77,10 +77,14 @@ Mirror* mirror_of(hycom_tsadvc_handle* h, int field, int ktr) {
     case HYCOM_F_TRACER:
       if (ktr >= 1 && ktr <= h->d.ntracr) return &h->tracer[ktr - 1];
       return nullptr;
+    case HYCOM_F_ONETA: return &h->oneta;
+    case HYCOM_F_THETA: return &h->theta;
   }
   return nullptr;
 }
-bool is3d(int field) { return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX; }
+bool is3d(int field) { return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX || field == HYCOM_F_THETA; }
+// slabs per time slot of a mirror
+int nlayers_of(const hycom_tsadvc_handle* h, int field) { return field == HYCOM_F_ONETA ? 1 : h->d.kdm; }
 
 // device pointer of slot tlev (1,2) of a mirror, allocated on first use
 int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
@@ -98,7 +102,7 @@ int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
       h->vflx.lev[0] = h->flux_block + 2 * K;
       h->dp.lev[1] = h->flux_block + 3 * K;
     } else {
-      int rc = dalloc_field(h, &mi->lev[s], (size_t)h->slab * h->d.kdm);
+      int rc = dalloc_field(h, &mi->lev[s], (size_t)h->slab * nlayers_of(h, field));
       if (rc) return rc;
     }
   }
@@ -352,8 +356,9 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const do
 int hycom_tsadvc_upload(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
                         int32_t k0, int32_t nk, const double* host) {
   if (!h || !host) return fail(h, HYCOM_TSADVC_EINVAL, "upload: null argument");
-  if (k0 < 1 || nk < 1 || k0 + nk - 1 > h->d.kdm)
-    return fail(h, HYCOM_TSADVC_EINVAL, "upload: layers %d..%d out of 1..%d", k0, k0 + nk - 1, h->d.kdm);
+  if (k0 < 1 || nk < 1 || k0 + nk - 1 > nlayers_of(h, field))
+    return fail(h, HYCOM_TSADVC_EINVAL, "upload: layers %d..%d out of 1..%d", k0, k0 + nk - 1,
+                nlayers_of(h, field));
   double* base;
   int rc = slot(h, field, ktr, tlev, &base);
   if (rc) return rc;
@@ -366,8 +371,9 @@ int hycom_tsadvc_upload(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int3
 int hycom_tsadvc_download(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
                           int32_t k0, int32_t nk, double* host) {
   if (!h || !host) return fail(h, HYCOM_TSADVC_EINVAL, "download: null argument");
-  if (k0 < 1 || nk < 1 || k0 + nk - 1 > h->d.kdm)
-    return fail(h, HYCOM_TSADVC_EINVAL, "download: layers %d..%d out of 1..%d", k0, k0 + nk - 1, h->d.kdm);
+  if (k0 < 1 || nk < 1 || k0 + nk - 1 > nlayers_of(h, field))
+    return fail(h, HYCOM_TSADVC_EINVAL, "download: layers %d..%d out of 1..%d", k0, k0 + nk - 1,
+                nlayers_of(h, field));
   double* base;
   int rc = slot(h, field, ktr, tlev, &base);
   if (rc) return rc;
@@ -381,7 +387,7 @@ int hycom_tsadvc_download(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, in
 int hycom_tsadvc_device_slab(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
                              int32_t k, void** dev_ptr, int64_t* pitch) {
   if (!h || !dev_ptr) return fail(h, HYCOM_TSADVC_EINVAL, "device_slab: null argument");
-  if (k < 1 || k > h->d.kdm) return fail(h, HYCOM_TSADVC_EINVAL, "device_slab: bad layer %d", k);
+  if (k < 1 || k > nlayers_of(h, field)) return fail(h, HYCOM_TSADVC_EINVAL, "device_slab: bad layer %d", k);
   double* base;
   int rc = slot(h, field, ktr, tlev, &base);
   if (rc) return rc;
@@ -401,10 +407,11 @@ int hycom_tsadvc_halo_local(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, 
     double* base;
     int rc = slot(h, field, ktr, t, &base);
     if (rc) return rc;
-    rc = launch_halo_local(base, h->slab, h->d.kdm, h->pitch, h->d.nbdy, h->d.ii, h->d.jj, mh, nh,
+    const int nl = nlayers_of(h, field);
+    rc = launch_halo_local(base, h->slab, nl, h->pitch, h->d.nbdy, h->d.ii, h->d.jj, mh, nh,
                            per_i, per_j, h->stream);
     if (!rc)
-      rc = launch_halo_outer(base, h->slab, h->d.kdm, h->pitch, h->nrows, h->d.nbdy, h->d.ii, h->d.jj,
+      rc = launch_halo_outer(base, h->slab, nl, h->pitch, h->nrows, h->d.nbdy, h->d.ii, h->d.jj,
                              mh, nh, h->stream);
     h->launches += 3;
     if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s",
@@ -439,7 +446,12 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   if (p.btrmas) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "btrmas (advem_fct2c) is not built yet");
   if (p.isopyc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc (k=1 flux smoothing) is not built yet");
   if (p.mxlmy) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "mxlmy (q2,q2l advection) is not built yet");
-  if (p.temdf2 > 0.0) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "temdf2>0 (tsdff_1x/2x) is not built yet");
+  if (p.temdf2 > 0.0) {
+    if (p.sigver < 1 || p.sigver > 8)
+      return fail(h, HYCOM_TSADVC_EINVAL, "temdf2>0 needs the equation of state: sigver=%d not in 1..8", p.sigver);
+    if (!h->scuy || !h->scvx || !h->aspux || !h->aspvy)
+      return fail(h, HYCOM_TSADVC_EINVAL, "temdf2>0 needs scuy, scvx, aspux, aspvy (set_static)");
+  }
   const int kk = h->d.kdm;
   const int nhyb = p.nhybrd < 0 ? 0 : (p.nhybrd > kk ? kk : p.nhybrd);
   adv.clear();
@@ -604,6 +616,72 @@ int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
   return 0;
 }
 
+
+// the arrays of the second exchange (mod_tsadvc.F90:2140-2151): saln, temp, th3d, tracers of
+// slot n, halo width mdf = 2
+int diff_halo_arrays(hycom_tsadvc_handle* h, int n, HaloArrays& a) {
+  memset(&a, 0, sizeof a);
+  int rc;
+  if ((rc = slot(h, HYCOM_F_SALN, 0, n, &a.base[a.narr++]))) return rc;
+  if ((rc = slot(h, HYCOM_F_TEMP, 0, n, &a.base[a.narr++]))) return rc;
+  if ((rc = slot(h, HYCOM_F_TH3D, 0, n, &a.base[a.narr++]))) return rc;
+  for (int t = 1; t <= h->d.ntracr; ++t)
+    if ((rc = slot(h, HYCOM_F_TRACER, t, n, &a.base[a.narr++]))) return rc;
+  a.kk = h->d.kdm; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+  a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 2; a.nh = 2;
+  return 0;
+}
+
+// :2153-2229 on the device mirrors: one launch for T/S/th3d + equation of state, one for the
+// tracers; slot n moves to the ping-pong buffers
+int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p) {
+  const int kk = h->d.kdm;
+  int rc;
+  DiffParams D;
+  memset(&D, 0, sizeof D);
+  double *dpn, *on;
+  if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
+  if ((rc = slot(h, HYCOM_F_ONETA, 0, n, &on))) return rc;
+  const int nhyb = p.nhybrd < 0 ? 0 : (p.nhybrd > kk ? kk : p.nhybrd);
+  const bool need_theta = nhyb < kk && !(kk == 1 && p.isopyc);
+  if (need_theta && !h->theta.lev[0])
+    return fail(h, HYCOM_TSADVC_EINVAL, "temdf2>0 with nhybrd<kdm reads theta: upload HYCOM_F_THETA first");
+  D.dp = dpn; D.oneta = on; D.theta = h->theta.lev[0];
+  D.mask = h->mask; D.scp2 = h->scp2; D.aspux = h->aspux; D.aspvy = h->aspvy;
+  D.scuy = h->scuy; D.scvx = h->scvx;
+  D.slab = h->slab; D.pitch = h->pitch; D.nrows = h->nrows; D.kk = kk;
+  D.nhybrd = nhyb; D.isopyc = p.isopyc; D.sigver = p.sigver;
+  D.temdf2 = p.temdf2; D.temdfc = p.temdfc; D.thbase = p.thbase; D.delt1 = p.delt1;
+  auto add = [&](int field, int ktr) -> int {
+    double *in, *out;
+    int r2 = slot(h, field, ktr, n, &in);
+    if (!r2) r2 = spare_of(h, mirror_of(h, field, ktr), &out);
+    if (r2) return r2;
+    D.f[D.nf].in = in; D.f[D.nf].out = out; ++D.nf;
+    return 0;
+  };
+  auto swap = [&](int field, int ktr) {
+    Mirror* mi = mirror_of(h, field, ktr);
+    double* t = mi->lev[n - 1]; mi->lev[n - 1] = mi->spare; mi->spare = t;
+  };
+  D.eos = 1;
+  if ((rc = add(HYCOM_F_TEMP, 0)) || (rc = add(HYCOM_F_SALN, 0)) || (rc = add(HYCOM_F_TH3D, 0))) return rc;
+  rc = launch_tsdff(D, h->stream);
+  h->launches += 1;
+  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  swap(HYCOM_F_TEMP, 0); swap(HYCOM_F_SALN, 0); swap(HYCOM_F_TH3D, 0);
+  if (h->d.ntracr > 0) {
+    D.eos = 0; D.nf = 0;
+    for (int t = 1; t <= h->d.ntracr; ++t)
+      if ((rc = add(HYCOM_F_TRACER, t))) return rc;
+    rc = launch_tsdff(D, h->stream);
+    h->launches += 1;
+    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    for (int t = 1; t <= h->d.ntracr; ++t) swap(HYCOM_F_TRACER, t);
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -630,7 +708,69 @@ int hycom_tsadvc_step_device_part(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   }
   if ((rc = run_march(h, m, n, *prm, adv, part))) return rc;
   if (part == HYCOM_TSADVC_PART_INTERIOR) return 0;
-  return finish_step(h, n, *prm, adv, xmin, xmax);
+  if ((rc = finish_step(h, n, *prm, adv, xmin, xmax))) return rc;
+  // :2138-2230; on a multi-tile handle the caller exchanges first (hycom_tsadvc_diff_halo_*)
+  if (prm->temdf2 > 0.0 && h->d.ipr * h->d.jpr == 1) return hycom_tsadvc_diffuse_device(h, m, n, prm);
+  return 0;
+}
+
+int hycom_tsadvc_diffuse_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                                const hycom_tsadvc_params* prm) {
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  if (!(prm->temdf2 > 0.0)) return 0;
+  CU(h, cudaSetDevice(h->d.device));
+  if (h->d.ipr * h->d.jpr == 1) {   // :2140-2151, mdf = 2
+    const int mdf = 2;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_SALN, 0, n, mdf, mdf))) return rc;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TEMP, 0, n, mdf, mdf))) return rc;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TH3D, 0, n, mdf, mdf))) return rc;
+    for (int t = 1; t <= h->d.ntracr; ++t)
+      if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TRACER, t, n, mdf, mdf))) return rc;
+  }
+  return run_diffuse(h, n, *prm);
+}
+
+int hycom_tsadvc_diff_halo_counts(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params* prm,
+                                  int64_t count[8]) {
+  if (!h || !prm || !count || n < 1 || n > 2) return fail(h, HYCOM_TSADVC_EINVAL, "diff_halo_counts: bad argument");
+  HaloArrays a;
+  int rc;
+  if ((rc = diff_halo_arrays(h, n, a))) return rc;
+  for (int d = 0; d < 8; ++d) {
+    int w, hh, c0, r0;
+    halo_region(a, d, false, w, hh, c0, r0);
+    count[d] = (int64_t)w * hh * a.narr * a.kk;
+  }
+  return 0;
+}
+
+static int diff_halo_xfer(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params* prm,
+                          double* const buf[8], void* cuda_stream, bool pack) {
+  if (!h || !prm || !buf || n < 1 || n > 2) return fail(h, HYCOM_TSADVC_EINVAL, "diff_halo: bad argument");
+  CU(h, cudaSetDevice(h->d.device));
+  HaloArrays a;
+  int rc;
+  if ((rc = diff_halo_arrays(h, n, a))) return rc;
+  HaloBufs b;
+  for (int d = 0; d < 8; ++d) { b.buf[d] = buf[d]; b.count[d] = 0; }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  rc = pack ? launch_halo_pack(a, b, st) : launch_halo_unpack(a, b, st);
+  h->launches += 1;
+  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s",
+                      cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
+int hycom_tsadvc_diff_halo_pack(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params* prm,
+                                double* const sendbuf[8], void* cuda_stream) {
+  return diff_halo_xfer(h, n, prm, sendbuf, cuda_stream, true);
+}
+
+int hycom_tsadvc_diff_halo_unpack(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params* prm,
+                                  double* const recvbuf[8], void* cuda_stream) {
+  return diff_halo_xfer(h, n, prm, recvbuf, cuda_stream, false);
 }
 
 int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
@@ -696,7 +836,6 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
                       double* temp, double* saln, double* th3d, double* tracer, const double* dp,
                       const double* uflx, const double* vflx, const double* oneta, double* xmin,
                       double* xmax) {
-  (void)oneta;  // only read when btrmas or temdf2>0 (:1804-1810, :2276), neither built yet
   if (!h || !prm) return fail(h, HYCOM_TSADVC_EINVAL, "step: null argument");
   if (m < 1 || m > 2 || n < 1 || n > 2 || m == n)
     return fail(h, HYCOM_TSADVC_EINVAL, "step: bad leapfrog slots m=%d n=%d", m, n);
@@ -719,6 +858,14 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   if ((rc = hycom_tsadvc_upload(h, HYCOM_F_DP, 0, n, 1, kk, dp + fs * kk * (n - 1)))) return rc;
   if ((rc = hycom_tsadvc_upload(h, HYCOM_F_UFLX, 0, 1, 1, kk, uflx))) return rc;
   if ((rc = hycom_tsadvc_upload(h, HYCOM_F_VFLX, 0, 1, 1, kk, vflx))) return rc;
+  const bool diffuse = prm->temdf2 > 0.0;
+  double* other = adv_th3d ? temp : th3d;   // the thermodynamic variable that is not advected
+  const int ofield = adv_th3d ? HYCOM_F_TEMP : HYCOM_F_TH3D;
+  if (diffuse) {  // onetamas(:,:,n) = oneta(:,:,n) (:1805,1808); th3d/temp(:,:,:,n) (:2143-2144)
+    if (!oneta || !other) return fail(h, HYCOM_TSADVC_EINVAL, "step: temdf2>0 needs oneta, temp and th3d");
+    if ((rc = hycom_tsadvc_upload(h, HYCOM_F_ONETA, 0, n, 1, 1, oneta + fs * (n - 1)))) return rc;
+    if ((rc = hycom_tsadvc_upload(h, ofield, 0, n, 1, kk, other + fs * kk * (n - 1)))) return rc;
+  }
   if ((rc = hycom_tsadvc_step_device(h, m, n, prm, xmin, xmax))) return rc;
   // copy back slot n of the advected fields on 1:ii,1:jj ("valid halo 0 wide", :104)
   auto back = [&](int field, int ktr, double* host_n) -> int {
@@ -739,6 +886,7 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   };
   if ((rc = back(ffield, 0, first + fs * kk * (n - 1)))) return rc;
   if ((rc = back(HYCOM_F_SALN, 0, saln + fs * kk * (n - 1)))) return rc;
+  if (diffuse && (rc = back(ofield, 0, other + fs * kk * (n - 1)))) return rc;
   for (int q = 1; q <= h->d.ntracr; ++q)
     if ((rc = back(HYCOM_F_TRACER, q, tracer + fs * kk * (2 * (size_t)(q - 1) + (n - 1))))) return rc;
   CU(h, cudaStreamSynchronize(h->stream));

@@ -28,6 +28,8 @@ struct hycom_tsadvc_handle {
   double *scp2 = nullptr, *scp2i = nullptr, *scuy = nullptr, *scvx = nullptr, *aspux = nullptr,
          *aspvy = nullptr;
   tsadvc::Mirror temp, saln, th3d, dp, uflx, vflx;
+  tsadvc::Mirror oneta;  // (:,:,2): one slab per time slot
+  tsadvc::Mirror theta;  // (:,:,kdm): lev[0] only
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
   // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)]
   double* flux_block = nullptr;

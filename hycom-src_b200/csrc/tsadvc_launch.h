@@ -89,3 +89,29 @@ int launch_halo_unpack(const HaloArrays& a, const HaloBufs& b, cudaStream_t stre
 int launch_halo_outer_multi(const HaloArrays& a, cudaStream_t stream);
 
 }  // namespace tsadvc
+
+// ---- diffusion + equation of state after advection (tsdff.cu) ---------------------------
+namespace tsadvc {
+
+struct DiffField { const double* in; double* out; };   // (:,:,1,n) and its ping-pong buffer
+
+// one launch of k_tsdff: either the T/S/th3d triple with the equation-of-state epilogue
+// (eos = 1: f[0] temp, f[1] saln, f[2] th3d; mod_tsadvc.F90:2166-2185 + :2199-2229) or nf
+// tracers (eos = 0; :2190-2198), all kk layers
+struct DiffParams {
+  DiffField f[kMaxFields];
+  int nf, eos;
+  const double* dp;      // dp(:,:,1,n)
+  const double* oneta;   // onetamas(:,:,n) = oneta(:,:,n)  (:1805,1808)
+  const double* theta;   // theta(:,:,1): read in exactly-isopycnal layers only (may be null)
+  const uint8_t* mask;
+  const double *scp2, *aspux, *aspvy, *scuy, *scvx;
+  long slab;
+  int pitch, nrows, kk;
+  int nhybrd, isopyc, sigver;
+  double temdf2, temdfc, thbase, delt1;
+};
+
+int launch_tsdff(const DiffParams& P, cudaStream_t stream);
+
+}  // namespace tsadvc

@@ -51,6 +51,7 @@ class CbArrays:
     uflx: np.ndarray = None
     vflx: np.ndarray = None
     oneta: np.ndarray = None
+    theta: np.ndarray = None   # (kdm, nrows, ncols): isopycnic target densities - thbase
     # blkdat scalars (defaults = the benchmark configuration: FCT2, T&S, hybrid)
     advtyp: int = 2
     advflg: int = 0
@@ -67,6 +68,7 @@ class CbArrays:
     temdfc: float = 1.0
     thbase: float = 34.0
     onemm: float = ONEM * 0.001
+    sigver: int = 6           # stmt_fns.h:2-22; 6 = -DEOS_SIG2 -DEOS_17T (the GLB builds)
 
     def params(self) -> Params:
         p = Params()
@@ -78,6 +80,7 @@ class CbArrays:
             p.trcflg[q] = self.trcflg[q] if q < len(self.trcflg) else 0
         p.delt1, p.temdf2, p.temdfc = self.delt1, self.temdf2, self.temdfc
         p.thbase, p.onemm = self.thbase, self.onemm
+        p.sigver = self.sigver
         return p
 
 
@@ -177,12 +180,24 @@ class Tsadvc:
         self.upload(cabi.F_DP, cb.dp[n - 1], n)
         self.upload(cabi.F_UFLX, cb.uflx, 1)
         self.upload(cabi.F_VFLX, cb.vflx, 1)
+        if cb.temdf2 > 0.0:   # operands of the diffusion part (mod_tsadvc.F90:2138-2230)
+            other, of = (cb.temp, cabi.F_TEMP) if cb.advflg else (cb.th3d, cabi.F_TH3D)
+            self.upload(of, other[n - 1], n)
+            self.upload(cabi.F_ONETA, cb.oneta[n - 1], n)
+            self.upload_theta()
+
+    def upload_theta(self):
+        """theta is constant in time: pushed once, read only in exactly-isopycnal layers"""
+        if self.cb.theta is not None:
+            self.upload(cabi.F_THETA, self.cb.theta, 1)
 
     # -- the path ---------------------------------------------------------
     def tsadvc(self, m: int, n: int):
         """tsadvc(m,n) on the host arrays of ``cb`` (copies in, computes, copies out)."""
         cb = self.cb
         p = cb.params()
+        if cb.temdf2 > 0.0:
+            self.upload_theta()
         self._ck(self.lib.hycom_tsadvc_step(
             self.h, m, n, C.byref(p), _ptr(cb.temp), _ptr(cb.saln), _ptr(cb.th3d), _ptr(cb.tracer),
             _ptr(cb.dp), _ptr(cb.uflx), _ptr(cb.vflx), _ptr(cb.oneta), _ptr(self.xmin),

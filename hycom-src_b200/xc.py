@@ -99,6 +99,24 @@ class DeviceHaloBackend:
                                                         C.c_void_p(stream) if stream else None))
 
 
+    # -- the second exchange of tsadvc (temdf2 > 0, mod_tsadvc.F90:2140-2151): slot n, width 2
+    def diff_counts(self, n):
+        cnt = (C.c_int64 * 8)()
+        p = self.ts.cb.params()
+        self.ts._ck(self.ts.lib.hycom_tsadvc_diff_halo_counts(self.ts.h, n, C.byref(p), C.byref(cnt)))
+        return [int(c) for c in cnt]
+
+    def diff_pack(self, n, send, stream=None):
+        p = self.ts.cb.params()
+        self.ts._ck(self.ts.lib.hycom_tsadvc_diff_halo_pack(self.ts.h, n, C.byref(p), C.byref(self._table(send)),
+                                                           C.c_void_p(stream) if stream else None))
+
+    def diff_unpack(self, n, recv, stream=None):
+        p = self.ts.cb.params()
+        self.ts._ck(self.ts.lib.hycom_tsadvc_diff_halo_unpack(self.ts.h, n, C.byref(p), C.byref(self._table(recv)),
+                                                             C.c_void_p(stream) if stream else None))
+
+
 class XcExchange:
     """``xctilr`` of the arrays tsadvc(m,n) exchanges (mod_tsadvc.F90:1829-1836) for one tile
     per rank of a ``torch.distributed`` group, plus the overlapped ``tsadvc_device``."""
@@ -217,6 +235,36 @@ class XcExchange:
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, xm, xx))
         if diag and (ts.cb.nstep % 3 == 0 or ts.cb.diagno):
             self.xcminmax(ts.xmin, ts.xmax)
+        if ts.cb.temdf2 > 0.0:   # mod_tsadvc.F90:2138-2230: second exchange (width 2), then tsdff + EOS
+            self.xctilr_diff(n)
+            ts._ck(ts.lib.hycom_tsadvc_diffuse_device(ts.h, m, n, C.byref(p)))
+
+    def xctilr_diff(self, n):
+        """xctilr(saln|temp|th3d|tracer(:,:,:,n), 1,kk, 2,2, halo_ps) of mod_tsadvc.F90:2140-2151"""
+        key = ("diff", n, self.ts.cb.ntracr)
+        if key not in self._bufs:
+            cnt = self.backend.diff_counts(n)
+            send = [self.backend.alloc(c) if self.nbr[d] >= 0 else None for d, c in enumerate(cnt)]
+            recv: List = [None] * 8
+            for d, c in enumerate(cnt):
+                if self.nbr[d] >= 0:
+                    recv[d] = send[OPP[d]] if self.nbr[d] == self.rank else self.backend.alloc(c)
+            self._bufs[key] = (send, recv, self.ops(send, recv))
+        send, recv, ops = self._bufs[key]
+        cs = self.comm_stream
+        if cs is not None:
+            cs.wait_stream(self._compute())
+            with self.torch.cuda.stream(cs):
+                self.backend.diff_pack(n, send, cs.cuda_stream)
+                for w in (self.dist.batch_isend_irecv(ops) if ops else []):
+                    w.wait()
+                self.backend.diff_unpack(n, recv, cs.cuda_stream)
+            self._compute().wait_stream(cs)
+        else:
+            self.backend.diff_pack(n, send)
+            for w in (self.dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+            self.backend.diff_unpack(n, recv)
 
     def xcminmax(self, xmin, xmax):
         """xcminr / xcmaxr of the per-layer salinity range (mod_tsadvc.F90:2093-2094):

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define HYCOM_TSADVC_ABI_VERSION 1
+#define HYCOM_TSADVC_ABI_VERSION 2
 #define HYCOM_TSADVC_MXTRCR 16
 
 enum {
@@ -58,7 +58,9 @@ enum {
   HYCOM_F_DP = 3,
   HYCOM_F_UFLX = 4,   /* 3-D: tlev ignored */
   HYCOM_F_VFLX = 5,   /* 3-D: tlev ignored */
-  HYCOM_F_TRACER = 6  /* with ktr = 1..ntracr */
+  HYCOM_F_TRACER = 6, /* with ktr = 1..ntracr */
+  HYCOM_F_ONETA = 7,  /* oneta(:,:,tlev): one slab per time slot (k0 = nk = 1) */
+  HYCOM_F_THETA = 8   /* theta(:,:,kdm), 3-D: tlev ignored (mod_cb_arrays.F90:81) */
 };
 
 /* mod_dimensions.F90:33,45-49 + mod_xc tile geometry (mod_xc_mp.h:2317-3288) */
@@ -82,6 +84,9 @@ typedef struct hycom_tsadvc_params {
   int32_t btrmas, nhybrd, hybrid, isopyc, mxlmy;
   int32_t nstep, diagno;
   int32_t trcflg[HYCOM_TSADVC_MXTRCR];
+  int32_t sigver;  /* stmt_fns.h:2-22: equation of state the host model was compiled with,
+                      1/2 = 7-term sigma-0/2, 3/4 = 9-term, 5/6 = 17-term, 7/8 = 12-term;
+                      read only when temdf2 > 0 (mod_tsadvc.F90:2199-2229) */
   double delt1;    /* dt2 of advem */
   double temdf2, temdfc, thbase, onemm;
 } hycom_tsadvc_params;
@@ -115,7 +120,12 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle *h, const double *scp2,
  * Copies temp/saln(/th3d/tracer) both time levels, dp(:,:,:,n), uflx, vflx to
  * the device, refreshes the halos, advects, and copies (:,:,:,n) of the advected
  * fields back on 1:ii,1:jj.  xmin/xmax (kdm reals, may be NULL) receive the
- * per-layer salinity range when mod(nstep,3)==0 or diagno (:2065-2094). */
+ * per-layer salinity range when mod(nstep,3)==0 or diagno (:2065-2094).
+ * temdf2 > 0 (:2138-2230): th3d(:,:,:,n) and oneta(:,:,n) are copied in as well, the
+ * fields are diffused (tsdff_1x/2x), the non-independent thermodynamic variable is rebuilt
+ * with the equation of state `sigver`, and temp, saln, th3d (:,:,:,n) are all copied back.
+ * theta (read in exactly-isopycnal layers, k > nhybrd) is constant in time: upload it once
+ * with hycom_tsadvc_upload(h, HYCOM_F_THETA, ...). */
 int hycom_tsadvc_step(hycom_tsadvc_handle *h, int32_t m, int32_t n,
                       const hycom_tsadvc_params *prm, double *temp,
                       double *saln, double *th3d, double *tracer,
@@ -184,6 +194,26 @@ int hycom_tsadvc_halo_unpack(hycom_tsadvc_handle *h, int32_t m, int32_t n,
 int hycom_tsadvc_step_device_part(hycom_tsadvc_handle *h, int32_t m, int32_t n,
                                   const hycom_tsadvc_params *prm, int32_t part,
                                   double *xmin, double *xmax);
+
+/* ---- diffusion part of tsadvc(m,n) (temdf2 > 0, mod_tsadvc.F90:2138-2230) ---------------
+ * On a single tile hycom_tsadvc_step_device / _part(PART_ALL|PART_FRAME) run it themselves.
+ * On a multi-tile handle the caller repeats the reference's second exchange
+ * (xctilr(saln|temp|th3d|tracer(:,:,:,n), 1,kk, 2,2, halo_ps), :2140-2151) between the
+ * advection and the diffusion: diff_halo_pack -> transport -> diff_halo_unpack ->
+ * hycom_tsadvc_diffuse_device.  A message is [array][k][row][col] over saln, temp, th3d,
+ * tracers of slot n, halo width 2; directions and NULL conventions as above. */
+int hycom_tsadvc_diff_halo_counts(hycom_tsadvc_handle *h, int32_t n,
+                                  const hycom_tsadvc_params *prm, int64_t count[8]);
+int hycom_tsadvc_diff_halo_pack(hycom_tsadvc_handle *h, int32_t n,
+                                const hycom_tsadvc_params *prm, double *const sendbuf[8],
+                                void *cuda_stream);
+int hycom_tsadvc_diff_halo_unpack(hycom_tsadvc_handle *h, int32_t n,
+                                  const hycom_tsadvc_params *prm, double *const recvbuf[8],
+                                  void *cuda_stream);
+/* tsdff_1x/2x of every layer and field + the equation-of-state sweep on the device mirrors
+ * (halos of slot n valid to width 1); a no-op returning 0 when temdf2 <= 0 */
+int hycom_tsadvc_diffuse_device(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                                const hycom_tsadvc_params *prm);
 
 /* number of kernels this library launched on the handle since creation */
 int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle *h);

@@ -232,7 +232,7 @@ def halo_single_tile(geom, a, mh, nh):
 
 
 def tsadvc(cb, m, n):
-    """tsadvc(m,n), hybrid coordinates, no diffusion (mod_tsadvc.F90:1804-2086).
+    """tsadvc(m,n), hybrid coordinates (mod_tsadvc.F90:1804-2230; diffusion when temdf2>0).
     `cb` is a product-side CbArrays of host numpy arrays; returns new slot-n fields."""
     g = cb.geom
     kk = g.kdm
@@ -272,4 +272,176 @@ def tsadvc(cb, m, n):
         for q in range(cb.ntracr):
             pd = 256.0 if (q < len(cb.trcflg) and cb.trcflg[q] == 2) else 0.0
             tracer[q, n - 1, k] = adv(tracer[q, n - 1, k], tracer[q, m - 1, k], k, pd, fco, fcn)
+    if cb.temdf2 > 0.0:
+        diffuse(cb, n, temp, saln, th3d, tracer)
     return dict(temp=temp, saln=saln, th3d=th3d, tracer=tracer)
+
+
+# ---- diffusion and equation of state (mod_tsadvc.F90:2138-2492, stmt_fns.h) ----------------
+
+_C79 = {  # stmt_fns.h:53-61, :65-73, :86-96, :100-110
+    1: (-1.36471E-01, 4.68181E-02, 8.07004E-01, -7.45353E-03, -2.94418E-03, 3.43570E-05, 3.48658E-05, 0.0, 0.0),
+    2: (9.77093E+00, -2.26493E-02, 7.89879E-01, -6.43205E-03, -2.62983E-03, 2.75835E-05, 3.15235E-05, 0.0, 0.0),
+    3: (-4.311829E-02, 5.429948E-02, 8.011774E-01, -7.641336E-03, -3.258442E-03, 3.757643E-05, 3.630361E-05,
+        8.675546E-05, 3.995086E-06),
+    4: (9.903308E+00, -1.618075E-02, 7.819166E-01, -6.593939E-03, -2.896464E-03, 3.038697E-05, 3.266933E-05,
+        1.180109E-04, 3.399511E-06),
+}
+_C12 = dict(  # stmt_fns.h:129-149
+    c001=-1.4627567840659594e-01, c002=6.4247392832635697e-02, c003=8.1213979591704621e-01,
+    c004=-8.1321489441909698e-03, c005=4.5199845091090296e-03, c006=4.6347888132781394e-04,
+    c007=5.0879498675039621e-03, c008=1.6333913018305079e-05, c009=4.3899924880543972e-06,
+    c011=1.0000000000000000e+00, c012=1.0316374535350838e-02, c013=8.9521792365142522e-04,
+    c014=-2.8438341552142710e-05, c015=-1.1887778959461776e-05, c016=-4.0163964812921489e-06,
+    c017=1.1995545126831476e-05, c018=5.5234008384648383e-08, c019=8.4310335919950873e-09)
+_C17 = dict(  # stmt_fns.h:216-242
+    c001=9.9984085444849347e+02, c002=7.3471625860981584e+00, c003=-5.3211231792841769e-02,
+    c004=3.6492439109814549e-04, c005=2.5880571023991390e+00, c006=6.7168282786692355e-03,
+    c007=1.9203202055760151e-03, c008=1.0000000000000000e+00, c009=7.2815210113327091e-03,
+    c010=-4.4787265461983921e-05, c011=3.3851002965802430e-07, c012=1.3651202389758572e-10,
+    c013=1.7632126669040377e-03, c014=8.8066583251206474e-06, c015=1.8832689434804897e-10,
+    c016=5.7463776745432097e-06, c017=1.4716275472242334e-09, c018=1.1798263740430364e-02,
+    c019=9.8920219266399117e-08, c020=4.6996642771754730e-06, c021=2.5862187075154352e-08,
+    c022=3.2921414007960662e-12, c023=6.7103246285651894e-06, c024=2.4461698007024582e-17,
+    c025=9.1534417604289062e-18)
+
+
+def _rpdb(sigma2):
+    return np.float64(2000.0e4 if sigma2 else 0.0) * np.float64(1.0e-4)
+
+
+def _c12(sigver):
+    k = _C12
+    r = _rpdb(sigver == 8)
+    return dict(k, c101=k["c001"] + r * k["c007"], c102=k["c002"] + r * k["c008"], c103=k["c003"] + r * k["c009"],
+                c111=k["c011"] + r * k["c017"], c112=k["c012"] + r * k["c018"], c113=k["c013"] + r * k["c019"])
+
+
+def sig(sigver, t, s):
+    """sig(t,s) of the equation of state `sigver` (stmt_fns.h:332, :368, :419-424, :503-509)"""
+    t = np.asarray(t, dtype=np.float64)
+    s = np.asarray(s, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        if sigver in (1, 2):
+            c1, c2, c3, c4, c5, c6, c7, _, _ = _C79[sigver]
+            return (c1 + c3 * s + t * (c2 + c5 * s + t * (c4 + c7 * s + c6 * t)))
+        if sigver in (3, 4):
+            c1, c2, c3, c4, c5, c6, c7, c8, c9 = _C79[sigver]
+            return (c1 + s * (c3 + s * c8) + t * (c2 + s * (c5 + s * c9) + t * (c4 + s * c7 + t * c6)))
+        if sigver in (7, 8):
+            k = _c12(sigver)
+            n = k["c101"] + (k["c102"] + k["c004"] * t + k["c005"] * s) * t + (k["c103"] + k["c006"] * s) * s
+            d = k["c111"] + (k["c112"] + k["c014"] * t + k["c015"] * s) * t + (k["c113"] + k["c016"] * s) * s
+            return n * (1.0 / d)
+        k = _C17
+        r = _rpdb(sigver == 6)
+        c101 = k["c001"] + (k["c018"] - k["c021"] * r) * r
+        c103 = k["c003"] + (k["c019"] - k["c022"] * r) * r
+        c105 = k["c005"] + k["c020"] * r
+        c108 = k["c008"] + k["c023"] * r
+        c109 = k["c009"] - k["c025"] * (r * r * r)
+        c111 = k["c011"] - k["c024"] * (r * r)
+        n = c101 + t * (k["c002"] + t * (c103 + t * k["c004"])) + s * (c105 - t * k["c006"] + s * k["c007"])
+        d = (c108 + t * (c109 + t * (k["c010"] + t * (c111 + t * k["c012"]))) +
+             s * (k["c013"] - t * (k["c014"] + t * t * k["c015"]) +
+                  np.sqrt(_fmax(0.0, s)) * (k["c016"] + t * t * k["c017"])))
+        return n * (1.0 / d) - 1000.0
+
+
+def tofsig(sigver, r, s):
+    """tofsig(r,s) (stmt_fns.h:308-323, :349-379, :441-449; 99.0 for the 17-term fit, :533)"""
+    r = np.asarray(r, dtype=np.float64)
+    s = np.asarray(s, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        if sigver in (1, 2, 3, 4):
+            c1, c2, c3, c4, c5, c6, c7, c8, c9 = _C79[sigver]
+            rc6 = np.float64(1.0) / np.float64(c6)
+            if sigver <= 2:
+                a0, a1, a2 = (c1 + c3 * s - r) * rc6, (c2 + c5 * s) * rc6, (c4 + c7 * s) * rc6
+            else:
+                a0, a1, a2 = (c1 + s * (c3 + s * c8) - r) * rc6, (c2 + s * (c5 + s * c9)) * rc6, (c4 + s * c7) * rc6
+            a3rd = np.float64(1.0) / np.float64(3.0)
+            x = a3rd * a2
+            cubq = a3rd * a1 - x * x
+            cubr = a3rd * (0.5 * a1 * a2 - 1.5 * a0) - x * x * x
+            cuban = a3rd * np.arctan2(np.sqrt(_fmax(0.0, -(cubq * cubq * cubq + cubr * cubr))), cubr)
+            cubrl = np.sqrt(-cubq) * np.cos(cuban)
+            cubim = np.sqrt(-cubq) * np.sin(cuban)
+            return -cubrl + np.sqrt(np.float64(3.0)) * cubim - a3rd * a2
+        if sigver in (7, 8):
+            k = _c12(sigver)
+            a = (k["c004"] - r * k["c014"])
+            b = ((k["c102"] + k["c005"] * s) - r * (k["c112"] + k["c015"] * s))
+            c = ((k["c101"] + (k["c103"] + k["c006"] * s) * s) - r * (k["c111"] + (k["c113"] + k["c016"] * s) * s))
+            return (-b - np.sqrt(_fmax(0.0, b * b - 4.0 * a * c))) / (2.0 * a)
+        return np.full(np.broadcast(r, s).shape, 99.0)
+
+
+def _harmonc(aa, bb):
+    """mod_tsadvc.F90:1770-1771"""
+    a, b = _fmax(aa, 0.0), _fmax(bb, 0.0)
+    return 2.0 * a * b / _fmax((a + b), 2.0 * 1.0e-20)
+
+
+def tsdff(geom, flds, dp_kn, oneta_n, cb, ip, iu, iv):
+    """tsdff_1x / tsdff_2x (mod_tsadvc.F90:2262-2492) for a list of fields of one layer: the
+    face fluxes as whole-array expressions (0.0 on land faces: :1812-1813, geopar.F90:826-843),
+    then the update on the sea points of 1:ii,1:jj"""
+    with np.errstate(all="ignore"):
+        h = dp_kn * oneta_n
+        fu = cb.temdf2 * cb.aspux * cb.scuy * _harmonc(_sh(h, -1, 0), h)
+        fv = cb.temdf2 * cb.aspvy * cb.scvx * _harmonc(_sh(h, 0, -1), h)
+        factor = -cb.delt1 / (cb.scp2 * _fmax(h, 1.0e-20))
+        upd = _region(geom, 0) & (ip != 0)
+        out = []
+        for f in flds:
+            ufl = np.where(iu != 0, fu * (_sh(f, -1, 0) - f), 0.0)
+            vfl = np.where(iv != 0, fv * (_sh(f, 0, -1) - f), 0.0)
+            util = ((_sh(ufl, 1, 0) - ufl) + (_sh(vfl, 0, 1) - vfl)) * factor
+            out.append(np.where(upd, f + util, f))
+        return out
+
+
+def diffuse(cb, n, temp, saln, th3d, tracer):
+    """mod_tsadvc.F90:2138-2230 on slot n of the (already advected) fields, in place"""
+    g = cb.geom
+    kk = g.kdm
+    nhyb = kk if cb.nhybrd < 0 else cb.nhybrd
+    ip, iu, iv = cb.ip, cb.iu, cb.iv
+    for a in (saln, temp, th3d) + ((tracer,) if cb.ntracr else ()):
+        a[..., n - 1, :, :, :] = halo_single_tile(g, a[..., n - 1, :, :, :], 2, 2)
+    upd = _region(g, 0) & (ip != 0)
+    for k in range(kk):
+        ldtemp = (k + 1 <= nhyb) and cb.temdfc > 0.0
+        ldth3d = ((k + 1 <= nhyb) and cb.temdfc < 1.0) or (k == 0 and cb.isopyc)
+        dpk, on = cb.dp[n - 1, k], cb.oneta[n - 1]
+        T, S, H = temp[n - 1, k], saln[n - 1, k], th3d[n - 1, k]
+        if ldtemp and ldth3d:
+            H, T = tsdff(g, [H, T], dpk, on, cb, ip, iu, iv)
+            S, = tsdff(g, [S], dpk, on, cb, ip, iu, iv)
+        elif ldtemp:
+            T, S = tsdff(g, [T, S], dpk, on, cb, ip, iu, iv)
+        elif ldth3d:
+            H, S = tsdff(g, [H, S], dpk, on, cb, ip, iu, iv)
+        else:
+            S, = tsdff(g, [S], dpk, on, cb, ip, iu, iv)
+        if cb.ntracr:
+            new = tsdff(g, [tracer[q, n - 1, k] for q in range(cb.ntracr)], dpk, on, cb, ip, iu, iv)
+            for q in range(cb.ntracr):
+                tracer[q, n - 1, k] = new[q]
+        # :2199-2229
+        with np.errstate(all="ignore"):
+            if ldtemp and ldth3d:
+                th3d_t = sig(cb.sigver, T, S) - cb.thbase
+                Hn = (1.0 - cb.temdfc) * H + cb.temdfc * th3d_t
+                Tn = tofsig(cb.sigver, Hn + cb.thbase, S)
+            elif ldtemp:
+                Hn, Tn = sig(cb.sigver, T, S) - cb.thbase, T
+            elif ldth3d:
+                Hn, Tn = H, tofsig(cb.sigver, H + cb.thbase, S)
+            else:
+                Hn = cb.theta[k]
+                Tn = tofsig(cb.sigver, Hn + cb.thbase, S)
+        temp[n - 1, k] = np.where(upd, Tn, T)
+        th3d[n - 1, k] = np.where(upd, Hn, H)
+        saln[n - 1, k] = S

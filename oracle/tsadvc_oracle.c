@@ -97,6 +97,7 @@ orc_tile *orc_tile_create(int idm, int jdm, int kdm, int nbdy, int ii, int jj,
   t->th3d = alloc_r(P * K * 2); t->dp = alloc_r(P * K * 2);
   t->tracer = ntracr > 0 ? alloc_r(P * K * 2 * (size_t)ntracr) : NULL;
   t->uflx = alloc_r(P * K); t->vflx = alloc_r(P * K);
+  t->theta = alloc_r(P * K);
   t->oneta = alloc_r(P * 2); t->onetamas = alloc_r(P * 2);
   t->uflux = alloc_r(P); t->vflux = alloc_r(P);
   t->uflux2 = alloc_r(P); t->vflux2 = alloc_r(P);
@@ -113,6 +114,7 @@ orc_tile *orc_tile_create(int idm, int jdm, int kdm, int nbdy, int ii, int jj,
   t->isopyc = 0; t->mxlmy = 0; t->nstep = 1; t->diagno = 0;
   t->delt1 = 480.0; t->temdf2 = 0.0; t->temdfc = 1.0; t->thbase = 34.0;
   t->onemm = 9806.0 * 0.001; /* mod_cb_arrays.F90:842-857 */
+  t->sigver = 6; /* -DEOS_SIG2 -DEOS_17T, the GLB build */
   return t;
 }
 
@@ -126,7 +128,7 @@ void orc_tile_destroy(orc_tile *t) {
                   t->vflux2, t->util1, t->util2, t->fmx, t->fmn, t->flx, t->fly,
                   t->fldlo, t->fmxlo, t->fmnlo, t->fax, t->fay, t->rp, t->rm,
                   t->flxdiv, t->tx1, t->ty1, t->fldao, t->fldan, t->xmin,
-                  t->xmax};
+                  t->xmax, t->theta};
   for (size_t q = 0; q < sizeof(ptrs) / sizeof(ptrs[0]); q++) free(ptrs[q]);
   free(t);
 }
@@ -139,7 +141,7 @@ double *orc_f64(orc_tile *t, const char *name) {
   F(util1); F(util2);
   F(fmx); F(fmn); F(flx); F(fly); F(fldlo); F(fmxlo); F(fmnlo); F(fax); F(fay);
   F(rp); F(rm); F(flxdiv); F(tx1); F(ty1); F(fldao); F(fldan);
-  F(xmin); F(xmax);
+  F(xmin); F(xmax); F(theta);
 #undef F
   return NULL;
 }
@@ -155,14 +157,14 @@ int *orc_i32(orc_tile *t, const char *name) {
 int orc_set_i(orc_tile *t, const char *name, int v) {
 #define S(n) if (!strcmp(name, #n)) { t->n = v; return 0; }
   S(advtyp) S(advflg) S(btrmas) S(nhybrd) S(hybrid) S(isopyc) S(mxlmy) S(ntracr)
-  S(nstep) S(diagno) S(nreg) S(nthreads) S(kk)
+  S(nstep) S(diagno) S(nreg) S(nthreads) S(kk) S(sigver)
 #undef S
   return 1;
 }
 int orc_get_i(const orc_tile *t, const char *name) {
 #define G(n) if (!strcmp(name, #n)) return t->n;
   G(advtyp) G(advflg) G(btrmas) G(nhybrd) G(hybrid) G(isopyc) G(mxlmy) G(ntracr)
-  G(nstep) G(diagno) G(nreg) G(nthreads) G(kk) G(ms) G(xminmax_valid)
+  G(nstep) G(diagno) G(nreg) G(nthreads) G(kk) G(ms) G(xminmax_valid) G(sigver)
   G(idm) G(jdm) G(kdm) G(nbdy) G(ii) G(jj) G(i0) G(j0) G(itdm) G(jtdm)
 #undef G
   return -999999;
@@ -932,6 +934,154 @@ int orc_advem(orc_tile *t, int advtyp, double *fld, const double *fldc,
   return 0;
 }
 
+
+/* ---- equation of state: stmt_fns.h ----------------------------------------
+ * The reference picks ONE set of statement functions at compile time (EOS_SIG0/
+ * EOS_SIG2 x EOS_7T/9T/12T/17T, stmt_fns.h:2-22 "sigver").  Here sigver is a run
+ * time scalar of the tile so that one oracle build covers all eight.  Every
+ * expression keeps the Fortran grouping; x**2 = x*x, x**3 = (x*x)*x (gfortran's
+ * expansion of small integer powers); parameter expressions (rc6, c101..) are
+ * evaluated in double like gfortran's constant folder does. */
+typedef struct eos_c79 { double c1, c2, c3, c4, c5, c6, c7, c8, c9; } eos_c79;
+static eos_c79 eos_coef79(int sigver) {
+  eos_c79 c = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  switch (sigver) {
+    case 1: /* stmt_fns.h:53-61 */
+      c.c1 = -1.36471E-01; c.c2 = 4.68181E-02; c.c3 = 8.07004E-01; c.c4 = -7.45353E-03;
+      c.c5 = -2.94418E-03; c.c6 = 3.43570E-05; c.c7 = 3.48658E-05; break;
+    case 2: /* :65-73 */
+      c.c1 = 9.77093E+00; c.c2 = -2.26493E-02; c.c3 = 7.89879E-01; c.c4 = -6.43205E-03;
+      c.c5 = -2.62983E-03; c.c6 = 2.75835E-05; c.c7 = 3.15235E-05; break;
+    case 3: /* :86-96 */
+      c.c1 = -4.311829E-02; c.c2 = 5.429948E-02; c.c3 = 8.011774E-01; c.c4 = -7.641336E-03;
+      c.c5 = -3.258442E-03; c.c6 = 3.757643E-05; c.c7 = 3.630361E-05; c.c8 = 8.675546E-05;
+      c.c9 = 3.995086E-06; break;
+    case 4: /* :100-110 */
+      c.c1 = 9.903308E+00; c.c2 = -1.618075E-02; c.c3 = 7.819166E-01; c.c4 = -6.593939E-03;
+      c.c5 = -2.896464E-03; c.c6 = 3.038697E-05; c.c7 = 3.266933E-05; c.c8 = 1.180109E-04;
+      c.c9 = 3.399511E-06; break;
+  }
+  return c;
+}
+/* tofsig of the 7- and 9-term fits: root of t**3+a2*t**2+a1*t+a0=0 (:311-323, :348-361) */
+static double eos_cubic_root(double a0, double a1, double a2) {
+  const double a3rd = 1.0 / 3.0;
+  const double x = a3rd * a2;
+  const double cubq = a3rd * a1 - x * x;
+  const double cubr = a3rd * (0.5 * a1 * a2 - 1.5 * a0) - x * x * x;
+  const double cuban =
+      a3rd * atan2(sqrt(MAX2(0.0, -(cubq * cubq * cubq + cubr * cubr))), cubr);
+  const double cubrl = sqrt(-cubq) * cos(cuban);
+  const double cubim = sqrt(-cubq) * sin(cuban);
+  return -cubrl + sqrt(3.0) * cubim - a3rd * a2;
+}
+/* 12-term rational function (:129-172) */
+typedef struct eos_c12 {
+  double c101, c102, c103, c004, c005, c006, c111, c112, c113, c014, c015, c016;
+} eos_c12;
+static eos_c12 eos_coef12(int sigver) {
+  const double c001 = -1.4627567840659594e-01, c002 = 6.4247392832635697e-02,
+               c003 = 8.1213979591704621e-01, c007 = 5.0879498675039621e-03,
+               c008 = 1.6333913018305079e-05, c009 = 4.3899924880543972e-06,
+               c011 = 1.0000000000000000e+00, c012 = 1.0316374535350838e-02,
+               c013 = 8.9521792365142522e-04, c017 = 1.1995545126831476e-05,
+               c018 = 5.5234008384648383e-08, c019 = 8.4310335919950873e-09;
+  const double prs2pdb = 1.e-4, pref = sigver == 7 ? 0.0 : 2000.e4;
+  const double rpdb = pref * prs2pdb;
+  eos_c12 c;
+  c.c004 = -8.1321489441909698e-03; c.c005 = 4.5199845091090296e-03;
+  c.c006 = 4.6347888132781394e-04; c.c014 = -2.8438341552142710e-05;
+  c.c015 = -1.1887778959461776e-05; c.c016 = -4.0163964812921489e-06;
+  c.c101 = c001 + rpdb * c007; c.c102 = c002 + rpdb * c008; c.c103 = c003 + rpdb * c009;
+  c.c111 = c011 + rpdb * c017; c.c112 = c012 + rpdb * c018; c.c113 = c013 + rpdb * c019;
+  return c;
+}
+/* sig(t,s): stmt_fns.h:332 (7T), :368-369 (9T), :419-424 (12T), :503-510 (17T) */
+static double eos_sig(int sigver, double t, double s) {
+  if (sigver == 1 || sigver == 2) {
+    const eos_c79 c = eos_coef79(sigver);
+    return (c.c1 + c.c3 * s + t * (c.c2 + c.c5 * s + t * (c.c4 + c.c7 * s + c.c6 * t)));
+  }
+  if (sigver == 3 || sigver == 4) {
+    const eos_c79 c = eos_coef79(sigver);
+    return (c.c1 + s * (c.c3 + s * c.c8) +
+            t * (c.c2 + s * (c.c5 + s * c.c9) + t * (c.c4 + s * c.c7 + t * c.c6)));
+  }
+  if (sigver == 7 || sigver == 8) {
+    const eos_c12 c = eos_coef12(sigver);
+    const double sig_n = c.c101 + (c.c102 + c.c004 * t + c.c005 * s) * t + (c.c103 + c.c006 * s) * s;
+    const double sig_d = c.c111 + (c.c112 + c.c014 * t + c.c015 * s) * t + (c.c113 + c.c016 * s) * s;
+    return sig_n * (1.0 / sig_d);
+  }
+  { /* 17-term, :216-290 and :503-510 */
+    const double c001 = 9.9984085444849347e+02, c002 = 7.3471625860981584e+00,
+                 c003 = -5.3211231792841769e-02, c004 = 3.6492439109814549e-04,
+                 c005 = 2.5880571023991390e+00, c006 = 6.7168282786692355e-03,
+                 c007 = 1.9203202055760151e-03, c008 = 1.0000000000000000e+00,
+                 c009 = 7.2815210113327091e-03, c010 = -4.4787265461983921e-05,
+                 c011 = 3.3851002965802430e-07, c012 = 1.3651202389758572e-10,
+                 c013 = 1.7632126669040377e-03, c014 = 8.8066583251206474e-06,
+                 c015 = 1.8832689434804897e-10, c016 = 5.7463776745432097e-06,
+                 c017 = 1.4716275472242334e-09, c018 = 1.1798263740430364e-02,
+                 c019 = 9.8920219266399117e-08, c020 = 4.6996642771754730e-06,
+                 c021 = 2.5862187075154352e-08, c022 = 3.2921414007960662e-12,
+                 c023 = 6.7103246285651894e-06, c024 = 2.4461698007024582e-17,
+                 c025 = 9.1534417604289062e-18;
+    const double prs2pdb = 1.e-4, pref = sigver == 5 ? 0.0 : 2000.e4;
+    const double rpdb = pref * prs2pdb;
+    const double c101 = c001 + (c018 - c021 * rpdb) * rpdb, c103 = c003 + (c019 - c022 * rpdb) * rpdb,
+                 c105 = c005 + c020 * rpdb, c108 = c008 + c023 * rpdb,
+                 c109 = c009 - c025 * (rpdb * rpdb * rpdb), c111 = c011 - c024 * (rpdb * rpdb);
+    const double sig_n = c101 + t * (c002 + t * (c103 + t * c004)) + s * (c105 - t * c006 + s * c007);
+    const double sig_d = c108 + t * (c109 + t * (c010 + t * (c111 + t * c012))) +
+                         s * (c013 - t * (c014 + t * t * c015) +
+                              sqrt(MAX2(0.0, s)) * (c016 + t * t * c017));
+    return sig_n * (1.0 / sig_d) - 1000.0;
+  }
+}
+/* tofsig(r,s): :323 (7T), :379 (9T), :441-449 (12T), :533 (17T: "NOT AVAILABLE", 99.0) */
+static double eos_tofsig(int sigver, double r, double s) {
+  if (sigver == 1 || sigver == 2) {
+    const eos_c79 c = eos_coef79(sigver);
+    const double rc6 = 1.0 / c.c6;
+    return eos_cubic_root((c.c1 + c.c3 * s - r) * rc6, (c.c2 + c.c5 * s) * rc6,
+                          (c.c4 + c.c7 * s) * rc6);
+  }
+  if (sigver == 3 || sigver == 4) {
+    const eos_c79 c = eos_coef79(sigver);
+    const double rc6 = 1.0 / c.c6;
+    return eos_cubic_root((c.c1 + s * (c.c3 + s * c.c8) - r) * rc6,
+                          (c.c2 + s * (c.c5 + s * c.c9)) * rc6, (c.c4 + s * c.c7) * rc6);
+  }
+  if (sigver == 7 || sigver == 8) {
+    const eos_c12 c = eos_coef12(sigver);
+    const double a = (c.c004 - r * c.c014);
+    const double b = ((c.c102 + c.c005 * s) - r * (c.c112 + c.c015 * s));
+    const double cc = ((c.c101 + (c.c103 + c.c006 * s) * s) - r * (c.c111 + (c.c113 + c.c016 * s) * s));
+    return (-b - sqrt(MAX2(0.0, b * b - 4.0 * a * cc))) / (2.0 * a);
+  }
+  return 99.0;
+}
+double orc_sig(int sigver, double t, double s) { return eos_sig(sigver, t, s); }
+double orc_tofsig(int sigver, double r, double s) { return eos_tofsig(sigver, r, s); }
+
+/* geopar.F90:776-783, :826-843, :851, :862-879: uflux2/vflux2 (and uflux/vflux) are
+ * `hugel` everywhere, then 0.0 on every face ifp..ilp+1 of each sea segment, then halo
+ * updated: a face that borders a sea cell but is not an iu/iv point is 0.  tsdff_2x reads
+ * them there (mod_tsadvc.F90:2316-2321). */
+static void geopar_zero_coast_faces(orc_tile *t, double *fx, double *fy) {
+  const int nb = t->nbdy;
+  const int ncol = t->idm + 2 * nb, nrow = t->jdm + 2 * nb;
+  const double hugel = 1.2676506002282294e30; /* 2.0**100, mod_cb_arrays.F90 */
+  for (int r = 0; r < nrow; r++)
+    for (int c = 0; c < ncol; c++) {
+      const size_t q = (size_t)r * ncol + c;
+      const int pw = c > 0 ? t->ip[q - 1] : 0, ps = r > 0 ? t->ip[q - ncol] : 0;
+      fx[q] = (t->ip[q] != 0 || pw != 0) ? 0.0 : hugel;
+      fy[q] = (t->ip[q] != 0 || ps != 0) ? 0.0 : hugel;
+    }
+}
+
 /* ---- diffusion: mod_tsadvc.F90:2262-2492 ---------------------------------- */
 static double harmonc(double aa, double bb) { /* :1770-1771 */
   const double eps_har = 1.0e-20;
@@ -1131,10 +1281,11 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
       t->xmax[k - 1] = smax;
     }
   }
-  /* :2138-2230 diffusion (EOS back-conversion sweep :2199-2229 is not restated:
-   * it needs stmt_fns.h; temdf2>0 is accepted only for the flux/update part) */
+  /* :2138-2230 diffusion of the thermodynamic variables and the tracers */
   if (t->temdf2 > 0.0) {
     const int mdf = 2;
+    /* uflux/vflux land faces are 0 (:1812-1813); uflux2/vflux2 land faces as geopar left them */
+    geopar_zero_coast_faces(t, t->uflux2, t->vflux2);
     if (do_halo) {
       orc_xctilr(t, t->saln + P * K * (size_t)(n - 1), 1, kk, mdf, mdf);
       orc_xctilr(t, t->temp + P * K * (size_t)(n - 1), 1, kk, mdf, mdf);
@@ -1167,6 +1318,35 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
         else
           tsdff(t, k, n, tr1, NULL);
       }
+    }
+    /* :2199-2229 non-independent thermodynamic variable (margin 0) */
+    {
+      OMP_J
+      for (int j = 1; j <= jj; j++)
+        for (int k = 1; k <= kk; k++) {
+          double *temp_n = t->temp + P * ((size_t)(k - 1) + K * (size_t)(n - 1));
+          double *saln_n = t->saln + P * ((size_t)(k - 1) + K * (size_t)(n - 1));
+          double *th3d_n = t->th3d + P * ((size_t)(k - 1) + K * (size_t)(n - 1));
+          const double *theta_k = t->theta + P * (size_t)(k - 1);
+          const int ldtemp = k <= t->nhybrd && t->temdfc > 0.0;
+          const int ldth3d = (k <= t->nhybrd && t->temdfc < 1.0) || (k == 1 && t->isopyc);
+          for (int i = 1; i <= ii; i++)
+            if (SEA_P) {
+              const size_t c = IX(i, j);
+              if (ldtemp && ldth3d) {
+                const double th3d_t = eos_sig(t->sigver, temp_n[c], saln_n[c]) - t->thbase;
+                th3d_n[c] = (1.0 - t->temdfc) * th3d_n[c] + t->temdfc * th3d_t;
+                temp_n[c] = eos_tofsig(t->sigver, th3d_n[c] + t->thbase, saln_n[c]);
+              } else if (ldtemp) {
+                th3d_n[c] = eos_sig(t->sigver, temp_n[c], saln_n[c]) - t->thbase;
+              } else if (ldth3d) {
+                temp_n[c] = eos_tofsig(t->sigver, th3d_n[c] + t->thbase, saln_n[c]);
+              } else {
+                th3d_n[c] = theta_k[c];
+                temp_n[c] = eos_tofsig(t->sigver, th3d_n[c] + t->thbase, saln_n[c]);
+              }
+            }
+        }
     }
   }
   return 0;

@@ -48,6 +48,7 @@ typedef struct orc_tile {
   double *temp, *saln, *th3d, *dp;   /* (P,kdm,2) */
   double *tracer;                    /* (P,kdm,2,ntracr) */
   double *uflx, *vflx;               /* (P,kdm) */
+  double *theta;                     /* (P,kdm) isopycnic target densities, mod_cb_arrays.F90 */
   double *oneta, *onetamas;          /* (P,2) */
   double *uflux, *vflux, *uflux2, *vflux2, *util1, *util2; /* (P) */
   /* run-time scalars (blkdat) */
@@ -55,6 +56,7 @@ typedef struct orc_tile {
       diagno;
   int trcflg[ORC_MXTRCR];
   double delt1, temdf2, temdfc, thbase, onemm;
+  int sigver;                        /* stmt_fns.h:2-22: 1..8 = {7,9,17,12}-term x sigma-{0,2} */
   /* mod_tsadvc.F90:38-51 scratch */
   double *fmx, *fmn, *flx, *fly, *fldlo, *fmxlo, *fmnlo, *fax, *fay, *rp, *rm,
       *flxdiv, *tx1, *ty1, *fldao, *fldan;
@@ -105,6 +107,10 @@ int orc_advem(orc_tile *t, int advtyp, double *fld, const double *fldc,
               const double *u, const double *v, const double *fco,
               const double *fcn, double posdef, const double *scal,
               const double *scali, double dt2, int btrmas);
+
+/* stmt_fns.h: sig(t,s) and tofsig(r,s) of the equation of state `sigver` */
+double orc_sig(int sigver, double t, double s);
+double orc_tofsig(int sigver, double r, double s);
 
 /* mod_tsadvc.F90:1708-2258.  m,n are the 1-based leapfrog slots.
  * do_halo=1: call the single-tile xctilr exactly where the reference does;

@@ -36,7 +36,7 @@ class OracleTile:
             pass
 
     _SHAPES = {"temp": 4, "saln": 4, "th3d": 4, "dp": 4, "tracer": 5, "uflx": 3, "vflx": 3,
-               "oneta": -2, "onetamas": -2, "xmin": 1, "xmax": 1}
+               "oneta": -2, "onetamas": -2, "xmin": 1, "xmax": 1, "theta": 3}
 
     def f64(self, name):
         g = self.geom
@@ -102,13 +102,13 @@ class OracleTile:
     def load_cb(self, cb):
         """copy a product-side CbArrays (host numpy) into this oracle tile"""
         for name in ("scp2", "scp2i", "scuy", "scvx", "aspux", "aspvy", "temp", "saln", "th3d",
-                     "dp", "uflx", "vflx", "oneta"):
+                     "dp", "uflx", "vflx", "oneta", "theta"):
             src = getattr(cb, name)
             if src is not None:
                 self.f64(name)[...] = src
         if cb.ntracr > 0:
             self.f64("tracer")[...] = cb.tracer
-        for name in ("advtyp", "advflg", "btrmas", "hybrid", "isopyc", "mxlmy", "nstep", "diagno"):
+        for name in ("advtyp", "advflg", "btrmas", "hybrid", "isopyc", "mxlmy", "nstep", "diagno", "sigver"):
             self.set_i(name, int(getattr(cb, name)))
         self.set_i("nhybrd", cb.geom.kdm if cb.nhybrd < 0 else cb.nhybrd)
         for name in ("delt1", "temdf2", "temdfc", "thbase", "onemm"):
@@ -146,6 +146,10 @@ class Oracle:
         lib.orc_advem.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp,
                                   C.c_double, C.c_int]
         lib.orc_tsadvc.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+        lib.orc_sig.restype = C.c_double
+        lib.orc_sig.argtypes = [C.c_int, C.c_double, C.c_double]
+        lib.orc_tofsig.restype = C.c_double
+        lib.orc_tofsig.argtypes = [C.c_int, C.c_double, C.c_double]
         lib.orc_set_tap.restype = None
         lib.orc_set_tap.argtypes = [C.c_char_p, _vp]
         lib.orc_clear_taps.restype = None
@@ -154,6 +158,12 @@ class Oracle:
 
     def last_error(self):
         return self.lib.orc_last_error().decode()
+
+    def sig(self, sigver, t, s):
+        return self.lib.orc_sig(sigver, t, s)
+
+    def tofsig(self, sigver, r, s):
+        return self.lib.orc_tofsig(sigver, r, s)
 
     def tile(self, geom, ntracr=0):
         return OracleTile(self, geom, ntracr)

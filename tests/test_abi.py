@@ -36,13 +36,14 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_abi_version(pkg):
     lib = cabi.load_library()
-    assert lib.hycom_tsadvc_abi_version() == 1
+    assert lib.hycom_tsadvc_abi_version() == 2
 
 
 def test_struct_layout_matches_header(pkg):
-    # hycom_tsadvc_dims: 17 int32; params: 9 int32 + 16 int32 + pad + 5 doubles
+    # hycom_tsadvc_dims: 17 int32; params: 9 int32 + trcflg[16] + sigver + 5 doubles
     assert C.sizeof(cabi.Dims) == 17 * 4
-    assert C.sizeof(cabi.Params) == (9 + 16) * 4 + 4 + 5 * 8
+    assert C.sizeof(cabi.Params) == (9 + 16 + 1) * 4 + 5 * 8
+    assert cabi.Params.sigver.offset == 100
     assert cabi.Params.delt1.offset == 104
 
 

@@ -236,3 +236,79 @@ def test_xminmax_diagnostic(oracle):
         sel = msk & (cb.dp[1, k] > cb.onemm)
         assert ref["xmin"][k] == ref["saln"][1, k][sel].min()
         assert ref["xmax"][k] == ref["saln"][1, k][sel].max()
+
+
+# ---- diffusion + equation of state (mod_tsadvc.F90:2138-2230, stmt_fns.h) -------------------
+
+# sigma-0 / sigma-2 of standard seawater: UNESCO-83 gives sigma0(S=35,T=10) = 26.952 and
+# sigma2(35,10) = 35.80 (potential density referenced to 2000 dbar, HYCOM's sigma-2 fits agree to
+# a few 0.01); every family must reproduce them to the accuracy of its fit.  This pins the
+# transcription of the 100-odd coefficients of stmt_fns.h.
+@pytest.mark.parametrize("sigver", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_eos_known_seawater_density(oracle, sigver):
+    want = 26.952 if sigver % 2 == 1 else 35.80
+    got = oracle.sig(sigver, 10.0, 35.0)
+    assert abs(got - want) < 0.06, (sigver, got)
+    # d(sig)/dS ~ 0.78, d(sig)/dT ~ -0.17 at this point for every fit
+    ds = oracle.sig(sigver, 10.0, 36.0) - got
+    dt = oracle.sig(sigver, 11.0, 35.0) - got
+    assert 0.70 < ds < 0.85 and -0.22 < dt < -0.12, (sigver, ds, dt)
+    assert oracle.sig(sigver, 10.0, 35.0) == float(npr.sig(sigver, 10.0, 35.0))
+
+
+@pytest.mark.parametrize("sigver", [1, 2, 3, 4, 7, 8])
+def test_eos_tofsig_inverts_sig(oracle, sigver):
+    for t, s in [(-1.5, 34.5), (4.0, 34.9), (12.0, 35.5), (28.0, 36.5)]:
+        r = oracle.sig(sigver, t, s)
+        assert abs(oracle.tofsig(sigver, r, s) - t) < 1e-8, (sigver, t, s)
+        assert abs(float(npr.tofsig(sigver, r, s)) - t) < 1e-8
+    assert oracle.tofsig(5, 27.0, 35.0) == 99.0 and oracle.tofsig(6, 36.0, 35.0) == 99.0   # stmt_fns.h:533
+
+
+@pytest.mark.parametrize("sigver,temdfc,nhybrd,ntracr", [
+    (6, 1.0, -1, 0), (5, 1.0, -1, 3), (2, 1.0, -1, 0), (4, 1.0, -1, 2), (8, 1.0, -1, 0),
+    (8, 0.0, -1, 1), (7, 0.5, -1, 0), (8, 0.5, 2, 2), (2, 0.5, -1, 0), (3, 0.0, 2, 1), (1, 0.0, -1, 0)])
+def test_diffusion_c_oracle_equals_numpy_restatement(oracle, sigver, temdfc, nhybrd, ntracr):
+    cfg, sea, g, cb = util.make_diffusion_case(53, 41, 3, sigver, temdfc, ntracr=ntracr, nhybrd=nhybrd)
+    m, n = 1, 2
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    alt = npr.tsadvc(cb, m, n)
+    msk = util.interior_sea(cb)
+    # tofsig of the 7/9-term fits goes through atan2/cos/sin: glibc and numpy may differ in the last bit
+    libm = sigver <= 4 and (temdfc < 1.0 or (0 <= nhybrd < g.kdm))
+    for name in ("temp", "saln", "th3d"):
+        for k in range(g.kdm):
+            a, b = ref[name][n - 1, k], alt[name][n - 1, k]
+            if libm and name != "saln":
+                assert util.rel_err(a, b, msk) < 1e-13, (name, k)
+            else:
+                assert _sea_eq(a, b, msk), (name, k)
+    for q in range(ntracr):
+        for k in range(g.kdm):
+            assert _sea_eq(ref["tracer"][q, n - 1, k], alt["tracer"][q, n - 1, k], msk), ("tracer", q, k)
+    # diffusion did something, and only smoothed: the advected-only result differs
+    cb0 = util.make_diffusion_case(53, 41, 3, sigver, temdfc, ntracr=ntracr, nhybrd=nhybrd, temdf2=0.0)[3]
+    adv = util.run_oracle(oracle, cb0, sea, m, n)
+    assert not _sea_eq(ref["saln"][n - 1, 0], adv["saln"][n - 1, 0], msk)
+
+
+def test_diffusion_preserves_constant_and_conserves(oracle):
+    """a constant field stays constant; the dp-weighted integral of a diffused field is conserved
+    to rounding (fluxes are antisymmetric: what leaves a cell enters its neighbour)"""
+    cfg, sea, g, cb = util.make_diffusion_case(61, 47, 2, 6, 1.0, ntracr=1, temdf2=0.05)
+    m, n = 1, 2
+    cb.tracer[...] = np.where(np.isfinite(cb.tracer), 0.75, cb.tracer)
+    cb0 = util.make_diffusion_case(61, 47, 2, 6, 1.0, ntracr=1, temdf2=0.0)[3]
+    cb0.tracer[...] = cb.tracer
+    for c in (cb, cb0):   # no massless layers in this test (see the note below)
+        c.dp[...] = np.where(c.dp < 9806.0, 9806.0, c.dp)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    adv = util.run_oracle(oracle, cb0, sea, m, n)
+    msk = util.interior_sea(cb)
+    assert np.all(ref["tracer"][0, n - 1][:, msk] == 0.75)
+    for k in range(g.kdm):
+        w = np.where(msk, cb.dp[n - 1, k] * cb.oneta[n - 1] * cb.scp2, 0.0)
+        # (max(dp,eps_har) at :2314 breaks conservation in massless cells, by design)
+        a = float((w * np.where(msk, ref["saln"][n - 1, k], 0.0)).sum())
+        b = float((w * np.where(msk, adv["saln"][n - 1, k], 0.0)).sum())
+        assert abs(a - b) <= 1e-10 * abs(b), (k, a, b)

@@ -326,3 +326,118 @@ def test_tiling_invariance_on_device(oracle, itdm, jtdm, kdm, ipr, jpr, nreg, nt
             assert np.array_equal(dev[:, sea_t], r[glob][:, sea_t]), (g.mproc, g.nproc, fld)
         ts.close()
     assert np.array_equal(xmin, ref["xmin"]) and np.array_equal(xmax, ref["xmax"])
+
+
+# ---------------------------------------------------------------------------------------
+# temdf2 > 0: tsdff_1x/2x + the equation-of-state sweep (mod_tsadvc.F90:2138-2230)
+# ---------------------------------------------------------------------------------------
+DIFF_CASES = [
+    # itdm, jtdm, kdm, nreg, ntracr, advtyp, sigver, temdfc, nhybrd
+    (150, 150, 22, 0, 0, 2, 6, 1.0, -1),   # box basin, the GLB build's EOS (sigma-2, 17-term): temp & saln diffused
+    (150, 150, 4, 0, 3, 2, 5, 1.0, -1),    # odd number of tracers: tsdff_2x pair + tsdff_1x
+    (131, 77, 3, 3, 2, 1, 8, 0.5, -1),     # 12-term: th3d & temp diffused, combined in density space
+    (64, 203, 2, 1, 0, 2, 8, 0.0, -1),     # th3d & saln diffused, temp = tofsig
+    (70, 45, 4, 0, 1, 2, 7, 0.5, 2),       # exactly-isopycnal layers below nhybrd: th3d = theta
+    (90, 61, 3, 0, 0, 2, 2, 1.0, -1),      # 7-term sig
+    (90, 61, 3, 4, 1, 2, 4, 1.0, -1),      # 9-term sig
+    (90, 61, 3, 0, 0, 2, 1, 0.5, -1),      # 7-term tofsig: atan2/cos/sin (tolerance, not bits)
+    (90, 61, 3, 0, 0, 2, 3, 0.0, 2),       # 9-term tofsig
+    (70, 45, 3, 0, 0, 2, 8, 0.5, -1),
+]
+
+
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,ntracr,advtyp,sigver,temdfc,nhybrd", DIFF_CASES)
+def test_diffusion_host_path_matches_oracle(oracle, itdm, jtdm, kdm, nreg, ntracr, advtyp, sigver, temdfc, nhybrd):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_diffusion_case(itdm, jtdm, kdm, sigver, temdfc, nreg=nreg, ntracr=ntracr,
+                                               nhybrd=nhybrd, seed=17, advtyp=advtyp, nstep=3)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    got, before, launches = _run_host_path(cb, m, n)
+    # device atan2/cos/sin are not glibc's to the last bit: 7/9-term tofsig within 1e-12 only
+    libm = sigver <= 4 and (temdfc < 1.0 or (0 <= nhybrd < kdm))
+    _compare(cb, g, got, ref, n, ["saln"])
+    _compare(cb, g, got, ref, n, ["temp", "th3d"], exact=not libm)
+    for q in range(ntracr):
+        _compare(cb, g, {"t": got["tracer"][q]}, {"t": ref["tracer"][q]}, n, ["t"])
+    msk = util.interior_sea(cb)
+    for name in ("temp", "saln", "th3d"):
+        a, b = got[name], before[name]
+        assert np.array_equal(a[m - 1], b[m - 1], equal_nan=True), (name, "slot m modified")
+        assert np.array_equal(a[n - 1][:, ~msk], b[n - 1][:, ~msk], equal_nan=True), (name, "land/halo modified")
+    assert np.array_equal(got["xmin"], ref["xmin"]) and np.array_equal(got["xmax"], ref["xmax"])
+
+
+def test_diffusion_needs_eos_and_metrics():
+    cfg, sea, g, cb = util.make_diffusion_case(40, 30, 2, 6, 1.0)
+    cb.sigver = 0
+    ts = pkg.Tsadvc(cb)
+    with pytest.raises(cabi.TsadvcError):
+        ts.tsadvc(1, 2)
+    ts.close()
+
+
+@pytest.mark.parametrize("ipr,jpr,nreg,ntracr,sigver,temdfc", [(2, 2, 0, 1, 6, 1.0), (2, 1, 3, 0, 8, 0.5)])
+def test_diffusion_tiling_invariance_on_device(oracle, ipr, jpr, nreg, ntracr, sigver, temdfc):
+    """N tiles with the second exchange (width 2, :2140-2151) == the oracle on 1 tile"""
+    import torch  # noqa: F401
+    xc = __import__("importlib").import_module("hycom-src_b200.xc")
+    m, n = 1, 2
+    itdm, jtdm, kdm = 150, 120, 3
+    cfg, sea, g1, cb1 = util.make_diffusion_case(itdm, jtdm, kdm, sigver, temdfc, nreg=nreg, ntracr=ntracr,
+                                                 seed=5, nstep=3)
+    ref = util.run_oracle(oracle, cb1, sea, m, n)
+    nb = g1.nbdy
+    tss = []
+    for g in pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg):
+        cb = syn.build_cb_arrays(cfg, g, sea, m, n, nstep=3, temdf2=cb1.temdf2, temdfc=temdfc, sigver=sigver,
+                                 thbase=cb1.thbase)
+        # the tile's window of the global th3d/theta (halo cells come from the exchange)
+        cb.th3d = np.ascontiguousarray(_tile_window(cb1.th3d, g1, g, nreg))
+        cb.theta = np.ascontiguousarray(_tile_window(cb1.theta, g1, g, nreg))
+        ts = pkg.Tsadvc(cb)
+        ts.upload_state(m, n)
+        tss.append(ts)
+    _exchange_in_process(tss, m, n)
+    for ts in tss:
+        p = ts.cb.params()
+        ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, None, None))
+    # second exchange, then diffusion
+    sends, nbrs = [], []
+    for ts in tss:
+        be = xc.DeviceHaloBackend(ts)
+        nbr = xc.neighbors(ts.cb.geom)
+        cnt = be.diff_counts(n)
+        assert cnt == xc.halo_counts(ts.cb.geom, (3 + ntracr) * kdm, 2, 2)
+        send = [be.alloc(c) if nbr[d] >= 0 else None for d, c in enumerate(cnt)]
+        be.diff_pack(n, send)
+        sends.append(send); nbrs.append(nbr)
+        ts.synchronize()
+    for t, ts in enumerate(tss):
+        recv = [sends[nbrs[t][d]][xc.OPP[d]] if nbrs[t][d] >= 0 else None for d in range(8)]
+        xc.DeviceHaloBackend(ts).diff_unpack(n, recv)
+        p = ts.cb.params()
+        ts._ck(ts.lib.hycom_tsadvc_diffuse_device(ts.h, m, n, C.byref(p)))
+        ts.synchronize()
+    for ts in tss:
+        g = ts.cb.geom
+        sea_t = ts.cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
+        glob = (slice(None), slice(nb + g.j0, nb + g.j0 + g.jj), slice(nb + g.i0, nb + g.i0 + g.ii))
+        pairs = [(cabi.F_TEMP, 0, ref["temp"][n - 1]), (cabi.F_SALN, 0, ref["saln"][n - 1]),
+                 (cabi.F_TH3D, 0, ref["th3d"][n - 1])]
+        pairs += [(cabi.F_TRACER, q + 1, ref["tracer"][q, n - 1]) for q in range(ntracr)]
+        for fld, ktr, r in pairs:
+            dev = ts.download(fld, n, ktr=ktr)[:, nb:nb + g.jj, nb:nb + g.ii]
+            assert np.array_equal(dev[:, sea_t], r[glob][:, sea_t]), (g.mproc, g.nproc, fld)
+        ts.close()
+
+
+def _tile_window(a, g1, g, nreg):
+    """the padded window of tile g cut out of a single-tile global array (..., nrows, ncols);
+    cells beyond the global array are NaN (the exchange or the closed-edge rule fills them)"""
+    nb = g.nbdy
+    out = np.full(a.shape[:-2] + (g.nrows, g.ncols), np.nan)
+    jj0, ii0 = g.j0, g.i0           # global window starts at padded index (j0, i0)
+    js = slice(jj0, min(jj0 + g.nrows, g1.nrows))
+    is_ = slice(ii0, min(ii0 + g.ncols, g1.ncols))
+    out[..., : js.stop - js.start, : is_.stop - is_.start] = a[..., js, is_]
+    return out

@@ -71,3 +71,26 @@ def interior_sea(cb):
     m = np.zeros((g.nrows, g.ncols), dtype=bool)
     m[nb:nb + g.jj, nb:nb + g.ii] = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
     return m
+
+
+def make_diffusion_case(itdm, jtdm, kdm, sigver, temdfc, nreg=0, ntracr=0, nhybrd=-1, seed=3, temdf2=None,
+                        **scalars):
+    """a case with temdf2 > 0 (mod_tsadvc.F90:2138-2230): th3d is made consistent with the
+    equation of state (sig(T,S)-thbase plus a smooth offset, so that tofsig has a root to
+    find) and theta holds per-layer target densities"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import np_restatement as npr
+    thbase = 34.0 if sigver % 2 == 0 else 25.0
+    if temdf2 is None:
+        temdf2 = 0.02          # m/s diffusion velocity (blkdat temdf2 is O(0.005..0.02))
+    cfg, sea, g, cb = make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=seed, temdf2=temdf2,
+                                temdfc=temdfc, sigver=sigver, thbase=thbase, nhybrd=nhybrd, **scalars)
+    sv = sigver if sigver not in (5, 6) else sigver - 4   # the 17-term fit has no tofsig: seed from the 7-term
+    with np.errstate(all="ignore"):
+        cb.th3d = np.ascontiguousarray(npr.sig(sv, cb.temp, cb.saln) - thbase + 0.01 * np.cos(cb.temp))
+    cb.th3d[~np.isfinite(cb.th3d)] = np.nan
+    cb.theta = np.empty((kdm, g.nrows, g.ncols))
+    for k in range(kdm):
+        cb.theta[k] = np.nanmean(cb.th3d[:, k]) + 0.001 * k
+    return cfg, sea, g, cb
