@@ -210,14 +210,14 @@ def run_b200(args):
     tiles = pkg.partition(idm, jdm, kdm, ipr, jpr, 0)
     g = tiles[rank]
     cb = syn.build_cb_arrays(cfg, g, sea, 1, 2, with_state=False, advtyp=args.advtyp,
-                             trcflg=[0] * args.ntracr)
+                             trcflg=[0] * args.ntracr, temdf2=args.temdf2, temdfc=1.0, sigver=6)
     stream = torch.cuda.Stream()
     ts = pkg.Tsadvc(cb, device=local, stream=stream.cuda_stream)
     xc = None
     if world > 1:
         xc = pkg.XcExchange(ts, dist, compute_stream=stream)
     # device-resident synthetic state, both leapfrog slots (dp too: the slots alternate)
-    syn.fill_device(ts, cfg, sea, 1, 2)
+    syn.fill_device(ts, cfg, sea, 1, 2, diffusion=args.temdf2 > 0.0)
     ts._ck(ts.lib.hycom_tsadvc_synth_fill(ts.h, cabi.C.byref(cfg), cabi.F_DP, 0, 1, 0, 1, float("nan")))
     ts.synchronize()
 
@@ -310,7 +310,8 @@ def run_b200(args):
                                    + (" (REDUCED kdm: profiling run, not a bench value)" if args.kdm else ""),
                        "tiling": f"{ipr}x{jpr}", "tile": f"{g.ii}x{g.jj}", "nreg": 0,
                        "l2": "inputs per step (%.1f GB) exceed L2 (126 MB); no flush" % (alg / 1e9),
-                       "diag": "salinity min/max every 3rd step as mod_tsadvc.F90:2065"},
+                       "diag": "salinity min/max every 3rd step as mod_tsadvc.F90:2065",
+                       "temdf2": args.temdf2},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
             "clocks": clocks, "pct_of_hbm_roofline": 100.0 * alg * (1 if world == 1 else 1) /
                                                      (ms_step * 1e-3) / 1e9 / peak,
@@ -399,6 +400,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange first, then the whole tile")
+    ap.add_argument("--temdf2", type=float, default=0.0,
+                    help="> 0: the step also runs tsdff_1x/2x + the EOS sweep (mod_tsadvc.F90:2138-2230); "
+                         "the BASELINE metric is quoted without it")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -102,8 +102,10 @@ def build_cb_arrays(cfg: SynthCfg, g: TileGeom, sea: np.ndarray, m: int, n: int,
     return cb
 
 
-def fill_device(ts, cfg: SynthCfg, sea: np.ndarray, m: int, n: int, advflg: int = 0):
-    """Generate the same state straight into the device mirrors of ``ts`` (Tsadvc)."""
+def fill_device(ts, cfg: SynthCfg, sea: np.ndarray, m: int, n: int, advflg: int = 0, diffusion: bool = False):
+    """Generate the same state straight into the device mirrors of ``ts`` (Tsadvc).
+    ``diffusion``: also the operands of the temdf2>0 part (the other thermodynamic variable
+    and oneta, both slots)."""
     lib, h = ts.lib, ts.h
     ck = ts._ck
     ck(lib.hycom_tsadvc_synth_set_sea(h, C.byref(cfg), sea.ctypes.data_as(C.c_void_p)))
@@ -118,4 +120,10 @@ def fill_device(ts, cfg: SynthCfg, sea: np.ndarray, m: int, n: int, advflg: int 
     ck(lib.hycom_tsadvc_synth_fill(h, C.byref(cfg), cabi.F_DP, 0, n, 0, 1, nan))
     ck(lib.hycom_tsadvc_synth_fill(h, C.byref(cfg), cabi.F_UFLX, 0, 1, 0, 0, nan))
     ck(lib.hycom_tsadvc_synth_fill(h, C.byref(cfg), cabi.F_VFLX, 0, 1, 0, 0, nan))
+    if diffusion:
+        other = cabi.F_TEMP if advflg else cabi.F_TH3D
+        for slot in (1, 2):
+            lev = 0 if slot == n else 1
+            ck(lib.hycom_tsadvc_synth_fill(h, C.byref(cfg), other, 0, slot, lev, 0, nan))
+            ck(lib.hycom_tsadvc_synth_fill(h, C.byref(cfg), cabi.S_ONETA, 0, slot, lev, 1, nan))
     ts.synchronize()
