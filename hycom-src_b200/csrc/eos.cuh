@@ -11,8 +11,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "march_common.cuh"
+
 namespace tsadvc {
 namespace eos {
+
+// aone/x, IEEE round-to-nearest: the short division sequence with its exact fallback
+__device__ __forceinline__ double rcp_exact(double x) { return div_rn(1.0, x); }
 
 struct Poly79 { double c1, c2, c3, c4, c5, c6, c7, c8, c9; };
 
@@ -85,7 +90,7 @@ __device__ __forceinline__ double sig17(int sigver, double t, double s) {
   const double sp = 0.0 > s ? 0.0 : s;                                                               // max(sqrmin,s)
   const double den = c108 + t * (c109 + t * (c010 + t * (c111 + t * c012))) +
                      s * (c013 - t * (c014 + t * t * c015) + sqrt(sp) * (c016 + t * t * c017));       // :505-507
-  return num * (1.0 / den) - 1000.0;                                                                 // :508-509
+  return num * rcp_exact(den) - 1000.0;                                                                 // :508-509
 }
 
 // sigma(t,s)
@@ -102,7 +107,7 @@ __device__ __forceinline__ double sig(int sigver, double t, double s) {
     const Rat12 c = rat12(sigver);     // :419-424
     const double num = c.n1 + (c.n2 + c.n4 * t + c.n5 * s) * t + (c.n3 + c.n6 * s) * s;
     const double den = c.d1 + (c.d2 + c.d4 * t + c.d5 * s) * t + (c.d3 + c.d6 * s) * s;
-    return num * (1.0 / den);
+    return num * rcp_exact(den);
   }
   return sig17(sigver, t, s);
 }

@@ -246,6 +246,9 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   cudaFree(h->aspux); cudaFree(h->aspvy); cudaFree(h->d_minmax); cudaFree(h->d_sea);
   for (auto* v : {&h->ev_pending, &h->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+  if (h->up_stream) cudaStreamDestroy(h->up_stream);
+  if (h->down_stream) cudaStreamDestroy(h->down_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -353,8 +356,17 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const do
   return 0;
 }
 
+static int upload_on(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev, int32_t k0,
+                     int32_t nk, const double* host, cudaStream_t st);
+
 int hycom_tsadvc_upload(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
                         int32_t k0, int32_t nk, const double* host) {
+  return upload_on(h, field, ktr, tlev, k0, nk, host, h ? h->stream : nullptr);
+}
+
+// `host` = the nk slabs starting at layer k0
+static int upload_on(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev, int32_t k0,
+                     int32_t nk, const double* host, cudaStream_t st) {
   if (!h || !host) return fail(h, HYCOM_TSADVC_EINVAL, "upload: null argument");
   if (k0 < 1 || nk < 1 || k0 + nk - 1 > nlayers_of(h, field))
     return fail(h, HYCOM_TSADVC_EINVAL, "upload: layers %d..%d out of 1..%d", k0, k0 + nk - 1,
@@ -364,7 +376,7 @@ int hycom_tsadvc_upload(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int3
   if (rc) return rc;
   CU(h, cudaMemcpy2DAsync(base + h->slab * (k0 - 1), sizeof(double) * h->pitch, host,
                           sizeof(double) * h->ncols, sizeof(double) * h->ncols,
-                          (size_t)h->nrows * nk, cudaMemcpyHostToDevice, h->stream));
+                          (size_t)h->nrows * nk, cudaMemcpyHostToDevice, st));
   return 0;
 }
 
@@ -396,9 +408,18 @@ int hycom_tsadvc_device_slab(hycom_tsadvc_handle* h, int32_t field, int32_t ktr,
   return 0;
 }
 
+static int halo_local_range(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
+                            int32_t mh, int32_t nh, int k0, int nk);
+
 int hycom_tsadvc_halo_local(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
                             int32_t mh, int32_t nh) {
   if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  return halo_local_range(h, field, ktr, tlev, mh, nh, 0, nlayers_of(h, field));
+}
+
+// layers k0 .. k0+nk-1 (0-based) only
+static int halo_local_range(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
+                            int32_t mh, int32_t nh, int k0, int nk) {
   const int nreg = h->d.nreg;
   const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
   const int t0 = is3d(field) ? 1 : (tlev == 0 ? 1 : tlev);
@@ -407,7 +428,8 @@ int hycom_tsadvc_halo_local(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, 
     double* base;
     int rc = slot(h, field, ktr, t, &base);
     if (rc) return rc;
-    const int nl = nlayers_of(h, field);
+    const int nl = nk;
+    base += h->slab * k0;
     rc = launch_halo_local(base, h->slab, nl, h->pitch, h->d.nbdy, h->d.ii, h->d.jj, mh, nh,
                            per_i, per_j, h->stream);
     if (!rc)
@@ -491,9 +513,11 @@ int neighbour(const hycom_tsadvc_dims& d, int dir) {
   return mp + d.ipr * np;
 }
 
+// layers k0 .. k0+nk-1 (0-based; nk < 0: all)
 int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
-              const std::vector<Adv>& adv, int part) {
-  const int kk = h->d.kdm, aadv = abs(p.advtyp);
+              const std::vector<Adv>& adv, int part, int k0 = 0, int nk = -1) {
+  const int kk = nk < 0 ? h->d.kdm : nk, aadv = abs(p.advtyp);
+  const long koff = h->slab * k0;
   int rc;
   MarchParams P;
   memset(&P, 0, sizeof P);
@@ -504,17 +528,18 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     if ((rc = slot(h, adv[f].field, adv[f].ktr, n, &in))) return rc;
     if ((rc = slot(h, adv[f].field, adv[f].ktr, m, &ctr))) return rc;
     if ((rc = spare_of(h, mirror_of(h, adv[f].field, adv[f].ktr), &out))) return rc;
-    P.fld[f].fld = in;
-    P.fld[f].fldc = ctr;
-    P.fld[f].out = out;
+    P.fld[f].fld = in + koff;
+    P.fld[f].fldc = ctr + koff;
+    P.fld[f].out = out + koff;
     P.fld[f].posdef = adv[f].posdef;
-    P.fld[f].nlay = adv[f].nlay;
+    const int nl = adv[f].nlay - k0;
+    P.fld[f].nlay = nl < 0 ? 0 : (nl > kk ? kk : nl);
   }
   double *u, *v, *dpn;
   if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &u))) return rc;
   if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &v))) return rc;
   if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
-  P.u = u; P.v = v; P.dp = dpn;
+  P.u = u + koff; P.v = v + koff; P.dp = dpn + koff;
   P.slab = h->slab;
   P.njobs = P.nfld * kk;
   P.g.pitch = h->pitch; P.g.ncols = h->ncols; P.g.nrows = h->nrows; P.g.nbdy = h->d.nbdy;
@@ -616,6 +641,8 @@ int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
   return 0;
 }
 
+
+inline int ffield_of(bool adv_th3d) { return adv_th3d ? HYCOM_F_TH3D : HYCOM_F_TEMP; }
 
 // the arrays of the second exchange (mod_tsadvc.F90:2140-2151): saln, temp, th3d, tracers of
 // slot n, halo width mdf = 2
@@ -832,63 +859,140 @@ int hycom_tsadvc_halo_unpack(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   return halo_xfer(h, m, n, prm, recvbuf, cuda_stream, false);
 }
 
+// Layers are independent (mod_tsadvc.F90:1842 `do k=1,kk`), so the host-array call is a
+// pipeline over layer chunks on three streams: chunk c+1 is copied in while chunk c is advected
+// and chunk c-1 is copied out.  PCIe is full duplex: the step costs about the host->device
+// copy alone (it moves 3.5x the bytes of the way back) instead of copy-in + compute + copy-out.
 int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
                       double* temp, double* saln, double* th3d, double* tracer, const double* dp,
                       const double* uflx, const double* vflx, const double* oneta, double* xmin,
                       double* xmax) {
-  if (!h || !prm) return fail(h, HYCOM_TSADVC_EINVAL, "step: null argument");
-  if (m < 1 || m > 2 || n < 1 || n > 2 || m == n)
-    return fail(h, HYCOM_TSADVC_EINVAL, "step: bad leapfrog slots m=%d n=%d", m, n);
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
   const int kk = h->d.kdm;
   const size_t fs = (size_t)h->ncols * h->nrows;  // Fortran slab
   const bool adv_th3d = prm->advflg != 0;
   double* first = adv_th3d ? th3d : temp;
   if (!first || !saln || !dp || !uflx || !vflx || (h->d.ntracr > 0 && !tracer))
     return fail(h, HYCOM_TSADVC_EINVAL, "step: a required array is NULL");
-  int rc;
-  const int ffield = adv_th3d ? HYCOM_F_TH3D : HYCOM_F_TEMP;
-  for (int t = 1; t <= 2; ++t) {
-    if ((rc = hycom_tsadvc_upload(h, ffield, 0, t, 1, kk, first + fs * kk * (t - 1)))) return rc;
-    if ((rc = hycom_tsadvc_upload(h, HYCOM_F_SALN, 0, t, 1, kk, saln + fs * kk * (t - 1)))) return rc;
-    for (int q = 1; q <= h->d.ntracr; ++q)
-      if ((rc = hycom_tsadvc_upload(h, HYCOM_F_TRACER, q, t, 1, kk,
-                                    tracer + fs * kk * (2 * (size_t)(q - 1) + (t - 1)))))
-        return rc;
-  }
-  if ((rc = hycom_tsadvc_upload(h, HYCOM_F_DP, 0, n, 1, kk, dp + fs * kk * (n - 1)))) return rc;
-  if ((rc = hycom_tsadvc_upload(h, HYCOM_F_UFLX, 0, 1, 1, kk, uflx))) return rc;
-  if ((rc = hycom_tsadvc_upload(h, HYCOM_F_VFLX, 0, 1, 1, kk, vflx))) return rc;
   const bool diffuse = prm->temdf2 > 0.0;
   double* other = adv_th3d ? temp : th3d;   // the thermodynamic variable that is not advected
   const int ofield = adv_th3d ? HYCOM_F_TEMP : HYCOM_F_TH3D;
-  if (diffuse) {  // onetamas(:,:,n) = oneta(:,:,n) (:1805,1808); th3d/temp(:,:,:,n) (:2143-2144)
-    if (!oneta || !other) return fail(h, HYCOM_TSADVC_EINVAL, "step: temdf2>0 needs oneta, temp and th3d");
-    if ((rc = hycom_tsadvc_upload(h, HYCOM_F_ONETA, 0, n, 1, 1, oneta + fs * (n - 1)))) return rc;
-    if ((rc = hycom_tsadvc_upload(h, ofield, 0, n, 1, kk, other + fs * kk * (n - 1)))) return rc;
+  if (diffuse && (!oneta || !other))
+    return fail(h, HYCOM_TSADVC_EINVAL, "step: temdf2>0 needs oneta, temp and th3d");
+  CU(h, cudaSetDevice(h->d.device));
+  if (!h->up_stream) {
+    CU(h, cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    CU(h, cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
   }
-  if ((rc = hycom_tsadvc_step_device(h, m, n, prm, xmin, xmax))) return rc;
-  // copy back slot n of the advected fields on 1:ii,1:jj ("valid halo 0 wide", :104)
-  auto back = [&](int field, int ktr, double* host_n) -> int {
-    double* base;
-    int r2 = slot(h, field, ktr, n, &base);
-    if (r2) return r2;
-    const int nb = h->d.nbdy;
+  const char* ce = getenv("HYCOM_TSADVC_STEP_CHUNK");
+  int chunk = ce ? atoi(ce) : 4;
+  if (chunk < 1 || chunk > kk) chunk = kk;
+  const int nchunks = (kk + chunk - 1) / chunk;
+  while ((int)h->ev_chunk.size() < 2 * nchunks + 1) {
+    cudaEvent_t e;
+    CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev_chunk.push_back(e);
+  }
+  // host address of layer k0 (0-based) of slot t of a 4-D array / of tracer q
+  auto h4 = [&](double* a, int t, int k0) { return a + fs * ((size_t)kk * (t - 1) + k0); };
+  auto htr = [&](int q, int t, int k0) { return tracer + fs * ((size_t)kk * (2 * (size_t)(q - 1) + (t - 1)) + k0); };
+  // the copies must not overtake earlier work of the handle on the mirrors they overwrite
+  CU(h, cudaEventRecord(h->ev_chunk[2 * nchunks], h->stream));
+  CU(h, cudaStreamWaitEvent(h->up_stream, h->ev_chunk[2 * nchunks], 0));
+  CU(h, cudaStreamWaitEvent(h->down_stream, h->ev_chunk[2 * nchunks], 0));
+  // make sure every mirror (and ping-pong buffer) exists before the streams fork
+  for (const Adv& a : adv) {
+    double* t;
+    if ((rc = slot(h, a.field, a.ktr, 1, &t)) || (rc = slot(h, a.field, a.ktr, 2, &t)) ||
+        (rc = spare_of(h, mirror_of(h, a.field, a.ktr), &t))) return rc;
+  }
+  { double* t; if ((rc = slot(h, HYCOM_F_DP, 0, n, &t))) return rc; }
+  CU(h, cudaStreamSynchronize(h->stream));   // allocations zero-fill on h->stream
+
+  const bool single = h->d.ipr * h->d.jpr == 1;
+  const int nb = h->d.nbdy;
+  // D2H of layers k0..k0+nk-1 of a device buffer on 1:ii,1:jj ("valid halo 0 wide", :104)
+  auto back = [&](const double* dev, double* host, int nk, cudaStream_t st) -> int {
     cudaMemcpy3DParms cp;
     memset(&cp, 0, sizeof cp);
-    cp.srcPtr = make_cudaPitchedPtr(base, sizeof(double) * h->pitch, h->pitch, h->nrows);
-    cp.dstPtr = make_cudaPitchedPtr(host_n, sizeof(double) * h->ncols, h->ncols, h->nrows);
+    cp.srcPtr = make_cudaPitchedPtr((void*)dev, sizeof(double) * h->pitch, h->pitch, h->nrows);
+    cp.dstPtr = make_cudaPitchedPtr(host, sizeof(double) * h->ncols, h->ncols, h->nrows);
     cp.srcPos = make_cudaPos(sizeof(double) * nb, nb, 0);
     cp.dstPos = make_cudaPos(sizeof(double) * nb, nb, 0);
-    cp.extent = make_cudaExtent(sizeof(double) * h->d.ii, h->d.jj, kk);
+    cp.extent = make_cudaExtent(sizeof(double) * h->d.ii, h->d.jj, nk);
     cp.kind = cudaMemcpyDeviceToHost;
-    CU(h, cudaMemcpy3DAsync(&cp, h->stream));
+    CU(h, cudaMemcpy3DAsync(&cp, st));
     return 0;
   };
-  if ((rc = back(ffield, 0, first + fs * kk * (n - 1)))) return rc;
-  if ((rc = back(HYCOM_F_SALN, 0, saln + fs * kk * (n - 1)))) return rc;
-  if (diffuse && (rc = back(ofield, 0, other + fs * kk * (n - 1)))) return rc;
-  for (int q = 1; q <= h->d.ntracr; ++q)
-    if ((rc = back(HYCOM_F_TRACER, q, tracer + fs * kk * (2 * (size_t)(q - 1) + (n - 1))))) return rc;
+  for (int c = 0; c < nchunks; ++c) {
+    const int k0 = c * chunk, nk = (k0 + chunk <= kk) ? chunk : kk - k0;
+    // ---- copy in
+    for (const Adv& a : adv) {
+      if (k0 >= a.nlay) continue;   // layers below nhybrd of temp/th3d are not advected (:1855)
+      const int na = (k0 + nk <= a.nlay) ? nk : a.nlay - k0;
+      for (int t = 1; t <= 2; ++t) {
+        double* src = a.field == HYCOM_F_TRACER ? htr(a.ktr, t, k0)
+                                                : h4(a.field == HYCOM_F_SALN ? saln : first, t, k0);
+        if ((rc = upload_on(h, a.field, a.ktr, t, k0 + 1, na, src, h->up_stream))) return rc;
+      }
+    }
+    if ((rc = upload_on(h, HYCOM_F_DP, 0, n, k0 + 1, nk, h4((double*)dp, n, k0), h->up_stream))) return rc;
+    if ((rc = upload_on(h, HYCOM_F_UFLX, 0, 1, k0 + 1, nk, uflx + fs * k0, h->up_stream))) return rc;
+    if ((rc = upload_on(h, HYCOM_F_VFLX, 0, 1, k0 + 1, nk, vflx + fs * k0, h->up_stream))) return rc;
+    CU(h, cudaEventRecord(h->ev_chunk[2 * c], h->up_stream));
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c], 0));
+    // ---- :1827-1836 halos (single tile; a multi-tile host program hands over valid halos)
+    if (single) {
+      for (const Adv& a : adv) {
+        if (k0 >= a.nlay) continue;
+        const int na = (k0 + nk <= a.nlay) ? nk : a.nlay - k0;
+        if ((rc = halo_local_range(h, a.field, a.ktr, 0, mbdy, mbdy, k0, na))) return rc;
+      }
+      if ((rc = halo_local_range(h, HYCOM_F_UFLX, 0, 1, mbdy, mbdy, k0, nk))) return rc;
+      if ((rc = halo_local_range(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy, k0, nk))) return rc;
+    }
+    // ---- advection of these layers into the ping-pong buffers
+    if ((rc = run_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_ALL, k0, nk))) return rc;
+    if (diffuse) continue;   // the diffusion needs every layer's neighbours first: copy out after it
+    CU(h, cudaEventRecord(h->ev_chunk[2 * c + 1], h->stream));
+    CU(h, cudaStreamWaitEvent(h->down_stream, h->ev_chunk[2 * c + 1], 0));
+    // ---- copy out (the new time level still sits in the ping-pong buffer)
+    for (const Adv& a : adv) {
+      if (k0 >= a.nlay) continue;
+      const int na = (k0 + nk <= a.nlay) ? nk : a.nlay - k0;
+      double* dst = a.field == HYCOM_F_TRACER ? htr(a.ktr, n, k0)
+                                              : h4(a.field == HYCOM_F_SALN ? saln : first, n, k0);
+      if ((rc = back(mirror_of(h, a.field, a.ktr)->spare + h->slab * k0, dst, na, h->down_stream))) return rc;
+    }
+  }
+  // layers that were not advected must still be in the mirror the ping-pong swap retires
+  for (const Adv& a : adv)
+    if (a.nlay < kk) {
+      for (int t = 1; t <= 2; ++t) {
+        double* src = a.field == HYCOM_F_TRACER ? htr(a.ktr, t, a.nlay)
+                                                : h4(a.field == HYCOM_F_SALN ? saln : first, t, a.nlay);
+        if ((rc = upload_on(h, a.field, a.ktr, t, a.nlay + 1, kk - a.nlay, src, h->stream))) return rc;
+      }
+    }
+  if ((rc = finish_step(h, n, *prm, adv, xmin, xmax))) return rc;
+  if (diffuse) {  // onetamas(:,:,n) = oneta(:,:,n) (:1805,1808); th3d/temp(:,:,:,n) (:2143-2144)
+    if ((rc = upload_on(h, HYCOM_F_ONETA, 0, n, 1, 1, oneta + fs * (n - 1), h->stream))) return rc;
+    if ((rc = upload_on(h, ofield, 0, n, 1, kk, h4(other, n, 0), h->stream))) return rc;
+    if (single && (rc = hycom_tsadvc_diffuse_device(h, m, n, prm))) return rc;
+    auto back_all = [&](int field, int ktr, double* host_n) -> int {
+      double* base;
+      int r2 = slot(h, field, ktr, n, &base);
+      return r2 ? r2 : back(base, host_n, kk, h->stream);
+    };
+    if ((rc = back_all(ffield_of(adv_th3d), 0, h4(first, n, 0)))) return rc;
+    if ((rc = back_all(HYCOM_F_SALN, 0, h4(saln, n, 0)))) return rc;
+    if ((rc = back_all(ofield, 0, h4(other, n, 0)))) return rc;
+    for (int q = 1; q <= h->d.ntracr; ++q)
+      if ((rc = back_all(HYCOM_F_TRACER, q, htr(q, n, 0)))) return rc;
+  }
+  CU(h, cudaStreamSynchronize(h->down_stream));
   CU(h, cudaStreamSynchronize(h->stream));
   return 0;
 }

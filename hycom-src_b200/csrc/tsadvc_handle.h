@@ -21,6 +21,9 @@ struct hycom_tsadvc_handle {
   long slab;  // doubles per slab on the device
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // copy-in / copy-out streams and per-chunk events of the pipelined host-array call
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  std::vector<cudaEvent_t> ev_chunk;
   int64_t bytes = 0;
   int64_t launches = 0;
   bool have_static = false;

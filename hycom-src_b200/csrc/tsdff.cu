@@ -3,10 +3,10 @@
 // tsdff_1x :2347-2492, EOS sweep :2199-2229), fused: the reference runs, per layer and field
 // pair, one sweep that stores the face fluxes uflux/vflux(/uflux2/vflux2), one sweep that
 // applies their divergence, and at the end one sweep over all layers for the equation of
-// state.  Here one thread owns one cell of one layer, forms the four face factors once
-// (they depend on dp only and are shared by every field of the layer), diffuses every field
-// of the launch and - for the T/S/th3d launch - applies the equation of state to the fresh
-// values before the single store.
+// state.  Here one thread owns one (i,j) column and walks the layers; per layer it forms the
+// four face factors once (they depend on dp only and are shared by every field of the layer),
+// diffuses every field of the launch and - for the T/S/th3d launch - applies the equation of
+// state to the fresh values before the single store.
 //
 // HBM bound: per layer-cell it reads dp(n) and each field once (neighbours come from L1/L2)
 // and writes each field once: T,S,th3d launch 7 x 8 B = 56 B, tracer launch 8 + 16 B/tracer.
@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "eos.cuh"
+#include "march_common.cuh"   // div_rn: IEEE round-to-nearest a/b, short sequence + exact fallback
 #include "tsadvc_dev.h"
 #include "tsadvc_launch.h"
 
@@ -36,88 +37,106 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 __device__ __forceinline__ double harmonc(double aa, double bb) {
   const double eps_har = 1.0e-20;   // :1763
   const double a = dmax(aa, 0.0), b = dmax(bb, 0.0);
-  return 2.0 * a * b / dmax((a + b), 2.0 * eps_har);
+  return div_rn(2.0 * a * b, dmax((a + b), 2.0 * eps_har));
 }
 
+// One thread owns one (i,j) column and walks the layers: everything that does not depend on k
+// (masks, temdf2*aspux*scuy, temdf2*aspvy*scvx, scp2, oneta at the five points) is loaded and
+// formed once and stays in registers, so per layer the thread reads dp and the fields only.
 template <bool EOS>
-__global__ void __launch_bounds__(256) k_tsdff(const DiffParams P) {
+__global__ void __launch_bounds__(256, 3) k_tsdff(const DiffParams P) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r = blockIdx.y * 8 + threadIdx.y;
-  const int k0 = blockIdx.z;   // k-1
   if (c >= P.pitch || r >= P.nrows) return;
   const long q = (long)r * P.pitch + c;
-  const long qk = q + (long)k0 * P.slab;
   const unsigned m = P.mask[q];
   if (!(m & M_OUT)) {   // land, halo, pad: the ping-pong slab keeps the old value
+    for (int k0 = 0; k0 < P.kk; ++k0) {
+      const long qk = q + (long)k0 * P.slab;
 #pragma unroll 1
-    for (int f = 0; f < P.nf; ++f) P.f[f].out[qk] = P.f[f].in[qk];
+      for (int f = 0; f < P.nf; ++f) P.f[f].out[qk] = P.f[f].in[qk];
+    }
     return;
   }
   // faces of this cell: west/south are its own iu/iv, east/north those of the neighbours
   const bool fw = m & M_IU, fs = m & M_IV;
   const bool fe = P.mask[q + 1] & M_IU, fn = P.mask[q + P.pitch] & M_IV;
-  const double* dp = P.dp + (long)k0 * P.slab;
-  const double hc = dp[q] * P.oneta[q];
-  double gw = 0.0, ge = 0.0, gs = 0.0, gn = 0.0;
-  if (fw) gw = P.temdf2 * P.aspux[q] * P.scuy[q] * harmonc(dp[q - 1] * P.oneta[q - 1], hc);
-  if (fe) ge = P.temdf2 * P.aspux[q + 1] * P.scuy[q + 1] * harmonc(hc, dp[q + 1] * P.oneta[q + 1]);
-  if (fs) gs = P.temdf2 * P.aspvy[q] * P.scvx[q] * harmonc(dp[q - P.pitch] * P.oneta[q - P.pitch], hc);
-  if (fn) gn = P.temdf2 * P.aspvy[q + P.pitch] * P.scvx[q + P.pitch] *
-               harmonc(hc, dp[q + P.pitch] * P.oneta[q + P.pitch]);
-  const double factor = -P.delt1 / (P.scp2[q] * dmax(hc, 1.0e-20));   // :2314-2315
-  const int k = k0 + 1;
-  const bool ldtemp = k <= P.nhybrd && P.temdfc > 0.0;                               // :2170
-  const bool ldth3d = (k <= P.nhybrd && P.temdfc < 1.0) || (k == 1 && P.isopyc);     // :2171-2172
-  // one field: the divergence of the four face fluxes applied to the centre value
-  auto diffuse = [&](const double* __restrict__ a, double x) {
-    const double uw = fw ? gw * (a[q - 1] - x) : 0.0;
-    const double ue = fe ? ge * (x - a[q + 1]) : 0.0;
-    const double vs = fs ? gs * (a[q - P.pitch] - x) : 0.0;
-    const double vn = fn ? gn * (x - a[q + P.pitch]) : 0.0;
-    const double util = ((ue - uw) + (vn - vs)) * factor;
-    return x + util;
-  };
-  if (!EOS) {
+  const long qw = q - 1, qe = q + 1, qs = q - P.pitch, qn = q + P.pitch;
+  // temdf2*aspux(i,j)*scuy(i,j) and temdf2*aspvy(i,j)*scvx(i,j): left to right as written
+  const double aw = fw ? P.temdf2 * P.aspux[q] * P.scuy[q] : 0.0;
+  const double ae = fe ? P.temdf2 * P.aspux[qe] * P.scuy[qe] : 0.0;
+  const double as = fs ? P.temdf2 * P.aspvy[q] * P.scvx[q] : 0.0;
+  const double an = fn ? P.temdf2 * P.aspvy[qn] * P.scvx[qn] : 0.0;
+  const double oc = P.oneta[q];
+  const double ow = fw ? P.oneta[qw] : 0.0, oe = fe ? P.oneta[qe] : 0.0;
+  const double os = fs ? P.oneta[qs] : 0.0, on = fn ? P.oneta[qn] : 0.0;
+  const double scp2 = P.scp2[q];
+#pragma unroll 2
+  for (int k0 = 0; k0 < P.kk; ++k0) {
+    const long ko = (long)k0 * P.slab;
+    const long qk = q + ko;
+    const double* dp = P.dp + ko;
+    const double hc = dp[q] * oc;
+    double gw = 0.0, ge = 0.0, gs = 0.0, gn = 0.0;
+    if (fw) gw = aw * harmonc(dp[qw] * ow, hc);
+    if (fe) ge = ae * harmonc(hc, dp[qe] * oe);
+    if (fs) gs = as * harmonc(dp[qs] * os, hc);
+    if (fn) gn = an * harmonc(hc, dp[qn] * on);
+    const double factor = div_rn(-P.delt1, scp2 * dmax(hc, 1.0e-20));   // :2314-2315
+    // one field: the divergence of the four face fluxes applied to the centre value
+    auto diffuse = [&](const double* __restrict__ a, double x) {
+      const double uw = fw ? gw * (a[qw] - x) : 0.0;
+      const double ue = fe ? ge * (x - a[qe]) : 0.0;
+      const double vs = fs ? gs * (a[qs] - x) : 0.0;
+      const double vn = fn ? gn * (x - a[qn]) : 0.0;
+      const double util = ((ue - uw) + (vn - vs)) * factor;
+      return x + util;
+    };
+    if (!EOS) {
 #pragma unroll 1
-    for (int f = 0; f < P.nf; ++f) {
-      const double* a = P.f[f].in + (long)k0 * P.slab;
-      P.f[f].out[qk] = diffuse(a, a[q]);
+      for (int f = 0; f < P.nf; ++f) {
+        const double* a = P.f[f].in + ko;
+        P.f[f].out[qk] = diffuse(a, a[q]);
+      }
+      continue;
     }
-    return;
-  }
-  // T/S/th3d launch: f = 0 temp, 1 saln, 2 th3d; which of them are diffused is :2173-2185
-  double v[3];
+    const int k = k0 + 1;
+    const bool ldtemp = k <= P.nhybrd && P.temdfc > 0.0;                               // :2170
+    const bool ldth3d = (k <= P.nhybrd && P.temdfc < 1.0) || (k == 1 && P.isopyc);     // :2171-2172
+    // T/S/th3d launch: f = 0 temp, 1 saln, 2 th3d; which of them are diffused is :2173-2185
+    double v[3];
 #pragma unroll
-  for (int f = 0; f < 3; ++f) {
-    const double* a = P.f[f].in + (long)k0 * P.slab;
-    const double x = a[q];
-    const bool on = f == 1 || (f == 0 ? ldtemp : ldth3d);
-    v[f] = on ? diffuse(a, x) : x;
-  }
-  {   // :2199-2229
-    double t = v[0], s = v[1], h = v[2];
-    if (ldtemp && ldth3d) {
-      const double th3d_t = eos::sig(P.sigver, t, s) - P.thbase;
-      h = (1.0 - P.temdfc) * h + P.temdfc * th3d_t;
-      t = eos::tofsig(P.sigver, h + P.thbase, s);
-    } else if (ldtemp) {
-      h = eos::sig(P.sigver, t, s) - P.thbase;
-    } else if (ldth3d) {
-      t = eos::tofsig(P.sigver, h + P.thbase, s);
-    } else {
-      h = P.theta[qk];
-      t = eos::tofsig(P.sigver, h + P.thbase, s);
+    for (int f = 0; f < 3; ++f) {
+      const double* a = P.f[f].in + ko;
+      const double x = a[q];
+      const bool on_ = f == 1 || (f == 0 ? ldtemp : ldth3d);
+      v[f] = on_ ? diffuse(a, x) : x;
     }
-    P.f[0].out[qk] = t;
-    P.f[1].out[qk] = s;
-    P.f[2].out[qk] = h;
+    {   // :2199-2229
+      double t = v[0], s = v[1], h = v[2];
+      if (ldtemp && ldth3d) {
+        const double th3d_t = eos::sig(P.sigver, t, s) - P.thbase;
+        h = (1.0 - P.temdfc) * h + P.temdfc * th3d_t;
+        t = eos::tofsig(P.sigver, h + P.thbase, s);
+      } else if (ldtemp) {
+        h = eos::sig(P.sigver, t, s) - P.thbase;
+      } else if (ldth3d) {
+        t = eos::tofsig(P.sigver, h + P.thbase, s);
+      } else {
+        h = P.theta[qk];
+        t = eos::tofsig(P.sigver, h + P.thbase, s);
+      }
+      P.f[0].out[qk] = t;
+      P.f[1].out[qk] = s;
+      P.f[2].out[qk] = h;
+    }
   }
 }
 
 }  // namespace
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream) {
-  const dim3 block(32, 8), grid((P.pitch + 31) / 32, (P.nrows + 7) / 8, P.kk);
+  const dim3 block(32, 8), grid((P.pitch + 31) / 32, (P.nrows + 7) / 8);
   if (P.eos) k_tsdff<true><<<grid, block, 0, stream>>>(P);
   else k_tsdff<false><<<grid, block, 0, stream>>>(P);
   return (int)cudaGetLastError();
