@@ -198,6 +198,76 @@ def advem_pcm(geom, fld, u, v, fco, fcn, scal, scali, dt2, ip, iu, iv):
         return np.where(r0, _fmax(fmn, _fmin(fmx, q / (fcn + ONEMU))), fld), {}
 
 
+def advem_fct2c(geom, fld, fldc, u, v, fco, scal, scali, dt2, ip, iu, iv):
+    """advem_fct2c (mod_tsadvc.F90:999-1368): FCT2 with a sub-cycled low-order step (5 iterations,
+    local time step dtloc, per-face elapsed time ucumdt/vcumdt), single-tile xctilr of hloc and
+    fldlo after every iteration.  Whole-array form: state arrays are updated through masks."""
+    epsil = 1.0e-10
+    with np.errstate(all="ignore"):
+        sea, su, sv = ip != 0, iu != 0, iv != 0
+        shp = ip.shape
+        lcalc = np.ones(shp, dtype=bool)
+        flxcum, flycum = np.zeros(shp), np.zeros(shp)
+        hloc, fldlo = fco.copy(), fld.copy()
+        ucum, vcum = np.zeros(shp), np.zeros(shp)
+        uloc, vloc, flx, fly = np.zeros(shp), np.zeros(shp), np.zeros(shp), np.zeros(shp)
+        dtloc = np.zeros(shp)
+        up, vp = u >= 0, v >= 0
+        for _ in range(5):
+            q = _fmax(_sh(u, 1, 0), 0.0) - _fmin(u, 0.0) + _fmax(_sh(v, 0, 1), 0.0) - _fmin(v, 0.0)
+            dtloc = np.where(_region(geom, 5) & sea, np.where(q > 0.0, _fmin(dt2, hloc / (q * scali)), dt2), dtloc)
+            r4 = _region(geom, 4)
+            # x faces
+            act = r4 & su & (ucum != dt2)
+            dtu = _fmin(dt2 - ucum, np.where(up, _sh(dtloc, -1, 0), dtloc))
+            ul = dtu * u
+            fx = np.where(up, _sh(fldlo, -1, 0), fldlo) * ul
+            uloc = np.where(act, ul, np.where(r4 & su, 0.0, uloc))
+            flx = np.where(act, fx, np.where(r4 & su, 0.0, flx))
+            ucum = np.where(act, ucum + dtu, ucum)
+            flxcum = np.where(act, flxcum + flx, flxcum)
+            # y faces
+            act = r4 & sv & (vcum != dt2)
+            dtv = _fmin(dt2 - vcum, np.where(vp, _sh(dtloc, 0, -1), dtloc))
+            vl = dtv * v
+            fy = np.where(vp, _sh(fldlo, 0, -1), fldlo) * vl
+            vloc = np.where(act, vl, np.where(r4 & sv, 0.0, vloc))
+            fly = np.where(act, fy, np.where(r4 & sv, 0.0, fly))
+            vcum = np.where(act, vcum + dtv, vcum)
+            flycum = np.where(act, flycum + fly, flycum)
+            # cells
+            go = _region(geom, 3) & sea & lcalc
+            qp = hloc - (_sh(uloc, 1, 0) - uloc + _sh(vloc, 0, 1) - vloc) * scali
+            new = ((epsil + hloc) * fldlo - (_sh(flx, 1, 0) - flx + _sh(fly, 0, 1) - fly) * scali) / (epsil + qp)
+            fldlo = np.where(go & (qp > 0.0), new, fldlo)
+            hloc = np.where(go, qp, hloc)
+            more = (_sh(ucum, 1, 0) != dt2) | (ucum != dt2) | (_sh(vcum, 0, 1) != dt2) | (vcum != dt2)
+            lcalc = np.where(go, more, lcalc)
+            hloc = halo_single_tile(geom, hloc, 5, 5)
+            fldlo = halo_single_tile(geom, fldlo, 5, 5)
+        fhx = u * 0.5 * (fldc + _sh(fldc, -1, 0))
+        fhy = v * 0.5 * (fldc + _sh(fldc, 0, -1))
+        fax, fay = _faces(geom, ip, iu, iv, 3, fhx - flxcum / dt2, fhy - flycum / dt2)
+        fqmax, fqmin = _extrema5(fldlo, ip)
+        faxe, fayn = _sh(fax, 1, 0), _sh(fay, 0, 1)
+        famax = _fmax(0.0, fax) - _fmin(0.0, faxe) + _fmax(0.0, fay) - _fmin(0.0, fayn)
+        famin = _fmax(0.0, faxe) - _fmin(0.0, fax) + _fmax(0.0, fayn) - _fmin(0.0, fay)
+        qdt2 = 1.0 / dt2
+        qp = (fqmax - fldlo) * hloc * scal * qdt2
+        qm = (fldlo - fqmin) * hloc * scal * qdt2
+        r2 = _region(geom, 2) & sea
+        rp = np.where(r2, np.where(famax > epsil, np.where(qp < famax, qp / famax, 1.0), 0.0), np.nan)
+        rm = np.where(r2, np.where(famin > epsil, np.where(qm < famin, qm / famin, 1.0), 0.0), np.nan)
+        fx = np.where(fax < 0.0, _fmin(_sh(rp, -1, 0), rm), _fmin(rp, _sh(rm, -1, 0))) * fax
+        fy = np.where(fay < 0.0, _fmin(_sh(rp, 0, -1), rm), _fmin(rp, _sh(rm, 0, -1))) * fay
+        r1 = _region(geom, 1)
+        fax = np.where(r1 & su, fx, fax)
+        fay = np.where(r1 & sv, fy, fay)
+        flxdiv = ((_sh(fax, 1, 0) - fax) + (_sh(fay, 0, 1) - fay)) * dt2 * scali
+        new = np.where(hloc > 0.0, ((epsil + hloc) * fldlo - flxdiv) / (epsil + hloc), fldlo)
+        return np.where(_region(geom, 0) & sea, new, fld), {}
+
+
 def prolog(geom, uflx_k, vflx_k, dp_kn, onetamas_m, delt1, scp2i, ip, margin):
     """tsadvc prolog, mod_tsadvc.F90:1905-1942: util1 = fco, util2 = fcn"""
     with np.errstate(all="ignore"):
@@ -244,11 +314,14 @@ def tsadvc(cb, m, n):
     uflx = halo_single_tile(g, cb.uflx, mbdy, mbdy)
     vflx = halo_single_tile(g, cb.vflx, mbdy, mbdy)
     tracer = halo_single_tile(g, cb.tracer, mbdy, mbdy) if cb.ntracr else None
-    oem = np.ones((g.nrows, g.ncols))  # onetamas(:,:,m) = 1.0, :1809
+    # onetamas(:,:,m) = 1.0 (:1809), or oneta(:,:,n) when btrmas (:1806)
+    oem = cb.oneta[n - 1] if cb.btrmas else np.ones((g.nrows, g.ncols))
     ip, iu, iv = cb.ip, cb.iu, cb.iv
 
     def adv(fld_n, fld_m, k, posdef, fco, fcn):
         a = (g, fld_n, fld_m, uflx[k], vflx[k], fco, fcn, cb.scp2, cb.scp2i, cb.delt1, ip, iu, iv)
+        if cb.advtyp == 2 and cb.btrmas:
+            return advem_fct2c(g, fld_n, fld_m, uflx[k], vflx[k], fco, cb.scp2, cb.scp2i, cb.delt1, ip, iu, iv)[0]
         if cb.advtyp == 2:
             return advem_fct(a[0], 2, *a[1:])[0]
         if cb.advtyp == 4:

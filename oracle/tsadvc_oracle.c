@@ -911,6 +911,200 @@ static void advem_fct(orc_tile *t, int order, double *fld, const double *fldc,
   tap(t, "ad:620:flxdv", flxdiv);
 }
 
+
+/* advem_fct2c: mod_tsadvc.F90:999-1368 (Baraille 2008: leapfrog FCT2 whose low-order step is
+ * sub-cycled, 5 iterations with a local time step so that no cell is emptied; used when
+ * btrmas, :96-97).  Scratch uloc..lcalc as :1041-1063; each iteration ends with
+ * xctilr(hloc), xctilr(fldlo) (:1186-1187) - single-tile semantics here. */
+static void advem_fct2c(orc_tile *t, double *fld, const double *fldc,
+                        const double *u, const double *v, const double *fco,
+                        const double *fcn, const double *scal,
+                        const double *scali, double dt2) {
+  GEOM(t); MASKS(t);
+  (void)fcn;
+  const double epsil = 1.e-10; /* :1027 */
+  const size_t P = (size_t)orc_slab(t);
+  double *flx = t->flx, *fly = t->fly, *fmx = t->fmx, *fmn = t->fmn,
+         *fldlo = t->fldlo, *fax = t->fax, *fay = t->fay, *rp = t->rp,
+         *rm = t->rm, *flxdiv = t->flxdiv;
+  double *uloc = alloc_r(P), *vloc = alloc_r(P), *hloc = alloc_r(P),
+         *dtloc = alloc_r(P), *ucumdt = alloc_r(P), *vcumdt = alloc_r(P),
+         *flxcum = alloc_r(P), *flycum = alloc_r(P);
+  int *lcalc = alloc_i(P);
+  const int mbdy_a = 5; /* :1065 */
+  const int nthr = nthr_of(t), jblk = jblk_of(t, nthr);
+  int margin;
+  /* :1072-1086 */
+  for (size_t q = 0; q < P; q++) {
+    lcalc[q] = 1; flxcum[q] = 0.0; flycum[q] = 0.0; dtloc[q] = 0.0;
+    hloc[q] = fco[q]; fldlo[q] = fld[q];
+    ucumdt[q] = 0.0; vcumdt[q] = 0.0; uloc[q] = 0.0; vloc[q] = 0.0;
+    flx[q] = 0.0; fly[q] = 0.0;
+  }
+  for (int iter = 1; iter <= 5; iter++) { /* :1088 */
+    margin = mbdy_a; /* :1090-1107 */
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++)
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_P) {
+          const size_t c = IX(i, j);
+          const double q = MAX2(u[IX(i + 1, j)], 0.0) - MIN2(u[c], 0.0) +
+                           MAX2(v[IX(i, j + 1)], 0.0) - MIN2(v[c], 0.0);
+          if (q > 0.0)
+            dtloc[c] = MIN2(dt2, hloc[c] / (q * scali[c]));
+          else
+            dtloc[c] = dt2;
+        }
+    margin = mbdy_a - 1; /* :1109-1158 */
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++)
+      for (int i = 1 - margin; i <= ii + margin; i++) {
+        const size_t c = IX(i, j);
+        if (SEA_U) {
+          if (ucumdt[c] != dt2) {
+            if (u[c] >= 0) {
+              uloc[c] = MIN2(dt2 - ucumdt[c], dtloc[IX(i - 1, j)]) * u[c];
+              flx[c] = fldlo[IX(i - 1, j)] * uloc[c];
+              ucumdt[c] = ucumdt[c] + MIN2(dt2 - ucumdt[c], dtloc[IX(i - 1, j)]);
+            } else {
+              uloc[c] = MIN2(dt2 - ucumdt[c], dtloc[c]) * u[c];
+              flx[c] = fldlo[c] * uloc[c];
+              ucumdt[c] = ucumdt[c] + MIN2(dt2 - ucumdt[c], dtloc[c]);
+            }
+            flxcum[c] = flxcum[c] + flx[c];
+          } else {
+            uloc[c] = 0.0;
+            flx[c] = 0.0;
+          }
+        }
+        if (SEA_V) {
+          if (vcumdt[c] != dt2) {
+            if (v[c] >= 0) {
+              vloc[c] = MIN2(dt2 - vcumdt[c], dtloc[IX(i, j - 1)]) * v[c];
+              fly[c] = fldlo[IX(i, j - 1)] * vloc[c];
+              vcumdt[c] = vcumdt[c] + MIN2(dt2 - vcumdt[c], dtloc[IX(i, j - 1)]);
+            } else {
+              vloc[c] = MIN2(dt2 - vcumdt[c], dtloc[c]) * v[c];
+              fly[c] = fldlo[c] * vloc[c];
+              vcumdt[c] = vcumdt[c] + MIN2(dt2 - vcumdt[c], dtloc[c]);
+            }
+            flycum[c] = flycum[c] + fly[c];
+          } else {
+            vloc[c] = 0.0;
+            fly[c] = 0.0;
+          }
+        }
+      }
+    margin = mbdy_a - 2; /* :1160-1184 */
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++)
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_P) {
+          const size_t c = IX(i, j);
+          if (lcalc[c]) {
+            const double qp =
+                hloc[c] - (uloc[IX(i + 1, j)] - uloc[c] + vloc[IX(i, j + 1)] - vloc[c]) * scali[c];
+            if (qp > 0.0)
+              fldlo[c] = ((epsil + hloc[c]) * fldlo[c] -
+                          (flx[IX(i + 1, j)] - flx[c] + fly[IX(i, j + 1)] - fly[c]) * scali[c]) /
+                         (epsil + qp);
+            hloc[c] = qp;
+            lcalc[c] = ucumdt[IX(i + 1, j)] != dt2 || ucumdt[c] != dt2 ||
+                       vcumdt[IX(i, j + 1)] != dt2 || vcumdt[c] != dt2;
+          }
+        }
+    orc_xctilr(t, hloc, 1, 1, mbdy_a, mbdy_a);  /* :1186 */
+    orc_xctilr(t, fldlo, 1, 1, mbdy_a, mbdy_a); /* :1187 */
+    tap(t, "aditer:fldlo", fldlo); tap(t, "aditer:hloc", hloc);
+  }
+  /* :1202-1215 high-order minus the cumulated low-order fluxes */
+  margin = mbdy_a - 2;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int i = 1 - margin; i <= ii + margin; i++) {
+      const size_t c = IX(i, j);
+      if (SEA_U) {
+        const double fhx = u[c] * 0.5 * (fldc[c] + fldc[IX(i - 1, j)]);
+        fax[c] = fhx - flxcum[c] / dt2;
+      }
+      if (SEA_V) {
+        const double fhy = v[c] * 0.5 * (fldc[c] + fldc[IX(i, j - 1)]);
+        fay[c] = fhy - flycum[c] / dt2;
+      }
+    }
+  coast_zero(t, fax, fay, margin); /* :1223-1245 */
+  tap(t, "ad:ip:0:fax", fax); tap(t, "ad:ip:0:fay", fay);
+  /* :1258-1306 */
+  margin = mbdy_a - 3;
+  const double qdt2 = 1.0 / dt2;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int i = 1 - margin; i <= ii + margin; i++)
+      if (SEA_P) {
+        const size_t c = IX(i, j);
+        int ia = i - 1; if (ip[IX(ia, j)] == 0) ia = i;
+        int ib = i + 1; if (ip[IX(ib, j)] == 0) ib = i;
+        int ja = j - 1; if (ip[IX(i, ja)] == 0) ja = j;
+        int jb = j + 1; if (ip[IX(i, jb)] == 0) jb = j;
+        const double fqmax = MAX5(fldlo[c], fldlo[IX(ia, j)], fldlo[IX(ib, j)],
+                                  fldlo[IX(i, ja)], fldlo[IX(i, jb)]);
+        const double fqmin = MIN5(fldlo[c], fldlo[IX(ia, j)], fldlo[IX(ib, j)],
+                                  fldlo[IX(i, ja)], fldlo[IX(i, jb)]);
+        const double famax = MAX2(0.0, fax[c]) - MIN2(0.0, fax[IX(i + 1, j)]) +
+                             MAX2(0.0, fay[c]) - MIN2(0.0, fay[IX(i, j + 1)]);
+        const double famin = MAX2(0.0, fax[IX(i + 1, j)]) - MIN2(0.0, fax[c]) +
+                             MAX2(0.0, fay[IX(i, j + 1)]) - MIN2(0.0, fay[c]);
+        if (famax > epsil) {
+          const double qp = (fqmax - fldlo[c]) * hloc[c] * scal[c] * qdt2;
+          rp[c] = qp < famax ? qp / famax : 1.0;
+        } else {
+          rp[c] = 0.0;
+        }
+        if (famin > epsil) {
+          const double qm = (fldlo[c] - fqmin) * hloc[c] * scal[c] * qdt2;
+          rm[c] = qm < famin ? qm / famin : 1.0;
+        } else {
+          rm[c] = 0.0;
+        }
+        fmx[c] = fqmax;
+        fmn[c] = fqmin;
+      }
+  /* :1311-1335 */
+  margin = mbdy_a - 4;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int i = 1 - margin; i <= ii + margin; i++) {
+      const size_t c = IX(i, j);
+      if (SEA_U) {
+        const double fact = fax[c] < 0.0 ? MIN2(rp[IX(i - 1, j)], rm[c])
+                                         : MIN2(rp[c], rm[IX(i - 1, j)]);
+        fax[c] = fact * fax[c];
+      }
+      if (SEA_V) {
+        const double fact = fay[c] < 0.0 ? MIN2(rp[IX(i, j - 1)], rm[c])
+                                         : MIN2(rp[c], rm[IX(i, j - 1)]);
+        fay[c] = fact * fay[c];
+      }
+    }
+  /* :1343-1361 */
+  margin = mbdy_a - 5;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int i = 1 - margin; i <= ii + margin; i++)
+      if (SEA_P) {
+        const size_t c = IX(i, j);
+        flxdiv[c] = ((fax[IX(i + 1, j)] - fax[c]) +
+                     (fay[IX(i, j + 1)] - fay[c])) * dt2 * scali[c];
+        if (hloc[c] > 0.)
+          fld[c] = ((epsil + hloc[c]) * fldlo[c] - flxdiv[c]) / (epsil + hloc[c]);
+        else
+          fld[c] = fldlo[c];
+      }
+  tap(t, "ad:fct2c:fld", fld);
+  free(uloc); free(vloc); free(hloc); free(dtloc); free(ucumdt); free(vcumdt);
+  free(flxcum); free(flycum); free(lcalc);
+}
+
 /* mod_tsadvc.F90:69-205 (lconserve is compile-time .false., :32) */
 int orc_advem(orc_tile *t, int advtyp, double *fld, const double *fldc,
               const double *u, const double *v, const double *fco,
@@ -921,8 +1115,7 @@ int orc_advem(orc_tile *t, int advtyp, double *fld, const double *fldc,
   } else if (advtyp == 1) {
     advem_mpdata(t, fld, u, v, fco, fcn, posdef, scal, scali, dt2);
   } else if (advtyp == 2 && btrmas) {
-    snprintf(g_err, sizeof g_err, "advem_fct2c (btrmas) not restated");
-    return 4;
+    advem_fct2c(t, fld, fldc, u, v, fco, fcn, scal, scali, dt2);
   } else if (advtyp == 2) {
     advem_fct(t, 2, fld, fldc, u, v, fco, fcn, scal, scali, dt2);
   } else if (advtyp == 4) {
