@@ -465,7 +465,11 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     return fail(h, HYCOM_TSADVC_ENBDY,
                 "error: nbdy (dimensions.h) must be at least%3d for the advection scheme indicated by advtyp",
                 mbdy);
-  if (p.btrmas) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "btrmas (advem_fct2c) is not built yet");
+  if (p.btrmas && aadv == 2 && h->d.ipr * h->d.jpr > 1)
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED,
+                "btrmas (advem_fct2c) on more than one tile: the five xctilr inside the scheme are not exchanged yet");
+  if (p.btrmas && aadv != 2)
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "btrmas with advtyp=%d: only advem_fct2c (advtyp=2) reads onetamas here", p.advtyp);
   if (p.isopyc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc (k=1 flux smoothing) is not built yet");
   if (p.mxlmy) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "mxlmy (q2,q2l advection) is not built yet");
   if (p.temdf2 > 0.0) {
@@ -608,6 +612,89 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   return 0;
 }
 
+// advem_fct2c for every field and layer (advtyp=2 with btrmas, mod_tsadvc.F90:96-97,999-1368),
+// single tile: layer batches of whole-tile kernels, the five xctilr of hloc/fldlo by the
+// single-tile halo kernels
+int run_fct2c(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
+              const std::vector<Adv>& adv) {
+  const int kk = h->d.kdm, nf = (int)adv.size();
+  int rc;
+  const char* ce = getenv("HYCOM_TSADVC_FCT2C_BATCH");
+  int nb = ce ? atoi(ce) : 8;
+  if (nb < 1) nb = 1;
+  if (nb > kk) nb = kk;
+  const long nslab = (long)(6 + 5 * nf) * nb;
+  if (!h->fct2c_block || h->fct2c_slabs < nslab || h->fct2c_nb != nb) {
+    if ((rc = dalloc_field(h, &h->fct2c_block, (size_t)nslab * h->slab))) return rc;
+    if ((rc = dalloc(h, (void**)&h->fct2c_lcalc, (size_t)nb * h->slab, true))) return rc;
+    h->fct2c_slabs = nslab; h->fct2c_nb = nb;
+  }
+  Fct2cParams P;
+  memset(&P, 0, sizeof P);
+  for (int f = 0; f < nf; ++f) {
+    double *in, *ctr, *out;
+    if ((rc = slot(h, adv[f].field, adv[f].ktr, n, &in))) return rc;
+    if ((rc = slot(h, adv[f].field, adv[f].ktr, m, &ctr))) return rc;
+    if ((rc = spare_of(h, mirror_of(h, adv[f].field, adv[f].ktr), &out))) return rc;
+    P.fld[f] = in; P.fldc[f] = ctr; P.out[f] = out; P.nlay[f] = adv[f].nlay;
+  }
+  double *u, *v, *dpn, *on;
+  if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &u))) return rc;
+  if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &v))) return rc;
+  if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
+  if ((rc = slot(h, HYCOM_F_ONETA, 0, n, &on))) return rc;
+  P.nf = nf; P.pitch = h->pitch; P.ncols = h->ncols; P.nrows = h->nrows; P.nbdy = h->d.nbdy;
+  P.ii = h->d.ii; P.jj = h->d.jj; P.slab = h->slab;
+  P.mask = h->mask; P.scp2 = h->scp2; P.scp2i = h->scp2i; P.oneta = on;
+  P.u = u; P.v = v; P.dp = dpn; P.dt2 = p.delt1;
+  const long S = h->slab;
+  double* b = h->fct2c_block;
+  P.hloc = b; P.dtloc = b + S * nb; P.ucum = b + 2 * S * nb; P.vcum = b + 3 * S * nb;
+  P.uloc = b + 4 * S * nb; P.vloc = b + 5 * S * nb;
+  double* pf = b + 6 * S * nb;
+  const long F = S * nb * nf;
+  P.fldlo = pf; P.flx = pf + F; P.fly = pf + 2 * F; P.flxcum = pf + 3 * F; P.flycum = pf + 4 * F;
+  P.lcalc = h->fct2c_lcalc;
+  const int nreg = h->d.nreg;
+  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
+  auto launch = [&](int stage) -> int {
+    int r2 = launch_fct2c(stage, P, h->stream);
+    h->launches += 1;
+    if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "fct2c stage %d launch failed: %s", stage,
+                        r2 > 0 ? cudaGetErrorString((cudaError_t)r2) : "bad stage");
+    return 0;
+  };
+  auto halo = [&](double* base, int nslabs) -> int {   // xctilr(a,1,nslabs, 5,5, halo_ps)
+    int r2 = launch_halo_local(base, S, nslabs, h->pitch, h->d.nbdy, h->d.ii, h->d.jj, 5, 5, per_i, per_j,
+                               h->stream);
+    h->launches += 2;
+    if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s", cudaGetErrorString((cudaError_t)r2));
+    return 0;
+  };
+  for (int k0 = 0; k0 < kk; k0 += nb) {
+    P.k0 = k0;
+    P.nb = (k0 + nb <= kk) ? nb : kk - k0;
+    // the per-field slab stride follows the allocated batch size
+    if (P.nb != nb) {   // last, shorter batch: re-point the per-field arrays with the shorter stride
+      const long F2 = S * P.nb * nf;
+      P.dtloc = b + S * P.nb; P.ucum = b + 2 * S * P.nb; P.vcum = b + 3 * S * P.nb;
+      P.uloc = b + 4 * S * P.nb; P.vloc = b + 5 * S * P.nb;
+      double* pf2 = b + 6 * S * P.nb;
+      P.fldlo = pf2; P.flx = pf2 + F2; P.fly = pf2 + 2 * F2; P.flxcum = pf2 + 3 * F2; P.flycum = pf2 + 4 * F2;
+    }
+    // :1072-1086  everything but hloc, fldlo, lcalc starts from 0.0
+    CU(h, cudaMemsetAsync(P.dtloc, 0, sizeof(double) * S * P.nb * 5, h->stream));
+    CU(h, cudaMemsetAsync(P.flx, 0, sizeof(double) * S * P.nb * nf * 4, h->stream));
+    if ((rc = launch(0))) return rc;
+    for (int iter = 1; iter <= 5; ++iter) {   // :1088
+      if ((rc = launch(1)) || (rc = launch(2)) || (rc = launch(3))) return rc;
+      if ((rc = halo(P.hloc, P.nb)) || (rc = halo(P.fldlo, P.nb * nf))) return rc;   // :1186-1187
+    }
+    if ((rc = launch(4)) || (rc = launch(5)) || (rc = launch(6))) return rc;
+  }
+  return 0;
+}
+
 // slot n moves to the ping-pong buffer; salinity range diagnostics (:2065-2094)
 int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
                 const std::vector<Adv>& adv, double* xmin, double* xmax) {
@@ -677,7 +764,8 @@ int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p)
   D.mask = h->mask; D.scp2 = h->scp2; D.aspux = h->aspux; D.aspvy = h->aspvy;
   D.scuy = h->scuy; D.scvx = h->scvx;
   D.slab = h->slab; D.pitch = h->pitch; D.nrows = h->nrows; D.kk = kk;
-  D.nhybrd = nhyb; D.isopyc = p.isopyc; D.sigver = p.sigver;
+  D.nhybrd = nhyb; D.isopyc = p.isopyc;
+  eos::fill(p.sigver, D.eosc);
   D.temdf2 = p.temdf2; D.temdfc = p.temdfc; D.thbase = p.thbase; D.delt1 = p.delt1;
   auto add = [&](int field, int ktr) -> int {
     double *in, *out;
@@ -733,7 +821,11 @@ int hycom_tsadvc_step_device_part(hycom_tsadvc_handle* h, int32_t m, int32_t n,
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_UFLX, 0, 1, mbdy, mbdy))) return rc;
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy))) return rc;
   }
-  if ((rc = run_march(h, m, n, *prm, adv, part))) return rc;
+  if (prm->btrmas && abs(prm->advtyp) == 2) {   // advem_fct2c (:96-97)
+    if ((rc = run_fct2c(h, m, n, *prm, adv))) return rc;
+  } else if ((rc = run_march(h, m, n, *prm, adv, part))) {
+    return rc;
+  }
   if (part == HYCOM_TSADVC_PART_INTERIOR) return 0;
   if ((rc = finish_step(h, n, *prm, adv, xmin, xmax))) return rc;
   // :2138-2230; on a multi-tile handle the caller exchanges first (hycom_tsadvc_diff_halo_*)
@@ -889,6 +981,11 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   const char* ce = getenv("HYCOM_TSADVC_STEP_CHUNK");
   int chunk = ce ? atoi(ce) : 4;
   if (chunk < 1 || chunk > kk) chunk = kk;
+  const bool fct2c = prm->btrmas && abs(prm->advtyp) == 2;   // advem_fct2c: its own layer batches
+  if (fct2c) {
+    if (!oneta) return fail(h, HYCOM_TSADVC_EINVAL, "step: btrmas needs oneta");
+    chunk = kk;
+  }
   const int nchunks = (kk + chunk - 1) / chunk;
   while ((int)h->ev_chunk.size() < 2 * nchunks + 1) {
     cudaEvent_t e;
@@ -954,7 +1051,12 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
       if ((rc = halo_local_range(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy, k0, nk))) return rc;
     }
     // ---- advection of these layers into the ping-pong buffers
-    if ((rc = run_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_ALL, k0, nk))) return rc;
+    if (fct2c) {   // onetamas(:,:,m) = oneta(:,:,n) (:1806)
+      if ((rc = upload_on(h, HYCOM_F_ONETA, 0, n, 1, 1, oneta + fs * (n - 1), h->stream))) return rc;
+      if ((rc = run_fct2c(h, m, n, *prm, adv))) return rc;
+    } else if ((rc = run_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_ALL, k0, nk))) {
+      return rc;
+    }
     if (diffuse) continue;   // the diffusion needs every layer's neighbours first: copy out after it
     CU(h, cudaEventRecord(h->ev_chunk[2 * c + 1], h->stream));
     CU(h, cudaStreamWaitEvent(h->down_stream, h->ev_chunk[2 * c + 1], 0));

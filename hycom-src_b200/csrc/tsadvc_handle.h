@@ -41,6 +41,11 @@ struct hycom_tsadvc_handle {
   // every field buffer is allocated with one guard row in front and behind (the bulk copies
   // of the first/last strip start 4 columns before / end after their row); freed from here
   std::vector<void*> raw_allocs;
+  // advem_fct2c scratch (btrmas): one block of (6 + 5*nf)*nb slabs + nb byte slabs
+  double* fct2c_block = nullptr;
+  uint8_t* fct2c_lcalc = nullptr;
+  long fct2c_slabs = 0;
+  int fct2c_nb = 0;
   double* d_minmax = nullptr;  // 2*kdm
   uint8_t* d_sea = nullptr;    // synthetic generator: global sea mask
   // optional per-launch timing of the marching kernel (hycom_tsadvc_set_timing)

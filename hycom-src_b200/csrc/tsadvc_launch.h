@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "eos.cuh"
 #include "tsadvc_dev.h"
 
 namespace tsadvc {
@@ -108,10 +109,39 @@ struct DiffParams {
   const double *scp2, *aspux, *aspvy, *scuy, *scvx;
   long slab;
   int pitch, nrows, kk;
-  int nhybrd, isopyc, sigver;
+  int nhybrd, isopyc;
+  eos::Coef eosc;        // equation of state `sigver` of the host model (stmt_fns.h)
   double temdf2, temdfc, thbase, delt1;
 };
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream);
+
+}  // namespace tsadvc
+
+// ---- advem_fct2c (btrmas), fct2c.cu ------------------------------------------------------
+namespace tsadvc {
+
+// one batch of nb layers starting at layer k0 (0-based), every advected field
+struct Fct2cParams {
+  const double* fld[kMaxFields];    // (:,:,1,n)  time level t-1
+  const double* fldc[kMaxFields];   // (:,:,1,m)  time level t
+  double* out[kMaxFields];          // ping-pong buffer of (:,:,1,n)
+  int nlay[kMaxFields];             // layers 1..nlay of the field are advected
+  int nf, k0, nb;
+  int pitch, ncols, nrows, nbdy, ii, jj;
+  long slab;
+  const uint8_t* mask;
+  const double *scp2, *scp2i, *oneta;   // oneta(:,:,n): onetamas(:,:,m) when btrmas (:1806)
+  const double *u, *v, *dp;             // uflx(:,:,1), vflx(:,:,1), dp(:,:,1,n)
+  double dt2;
+  // scratch, per layer of the batch: [nb] slabs
+  double *hloc, *dtloc, *ucum, *vcum, *uloc, *vloc;
+  uint8_t* lcalc;
+  // scratch, per field and layer: [nf][nb] slabs
+  double *fldlo, *flx, *fly, *flxcum, *flycum;
+};
+
+// stage 0 init, 1 dtloc, 2 faces, 3 cells, 4 fax/fay, 5 rp/rm, 6 final update
+int launch_fct2c(int stage, const Fct2cParams& P, cudaStream_t stream);
 
 }  // namespace tsadvc

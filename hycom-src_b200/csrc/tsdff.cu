@@ -63,32 +63,35 @@ __global__ void __launch_bounds__(256, 3) k_tsdff(const DiffParams P) {
   const bool fe = P.mask[q + 1] & M_IU, fn = P.mask[q + P.pitch] & M_IV;
   const long qw = q - 1, qe = q + 1, qs = q - P.pitch, qn = q + P.pitch;
   // temdf2*aspux(i,j)*scuy(i,j) and temdf2*aspvy(i,j)*scvx(i,j): left to right as written
-  const double aw = fw ? P.temdf2 * P.aspux[q] * P.scuy[q] : 0.0;
-  const double ae = fe ? P.temdf2 * P.aspux[qe] * P.scuy[qe] : 0.0;
-  const double as = fs ? P.temdf2 * P.aspvy[q] * P.scvx[q] : 0.0;
-  const double an = fn ? P.temdf2 * P.aspvy[qn] * P.scvx[qn] : 0.0;
+  const double aw = P.temdf2 * P.aspux[q] * P.scuy[q];
+  const double ae = P.temdf2 * P.aspux[qe] * P.scuy[qe];
+  const double as = P.temdf2 * P.aspvy[q] * P.scvx[q];
+  const double an = P.temdf2 * P.aspvy[qn] * P.scvx[qn];
   const double oc = P.oneta[q];
-  const double ow = fw ? P.oneta[qw] : 0.0, oe = fe ? P.oneta[qe] : 0.0;
-  const double os = fs ? P.oneta[qs] : 0.0, on = fn ? P.oneta[qn] : 0.0;
+  const double ow = P.oneta[qw], oe = P.oneta[qe], os = P.oneta[qs], on = P.oneta[qn];
   const double scp2 = P.scp2[q];
+  // every neighbour of a cell tsadvc writes exists in the slab, so all loads are unconditional
+  // (issued together, read-only path) and land neighbours are removed by select afterwards
 #pragma unroll 2
   for (int k0 = 0; k0 < P.kk; ++k0) {
     const long ko = (long)k0 * P.slab;
     const long qk = q + ko;
     const double* dp = P.dp + ko;
-    const double hc = dp[q] * oc;
-    double gw = 0.0, ge = 0.0, gs = 0.0, gn = 0.0;
-    if (fw) gw = aw * harmonc(dp[qw] * ow, hc);
-    if (fe) ge = ae * harmonc(hc, dp[qe] * oe);
-    if (fs) gs = as * harmonc(dp[qs] * os, hc);
-    if (fn) gn = an * harmonc(hc, dp[qn] * on);
+    const double dc = __ldg(dp + q), dw = __ldg(dp + qw), de = __ldg(dp + qe), ds = __ldg(dp + qs),
+                 dn = __ldg(dp + qn);
+    const double hc = dc * oc;
+    const double gw = fw ? aw * harmonc(dw * ow, hc) : 0.0;
+    const double ge = fe ? ae * harmonc(hc, de * oe) : 0.0;
+    const double gs = fs ? as * harmonc(ds * os, hc) : 0.0;
+    const double gn = fn ? an * harmonc(hc, dn * on) : 0.0;
     const double factor = div_rn(-P.delt1, scp2 * dmax(hc, 1.0e-20));   // :2314-2315
     // one field: the divergence of the four face fluxes applied to the centre value
     auto diffuse = [&](const double* __restrict__ a, double x) {
-      const double uw = fw ? gw * (a[qw] - x) : 0.0;
-      const double ue = fe ? ge * (x - a[qe]) : 0.0;
-      const double vs = fs ? gs * (a[qs] - x) : 0.0;
-      const double vn = fn ? gn * (x - a[qn]) : 0.0;
+      const double xw = __ldg(a + qw), xe = __ldg(a + qe), xs = __ldg(a + qs), xn = __ldg(a + qn);
+      const double uw = fw ? gw * (xw - x) : 0.0;
+      const double ue = fe ? ge * (x - xe) : 0.0;
+      const double vs = fs ? gs * (xs - x) : 0.0;
+      const double vn = fn ? gn * (x - xn) : 0.0;
       const double util = ((ue - uw) + (vn - vs)) * factor;
       return x + util;
     };
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(256, 3) k_tsdff(const DiffParams P) {
 #pragma unroll 1
       for (int f = 0; f < P.nf; ++f) {
         const double* a = P.f[f].in + ko;
-        P.f[f].out[qk] = diffuse(a, a[q]);
+        P.f[f].out[qk] = diffuse(a, __ldg(a + q));
       }
       continue;
     }
@@ -108,23 +111,24 @@ __global__ void __launch_bounds__(256, 3) k_tsdff(const DiffParams P) {
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
       const double* a = P.f[f].in + ko;
-      const double x = a[q];
+      const double x = __ldg(a + q);
       const bool on_ = f == 1 || (f == 0 ? ldtemp : ldth3d);
-      v[f] = on_ ? diffuse(a, x) : x;
+      const double y = diffuse(a, x);
+      v[f] = on_ ? y : x;
     }
     {   // :2199-2229
       double t = v[0], s = v[1], h = v[2];
       if (ldtemp && ldth3d) {
-        const double th3d_t = eos::sig(P.sigver, t, s) - P.thbase;
+        const double th3d_t = eos::sig(P.eosc, t, s) - P.thbase;
         h = (1.0 - P.temdfc) * h + P.temdfc * th3d_t;
-        t = eos::tofsig(P.sigver, h + P.thbase, s);
+        t = eos::tofsig(P.eosc, h + P.thbase, s);
       } else if (ldtemp) {
-        h = eos::sig(P.sigver, t, s) - P.thbase;
+        h = eos::sig(P.eosc, t, s) - P.thbase;
       } else if (ldth3d) {
-        t = eos::tofsig(P.sigver, h + P.thbase, s);
+        t = eos::tofsig(P.eosc, h + P.thbase, s);
       } else {
         h = P.theta[qk];
-        t = eos::tofsig(P.sigver, h + P.thbase, s);
+        t = eos::tofsig(P.eosc, h + P.thbase, s);
       }
       P.f[0].out[qk] = t;
       P.f[1].out[qk] = s;

@@ -180,6 +180,8 @@ class Tsadvc:
         self.upload(cabi.F_DP, cb.dp[n - 1], n)
         self.upload(cabi.F_UFLX, cb.uflx, 1)
         self.upload(cabi.F_VFLX, cb.vflx, 1)
+        if cb.btrmas:          # onetamas(:,:,m) = oneta(:,:,n) (mod_tsadvc.F90:1806)
+            self.upload(cabi.F_ONETA, cb.oneta[n - 1], n)
         if cb.temdf2 > 0.0:   # operands of the diffusion part (mod_tsadvc.F90:2138-2230)
             other, of = (cb.temp, cabi.F_TEMP) if cb.advflg else (cb.th3d, cabi.F_TH3D)
             self.upload(of, other[n - 1], n)

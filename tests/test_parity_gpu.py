@@ -441,3 +441,58 @@ def _tile_window(a, g1, g, nreg):
     is_ = slice(ii0, min(ii0 + g.ncols, g1.ncols))
     out[..., : js.stop - js.start, : is_.stop - is_.start] = a[..., js, is_]
     return out
+
+
+# ---------------------------------------------------------------------------------------
+# btrmas: advem_fct2c (mod_tsadvc.F90:999-1368), five sub-cycled low-order iterations
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,ntracr,extra", [
+    (150, 150, 22, 0, 0, {}),             # box basin: three layer batches (8 + 8 + 6)
+    (131, 77, 3, 3, 1, {}),               # doubly periodic: sea halo cells, margins 5..0 all matter
+    (64, 203, 2, 1, 0, {}),
+    (200, 60, 2, 4, 1, {}),
+    (58, 31, 10, 0, 1, {"nhybrd": 4}),    # temp advected in the top layers only; batch 8 + 2
+    (9, 8, 2, 0, 0, {}),
+    (70, 45, 3, 0, 0, {"advflg": 1}),
+])
+def test_fct2c_host_path_matches_oracle(oracle, itdm, jtdm, kdm, nreg, ntracr, extra):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=23, m=m, n=n,
+                                     advtyp=2, btrmas=True, nstep=3, **extra)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    got, before, launches = _run_host_path(cb, m, n)
+    names = ["saln"] + (["th3d"] if cb.advflg else ["temp"])
+    _compare(cb, g, got, ref, n, names)
+    for q in range(ntracr):
+        _compare(cb, g, {"t": got["tracer"][q]}, {"t": ref["tracer"][q]}, n, ["t"])
+    msk = util.interior_sea(cb)
+    for name in names:
+        a, b = got[name], before[name]
+        assert np.array_equal(a[m - 1], b[m - 1], equal_nan=True), (name, "slot m modified")
+        assert np.array_equal(a[n - 1][:, ~msk], b[n - 1][:, ~msk], equal_nan=True), (name, "land/halo modified")
+    assert np.array_equal(got["xmin"], ref["xmin"]) and np.array_equal(got["xmax"], ref["xmax"])
+    assert not np.array_equal(got["saln"][n - 1, 0][msk], before["saln"][n - 1, 0][msk])
+
+
+def test_fct2c_device_path_two_steps(oracle):
+    """device-resident mirrors, two leapfrog steps with swapped slots"""
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(90, 70, 3, nreg=0, seed=21, m=m, n=n, advtyp=2, btrmas=True)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_state(m, n)
+    ts.upload(cabi.F_DP, cb.dp[m - 1], m)
+    ts.upload(cabi.F_ONETA, cb.oneta[m - 1], m)
+    ot.tsadvc(m, n, 1)
+    ts.tsadvc_device(m, n)
+    ot.tsadvc(n, m, 1)
+    ts.tsadvc_device(n, m)
+    msk = util.interior_sea(cb)
+    for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+        for slot in (1, 2):
+            dev = ts.download(fld, slot)
+            ref = ot.f64(name)[slot - 1]
+            for k in range(g.kdm):
+                assert np.array_equal(dev[k][msk], ref[k][msk]), (name, slot, k)
+    ts.close()
+    ot.close()
