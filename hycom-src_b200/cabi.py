@@ -91,6 +91,14 @@ PROTOTYPES = {
                                            C.POINTER(_vp * 8), _vp]),
     "hycom_tsadvc_step_device_part": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params),
                                                 C.c_int32, _vp, _vp]),
+    "hycom_tsadvc_fct2c_batches": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hycom_tsadvc_fct2c_stage": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params), C.c_int32, C.c_int32]),
+    "hycom_tsadvc_fct2c_halo_counts": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params), C.c_int32,
+                                                 C.POINTER(C.c_int64 * 8)]),
+    "hycom_tsadvc_fct2c_halo_pack": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params), C.c_int32,
+                                               C.POINTER(_vp * 8), _vp]),
+    "hycom_tsadvc_fct2c_halo_unpack": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params), C.c_int32,
+                                                 C.POINTER(_vp * 8), _vp]),
     "hycom_tsadvc_diff_halo_counts": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(C.c_int64 * 8)]),
     "hycom_tsadvc_diff_halo_pack": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(_vp * 8), _vp]),
     "hycom_tsadvc_diff_halo_unpack": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(_vp * 8), _vp]),

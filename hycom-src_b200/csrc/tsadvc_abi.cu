@@ -465,9 +465,6 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     return fail(h, HYCOM_TSADVC_ENBDY,
                 "error: nbdy (dimensions.h) must be at least%3d for the advection scheme indicated by advtyp",
                 mbdy);
-  if (p.btrmas && aadv == 2 && h->d.ipr * h->d.jpr > 1)
-    return fail(h, HYCOM_TSADVC_EUNSUPPORTED,
-                "btrmas (advem_fct2c) on more than one tile: the five xctilr inside the scheme are not exchanged yet");
   if (p.btrmas && aadv != 2)
     return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "btrmas with advtyp=%d: only advem_fct2c (advtyp=2) reads onetamas here", p.advtyp);
   if (p.isopyc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc (k=1 flux smoothing) is not built yet");
@@ -612,24 +609,29 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   return 0;
 }
 
-// advem_fct2c for every field and layer (advtyp=2 with btrmas, mod_tsadvc.F90:96-97,999-1368),
-// single tile: layer batches of whole-tile kernels, the five xctilr of hloc/fldlo by the
-// single-tile halo kernels
-int run_fct2c(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
-              const std::vector<Adv>& adv) {
-  const int kk = h->d.kdm, nf = (int)adv.size();
-  int rc;
+// ---- advem_fct2c (advtyp=2 with btrmas, mod_tsadvc.F90:96-97, 999-1368) -------------------
+// Layer batches of whole-tile kernels.  The scheme exchanges hloc and fldlo after each of its
+// five iterations (:1186-1187): on a single tile the halo kernels do that, on several tiles
+// the caller does (hycom_tsadvc_fct2c_stage / _halo_pack / _halo_unpack).
+int fct2c_batch_layers(const hycom_tsadvc_handle* h) {
   const char* ce = getenv("HYCOM_TSADVC_FCT2C_BATCH");
   int nb = ce ? atoi(ce) : 8;
   if (nb < 1) nb = 1;
-  if (nb > kk) nb = kk;
+  return nb > h->d.kdm ? h->d.kdm : nb;
+}
+
+int fct2c_params(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
+                 const std::vector<Adv>& adv, int batch, Fct2cParams& P) {
+  const int kk = h->d.kdm, nf = (int)adv.size();
+  int rc;
+  const int nb = fct2c_batch_layers(h);
+  if (batch < 0 || batch * nb >= kk) return fail(h, HYCOM_TSADVC_EINVAL, "fct2c: bad layer batch %d", batch);
   const long nslab = (long)(6 + 5 * nf) * nb;
   if (!h->fct2c_block || h->fct2c_slabs < nslab || h->fct2c_nb != nb) {
     if ((rc = dalloc_field(h, &h->fct2c_block, (size_t)nslab * h->slab))) return rc;
     if ((rc = dalloc(h, (void**)&h->fct2c_lcalc, (size_t)nb * h->slab, true))) return rc;
     h->fct2c_slabs = nslab; h->fct2c_nb = nb;
   }
-  Fct2cParams P;
   memset(&P, 0, sizeof P);
   for (int f = 0; f < nf; ++f) {
     double *in, *ctr, *out;
@@ -647,50 +649,74 @@ int run_fct2c(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   P.ii = h->d.ii; P.jj = h->d.jj; P.slab = h->slab;
   P.mask = h->mask; P.scp2 = h->scp2; P.scp2i = h->scp2i; P.oneta = on;
   P.u = u; P.v = v; P.dp = dpn; P.dt2 = p.delt1;
-  const long S = h->slab;
+  P.k0 = batch * nb;
+  P.nb = (P.k0 + nb <= kk) ? nb : kk - P.k0;
+  // scratch: [hloc | dtloc | ucum | vcum | uloc | vloc] of P.nb slabs each, then
+  // [fldlo | flx | fly | flxcum | flycum] of nf*P.nb slabs each (a shorter last batch packs tighter)
+  const long S = h->slab, L = S * P.nb, F = L * nf;
   double* b = h->fct2c_block;
-  P.hloc = b; P.dtloc = b + S * nb; P.ucum = b + 2 * S * nb; P.vcum = b + 3 * S * nb;
-  P.uloc = b + 4 * S * nb; P.vloc = b + 5 * S * nb;
-  double* pf = b + 6 * S * nb;
-  const long F = S * nb * nf;
+  P.hloc = b; P.dtloc = b + L; P.ucum = b + 2 * L; P.vcum = b + 3 * L; P.uloc = b + 4 * L; P.vloc = b + 5 * L;
+  double* pf = b + 6 * L;
   P.fldlo = pf; P.flx = pf + F; P.fly = pf + 2 * F; P.flxcum = pf + 3 * F; P.flycum = pf + 4 * F;
   P.lcalc = h->fct2c_lcalc;
-  const int nreg = h->d.nreg;
-  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
-  auto launch = [&](int stage) -> int {
-    int r2 = launch_fct2c(stage, P, h->stream);
+  return 0;
+}
+
+// stage 0: :1072-1086; stage 1: one iteration :1090-1184 (without its xctilr); stage 2: :1202-1361
+int fct2c_stage(hycom_tsadvc_handle* h, const Fct2cParams& P, int stage) {
+  int rc;
+  auto launch = [&](int st) -> int {
+    int r2 = launch_fct2c(st, P, h->stream);
     h->launches += 1;
-    if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "fct2c stage %d launch failed: %s", stage,
+    if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "fct2c kernel %d launch failed: %s", st,
                         r2 > 0 ? cudaGetErrorString((cudaError_t)r2) : "bad stage");
     return 0;
   };
-  auto halo = [&](double* base, int nslabs) -> int {   // xctilr(a,1,nslabs, 5,5, halo_ps)
-    int r2 = launch_halo_local(base, S, nslabs, h->pitch, h->d.nbdy, h->d.ii, h->d.jj, 5, 5, per_i, per_j,
-                               h->stream);
-    h->launches += 2;
-    if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s", cudaGetErrorString((cudaError_t)r2));
+  const long L = P.slab * P.nb;
+  if (stage == 0) {   // everything but hloc, fldlo, lcalc starts from 0.0
+    CU(h, cudaMemsetAsync(P.dtloc, 0, sizeof(double) * L * 5, h->stream));
+    CU(h, cudaMemsetAsync(P.flx, 0, sizeof(double) * L * P.nf * 4, h->stream));
+    return launch(0);
+  }
+  if (stage == 1) {
+    if ((rc = launch(1)) || (rc = launch(2)) || (rc = launch(3))) return rc;
     return 0;
-  };
-  for (int k0 = 0; k0 < kk; k0 += nb) {
-    P.k0 = k0;
-    P.nb = (k0 + nb <= kk) ? nb : kk - k0;
-    // the per-field slab stride follows the allocated batch size
-    if (P.nb != nb) {   // last, shorter batch: re-point the per-field arrays with the shorter stride
-      const long F2 = S * P.nb * nf;
-      P.dtloc = b + S * P.nb; P.ucum = b + 2 * S * P.nb; P.vcum = b + 3 * S * P.nb;
-      P.uloc = b + 4 * S * P.nb; P.vloc = b + 5 * S * P.nb;
-      double* pf2 = b + 6 * S * P.nb;
-      P.fldlo = pf2; P.flx = pf2 + F2; P.fly = pf2 + 2 * F2; P.flxcum = pf2 + 3 * F2; P.flycum = pf2 + 4 * F2;
-    }
-    // :1072-1086  everything but hloc, fldlo, lcalc starts from 0.0
-    CU(h, cudaMemsetAsync(P.dtloc, 0, sizeof(double) * S * P.nb * 5, h->stream));
-    CU(h, cudaMemsetAsync(P.flx, 0, sizeof(double) * S * P.nb * nf * 4, h->stream));
-    if ((rc = launch(0))) return rc;
+  }
+  if ((rc = launch(4)) || (rc = launch(5)) || (rc = launch(6))) return rc;
+  return 0;
+}
+
+// hloc and fldlo of the batch as the arrays of one exchange, halo width 5 (:1186-1187)
+void fct2c_halo_arrays(const hycom_tsadvc_handle* h, const Fct2cParams& P, HaloArrays& a) {
+  memset(&a, 0, sizeof a);
+  a.base[a.narr++] = P.hloc;
+  for (int f = 0; f < P.nf; ++f) a.base[a.narr++] = P.fldlo + (long)f * P.nb * P.slab;
+  a.kk = P.nb; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+  a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 5; a.nh = 5;
+}
+
+// the whole scheme on a single tile
+int run_fct2c(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
+              const std::vector<Adv>& adv) {
+  const int kk = h->d.kdm, nb = fct2c_batch_layers(h);
+  const int nreg = h->d.nreg;
+  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
+  int rc;
+  for (int batch = 0; batch * nb < kk; ++batch) {
+    Fct2cParams P;
+    if ((rc = fct2c_params(h, m, n, p, adv, batch, P))) return rc;
+    if ((rc = fct2c_stage(h, P, 0))) return rc;
     for (int iter = 1; iter <= 5; ++iter) {   // :1088
-      if ((rc = launch(1)) || (rc = launch(2)) || (rc = launch(3))) return rc;
-      if ((rc = halo(P.hloc, P.nb)) || (rc = halo(P.fldlo, P.nb * nf))) return rc;   // :1186-1187
+      if ((rc = fct2c_stage(h, P, 1))) return rc;
+      // xctilr(hloc), xctilr(fldlo): hloc and the fldlo stack are contiguous slabs
+      for (int q = 0; q < 2; ++q) {
+        int r2 = launch_halo_local(q ? P.fldlo : P.hloc, h->slab, q ? P.nb * P.nf : P.nb, h->pitch, h->d.nbdy,
+                                   h->d.ii, h->d.jj, 5, 5, per_i, per_j, h->stream);
+        h->launches += 2;
+        if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s", cudaGetErrorString((cudaError_t)r2));
+      }
     }
-    if ((rc = launch(4)) || (rc = launch(5)) || (rc = launch(6))) return rc;
+    if ((rc = fct2c_stage(h, P, 2))) return rc;
   }
   return 0;
 }
@@ -822,7 +848,9 @@ int hycom_tsadvc_step_device_part(hycom_tsadvc_handle* h, int32_t m, int32_t n,
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy))) return rc;
   }
   if (prm->btrmas && abs(prm->advtyp) == 2) {   // advem_fct2c (:96-97)
-    if ((rc = run_fct2c(h, m, n, *prm, adv))) return rc;
+    if (part == HYCOM_TSADVC_PART_INTERIOR) return 0;   // no overlap: the scheme exchanges five times itself
+    // several tiles: the caller has driven hycom_tsadvc_fct2c_stage + exchanges; this call finishes the step
+    if (h->d.ipr * h->d.jpr == 1 && (rc = run_fct2c(h, m, n, *prm, adv))) return rc;
   } else if ((rc = run_march(h, m, n, *prm, adv, part))) {
     return rc;
   }
@@ -849,6 +877,69 @@ int hycom_tsadvc_diffuse_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
       if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TRACER, t, n, mdf, mdf))) return rc;
   }
   return run_diffuse(h, n, *prm);
+}
+
+int hycom_tsadvc_fct2c_batches(hycom_tsadvc_handle* h, int32_t* nbatch, int32_t* layers_per_batch) {
+  if (!h || !nbatch) return fail(h, HYCOM_TSADVC_EINVAL, "fct2c_batches: null argument");
+  const int nb = fct2c_batch_layers(h);
+  *nbatch = (h->d.kdm + nb - 1) / nb;
+  if (layers_per_batch) *layers_per_batch = nb;
+  return 0;
+}
+
+int hycom_tsadvc_fct2c_stage(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                             int32_t batch, int32_t stage) {
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  if (!(prm->btrmas && abs(prm->advtyp) == 2)) return fail(h, HYCOM_TSADVC_EINVAL, "fct2c_stage: needs advtyp=2 and btrmas");
+  if (stage < 0 || stage > 2) return fail(h, HYCOM_TSADVC_EINVAL, "fct2c_stage: bad stage %d", stage);
+  CU(h, cudaSetDevice(h->d.device));
+  Fct2cParams P;
+  if ((rc = fct2c_params(h, m, n, *prm, adv, batch, P))) return rc;
+  return fct2c_stage(h, P, stage);
+}
+
+static int fct2c_halo_xfer(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                           int32_t batch, double* const buf[8], int64_t* count, void* cuda_stream, int mode) {
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  CU(h, cudaSetDevice(h->d.device));
+  Fct2cParams P;
+  if ((rc = fct2c_params(h, m, n, *prm, adv, batch, P))) return rc;
+  HaloArrays a;
+  fct2c_halo_arrays(h, P, a);
+  if (mode == 0) {
+    for (int d = 0; d < 8; ++d) {
+      int w, hh, c0, r0;
+      halo_region(a, d, false, w, hh, c0, r0);
+      count[d] = (int64_t)w * hh * a.narr * a.kk;
+    }
+    return 0;
+  }
+  if (!buf) return fail(h, HYCOM_TSADVC_EINVAL, "fct2c halo: null buffer table");
+  HaloBufs b;
+  for (int d = 0; d < 8; ++d) { b.buf[d] = buf[d]; b.count[d] = 0; }
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  rc = mode == 1 ? launch_halo_pack(a, b, st) : launch_halo_unpack(a, b, st);
+  h->launches += 1;
+  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "halo kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return 0;
+}
+
+int hycom_tsadvc_fct2c_halo_counts(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                                   const hycom_tsadvc_params* prm, int32_t batch, int64_t count[8]) {
+  if (!count) return fail(h, HYCOM_TSADVC_EINVAL, "fct2c_halo_counts: null argument");
+  return fct2c_halo_xfer(h, m, n, prm, batch, nullptr, count, nullptr, 0);
+}
+int hycom_tsadvc_fct2c_halo_pack(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                                 int32_t batch, double* const sendbuf[8], void* cuda_stream) {
+  return fct2c_halo_xfer(h, m, n, prm, batch, sendbuf, nullptr, cuda_stream, 1);
+}
+int hycom_tsadvc_fct2c_halo_unpack(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                                   int32_t batch, double* const recvbuf[8], void* cuda_stream) {
+  return fct2c_halo_xfer(h, m, n, prm, batch, recvbuf, nullptr, cuda_stream, 2);
 }
 
 int hycom_tsadvc_diff_halo_counts(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params* prm,

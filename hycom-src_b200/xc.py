@@ -99,6 +99,26 @@ class DeviceHaloBackend:
                                                         C.c_void_p(stream) if stream else None))
 
 
+    # -- the exchanges inside advem_fct2c (btrmas, mod_tsadvc.F90:1186-1187): hloc and fldlo of one
+    # -- layer batch, width 5
+    def fct2c_counts(self, m, n, batch):
+        cnt = (C.c_int64 * 8)()
+        p = self.ts.cb.params()
+        self.ts._ck(self.ts.lib.hycom_tsadvc_fct2c_halo_counts(self.ts.h, m, n, C.byref(p), batch, C.byref(cnt)))
+        return [int(c) for c in cnt]
+
+    def fct2c_pack(self, m, n, batch, send, stream=None):
+        p = self.ts.cb.params()
+        self.ts._ck(self.ts.lib.hycom_tsadvc_fct2c_halo_pack(self.ts.h, m, n, C.byref(p), batch,
+                                                            C.byref(self._table(send)),
+                                                            C.c_void_p(stream) if stream else None))
+
+    def fct2c_unpack(self, m, n, batch, recv, stream=None):
+        p = self.ts.cb.params()
+        self.ts._ck(self.ts.lib.hycom_tsadvc_fct2c_halo_unpack(self.ts.h, m, n, C.byref(p), batch,
+                                                              C.byref(self._table(recv)),
+                                                              C.c_void_p(stream) if stream else None))
+
     # -- the second exchange of tsadvc (temdf2 > 0, mod_tsadvc.F90:2140-2151): slot n, width 2
     def diff_counts(self, n):
         cnt = (C.c_int64 * 8)()
@@ -226,7 +246,12 @@ class XcExchange:
         xm = ts.xmin.ctypes.data_as(C.c_void_p) if diag else None
         xx = ts.xmax.ctypes.data_as(C.c_void_p) if diag else None
         pending = self.start(m, n)
-        if overlap:
+        if ts.cb.btrmas and abs(ts.cb.advtyp) == 2:
+            # advem_fct2c exchanges hloc/fldlo after each of its five iterations: no interior overlap
+            self.finish(m, n, pending)
+            self._fct2c(m, n, p)
+            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, xm, xx))
+        elif overlap:
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_INTERIOR, None, None))
             self.finish(m, n, pending)
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_FRAME, xm, xx))
@@ -238,6 +263,48 @@ class XcExchange:
         if ts.cb.temdf2 > 0.0:   # mod_tsadvc.F90:2138-2230: second exchange (width 2), then tsdff + EOS
             self.xctilr_diff(n)
             ts._ck(ts.lib.hycom_tsadvc_diffuse_device(ts.h, m, n, C.byref(p)))
+
+    def _exchange(self, key, counts, pack, unpack):
+        """one blocking exchange of a set of device arrays (buffers and P2P ops cached per key)"""
+        if key not in self._bufs:
+            cnt = counts()
+            send = [self.backend.alloc(c) if self.nbr[d] >= 0 else None for d, c in enumerate(cnt)]
+            recv: List = [None] * 8
+            for d, c in enumerate(cnt):
+                if self.nbr[d] >= 0:
+                    recv[d] = send[OPP[d]] if self.nbr[d] == self.rank else self.backend.alloc(c)
+            self._bufs[key] = (send, recv, self.ops(send, recv))
+        send, recv, ops = self._bufs[key]
+        cs = self.comm_stream
+        if cs is not None:
+            cs.wait_stream(self._compute())
+            with self.torch.cuda.stream(cs):
+                pack(send, cs.cuda_stream)
+                for w in (self.dist.batch_isend_irecv(ops) if ops else []):
+                    w.wait()
+                unpack(recv, cs.cuda_stream)
+            self._compute().wait_stream(cs)
+        else:
+            pack(send, None)
+            for w in (self.dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+            unpack(recv, None)
+
+    def _fct2c(self, m, n, p):
+        """advem_fct2c on several tiles: per layer batch, set-up, five iterations each followed by
+        xctilr(hloc), xctilr(fldlo) (mod_tsadvc.F90:1088-1187), then the limiter and the update"""
+        ts, be = self.ts, self.backend
+        nbatch, per = C.c_int32(0), C.c_int32(0)
+        ts._ck(ts.lib.hycom_tsadvc_fct2c_batches(ts.h, C.byref(nbatch), C.byref(per)))
+        for b in range(nbatch.value):
+            ts._ck(ts.lib.hycom_tsadvc_fct2c_stage(ts.h, m, n, C.byref(p), b, 0))
+            for _ in range(5):
+                ts._ck(ts.lib.hycom_tsadvc_fct2c_stage(ts.h, m, n, C.byref(p), b, 1))
+                self._exchange(("fct2c", m, n, b, ts.cb.ntracr),
+                               lambda: be.fct2c_counts(m, n, b),
+                               lambda send, st: be.fct2c_pack(m, n, b, send, st),
+                               lambda recv, st: be.fct2c_unpack(m, n, b, recv, st))
+            ts._ck(ts.lib.hycom_tsadvc_fct2c_stage(ts.h, m, n, C.byref(p), b, 2))
 
     def xctilr_diff(self, n):
         """xctilr(saln|temp|th3d|tracer(:,:,:,n), 1,kk, 2,2, halo_ps) of mod_tsadvc.F90:2140-2151"""

@@ -195,6 +195,32 @@ int hycom_tsadvc_step_device_part(hycom_tsadvc_handle *h, int32_t m, int32_t n,
                                   const hycom_tsadvc_params *prm, int32_t part,
                                   double *xmin, double *xmax);
 
+/* ---- advem_fct2c on several tiles (advtyp = 2 with btrmas, mod_tsadvc.F90:96-97, 999-1368) ---
+ * The scheme calls xctilr(hloc) and xctilr(fldlo) after each of its five iterations
+ * (:1186-1187).  A single-tile handle does that inside hycom_tsadvc_step_device; on several
+ * tiles the caller drives the scheme per layer batch between the first exchange
+ * (hycom_tsadvc_halo_*) and hycom_tsadvc_step_device_part(PART_ALL), which then only finishes
+ * the step (time-level switch, diagnostics):
+ *     for batch in 0..nbatch-1:  stage 0;  5 x { stage 1; fct2c_halo_pack -> transport ->
+ *                                fct2c_halo_unpack };  stage 2
+ * A message is [array][k][row][col] over hloc and fldlo of every advected field, the layers
+ * of the batch, halo width 5. */
+int hycom_tsadvc_fct2c_batches(hycom_tsadvc_handle *h, int32_t *nbatch,
+                               int32_t *layers_per_batch);
+/* stage 0: :1072-1086 (set-up); 1: one iteration :1090-1184 without its xctilr;
+ * 2: :1202-1361 (antidiffusive fluxes, limiter, update) */
+int hycom_tsadvc_fct2c_stage(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                             const hycom_tsadvc_params *prm, int32_t batch, int32_t stage);
+int hycom_tsadvc_fct2c_halo_counts(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                                   const hycom_tsadvc_params *prm, int32_t batch,
+                                   int64_t count[8]);
+int hycom_tsadvc_fct2c_halo_pack(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                                 const hycom_tsadvc_params *prm, int32_t batch,
+                                 double *const sendbuf[8], void *cuda_stream);
+int hycom_tsadvc_fct2c_halo_unpack(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                                   const hycom_tsadvc_params *prm, int32_t batch,
+                                   double *const recvbuf[8], void *cuda_stream);
+
 /* ---- diffusion part of tsadvc(m,n) (temdf2 > 0, mod_tsadvc.F90:2138-2230) ---------------
  * On a single tile hycom_tsadvc_step_device / _part(PART_ALL|PART_FRAME) run it themselves.
  * On a multi-tile handle the caller repeats the reference's second exchange

@@ -496,3 +496,65 @@ def test_fct2c_device_path_two_steps(oracle):
                 assert np.array_equal(dev[k][msk], ref[k][msk]), (name, slot, k)
     ts.close()
     ot.close()
+
+
+@pytest.mark.parametrize("ipr,jpr,nreg,ntracr,kdm", [(2, 2, 0, 1, 3), (2, 1, 3, 0, 10), (1, 2, 1, 0, 2)])
+def test_fct2c_tiling_invariance_on_device(oracle, ipr, jpr, nreg, ntracr, kdm):
+    """advem_fct2c on N tiles, the five in-scheme exchanges done between the tiles of one process,
+    == the oracle on 1 tile, bit for bit"""
+    xc = __import__("importlib").import_module("hycom-src_b200.xc")
+    m, n = 1, 2
+    itdm, jtdm = 150, 120
+    cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=5, m=m, n=n,
+                                       advtyp=2, btrmas=True, nstep=3)
+    ref = util.run_oracle(oracle, cb1, sea, m, n)
+    nb = g1.nbdy
+    tss = []
+    for g in pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg):
+        cb = syn.build_cb_arrays(cfg, g, sea, m, n, advtyp=2, btrmas=True, nstep=3)
+        ts = pkg.Tsadvc(cb)
+        ts.upload_state(m, n)
+        tss.append(ts)
+    _exchange_in_process(tss, m, n)
+    bes = [xc.DeviceHaloBackend(ts) for ts in tss]
+    nbrs = [xc.neighbors(ts.cb.geom) for ts in tss]
+    nbatch, per = C.c_int32(0), C.c_int32(0)
+    tss[0]._ck(tss[0].lib.hycom_tsadvc_fct2c_batches(tss[0].h, C.byref(nbatch), C.byref(per)))
+    assert nbatch.value == (kdm + per.value - 1) // per.value
+
+    def stage(b, st):
+        for ts in tss:
+            p = ts.cb.params()
+            ts._ck(ts.lib.hycom_tsadvc_fct2c_stage(ts.h, m, n, C.byref(p), b, st))
+
+    for b in range(nbatch.value):
+        stage(b, 0)
+        for it in range(5):
+            stage(b, 1)
+            sends = []
+            for t, ts in enumerate(tss):
+                cnt = bes[t].fct2c_counts(m, n, b)
+                layers = min(per.value, kdm - b * per.value)
+                assert cnt == xc.halo_counts(ts.cb.geom, (1 + 2 + ntracr) * layers, 5, 5)
+                send = [bes[t].alloc(c) if nbrs[t][d] >= 0 else None for d, c in enumerate(cnt)]
+                bes[t].fct2c_pack(m, n, b, send)
+                sends.append(send)
+                ts.synchronize()
+            for t, ts in enumerate(tss):
+                recv = [sends[nbrs[t][d]][xc.OPP[d]] if nbrs[t][d] >= 0 else None for d in range(8)]
+                bes[t].fct2c_unpack(m, n, b, recv)
+                ts.synchronize()
+        stage(b, 2)
+    for ts in tss:
+        p = ts.cb.params()
+        ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, None, None))
+    for ts in tss:
+        g = ts.cb.geom
+        sea_t = ts.cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
+        glob = (slice(None), slice(nb + g.j0, nb + g.j0 + g.jj), slice(nb + g.i0, nb + g.i0 + g.ii))
+        pairs = [(cabi.F_TEMP, 0, ref["temp"][n - 1]), (cabi.F_SALN, 0, ref["saln"][n - 1])]
+        pairs += [(cabi.F_TRACER, q + 1, ref["tracer"][q, n - 1]) for q in range(ntracr)]
+        for fld, ktr, r in pairs:
+            dev = ts.download(fld, n, ktr=ktr)[:, nb:nb + g.jj, nb:nb + g.ii]
+            assert np.array_equal(dev[:, sea_t], r[glob][:, sea_t]), (g.mproc, g.nproc, fld)
+        ts.close()

@@ -25,17 +25,42 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ipr, jpr = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
     ok_all = True
-    for (itdm, jtdm, kdm, nreg, ntracr, advtyp) in [(150, 150, 4, 0, 0, 2), (301, 203, 3, 3, 1, 2), (180, 120, 2, 1, 1, 1)]:
+    cases = [(150, 150, 4, 0, 0, 2, {}), (301, 203, 3, 3, 1, 2, {}), (180, 120, 2, 1, 1, 1, {}),
+             # temdf2 > 0: second exchange (width 2) + tsdff + EOS; btrmas: advem_fct2c with five exchanges
+             (150, 150, 3, 0, 1, 2, {"diffusion": (6, 1.0)}), (301, 203, 2, 3, 0, 2, {"diffusion": (8, 0.5)}),
+             (150, 150, 10, 0, 1, 2, {"btrmas": True}), (301, 203, 2, 3, 0, 2, {"btrmas": True})]
+    for (itdm, jtdm, kdm, nreg, ntracr, advtyp, extra) in cases:
         m, n = 1, 2
-        cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=9, m=m, n=n, advtyp=advtyp)
+        scal = dict(advtyp=advtyp)
+        if "btrmas" in extra:
+            scal["btrmas"] = True
+        if "diffusion" in extra:
+            sigver, temdfc = extra["diffusion"]
+            cfg, sea, g1, cb1 = util.make_diffusion_case(itdm, jtdm, kdm, sigver, temdfc, nreg=nreg, ntracr=ntracr,
+                                                         seed=9, **scal)
+            scal.update(temdf2=cb1.temdf2, temdfc=temdfc, sigver=sigver, thbase=cb1.thbase)
+        else:
+            cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=9, m=m, n=n, **scal)
         orc = oracle_binding.Oracle(os.path.join(ROOT, "oracle", "_build", "liboracle.so"))
         ot = util.oracle_tile_from_cb(orc, cb1, sea)
         g = pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)[rank]
-        cb = syn.build_cb_arrays(cfg, g, sea, m, n, advtyp=advtyp)
+        cb = syn.build_cb_arrays(cfg, g, sea, m, n, **scal)
+        if "diffusion" in extra:   # this tile's window of the single-tile th3d/theta (both slots)
+            nbd = g.nbdy
+            win = (Ellipsis, slice(g.j0, g.j0 + g.nrows), slice(g.i0, g.i0 + g.ncols))
+            cb.th3d = np.full((2, kdm, g.nrows, g.ncols), np.nan)
+            cb.theta = np.full((kdm, g.nrows, g.ncols), np.nan)
+            a, b = cb1.th3d[win], cb1.theta[win]
+            cb.th3d[..., :a.shape[-2], :a.shape[-1]] = a
+            cb.theta[..., :b.shape[-2], :b.shape[-1]] = b
         stream = torch.cuda.Stream()
         ts = pkg.Tsadvc(cb, device=local, stream=stream.cuda_stream)
         ts.upload_state(m, n)
         ts.upload(cabi.F_DP, cb.dp[m - 1], m)
+        ts.upload(cabi.F_ONETA, cb.oneta[m - 1], m)
+        ts.upload(cabi.F_ONETA, cb.oneta[n - 1], n)
+        if "diffusion" in extra:
+            ts.upload(cabi.F_TH3D, cb.th3d[m - 1], m)
         xc = pkg.XcExchange(ts, dist, compute_stream=stream)
         nb = g.nbdy
         for step, (mm, nn) in enumerate([(m, n), (n, m)]):
@@ -47,13 +72,14 @@ def main():
             ts.synchronize()
             sea_t = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
             glob = (slice(None), slice(nb + g.j0, nb + g.j0 + g.jj), slice(nb + g.i0, nb + g.i0 + g.ii))
-            for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+            flds = ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")) + (((cabi.F_TH3D, "th3d"),) if "diffusion" in extra else ())
+            for fld, name in flds:
                 dev = ts.download(fld, nn)[:, nb:nb + g.jj, nb:nb + g.ii]
                 ref = ot.f64(name)[nn - 1][glob]
                 ok = np.array_equal(dev[:, sea_t], ref[:, sea_t])
                 ok_all = ok_all and ok
                 if not ok:
-                    print(f"rank {rank}: MISMATCH {name} step {step} case {(itdm, jtdm, nreg, advtyp)}", flush=True)
+                    print(f"rank {rank}: MISMATCH {name} step {step} case {(itdm, jtdm, nreg, advtyp, extra)}", flush=True)
         ts.close()
         ot.close()
     t = torch.tensor([1 if ok_all else 0], device="cuda")
