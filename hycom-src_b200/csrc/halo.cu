@@ -1,7 +1,7 @@
 // Halo update of the device mirrors: the device-side xctilr.
 //
 // Single tile (mod_xc_sm.h:1337-1428): closed edges receive vland (0.0),
-// periodic edges wrap.  North/south lines are filled first over i=1..ii, then
+// periodic edges wrap; nreg=2 (mod_xc_sm.h:1172-1335): tripole fold across the arctic.  North/south lines are filled first over i=1..ii, then
 // east/west columns over j=1-nhl..jj+nhl, so corners come from the second pass
 // applied to the lines written by the first.
 #include <cuda_runtime.h>
@@ -27,9 +27,18 @@ __global__ void k_halo_ns(double* __restrict__ base, long slab, int nslab, int p
     const int i = (int)(q % ii) + 1;
     double* a = base + slab * s;
     double vs = 0.0, vn = 0.0;  // vland
-    if (periodic_j) {
+    if (periodic_j == 1) {
       vs = a[fidx(i, jj + 1 - j, nb, pitch)];
       vn = a[fidx(i, j, nb, pitch)];
+    } else if (periodic_j >= 100) {
+      // global grid that includes the arctic (mod_xc_sm.h:1172-1335): the southern boundary is
+      // closed, the northern rows are the tripole fold of rows below jj, mirrored in i; the
+      // mirror index and row depend on the grid (itype 1 p, 2 q, 3 u, 4 v; +10: vector, sign flips)
+      const int itype = periodic_j - 100, grid = itype % 10;
+      const int io = (grid == 1 || grid == 4) ? ii - (i - 1) % ii : (ii - (i - 1)) % ii + 1;
+      const int jo = (grid == 1 || grid == 3) ? jj - 1 - j : jj - j;
+      const double v = a[fidx(io, jo, nb, pitch)];
+      vn = itype > 10 ? -v : v;
     }
     a[fidx(i, 1 - j, nb, pitch)] = vs;
     a[fidx(i, jj + j, nb, pitch)] = vn;

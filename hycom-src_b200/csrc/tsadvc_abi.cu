@@ -213,7 +213,9 @@ int hycom_tsadvc_create(const hycom_tsadvc_dims* dims, hycom_tsadvc_handle** out
       d.ii > d.idm || d.jj > d.jdm || d.ntracr < 0 || d.ntracr > HYCOM_TSADVC_MXTRCR)
     return fail(nullptr, HYCOM_TSADVC_EINVAL, "bad dimensions idm=%d jdm=%d kdm=%d nbdy=%d ii=%d jj=%d ntracr=%d",
                 d.idm, d.jdm, d.kdm, d.nbdy, d.ii, d.jj, d.ntracr);
-  if (d.nreg == 2) return fail(nullptr, HYCOM_TSADVC_EUNSUPPORTED, "nreg=2 (arctic tripole) not supported");
+  if (d.nreg == 2 && d.ipr * d.jpr != 1)
+    return fail(nullptr, HYCOM_TSADVC_EUNSUPPORTED,
+                "nreg=2 (arctic tripole) on more than one tile: the folded top-row exchange of mod_xc_mp.h:4114-4662 is not built yet");
   if (d.nreg < 0 || d.nreg > 4) return fail(nullptr, HYCOM_TSADVC_EINVAL, "bad nreg %d", d.nreg);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -421,7 +423,10 @@ int hycom_tsadvc_halo_local(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, 
 static int halo_local_range(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev,
                             int32_t mh, int32_t nh, int k0, int nk) {
   const int nreg = h->d.nreg;
-  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
+  // xctilr's itype (mod_tsadvc.F90:1829-1836): halo_ps = 1 for scalars, halo_uv = 13 / halo_vv = 14 for
+  // the mass fluxes; it only matters across the arctic (nreg = 2)
+  const int itype = field == HYCOM_F_UFLX ? 13 : field == HYCOM_F_VFLX ? 14 : 1;
+  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg == 2 ? 100 + itype : nreg > 2;
   const int t0 = is3d(field) ? 1 : (tlev == 0 ? 1 : tlev);
   const int t1 = is3d(field) ? 1 : (tlev == 0 ? 2 : tlev);
   for (int t = t0; t <= t1; ++t) {
@@ -700,7 +705,7 @@ int run_fct2c(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
               const std::vector<Adv>& adv) {
   const int kk = h->d.kdm, nb = fct2c_batch_layers(h);
   const int nreg = h->d.nreg;
-  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
+  const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg == 2 ? 101 : nreg > 2;   // halo_ps
   int rc;
   for (int batch = 0; batch * nb < kk; ++batch) {
     Fct2cParams P;

@@ -99,6 +99,8 @@ def bigrid_masks(sea: np.ndarray, g: TileGeom):
     1-nbdy..ii+nbdy (zero in the unused part of a ragged tile).
     """
     nb = g.nbdy
+    if g.nreg == 2:
+        return _bigrid_masks_arctic(sea, g)
     ig, jg = _global_index(g)
     nr, nc = g.nrows, g.ncols
     # one extra cell to the west/south for iu/iv at the first halo line
@@ -128,6 +130,34 @@ def bigrid_masks(sea: np.ndarray, g: TileGeom):
     iu = np.where(live, iu, 0).astype(np.int32)
     iv = np.where(live, iv, 0).astype(np.int32)
     return np.ascontiguousarray(ip), np.ascontiguousarray(iu), np.ascontiguousarray(iv)
+
+
+def _bigrid_masks_arctic(sea: np.ndarray, g: TileGeom):
+    """nreg=2 (global grid across the arctic, single tile): periodic in i, land south of row 1,
+    and the rows above jtdm are the tripole fold ip(i,jtdm+j) = ip(itdm+1-i, jtdm-1-j)
+    (bigrid.F90:116-131 + xctilr halo_ps of mod_xc_sm.h:1215-1232).  iu/iv follow from ip: for a
+    depth array that is itself fold-consistent in row jtdm this equals the reference's
+    halo_us/halo_vs updates of the interior iu/iv."""
+    assert g.ipr == 1 and g.jpr == 1, "arctic masks: single tile only"
+    nb, ni, nj = g.nbdy, g.itdm, g.jtdm
+    ipg = np.zeros((nj + 2 * nb + 1, ni + 2 * nb + 1), dtype=np.int32)   # one extra cell west/south
+    jj = np.arange(-nb, nj + nb + 1)       # Fortran j of every row (from 1-nb-1)
+    ii = np.arange(-nb, ni + nb + 1)
+    for r, j in enumerate(jj):
+        for_i = (ii - 1) % ni + 1           # periodic in i
+        if j < 1:
+            continue                        # south boundary is all land
+        if j <= nj:
+            ipg[r] = sea[j - 1, for_i - 1]
+        else:
+            jo = nj - 1 - (j - nj)
+            io = ni + 1 - for_i
+            ipg[r] = sea[jo - 1, io - 1]
+    ip = ipg[1:, 1:]
+    iu = ip & ipg[1:, :-1]
+    iv = ip & ipg[:-1, 1:]
+    return (np.ascontiguousarray(ip, dtype=np.int32), np.ascontiguousarray(iu, dtype=np.int32),
+            np.ascontiguousarray(iv, dtype=np.int32))
 
 
 def geopar_metrics(scpx, scpy, scux, scuy, scvx, scvy, aspmax: float = 2.0):

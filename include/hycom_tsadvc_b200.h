@@ -69,7 +69,8 @@ typedef struct hycom_tsadvc_dims {
   int32_t ii, jj;               /* tile extents actually used (<= idm, jdm) */
   int32_t i0, j0;               /* offset of the tile in the global grid */
   int32_t itdm, jtdm;           /* global extents */
-  int32_t nreg;                 /* mod_xc.F90:25-31: 0 closed, 1 periodic in i,
+  int32_t nreg;                 /* mod_xc.F90:25-31: 0 closed, 1 periodic in i, 2 global grid
+                                   across the arctic (tripole fold, one tile only for now),
                                    3 periodic in i and j (f-plane), 4 closed f-plane */
   int32_t ipr, jpr;             /* number of tiles in i and j */
   int32_t mproc, nproc;         /* 1-based tile coordinates */

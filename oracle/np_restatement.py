@@ -278,12 +278,24 @@ def prolog(geom, uflx_k, vflx_k, dp_kn, onetamas_m, delt1, scp2i, ip, margin):
         return fco, fcn
 
 
-def halo_single_tile(geom, a, mh, nh):
-    """xctilr on one tile, mod_xc_sm.h:1337-1428, for an array (..., nrows, ncols)"""
+def halo_single_tile(geom, a, mh, nh, itype=1):
+    """xctilr on one tile, mod_xc_sm.h:1337-1428 (nreg=2: the arctic version, :1172-1335, where
+    itype selects grid and sign, mod_xc.F90:41-44), for an array (..., nrows, ncols)"""
     nb, ii, jj = geom.nbdy, geom.ii, geom.jj
     a = a.copy()
     i1, j1 = nb, nb   # numpy index of i=1 / j=1
+    if geom.nreg == 2:
+        grid, sgn = itype % 10, (1.0 if itype < 10 else -1.0)
+        i = np.arange(1, ii + 1)
+        io = (ii - (i - 1) % ii) if grid in (1, 4) else ((ii - (i - 1)) % ii + 1)
+        for j in range(1, nh + 1):
+            a[..., j1 - j, i1:i1 + ii] = 0.0
+            jo = (jj - 1 - j) if grid in (1, 3) else (jj - j)
+            src = a[..., j1 + jo - 1, :][..., i1 + io - 1]
+            a[..., j1 + jj - 1 + j, i1:i1 + ii] = src if itype < 10 else sgn * src
     for j in range(1, nh + 1):
+        if geom.nreg == 2:
+            break
         if geom.nreg <= 2:
             a[..., j1 - j, i1:i1 + ii] = 0.0
             a[..., j1 + jj - 1 + j, i1:i1 + ii] = 0.0
@@ -311,8 +323,8 @@ def tsadvc(cb, m, n):
     temp = halo_single_tile(g, cb.temp, mbdy, mbdy)
     saln = halo_single_tile(g, cb.saln, mbdy, mbdy)
     th3d = halo_single_tile(g, cb.th3d, mbdy, mbdy)
-    uflx = halo_single_tile(g, cb.uflx, mbdy, mbdy)
-    vflx = halo_single_tile(g, cb.vflx, mbdy, mbdy)
+    uflx = halo_single_tile(g, cb.uflx, mbdy, mbdy, 13)   # halo_uv
+    vflx = halo_single_tile(g, cb.vflx, mbdy, mbdy, 14)   # halo_vv
     tracer = halo_single_tile(g, cb.tracer, mbdy, mbdy) if cb.ntracr else None
     # onetamas(:,:,m) = 1.0 (:1809), or oneta(:,:,n) when btrmas (:1806)
     oem = cb.oneta[n - 1] if cb.btrmas else np.ones((g.nrows, g.ncols))

@@ -178,12 +178,35 @@ int orc_set_d(orc_tile *t, const char *name, double v) {
 
 /* ---- xctilr, single tile: mod_xc_sm.h:1337-1428 --------------------------- */
 void orc_xctilr(const orc_tile *t, double *a, int l1, int ld_, int mh, int nh) {
+  orc_xctilr_type(t, a, l1, ld_, mh, nh, 1); /* halo_ps */
+}
+
+/* itype as mod_xc.F90:41-44 (halo_ps=1, halo_qs=2, halo_us=3, halo_vs=4, +10: vector field);
+ * it only matters on a global grid that includes the arctic (nreg=2, mod_xc_sm.h:1172-1335) */
+void orc_xctilr_type(const orc_tile *t, double *a, int l1, int ld_, int mh, int nh, int itype) {
   GEOM(t);
   const size_t P = (size_t)orc_slab(t);
   const double vland = 0.0; /* mod_xc.F90:37, set to 0.0 by xcspmd */
   const int mhl = MAX2(0, MIN2(mh, nb)), nhl = MAX2(0, MIN2(nh, nb));
   if (nhl > 0) {
-    if (t->nreg <= 2) { /* closed in latitude, :1381-1389 */
+    if (t->nreg == 2) { /* arctic: mod_xc_sm.h:1215-1320 */
+      for (int k = l1; k <= ld_; k++) {
+        double *ak = a + P * (size_t)(k - 1);
+        for (int j = 1; j <= nhl; j++)
+          for (int i = 1; i <= ii; i++) ak[IX(i, 1 - j)] = vland; /* southern boundary is closed */
+        const int grid = itype % 10;
+        const double sgn = itype < 10 ? 1.0 : -1.0; /* vector field, swap sign */
+        for (int j = 1; j <= nhl; j++)
+          for (int i = 1; i <= ii; i++) {
+            int io, jo;
+            if (grid == 1) { io = ii - (i - 1) % ii; jo = jj - 1 - j; }            /* p-grid */
+            else if (grid == 2) { io = (ii - (i - 1)) % ii + 1; jo = jj - j; }     /* q-grid */
+            else if (grid == 3) { io = (ii - (i - 1)) % ii + 1; jo = jj - 1 - j; } /* u-grid */
+            else { io = ii - (i - 1) % ii; jo = jj - j; }                          /* v-grid */
+            ak[IX(i, jj + j)] = itype < 10 ? ak[IX(io, jo)] : sgn * ak[IX(io, jo)];
+          }
+      }
+    } else if (t->nreg <= 2) { /* closed in latitude, :1381-1389 */
       for (int k = l1; k <= ld_; k++) {
         double *ak = a + P * (size_t)(k - 1);
         for (int j = 1; j <= nhl; j++)
@@ -411,7 +434,7 @@ int orc_bigrid_stage1(orc_tile *t, double *depth) {
   const int lperiod = !(nreg == 0 || nreg == 4);      /* :25-33 via nreg */
   const int lfplane = (nreg == 3 || nreg == 4);       /* :44-45 */
   const int larctic = (nreg == 2);
-  if (larctic) { snprintf(g_err, sizeof g_err, "bigrid: arctic not supported"); return 2; }
+  if (larctic && !lperiod) { snprintf(g_err, sizeof g_err, "arctic   domain, but non-periodic"); return 2; } /* :48-56 */
   /* :119-154 non-periodic boundaries (part I) */
   if (!lfplane && t->j0 == 0)
     for (int j = 1 - nb; j <= 0; j++)
@@ -521,9 +544,9 @@ int orc_bigrid(orc_tile *t, double *depth) {
   int rc = orc_bigrid_stage1(t, depth);
   if (rc) return rc;
   /* :241-243 */
-  orc_xctilr(t, t->util1, 1, 1, t->nbdy, t->nbdy);
-  orc_xctilr(t, t->util2, 1, 1, t->nbdy, t->nbdy);
-  orc_xctilr(t, t->uflux, 1, 1, t->nbdy, t->nbdy);
+  orc_xctilr_type(t, t->util1, 1, 1, t->nbdy, t->nbdy, 3); /* halo_us */
+  orc_xctilr_type(t, t->util2, 1, 1, t->nbdy, t->nbdy, 4); /* halo_vs */
+  orc_xctilr_type(t, t->uflux, 1, 1, t->nbdy, t->nbdy, 2); /* halo_qs */
   return orc_bigrid_stage2(t);
 }
 
@@ -1370,8 +1393,8 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
     orc_xctilr(t, t->saln, 1, 2 * kk, l, l);
     orc_xctilr(t, t->temp, 1, 2 * kk, l, l);
     orc_xctilr(t, t->th3d, 1, 2 * kk, l, l);
-    orc_xctilr(t, t->uflx, 1, kk, l, l);
-    orc_xctilr(t, t->vflx, 1, kk, l, l);
+    orc_xctilr_type(t, t->uflx, 1, kk, l, l, 13); /* halo_uv */
+    orc_xctilr_type(t, t->vflx, 1, kk, l, l, 14); /* halo_vv */
     for (int ktr = 1; ktr <= t->ntracr; ktr++)
       orc_xctilr(t, t->tracer + P * K * 2 * (size_t)(ktr - 1), 1, 2 * kk, l, l);
   }

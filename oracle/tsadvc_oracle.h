@@ -82,6 +82,9 @@ int orc_set_d(orc_tile *t, const char *name, double v);
 
 /* mod_xc_sm.h:1337-1428  single-tile halo update (closed: vland=0, periodic) */
 void orc_xctilr(const orc_tile *t, double *a, int l1, int ld, int mh, int nh);
+/* the same with xctilr's itype (mod_xc.F90:41-44); nreg=2 is the single-tile arctic version,
+ * mod_xc_sm.h:1172-1335 */
+void orc_xctilr_type(const orc_tile *t, double *a, int l1, int ld, int mh, int nh, int itype);
 /* mod_xc_mp.h:4664-4987 emulated over an ipr x jpr array of tiles living in one
  * address space: a[m + ipr*n] is the same field on tile (m,n), 0-based. */
 void orc_world_xctilr(int ipr, int jpr, orc_tile *const *tiles,

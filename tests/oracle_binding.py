@@ -135,6 +135,8 @@ class Oracle:
         lib.orc_set_d.argtypes = [_vp, C.c_char_p, C.c_double]
         lib.orc_xctilr.restype = None
         lib.orc_xctilr.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.orc_xctilr_type.restype = None
+        lib.orc_xctilr_type.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         lib.orc_world_xctilr.restype = None
         lib.orc_world_xctilr.argtypes = [C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp),
                                          C.c_int, C.c_int, C.c_int, C.c_int]

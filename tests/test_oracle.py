@@ -344,3 +344,33 @@ def test_fct2c_constant_field_and_bounds(oracle):
     # fct2c has no [fmn,fmx] clamp: a constant is kept to rounding except next to the ~1 % of
     # cells the generator drives to dp+flxdiv < 0 (":1169 it may happen that the cfl is violated")
     assert np.median(err) < 1e-14 and (err > 1e-12).mean() < 0.08 and err.max() < 1e-2, (err.max(), (err > 1e-12).mean())
+
+
+# ---- nreg=2: global grid across the arctic, single tile (mod_xc_sm.h:1172-1335) ---------------
+@pytest.mark.parametrize("advtyp,ntracr,extra", [(2, 1, {}), (1, 0, {}), (4, 0, {}), (2, 0, {"btrmas": True})])
+def test_arctic_c_oracle_equals_numpy_restatement(oracle, advtyp, ntracr, extra):
+    cfg, sea, g, cb = util.make_arctic_case(60, 47, 2, ntracr=ntracr, seed=7, advtyp=advtyp, **extra)
+    m, n = 1, 2
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    for name in ("ip", "iu", "iv"):          # bigrid with halo_us/halo_vs across the fold
+        assert np.array_equal(ot.i32(name), getattr(cb, name)), name
+    assert ot.i32("ip")[g.nbdy + g.jj:, g.nbdy:g.nbdy + g.ii].any()   # sea cells in the north halo
+    ot.tsadvc(m, n, 1)
+    alt = npr.tsadvc(cb, m, n)
+    msk = util.interior_sea(cb)
+    for k in range(g.kdm):
+        assert _sea_eq(ot.f64("temp")[n - 1, k], alt["temp"][n - 1, k], msk), ("temp", k)
+        assert _sea_eq(ot.f64("saln")[n - 1, k], alt["saln"][n - 1, k], msk), ("saln", k)
+    # the fold is felt: the top rows differ from a run that closes the northern boundary
+    cb1 = util.make_arctic_case(60, 47, 2, ntracr=ntracr, seed=7, advtyp=advtyp, **extra)[3]
+    g1 = pkg_partition_closed(g)
+    cb1.geom = g1
+    alt1 = npr.tsadvc(cb1, m, n)
+    top = np.zeros_like(msk); top[g.nbdy + g.jj - 3:g.nbdy + g.jj] = True
+    assert not _sea_eq(alt["saln"][n - 1, 0], alt1["saln"][n - 1, 0], msk & top)
+    ot.close()
+
+
+def pkg_partition_closed(g):
+    import dataclasses
+    return dataclasses.replace(g, nreg=1)

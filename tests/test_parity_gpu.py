@@ -558,3 +558,45 @@ def test_fct2c_tiling_invariance_on_device(oracle, ipr, jpr, nreg, ntracr, kdm):
             dev = ts.download(fld, n, ktr=ktr)[:, nb:nb + g.jj, nb:nb + g.ii]
             assert np.array_equal(dev[:, sea_t], r[glob][:, sea_t]), (g.mproc, g.nproc, fld)
         ts.close()
+
+
+# ---------------------------------------------------------------------------------------
+# nreg=2: global grid across the arctic on one tile (tripole fold, mod_xc_sm.h:1172-1335)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("itdm,jtdm,kdm,ntracr,advtyp,extra", [
+    (150, 97, 3, 1, 2, {}),
+    (131, 77, 2, 0, 1, {}),
+    (90, 64, 2, 0, 4, {}),
+    (90, 64, 2, 1, 0, {}),
+    (120, 70, 3, 0, 2, {"btrmas": True}),
+])
+def test_arctic_host_path_matches_oracle(oracle, itdm, jtdm, kdm, ntracr, advtyp, extra):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_arctic_case(itdm, jtdm, kdm, ntracr=ntracr, seed=29, m=m, n=n, advtyp=advtyp,
+                                            nstep=3, **extra)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    got, before, launches = _run_host_path(cb, m, n)
+    _compare(cb, g, got, ref, n, ["saln", "temp"])
+    for q in range(ntracr):
+        _compare(cb, g, {"t": got["tracer"][q]}, {"t": ref["tracer"][q]}, n, ["t"])
+    assert np.array_equal(got["xmin"], ref["xmin"]) and np.array_equal(got["xmax"], ref["xmax"])
+
+
+def test_arctic_device_halo_matches_xctilr(oracle):
+    """the fold per grid type: scalars (halo_ps), uflx (halo_uv), vflx (halo_vv)"""
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_arctic_case(64, 50, 2, seed=3, m=m, n=n)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_state(m, n)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    for fld, name, itype in ((cabi.F_SALN, "saln", 1), (cabi.F_UFLX, "uflx", 13), (cabi.F_VFLX, "vflx", 14)):
+        ts._ck(ts.lib.hycom_tsadvc_halo_local(ts.h, fld, 0, 1, 5, 5))
+        dev = ts.download(fld, 1)
+        a = ot.f64(name)
+        a3 = a[0] if a.ndim == 4 else a
+        ot.lib.orc_xctilr_type(ot.t, a3.ctypes.data_as(C.c_void_p), 1, g.kdm, 5, 5, itype)
+        nb = g.nbdy
+        win = (slice(None), slice(nb - 5, nb + g.jj + 5), slice(nb - 5, nb + g.ii + 5))
+        assert np.array_equal(dev[win], a3[win], equal_nan=True), name
+    ts.close()
+    ot.close()

@@ -94,3 +94,24 @@ def make_diffusion_case(itdm, jtdm, kdm, sigver, temdfc, nreg=0, ntracr=0, nhybr
     for k in range(kdm):
         cb.theta[k] = np.nanmean(cb.th3d[:, k]) + 0.001 * k
     return cfg, sea, g, cb
+
+
+def make_arctic_case(itdm, jtdm, kdm, ntracr=0, seed=1, m=1, n=2, **scalars):
+    """nreg=2: a global grid across the arctic on one tile (periodic in i, tripole fold at the
+    top).  The generator builds a periodic/closed basin; the top rows are then opened (all sea,
+    hence fold-consistent) and every array that must arrive with a valid halo (dp, oneta,
+    metrics) gets the arctic halo of its grid."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import np_restatement as npr
+    cfg = make_cfg(itdm, jtdm, kdm, nreg=2, ntracr=ntracr, seed=seed)
+    sea = syn.sea_mask(cfg)
+    sea[jtdm - 8:, :] = 1
+    g = pkg.partition(itdm, jtdm, kdm, 1, 1, 2)[0]
+    cb = syn.build_cb_arrays(cfg, g, sea, m, n, **scalars)
+    nb = g.nbdy
+    cb.dp = npr.halo_single_tile(g, cb.dp, nb, nb, 1)
+    cb.oneta = npr.halo_single_tile(g, cb.oneta, nb, nb, 1)
+    for name, it in (("scp2", 1), ("scp2i", 1), ("scuy", 3), ("aspux", 3), ("scvx", 4), ("aspvy", 4)):
+        setattr(cb, name, np.ascontiguousarray(npr.halo_single_tile(g, getattr(cb, name), nb, nb, it)))
+    return cfg, sea, g, cb
