@@ -13,7 +13,7 @@ _LIB_NAME = "libhycom_tsadvc_b200.so"
 
 MXTRCR = 16
 
-F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER, F_ONETA, F_THETA = range(9)
+F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER, F_ONETA, F_THETA, F_Q2, F_Q2L = range(11)
 S_SCPX, S_SCPY, S_SCUX, S_SCUY, S_SCVX, S_SCVY, S_ONETA = range(10, 17)
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENBDY, EADVTYP, ENOMEM = range(7)

@@ -79,12 +79,20 @@ Mirror* mirror_of(hycom_tsadvc_handle* h, int field, int ktr) {
       return nullptr;
     case HYCOM_F_ONETA: return &h->oneta;
     case HYCOM_F_THETA: return &h->theta;
+    case HYCOM_F_Q2: return &h->q2;
+    case HYCOM_F_Q2L: return &h->q2l;
   }
   return nullptr;
 }
 bool is3d(int field) { return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX || field == HYCOM_F_THETA; }
 // slabs per time slot of a mirror
-int nlayers_of(const hycom_tsadvc_handle* h, int field) { return field == HYCOM_F_ONETA ? 1 : h->d.kdm; }
+int nlayers_of(const hycom_tsadvc_handle* h, int field) {
+  if (field == HYCOM_F_ONETA) return 1;
+  if (field == HYCOM_F_Q2 || field == HYCOM_F_Q2L) return h->d.kdm + 2;   // layers 0..kk+1
+  return h->d.kdm;
+}
+// slab index of model layer k = 1 inside one time slot of a mirror
+int layer1_of(int field) { return (field == HYCOM_F_Q2 || field == HYCOM_F_Q2L) ? 1 : 0; }
 
 // device pointer of slot tlev (1,2) of a mirror, allocated on first use
 int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
@@ -112,7 +120,8 @@ int slot(hycom_tsadvc_handle* h, int field, int ktr, int tlev, double** out) {
 
 int spare_of(hycom_tsadvc_handle* h, Mirror* mi, double** out) {
   if (!mi->spare) {
-    int rc = dalloc_field(h, &mi->spare, (size_t)h->slab * h->d.kdm);
+    const bool my = mi == &h->q2 || mi == &h->q2l;
+    int rc = dalloc_field(h, &mi->spare, (size_t)h->slab * (h->d.kdm + (my ? 2 : 0)));
     if (rc) return rc;
   }
   *out = mi->spare;
@@ -451,7 +460,8 @@ static int halo_local_range(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, 
 
 namespace {
 
-struct Adv { int field, ktr; double posdef; int nlay; };
+// an advected field: layers 1..nlay of the mirror, which start at slab `koff` of a time slot
+struct Adv { int field, ktr; double posdef; int nlay; int koff = 0; };
 
 // argument checks of tsadvc/advem (mod_tsadvc.F90:1815-1825, :159-166) and the list of
 // advected fields (:1855-1857, :1969-2034)
@@ -472,8 +482,9 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
                 mbdy);
   if (p.btrmas && aadv != 2)
     return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "btrmas with advtyp=%d: only advem_fct2c (advtyp=2) reads onetamas here", p.advtyp);
-  if (p.isopyc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc (k=1 flux smoothing) is not built yet");
-  if (p.mxlmy) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "mxlmy (q2,q2l advection) is not built yet");
+  if (p.isopyc && (h->d.ntracr > 0 || p.mxlmy || p.btrmas))
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED,
+                "isopyc with tracers, mxlmy or btrmas: layer 1 then mixes smoothed thickness changes with unsmoothed fluxes");
   if (p.temdf2 > 0.0) {
     if (p.sigver < 1 || p.sigver > 8)
       return fail(h, HYCOM_TSADVC_EINVAL, "temdf2>0 needs the equation of state: sigver=%d not in 1..8", p.sigver);
@@ -483,11 +494,17 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   const int kk = h->d.kdm;
   const int nhyb = p.nhybrd < 0 ? 0 : (p.nhybrd > kk ? kk : p.nhybrd);
   adv.clear();
+  // :1855-1857  latemp = k<=nhybrd & advflg==0; lath3d = (k<=nhybrd & advflg==1) | (k==1 & isopyc)
   if (p.advflg == 0) { if (nhyb > 0) adv.push_back({HYCOM_F_TEMP, 0, 256.0, nhyb}); }
   else               { if (nhyb > 0) adv.push_back({HYCOM_F_TH3D, 0, 32.0, nhyb}); }
+  if (p.isopyc && !(p.advflg != 0 && nhyb > 0)) adv.push_back({HYCOM_F_TH3D, 0, 32.0, 1});
   adv.push_back({HYCOM_F_SALN, 0, 0.0, kk});
   for (int t = 1; t <= h->d.ntracr; ++t)
     adv.push_back({HYCOM_F_TRACER, t, p.trcflg[t - 1] == 2 ? 256.0 : 0.0, kk});
+  if (p.mxlmy) {   // :2035-2048, pdq2 = 1.0 (:1762)
+    adv.push_back({HYCOM_F_Q2, 0, 1.0, kk, 1});
+    adv.push_back({HYCOM_F_Q2L, 0, 1.0, kk, 1});
+  }
   if ((int)adv.size() > kMaxFields) return fail(h, HYCOM_TSADVC_EINVAL, "too many advected fields");
   return 0;
 }
@@ -498,8 +515,10 @@ int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, H
   memset(&a, 0, sizeof a);
   int rc;
   for (const Adv& f : adv)
-    for (int t = 1; t <= 2; ++t)
-      if ((rc = slot(h, f.field, f.ktr, t, &a.base[a.narr++]))) return rc;
+    for (int t = 1; t <= 2; ++t) {
+      if ((rc = slot(h, f.field, f.ktr, t, &a.base[a.narr]))) return rc;
+      a.base[a.narr++] += h->slab * f.koff;   // q2,q2l: the advected layers 1..kk
+    }
   if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &a.base[a.narr++]))) return rc;
   if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &a.base[a.narr++]))) return rc;
   a.kk = h->d.kdm; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
@@ -521,7 +540,8 @@ int neighbour(const hycom_tsadvc_dims& d, int dir) {
 
 // layers k0 .. k0+nk-1 (0-based; nk < 0: all)
 int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
-              const std::vector<Adv>& adv, int part, int k0 = 0, int nk = -1) {
+              const std::vector<Adv>& adv, int part, int k0 = 0, int nk = -1,
+              const double* u_over = nullptr, const double* v_over = nullptr) {
   const int kk = nk < 0 ? h->d.kdm : nk, aadv = abs(p.advtyp);
   const long koff = h->slab * k0;
   int rc;
@@ -534,9 +554,10 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     if ((rc = slot(h, adv[f].field, adv[f].ktr, n, &in))) return rc;
     if ((rc = slot(h, adv[f].field, adv[f].ktr, m, &ctr))) return rc;
     if ((rc = spare_of(h, mirror_of(h, adv[f].field, adv[f].ktr), &out))) return rc;
-    P.fld[f].fld = in + koff;
-    P.fld[f].fldc = ctr + koff;
-    P.fld[f].out = out + koff;
+    const long kf = koff + h->slab * adv[f].koff;
+    P.fld[f].fld = in + kf;
+    P.fld[f].fldc = ctr + kf;
+    P.fld[f].out = out + kf;
     P.fld[f].posdef = adv[f].posdef;
     const int nl = adv[f].nlay - k0;
     P.fld[f].nlay = nl < 0 ? 0 : (nl > kk ? kk : nl);
@@ -546,6 +567,7 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &v))) return rc;
   if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
   P.u = u + koff; P.v = v + koff; P.dp = dpn + koff;
+  if (u_over) { P.u = u_over; P.v = v_over; }   // isopyc layer 1: the smoothed fluxes, prolog included (:1930-1932)
   P.slab = h->slab;
   P.njobs = P.nfld * kk;
   P.g.pitch = h->pitch; P.g.ncols = h->ncols; P.g.nrows = h->nrows; P.g.nbdy = h->d.nbdy;
@@ -614,6 +636,27 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   return 0;
 }
 
+// the marching launch(es) of one call: with isopycnic coordinates layer 1 runs on the laterally
+// smoothed mass fluxes (:1859-1897, :1930-1932, :1992-2005), the layers below on uflx, vflx
+int advect_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
+                 const std::vector<Adv>& adv, int part) {
+  if (!p.isopyc) return run_march(h, m, n, p, adv, part);
+  if (part == HYCOM_TSADVC_PART_INTERIOR) return 0;   // the smoothing reads the halo: no overlap
+  int rc;
+  if (!h->isopyc_flux && (rc = dalloc_field(h, &h->isopyc_flux, 2 * (size_t)h->slab))) return rc;
+  double *u, *v;
+  if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &u))) return rc;
+  if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &v))) return rc;
+  const int mbdy = abs(p.advtyp) == 0 ? 2 : 5;
+  rc = launch_isopyc_smooth(u, v, h->isopyc_flux, h->isopyc_flux + h->slab, h->mask, h->pitch, h->nrows,
+                            h->d.nbdy, h->d.ii, h->d.jj, mbdy - 1, h->stream);
+  h->launches += 1;
+  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "isopyc smoothing launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  if ((rc = run_march(h, m, n, p, adv, HYCOM_TSADVC_PART_ALL, 0, 1, h->isopyc_flux, h->isopyc_flux + h->slab))) return rc;
+  if (h->d.kdm > 1 && (rc = run_march(h, m, n, p, adv, HYCOM_TSADVC_PART_ALL, 1, h->d.kdm - 1))) return rc;
+  return 0;
+}
+
 // ---- advem_fct2c (advtyp=2 with btrmas, mod_tsadvc.F90:96-97, 999-1368) -------------------
 // Layer batches of whole-tile kernels.  The scheme exchanges hloc and fldlo after each of its
 // five iterations (:1186-1187): on a single tile the halo kernels do that, on several tiles
@@ -643,7 +686,8 @@ int fct2c_params(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadv
     if ((rc = slot(h, adv[f].field, adv[f].ktr, n, &in))) return rc;
     if ((rc = slot(h, adv[f].field, adv[f].ktr, m, &ctr))) return rc;
     if ((rc = spare_of(h, mirror_of(h, adv[f].field, adv[f].ktr), &out))) return rc;
-    P.fld[f] = in; P.fldc[f] = ctr; P.out[f] = out; P.nlay[f] = adv[f].nlay;
+    const long kf = h->slab * adv[f].koff;
+    P.fld[f] = in + kf; P.fldc[f] = ctr + kf; P.out[f] = out + kf; P.nlay[f] = adv[f].nlay;
   }
   double *u, *v, *dpn, *on;
   if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &u))) return rc;
@@ -733,9 +777,14 @@ int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
   int rc;
   for (const Adv& f : adv) {
     Mirror* mi = mirror_of(h, f.field, f.ktr);
-    if (f.nlay < kk)  // layers that were not advected keep their values (:2008-2014)
-      CU(h, cudaMemcpyAsync(mi->spare + h->slab * f.nlay, mi->lev[n - 1] + h->slab * f.nlay,
-                            sizeof(double) * (size_t)h->slab * (kk - f.nlay),
+    // layers that were not advected keep their values (:2008-2014; q2,q2l: layers 0 and kk+1)
+    const int nsl = nlayers_of(h, f.field), hi = f.koff + f.nlay;
+    if (f.koff > 0)
+      CU(h, cudaMemcpyAsync(mi->spare, mi->lev[n - 1], sizeof(double) * (size_t)h->slab * f.koff,
+                            cudaMemcpyDeviceToDevice, h->stream));
+    if (hi < nsl)
+      CU(h, cudaMemcpyAsync(mi->spare + h->slab * hi, mi->lev[n - 1] + h->slab * hi,
+                            sizeof(double) * (size_t)h->slab * (nsl - hi),
                             cudaMemcpyDeviceToDevice, h->stream));
     double* t = mi->lev[n - 1];
     mi->lev[n - 1] = mi->spare;
@@ -764,7 +813,7 @@ inline int ffield_of(bool adv_th3d) { return adv_th3d ? HYCOM_F_TH3D : HYCOM_F_T
 
 // the arrays of the second exchange (mod_tsadvc.F90:2140-2151): saln, temp, th3d, tracers of
 // slot n, halo width mdf = 2
-int diff_halo_arrays(hycom_tsadvc_handle* h, int n, HaloArrays& a) {
+int diff_halo_arrays(hycom_tsadvc_handle* h, int n, bool mxlmy, HaloArrays& a) {
   memset(&a, 0, sizeof a);
   int rc;
   if ((rc = slot(h, HYCOM_F_SALN, 0, n, &a.base[a.narr++]))) return rc;
@@ -772,6 +821,11 @@ int diff_halo_arrays(hycom_tsadvc_handle* h, int n, HaloArrays& a) {
   if ((rc = slot(h, HYCOM_F_TH3D, 0, n, &a.base[a.narr++]))) return rc;
   for (int t = 1; t <= h->d.ntracr; ++t)
     if ((rc = slot(h, HYCOM_F_TRACER, t, n, &a.base[a.narr++]))) return rc;
+  if (mxlmy)   // :2143-2146 (the reference sends layers 0..kk+1; 1..kk are the ones tsdff reads)
+    for (int f : {HYCOM_F_Q2, HYCOM_F_Q2L}) {
+      if ((rc = slot(h, f, 0, n, &a.base[a.narr]))) return rc;
+      a.base[a.narr++] += h->slab;
+    }
   a.kk = h->d.kdm; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
   a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 2; a.nh = 2;
   return 0;
@@ -803,12 +857,20 @@ int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p)
     int r2 = slot(h, field, ktr, n, &in);
     if (!r2) r2 = spare_of(h, mirror_of(h, field, ktr), &out);
     if (r2) return r2;
-    D.f[D.nf].in = in; D.f[D.nf].out = out; ++D.nf;
+    const long kf = h->slab * layer1_of(field);
+    D.f[D.nf].in = in + kf; D.f[D.nf].out = out + kf; ++D.nf;
     return 0;
   };
-  auto swap = [&](int field, int ktr) {
+  auto swap = [&](int field, int ktr) -> int {
     Mirror* mi = mirror_of(h, field, ktr);
+    if (layer1_of(field)) {   // q2,q2l: layers 0 and kk+1 travel with the buffer
+      const long last = h->slab * (kk + 1);
+      CU(h, cudaMemcpyAsync(mi->spare, mi->lev[n - 1], sizeof(double) * h->slab, cudaMemcpyDeviceToDevice, h->stream));
+      CU(h, cudaMemcpyAsync(mi->spare + last, mi->lev[n - 1] + last, sizeof(double) * h->slab,
+                            cudaMemcpyDeviceToDevice, h->stream));
+    }
     double* t = mi->lev[n - 1]; mi->lev[n - 1] = mi->spare; mi->spare = t;
+    return 0;
   };
   D.eos = 1;
   if ((rc = add(HYCOM_F_TEMP, 0)) || (rc = add(HYCOM_F_SALN, 0)) || (rc = add(HYCOM_F_TH3D, 0))) return rc;
@@ -816,13 +878,15 @@ int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p)
   h->launches += 1;
   if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   swap(HYCOM_F_TEMP, 0); swap(HYCOM_F_SALN, 0); swap(HYCOM_F_TH3D, 0);
-  if (h->d.ntracr > 0) {
+  if (h->d.ntracr > 0 || p.mxlmy) {   // :2180-2198: q2 & q2l, then the tracers, same face factors
     D.eos = 0; D.nf = 0;
+    if (p.mxlmy && ((rc = add(HYCOM_F_Q2, 0)) || (rc = add(HYCOM_F_Q2L, 0)))) return rc;
     for (int t = 1; t <= h->d.ntracr; ++t)
       if ((rc = add(HYCOM_F_TRACER, t))) return rc;
     rc = launch_tsdff(D, h->stream);
     h->launches += 1;
     if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (p.mxlmy && ((rc = swap(HYCOM_F_Q2, 0)) || (rc = swap(HYCOM_F_Q2L, 0)))) return rc;
     for (int t = 1; t <= h->d.ntracr; ++t) swap(HYCOM_F_TRACER, t);
   }
   return 0;
@@ -856,7 +920,7 @@ int hycom_tsadvc_step_device_part(hycom_tsadvc_handle* h, int32_t m, int32_t n,
     if (part == HYCOM_TSADVC_PART_INTERIOR) return 0;   // no overlap: the scheme exchanges five times itself
     // several tiles: the caller has driven hycom_tsadvc_fct2c_stage + exchanges; this call finishes the step
     if (h->d.ipr * h->d.jpr == 1 && (rc = run_fct2c(h, m, n, *prm, adv))) return rc;
-  } else if ((rc = run_march(h, m, n, *prm, adv, part))) {
+  } else if ((rc = advect_march(h, m, n, *prm, adv, part))) {
     return rc;
   }
   if (part == HYCOM_TSADVC_PART_INTERIOR) return 0;
@@ -880,6 +944,10 @@ int hycom_tsadvc_diffuse_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TH3D, 0, n, mdf, mdf))) return rc;
     for (int t = 1; t <= h->d.ntracr; ++t)
       if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_TRACER, t, n, mdf, mdf))) return rc;
+    if (prm->mxlmy) {
+      if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_Q2, 0, n, mdf, mdf))) return rc;
+      if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_Q2L, 0, n, mdf, mdf))) return rc;
+    }
   }
   return run_diffuse(h, n, *prm);
 }
@@ -952,7 +1020,7 @@ int hycom_tsadvc_diff_halo_counts(hycom_tsadvc_handle* h, int32_t n, const hycom
   if (!h || !prm || !count || n < 1 || n > 2) return fail(h, HYCOM_TSADVC_EINVAL, "diff_halo_counts: bad argument");
   HaloArrays a;
   int rc;
-  if ((rc = diff_halo_arrays(h, n, a))) return rc;
+  if ((rc = diff_halo_arrays(h, n, prm->mxlmy != 0, a))) return rc;
   for (int d = 0; d < 8; ++d) {
     int w, hh, c0, r0;
     halo_region(a, d, false, w, hh, c0, r0);
@@ -967,7 +1035,7 @@ static int diff_halo_xfer(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_
   CU(h, cudaSetDevice(h->d.device));
   HaloArrays a;
   int rc;
-  if ((rc = diff_halo_arrays(h, n, a))) return rc;
+  if ((rc = diff_halo_arrays(h, n, prm->mxlmy != 0, a))) return rc;
   HaloBufs b;
   for (int d = 0; d < 8; ++d) { b.buf[d] = buf[d]; b.count[d] = 0; }
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
@@ -1062,7 +1130,7 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   const size_t fs = (size_t)h->ncols * h->nrows;  // Fortran slab
   const bool adv_th3d = prm->advflg != 0;
   double* first = adv_th3d ? th3d : temp;
-  if (!first || !saln || !dp || !uflx || !vflx || (h->d.ntracr > 0 && !tracer))
+  if (!first || !saln || !dp || !uflx || !vflx || (h->d.ntracr > 0 && !tracer) || (prm->isopyc && !th3d))
     return fail(h, HYCOM_TSADVC_EINVAL, "step: a required array is NULL");
   const bool diffuse = prm->temdf2 > 0.0;
   double* other = adv_th3d ? temp : th3d;   // the thermodynamic variable that is not advected
@@ -1082,6 +1150,7 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
     if (!oneta) return fail(h, HYCOM_TSADVC_EINVAL, "step: btrmas needs oneta");
     chunk = kk;
   }
+  if (prm->isopyc) chunk = kk;   // layer 1 runs on smoothed fluxes: advect_march splits the launch itself
   const int nchunks = (kk + chunk - 1) / chunk;
   while ((int)h->ev_chunk.size() < 2 * nchunks + 1) {
     cudaEvent_t e;
@@ -1106,6 +1175,8 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
 
   const bool single = h->d.ipr * h->d.jpr == 1;
   const int nb = h->d.nbdy;
+  auto host_of = [&](int field) { return field == HYCOM_F_SALN ? saln : field == HYCOM_F_TH3D ? th3d : temp; };
+  auto resident = [](const Adv& a) { return a.field == HYCOM_F_Q2 || a.field == HYCOM_F_Q2L; };
   // D2H of layers k0..k0+nk-1 of a device buffer on 1:ii,1:jj ("valid halo 0 wide", :104)
   auto back = [&](const double* dev, double* host, int nk, cudaStream_t st) -> int {
     cudaMemcpy3DParms cp;
@@ -1121,13 +1192,13 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   };
   for (int c = 0; c < nchunks; ++c) {
     const int k0 = c * chunk, nk = (k0 + chunk <= kk) ? chunk : kk - k0;
-    // ---- copy in
+    // ---- copy in (q2, q2l stay in their mirrors: the caller uploaded them)
     for (const Adv& a : adv) {
-      if (k0 >= a.nlay) continue;   // layers below nhybrd of temp/th3d are not advected (:1855)
+      if (k0 >= a.nlay || resident(a)) continue;   // layers below nhybrd of temp/th3d are not advected (:1855)
       const int na = (k0 + nk <= a.nlay) ? nk : a.nlay - k0;
       for (int t = 1; t <= 2; ++t) {
         double* src = a.field == HYCOM_F_TRACER ? htr(a.ktr, t, k0)
-                                                : h4(a.field == HYCOM_F_SALN ? saln : first, t, k0);
+                                                : h4(host_of(a.field), t, k0);
         if ((rc = upload_on(h, a.field, a.ktr, t, k0 + 1, na, src, h->up_stream))) return rc;
       }
     }
@@ -1141,7 +1212,7 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
       for (const Adv& a : adv) {
         if (k0 >= a.nlay) continue;
         const int na = (k0 + nk <= a.nlay) ? nk : a.nlay - k0;
-        if ((rc = halo_local_range(h, a.field, a.ktr, 0, mbdy, mbdy, k0, na))) return rc;
+        if ((rc = halo_local_range(h, a.field, a.ktr, 0, mbdy, mbdy, k0 + a.koff, na))) return rc;
       }
       if ((rc = halo_local_range(h, HYCOM_F_UFLX, 0, 1, mbdy, mbdy, k0, nk))) return rc;
       if ((rc = halo_local_range(h, HYCOM_F_VFLX, 0, 1, mbdy, mbdy, k0, nk))) return rc;
@@ -1150,6 +1221,8 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
     if (fct2c) {   // onetamas(:,:,m) = oneta(:,:,n) (:1806)
       if ((rc = upload_on(h, HYCOM_F_ONETA, 0, n, 1, 1, oneta + fs * (n - 1), h->stream))) return rc;
       if ((rc = run_fct2c(h, m, n, *prm, adv))) return rc;
+    } else if (prm->isopyc) {
+      if ((rc = advect_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_ALL))) return rc;
     } else if ((rc = run_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_ALL, k0, nk))) {
       return rc;
     }
@@ -1158,19 +1231,19 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
     CU(h, cudaStreamWaitEvent(h->down_stream, h->ev_chunk[2 * c + 1], 0));
     // ---- copy out (the new time level still sits in the ping-pong buffer)
     for (const Adv& a : adv) {
-      if (k0 >= a.nlay) continue;
+      if (k0 >= a.nlay || resident(a)) continue;
       const int na = (k0 + nk <= a.nlay) ? nk : a.nlay - k0;
       double* dst = a.field == HYCOM_F_TRACER ? htr(a.ktr, n, k0)
-                                              : h4(a.field == HYCOM_F_SALN ? saln : first, n, k0);
+                                              : h4(host_of(a.field), n, k0);
       if ((rc = back(mirror_of(h, a.field, a.ktr)->spare + h->slab * k0, dst, na, h->down_stream))) return rc;
     }
   }
   // layers that were not advected must still be in the mirror the ping-pong swap retires
   for (const Adv& a : adv)
-    if (a.nlay < kk) {
+    if (a.nlay < kk && !resident(a)) {
       for (int t = 1; t <= 2; ++t) {
         double* src = a.field == HYCOM_F_TRACER ? htr(a.ktr, t, a.nlay)
-                                                : h4(a.field == HYCOM_F_SALN ? saln : first, t, a.nlay);
+                                                : h4(host_of(a.field), t, a.nlay);
         if ((rc = upload_on(h, a.field, a.ktr, t, a.nlay + 1, kk - a.nlay, src, h->stream))) return rc;
       }
     }

@@ -33,6 +33,7 @@ struct hycom_tsadvc_handle {
   tsadvc::Mirror temp, saln, th3d, dp, uflx, vflx;
   tsadvc::Mirror oneta;  // (:,:,2): one slab per time slot
   tsadvc::Mirror theta;  // (:,:,kdm): lev[0] only
+  tsadvc::Mirror q2, q2l;  // (:,:,0:kdm+1,2): kdm+2 slabs per slot (mxlmy)
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
   // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)]
   double* flux_block = nullptr;
@@ -46,6 +47,7 @@ struct hycom_tsadvc_handle {
   uint8_t* fct2c_lcalc = nullptr;
   long fct2c_slabs = 0;
   int fct2c_nb = 0;
+  double* isopyc_flux = nullptr;   // smoothed uflux | vflux of layer 1 (isopyc), 2 slabs
   double* d_minmax = nullptr;  // 2*kdm
   uint8_t* d_sea = nullptr;    // synthetic generator: global sea mask
   // optional per-launch timing of the marching kernel (hycom_tsadvc_set_timing)

@@ -115,6 +115,9 @@ struct DiffParams {
 };
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream);
+// uflux, vflux of mod_tsadvc.F90:1859-1897 from uflx(:,:,1), vflx(:,:,1)
+int launch_isopyc_smooth(const double* u, const double* v, double* us, double* vs, const uint8_t* mask,
+                         int pitch, int nrows, int nbdy, int ii, int jj, int margin, cudaStream_t stream);
 
 }  // namespace tsadvc
 

@@ -137,7 +137,43 @@ __global__ void __launch_bounds__(256, 3) k_tsdff(const DiffParams P) {
   }
 }
 
+// isopycnic coordinates, layer 1: lateral smoothing of the mixed-layer mass fluxes
+// (mod_tsadvc.F90:1859-1897, margin mbdy-1); faces that are not iu/iv points and everything
+// outside the margin keep the 0.0 of :1812-1813
+__global__ void __launch_bounds__(256) k_isopyc_smooth(const double* __restrict__ u, const double* __restrict__ v,
+                                                         double* __restrict__ us, double* __restrict__ vs,
+                                                         const uint8_t* __restrict__ mask, int pitch, int nrows,
+                                                         int nbdy, int ii, int jj, int margin) {
+  const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+  if (c >= pitch || r >= nrows) return;
+  const long q = (long)r * pitch + c;
+  const int i = c + 1 - nbdy, j = r + 1 - nbdy;
+  double uo = 0.0, vo = 0.0;
+  if (i >= 1 - margin && i <= ii + margin && j >= 1 - margin && j <= jj + margin) {
+    const unsigned m = mask[q];
+    if (m & M_IV) {
+      const double vfa = (mask[q - 1] & M_IV) ? v[q - 1] : v[q];
+      const double vfb = (mask[q + 1] & M_IV) ? v[q + 1] : v[q];
+      vo = .5 * v[q] + .25 * (vfa + vfb);
+    }
+    if (m & M_IU) {
+      const double ufa = (mask[q - pitch] & M_IU) ? u[q - pitch] : u[q];
+      const double ufb = (mask[q + pitch] & M_IU) ? u[q + pitch] : u[q];
+      uo = .5 * u[q] + .25 * (ufa + ufb);
+    }
+  }
+  us[q] = uo;
+  vs[q] = vo;
+}
+
 }  // namespace
+
+int launch_isopyc_smooth(const double* u, const double* v, double* us, double* vs, const uint8_t* mask,
+                         int pitch, int nrows, int nbdy, int ii, int jj, int margin, cudaStream_t stream) {
+  const dim3 block(32, 8), grid((pitch + 31) / 32, (nrows + 7) / 8);
+  k_isopyc_smooth<<<grid, block, 0, stream>>>(u, v, us, vs, mask, pitch, nrows, nbdy, ii, jj, margin);
+  return (int)cudaGetLastError();
+}
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream) {
   const dim3 block(32, 8), grid((P.pitch + 31) / 32, (P.nrows + 7) / 8);

@@ -51,6 +51,8 @@ class CbArrays:
     uflx: np.ndarray = None
     vflx: np.ndarray = None
     oneta: np.ndarray = None
+    q2: np.ndarray = None      # (2, kdm+2, nrows, ncols): q2(:,:,0:kk+1,2), Mellor-Yamada tke (mxlmy)
+    q2l: np.ndarray = None
     theta: np.ndarray = None   # (kdm, nrows, ncols): isopycnic target densities - thbase
     # blkdat scalars (defaults = the benchmark configuration: FCT2, T&S, hybrid)
     advtyp: int = 2
@@ -180,6 +182,8 @@ class Tsadvc:
         self.upload(cabi.F_DP, cb.dp[n - 1], n)
         self.upload(cabi.F_UFLX, cb.uflx, 1)
         self.upload(cabi.F_VFLX, cb.vflx, 1)
+        if cb.mxlmy:           # q2, q2l (0:kk+1, both slots), mod_tsadvc.F90:2035-2048
+            self.upload_q2()
         if cb.btrmas:          # onetamas(:,:,m) = oneta(:,:,n) (mod_tsadvc.F90:1806)
             self.upload(cabi.F_ONETA, cb.oneta[n - 1], n)
         if cb.temdf2 > 0.0:   # operands of the diffusion part (mod_tsadvc.F90:2138-2230)
@@ -187,6 +191,11 @@ class Tsadvc:
             self.upload(of, other[n - 1], n)
             self.upload(cabi.F_ONETA, cb.oneta[n - 1], n)
             self.upload_theta()
+
+    def upload_q2(self):
+        for t in (1, 2):
+            self.upload(cabi.F_Q2, self.cb.q2[t - 1], t)
+            self.upload(cabi.F_Q2L, self.cb.q2l[t - 1], t)
 
     def upload_theta(self):
         """theta is constant in time: pushed once, read only in exactly-isopycnal layers"""
@@ -200,10 +209,17 @@ class Tsadvc:
         p = cb.params()
         if cb.temdf2 > 0.0:
             self.upload_theta()
+        if cb.mxlmy:      # not in the argument list of the C entry: mirrors are filled around the call
+            self.upload_q2()
         self._ck(self.lib.hycom_tsadvc_step(
             self.h, m, n, C.byref(p), _ptr(cb.temp), _ptr(cb.saln), _ptr(cb.th3d), _ptr(cb.tracer),
             _ptr(cb.dp), _ptr(cb.uflx), _ptr(cb.vflx), _ptr(cb.oneta), _ptr(self.xmin),
             _ptr(self.xmax)))
+        if cb.mxlmy:      # slot n back on 1:ii,1:jj, like the fields in the argument list
+            g = cb.geom
+            rows, cols = g.interior()
+            for fld, a in ((cabi.F_Q2, cb.q2), (cabi.F_Q2L, cb.q2l)):
+                a[n - 1][:, rows, cols] = self.download(fld, n, nk=g.kdm + 2)[:, rows, cols]
 
     def tsadvc_device(self, m: int, n: int, diag: bool = True):
         """tsadvc(m,n) on the device mirrors (no host<->device traffic)."""

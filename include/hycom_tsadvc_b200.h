@@ -60,7 +60,9 @@ enum {
   HYCOM_F_VFLX = 5,   /* 3-D: tlev ignored */
   HYCOM_F_TRACER = 6, /* with ktr = 1..ntracr */
   HYCOM_F_ONETA = 7,  /* oneta(:,:,tlev): one slab per time slot (k0 = nk = 1) */
-  HYCOM_F_THETA = 8   /* theta(:,:,kdm), 3-D: tlev ignored (mod_cb_arrays.F90:81) */
+  HYCOM_F_THETA = 8,  /* theta(:,:,kdm), 3-D: tlev ignored (mod_cb_arrays.F90:81) */
+  HYCOM_F_Q2 = 9,     /* q2(:,:,0:kdm+1,tlev): kdm+2 slabs per slot, layer k0 = 1 is k = 0 */
+  HYCOM_F_Q2L = 10    /* (mod_cb_arrays.F90:513-514; advected and diffused when mxlmy) */
 };
 
 /* mod_dimensions.F90:33,45-49 + mod_xc tile geometry (mod_xc_mp.h:2317-3288) */
@@ -126,7 +128,10 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle *h, const double *scp2,
  * fields are diffused (tsdff_1x/2x), the non-independent thermodynamic variable is rebuilt
  * with the equation of state `sigver`, and temp, saln, th3d (:,:,:,n) are all copied back.
  * theta (read in exactly-isopycnal layers, k > nhybrd) is constant in time: upload it once
- * with hycom_tsadvc_upload(h, HYCOM_F_THETA, ...). */
+ * with hycom_tsadvc_upload(h, HYCOM_F_THETA, ...).
+ * mxlmy: q2 and q2l (both time slots, kdm+2 layers) are not in this argument list; the caller
+ * uploads them before the call with hycom_tsadvc_upload(h, HYCOM_F_Q2 | HYCOM_F_Q2L, ...) and
+ * downloads slot n afterwards (the shim does, fortran/mod_tsadvc_b200.F90). */
 int hycom_tsadvc_step(hycom_tsadvc_handle *h, int32_t m, int32_t n,
                       const hycom_tsadvc_params *prm, double *temp,
                       double *saln, double *th3d, double *tracer,

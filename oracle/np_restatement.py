@@ -326,6 +326,8 @@ def tsadvc(cb, m, n):
     uflx = halo_single_tile(g, cb.uflx, mbdy, mbdy, 13)   # halo_uv
     vflx = halo_single_tile(g, cb.vflx, mbdy, mbdy, 14)   # halo_vv
     tracer = halo_single_tile(g, cb.tracer, mbdy, mbdy) if cb.ntracr else None
+    q2 = halo_single_tile(g, cb.q2, mbdy, mbdy) if cb.mxlmy else None
+    q2l = halo_single_tile(g, cb.q2l, mbdy, mbdy) if cb.mxlmy else None
     # onetamas(:,:,m) = 1.0 (:1809), or oneta(:,:,n) when btrmas (:1806)
     oem = cb.oneta[n - 1] if cb.btrmas else np.ones((g.nrows, g.ncols))
     ip, iu, iv = cb.ip, cb.iu, cb.iv
@@ -346,8 +348,24 @@ def tsadvc(cb, m, n):
                              ip, iu, iv)[0]
         raise ValueError(cb.advtyp)
 
+    if cb.isopyc:
+        # :1859-1897 layer 1 runs on laterally smoothed mass fluxes (0.0 off the iu/iv points and
+        # outside margin mbdy-1, :1812-1813); a private copy so that the tracers keep uflx(:,:,1)
+        reg = _region(g, mbdy - 1)
+        u1, v1 = uflx[0], vflx[0]
+        vfa = np.where(_sh(iv, -1, 0) != 0, _sh(v1, -1, 0), v1)
+        vfb = np.where(_sh(iv, +1, 0) != 0, _sh(v1, +1, 0), v1)
+        ufa = np.where(_sh(iu, 0, -1) != 0, _sh(u1, 0, -1), u1)
+        ufb = np.where(_sh(iu, 0, +1) != 0, _sh(u1, 0, +1), u1)
+        with np.errstate(all="ignore"):
+            usm = np.where(reg & (iu != 0), .5 * u1 + .25 * (ufa + ufb), 0.0)
+            vsm = np.where(reg & (iv != 0), .5 * v1 + .25 * (vfa + vfb), 0.0)
+        uflx, vflx = uflx.copy(), vflx.copy()
+        uflx[0], vflx[0] = usm, vsm
     for k in range(kk):
         fco, fcn = prolog(g, uflx[k], vflx[k], cb.dp[n - 1, k], oem, cb.delt1, cb.scp2i, ip, mbdy - 1)
+        if cb.isopyc and k == 0 and not (cb.advflg == 1 and nhyb > 0):
+            th3d[n - 1, k] = adv(th3d[n - 1, k], th3d[m - 1, k], k, 32.0, fco, fcn)
         if k + 1 <= nhyb:
             if cb.advflg == 0:
                 temp[n - 1, k] = adv(temp[n - 1, k], temp[m - 1, k], k, 256.0, fco, fcn)
@@ -357,9 +375,18 @@ def tsadvc(cb, m, n):
         for q in range(cb.ntracr):
             pd = 256.0 if (q < len(cb.trcflg) and cb.trcflg[q] == 2) else 0.0
             tracer[q, n - 1, k] = adv(tracer[q, n - 1, k], tracer[q, m - 1, k], k, pd, fco, fcn)
+        if cb.mxlmy:   # :2035-2048, layer k of q2(.., 0:kk+1, ..) is index k+1
+            q2[n - 1, k + 1] = adv(q2[n - 1, k + 1], q2[m - 1, k + 1], k, 1.0, fco, fcn)
+            q2l[n - 1, k + 1] = adv(q2l[n - 1, k + 1], q2l[m - 1, k + 1], k, 1.0, fco, fcn)
     if cb.temdf2 > 0.0:
         diffuse(cb, n, temp, saln, th3d, tracer)
-    return dict(temp=temp, saln=saln, th3d=th3d, tracer=tracer)
+        if cb.mxlmy:   # :2143-2146, :2180-2183
+            for a in (q2, q2l):
+                a[n - 1] = halo_single_tile(g, a[n - 1], 2, 2)
+            for k in range(kk):
+                q2[n - 1, k + 1], q2l[n - 1, k + 1] = tsdff(g, [q2[n - 1, k + 1], q2l[n - 1, k + 1]], cb.dp[n - 1, k],
+                                                            cb.oneta[n - 1], cb, ip, iu, iv)
+    return dict(temp=temp, saln=saln, th3d=th3d, tracer=tracer, q2=q2, q2l=q2l)
 
 
 # ---- diffusion and equation of state (mod_tsadvc.F90:2138-2492, stmt_fns.h) ----------------

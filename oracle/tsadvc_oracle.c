@@ -98,6 +98,7 @@ orc_tile *orc_tile_create(int idm, int jdm, int kdm, int nbdy, int ii, int jj,
   t->tracer = ntracr > 0 ? alloc_r(P * K * 2 * (size_t)ntracr) : NULL;
   t->uflx = alloc_r(P * K); t->vflx = alloc_r(P * K);
   t->theta = alloc_r(P * K);
+  t->q2 = alloc_r(P * (K + 2) * 2); t->q2l = alloc_r(P * (K + 2) * 2); /* (0:kk+1,2), mod_cb_arrays.F90:513-514 */
   t->oneta = alloc_r(P * 2); t->onetamas = alloc_r(P * 2);
   t->uflux = alloc_r(P); t->vflux = alloc_r(P);
   t->uflux2 = alloc_r(P); t->vflux2 = alloc_r(P);
@@ -128,7 +129,7 @@ void orc_tile_destroy(orc_tile *t) {
                   t->vflux2, t->util1, t->util2, t->fmx, t->fmn, t->flx, t->fly,
                   t->fldlo, t->fmxlo, t->fmnlo, t->fax, t->fay, t->rp, t->rm,
                   t->flxdiv, t->tx1, t->ty1, t->fldao, t->fldan, t->xmin,
-                  t->xmax, t->theta};
+                  t->xmax, t->theta, t->q2, t->q2l};
   for (size_t q = 0; q < sizeof(ptrs) / sizeof(ptrs[0]); q++) free(ptrs[q]);
   free(t);
 }
@@ -141,7 +142,7 @@ double *orc_f64(orc_tile *t, const char *name) {
   F(util1); F(util2);
   F(fmx); F(fmn); F(flx); F(fly); F(fldlo); F(fmxlo); F(fmnlo); F(fax); F(fay);
   F(rp); F(rm); F(flxdiv); F(tx1); F(ty1); F(fldao); F(fldan);
-  F(xmin); F(xmax); F(theta);
+  F(xmin); F(xmax); F(theta); F(q2); F(q2l);
 #undef F
   return NULL;
 }
@@ -1365,7 +1366,6 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
     snprintf(g_err, sizeof g_err, "tsadvc: bad leapfrog slots m=%d n=%d", m, n);
     return 6;
   }
-  if (t->mxlmy) { snprintf(g_err, sizeof g_err, "tsadvc: mxlmy not restated"); return 7; }
   const int aadv = abs(t->advtyp);
   if (aadv > 4 || aadv == 3) {
     snprintf(g_err, sizeof g_err, "error: advem called with advtyp =%4d", t->advtyp);
@@ -1397,6 +1397,10 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
     orc_xctilr_type(t, t->vflx, 1, kk, l, l, 14); /* halo_vv */
     for (int ktr = 1; ktr <= t->ntracr; ktr++)
       orc_xctilr(t, t->tracer + P * K * 2 * (size_t)(ktr - 1), 1, 2 * kk, l, l);
+    if (t->mxlmy) { /* :1837-1840 */
+      orc_xctilr(t, t->q2, 1, 2 * kk + 4, l, l);
+      orc_xctilr(t, t->q2l, 1, 2 * kk + 4, l, l);
+    }
   }
   const int diag = (t->nstep % 3 == 0) || t->diagno; /* :2065 */
   t->xminmax_valid = diag;
@@ -1483,6 +1487,17 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
                       t->trcflg[ktr - 1] == 2 ? pdtemp : pdzero, t->scp2,
                       t->scp2i, t->delt1, t->btrmas);
     }
+    if (t->mxlmy) { /* :2035-2048, q2(i,j,k,t): slab k + (kk+2)*(t-1), k = 0..kk+1 */
+      const double pdq2 = 1.0; /* :1762 */
+      double *q2_n = t->q2 + P * ((size_t)k + (K + 2) * (size_t)(n - 1));
+      double *q2_m = t->q2 + P * ((size_t)k + (K + 2) * (size_t)(m - 1));
+      double *q2l_n = t->q2l + P * ((size_t)k + (K + 2) * (size_t)(n - 1));
+      double *q2l_m = t->q2l + P * ((size_t)k + (K + 2) * (size_t)(m - 1));
+      rc |= orc_advem(t, t->advtyp, q2_n, q2_m, ua, va, t->util1, t->util2, pdq2,
+                      t->scp2, t->scp2i, t->delt1, t->btrmas);
+      rc |= orc_advem(t, t->advtyp, q2l_n, q2l_m, ua, va, t->util1, t->util2, pdq2,
+                      t->scp2, t->scp2i, t->delt1, t->btrmas);
+    }
     if (rc) return rc;
     /* :2065-2084 */
     if (diag) {
@@ -1509,6 +1524,10 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
       for (int ktr = 1; ktr <= t->ntracr; ktr++)
         orc_xctilr(t, t->tracer + P * K * (2 * (size_t)(ktr - 1) + (size_t)(n - 1)),
                    1, kk, mdf, mdf);
+      if (t->mxlmy) { /* :2143-2146 */
+        orc_xctilr(t, t->q2 + P * (K + 2) * (size_t)(n - 1), 1, kk + 2, mdf, mdf);
+        orc_xctilr(t, t->q2l + P * (K + 2) * (size_t)(n - 1), 1, kk + 2, mdf, mdf);
+      }
     }
     for (int k = 1; k <= kk; k++) {
       double *temp_n = t->temp + P * ((size_t)(k - 1) + K * (size_t)(n - 1));
@@ -1526,6 +1545,9 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
       } else {
         tsdff(t, k, n, saln_n, NULL);
       }
+      if (t->mxlmy) /* :2180-2183 */
+        tsdff(t, k, n, t->q2 + P * ((size_t)k + (K + 2) * (size_t)(n - 1)),
+              t->q2l + P * ((size_t)k + (K + 2) * (size_t)(n - 1)));
       for (int ktr = 1; ktr <= t->ntracr; ktr += 2) {
         double *tr1 = t->tracer + P * K * 2 * (size_t)(ktr - 1) +
                       P * ((size_t)(k - 1) + K * (size_t)(n - 1));

@@ -48,6 +48,7 @@ typedef struct orc_tile {
   double *temp, *saln, *th3d, *dp;   /* (P,kdm,2) */
   double *tracer;                    /* (P,kdm,2,ntracr) */
   double *uflx, *vflx;               /* (P,kdm) */
+  double *q2, *q2l;                  /* (P,0:kdm+1,2) Mellor-Yamada tke fields (mxlmy) */
   double *theta;                     /* (P,kdm) isopycnic target densities, mod_cb_arrays.F90 */
   double *oneta, *onetamas;          /* (P,2) */
   double *uflux, *vflux, *uflux2, *vflux2, *util1, *util2; /* (P) */

@@ -36,7 +36,7 @@ class OracleTile:
             pass
 
     _SHAPES = {"temp": 4, "saln": 4, "th3d": 4, "dp": 4, "tracer": 5, "uflx": 3, "vflx": 3,
-               "oneta": -2, "onetamas": -2, "xmin": 1, "xmax": 1, "theta": 3}
+               "oneta": -2, "onetamas": -2, "xmin": 1, "xmax": 1, "theta": 3, "q2": 6, "q2l": 6}
 
     def f64(self, name):
         g = self.geom
@@ -46,7 +46,7 @@ class OracleTile:
         kind = self._SHAPES.get(name, 2)
         shape = {2: (g.nrows, g.ncols), 3: (g.kdm, g.nrows, g.ncols),
                  4: (2, g.kdm, g.nrows, g.ncols), 5: (self.ntracr, 2, g.kdm, g.nrows, g.ncols),
-                 -2: (2, g.nrows, g.ncols), 1: (g.kdm,)}[kind]
+                 -2: (2, g.nrows, g.ncols), 1: (g.kdm,), 6: (2, g.kdm + 2, g.nrows, g.ncols)}[kind]
         n = int(np.prod(shape))
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,)).reshape(shape)
 
@@ -102,7 +102,7 @@ class OracleTile:
     def load_cb(self, cb):
         """copy a product-side CbArrays (host numpy) into this oracle tile"""
         for name in ("scp2", "scp2i", "scuy", "scvx", "aspux", "aspvy", "temp", "saln", "th3d",
-                     "dp", "uflx", "vflx", "oneta", "theta"):
+                     "dp", "uflx", "vflx", "oneta", "theta", "q2", "q2l"):
             src = getattr(cb, name)
             if src is not None:
                 self.f64(name)[...] = src

@@ -374,3 +374,44 @@ def test_arctic_c_oracle_equals_numpy_restatement(oracle, advtyp, ntracr, extra)
 def pkg_partition_closed(g):
     import dataclasses
     return dataclasses.replace(g, nreg=1)
+
+
+# ---- mxlmy: q2, q2l advected and diffused with the thermodynamic fields (:2035-2048, :2180-2183) --
+@pytest.mark.parametrize("advtyp,temdf2,nreg", [(2, 0.0, 0), (1, 0.0, 3), (2, 0.02, 0)])
+def test_mxlmy_c_oracle_equals_numpy_restatement(oracle, advtyp, temdf2, nreg):
+    if temdf2 > 0:
+        cfg, sea, g, cb = util.make_diffusion_case(57, 44, 3, 6, 1.0, nreg=nreg, seed=5, advtyp=advtyp, temdf2=temdf2)
+    else:
+        cfg, sea, g, cb = util.make_case(57, 44, 3, nreg=nreg, seed=5, advtyp=advtyp)
+    m, n = 1, 2
+    util.add_q2(cfg, sea, g, cb, m, n)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    alt = npr.tsadvc(cb, m, n)
+    msk = util.interior_sea(cb)
+    for name in ("q2", "q2l"):
+        for k in range(1, g.kdm + 1):
+            assert _sea_eq(ref[name][n - 1, k], alt[name][n - 1, k], msk), (name, k)
+        assert not _sea_eq(ref[name][n - 1, 1], cb.__dict__[name][n - 1, 1], msk)
+        for k in (0, g.kdm + 1):      # the boundary layers are not advected
+            assert np.array_equal(ref[name][n - 1, k][msk], cb.__dict__[name][n - 1, k][msk])
+
+
+# ---- isopycnic coordinates: layer 1 on smoothed mass fluxes (:1859-1897), th3d & saln there, ----
+# ---- saln only below (:1848-1850)
+@pytest.mark.parametrize("advtyp,nreg", [(2, 0), (1, 3), (0, 0)])
+def test_isopyc_c_oracle_equals_numpy_restatement(oracle, advtyp, nreg):
+    cfg, sea, g, cb = util.make_case(57, 44, 3, nreg=nreg, seed=5, advtyp=advtyp, isopyc=True, hybrid=False, nhybrd=0)
+    m, n = 1, 2
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    alt = npr.tsadvc(cb, m, n)
+    msk = util.interior_sea(cb)
+    for k in range(g.kdm):
+        assert _sea_eq(ref["saln"][n - 1, k], alt["saln"][n - 1, k], msk), ("saln", k)
+        assert _sea_eq(ref["th3d"][n - 1, k], alt["th3d"][n - 1, k], msk), ("th3d", k)
+        assert _sea_eq(ref["temp"][n - 1, k], cb.temp[n - 1, k], msk)                       # temp is not advected
+    assert not _sea_eq(ref["th3d"][n - 1, 0], cb.th3d[n - 1, 0], msk)
+    assert _sea_eq(ref["th3d"][n - 1, 1], cb.th3d[n - 1, 1], msk)                          # th3d only in layer 1
+    hyb = util.make_case(57, 44, 3, nreg=nreg, seed=5, advtyp=advtyp)[3]
+    ref2 = util.run_oracle(oracle, hyb, sea, m, n)
+    assert not _sea_eq(ref["saln"][n - 1, 0], ref2["saln"][n - 1, 0], msk)                 # smoothing changes layer 1
+    assert _sea_eq(ref["saln"][n - 1, 1], ref2["saln"][n - 1, 1], msk)                     # ... and only layer 1

@@ -600,3 +600,58 @@ def test_arctic_device_halo_matches_xctilr(oracle):
         assert np.array_equal(dev[win], a3[win], equal_nan=True), name
     ts.close()
     ot.close()
+
+
+# ---------------------------------------------------------------------------------------
+# mxlmy: q2, q2l (layers 0..kk+1) advected and diffused with the other fields
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("advtyp,nreg,diff,extra", [(2, 0, False, {}), (1, 3, False, {}), (2, 0, True, {}),
+                                                    (2, 1, False, {"btrmas": True}), (4, 0, False, {"nhybrd": 2})])
+def test_mxlmy_host_path_matches_oracle(oracle, advtyp, nreg, diff, extra):
+    m, n = 1, 2
+    kdm = 5
+    if diff:
+        cfg, sea, g, cb = util.make_diffusion_case(90, 61, kdm, 6, 1.0, nreg=nreg, ntracr=1, seed=31, advtyp=advtyp,
+                                                   nstep=3, **extra)
+    else:
+        cfg, sea, g, cb = util.make_case(90, 61, kdm, nreg=nreg, ntracr=1, seed=31, m=m, n=n, advtyp=advtyp,
+                                         nstep=3, **extra)
+    util.add_q2(cfg, sea, g, cb, m, n)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    q2_before = cb.q2.copy()
+    got, before, launches = _run_host_path(cb, m, n)
+    _compare(cb, g, got, ref, n, ["saln", "temp"])
+    msk = util.interior_sea(cb)
+    for name in ("q2", "q2l"):
+        a, b = getattr(cb, name), ref[name]
+        for k in range(kdm + 2):
+            assert np.array_equal(a[n - 1, k][msk], b[n - 1, k][msk]), (name, k)
+        assert np.array_equal(a[m - 1], (q2_before if name == "q2" else a)[m - 1], equal_nan=True)
+    assert not np.array_equal(cb.q2[n - 1, 1][msk], q2_before[n - 1, 1][msk])
+
+
+@pytest.mark.parametrize("advtyp,nreg,temdf2", [(2, 0, 0.0), (1, 3, 0.0), (0, 1, 0.0), (4, 0, 0.0), (2, 0, 0.02)])
+def test_isopyc_host_path_matches_oracle(oracle, advtyp, nreg, temdf2):
+    """isopycnic coordinates: th3d & saln in layer 1 on smoothed fluxes, saln only below"""
+    m, n = 1, 2
+    if temdf2 > 0:
+        cfg, sea, g, cb = util.make_diffusion_case(90, 61, 4, 8, 0.0, nreg=nreg, seed=37, advtyp=advtyp, nstep=3,
+                                                   isopyc=True, hybrid=False, nhybrd=0)
+    else:
+        cfg, sea, g, cb = util.make_case(90, 61, 4, nreg=nreg, seed=37, m=m, n=n, advtyp=advtyp, nstep=3,
+                                         isopyc=True, hybrid=False, nhybrd=0)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    got, before, launches = _run_host_path(cb, m, n)
+    _compare(cb, g, got, ref, n, ["saln", "th3d"] + (["temp"] if temdf2 > 0 else []))
+    if temdf2 == 0:
+        assert np.array_equal(got["temp"], before["temp"], equal_nan=True)
+    assert np.array_equal(got["xmin"], ref["xmin"]) and np.array_equal(got["xmax"], ref["xmax"])
+
+
+def test_isopyc_with_tracers_is_refused():
+    cfg, sea, g, cb = util.make_case(40, 30, 2, ntracr=1, advtyp=2, isopyc=True, hybrid=False, nhybrd=0)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_state(1, 2)
+    with pytest.raises(cabi.TsadvcError, match="isopyc"):
+        ts.tsadvc_device(1, 2)
+    ts.close()

@@ -45,12 +45,28 @@ def oracle_tile_from_cb(oracle, cb, sea=None):
     return ot
 
 
+def add_q2(cfg, sea, g, cb, m, n):
+    """Mellor-Yamada fields q2, q2l (layers 0..kk+1, both slots) for mxlmy cases: tracer-like
+    synthetic fields, NaN halos like every array tsadvc exchanges"""
+    def lev_of(slot):
+        return 0 if slot == n else 1
+    for name, ktr in (("q2", 31), ("q2l", 32)):
+        a = np.empty((2, g.kdm + 2, g.nrows, g.ncols))
+        for slot in (1, 2):
+            a[slot - 1] = syn.fill_host(cfg, g, sea, cabi.F_TRACER, ktr, lev_of(slot), 1, g.kdm + 2, 0)
+        setattr(cb, name, a)
+    cb.mxlmy = True
+    return cb
+
+
 def run_oracle(oracle, cb, sea, m, n):
     """CPU oracle tsadvc(m,n) on a private copy of cb; returns dict of slot-n results"""
     ot = oracle_tile_from_cb(oracle, cb, sea)
     ot.tsadvc(m, n, 1)
     out = dict(temp=ot.f64("temp").copy(), saln=ot.f64("saln").copy(), th3d=ot.f64("th3d").copy(),
                xmin=ot.f64("xmin").copy(), xmax=ot.f64("xmax").copy())
+    if cb.mxlmy:
+        out["q2"], out["q2l"] = ot.f64("q2").copy(), ot.f64("q2l").copy()
     if cb.ntracr:
         out["tracer"] = ot.f64("tracer").copy()
     ot.close()
