@@ -1250,7 +1250,9 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   if ((rc = finish_step(h, n, *prm, adv, xmin, xmax))) return rc;
   if (diffuse) {  // onetamas(:,:,n) = oneta(:,:,n) (:1805,1808); th3d/temp(:,:,:,n) (:2143-2144)
     if ((rc = upload_on(h, HYCOM_F_ONETA, 0, n, 1, 1, oneta + fs * (n - 1), h->stream))) return rc;
-    if ((rc = upload_on(h, ofield, 0, n, 1, kk, h4(other, n, 0), h->stream))) return rc;
+    bool other_advected = false;   // isopyc: th3d is advected in layer 1 and already in its mirror
+    for (const Adv& a : adv) other_advected = other_advected || a.field == ofield;
+    if (!other_advected && (rc = upload_on(h, ofield, 0, n, 1, kk, h4(other, n, 0), h->stream))) return rc;
     if (single && (rc = hycom_tsadvc_diffuse_device(h, m, n, prm))) return rc;
     auto back_all = [&](int field, int ktr, double* host_n) -> int {
       double* base;
