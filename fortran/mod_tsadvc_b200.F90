@@ -60,6 +60,12 @@ c
           type(c_ptr), value        :: h, host
           integer(c_int32_t), value :: field,ktr,tlev,k0,nk
         end function
+        integer(c_int) function hycom_tsadvc_download(h,field,ktr,
+     &           tlev,k0,nk,host) bind(c,name='hycom_tsadvc_download')
+          import
+          type(c_ptr), value        :: h, host
+          integer(c_int32_t), value :: field,ktr,tlev,k0,nk
+        end function
         function hycom_tsadvc_last_error(h)
      &           bind(c,name='hycom_tsadvc_last_error')
           import
@@ -84,7 +90,9 @@ c
       type(tsadvc_params) :: p
       real, save, allocatable, target :: xmin(:),xmax(:)
       type(c_ptr) :: ptrc
-      integer rc,ktr
+      integer rc,ktr,t
+c
+      include 'stmt_fns.h'   ! for sigver: the EOS family compiled in
 c
       if     (.not.c_associated(handle)) then
 c ---   first call: device mirrors + scratch (the analogue of the lazy
@@ -128,6 +136,19 @@ c --- HOST arrays here (halo width 5 of temp,saln,tracer both slots, uflx,
 c --- vflx) so that the arrays handed over have valid halos; the device
 c --- resident mode exchanges on the device instead (INTEGRATION.md).
 c
+c --- mxlmy: q2,q2l (0:kk+1, both slots) are not in the argument list of
+c --- hycom_tsadvc_step; fill their mirrors (field ids 9, 10) around the call
+      if     (mxlmy) then
+        do t= 1,2
+          rc = hycom_tsadvc_upload(handle, 9,0,t,1,kdm+2,
+     &           c_loc(q2( 1-nbdy,1-nbdy,0,t)))
+          if (rc.ne.0) call b200_stop(rc)
+          rc = hycom_tsadvc_upload(handle,10,0,t,1,kdm+2,
+     &           c_loc(q2l(1-nbdy,1-nbdy,0,t)))
+          if (rc.ne.0) call b200_stop(rc)
+        enddo
+      endif
+c
       ptrc = c_null_ptr
       if (ntracr.gt.0) ptrc = c_loc(tracer)
       rc = hycom_tsadvc_step(handle,m,n,p,
@@ -135,6 +156,16 @@ c
      &       c_loc(dp),c_loc(uflx),c_loc(vflx),c_loc(oneta),
      &       c_loc(xmin),c_loc(xmax))
       if (rc.ne.0) call b200_stop(rc)
+      if     (mxlmy) then
+c ---   the device copy returns whole slabs: the halo of q2,q2l(:,:,:,n)
+c ---   comes back as the exchange left it (valid to width mbdy)
+        rc = hycom_tsadvc_download(handle, 9,0,n,1,kdm+2,
+     &         c_loc(q2( 1-nbdy,1-nbdy,0,n)))
+        if (rc.ne.0) call b200_stop(rc)
+        rc = hycom_tsadvc_download(handle,10,0,n,1,kdm+2,
+     &         c_loc(q2l(1-nbdy,1-nbdy,0,n)))
+        if (rc.ne.0) call b200_stop(rc)
+      endif
 c
 c --- xmin/xmax now hold this tile's salinity range per layer when
 c --- mod(nstep,3).eq.0 or diagno: xcminr/xcmaxr and the negative-salinity
