@@ -576,13 +576,26 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   P.g.mask64 = h->static_block + 2 * h->slab;
   P.g.delt1 = p.delt1; P.g.onemm = p.onemm;
   const char* cn = getenv("HYCOM_TSADVC_NC");
-  // cells per lane (tuning knobs HYCOM_TSADVC_NC / _MINB / _CHUNK_ROWS; defaults measured on
-  // B200: FCT2 1 cell per lane at 4 blocks per SM, MPDATA 2 cells per lane at 2 blocks)
-  P.nc = (aadv == 0 || aadv == 4) ? 1 : cn ? (atoi(cn) == 2 ? 2 : 1) : (aadv == 1 ? 2 : 1);
+  // cells per lane (tuning knobs HYCOM_TSADVC_NC / _MINB / _CHUNK_ROWS).  Defaults measured on B200
+  // (profiles/r01p_variants.txt): FCT2 and MPDATA 2 cells per lane at 2 blocks per SM (11.8 warp-
+  // instructions per useful cell against 15.4 with one cell per lane), FCT4 and PCM 1 cell per lane
+  P.nc = (aadv == 0 || aadv == 4) ? 1 : cn ? (atoi(cn) == 2 ? 2 : 1) : 2;
   const char* cb = getenv("HYCOM_TSADVC_MINB");
-  P.minb = cb ? atoi(cb) : 3;
+  P.minb = cb ? atoi(cb) : (P.nc == 2 ? 2 : 3);
+  // rows one warp marches: long chunks amortise the 6 rows of pipeline fill (1024: 0.6 %), but the
+  // launch needs about ten waves of blocks to hide the tail - small tiles get shorter chunks
   const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
-  int chunk_rows = ce ? atoi(ce) : 512;
+  int chunk_rows;
+  if (ce) {
+    chunk_rows = atoi(ce);
+  } else {
+    const long per_chunk = (long)P.njobs * strip_count(h->pitch, P.nc);          // warps per chunk row-band
+    const long want = 10L * 148 * P.minb * kWarpsPerBlock;
+    const long nch = (want + per_chunk - 1) / per_chunk;
+    chunk_rows = (int)((h->nrows + nch - 1) / (nch > 0 ? nch : 1));
+    if (chunk_rows > 1024) chunk_rows = 1024;
+    if (chunk_rows < 128) chunk_rows = 128;
+  }
   if (chunk_rows < 8) chunk_rows = 8;
 
   // (strip,row) rectangles of this part.  Interior = units whose staged window (apron and
@@ -624,7 +637,6 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     else { CU(h, cudaEventCreate(&ev.first)); CU(h, cudaEventCreate(&ev.second)); }
     CU(h, cudaEventRecord(ev.first, h->stream));
   }
-  if (!cb) P.minb = (P.nc == 2) ? 2 : 3;
   rc = launch_march_tma(aadv, P, h->stream);
   h->launches += 1;
   if (h->timing) {
