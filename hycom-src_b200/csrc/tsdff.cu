@@ -21,6 +21,8 @@
 // points.  The output goes to the ping-pong buffer (neighbours read the old values).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "eos.cuh"
 #include "march_common.cuh"   // div_rn: IEEE round-to-nearest a/b, short sequence + exact fallback
 #include "tsadvc_dev.h"
@@ -43,8 +45,8 @@ __device__ __forceinline__ double harmonc(double aa, double bb) {
 // One thread owns one (i,j) column and walks the layers: everything that does not depend on k
 // (masks, temdf2*aspux*scuy, temdf2*aspvy*scvx, scp2, oneta at the five points) is loaded and
 // formed once and stays in registers, so per layer the thread reads dp and the fields only.
-template <bool EOS>
-__global__ void __launch_bounds__(256, 3) k_tsdff(const DiffParams P) {
+template <bool EOS, int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_tsdff(const DiffParams P) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r = blockIdx.y * 8 + threadIdx.y;
   if (c >= P.pitch || r >= P.nrows) return;
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256, 3) k_tsdff(const DiffParams P) {
   const double scp2 = P.scp2[q];
   // every neighbour of a cell tsadvc writes exists in the slab, so all loads are unconditional
   // (issued together, read-only path) and land neighbours are removed by select afterwards
-#pragma unroll 2
+#pragma unroll UNROLL
   for (int k0 = 0; k0 < P.kk; ++k0) {
     const long ko = (long)k0 * P.slab;
     const long qk = q + ko;
@@ -177,8 +179,15 @@ int launch_isopyc_smooth(const double* u, const double* v, double* us, double* v
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream) {
   const dim3 block(32, 8), grid((P.pitch + 31) / 32, (P.nrows + 7) / 8);
-  if (P.eos) k_tsdff<true><<<grid, block, 0, stream>>>(P);
-  else k_tsdff<false><<<grid, block, 0, stream>>>(P);
+  static const int variant = [] { const char* e = getenv("HYCOM_TSADVC_TSDFF_VARIANT"); return e ? atoi(e) : 0; }();
+  if (P.eos) {
+    if (variant == 1) k_tsdff<true, 2, 2><<<grid, block, 0, stream>>>(P);
+    else if (variant == 2) k_tsdff<true, 1, 4><<<grid, block, 0, stream>>>(P);
+    else if (variant == 3) k_tsdff<true, 1, 3><<<grid, block, 0, stream>>>(P);
+    else k_tsdff<true, 2, 3><<<grid, block, 0, stream>>>(P);
+  } else {
+    k_tsdff<false, 2, 3><<<grid, block, 0, stream>>>(P);
+  }
   return (int)cudaGetLastError();
 }
 
