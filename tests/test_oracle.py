@@ -415,3 +415,24 @@ def test_isopyc_c_oracle_equals_numpy_restatement(oracle, advtyp, nreg):
     ref2 = util.run_oracle(oracle, hyb, sea, m, n)
     assert not _sea_eq(ref["saln"][n - 1, 0], ref2["saln"][n - 1, 0], msk)                 # smoothing changes layer 1
     assert _sea_eq(ref["saln"][n - 1, 1], ref2["saln"][n - 1, 1], msk)                     # ... and only layer 1
+
+
+# ---- frozen vectors (tests/golden): the oracle and the numpy restatement reproduce them ---------
+import json as _json
+import os as _os
+
+_GOLD = _json.load(open(_os.path.join(_os.path.dirname(__file__), "golden", "tsadvc_golden.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_GOLD))
+def test_oracle_reproduces_golden_vectors(oracle, name):
+    import sys
+    sys.path.insert(0, _os.path.join(_os.path.dirname(__file__), "golden"))
+    import make_golden
+    got, (cfg, sea, g, cb) = make_golden.run_oracle_case(oracle, name)
+    assert got == _GOLD[name], name
+    # and so does the independent restatement (the golden bits are not the C code's private opinion)
+    alt = npr.tsadvc(cb, 1, 2)
+    msk = util.interior_sea(cb)
+    flds = dict(temp=alt["temp"], saln=alt["saln"], th3d=alt["th3d"], tracer=alt.get("tracer"))
+    assert make_golden.digest(flds, msk, 2) == _GOLD[name], (name, "numpy restatement")

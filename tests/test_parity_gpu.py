@@ -655,3 +655,26 @@ def test_isopyc_with_tracers_is_refused():
     with pytest.raises(cabi.TsadvcError, match="isopyc"):
         ts.tsadvc_device(1, 2)
     ts.close()
+
+
+# ---------------------------------------------------------------------------------------
+# frozen vectors (tests/golden/tsadvc_golden.json): the CUDA path reproduces their bits
+# ---------------------------------------------------------------------------------------
+import json as _json
+import os as _os
+
+_GOLD = _json.load(open(_os.path.join(_os.path.dirname(__file__), "golden", "tsadvc_golden.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_GOLD))
+def test_golden_vectors_on_device(name):
+    import sys
+    sys.path.insert(0, _os.path.join(_os.path.dirname(__file__), "golden"))
+    import make_golden
+    kind, kw = make_golden.CASES[name]
+    cfg, sea, g, cb = make_golden.build(kind, kw)
+    got, before, launches = _run_host_path(cb, 1, 2)
+    assert launches > 0
+    msk = util.interior_sea(cb)
+    flds = dict(temp=got["temp"], saln=got["saln"], th3d=got["th3d"], tracer=got["tracer"])
+    assert make_golden.digest(flds, msk, 2) == _GOLD[name], name
