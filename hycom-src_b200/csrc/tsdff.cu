@@ -21,8 +21,6 @@
 // points.  The output goes to the ping-pong buffer (neighbours read the old values).
 #include <cuda_runtime.h>
 
-#include <cstdlib>
-
 #include "eos.cuh"
 #include "march_common.cuh"   // div_rn: IEEE round-to-nearest a/b, short sequence + exact fallback
 #include "tsadvc_dev.h"
@@ -179,15 +177,11 @@ int launch_isopyc_smooth(const double* u, const double* v, double* us, double* v
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream) {
   const dim3 block(32, 8), grid((P.pitch + 31) / 32, (P.nrows + 7) / 8);
-  static const int variant = [] { const char* e = getenv("HYCOM_TSADVC_TSDFF_VARIANT"); return e ? atoi(e) : 0; }();
-  if (P.eos) {
-    if (variant == 1) k_tsdff<true, 2, 2><<<grid, block, 0, stream>>>(P);
-    else if (variant == 2) k_tsdff<true, 1, 4><<<grid, block, 0, stream>>>(P);
-    else if (variant == 3) k_tsdff<true, 1, 3><<<grid, block, 0, stream>>>(P);
-    else k_tsdff<true, 2, 3><<<grid, block, 0, stream>>>(P);
-  } else {
-    k_tsdff<false, 2, 3><<<grid, block, 0, stream>>>(P);
-  }
+  // measured on B200 (profiles/r01q_tsdff_variants.txt): the kernel is load-latency bound, the
+  // variant with the most resident warps wins (64 registers, 4 blocks per SM: 15.5 ms at GLBb0.08
+  // against 17.1 with unroll 2 at 80 registers and 21.1 with unroll 2 at 103)
+  if (P.eos) k_tsdff<true, 1, 4><<<grid, block, 0, stream>>>(P);
+  else k_tsdff<false, 1, 4><<<grid, block, 0, stream>>>(P);
   return (int)cudaGetLastError();
 }
 
