@@ -21,6 +21,8 @@
 // points.  The output goes to the ping-pong buffer (neighbours read the old values).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "eos.cuh"
 #include "march_common.cuh"   // div_rn: IEEE round-to-nearest a/b, short sequence + exact fallback
 #include "tsadvc_dev.h"
@@ -180,8 +182,14 @@ int launch_tsdff(const DiffParams& P, cudaStream_t stream) {
   // measured on B200 (profiles/r01q_tsdff_variants.txt): the kernel is load-latency bound, the
   // variant with the most resident warps wins (64 registers, 4 blocks per SM: 15.5 ms at GLBb0.08
   // against 17.1 with unroll 2 at 80 registers and 21.1 with unroll 2 at 103)
-  if (P.eos) k_tsdff<true, 1, 4><<<grid, block, 0, stream>>>(P);
-  else k_tsdff<false, 1, 4><<<grid, block, 0, stream>>>(P);
+  static const int variant = [] { const char* e = getenv("HYCOM_TSADVC_TSDFF_VARIANT"); return e ? atoi(e) : 0; }();
+  if (P.eos) {
+    if (variant == 5) k_tsdff<true, 1, 5><<<grid, block, 0, stream>>>(P);
+    else if (variant == 6) k_tsdff<true, 1, 6><<<grid, block, 0, stream>>>(P);
+    else k_tsdff<true, 1, 4><<<grid, block, 0, stream>>>(P);
+  } else {
+    k_tsdff<false, 1, 4><<<grid, block, 0, stream>>>(P);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -59,3 +59,47 @@ class NumpyHaloBackend:
                 blk = a[:, rs, cs]
                 blk[...] = buf[off:off + blk.size].reshape(blk.shape)
                 off += blk.size
+
+
+class NumpyStagedBackend(NumpyHaloBackend):
+    """the second (diffusion, width 2) and the in-scheme (fct2c, width 5, per layer batch) exchanges of
+    XcExchange with numpy arrays in place of the device mirrors"""
+
+    def __init__(self, geom, arrays, diff_arrays, batch_arrays):
+        super().__init__(geom, arrays)
+        self.diff_arrays, self.batch_arrays = diff_arrays, batch_arrays
+
+    def _xfer(self, arrays, bufs, recv, mh, nh):
+        for d in range(8):
+            rs, cs = region(self.geom, d, recv, mh, nh)
+            if not recv:
+                if bufs[d] is not None:
+                    bufs[d].copy_(torch.from_numpy(np.concatenate([a[:, rs, cs].ravel() for a in arrays])))
+                continue
+            if bufs[d] is None:
+                for a in arrays:
+                    a[:, rs, cs] = 0.0
+                continue
+            buf, off = bufs[d].numpy(), 0
+            for a in arrays:
+                blk = a[:, rs, cs]
+                blk[...] = buf[off:off + blk.size].reshape(blk.shape)
+                off += blk.size
+
+    def diff_counts(self, n):
+        return xc.halo_counts(self.geom, sum(a.shape[0] for a in self.diff_arrays), 2, 2)
+
+    def diff_pack(self, n, send, stream=None):
+        self._xfer(self.diff_arrays, send, False, 2, 2)
+
+    def diff_unpack(self, n, recv, stream=None):
+        self._xfer(self.diff_arrays, recv, True, 2, 2)
+
+    def fct2c_counts(self, m, n, batch):
+        return xc.halo_counts(self.geom, sum(a.shape[0] for a in self.batch_arrays[batch]), 5, 5)
+
+    def fct2c_pack(self, m, n, batch, send, stream=None):
+        self._xfer(self.batch_arrays[batch], send, False, 5, 5)
+
+    def fct2c_unpack(self, m, n, batch, recv, stream=None):
+        self._xfer(self.batch_arrays[batch], recv, True, 5, 5)

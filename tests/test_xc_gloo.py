@@ -79,6 +79,66 @@ def _worker(rank, world, port, itdm, jtdm, ipr, jpr, nreg, q):
         dist.destroy_process_group()
 
 
+def _worker_staged(rank, world, port, itdm, jtdm, ipr, jpr, nreg, q):
+    """the schedule of the diffusion exchange (width 2) and of the per-batch fct2c exchanges"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import np_halo
+        kk = 3
+        g = pkg.partition(itdm, jtdm, kk, ipr, jpr, nreg)[rank]
+        nb = g.nbdy
+
+        def make(a, layers):
+            arr = np.full((layers, g.nrows, g.ncols), np.nan)
+            jj_, ii_ = np.meshgrid(np.arange(1, g.jj + 1), np.arange(1, g.ii + 1), indexing="ij")
+            for k in range(layers):
+                arr[k, nb:nb + g.jj, nb:nb + g.ii] = _field(g.i0 + ii_, g.j0 + jj_, k, a)
+            return arr
+        diff = [make(a, kk) for a in (10, 11, 12)]
+        batches = {0: [make(20, 2), make(21, 2)], 1: [make(22, 1), make(23, 1)]}   # 2 + 1 layers
+        be = np_halo.NumpyStagedBackend(g, [], diff, batches)
+        ex = pkg.XcExchange(None, dist, backend=be)
+        ok = True
+
+        def check(arrays, ids, w):
+            good = True
+            for arr, a in zip(arrays, ids):
+                exp = _expected(g, a, arr.shape[0], w, w)
+                live = ~np.isnan(exp)
+                good = good and np.array_equal(arr[live], exp[live]) and np.isnan(arr[~live]).all()
+            return good
+        for _ in range(2):
+            ex._exchange(("diff", 2), lambda: be.diff_counts(2), lambda s, st: be.diff_pack(2, s, st),
+                         lambda r, st: be.diff_unpack(2, r, st))
+        ok = ok and check(diff, (10, 11, 12), 2)
+        for b in (0, 1):
+            for _ in range(2):
+                ex._exchange(("fct2c", b), lambda: be.fct2c_counts(1, 2, b), lambda s, st: be.fct2c_pack(1, 2, b, s, st),
+                             lambda r, st: be.fct2c_unpack(1, 2, b, r, st))
+        ok = ok and check(batches[0], (20, 21), 5) and check(batches[1], (22, 23), 5)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,itdm,jtdm,ipr,jpr,nreg", [(2, 57, 41, 2, 1, 0), (2, 44, 36, 1, 2, 3), (4, 45, 38, 2, 2, 3)])
+def test_staged_exchanges_over_gloo(world, itdm, jtdm, ipr, jpr, nreg):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_staged, args=(r, world, port, itdm, jtdm, ipr, jpr, nreg, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res.values()), res
+
+
 CASES = [
     (2, 57, 41, 2, 1, 0),   # BASELINE configs[3] at 2 GPUs: 2x1 tiles, closed basin, ragged split
     (2, 40, 37, 1, 2, 1),   # 1x2 tiles, periodic in i: E/W wrap onto the tile itself
