@@ -884,20 +884,63 @@ int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p)
     double* t = mi->lev[n - 1]; mi->lev[n - 1] = mi->spare; mi->spare = t;
     return 0;
   };
-  D.eos = 1;
+  // default: the marching kernel (rows staged by the TMA engine, shared face factors);
+  // HYCOM_TSADVC_TSDFF=column selects the first, column-per-thread kernel (kept for comparison)
+  const char* ev = getenv("HYCOM_TSADVC_TSDFF");
+  const bool column = ev && !strcmp(ev, "column");
+  DiffMarchParams M;
+  memset(&M, 0, sizeof M);
+  if (!column) {
+    if (!h->diff_static && (rc = dalloc_field(h, &h->diff_static, 2 * (size_t)h->slab))) return rc;
+    rc = launch_diff_static(h->aspux, h->scuy, h->aspvy, h->scvx, p.temdf2, h->diff_static,
+                            h->diff_static + h->slab, h->slab, h->stream);
+    h->launches += 1;
+    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    M.dp = dpn; M.oneta = on; M.au = h->diff_static; M.av = h->diff_static + h->slab;
+    M.scp2 = h->scp2; M.mask64 = h->static_block + 2 * h->slab; M.theta = h->theta.lev[0];
+    M.slab = h->slab; M.pitch = h->pitch; M.nrows = h->nrows; M.kk = kk;
+    M.nstrips = (h->pitch + 1 + 29) / 30;
+    // about ten waves of 4-warp blocks at 4 blocks per SM
+    const long per_chunk = (long)kk * M.nstrips, want = 10L * 148 * 4 * 4;
+    const long nch = (want + per_chunk - 1) / per_chunk;
+    M.chunk_rows = (int)((h->nrows + nch - 1) / (nch > 0 ? nch : 1));
+    if (M.chunk_rows > 1024) M.chunk_rows = 1024;
+    if (M.chunk_rows < 64) M.chunk_rows = 64;
+    M.nchunks = (h->nrows + M.chunk_rows - 1) / M.chunk_rows;
+    M.nunits = (long)kk * M.nstrips * M.nchunks;
+    M.nhybrd = nhyb; M.isopyc = p.isopyc; M.eosc = D.eosc;
+    M.temdfc = p.temdfc; M.thbase = p.thbase; M.delt1 = p.delt1;
+  }
+  // one launch group: nf fields sharing the face factors (column kernel: any nf; march: 1..3)
+  auto launch_group = [&](int eos) -> int {
+    int r2;
+    if (column) {
+      D.eos = eos;
+      r2 = launch_tsdff(D, h->stream);
+      h->launches += 1;
+    } else {
+      r2 = 0;
+      for (int f0 = 0; f0 < D.nf && !r2; f0 += eos ? 3 : 2) {   // tsdff_2x pairs, a last tsdff_1x (:2190-2198)
+        M.eos = eos;
+        M.nf = eos ? 3 : (D.nf - f0 >= 2 ? 2 : 1);
+        for (int q = 0; q < M.nf; ++q) { M.in[q] = D.f[f0 + q].in; M.out[q] = D.f[f0 + q].out; }
+        r2 = launch_tsdff_march(M, h->stream);
+        h->launches += 1;
+      }
+    }
+    if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s",
+                        r2 > 0 ? cudaGetErrorString((cudaError_t)r2) : "bad field group");
+    return 0;
+  };
   if ((rc = add(HYCOM_F_TEMP, 0)) || (rc = add(HYCOM_F_SALN, 0)) || (rc = add(HYCOM_F_TH3D, 0))) return rc;
-  rc = launch_tsdff(D, h->stream);
-  h->launches += 1;
-  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  if ((rc = launch_group(1))) return rc;
   swap(HYCOM_F_TEMP, 0); swap(HYCOM_F_SALN, 0); swap(HYCOM_F_TH3D, 0);
   if (h->d.ntracr > 0 || p.mxlmy) {   // :2180-2198: q2 & q2l, then the tracers, same face factors
-    D.eos = 0; D.nf = 0;
+    D.nf = 0;
     if (p.mxlmy && ((rc = add(HYCOM_F_Q2, 0)) || (rc = add(HYCOM_F_Q2L, 0)))) return rc;
     for (int t = 1; t <= h->d.ntracr; ++t)
       if ((rc = add(HYCOM_F_TRACER, t))) return rc;
-    rc = launch_tsdff(D, h->stream);
-    h->launches += 1;
-    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if ((rc = launch_group(0))) return rc;
     if (p.mxlmy && ((rc = swap(HYCOM_F_Q2, 0)) || (rc = swap(HYCOM_F_Q2L, 0)))) return rc;
     for (int t = 1; t <= h->d.ntracr; ++t) swap(HYCOM_F_TRACER, t);
   }

@@ -47,6 +47,7 @@ struct hycom_tsadvc_handle {
   uint8_t* fct2c_lcalc = nullptr;
   long fct2c_slabs = 0;
   int fct2c_nb = 0;
+  double* diff_static = nullptr;   // au | av: temdf2*aspux*scuy, temdf2*aspvy*scvx (2 slabs), per call
   double* isopyc_flux = nullptr;   // smoothed uflux | vflux of layer 1 (isopyc), 2 slabs
   double* d_minmax = nullptr;  // 2*kdm
   uint8_t* d_sea = nullptr;    // synthetic generator: global sea mask

@@ -115,6 +115,24 @@ struct DiffParams {
 };
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream);
+
+// the marching form (k_tsdff_march): nf fields of one launch group, all kk layers
+struct DiffMarchParams {
+  const double* in[3];
+  double* out[3];
+  int nf, eos;
+  const double *dp, *oneta, *au, *av, *scp2, *mask64, *theta;
+  long slab;
+  int pitch, nrows, kk;
+  int nstrips, chunk_rows, nchunks;
+  long nunits;          // kk * nstrips * nchunks warps
+  int nhybrd, isopyc;
+  eos::Coef eosc;
+  double temdfc, thbase, delt1;
+};
+int launch_tsdff_march(const DiffMarchParams& P, cudaStream_t stream);
+int launch_diff_static(const double* aspux, const double* scuy, const double* aspvy, const double* scvx,
+                       double temdf2, double* au, double* av, long n, cudaStream_t stream);
 // uflux, vflux of mod_tsadvc.F90:1859-1897 from uflx(:,:,1), vflx(:,:,1)
 int launch_isopyc_smooth(const double* u, const double* v, double* us, double* vs, const uint8_t* mask,
                          int pitch, int nrows, int nbdy, int ii, int jj, int margin, cudaStream_t stream);

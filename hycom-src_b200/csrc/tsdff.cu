@@ -24,7 +24,7 @@
 #include <cstdlib>
 
 #include "eos.cuh"
-#include "march_common.cuh"   // div_rn: IEEE round-to-nearest a/b, short sequence + exact fallback
+#include "march_tma_common.cuh"   // div_rn (exact a/b), mbarrier / bulk-copy helpers of the TMA-staged march
 #include "tsadvc_dev.h"
 #include "tsadvc_launch.h"
 
@@ -168,6 +168,186 @@ __global__ void __launch_bounds__(256) k_isopyc_smooth(const double* __restrict_
   vs[q] = vo;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The marching form of the same computation: one warp owns a strip of 32 columns of one layer and
+// walks along j; the rows of every operand are staged through a shared-memory ring by the TMA
+// engine (cp.async.bulk + one mbarrier per slot, three rows in flight) exactly like the advection
+// (march_tma_common.cuh).  Marching lets neighbouring cells share their face factors: the north
+// face of row r-1 is the south face of row r (carried in a register), the east face of column i
+// is the west face of column i+1 (one shuffle) - two harmonc divisions per cell instead of four -
+// and every operand is read from HBM once.  Dependency radius 1: a strip yields 30 columns.
+//   ring slot = [fld_0 .. fld_NF-1 | dp | oneta | au | av | scp2 | mask words], 256 B each
+// ---------------------------------------------------------------------------------------------
+template <int NF>
+struct DRing {
+  static constexpr int RB = 256, NARR = NF + 6, SLOT = NARR * RB, NSLOT = 6, BYTES = NSLOT * SLOT;
+  enum { DPA = NF, ON = NF + 1, AU = NF + 2, AV = NF + 3, SC = NF + 4, MSK = NF + 5 };
+};
+constexpr int kDiffUse = 30;   // columns a strip yields; its first staged column is 30*s - 2 (even)
+
+template <int NF>
+__device__ __forceinline__ void diff_issue_row(const DiffMarchParams& P, const double* const (&src)[NF + 6],
+                                               int nrows, int pitch, int r, uint32_t ring_s, uint32_t bar_s,
+                                               int slot) {
+  typedef DRing<NF> R;
+  const uint32_t bar = bar_s + 8u * slot, dst = ring_s + (uint32_t)(slot * R::SLOT);
+  const long off = (long)max(0, min(r, nrows - 1)) * pitch;
+  mbar_expect_tx(bar, R::SLOT);
+#pragma unroll
+  for (int a = 0; a < R::NARR; ++a) bulk_g2s(dst + a * R::RB, src[a] + off, R::RB, bar);
+}
+
+template <int NF, bool EOS>
+__global__ void __launch_bounds__(128, 4) k_tsdff_march(const DiffMarchParams P) {
+  typedef DRing<NF> R;
+  extern __shared__ unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const long unit = (long)blockIdx.x * 4 + wid;
+  if (unit >= P.nunits) return;
+  // layer fastest: the warps that run together share the 2-D operands through L2
+  const int k0 = (int)(unit % P.kk);
+  const long t0 = unit / P.kk;
+  const int strip = (int)(t0 % P.nstrips), chunk = (int)(t0 / P.nstrips);
+  const int w0 = strip * kDiffUse - 2;
+  const int j0 = chunk * P.chunk_rows, j1 = min(j0 + P.chunk_rows, P.nrows);
+  const uint32_t s0 = smem_u32(smem_raw);
+  const uint32_t pad = ((s0 + 127u) & ~127u) - s0;
+  const unsigned char* ring = smem_raw + pad + wid * R::BYTES;
+  const uint32_t ring_s = s0 + pad + wid * R::BYTES;
+  const uint32_t bar_s = s0 + pad + 4 * R::BYTES + wid * 64;
+  const long ko = (long)k0 * P.slab + w0;
+  const double* src[R::NARR];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) src[f] = P.in[f] + ko;
+  src[R::DPA] = P.dp + ko;
+  src[R::ON] = P.oneta + w0; src[R::AU] = P.au + w0; src[R::AV] = P.av + w0;
+  src[R::SC] = P.scp2 + w0; src[R::MSK] = P.mask64 + w0;
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < R::NSLOT; ++q) mbar_init(bar_s + 8u * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int r0 = j0 - 1;                                   // two warm-up rows: see the header of the loop
+  const int niter = ((j1 - j0) + 2 + 5) / 6 * 6;
+  {   // rows r0-2, r0-1 ("below the chunk"): zeros, all land
+    double* z = reinterpret_cast<double*>(const_cast<unsigned char*>(ring) + 4 * R::SLOT);
+    for (int i = lane; i < 2 * R::SLOT / 8; i += 32) z[i] = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+  }
+  if (elect_one()) {
+    diff_issue_row<NF>(P, src, P.nrows, P.pitch, r0, ring_s, bar_s, 0);
+    diff_issue_row<NF>(P, src, P.nrows, P.pitch, r0 + 1, ring_s, bar_s, 1);
+    diff_issue_row<NF>(P, src, P.nrows, P.pitch, r0 + 2, ring_s, bar_s, 2);
+  }
+  const unsigned char* pc = ring + 8 * lane;
+  const unsigned char* pw = ring + 8 * max(lane - 1, 0);
+  const unsigned char* pe = ring + 8 * min(lane + 1, 31);
+  auto at = [](const unsigned char* q, int slot, int arr) {
+    return *reinterpret_cast<const double*>(q + slot * R::SLOT + arr * R::RB);
+  };
+  auto mask_at = [](const unsigned char* q, int slot) {
+    return *reinterpret_cast<const unsigned*>(q + slot * R::SLOT + R::MSK * R::RB);
+  };
+  // carried from the previous row: dp*oneta and the mask of the centre row, its south face factor
+  double hc = 0.0, gs = 0.0;
+  unsigned mc = 0u;
+  uint32_t round = 0;
+  const int k = k0 + 1;
+  const bool ldtemp = k <= P.nhybrd && P.temdfc > 0.0;                               // :2170
+  const bool ldth3d = (k <= P.nhybrd && P.temdfc < 1.0) || (k == 1 && P.isopyc);     // :2171-2172
+  // step t: row r = r0+t is the NORTH row (slot t%6), r-1 the centre (stored when inside the
+  // chunk), r-2 the south row.  t = 0,1 only build the carried values for the first stored row.
+  for (int t = 0; t < niter; ++t) {
+    const int sn = t % 6, sc_ = (t + 5) % 6, ss = (t + 4) % 6;
+    mbar_wait(bar_s + 8u * sn, round & 1u);
+    const int r = r0 + t, rc = r - 1;
+    const unsigned mn = mask_at(pc, sn);
+    const double hn = at(pc, sn, R::DPA) * at(pc, sn, R::ON);
+    // east and north face factors of the centre cell (west = east of the lane to the left, south =
+    // north of the previous row)
+    const double he = shdn(hc);
+    const unsigned me = __shfl_down_sync(TSADVC_FULLMASK, mc, 1);
+    const bool fe = me & M_IU, fn = mn & M_IV, fw = mc & M_IU, fs = mc & M_IV;
+    const double ge = fe ? at(pe, sc_, R::AU) * harmonc(hc, he) : 0.0;
+    const double gn = fn ? at(pc, sn, R::AV) * harmonc(hc, hn) : 0.0;
+    const double gw = shup(ge);
+    const double factor = div_rn(-P.delt1, at(pc, sc_, R::SC) * dmax(hc, 1.0e-20));   // :2314-2315
+    double v[NF], old[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const double x = at(pc, sc_, f);
+      const double uw = fw ? gw * (at(pw, sc_, f) - x) : 0.0;
+      const double ue = fe ? ge * (x - at(pe, sc_, f)) : 0.0;
+      const double vs = fs ? gs * (at(pc, ss, f) - x) : 0.0;
+      const double vn = fn ? gn * (x - at(pc, sn, f)) : 0.0;
+      const double util = ((ue - uw) + (vn - vs)) * factor;
+      const bool on_ = !EOS || f == 1 || (f == 0 ? ldtemp : ldth3d);   // :2173-2185
+      old[f] = x;
+      v[f] = on_ ? x + util : x;
+    }
+    const int col = w0 + lane;
+    if (lane >= 1 && lane <= kDiffUse && (unsigned)col < (unsigned)P.pitch && rc >= j0 && rc < j1) {
+      const long qk = (long)k0 * P.slab + (long)rc * P.pitch + col;
+      const bool wr = mc & M_OUT;
+      if (EOS) {   // :2199-2229
+        double tt = v[0], s = v[1], h = v[NF - 1];
+        if (wr) {
+          if (ldtemp && ldth3d) {
+            const double th3d_t = eos::sig(P.eosc, tt, s) - P.thbase;
+            h = (1.0 - P.temdfc) * h + P.temdfc * th3d_t;
+            tt = eos::tofsig(P.eosc, h + P.thbase, s);
+          } else if (ldtemp) {
+            h = eos::sig(P.eosc, tt, s) - P.thbase;
+          } else if (ldth3d) {
+            tt = eos::tofsig(P.eosc, h + P.thbase, s);
+          } else {
+            h = P.theta[qk];
+            tt = eos::tofsig(P.eosc, h + P.thbase, s);
+          }
+        }
+        P.out[0][qk] = wr ? tt : old[0];
+        P.out[1][qk] = wr ? s : old[1];
+        P.out[NF - 1][qk] = wr ? h : old[NF - 1];
+      } else {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) P.out[f][qk] = wr ? v[f] : old[f];
+      }
+    }
+    hc = hn; gs = gn; mc = mn;
+    __syncwarp();
+    if (t + 3 < niter && elect_one())
+      diff_issue_row<NF>(P, src, P.nrows, P.pitch, r + 3, ring_s, bar_s, (t + 3) % 6);
+    if (sn == 5) ++round;
+  }
+}
+
+template <int NF, bool EOS>
+static int launch_diff_march_variant(const DiffMarchParams& P, cudaStream_t stream) {
+  static bool attr_set = false;
+  const int bytes = 4 * (DRing<NF>::BYTES + 64) + 128;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tsdff_march<NF, EOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long nblocks = (P.nunits + 3) / 4;
+  k_tsdff_march<NF, EOS><<<(unsigned)nblocks, 128, bytes, stream>>>(P);
+  return (int)cudaGetLastError();
+}
+
+// au = temdf2*aspux*scuy, av = temdf2*aspvy*scvx (left to right, as the face factors are written)
+__global__ void k_diff_static(const double* __restrict__ aspux, const double* __restrict__ scuy,
+                              const double* __restrict__ aspvy, const double* __restrict__ scvx, double temdf2,
+                              double* __restrict__ au, double* __restrict__ av, long n) {
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) {
+    au[q] = temdf2 * aspux[q] * scuy[q];
+    av[q] = temdf2 * aspvy[q] * scvx[q];
+  }
+}
+
 }  // namespace
 
 int launch_isopyc_smooth(const double* u, const double* v, double* us, double* vs, const uint8_t* mask,
@@ -175,6 +355,21 @@ int launch_isopyc_smooth(const double* u, const double* v, double* us, double* v
   const dim3 block(32, 8), grid((pitch + 31) / 32, (nrows + 7) / 8);
   k_isopyc_smooth<<<grid, block, 0, stream>>>(u, v, us, vs, mask, pitch, nrows, nbdy, ii, jj, margin);
   return (int)cudaGetLastError();
+}
+
+int launch_diff_static(const double* aspux, const double* scuy, const double* aspvy, const double* scvx,
+                       double temdf2, double* au, double* av, long n, cudaStream_t stream) {
+  k_diff_static<<<148 * 4, 256, 0, stream>>>(aspux, scuy, aspvy, scvx, temdf2, au, av, n);
+  return (int)cudaGetLastError();
+}
+
+// nf = 3 with eos (temp, saln, th3d), or 1 / 2 plain fields
+int launch_tsdff_march(const DiffMarchParams& P, cudaStream_t stream) {
+  if (P.nunits <= 0) return 0;
+  if (P.eos && P.nf == 3) return launch_diff_march_variant<3, true>(P, stream);
+  if (!P.eos && P.nf == 2) return launch_diff_march_variant<2, false>(P, stream);
+  if (!P.eos && P.nf == 1) return launch_diff_march_variant<1, false>(P, stream);
+  return -1;
 }
 
 int launch_tsdff(const DiffParams& P, cudaStream_t stream) {
