@@ -216,6 +216,7 @@ def run_b200(args):
     xc = None
     if world > 1:
         xc = pkg.XcExchange(ts, dist, compute_stream=stream)
+        xc.frame_concurrent = not args.frame_serial
     # device-resident synthetic state, both leapfrog slots (dp too: the slots alternate)
     syn.fill_device(ts, cfg, sea, 1, 2, diffusion=args.temdf2 > 0.0)
     ts._ck(ts.lib.hycom_tsadvc_synth_fill(ts.h, cabi.C.byref(cfg), cabi.F_DP, 0, 1, 0, 1, float("nan")))
@@ -400,6 +401,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange first, then the whole tile")
+    ap.add_argument("--frame-serial", action="store_true",
+                    help="N>1: launch the frame behind the interior instead of next to it (comparison)")
     ap.add_argument("--temdf2", type=float, default=0.0,
                     help="> 0: the step also runs tsdff_1x/2x + the EOS sweep (mod_tsadvc.F90:2138-2230); "
                          "the BASELINE metric is quoted without it")

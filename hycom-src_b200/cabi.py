@@ -103,6 +103,7 @@ PROTOTYPES = {
     "hycom_tsadvc_diff_halo_pack": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(_vp * 8), _vp]),
     "hycom_tsadvc_diff_halo_unpack": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(_vp * 8), _vp]),
     "hycom_tsadvc_diffuse_device": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params)]),
+    "hycom_tsadvc_set_frame_stream": (C.c_int, [_vp, _vp]),
     "hycom_tsadvc_set_timing": (C.c_int, [_vp, C.c_int32]),
     "hycom_tsadvc_get_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "hycom_synth_sea_mask": (C.c_int, [C.POINTER(SynthCfg), _vp]),

@@ -258,6 +258,7 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   for (auto* v : {&h->ev_pending, &h->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+  if (h->ev_frame) cudaEventDestroy(h->ev_frame);
   if (h->up_stream) cudaStreamDestroy(h->up_stream);
   if (h->down_stream) cudaStreamDestroy(h->down_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -278,6 +279,12 @@ int hycom_tsadvc_set_stream(hycom_tsadvc_handle* h, void* cuda_stream) {
     CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
   }
+  return 0;
+}
+
+int hycom_tsadvc_set_frame_stream(hycom_tsadvc_handle* h, void* cuda_stream) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  h->frame_stream = (cudaStream_t)cuda_stream;
   return 0;
 }
 
@@ -542,6 +549,9 @@ int neighbour(const hycom_tsadvc_dims& d, int dir) {
 int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
               const std::vector<Adv>& adv, int part, int k0 = 0, int nk = -1,
               const double* u_over = nullptr, const double* v_over = nullptr) {
+  // the frame of a multi-tile step may run on its own stream (hycom_tsadvc_set_frame_stream), next
+  // to the interior launch instead of behind it: it depends on the unpacked halos only
+  cudaStream_t lst = (part == HYCOM_TSADVC_PART_FRAME && h->frame_stream) ? h->frame_stream : h->stream;
   const int kk = nk < 0 ? h->d.kdm : nk, aadv = abs(p.advtyp);
   const long koff = h->slab * k0;
   int rc;
@@ -635,13 +645,18 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   if (h->timing) {
     if (!h->ev_free.empty()) { ev = h->ev_free.back(); h->ev_free.pop_back(); }
     else { CU(h, cudaEventCreate(&ev.first)); CU(h, cudaEventCreate(&ev.second)); }
-    CU(h, cudaEventRecord(ev.first, h->stream));
+    CU(h, cudaEventRecord(ev.first, lst));
   }
-  rc = launch_march_tma(aadv, P, h->stream);
+  rc = launch_march_tma(aadv, P, lst);
   h->launches += 1;
   if (h->timing) {
-    CU(h, cudaEventRecord(ev.second, h->stream));
+    CU(h, cudaEventRecord(ev.second, lst));
     h->ev_pending.push_back(ev);
+  }
+  if (lst != h->stream) {   // everything after the frame (time-level switch, diagnostics) waits for it
+    if (!h->ev_frame) CU(h, cudaEventCreateWithFlags(&h->ev_frame, cudaEventDisableTiming));
+    CU(h, cudaEventRecord(h->ev_frame, lst));
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_frame, 0));
   }
   if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "march kernel launch failed: %s",
                       rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "bad scheme");

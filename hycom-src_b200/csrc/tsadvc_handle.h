@@ -24,6 +24,9 @@ struct hycom_tsadvc_handle {
   // copy-in / copy-out streams and per-chunk events of the pipelined host-array call
   cudaStream_t up_stream = nullptr, down_stream = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
+  // optional stream of the PART_FRAME launch (caller-owned) and the event the main stream waits on
+  cudaStream_t frame_stream = nullptr;
+  cudaEvent_t ev_frame = nullptr;
   int64_t bytes = 0;
   int64_t launches = 0;
   bool have_static = false;

@@ -157,6 +157,7 @@ class XcExchange:
             ts._ck(ts.lib.hycom_tsadvc_halo_neighbors(ts.h, C.byref(nb)))
             assert list(nb) == self.nbr, (list(nb), self.nbr)
         self._bufs = {}
+        self.frame_concurrent = True
         self.comm_stream = None
         import torch
         self.torch = torch
@@ -253,8 +254,20 @@ class XcExchange:
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, xm, xx))
         elif overlap:
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_INTERIOR, None, None))
-            self.finish(m, n, pending)
-            ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_FRAME, xm, xx))
+            if self.comm_stream is not None and self.frame_concurrent:
+                # the frame runs on the comm stream right behind the unpack, next to the interior
+                # launch (it fills that launch's tail); the handle's stream joins both afterwards
+                works, recv = pending
+                with self.torch.cuda.stream(self.comm_stream):
+                    for w in works:
+                        w.wait()
+                    self.backend.unpack(m, n, recv, self.comm_stream.cuda_stream)
+                ts._ck(ts.lib.hycom_tsadvc_set_frame_stream(ts.h, C.c_void_p(self.comm_stream.cuda_stream)))
+                ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_FRAME, xm, xx))
+                ts._ck(ts.lib.hycom_tsadvc_set_frame_stream(ts.h, None))
+            else:
+                self.finish(m, n, pending)
+                ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_FRAME, xm, xx))
         else:
             self.finish(m, n, pending)
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, xm, xx))
@@ -338,9 +351,10 @@ class XcExchange:
         element-wise min/max over all tiles, in place"""
         torch = self.torch
         dev = self.backend.dev if self.comm_stream is not None else "cpu"
-        lo = torch.from_numpy(xmin).to(dev)
-        hi = torch.from_numpy(xmax).to(dev)
-        self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.group)
-        self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.group)
-        xmin[:] = lo.cpu().numpy()
-        xmax[:] = hi.cpu().numpy()
+        import numpy as np
+        kk = xmin.shape[0]
+        both = torch.from_numpy(np.concatenate([xmin, -xmax])).to(dev)   # max = -min(-x): one collective
+        self.dist.all_reduce(both, op=self.dist.ReduceOp.MIN, group=self.group)
+        both = both.cpu().numpy()
+        xmin[:] = both[:kk]
+        xmax[:] = -both[kk:]

@@ -200,6 +200,11 @@ int hycom_tsadvc_halo_unpack(hycom_tsadvc_handle *h, int32_t m, int32_t n,
 int hycom_tsadvc_step_device_part(hycom_tsadvc_handle *h, int32_t m, int32_t n,
                                   const hycom_tsadvc_params *prm, int32_t part,
                                   double *xmin, double *xmax);
+/* PART_FRAME depends on the unpacked halos, not on PART_INTERIOR: given a second stream (the one
+ * the unpack ran on; NULL: back to the handle's stream) its launch runs NEXT TO the interior
+ * launch instead of behind it and fills the tail of that launch; the rest of the step (time-
+ * level switch, diagnostics) waits for both. */
+int hycom_tsadvc_set_frame_stream(hycom_tsadvc_handle *h, void *cuda_stream);
 
 /* ---- advem_fct2c on several tiles (advtyp = 2 with btrmas, mod_tsadvc.F90:96-97, 999-1368) ---
  * The scheme calls xctilr(hloc) and xctilr(fldlo) after each of its five iterations
