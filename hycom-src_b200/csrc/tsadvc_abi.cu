@@ -863,8 +863,6 @@ int diff_halo_arrays(hycom_tsadvc_handle* h, int n, bool mxlmy, HaloArrays& a) {
 int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p) {
   const int kk = h->d.kdm;
   int rc;
-  DiffParams D;
-  memset(&D, 0, sizeof D);
   double *dpn, *on;
   if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
   if ((rc = slot(h, HYCOM_F_ONETA, 0, n, &on))) return rc;
@@ -872,25 +870,43 @@ int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p)
   const bool need_theta = nhyb < kk && !(kk == 1 && p.isopyc);
   if (need_theta && !h->theta.lev[0])
     return fail(h, HYCOM_TSADVC_EINVAL, "temdf2>0 with nhybrd<kdm reads theta: upload HYCOM_F_THETA first");
-  D.dp = dpn; D.oneta = on; D.theta = h->theta.lev[0];
-  D.mask = h->mask; D.scp2 = h->scp2; D.aspux = h->aspux; D.aspvy = h->aspvy;
-  D.scuy = h->scuy; D.scvx = h->scvx;
-  D.slab = h->slab; D.pitch = h->pitch; D.nrows = h->nrows; D.kk = kk;
-  D.nhybrd = nhyb; D.isopyc = p.isopyc;
-  eos::fill(p.sigver, D.eosc);
-  D.temdf2 = p.temdf2; D.temdfc = p.temdfc; D.thbase = p.thbase; D.delt1 = p.delt1;
-  auto add = [&](int field, int ktr) -> int {
-    double *in, *out;
-    int r2 = slot(h, field, ktr, n, &in);
-    if (!r2) r2 = spare_of(h, mirror_of(h, field, ktr), &out);
+  // au = temdf2*aspux*scuy, av = temdf2*aspvy*scvx: the k-independent part of the face factors
+  if (!h->diff_static && (rc = dalloc_field(h, &h->diff_static, 2 * (size_t)h->slab))) return rc;
+  rc = launch_diff_static(h->aspux, h->scuy, h->aspvy, h->scvx, p.temdf2, h->diff_static,
+                          h->diff_static + h->slab, h->slab, h->stream);
+  h->launches += 1;
+  if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  DiffMarchParams M;
+  memset(&M, 0, sizeof M);
+  M.dp = dpn; M.oneta = on; M.au = h->diff_static; M.av = h->diff_static + h->slab;
+  M.scp2 = h->scp2; M.mask64 = h->static_block + 2 * h->slab; M.theta = h->theta.lev[0];
+  M.slab = h->slab; M.pitch = h->pitch; M.nrows = h->nrows; M.kk = kk;
+  M.nstrips = (h->pitch + 1 + 29) / 30;
+  // about ten waves of 4-warp blocks at 4 blocks per SM
+  const long per_chunk = (long)kk * M.nstrips, want = 10L * 148 * 4 * 4;
+  const long nch = (want + per_chunk - 1) / per_chunk;
+  M.chunk_rows = (int)((h->nrows + nch - 1) / (nch > 0 ? nch : 1));
+  if (M.chunk_rows > 1024) M.chunk_rows = 1024;
+  if (M.chunk_rows < 64) M.chunk_rows = 64;
+  M.nchunks = (h->nrows + M.chunk_rows - 1) / M.chunk_rows;
+  M.nunits = (long)kk * M.nstrips * M.nchunks;
+  M.nhybrd = nhyb; M.isopyc = p.isopyc;
+  eos::fill(p.sigver, M.eosc);
+  M.temdfc = p.temdfc; M.thbase = p.thbase; M.delt1 = p.delt1;
+  struct Fld { int field, ktr; };
+  // slot n of a field (from model layer 1) and its ping-pong buffer
+  auto ptrs = [&](const Fld& f, const double** in, double** out) -> int {
+    double *i0, *o0;
+    int r2 = slot(h, f.field, f.ktr, n, &i0);
+    if (!r2) r2 = spare_of(h, mirror_of(h, f.field, f.ktr), &o0);
     if (r2) return r2;
-    const long kf = h->slab * layer1_of(field);
-    D.f[D.nf].in = in + kf; D.f[D.nf].out = out + kf; ++D.nf;
+    const long kf = h->slab * layer1_of(f.field);
+    *in = i0 + kf; *out = o0 + kf;
     return 0;
   };
-  auto swap = [&](int field, int ktr) -> int {
-    Mirror* mi = mirror_of(h, field, ktr);
-    if (layer1_of(field)) {   // q2,q2l: layers 0 and kk+1 travel with the buffer
+  auto swap = [&](const Fld& f) -> int {
+    Mirror* mi = mirror_of(h, f.field, f.ktr);
+    if (layer1_of(f.field)) {   // q2,q2l: layers 0 and kk+1 travel with the buffer
       const long last = h->slab * (kk + 1);
       CU(h, cudaMemcpyAsync(mi->spare, mi->lev[n - 1], sizeof(double) * h->slab, cudaMemcpyDeviceToDevice, h->stream));
       CU(h, cudaMemcpyAsync(mi->spare + last, mi->lev[n - 1] + last, sizeof(double) * h->slab,
@@ -899,65 +915,27 @@ int run_diffuse(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p)
     double* t = mi->lev[n - 1]; mi->lev[n - 1] = mi->spare; mi->spare = t;
     return 0;
   };
-  // default: the marching kernel (rows staged by the TMA engine, shared face factors);
-  // HYCOM_TSADVC_TSDFF=column selects the first, column-per-thread kernel (kept for comparison)
-  const char* ev = getenv("HYCOM_TSADVC_TSDFF");
-  const bool column = ev && !strcmp(ev, "column");
-  DiffMarchParams M;
-  memset(&M, 0, sizeof M);
-  if (!column) {
-    if (!h->diff_static && (rc = dalloc_field(h, &h->diff_static, 2 * (size_t)h->slab))) return rc;
-    rc = launch_diff_static(h->aspux, h->scuy, h->aspvy, h->scvx, p.temdf2, h->diff_static,
-                            h->diff_static + h->slab, h->slab, h->stream);
+  // one launch group: fields sharing the face factors
+  auto group = [&](const std::vector<Fld>& g, int eos) -> int {
+    M.eos = eos; M.nf = (int)g.size();
+    for (int q = 0; q < M.nf; ++q)
+      if ((rc = ptrs(g[q], &M.in[q], &M.out[q]))) return rc;
+    int r2 = launch_tsdff_march(M, h->stream);
     h->launches += 1;
-    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-    M.dp = dpn; M.oneta = on; M.au = h->diff_static; M.av = h->diff_static + h->slab;
-    M.scp2 = h->scp2; M.mask64 = h->static_block + 2 * h->slab; M.theta = h->theta.lev[0];
-    M.slab = h->slab; M.pitch = h->pitch; M.nrows = h->nrows; M.kk = kk;
-    M.nstrips = (h->pitch + 1 + 29) / 30;
-    // about ten waves of 4-warp blocks at 4 blocks per SM
-    const long per_chunk = (long)kk * M.nstrips, want = 10L * 148 * 4 * 4;
-    const long nch = (want + per_chunk - 1) / per_chunk;
-    M.chunk_rows = (int)((h->nrows + nch - 1) / (nch > 0 ? nch : 1));
-    if (M.chunk_rows > 1024) M.chunk_rows = 1024;
-    if (M.chunk_rows < 64) M.chunk_rows = 64;
-    M.nchunks = (h->nrows + M.chunk_rows - 1) / M.chunk_rows;
-    M.nunits = (long)kk * M.nstrips * M.nchunks;
-    M.nhybrd = nhyb; M.isopyc = p.isopyc; M.eosc = D.eosc;
-    M.temdfc = p.temdfc; M.thbase = p.thbase; M.delt1 = p.delt1;
-  }
-  // one launch group: nf fields sharing the face factors (column kernel: any nf; march: 1..3)
-  auto launch_group = [&](int eos) -> int {
-    int r2;
-    if (column) {
-      D.eos = eos;
-      r2 = launch_tsdff(D, h->stream);
-      h->launches += 1;
-    } else {
-      r2 = 0;
-      for (int f0 = 0; f0 < D.nf && !r2; f0 += eos ? 3 : 2) {   // tsdff_2x pairs, a last tsdff_1x (:2190-2198)
-        M.eos = eos;
-        M.nf = eos ? 3 : (D.nf - f0 >= 2 ? 2 : 1);
-        for (int q = 0; q < M.nf; ++q) { M.in[q] = D.f[f0 + q].in; M.out[q] = D.f[f0 + q].out; }
-        r2 = launch_tsdff_march(M, h->stream);
-        h->launches += 1;
-      }
-    }
     if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "tsdff kernel launch failed: %s",
                         r2 > 0 ? cudaGetErrorString((cudaError_t)r2) : "bad field group");
+    for (const Fld& f : g)
+      if ((rc = swap(f))) return rc;
     return 0;
   };
-  if ((rc = add(HYCOM_F_TEMP, 0)) || (rc = add(HYCOM_F_SALN, 0)) || (rc = add(HYCOM_F_TH3D, 0))) return rc;
-  if ((rc = launch_group(1))) return rc;
-  swap(HYCOM_F_TEMP, 0); swap(HYCOM_F_SALN, 0); swap(HYCOM_F_TH3D, 0);
-  if (h->d.ntracr > 0 || p.mxlmy) {   // :2180-2198: q2 & q2l, then the tracers, same face factors
-    D.nf = 0;
-    if (p.mxlmy && ((rc = add(HYCOM_F_Q2, 0)) || (rc = add(HYCOM_F_Q2L, 0)))) return rc;
-    for (int t = 1; t <= h->d.ntracr; ++t)
-      if ((rc = add(HYCOM_F_TRACER, t))) return rc;
-    if ((rc = launch_group(0))) return rc;
-    if (p.mxlmy && ((rc = swap(HYCOM_F_Q2, 0)) || (rc = swap(HYCOM_F_Q2L, 0)))) return rc;
-    for (int t = 1; t <= h->d.ntracr; ++t) swap(HYCOM_F_TRACER, t);
+  // :2166-2185 + :2199-2229  temp, saln, th3d with the equation of state
+  if ((rc = group({{HYCOM_F_TEMP, 0}, {HYCOM_F_SALN, 0}, {HYCOM_F_TH3D, 0}}, 1))) return rc;
+  // :2180-2183 q2 & q2l; :2190-2198 tracers in tsdff_2x pairs, a last single one with tsdff_1x
+  if (p.mxlmy && (rc = group({{HYCOM_F_Q2, 0}, {HYCOM_F_Q2L, 0}}, 0))) return rc;
+  for (int t = 1; t <= h->d.ntracr; t += 2) {
+    if (t + 1 <= h->d.ntracr) rc = group({{HYCOM_F_TRACER, t}, {HYCOM_F_TRACER, t + 1}}, 0);
+    else rc = group({{HYCOM_F_TRACER, t}}, 0);
+    if (rc) return rc;
   }
   return 0;
 }

@@ -94,29 +94,9 @@ int launch_halo_outer_multi(const HaloArrays& a, cudaStream_t stream);
 // ---- diffusion + equation of state after advection (tsdff.cu) ---------------------------
 namespace tsadvc {
 
-struct DiffField { const double* in; double* out; };   // (:,:,1,n) and its ping-pong buffer
-
-// one launch of k_tsdff: either the T/S/th3d triple with the equation-of-state epilogue
-// (eos = 1: f[0] temp, f[1] saln, f[2] th3d; mod_tsadvc.F90:2166-2185 + :2199-2229) or nf
-// tracers (eos = 0; :2190-2198), all kk layers
-struct DiffParams {
-  DiffField f[kMaxFields];
-  int nf, eos;
-  const double* dp;      // dp(:,:,1,n)
-  const double* oneta;   // onetamas(:,:,n) = oneta(:,:,n)  (:1805,1808)
-  const double* theta;   // theta(:,:,1): read in exactly-isopycnal layers only (may be null)
-  const uint8_t* mask;
-  const double *scp2, *aspux, *aspvy, *scuy, *scvx;
-  long slab;
-  int pitch, nrows, kk;
-  int nhybrd, isopyc;
-  eos::Coef eosc;        // equation of state `sigver` of the host model (stmt_fns.h)
-  double temdf2, temdfc, thbase, delt1;
-};
-
-int launch_tsdff(const DiffParams& P, cudaStream_t stream);
-
-// the marching form (k_tsdff_march): nf fields of one launch group, all kk layers
+// one launch group of k_tsdff_march: the T/S/th3d triple with the equation-of-state epilogue (eos = 1:
+// in[0] temp, in[1] saln, in[2] th3d; mod_tsadvc.F90:2166-2185 + :2199-2229) or one / two plain fields
+// (tracer pairs, q2 & q2l; :2180-2198), all kk layers
 struct DiffMarchParams {
   const double* in[3];
   double* out[3];
