@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhycom_tsadvc_b200.so")
-SOURCES = ["tsadvc_kernels.cu", "halo.cu", "tsadvc_abi.cu", "tsdff.cu", "fct2c.cu", "synth.cu"]
+SOURCES = ["tsadvc_kernels.cu", "halo.cu", "tsadvc_abi.cu", "tsdff.cu", "fct2c.cu", "asselin.cu", "synth.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

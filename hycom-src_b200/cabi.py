@@ -14,6 +14,7 @@ _LIB_NAME = "libhycom_tsadvc_b200.so"
 MXTRCR = 16
 
 F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER, F_ONETA, F_THETA, F_Q2, F_Q2L = range(11)
+(F_DPO, F_ONETAO, F_PBAVG, F_PBOT, F_OTEMP, F_OSALN, F_OTH3D, F_OTRACER, F_OQ2, F_OQ2L) = range(11, 21)
 S_SCPX, S_SCPY, S_SCUX, S_SCUY, S_SCVX, S_SCVY, S_ONETA = range(10, 17)
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENBDY, EADVTYP, ENOMEM = range(7)
@@ -104,6 +105,9 @@ PROTOTYPES = {
     "hycom_tsadvc_diff_halo_unpack": (C.c_int, [_vp, C.c_int32, C.POINTER(Params), C.POINTER(_vp * 8), _vp]),
     "hycom_tsadvc_diffuse_device": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params)]),
     "hycom_tsadvc_set_frame_stream": (C.c_int, [_vp, _vp]),
+    "hycom_tsadvc_asselin_save_device": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params), C.c_double]),
+    "hycom_tsadvc_asselin_filter_device": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(Params), C.c_double,
+                                                     C.c_double]),
     "hycom_tsadvc_set_timing": (C.c_int, [_vp, C.c_int32]),
     "hycom_tsadvc_get_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "hycom_synth_sea_mask": (C.c_int, [C.POINTER(SynthCfg), _vp]),

@@ -81,14 +81,31 @@ Mirror* mirror_of(hycom_tsadvc_handle* h, int field, int ktr) {
     case HYCOM_F_THETA: return &h->theta;
     case HYCOM_F_Q2: return &h->q2;
     case HYCOM_F_Q2L: return &h->q2l;
+    case HYCOM_F_DPO: return &h->dpo;
+    case HYCOM_F_ONETAO: return &h->onetao;
+    case HYCOM_F_PBAVG: return &h->pbavg;
+    case HYCOM_F_PBOT: return &h->pbot;
+    case HYCOM_F_OTEMP: return &h->otemp;
+    case HYCOM_F_OSALN: return &h->osaln;
+    case HYCOM_F_OTH3D: return &h->oth3d;
+    case HYCOM_F_OQ2: return &h->oq2;
+    case HYCOM_F_OQ2L: return &h->oq2l;
+    case HYCOM_F_OTRACER:
+      if (ktr >= 1 && ktr <= h->d.ntracr) return &h->otracer[ktr - 1];
+      return nullptr;
   }
   return nullptr;
 }
-bool is3d(int field) { return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX || field == HYCOM_F_THETA; }
+bool is3d(int field) {   // one time level only
+  return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX || field == HYCOM_F_THETA || field == HYCOM_F_PBAVG ||
+         field == HYCOM_F_PBOT || (field >= HYCOM_F_OTEMP && field <= HYCOM_F_OQ2L);
+}
 // slabs per time slot of a mirror
 int nlayers_of(const hycom_tsadvc_handle* h, int field) {
-  if (field == HYCOM_F_ONETA) return 1;
-  if (field == HYCOM_F_Q2 || field == HYCOM_F_Q2L) return h->d.kdm + 2;   // layers 0..kk+1
+  if (field == HYCOM_F_ONETA || field == HYCOM_F_ONETAO || field == HYCOM_F_PBOT) return 1;
+  if (field == HYCOM_F_PBAVG) return 3;
+  if (field == HYCOM_F_Q2 || field == HYCOM_F_Q2L || field == HYCOM_F_OQ2 || field == HYCOM_F_OQ2L)
+    return h->d.kdm + 2;   // layers 0..kk+1
   return h->d.kdm;
 }
 // slab index of model layer k = 1 inside one time slot of a mirror
@@ -1061,6 +1078,118 @@ int hycom_tsadvc_fct2c_halo_pack(hycom_tsadvc_handle* h, int32_t m, int32_t n, c
 int hycom_tsadvc_fct2c_halo_unpack(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
                                    int32_t batch, double* const recvbuf[8], void* cuda_stream) {
   return fct2c_halo_xfer(h, m, n, prm, batch, recvbuf, nullptr, cuda_stream, 2);
+}
+
+// ---- mod_asselin.F90 on the device mirrors -------------------------------------------------
+static int asselin_params(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                          double ra2fac, double oneta0, AsselinParams& A) {
+  if (!h || !prm) return fail(h, HYCOM_TSADVC_EINVAL, "asselin: null argument");
+  if (!h->have_static) return fail(h, HYCOM_TSADVC_EINVAL, "asselin: set_static has not been called");
+  if (m < 1 || m > 2 || n < 1 || n > 2 || m == n)
+    return fail(h, HYCOM_TSADVC_EINVAL, "asselin: bad leapfrog slots m=%d n=%d", m, n);
+  if (!(oneta0 > 0.0 && oneta0 < 1.0))   // blkdat.F90:436-444
+    return fail(h, HYCOM_TSADVC_EINVAL, "error - oneta0 must be above 0.0 and below 1.0");
+  if (prm->sigver < 1 || prm->sigver > 8)
+    return fail(h, HYCOM_TSADVC_EINVAL, "asselin: sigver=%d not in 1..8", prm->sigver);
+  CU(h, cudaSetDevice(h->d.device));
+  memset(&A, 0, sizeof A);
+  const int kk = h->d.kdm;
+  int rc;
+  double *pb, *pbot;
+  if ((rc = slot(h, HYCOM_F_PBAVG, 0, 1, &pb))) return rc;
+  if ((rc = slot(h, HYCOM_F_PBOT, 0, 1, &pbot))) return rc;
+  A.pbavg_n = pb + h->slab * (n - 1); A.pbavg_m = pb + h->slab * (m - 1); A.pbot = pbot;
+  if ((rc = slot(h, HYCOM_F_ONETA, 0, n, &A.oneta_n)) || (rc = slot(h, HYCOM_F_ONETA, 0, m, &A.oneta_m))) return rc;
+  if ((rc = slot(h, HYCOM_F_ONETAO, 0, n, &A.onetao_n)) || (rc = slot(h, HYCOM_F_ONETAO, 0, m, &A.onetao_m))) return rc;
+  A.pitch = h->pitch; A.nrows = h->nrows; A.nbdy = h->d.nbdy; A.ii = h->d.ii; A.jj = h->d.jj; A.kk = kk;
+  A.slab = h->slab; A.mask = h->mask;
+  A.nhybrd = prm->nhybrd < 0 ? 0 : (prm->nhybrd > kk ? kk : prm->nhybrd);
+  A.advflg = prm->advflg; A.isopyc = prm->isopyc;
+  eos::fill(prm->sigver, A.eosc);
+  A.ra2fac = ra2fac; A.oneta0 = oneta0; A.thbase = prm->thbase;
+  return 0;
+}
+
+int hycom_tsadvc_asselin_save_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                                     const hycom_tsadvc_params* prm, double oneta0) {
+  AsselinParams A;
+  int rc;
+  if ((rc = asselin_params(h, m, n, prm, 0.0, oneta0, A))) return rc;
+  auto launch = [&](int stage) -> int {
+    int r2 = launch_asselin(stage, A, h->stream);
+    h->launches += 1;
+    if (r2) return fail(h, HYCOM_TSADVC_ECUDA, "asselin kernel launch failed: %s",
+                        r2 > 0 ? cudaGetErrorString((cudaError_t)r2) : "bad stage");
+    return 0;
+  };
+  if ((rc = launch(1))) return rc;   // :52-55
+  // :57-75  time level t-1 of every scalar
+  auto cp = [&](int ofield, int field, int ktr, long off) -> int {
+    double *o, *f;
+    int r2 = slot(h, ofield, ktr, 1, &o);
+    if (!r2) r2 = slot(h, field, ktr, n, &f);
+    if (r2) return r2;
+    A.cp[A.nf].o = o + off; A.cp[A.nf].fn = f + off; ++A.nf;
+    return 0;
+  };
+  A.nf = 0; A.kcopy = h->d.kdm;
+  if ((rc = cp(HYCOM_F_OTEMP, HYCOM_F_TEMP, 0, 0)) || (rc = cp(HYCOM_F_OSALN, HYCOM_F_SALN, 0, 0)) ||
+      (rc = cp(HYCOM_F_OTH3D, HYCOM_F_TH3D, 0, 0))) return rc;
+  for (int t = 1; t <= h->d.ntracr; ++t)
+    if ((rc = cp(HYCOM_F_OTRACER, HYCOM_F_TRACER, t, 0))) return rc;
+  if (prm->mxlmy)   // oq2(i,j,k) = q2(i,j,k,n), k = 1..kk of the (0:kk+1) arrays (:67-74)
+    if ((rc = cp(HYCOM_F_OQ2, HYCOM_F_Q2, 0, h->slab)) || (rc = cp(HYCOM_F_OQ2L, HYCOM_F_Q2L, 0, h->slab))) return rc;
+  if ((rc = launch(2))) return rc;
+  if (h->d.ipr * h->d.jpr == 1) {   // :77-78 xctilr(oneta|onetao, 1,2, 6,6, halo_ps)
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_ONETA, 0, 0, 6, 6))) return rc;
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_ONETAO, 0, 0, 6, 6))) return rc;
+  }
+  return 0;
+}
+
+int hycom_tsadvc_asselin_filter_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
+                                       const hycom_tsadvc_params* prm, double ra2fac, double oneta0) {
+  AsselinParams A;
+  int rc;
+  if ((rc = asselin_params(h, m, n, prm, ra2fac, oneta0, A))) return rc;
+  const int kk = h->d.kdm;
+  double *dpo_n, *dpo_m, *dp_n, *dp_m;
+  if ((rc = slot(h, HYCOM_F_DPO, 0, n, &dpo_n)) || (rc = slot(h, HYCOM_F_DPO, 0, m, &dpo_m)) ||
+      (rc = slot(h, HYCOM_F_DP, 0, n, &dp_n)) || (rc = slot(h, HYCOM_F_DP, 0, m, &dp_m))) return rc;
+  A.dpo_n = dpo_n; A.dpo_m = dpo_m; A.dp_n = dp_n; A.dp_m = dp_m;
+  const bool need_theta = A.nhybrd < kk && !(kk == 1 && prm->isopyc);
+  if (need_theta && !h->theta.lev[0])
+    return fail(h, HYCOM_TSADVC_EINVAL, "asselin_filter with nhybrd<kdm reads theta: upload HYCOM_F_THETA first");
+  A.theta = h->theta.lev[0];
+  auto fld = [&](int ofield, int field, int ktr) -> int {
+    double *o, *fm, *fn;
+    int r2 = slot(h, ofield, ktr, 1, &o);
+    if (!r2) r2 = slot(h, field, ktr, m, &fm);
+    if (!r2) r2 = slot(h, field, ktr, n, &fn);
+    if (r2) return r2;
+    A.f[A.nf].o = o; A.f[A.nf].fm = fm; A.f[A.nf].fn = fn; ++A.nf;
+    return 0;
+  };
+  A.nf = 0;
+  if ((rc = fld(HYCOM_F_OSALN, HYCOM_F_SALN, 0)) || (rc = fld(HYCOM_F_OTEMP, HYCOM_F_TEMP, 0)) ||
+      (rc = fld(HYCOM_F_OTH3D, HYCOM_F_TH3D, 0))) return rc;
+  for (int t = 1; t <= h->d.ntracr; ++t)
+    if ((rc = fld(HYCOM_F_OTRACER, HYCOM_F_TRACER, t))) return rc;
+  if (prm->mxlmy) {
+    double *a, *b;
+    if ((rc = slot(h, HYCOM_F_OQ2, 0, 1, &a)) || (rc = slot(h, HYCOM_F_OQ2L, 0, 1, &b))) return rc;
+    A.q2_o = a; A.q2l_o = b;
+    if ((rc = slot(h, HYCOM_F_Q2, 0, m, &A.q2_m)) || (rc = slot(h, HYCOM_F_Q2L, 0, m, &A.q2l_m))) return rc;
+    if ((rc = slot(h, HYCOM_F_Q2, 0, n, &a)) || (rc = slot(h, HYCOM_F_Q2L, 0, n, &b))) return rc;
+    A.q2_n = a; A.q2l_n = b;
+  }
+  for (int stage : {0, 3}) {   // :115-118 oneta, then the filter
+    rc = launch_asselin(stage, A, h->stream);
+    h->launches += 1;
+    if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "asselin kernel launch failed: %s",
+                        rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "bad stage");
+  }
+  return 0;
 }
 
 int hycom_tsadvc_diff_halo_counts(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params* prm,

@@ -37,6 +37,10 @@ struct hycom_tsadvc_handle {
   tsadvc::Mirror oneta;  // (:,:,2): one slab per time slot
   tsadvc::Mirror theta;  // (:,:,kdm): lev[0] only
   tsadvc::Mirror q2, q2l;  // (:,:,0:kdm+1,2): kdm+2 slabs per slot (mxlmy)
+  // mod_asselin.F90 operands: dpo (kdm per slot), onetao (1 per slot), pbavg (3 slabs), pbot (1),
+  // otemp/osaln/oth3d/otracer (kdm), oq2/oq2l (kdm+2)
+  tsadvc::Mirror dpo, onetao, pbavg, pbot, otemp, osaln, oth3d, oq2, oq2l;
+  tsadvc::Mirror otracer[HYCOM_TSADVC_MXTRCR];
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
   // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)]
   double* flux_block = nullptr;

@@ -146,3 +146,30 @@ struct Fct2cParams {
 int launch_fct2c(int stage, const Fct2cParams& P, cudaStream_t stream);
 
 }  // namespace tsadvc
+
+// ---- Robert-Asselin filter of the scalar fields (asselin.cu; mod_asselin.F90) ---------------
+namespace tsadvc {
+
+struct AsselinField { const double* o; double* fm; const double* fn; };   // t-1 (saved), t, t+1
+struct AsselinCopy { double* o; const double* fn; };
+
+struct AsselinParams {
+  union { AsselinField f[kMaxFields + 1]; AsselinCopy cp[kMaxFields + 1]; };   // filter: saln, temp, th3d, tracers
+  int nf, kcopy;                     // kcopy: layers of the save copies (kk, or kk+2 for oq2/oq2l)
+  int pitch, nrows, nbdy, ii, jj, kk;
+  long slab;
+  const uint8_t* mask;
+  const double *pbavg_n, *pbavg_m, *pbot;
+  double *oneta_n, *oneta_m, *onetao_n, *onetao_m;
+  const double *dpo_n, *dpo_m, *dp_n;
+  double* dp_m;
+  const double* theta;
+  const double *q2_o, *q2l_o, *q2_n, *q2l_n;   // q2_o null unless mxlmy; all at slab 0 of (0:kk+1)
+  double *q2_m, *q2l_m;
+  int nhybrd, advflg, isopyc;
+  eos::Coef eosc;
+  double ra2fac, oneta0, thbase;
+};
+int launch_asselin(int stage, const AsselinParams& P, cudaStream_t stream);
+
+}  // namespace tsadvc

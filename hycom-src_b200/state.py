@@ -53,6 +53,20 @@ class CbArrays:
     oneta: np.ndarray = None
     q2: np.ndarray = None      # (2, kdm+2, nrows, ncols): q2(:,:,0:kk+1,2), Mellor-Yamada tke (mxlmy)
     q2l: np.ndarray = None
+    # mod_asselin.F90 operands: dpo (2,kdm,..), onetao (2,..), pbavg (3,..), pbot (..), otemp/osaln/oth3d
+    # (kdm,..), otracer (ntracr,kdm,..), oq2/oq2l (kdm+2,..)
+    dpo: np.ndarray = None
+    onetao: np.ndarray = None
+    pbavg: np.ndarray = None
+    pbot: np.ndarray = None
+    otemp: np.ndarray = None
+    osaln: np.ndarray = None
+    oth3d: np.ndarray = None
+    otracer: np.ndarray = None
+    oq2: np.ndarray = None
+    oq2l: np.ndarray = None
+    ra2fac: float = 0.125
+    oneta0: float = 0.01
     theta: np.ndarray = None   # (kdm, nrows, ncols): isopycnic target densities - thbase
     # blkdat scalars (defaults = the benchmark configuration: FCT2, T&S, hybrid)
     advtyp: int = 2
@@ -165,7 +179,10 @@ class Tsadvc:
 
     def download(self, fld: int, tlev: int = 1, ktr: int = 0, k0: int = 1, nk: Optional[int] = None):
         g = self.cb.geom
-        nk = g.kdm - k0 + 1 if nk is None else nk
+        if nk is None:
+            nlay = {cabi.F_ONETA: 1, cabi.F_ONETAO: 1, cabi.F_PBOT: 1, cabi.F_PBAVG: 3, cabi.F_Q2: g.kdm + 2,
+                    cabi.F_Q2L: g.kdm + 2, cabi.F_OQ2: g.kdm + 2, cabi.F_OQ2L: g.kdm + 2}.get(fld, g.kdm)
+            nk = nlay - k0 + 1
         out = np.empty((nk, g.nrows, g.ncols))
         self._ck(self.lib.hycom_tsadvc_download(self.h, fld, ktr, tlev, k0, nk, _ptr(out)))
         return out
@@ -201,6 +218,43 @@ class Tsadvc:
         """theta is constant in time: pushed once, read only in exactly-isopycnal layers"""
         if self.cb.theta is not None:
             self.upload(cabi.F_THETA, self.cb.theta, 1)
+
+    # -- next to the path: mod_asselin.F90 on the device mirrors ----------------
+    def upload_asselin_state(self, m: int, n: int):
+        """every operand of asselin_save / asselin_filter that tsadvc itself does not mirror"""
+        cb = self.cb
+        for t in (1, 2):
+            self.upload(cabi.F_DPO, cb.dpo[t - 1], t)
+            self.upload(cabi.F_DP, cb.dp[t - 1], t)
+            self.upload(cabi.F_ONETAO, cb.onetao[t - 1], t)
+            self.upload(cabi.F_ONETA, cb.oneta[t - 1], t)
+            self.upload(cabi.F_TEMP, cb.temp[t - 1], t)
+            self.upload(cabi.F_SALN, cb.saln[t - 1], t)
+            self.upload(cabi.F_TH3D, cb.th3d[t - 1], t)
+            for q in range(cb.ntracr):
+                self.upload(cabi.F_TRACER, cb.tracer[q, t - 1], t, ktr=q + 1)
+        self.upload(cabi.F_PBAVG, cb.pbavg, 1)
+        self.upload(cabi.F_PBOT, cb.pbot, 1)
+        for fld, a in ((cabi.F_OTEMP, cb.otemp), (cabi.F_OSALN, cb.osaln), (cabi.F_OTH3D, cb.oth3d)):
+            self.upload(fld, a, 1)
+        for q in range(cb.ntracr):
+            self.upload(cabi.F_OTRACER, cb.otracer[q], 1, ktr=q + 1)
+        if cb.mxlmy:
+            self.upload_q2()
+            self.upload(cabi.F_OQ2, cb.oq2, 1)
+            self.upload(cabi.F_OQ2L, cb.oq2l, 1)
+        self.upload_theta()
+
+    def asselin_save_device(self, m: int, n: int):
+        """asselin_save(m,n), mod_asselin.F90:28-82, on the device mirrors"""
+        p = self.cb.params()
+        self._ck(self.lib.hycom_tsadvc_asselin_save_device(self.h, m, n, C.byref(p), self.cb.oneta0))
+
+    def asselin_filter_device(self, m: int, n: int):
+        """asselin_filter(m,n), mod_asselin.F90:84-286, on the device mirrors"""
+        p = self.cb.params()
+        self._ck(self.lib.hycom_tsadvc_asselin_filter_device(self.h, m, n, C.byref(p), self.cb.ra2fac,
+                                                            self.cb.oneta0))
 
     # -- the path ---------------------------------------------------------
     def tsadvc(self, m: int, n: int):

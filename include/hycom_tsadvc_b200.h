@@ -62,7 +62,18 @@ enum {
   HYCOM_F_ONETA = 7,  /* oneta(:,:,tlev): one slab per time slot (k0 = nk = 1) */
   HYCOM_F_THETA = 8,  /* theta(:,:,kdm), 3-D: tlev ignored (mod_cb_arrays.F90:81) */
   HYCOM_F_Q2 = 9,     /* q2(:,:,0:kdm+1,tlev): kdm+2 slabs per slot, layer k0 = 1 is k = 0 */
-  HYCOM_F_Q2L = 10    /* (mod_cb_arrays.F90:513-514; advected and diffused when mxlmy) */
+  HYCOM_F_Q2L = 10,   /* (mod_cb_arrays.F90:513-514; advected and diffused when mxlmy) */
+  /* operands of the Robert-Asselin filter (mod_asselin.F90), see hycom_tsadvc_asselin_* below */
+  HYCOM_F_DPO = 11,     /* dpo(:,:,kdm,tlev) */
+  HYCOM_F_ONETAO = 12,  /* onetao(:,:,tlev): one slab per slot */
+  HYCOM_F_PBAVG = 13,   /* pbavg(:,:,3), 3-D: tlev ignored, layer k0 = time slot 1..3 */
+  HYCOM_F_PBOT = 14,    /* pbot(:,:), one slab */
+  HYCOM_F_OTEMP = 15,   /* otemp, osaln, oth3d (:,:,kdm); otracer(:,:,kdm,ktr): time level t-1 */
+  HYCOM_F_OSALN = 16,
+  HYCOM_F_OTH3D = 17,
+  HYCOM_F_OTRACER = 18,
+  HYCOM_F_OQ2 = 19,     /* oq2, oq2l (:,:,0:kdm+1) */
+  HYCOM_F_OQ2L = 20
 };
 
 /* mod_dimensions.F90:33,45-49 + mod_xc tile geometry (mod_xc_mp.h:2317-3288) */
@@ -251,6 +262,21 @@ int hycom_tsadvc_diff_halo_unpack(hycom_tsadvc_handle *h, int32_t n,
  * (halos of slot n valid to width 1); a no-op returning 0 when temdf2 <= 0 */
 int hycom_tsadvc_diffuse_device(hycom_tsadvc_handle *h, int32_t m, int32_t n,
                                 const hycom_tsadvc_params *prm);
+
+/* ---- next to tsadvc in the time step: the Robert-Asselin filter of
+ * the scalar fields, the pointwise consumer of tsadvc's output.  Both calls work on the device
+ * mirrors (fill them with hycom_tsadvc_upload, read them back with hycom_tsadvc_download);
+ * prm supplies advflg, nhybrd, isopyc, mxlmy, sigver, thbase.
+ *   asselin_save(m,n)   mod_asselin.F90:28-82 : oneta/onetao(:,:,n|m) = max(oneta0, 1+pbavg/pbot),
+ *                       otemp/osaln/oth3d/otracer(/oq2/oq2l) = slot n; on a single tile also the
+ *                       xctilr(oneta|onetao, 1,2, 6,6, halo_ps) of :77-78
+ *   asselin_filter(m,n) mod_asselin.F90:84-286: oneta(:,:,n|m), dp(:,:,:,m) and slot m of saln,
+ *                       temp, th3d, tracers (, q2, q2l) filtered in place */
+int hycom_tsadvc_asselin_save_device(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                                     const hycom_tsadvc_params *prm, double oneta0);
+int hycom_tsadvc_asselin_filter_device(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                                       const hycom_tsadvc_params *prm, double ra2fac,
+                                       double oneta0);
 
 /* number of kernels this library launched on the handle since creation */
 int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle *h);

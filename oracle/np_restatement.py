@@ -557,3 +557,84 @@ def diffuse(cb, n, temp, saln, th3d, tracer):
         temp[n - 1, k] = np.where(upd, Tn, T)
         th3d[n - 1, k] = np.where(upd, Hn, H)
         saln[n - 1, k] = S
+
+
+# ---- mod_asselin.F90 ---------------------------------------------
+
+def asselin_save(cb, m, n):
+    """asselin_save (mod_asselin.F90:28-82) on a CbArrays; returns the arrays it writes"""
+    g = cb.geom
+    upd = _region(g, 0)
+    sea = upd & (cb.ip != 0)
+    oneta, onetao = cb.oneta.copy(), cb.onetao.copy()
+    with np.errstate(all="ignore"):
+        for t in (n, m):
+            v = _fmax(cb.oneta0, 1.0 + cb.pbavg[t - 1] / cb.pbot)
+            oneta[t - 1] = np.where(sea, v, oneta[t - 1])
+            onetao[t - 1] = np.where(sea, oneta[t - 1], onetao[t - 1])
+    out = dict(oneta=halo_single_tile(g, oneta, 6, 6), onetao=halo_single_tile(g, onetao, 6, 6))
+    for name, src in (("otemp", cb.temp), ("osaln", cb.saln), ("oth3d", cb.th3d)):
+        out[name] = np.where(upd, src[n - 1], getattr(cb, name))
+    if cb.ntracr:
+        out["otracer"] = np.where(upd, cb.tracer[:, n - 1], cb.otracer)
+    if cb.mxlmy:
+        for name, src in (("oq2", cb.q2), ("oq2l", cb.q2l)):
+            o = getattr(cb, name).copy()
+            o[1:-1] = np.where(upd, src[n - 1, 1:-1], o[1:-1])
+            out[name] = o
+    return out
+
+
+def asselin_filter(cb, m, n):
+    """asselin_filter (mod_asselin.F90:84-286): whole-array form; returns the arrays it writes"""
+    g = cb.geom
+    kk = g.kdm
+    nhyb = kk if cb.nhybrd < 0 else cb.nhybrd
+    sea = _region(g, 0) & (cb.ip != 0)
+    onezm = 9806.0e-20
+    ra = cb.ra2fac
+    with np.errstate(all="ignore"):
+        oneta = cb.oneta.copy()
+        for t in (n, m):
+            oneta[t - 1] = np.where(sea, _fmax(cb.oneta0, 1.0 + cb.pbavg[t - 1] / cb.pbot), oneta[t - 1])
+        dp, temp, saln, th3d = cb.dp.copy(), cb.temp.copy(), cb.saln.copy(), cb.th3d.copy()
+        tracer = cb.tracer.copy() if cb.ntracr else None
+        q2 = cb.q2.copy() if cb.mxlmy else None
+        q2l = cb.q2l.copy() if cb.mxlmy else None
+        for k in range(kk):
+            latemp = (k + 1 <= nhyb) and cb.advflg == 0
+            lath3d = ((k + 1 <= nhyb) and cb.advflg == 1) or (k == 0 and cb.isopyc)
+            dpold = cb.dpo[n - 1, k] * cb.onetao[n - 1]
+            dpmid = cb.dpo[m - 1, k] * cb.onetao[m - 1]
+            dpnew = cb.dp[n - 1, k] * oneta[n - 1]
+            dpmidn = dpmid + 0.5 * ra * (dpold + dpnew - 2.0 * dpmid)
+            dp[m - 1, k] = np.where(sea, dpmidn / oneta[m - 1], dp[m - 1, k])
+            go = sea & (dpmidn > onezm)
+            qd = 1.0 / dpmidn
+
+            def ra_filter(o, fm, fn):
+                smin = _fmin(_fmin(o, fm), fn)
+                dpsold, dpsmid, dpsnew = dpold * (o - smin), dpmid * (fm - smin), dpnew * (fn - smin)
+                return smin + (dpsmid + 0.5 * ra * (dpsold + dpsnew - 2.0 * dpsmid)) * qd
+            S = ra_filter(cb.osaln[k], cb.saln[m - 1, k], cb.saln[n - 1, k])
+            saln[m - 1, k] = np.where(go, S, saln[m - 1, k])
+            if latemp:
+                T = ra_filter(cb.otemp[k], cb.temp[m - 1, k], cb.temp[n - 1, k])
+                H = sig(cb.sigver, T, S) - cb.thbase
+            elif lath3d:
+                H = ra_filter(cb.oth3d[k], cb.th3d[m - 1, k], cb.th3d[n - 1, k])
+                T = tofsig(cb.sigver, H + cb.thbase, S)
+            else:
+                H = cb.theta[k]
+                T = tofsig(cb.sigver, H + cb.thbase, S)
+            temp[m - 1, k] = np.where(go, T, temp[m - 1, k])
+            th3d[m - 1, k] = np.where(go, H, th3d[m - 1, k])
+            for q in range(cb.ntracr):
+                R = ra_filter(cb.otracer[q, k], cb.tracer[q, m - 1, k], cb.tracer[q, n - 1, k])
+                tracer[q, m - 1, k] = np.where(go, R, tracer[q, m - 1, k])
+            if cb.mxlmy:
+                for arr, o, src in ((q2, cb.oq2, cb.q2), (q2l, cb.oq2l, cb.q2l)):
+                    dpsold, dpsmid, dpsnew = dpold * o[k + 1], dpmid * src[m - 1, k + 1], dpnew * src[n - 1, k + 1]
+                    R = (dpsmid + 0.5 * ra * (dpsold + dpsnew - 2.0 * dpsmid)) * qd
+                    arr[m - 1, k + 1] = np.where(go, R, arr[m - 1, k + 1])
+    return dict(oneta=oneta, dp=dp, temp=temp, saln=saln, th3d=th3d, tracer=tracer, q2=q2, q2l=q2l)

@@ -98,6 +98,12 @@ orc_tile *orc_tile_create(int idm, int jdm, int kdm, int nbdy, int ii, int jj,
   t->tracer = ntracr > 0 ? alloc_r(P * K * 2 * (size_t)ntracr) : NULL;
   t->uflx = alloc_r(P * K); t->vflx = alloc_r(P * K);
   t->theta = alloc_r(P * K);
+  /* mod_asselin.F90 operands */
+  t->dpo = alloc_r(P * K * 2); t->onetao = alloc_r(P * 2); t->pbavg = alloc_r(P * 3); t->pbot = alloc_r(P);
+  t->otemp = alloc_r(P * K); t->osaln = alloc_r(P * K); t->oth3d = alloc_r(P * K);
+  t->otracer = ntracr > 0 ? alloc_r(P * K * (size_t)ntracr) : NULL;
+  t->oq2 = alloc_r(P * (K + 2)); t->oq2l = alloc_r(P * (K + 2));
+  t->ra2fac = 0.125; t->oneta0 = 0.01;
   t->q2 = alloc_r(P * (K + 2) * 2); t->q2l = alloc_r(P * (K + 2) * 2); /* (0:kk+1,2), mod_cb_arrays.F90:513-514 */
   t->oneta = alloc_r(P * 2); t->onetamas = alloc_r(P * 2);
   t->uflux = alloc_r(P); t->vflux = alloc_r(P);
@@ -129,7 +135,8 @@ void orc_tile_destroy(orc_tile *t) {
                   t->vflux2, t->util1, t->util2, t->fmx, t->fmn, t->flx, t->fly,
                   t->fldlo, t->fmxlo, t->fmnlo, t->fax, t->fay, t->rp, t->rm,
                   t->flxdiv, t->tx1, t->ty1, t->fldao, t->fldan, t->xmin,
-                  t->xmax, t->theta, t->q2, t->q2l};
+                  t->xmax, t->theta, t->q2, t->q2l, t->dpo, t->onetao, t->pbavg, t->pbot,
+                  t->otemp, t->osaln, t->oth3d, t->otracer, t->oq2, t->oq2l};
   for (size_t q = 0; q < sizeof(ptrs) / sizeof(ptrs[0]); q++) free(ptrs[q]);
   free(t);
 }
@@ -143,6 +150,7 @@ double *orc_f64(orc_tile *t, const char *name) {
   F(fmx); F(fmn); F(flx); F(fly); F(fldlo); F(fmxlo); F(fmnlo); F(fax); F(fay);
   F(rp); F(rm); F(flxdiv); F(tx1); F(ty1); F(fldao); F(fldan);
   F(xmin); F(xmax); F(theta); F(q2); F(q2l);
+  F(dpo); F(onetao); F(pbavg); F(pbot); F(otemp); F(osaln); F(oth3d); F(otracer); F(oq2); F(oq2l);
 #undef F
   return NULL;
 }
@@ -172,7 +180,7 @@ int orc_get_i(const orc_tile *t, const char *name) {
 }
 int orc_set_d(orc_tile *t, const char *name, double v) {
 #define S(n) if (!strcmp(name, #n)) { t->n = v; return 0; }
-  S(delt1) S(temdf2) S(temdfc) S(thbase) S(onemm)
+  S(delt1) S(temdf2) S(temdfc) S(thbase) S(onemm) S(ra2fac) S(oneta0)
 #undef S
   return 1;
 }
@@ -1353,6 +1361,118 @@ static void tsdff(orc_tile *t, int k, int n, double *fld1, double *fld2) {
           fld2[c] = fld2[c] + util2[c];
         }
       }
+}
+
+
+/* ---- mod_asselin.F90: Robert-Asselin filter of the scalar fields ---------------------------
+ * asselin_save :28-82 (time level t-1 saved, oneta/onetao of both slots, their halos to width 6)
+ * asselin_filter :84-286 (margin 0; smooths oneta*dp*scalar, conserving constants) */
+void orc_asselin_save(orc_tile *t, int m, int n, int do_halo) {
+  GEOM(t); MASKS(t);
+  const size_t P = (size_t)orc_slab(t), K = (size_t)t->kdm;
+  const int kk = t->kk;
+  for (int j = 1; j <= jj; j++) {
+    for (int i = 1; i <= ii; i++)
+      if (SEA_P) {
+        const size_t c = IX(i, j);
+        t->oneta[c + P * (size_t)(n - 1)] = MAX2(t->oneta0, 1.0 + t->pbavg[c + P * (size_t)(n - 1)] / t->pbot[c]);
+        t->oneta[c + P * (size_t)(m - 1)] = MAX2(t->oneta0, 1.0 + t->pbavg[c + P * (size_t)(m - 1)] / t->pbot[c]);
+        t->onetao[c + P * (size_t)(n - 1)] = t->oneta[c + P * (size_t)(n - 1)];
+        t->onetao[c + P * (size_t)(m - 1)] = t->oneta[c + P * (size_t)(m - 1)];
+      }
+    for (int k = 1; k <= kk; k++)
+      for (int i = 1; i <= ii; i++) {
+        const size_t c = IX(i, j), ck = c + P * (size_t)(k - 1), cn = ck + P * K * (size_t)(n - 1);
+        t->otemp[ck] = t->temp[cn];
+        t->osaln[ck] = t->saln[cn];
+        t->oth3d[ck] = t->th3d[cn];
+        for (int ktr = 1; ktr <= t->ntracr; ktr++)
+          t->otracer[ck + P * K * (size_t)(ktr - 1)] = t->tracer[cn + P * K * 2 * (size_t)(ktr - 1)];
+      }
+    if (t->mxlmy)
+      for (int k = 1; k <= kk; k++)
+        for (int i = 1; i <= ii; i++) {
+          const size_t c = IX(i, j);
+          t->oq2[c + P * (size_t)k] = t->q2[c + P * ((size_t)k + (K + 2) * (size_t)(n - 1))];
+          t->oq2l[c + P * (size_t)k] = t->q2l[c + P * ((size_t)k + (K + 2) * (size_t)(n - 1))];
+        }
+  }
+  if (do_halo) { /* :77-78 */
+    orc_xctilr(t, t->oneta, 1, 2, 6, 6);
+    orc_xctilr(t, t->onetao, 1, 2, 6, 6);
+  }
+}
+
+void orc_asselin_filter(orc_tile *t, int m, int n) {
+  GEOM(t); MASKS(t);
+  const size_t P = (size_t)orc_slab(t), K = (size_t)t->kdm;
+  const int kk = t->kk;
+  const double onezm = 9806.e-20; /* :93 */
+  const double ra2fac = t->ra2fac;
+  const int nthr = nthr_of(t), jblk = jblk_of(t, nthr);
+  OMP_J
+  for (int j = 1; j <= jj; j++) {
+    for (int i = 1; i <= ii; i++)
+      if (SEA_P) { /* :115-118 */
+        const size_t c = IX(i, j);
+        t->oneta[c + P * (size_t)(n - 1)] = MAX2(t->oneta0, 1.0 + t->pbavg[c + P * (size_t)(n - 1)] / t->pbot[c]);
+        t->oneta[c + P * (size_t)(m - 1)] = MAX2(t->oneta0, 1.0 + t->pbavg[c + P * (size_t)(m - 1)] / t->pbot[c]);
+      }
+    for (int k = 1; k <= kk; k++) {
+      const int latemp = k <= t->nhybrd && t->advflg == 0;
+      const int lath3d = (k <= t->nhybrd && t->advflg == 1) || (k == 1 && t->isopyc);
+      for (int i = 1; i <= ii; i++)
+        if (SEA_P) {
+          const size_t c = IX(i, j), ck = c + P * (size_t)(k - 1);
+          const size_t cn = ck + P * K * (size_t)(n - 1), cm = ck + P * K * (size_t)(m - 1);
+          const double dpold = t->dpo[cn] * t->onetao[c + P * (size_t)(n - 1)];
+          const double dpmid = t->dpo[cm] * t->onetao[c + P * (size_t)(m - 1)];
+          const double dpnew = t->dp[cn] * t->oneta[c + P * (size_t)(n - 1)];
+          double q = 0.5 * ra2fac * (dpold + dpnew - 2.0 * dpmid);
+          const double dpmidn = dpmid + q;
+          t->dp[cm] = dpmidn / t->oneta[c + P * (size_t)(m - 1)];
+          if (dpmidn > onezm) {
+            const double qdpmidn = 1.0 / dpmidn;
+            double smin, dpsold, dpsmid, dpsnew;
+#define RA_FILTER(o, fm, fn)                                   \
+  smin = MIN3((o), (fm), (fn));                                \
+  dpsold = dpold * ((o) - smin);                               \
+  dpsmid = dpmid * ((fm) - smin);                              \
+  dpsnew = dpnew * ((fn) - smin);                              \
+  q = 0.5 * ra2fac * (dpsold + dpsnew - 2.0 * dpsmid);         \
+  (fm) = smin + (dpsmid + q) * qdpmidn
+            RA_FILTER(t->osaln[ck], t->saln[cm], t->saln[cn]); /* :144-151 */
+            if (latemp) { /* :169-180 */
+              RA_FILTER(t->otemp[ck], t->temp[cm], t->temp[cn]);
+              t->th3d[cm] = eos_sig(t->sigver, t->temp[cm], t->saln[cm]) - t->thbase;
+            } else if (lath3d) { /* :181-192 */
+              RA_FILTER(t->oth3d[ck], t->th3d[cm], t->th3d[cn]);
+              t->temp[cm] = eos_tofsig(t->sigver, t->th3d[cm] + t->thbase, t->saln[cm]);
+            } else { /* :193-198 */
+              t->th3d[cm] = t->theta[ck];
+              t->temp[cm] = eos_tofsig(t->sigver, t->th3d[cm] + t->thbase, t->saln[cm]);
+            }
+            for (int ktr = 1; ktr <= t->ntracr; ktr++) { /* :199-225 */
+              const size_t o = ck + P * K * (size_t)(ktr - 1);
+              const size_t tm = cm + P * K * 2 * (size_t)(ktr - 1), tn = cn + P * K * 2 * (size_t)(ktr - 1);
+              RA_FILTER(t->otracer[o], t->tracer[tm], t->tracer[tn]);
+            }
+#undef RA_FILTER
+            if (t->mxlmy) { /* :226-237 */
+              const size_t qo = c + P * (size_t)k;
+              const size_t qm_ = c + P * ((size_t)k + (K + 2) * (size_t)(m - 1));
+              const size_t qn_ = c + P * ((size_t)k + (K + 2) * (size_t)(n - 1));
+              dpsold = dpold * t->oq2[qo]; dpsmid = dpmid * t->q2[qm_]; dpsnew = dpnew * t->q2[qn_];
+              q = 0.5 * ra2fac * (dpsold + dpsnew - 2.0 * dpsmid);
+              t->q2[qm_] = (dpsmid + q) * qdpmidn;
+              dpsold = dpold * t->oq2l[qo]; dpsmid = dpmid * t->q2l[qm_]; dpsnew = dpnew * t->q2l[qn_];
+              q = 0.5 * ra2fac * (dpsold + dpsnew - 2.0 * dpsmid);
+              t->q2l[qm_] = (dpsmid + q) * qdpmidn;
+            }
+          }
+        }
+    }
+  }
 }
 
 /* ---- tsadvc driver: mod_tsadvc.F90:1708-2258 ------------------------------ */

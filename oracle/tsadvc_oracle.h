@@ -49,6 +49,10 @@ typedef struct orc_tile {
   double *tracer;                    /* (P,kdm,2,ntracr) */
   double *uflx, *vflx;               /* (P,kdm) */
   double *q2, *q2l;                  /* (P,0:kdm+1,2) Mellor-Yamada tke fields (mxlmy) */
+  /* mod_asselin.F90: dpo (P,kdm,2), onetao (P,2), pbavg (P,3), pbot (P), otemp/osaln/oth3d (P,kdm),
+   * otracer (P,kdm,ntracr), oq2/oq2l (P,0:kdm+1) */
+  double *dpo, *onetao, *pbavg, *pbot, *otemp, *osaln, *oth3d, *otracer, *oq2, *oq2l;
+  double ra2fac, oneta0;
   double *theta;                     /* (P,kdm) isopycnic target densities, mod_cb_arrays.F90 */
   double *oneta, *onetamas;          /* (P,2) */
   double *uflux, *vflux, *uflux2, *vflux2, *util1, *util2; /* (P) */
@@ -121,6 +125,10 @@ double orc_tofsig(int sigver, double r, double s);
  * do_halo=0: the caller has already refreshed the halos (multi-tile emulation,
  *            orc_tsadvc_halo_list + orc_world_xctilr). Returns 0 or an error. */
 int orc_tsadvc(orc_tile *t, int m, int n, int do_halo);
+
+/* mod_asselin.F90:28-82 and :84-286 */
+void orc_asselin_save(orc_tile *t, int m, int n, int do_halo);
+void orc_asselin_filter(orc_tile *t, int m, int n);
 
 /* intermediate taps: the places the reference put pipe_compare_sym* hooks
  * (mod_tsadvc.F90:286-294,358-362,798-802,983-987).  When a tap buffer is set,

@@ -36,7 +36,9 @@ class OracleTile:
             pass
 
     _SHAPES = {"temp": 4, "saln": 4, "th3d": 4, "dp": 4, "tracer": 5, "uflx": 3, "vflx": 3,
-               "oneta": -2, "onetamas": -2, "xmin": 1, "xmax": 1, "theta": 3, "q2": 6, "q2l": 6}
+               "oneta": -2, "onetamas": -2, "xmin": 1, "xmax": 1, "theta": 3, "q2": 6, "q2l": 6,
+               "dpo": 4, "onetao": -2, "pbavg": -3, "otemp": 3, "osaln": 3, "oth3d": 3, "otracer": 7,
+               "oq2": 8, "oq2l": 8}
 
     def f64(self, name):
         g = self.geom
@@ -46,7 +48,9 @@ class OracleTile:
         kind = self._SHAPES.get(name, 2)
         shape = {2: (g.nrows, g.ncols), 3: (g.kdm, g.nrows, g.ncols),
                  4: (2, g.kdm, g.nrows, g.ncols), 5: (self.ntracr, 2, g.kdm, g.nrows, g.ncols),
-                 -2: (2, g.nrows, g.ncols), 1: (g.kdm,), 6: (2, g.kdm + 2, g.nrows, g.ncols)}[kind]
+                 -2: (2, g.nrows, g.ncols), 1: (g.kdm,), 6: (2, g.kdm + 2, g.nrows, g.ncols),
+                 -3: (3, g.nrows, g.ncols), 7: (self.ntracr, g.kdm, g.nrows, g.ncols),
+                 8: (g.kdm + 2, g.nrows, g.ncols)}[kind]
         n = int(np.prod(shape))
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,)).reshape(shape)
 
@@ -99,19 +103,28 @@ class OracleTile:
         if rc:
             raise RuntimeError(f"orc_tsadvc rc={rc}: {self.orc.last_error()}")
 
+    def asselin_save(self, m, n, do_halo=1):
+        self.lib.orc_asselin_save(self.t, m, n, do_halo)
+
+    def asselin_filter(self, m, n):
+        self.lib.orc_asselin_filter(self.t, m, n)
+
     def load_cb(self, cb):
         """copy a product-side CbArrays (host numpy) into this oracle tile"""
         for name in ("scp2", "scp2i", "scuy", "scvx", "aspux", "aspvy", "temp", "saln", "th3d",
-                     "dp", "uflx", "vflx", "oneta", "theta", "q2", "q2l"):
+                     "dp", "uflx", "vflx", "oneta", "theta", "q2", "q2l", "dpo", "onetao", "pbavg", "pbot",
+                     "otemp", "osaln", "oth3d", "oq2", "oq2l"):
             src = getattr(cb, name)
             if src is not None:
                 self.f64(name)[...] = src
         if cb.ntracr > 0:
             self.f64("tracer")[...] = cb.tracer
+            if cb.otracer is not None:
+                self.f64("otracer")[...] = cb.otracer
         for name in ("advtyp", "advflg", "btrmas", "hybrid", "isopyc", "mxlmy", "nstep", "diagno", "sigver"):
             self.set_i(name, int(getattr(cb, name)))
         self.set_i("nhybrd", cb.geom.kdm if cb.nhybrd < 0 else cb.nhybrd)
-        for name in ("delt1", "temdf2", "temdfc", "thbase", "onemm"):
+        for name in ("delt1", "temdf2", "temdfc", "thbase", "onemm", "ra2fac", "oneta0"):
             self.set_d(name, getattr(cb, name))
         tf = self.i32("trcflg")
         for q, v in enumerate(cb.trcflg):
@@ -148,6 +161,10 @@ class Oracle:
         lib.orc_advem.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp,
                                   C.c_double, C.c_int]
         lib.orc_tsadvc.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+        lib.orc_asselin_save.restype = None
+        lib.orc_asselin_save.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+        lib.orc_asselin_filter.restype = None
+        lib.orc_asselin_filter.argtypes = [_vp, C.c_int, C.c_int]
         lib.orc_sig.restype = C.c_double
         lib.orc_sig.argtypes = [C.c_int, C.c_double, C.c_double]
         lib.orc_tofsig.restype = C.c_double

@@ -436,3 +436,53 @@ def test_oracle_reproduces_golden_vectors(oracle, name):
     msk = util.interior_sea(cb)
     flds = dict(temp=alt["temp"], saln=alt["saln"], th3d=alt["th3d"], tracer=alt.get("tracer"))
     assert make_golden.digest(flds, msk, 2) == _GOLD[name], (name, "numpy restatement")
+
+
+# ---- mod_asselin.F90: asselin_save + asselin_filter ----------------
+@pytest.mark.parametrize("sigver,ntracr,extra", [(6, 2, {}), (8, 0, {"advflg": 1}), (2, 1, {"nhybrd": 1}),
+                                                  (7, 0, {"isopyc": True, "hybrid": False, "nhybrd": 0})])
+def test_asselin_c_oracle_equals_numpy_restatement(oracle, sigver, ntracr, extra):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(57, 44, 3, nreg=0, ntracr=ntracr, seed=5, **extra)
+    if sigver == 6:
+        util.add_q2(cfg, sea, g, cb, m, n)
+    util.add_asselin(cfg, sea, g, cb, m, n, sigver=sigver)
+    msk = util.interior_sea(cb)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    # asselin_save
+    ot.asselin_save(m, n, 1)
+    sv = npr.asselin_save(cb, m, n)
+    for name in ("oneta", "onetao"):
+        assert np.array_equal(ot.f64(name), sv[name], equal_nan=True), name
+    for name in ("otemp", "osaln", "oth3d") + (("otracer",) if ntracr else ()) + (("oq2", "oq2l") if cb.mxlmy else ()):
+        a, b = ot.f64(name), sv[name]
+        assert np.array_equal(a[..., msk], b[..., msk]), name
+    # asselin_filter from the same starting state
+    ot2 = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot2.asselin_filter(m, n)
+    fl = npr.asselin_filter(cb, m, n)
+    libm = sigver <= 4 and ("nhybrd" in extra or extra.get("advflg") == 1 or extra.get("isopyc"))
+    for name in ("oneta", "dp", "temp", "saln", "th3d") + (("tracer",) if ntracr else ()) + (("q2", "q2l") if cb.mxlmy else ()):
+        a, b = ot2.f64(name), fl[name]
+        if libm and name in ("temp",):
+            assert util.rel_err(a[m - 1], b[m - 1], msk) < 1e-13, name
+        else:
+            assert np.array_equal(a[..., msk], b[..., msk], equal_nan=True), name
+    assert not np.array_equal(ot2.f64("saln")[m - 1, 0][msk], cb.saln[m - 1, 0][msk])      # slot m was filtered
+    assert np.array_equal(ot2.f64("saln")[n - 1][:, msk], cb.saln[n - 1][:, msk])           # slot n untouched
+    ot.close(); ot2.close()
+
+
+def test_asselin_conserves_constants(oracle):
+    """'version that exactly conserves constant salinity' (mod_asselin.F90:143): a field that is the
+    same constant at t-1, t and t+1 comes out as that constant, bit for bit"""
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(40, 30, 2, ntracr=1, seed=3)
+    util.add_asselin(cfg, sea, g, cb, m, n)
+    cb.tracer[...] = 0.625
+    cb.otracer[...] = 0.625
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot.asselin_filter(m, n)
+    msk = util.interior_sea(cb)
+    assert np.all(ot.f64("tracer")[0, m - 1][:, msk] == 0.625)
+    ot.close()

@@ -678,3 +678,62 @@ def test_golden_vectors_on_device(name):
     msk = util.interior_sea(cb)
     flds = dict(temp=got["temp"], saln=got["saln"], th3d=got["th3d"], tracer=got["tracer"])
     assert make_golden.digest(flds, msk, 2) == _GOLD[name], name
+
+
+# ---------------------------------------------------------------------------------------
+# next to tsadvc: mod_asselin.F90 on the device mirrors
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sigver,ntracr,nreg,extra", [(6, 2, 0, {}), (8, 0, 3, {"advflg": 1}), (8, 1, 0, {"nhybrd": 1}),
+                                                       (2, 0, 1, {"nhybrd": 2}),
+                                                       (7, 0, 0, {"isopyc": True, "hybrid": False, "nhybrd": 0})])
+def test_asselin_device_matches_oracle(oracle, sigver, ntracr, nreg, extra):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(90, 61, 4, nreg=nreg, ntracr=ntracr, seed=41, **extra)
+    if sigver == 6:
+        util.add_q2(cfg, sea, g, cb, m, n)
+    util.add_asselin(cfg, sea, g, cb, m, n, sigver=sigver)
+    msk = util.interior_sea(cb)
+    flds = [(cabi.F_TEMP, "temp", 0), (cabi.F_SALN, "saln", 0), (cabi.F_TH3D, "th3d", 0), (cabi.F_DP, "dp", 0),
+            (cabi.F_ONETA, "oneta", 0)] + [(cabi.F_TRACER, "tracer", q + 1) for q in range(ntracr)]
+    if cb.mxlmy:
+        flds += [(cabi.F_Q2, "q2", 0), (cabi.F_Q2L, "q2l", 0)]
+    libm = sigver <= 4      # tofsig of the 7/9-term fits: atan2/cos/sin, 1e-12 instead of bits
+
+    def ref_of(ot, name, ktr, slot):
+        a = ot.f64(name)
+        return a[ktr - 1, slot - 1] if name == "tracer" else a[slot - 1]
+    # ---- asselin_save
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot.asselin_save(m, n, 1)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_asselin_state(m, n)
+    ts.asselin_save_device(m, n)
+    for slot in (1, 2):
+        for fld, name in ((cabi.F_ONETA, "oneta"), (cabi.F_ONETAO, "onetao")):
+            assert np.array_equal(ts.download(fld, slot)[0], ot.f64(name)[slot - 1], equal_nan=True), (name, slot)
+    olds = [(cabi.F_OTEMP, "otemp", 0), (cabi.F_OSALN, "osaln", 0), (cabi.F_OTH3D, "oth3d", 0)]
+    olds += [(cabi.F_OTRACER, "otracer", q + 1) for q in range(ntracr)]
+    if cb.mxlmy:
+        olds += [(cabi.F_OQ2, "oq2", 0), (cabi.F_OQ2L, "oq2l", 0)]
+    for fld, name, ktr in olds:
+        ref = ot.f64(name)[ktr - 1] if name == "otracer" else ot.f64(name)
+        assert np.array_equal(ts.download(fld, 1, ktr=ktr)[:, msk], ref[:, msk]), name
+    ts.close(); ot.close()
+    # ---- asselin_filter from the same starting state
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot.asselin_filter(m, n)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_asselin_state(m, n)
+    ts.asselin_filter_device(m, n)
+    for fld, name, ktr in flds:
+        for slot in (1, 2):
+            dev, ref = ts.download(fld, slot, ktr=ktr), ref_of(ot, name, ktr, slot)
+            if name == "oneta":
+                dev, ref = dev[0], ref
+                assert np.array_equal(dev[msk], ref[msk]), (name, slot)
+            elif libm and name == "temp":
+                assert util.rel_err(dev, ref, msk[None]) <= REL_TOL, (name, slot)
+            else:
+                assert np.array_equal(dev[:, msk], ref[:, msk]), (name, slot)
+    assert not np.array_equal(ts.download(cabi.F_SALN, m)[0][msk], cb.saln[m - 1, 0][msk])
+    ts.close(); ot.close()

@@ -131,3 +131,30 @@ def make_arctic_case(itdm, jtdm, kdm, ntracr=0, seed=1, m=1, n=2, **scalars):
     for name, it in (("scp2", 1), ("scp2i", 1), ("scuy", 3), ("aspux", 3), ("scvx", 4), ("aspvy", 4)):
         setattr(cb, name, np.ascontiguousarray(npr.halo_single_tile(g, getattr(cb, name), nb, nb, it)))
     return cfg, sea, g, cb
+
+
+def add_asselin(cfg, sea, g, cb, m, n, sigver=6, seed=77):
+    """operands of mod_asselin.F90 on top of a case: dpo both slots (a perturbed dp), pbot/pbavg so
+    that oneta = 1 + O(1e-3), the saved t-1 fields o* (a perturbed copy of slot n), dp of both slots"""
+    rng = np.random.default_rng(seed)
+    shp = (g.nrows, g.ncols)
+    kk = g.kdm
+    cb.sigver = sigver
+    cb.thbase = 34.0 if sigver % 2 == 0 else 25.0
+    cb.dpo = cb.dp * (1.0 + 0.02 * rng.standard_normal(cb.dp.shape))
+    cb.dpo[np.abs(cb.dp) == 0.0] = 0.0                     # massless layers stay massless at t-1 and t
+    cb.pbot = np.full(shp, 4.0e7) * (1.0 + 0.1 * rng.random(shp))
+    cb.pbavg = 4.0e4 * rng.standard_normal((3,) + shp)
+    cb.onetao = 1.0 + 1.0e-3 * rng.standard_normal((2,) + shp)
+    for name, src in (("otemp", cb.temp), ("osaln", cb.saln), ("oth3d", cb.th3d)):
+        setattr(cb, name, src[n - 1] * (1.0 + 1.0e-3 * rng.standard_normal(src[n - 1].shape)))
+    if cb.ntracr:
+        cb.otracer = cb.tracer[:, n - 1] * (1.0 + 1.0e-3 * rng.standard_normal(cb.tracer[:, n - 1].shape))
+    if cb.mxlmy:
+        cb.oq2 = cb.q2[n - 1] * (1.0 + 1.0e-3 * rng.standard_normal(cb.q2[n - 1].shape))
+        cb.oq2l = cb.q2l[n - 1] * (1.0 + 1.0e-3 * rng.standard_normal(cb.q2l[n - 1].shape))
+    if cb.theta is None:
+        cb.theta = np.empty((kk, g.nrows, g.ncols))
+        for k in range(kk):
+            cb.theta[k] = 1.0 + 0.1 * k
+    return cb
