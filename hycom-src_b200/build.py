@@ -41,6 +41,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libhycom_tsadvc_b200.so")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    cmd += os.environ.get("HYCOM_TSADVC_NVCC_EXTRA", "").split()   # experiments (e.g. -DTSADVC_...)
     cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     # the image exports CC/CXX=/opt/gcc/bin/* (no libgomp.spec); use the distro g++

@@ -148,8 +148,11 @@ __global__ void k_halo_xfer(HaloArrays a, HaloBufs b) {
 #pragma unroll
   for (int d = 0; d < 8; ++d) {
     first[d] = total;
-    halo_region(a, d, !PACK, w[d], h[d], c0[d], r0[d]);
-    const bool on = PACK ? (b.buf[d] != nullptr) : true;
+    if (halo_is_fold(a, d)) halo_fold_region(a, d, w[d], h[d], c0[d]);   // c0: first Fortran column sent
+    else halo_region(a, d, !PACK, w[d], h[d], c0[d], r0[d]);
+    // a fold direction is unpacked element by element of the message; without a message (never the
+    // case on a periodic top row) nothing is written
+    const bool on = (PACK || halo_is_fold(a, d)) ? (b.buf[d] != nullptr) : true;
     total += on ? (long)w[d] * h[d] * a.narr * a.kk : 0;
   }
   first[8] = total;
@@ -164,7 +167,23 @@ __global__ void k_halo_xfer(HaloArrays a, HaloBufs b) {
     const int s = (int)(q / per);
     const long e = q - (long)s * per;
     const int r = (int)(e / w[d]), c = (int)(e - (long)r * w[d]);
-    double* cell = a.base[s / a.kk] + a.slab * (s % a.kk) + (long)(r0[d] + r) * a.pitch + (c0[d] + c);
+    double* slab = a.base[s / a.kk] + a.slab * (s % a.kk);
+    if (halo_is_fold(a, d)) {
+      const int itype = a.itype[s / a.kk], grid = itype % 10;
+      const int j = r + 1, col = c0[d] + c;            // Fortran j of the halo line, column of the sender
+      if (PACK) {
+        const int jo = (grid == 1 || grid == 3) ? a.jj - 1 - j : a.jj - j;
+        const double v = slab[fidx(col, jo, a.nbdy, a.pitch)];
+        b.buf[d][q] = (itype > 10 && v != 0.0) ? -v : v;   // sarc*a unless a == vland
+      } else {
+        const int sh = (grid == 2 || grid == 3) ? 1 : 0;
+        const int ct = d == 3 ? col : d == 6 ? col + a.ii : col - a.ii;   // column relative to the twin
+        const int i = a.ii + 1 + sh - ct;
+        if (i >= 1 - a.mh && i <= a.ii + a.mh) slab[fidx(i, a.jj + j, a.nbdy, a.pitch)] = b.buf[d][q];
+      }
+      continue;
+    }
+    double* cell = slab + (long)(r0[d] + r) * a.pitch + (c0[d] + c);
     if (PACK) b.buf[d][q] = *cell;
     else *cell = b.buf[d] ? b.buf[d][q] : 0.0;  // vland
   }

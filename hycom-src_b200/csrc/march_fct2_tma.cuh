@@ -18,9 +18,14 @@
 //   * max(0,x), min(0,x) of S4 are formed as (x+|x|), (x-|x|) = twice the exact parts,
 //     the factor 2 is carried through famax/famin and 2*qdt2 and cancels in the quotient
 //     (scaling by 2 is exact, so every rounding is the reference's);
-//   * rp/rm are min(1, q/fa) evaluated with the reference's guard fa > 0; where fa == 0
-//     the reference stores 0 but that value only ever multiplies fluxes that are zero,
-//     so any finite stand-in gives identical results (and saves two selects);
+//   * rp/rm are the reference's (q < fa ? q/fa : 1) with the quotient formed unconditionally
+//     (one compare and one select per ratio); where fa == 0 the reference stores 0, here 1,
+//     but that value only ever multiplies fluxes that are zero, so any finite stand-in gives
+//     identical results;
+//   * row segments that are sea on every staged column are marched by a mask-free instantiation;
+//   * every register ring has period 3 and the ring slots of the staged rows rotate at run
+//     time, so the loop is unrolled three times, not six: both row bodies fit the
+//     instruction cache (march_tma_common.cuh, kPeriod);
 //   * comparisons against zero use the sign bit on the integer pipe;
 //   * one reciprocal of (fcn+onemu) serves the divisions of S2 and S6;
 //   * divisions are branch-free with a sticky flag and a whole-chunk redo (march_common.cuh).
@@ -31,21 +36,24 @@ namespace tsadvc {
 
 template <int NC>
 struct Fct2T {                                       // computed intermediates only
-  double DFLX[2][NC], FLY[2][NC];                    // flx(i+1)-flx(i), fly              [row&1]
+  // every ring is indexed by row mod 3 (the loop is unrolled three times); the two-row rings
+  // simply die one row earlier, registers are allocated by liveness
+  double DFLX[3][NC], FLY[3][NC];                    // flx(i+1)-flx(i), fly              [row%3]
   double FAX[3][NC], FAY[3][NC];                     // antidiffusive fluxes              [row%3]
   double LO[3][NC], FCN[3][NC], Y[3][NC];            // fldlo, fcn, 1/(fcn+onemu)         [row%3]
   double MXL[3][NC], MNL[3][NC];                     // fmxlo, fmnlo                      [row%3]
-  double RP[2][NC], RM[2][NC];                       //                                   [row&1]
-  double QMX[2][NC], QMN[2][NC];                     // fmx, fmn of S4                    [row&1]
-  double DFAXL[2][NC], FAYL[2][NC];                  // limited fluxes                    [row&1]
-  double FLXR[2][NC];                                // flx itself (fct4 only)            [row&1]
+  double RP[3][NC], RM[3][NC];                       //                                   [row%3]
+  double QMX[3][NC], QMN[3][NC];                     // fmx, fmn of S4                    [row%3]
+  double DFAXL[3][NC], FAYL[3][NC];                  // limited fluxes                    [row%3]
+  double FLXR[3][NC];                                // flx itself (fct4 only)            [row%3]
   unsigned m1, m2, m3;                               // masks of rows r-1, r-2, r-3
 };
 
-template <int NC, int ORDER = 2>
+template <int NC, int ORDER = 2, int SEA = 0>
 struct Fct2Scheme {
   typedef Fct2T<NC> State;
   static constexpr bool kNeedC = true;
+  static constexpr int kPeriod = 3;
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll
@@ -56,7 +64,7 @@ struct Fct2Scheme {
         s.Y[q][c] = 1.0; s.MXL[q][c] = 0.0; s.MNL[q][c] = 0.0;
       }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 3; ++q) {
         s.DFLX[q][c] = 0.0; s.FLY[q][c] = 0.0; s.RP[q][c] = 0.0; s.RM[q][c] = 0.0;
         s.QMX[q][c] = 0.0; s.QMN[q][c] = 0.0; s.DFAXL[q][c] = 0.0; s.FAYL[q][c] = 0.0;
         s.FLXR[q][c] = 0.0;
@@ -65,13 +73,29 @@ struct Fct2Scheme {
     s.m1 = s.m2 = s.m3 = 0u;
   }
 
+  // A marched row whose four live rows (r .. r-3) are sea, interior and surrounded by sea on all
+  // 32*NC columns (every mask byte 0xff) needs none of the mask logic: no land-face zeroing, no
+  // sea-only neighbour selection, no old-value select at the store: 14 % fewer instructions, all of
+  // them from the saturated ALU pipe.  Results are identical by construction (every select takes
+  // its "sea" branch).  The choice is made per row segment on the host, not per row in the loop: the
+  // launch is split into segments of all-sea rows (SEA = 1, the mask-free body) and the rest
+  // (SEA = 0), one kernel each (tsadvc_abi.cu, march_segments).  Both bodies in one loop, chosen by a
+  // vote per row, thrash the instruction cache (20 % of the stall samples unrolled six times, 8 %
+  // unrolled three times; profiles/r01z_*, r01zb_*) and end up slower than the general body alone.
   template <int PH, bool SAFE>
   static __device__ __forceinline__ void step(State& s, const TmaCtx& x, const RingPtr& p, const int r,
-                                              bool& bad) {
+                                              const SlotOff& so, bool& bad) {
+    const unsigned m0 = ld_mask_s<NC>(p, so.s0);
+    body<PH, SAFE, (SEA != 0)>(s, x, p, r, so, bad, m0);
+  }
+
+  template <int PH, bool SAFE, bool ALLSEA>
+  static __device__ __forceinline__ void body(State& s, const TmaCtx& x, const RingPtr& p, const int r,
+                                              const SlotOff& so, bool& bad, const unsigned m0) {
   typedef Ring<NC> R;
-  constexpr int p2 = PH & 1, q2 = p2 ^ 1;
+  // ring indices of rows r (and r-3), r-1, r-2
   constexpr int a3 = PH % 3, b3 = (PH + 2) % 3, c3 = (PH + 1) % 3;
-  constexpr int s0 = PH % 6, s1 = (PH + 5) % 6, s2 = (PH + 4) % 6, s3 = (PH + 3) % 6;  // rows r..r-3
+  const Off s0 = so.s0, s1 = so.s1, s2 = so.s2, s3 = so.s3;   // staged rows r..r-3
   const double onemu = 9806.e-12;  // :671
   const double dt2 = x.dt2;
 
@@ -80,7 +104,6 @@ struct Fct2Scheme {
   ld_own<NC, R::F>(p, s0, F0);
   ld_own<NC, R::F>(p, s1, F1);
   ld_own<NC, R::C>(p, s1, C1);
-  const unsigned m0 = ld_mask_s<NC>(p, s0);
   double V0[NC];
   ld_own<NC, R::V>(p, s0, V0);
   {
@@ -95,19 +118,19 @@ struct Fct2Scheme {
       const double F = F0[c], C = C0[c], U = U0[c], V = V0[c];
       const double qx = signbit_set(U) ? F : FW[c];               // :693-697
       const double qy = signbit_set(V) ? F : F1[c];               // :700-704
-      flx[c] = (mc & M_IU) ? U * qx : 0.0;
-      const double fly = (mc & M_IV) ? V * qy : 0.0;
+      flx[c] = (ALLSEA || (mc & M_IU)) ? U * qx : 0.0;
+      const double fly = (ALLSEA || (mc & M_IV)) ? V * qy : 0.0;
       if (ORDER == 2) {
         const double fhx = U * 0.5 * (C + CW[c]);                   // :824
         const double fhy = V * 0.5 * (C + C1[c]);                   // :828
-        s.FAX[a3][c] = (mc & M_IU) ? fhx - flx[c] : 0.0;
-        s.FAY[a3][c] = (mc & M_IV) ? fhy - fly : 0.0;
+        s.FAX[a3][c] = (ALLSEA || (mc & M_IU)) ? fhx - flx[c] : 0.0;
+        s.FAY[a3][c] = (ALLSEA || (mc & M_IV)) ? fhy - fly : 0.0;
       } else {
-        s.FLXR[p2][c] = flx[c];
+        s.FLXR[a3][c] = flx[c];
       }
-      s.FLY[p2][c] = fly;
+      s.FLY[a3][c] = fly;
     }
-    ediff<NC>(flx, s.DFLX[p2]);
+    ediff<NC>(flx, s.DFLX[a3]);
   }
   if (ORDER == 4) {
     // ---- S3 of advem_fct4 for row r-1 (:1528-1558): fldc of rows r-3..r and columns i-2..i+1
@@ -139,8 +162,8 @@ struct Fct2Scheme {
       const double fhy4 = V * (ft14 * (Cc[c] + Cs[c]) + ft24 * (Cn[c] + Css[c]));
       const double fhx = lowx ? fhx2 : fhx4;
       const double fhy = lowy ? fhy2 : fhy4;
-      s.FAX[b3][c] = (mc & M_IU) ? fhx - s.FLXR[q2][c] : 0.0;
-      s.FAY[b3][c] = (mc & M_IV) ? fhy - s.FLY[q2][c] : 0.0;
+      s.FAX[b3][c] = (mc & M_IU) ? fhx - s.FLXR[b3][c] : 0.0;
+      s.FAY[b3][c] = (mc & M_IV) ? fhy - s.FLY[b3][c] : 0.0;
     }
   }
 
@@ -162,10 +185,17 @@ struct Fct2Scheme {
       const double Fc = F1[c];
       // 5-point sea-only extrema of fld (:709-716)
       double mx, mn;
-      maxmin_first(mx, mn, Fc, Fc, Fw[c], Fw[c], m1, M_PW << (8 * c));
-      maxmin_if(mx, mn, Fe[c], Fe[c], m1, M_PE << (8 * c));
-      maxmin_if(mx, mn, F2[c], F2[c], m1, M_PS << (8 * c));
-      maxmin_if(mx, mn, F0[c], F0[c], m1, M_PN << (8 * c));
+      if (ALLSEA) {
+        mx = fmax2(Fw[c], Fc);    mn = fmin2(Fw[c], Fc);
+        mx = fmax2(Fe[c], mx);    mn = fmin2(Fe[c], mn);
+        mx = fmax2(F2[c], mx);    mn = fmin2(F2[c], mn);
+        mx = fmax2(F0[c], mx);    mn = fmin2(F0[c], mn);
+      } else {
+        maxmin_first(mx, mn, Fc, Fc, Fw[c], Fw[c], m1, M_PW << (8 * c));
+        maxmin_if(mx, mn, Fe[c], Fe[c], m1, M_PE << (8 * c));
+        maxmin_if(mx, mn, F2[c], F2[c], m1, M_PS << (8 * c));
+        maxmin_if(mx, mn, F0[c], F0[c], m1, M_PN << (8 * c));
+      }
       fmx[c] = mx; fmn[c] = mn;
       // tsadvc prolog :1934-1938 (onetamas(:,:,m) = 1.0 when .not.btrmas, :1809)
       const double fdp = ((UE[c] - U1[c]) + (V0[c] - V1[c])) * dt2 * SCI1[c];
@@ -173,7 +203,7 @@ struct Fct2Scheme {
       const double fco = pos_part(Dc + fdp);
       const double fcn = pos_part(Dc);
       // :786-793
-      const double flxdiv = ((s.DFLX[q2][c]) + (s.FLY[p2][c] - s.FLY[q2][c])) * dt2 * SCI1[c];
+      const double flxdiv = ((s.DFLX[b3][c]) + (s.FLY[a3][c] - s.FLY[b3][c])) * dt2 * SCI1[c];
       q[c] = Fc * (fco + onemu) - flxdiv;
       b[c] = fcn + onemu;
       y[c] = SAFE ? 0.0 : rcp_nr(b[c]);
@@ -204,16 +234,24 @@ struct Fct2Scheme {
     east_of<NC>(s.MNL[c3], mne);
     east_of<NC>(s.FAX[c3], faxe);
     double qq[2 * NC], bb[2 * NC], rr[2 * NC];
+    bool lt[2 * NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const unsigned mc = mk(m2, c);
-      const bool pe = mc & M_PE, pn = mc & M_PN;
+      const bool pe = ALLSEA || (mc & M_PE), pn = ALLSEA || (mc & M_PN);
       // 5-point sea-only extrema of fmxlo/fmnlo (:872-879)
       double fqmax, fqmin;
-      maxmin_first(fqmax, fqmin, s.MXL[c3][c], s.MNL[c3][c], mxw[c], mnw[c], m2, M_PW << (8 * c));
-      maxmin_if(fqmax, fqmin, mxe[c], mne[c], m2, M_PE << (8 * c));
-      maxmin_if(fqmax, fqmin, s.MXL[a3][c], s.MNL[a3][c], m2, M_PS << (8 * c));
-      maxmin_if(fqmax, fqmin, s.MXL[b3][c], s.MNL[b3][c], m2, M_PN << (8 * c));
+      if (ALLSEA) {
+        fqmax = fmax2(mxw[c], s.MXL[c3][c]);     fqmin = fmin2(mnw[c], s.MNL[c3][c]);
+        fqmax = fmax2(mxe[c], fqmax);            fqmin = fmin2(mne[c], fqmin);
+        fqmax = fmax2(s.MXL[a3][c], fqmax);      fqmin = fmin2(s.MNL[a3][c], fqmin);
+        fqmax = fmax2(s.MXL[b3][c], fqmax);      fqmin = fmin2(s.MNL[b3][c], fqmin);
+      } else {
+        maxmin_first(fqmax, fqmin, s.MXL[c3][c], s.MNL[c3][c], mxw[c], mnw[c], m2, M_PW << (8 * c));
+        maxmin_if(fqmax, fqmin, mxe[c], mne[c], m2, M_PE << (8 * c));
+        maxmin_if(fqmax, fqmin, s.MXL[a3][c], s.MNL[a3][c], m2, M_PS << (8 * c));
+        maxmin_if(fqmax, fqmin, s.MXL[b3][c], s.MNL[b3][c], m2, M_PN << (8 * c));
+      }
       const double faxc = s.FAX[c3][c];
       const double faxb = pe ? faxe[c] : faxc;             // fax(ib,j)  :880
       const double fayc = s.FAY[c3][c];
@@ -228,34 +266,36 @@ struct Fct2Scheme {
       const double lo = s.LO[c3][c], fcn = s.FCN[c3][c];
       const double qp2 = (fqmax - lo) * fcn * SC2[c] * x.qdt2x2;   // 2*qp  :885
       const double qm2 = (lo - fqmin) * fcn * SC2[c] * x.qdt2x2;   // 2*qm  :895
-      qq[2 * c] = qp2;     bb[2 * c] = (famax2 > 0.0) ? famax2 : 1.0;
-      qq[2 * c + 1] = qm2; bb[2 * c + 1] = (famin2 > 0.0) ? famin2 : 1.0;
-      s.QMX[p2][c] = fqmax;                                 // :904
-      s.QMN[p2][c] = fqmin;                                 // :905
+      // qp >= 0 and famax >= 0 (sums of non-negative parts), so qp < famax implies famax > 0
+      qq[2 * c] = qp2;     bb[2 * c] = famax2;     lt[2 * c] = qp2 < famax2;
+      qq[2 * c + 1] = qm2; bb[2 * c + 1] = famin2; lt[2 * c + 1] = qm2 < famin2;
+      s.QMX[c3][c] = fqmax;                                 // :904
+      s.QMN[c3][c] = fqmin;                                 // :905
     }
 #pragma unroll
     for (int i = 0; i < 2 * NC; ++i)
-      rr[i] = div_flag<SAFE>(qq[i], bb[i], SAFE ? 0.0 : rcp_nr(bb[i]), bad);
+      rr[i] = div_flag_if<SAFE>(qq[i], bb[i], SAFE ? 0.0 : rcp_nr(bb[i]), lt[i], bad);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      // :884-903: rp = famax>0 ? (qp<famax ? qp/famax : 1) : 0 ; see the header note for fa==0
-      s.RP[p2][c] = min_one(rr[2 * c]);
-      s.RM[p2][c] = min_one(rr[2 * c + 1]);
+      // :884-903: rp = famax>0 ? (qp<famax ? qp/famax : 1) : 0 ; see the header note for fa==0.
+      // The quotient is only used where qp < famax (elsewhere it may be inf/NaN: fa == 0)
+      s.RP[c3][c] = lt[2 * c] ? rr[2 * c] : 1.0;
+      s.RM[c3][c] = lt[2 * c + 1] ? rr[2 * c + 1] : 1.0;
     }
     // S5 (:926-945).  fax/fay are already zero on land faces, so no further select
     double rpw[NC], rmw[NC], faxl[NC];
-    west_of<NC>(s.RP[p2], rpw);
-    west_of<NC>(s.RM[p2], rmw);
+    west_of<NC>(s.RP[c3], rpw);
+    west_of<NC>(s.RM[c3], rmw);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const double faxc = s.FAX[c3][c], fayc = s.FAY[c3][c];
       const bool ngx = signbit_set(faxc), ngy = signbit_set(fayc);
-      const double fx = fmin2(ngx ? rpw[c] : s.RP[p2][c], ngx ? s.RM[p2][c] : rmw[c]);
-      const double fy = fmin2(ngy ? s.RP[q2][c] : s.RP[p2][c], ngy ? s.RM[p2][c] : s.RM[q2][c]);
+      const double fx = fmin2(ngx ? rpw[c] : s.RP[c3][c], ngx ? s.RM[c3][c] : rmw[c]);
+      const double fy = fmin2(ngy ? s.RP[a3][c] : s.RP[c3][c], ngy ? s.RM[c3][c] : s.RM[a3][c]);
       faxl[c] = fx * faxc;
-      s.FAYL[p2][c] = fy * fayc;
+      s.FAYL[c3][c] = fy * fayc;
     }
-    ediff<NC>(faxl, s.DFAXL[p2]);
+    ediff<NC>(faxl, s.DFAXL[c3]);
   }
 
   // ---- stage E: row r-3, S6 (:968-980) and store
@@ -266,16 +306,16 @@ struct Fct2Scheme {
     ld_own<NC, R::F>(p, s3, OLD3);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-      const double a = ((s.DFAXL[q2][c]) + (s.FAYL[p2][c] - s.FAYL[q2][c])) * dt2 * SCI3[c];
+      const double a = ((s.DFAXL[a3][c]) + (s.FAYL[c3][c] - s.FAYL[a3][c])) * dt2 * SCI3[c];
       const double d = div_flag<SAFE>(a, s.FCN[a3][c] + onemu, s.Y[a3][c], bad);
-      nv[c] = fmax2(s.QMN[q2][c], fmin2(s.QMX[q2][c], s.LO[a3][c] - d));
+      nv[c] = fmax2(s.QMN[a3][c], fmin2(s.QMX[a3][c], s.LO[a3][c] - d));
     }
     const int col = x.w0 + NC * x.lane;
     if ((unsigned)col < (unsigned)x.pitch && r3 >= x.j0 && r3 < x.j1) {
       Vec<NC> old;
 #pragma unroll
       for (int c = 0; c < NC; ++c) old.v[c] = OLD3[c];
-      store_vec<NC>(x.out, (long)r3 * x.pitch + col, x.lane, s.m3, old, nv);
+      store_vec<NC>(x.out, (long)r3 * x.pitch + col, x.lane, ALLSEA ? ((NC == 2) ? 0xffffu : 0xffu) : s.m3, old, nv);
     }
   }
   s.m3 = s.m2; s.m2 = s.m1; s.m1 = m0;

@@ -34,6 +34,7 @@ template <int NC>
 struct MpdataScheme {
   typedef MpdataT<NC> State;
   static constexpr bool kNeedC = false;
+  static constexpr int kPeriod = 6;
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll

@@ -16,6 +16,7 @@ template <int NC>
 struct PcmScheme {
   typedef PcmT<NC> State;
   static constexpr bool kNeedC = false;
+  static constexpr int kPeriod = 6;
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll

@@ -166,12 +166,66 @@ __device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, int slot) {
 }
 
 
+// The same accessors for a slot given by its byte offset in the ring at run time (a scheme whose
+// register rings all have period 3 is unrolled three times, not six, so the slot of a row is no
+// longer a compile-time constant; the offset is warp-uniform).
+struct Off { int b; };
+struct SlotOff { Off s0, s1, s2, s3; };   // slots of rows r, r-1, r-2, r-3
+template <int NC, int ARR>
+__device__ __forceinline__ void ld_own(const RingPtr& p, Off o, double (&x)[NC]) {
+  typedef Ring<NC> R;
+  const unsigned char* a = p.c + o.b + ARR * R::RB;
+  if (NC == 2) {
+    const double2 v = *reinterpret_cast<const double2*>(a);
+    x[0] = v.x; x[NC - 1] = v.y;
+  } else {
+    x[0] = *reinterpret_cast<const double*>(a);
+  }
+}
+template <int NC, int ARR>
+__device__ __forceinline__ void ld_west(const RingPtr& p, Off o, const double (&own)[NC], double (&w)[NC]) {
+  typedef Ring<NC> R;
+  w[0] = *reinterpret_cast<const double*>(p.w + o.b + ARR * R::RB);
+  if (NC == 2) w[NC - 1] = own[0];
+}
+template <int NC, int ARR>
+__device__ __forceinline__ void ld_east(const RingPtr& p, Off o, const double (&own)[NC], double (&e)[NC]) {
+  typedef Ring<NC> R;
+  e[NC - 1] = *reinterpret_cast<const double*>(p.e + o.b + ARR * R::RB);
+  if (NC == 2) e[0] = own[NC - 1];
+}
+template <int NC, int ARR>
+__device__ __forceinline__ double ld_at(const unsigned char* q, Off o) {
+  typedef Ring<NC> R;
+  return *reinterpret_cast<const double*>(q + o.b + ARR * R::RB);
+}
+template <int NC>
+__device__ __forceinline__ unsigned ld_mask_at(const unsigned char* q, Off o) {
+  typedef Ring<NC> R;
+  return *reinterpret_cast<const unsigned*>(q + o.b + R::MSK * R::RB);
+}
+template <int NC>
+__device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, Off o) {
+  typedef Ring<NC> R;
+  const unsigned char* a = p.c + o.b + R::MSK * R::RB;
+  unsigned m = *reinterpret_cast<const unsigned*>(a);
+  if (NC == 2) m |= *reinterpret_cast<const unsigned*>(a + 8) << 8;
+  return m;
+}
+
 // ---------------------------------------------------------------------------------------
 // the march of one (field, layer, strip, chunk) unit for a scheme S:
 //   S::State          computed intermediates (register rings)
 //   S::kNeedC         fldc is staged
 //   S::init(State&)   rows below the chunk
-//   S::step<PH,SAFE>(State&, ctx, ringptr, r, bad)   one marched row, phase PH = row mod 6
+//   S::kPeriod        6: S::step<PH,SAFE>(State&, ctx, ringptr, r, bad), phase PH = row mod 6, ring
+//                        slots are compile-time constants;
+//                     3: S::step<PH,SAFE>(State&, ctx, ringptr, r, SlotOff, bad), PH = row mod 3, the
+//                        slots rotate at run time.  Half the code: the six-fold unrolled loop of
+//                        FCT2 (64 KB of SASS) already missed in the instruction cache (3 % of the
+//                        stall samples), and two copies of it (the all-sea and the general row body)
+//                        thrash it (21 %, profiles/r01z); unrolled three times, both bodies fit.
+//                        (Period 2 would need register moves: a value lives three rows.)
 // ---------------------------------------------------------------------------------------
 template <class S, int NC, bool SAFE>
 __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p, uint32_t& round) {
@@ -193,6 +247,28 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     issue_row<NC, S::kNeedC>(x, r0 + 1, 1);
     issue_row<NC, S::kNeedC>(x, r0 + 2, 2);
   }
+  if constexpr (S::kPeriod == 3) {
+    int slot = 0;                        // slot of row r; rows r-1..r-3 sit in slot-1..slot-3 (mod 6)
+    uint32_t par = round & 1u;           // parity the barrier of that slot completes next
+    SlotOff so{{0}, {5 * R::SLOT}, {4 * R::SLOT}, {3 * R::SLOT}};
+#define TSADVC_PHASE3(PH)                                                                 \
+  {                                                                                       \
+    mbar_wait(x.bar_s + 8u * slot, par);                                                  \
+    S::template step<PH, SAFE>(s, x, p, r0 + t + (PH), so, bad);                          \
+    __syncwarp();                                                                         \
+    const int slot3 = slot >= 3 ? slot - 3 : slot + 3;   /* row r-3: free now */           \
+    if (t + (PH) + 3 < niter && elect_one())                                              \
+      issue_row<NC, S::kNeedC>(x, r0 + t + (PH) + 3, slot3);                              \
+    so.s3 = so.s2; so.s2 = so.s1; so.s1 = so.s0;                                          \
+    slot = slot == 5 ? 0 : slot + 1;                                                      \
+    par ^= (slot == 0) ? 1u : 0u;                                                         \
+    so.s0.b = slot * R::SLOT;                                                             \
+  }
+    for (int t = 0; t < niter; t += 3) { TSADVC_PHASE3(0) TSADVC_PHASE3(1) TSADVC_PHASE3(2) }
+#undef TSADVC_PHASE3
+    round += (uint32_t)(niter / 6);
+    return bad;
+  } else {
 #define TSADVC_PHASE(PH)                                                                  \
   {                                                                                       \
     mbar_wait(x.bar_s + 8u * (PH), round & 1u); /* row r has landed in slot PH */          \
@@ -208,6 +284,7 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
   }
 #undef TSADVC_PHASE
   return bad;
+  }
 }
 
 // the whole chunk again with the compiler's a/b: taken by a warp only when one of its lanes

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/hycom_tsadvc_b200.h"
@@ -239,9 +240,15 @@ int hycom_tsadvc_create(const hycom_tsadvc_dims* dims, hycom_tsadvc_handle** out
       d.ii > d.idm || d.jj > d.jdm || d.ntracr < 0 || d.ntracr > HYCOM_TSADVC_MXTRCR)
     return fail(nullptr, HYCOM_TSADVC_EINVAL, "bad dimensions idm=%d jdm=%d kdm=%d nbdy=%d ii=%d jj=%d ntracr=%d",
                 d.idm, d.jdm, d.kdm, d.nbdy, d.ii, d.jj, d.ntracr);
-  if (d.nreg == 2 && d.ipr * d.jpr != 1)
-    return fail(nullptr, HYCOM_TSADVC_EUNSUPPORTED,
-                "nreg=2 (arctic tripole) on more than one tile: the folded top-row exchange of mod_xc_mp.h:4114-4662 is not built yet");
+  // xcspmd's conditions for the arctic patch (mod_xc_mp.h:2614-2643, :2817-2823): ipr even or 1, and
+  // every tile of the top row itdm/ipr wide (twins exchange whole, mirrored rows)
+  if (d.nreg == 2 && d.ipr * d.jpr != 1) {
+    if (d.ipr > 1 && d.ipr % 2 != 0)
+      return fail(nullptr, HYCOM_TSADVC_EINVAL, "Error in xcspmd (arctic) - ipr must be even (ipr=%d)", d.ipr);
+    if (d.nproc == d.jpr && (d.itdm % d.ipr != 0 || d.ii != d.itdm / d.ipr))
+      return fail(nullptr, HYCOM_TSADVC_EINVAL, "error - arctic patch tiles should have ii = %d (ii=%d)",
+                  d.itdm / d.ipr, d.ii);
+  }
   if (d.nreg < 0 || d.nreg > 4) return fail(nullptr, HYCOM_TSADVC_EINVAL, "bad nreg %d", d.nreg);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -271,6 +278,7 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   cudaDeviceSynchronize();
   for (void* raw : h->raw_allocs) cudaFree(raw);  // field mirrors, flux block, static block
   cudaFree(h->mask); cudaFree(h->scuy); cudaFree(h->scvx);
+  for (auto& kv : h->seg_cache) { cudaFree(kv.second.d[0]); cudaFree(kv.second.d[1]); }
   cudaFree(h->aspux); cudaFree(h->aspvy); cudaFree(h->d_minmax); cudaFree(h->d_sea);
   for (auto* v : {&h->ev_pending, &h->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -379,6 +387,9 @@ int hycom_tsadvc_set_static(hycom_tsadvc_handle* h, const double* scp2, const do
     }
   if (!h->mask && (rc = dalloc(h, (void**)&h->mask, (size_t)h->slab, true))) return rc;
   CU(h, cudaMemcpyAsync(h->mask, m.data(), (size_t)h->slab, cudaMemcpyHostToDevice, h->stream));
+  h->mask_host = m;
+  for (auto& kv : h->seg_cache) { cudaFree(kv.second.d[0]); cudaFree(kv.second.d[1]); }
+  h->seg_cache.clear();
   {  // third plane of the static block: the mask byte in the low bits of a 64-bit word
     std::vector<uint64_t> m64((size_t)h->slab);
     for (size_t q = 0; q < m64.size(); ++q) m64[q] = m[q];
@@ -533,6 +544,12 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   return 0;
 }
 
+// a tile of the top row of a multi-tile global grid across the arctic: its northern exchange is the
+// tripole fold (mod_xc_mp.h:4263-4372, :4400-4428)
+inline int arctic_fold(const hycom_tsadvc_dims& d) {
+  return (d.nreg == 2 && d.ipr * d.jpr > 1 && d.nproc == d.jpr) ? 1 : 0;
+}
+
 // the arrays xctilr is called on at mod_tsadvc.F90:1829-1836 (th3d is exchanged by the
 // reference too but not read when advflg=0 and temdf2=0: left out of the multi-tile messages)
 int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, HaloArrays& a) {
@@ -543,23 +560,112 @@ int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, H
       if ((rc = slot(h, f.field, f.ktr, t, &a.base[a.narr]))) return rc;
       a.base[a.narr++] += h->slab * f.koff;   // q2,q2l: the advected layers 1..kk
     }
+  for (int q = 0; q < a.narr; ++q) a.itype[q] = 1;                  // halo_ps (:1829-1836)
+  a.itype[a.narr] = 13;                                             // halo_uv
   if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &a.base[a.narr++]))) return rc;
+  a.itype[a.narr] = 14;                                             // halo_vv
   if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &a.base[a.narr++]))) return rc;
   a.kk = h->d.kdm; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
   a.ii = h->d.ii; a.jj = h->d.jj; a.mh = mbdy; a.nh = mbdy;
+  a.fold = arctic_fold(h->d);
   return 0;
 }
 
 // 0-based tile index of the neighbour in direction d, -1 at a closed edge
-// (mod_xc.F90:25-31: nreg 1,3 periodic in i; nreg 3,4 periodic in j)
+// (mod_xc.F90:25-31: nreg 1,3 periodic in i; nreg 3,4 periodic in j).  Across the arctic (nreg=2)
+// the tiles of the top row face their twins: idproc(m,jpr+1) = idproc(ipr+1-m,jpr)
+// (mod_xc_mp.h:2830), so N is the twin of this tile, NW the twin of the western and NE the twin of
+// the eastern neighbour.
 int neighbour(const hycom_tsadvc_dims& d, int dir) {
   static const int dx[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
   static const int dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};
   const bool per_i = !(d.nreg == 0 || d.nreg == 4), per_j = d.nreg > 2;
+  if (arctic_fold(d) && dy[dir] > 0) {
+    const int mw = ((d.mproc - 1 + dx[dir]) % d.ipr + d.ipr) % d.ipr;
+    return (d.ipr - 1 - mw) + d.ipr * (d.nproc - 1);
+  }
   int mp = d.mproc - 1 + dx[dir], np = d.nproc - 1 + dy[dir];
   if (mp < 0 || mp >= d.ipr) { if (!per_i) return -1; mp = (mp + d.ipr) % d.ipr; }
   if (np < 0 || np >= d.jpr) { if (!per_j) return -1; np = (np + d.jpr) % d.jpr; }
   return mp + d.ipr * np;
+}
+
+// Row segments of an FCT2 launch.  Every (strip, row) of the rectangles of P is assigned to a run of
+// rows: runs whose staged window (32*nc columns, rows j0-3 .. j1+2) holds nothing but mask bytes 0xff
+// (sea, interior, sea on all four sides) are marched by the mask-free instantiation of the kernel, the
+// rest by the general one.  The marching loop works in rounds of six rows, so the all-sea runs are cut
+// to a multiple of six rows (no row beyond the run is ever computed); short runs are not worth the six
+// rows of pipeline fill and stay with the general kernel.  Built once per (part, nc, chunk rows).
+static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part, int chunk_rows,
+                          const hycom_tsadvc_handle::SegLists** out) {
+  const long key = ((long)part << 40) | ((long)P.nc << 32) | (long)chunk_rows;
+  auto it = h->seg_cache.find(key);
+  if (it != h->seg_cache.end()) { *out = &it->second; return 0; }
+  const int use = strip_use(P.nc), lead = strip_lead(P.nc), wid = 32 * P.nc;
+  const int pitch = h->pitch, nrows = h->nrows;
+  const int kMinRows = 48;
+  std::vector<MarchSeg> seg[2];
+  std::vector<char> good(nrows + 8), taken(nrows);
+  for (int q = 0; q < P.nrect; ++q) {
+    const MarchRect& R = P.rect[q];
+    const int fast_piece = (R.chunk_rows / 6) * 6;
+    for (int st = R.strip0; st < R.strip0 + R.nstrips; ++st) {
+      const int w0 = st * use - lead;
+      const bool cols_ok = w0 >= 0 && w0 + wid <= pitch;
+      for (int r = 0; r < nrows; ++r) {
+        bool g = cols_ok;
+        if (g) {
+          const uint8_t* mrow = h->mask_host.data() + (size_t)r * pitch + w0;
+          for (int c = 0; c < wid && g; ++c) g = mrow[c] == 0xff;
+        }
+        good[r] = g;
+        taken[r] = 0;
+      }
+      if (fast_piece >= kMinRows) {
+        int r = 0;
+        while (r < nrows) {
+          if (!good[r]) { ++r; continue; }
+          int b = r;
+          while (b < nrows && good[b]) ++b;                  // good rows [r, b)
+          int j0 = std::max(r + 3, R.row0), j1 = std::min(b - 3, R.row1);
+          int len = ((j1 - j0) / 6) * 6;
+          if (len >= kMinRows) {
+            for (int a = j0; a < j0 + len; a += fast_piece) {
+              const int e = std::min(a + fast_piece, j0 + len);
+              seg[0].push_back(MarchSeg{st, a, e, 0});
+              for (int t = a; t < e; ++t) taken[t] = 1;
+            }
+          }
+          r = b;
+        }
+      }
+      int r = R.row0;
+      while (r < R.row1) {
+        if (taken[r]) { ++r; continue; }
+        int b = r;
+        while (b < R.row1 && !taken[b] && b - r < R.chunk_rows) ++b;
+        seg[1].push_back(MarchSeg{st, r, b, 0});
+        r = b;
+      }
+    }
+  }
+  hycom_tsadvc_handle::SegLists L;
+  for (int c = 0; c < 2; ++c) {
+    // neighbouring strips of the same rows next to each other: they share their aprons through L2
+    std::stable_sort(seg[c].begin(), seg[c].end(), [&](const MarchSeg& a, const MarchSeg& b) {
+      const int ba = a.j0 / (chunk_rows > 0 ? chunk_rows : 1), bb = b.j0 / (chunk_rows > 0 ? chunk_rows : 1);
+      return ba != bb ? ba < bb : a.strip < b.strip;
+    });
+    L.n[c] = (long)seg[c].size();
+    if (L.n[c]) {
+      CU(h, cudaMalloc(&L.d[c], sizeof(MarchSeg) * seg[c].size()));
+      CU(h, cudaMemcpyAsync(L.d[c], seg[c].data(), sizeof(MarchSeg) * seg[c].size(), cudaMemcpyHostToDevice,
+                            h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+    }
+  }
+  *out = &(h->seg_cache[key] = L);
+  return 0;
 }
 
 // layers k0 .. k0+nk-1 (0-based; nk < 0: all)
@@ -664,8 +770,25 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     else { CU(h, cudaEventCreate(&ev.first)); CU(h, cudaEventCreate(&ev.second)); }
     CU(h, cudaEventRecord(ev.first, lst));
   }
-  rc = launch_march_tma(aadv, P, lst);
-  h->launches += 1;
+  // FCT2: the all-sea row segments go to the mask-free instantiation, the rest to the general one
+  // (HYCOM_TSADVC_SPLIT=0: one general launch over the regular chunks)
+  const char* cs = getenv("HYCOM_TSADVC_SPLIT");
+  if (aadv == 2 && !p.btrmas && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
+    const hycom_tsadvc_handle::SegLists* L = nullptr;
+    if ((rc = march_segments(h, P, part, chunk_rows, &L))) return rc;
+    rc = 0;
+    for (int c = 1; c >= 0 && !rc; --c) {       // the general segments first: the long launch hides their tail
+      if (!L->n[c]) continue;
+      MarchParams Q = P;
+      Q.seg = (const MarchSeg*)L->d[c]; Q.nseg = L->n[c]; Q.allsea = (c == 0);
+      Q.nunits = (long)Q.njobs * Q.nseg;
+      rc = launch_march_tma(aadv, Q, lst);
+      h->launches += 1;
+    }
+  } else {
+    rc = launch_march_tma(aadv, P, lst);
+    h->launches += 1;
+  }
   if (h->timing) {
     CU(h, cudaEventRecord(ev.second, lst));
     h->ev_pending.push_back(ev);
@@ -786,6 +909,8 @@ void fct2c_halo_arrays(const hycom_tsadvc_handle* h, const Fct2cParams& P, HaloA
   for (int f = 0; f < P.nf; ++f) a.base[a.narr++] = P.fldlo + (long)f * P.nb * P.slab;
   a.kk = P.nb; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
   a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 5; a.nh = 5;
+  for (int q = 0; q < a.narr; ++q) a.itype[q] = 1;   // halo_ps (:1186-1187)
+  a.fold = arctic_fold(h->d);
 }
 
 // the whole scheme on a single tile
@@ -872,6 +997,8 @@ int diff_halo_arrays(hycom_tsadvc_handle* h, int n, bool mxlmy, HaloArrays& a) {
     }
   a.kk = h->d.kdm; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
   a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 2; a.nh = 2;
+  for (int q = 0; q < a.narr; ++q) a.itype[q] = 1;   // halo_ps (:2140-2151)
+  a.fold = arctic_fold(h->d);
   return 0;
 }
 
@@ -1050,9 +1177,7 @@ static int fct2c_halo_xfer(hycom_tsadvc_handle* h, int32_t m, int32_t n, const h
   fct2c_halo_arrays(h, P, a);
   if (mode == 0) {
     for (int d = 0; d < 8; ++d) {
-      int w, hh, c0, r0;
-      halo_region(a, d, false, w, hh, c0, r0);
-      count[d] = (int64_t)w * hh * a.narr * a.kk;
+      count[d] = (int64_t)halo_count(a, d);
     }
     return 0;
   }
@@ -1199,9 +1324,7 @@ int hycom_tsadvc_diff_halo_counts(hycom_tsadvc_handle* h, int32_t n, const hycom
   int rc;
   if ((rc = diff_halo_arrays(h, n, prm->mxlmy != 0, a))) return rc;
   for (int d = 0; d < 8; ++d) {
-    int w, hh, c0, r0;
-    halo_region(a, d, false, w, hh, c0, r0);
-    count[d] = (int64_t)w * hh * a.narr * a.kk;
+    count[d] = (int64_t)halo_count(a, d);
   }
   return 0;
 }
@@ -1253,9 +1376,7 @@ int hycom_tsadvc_halo_counts(hycom_tsadvc_handle* h, int32_t m, int32_t n,
   HaloArrays a;
   if ((rc = halo_arrays(h, adv, mbdy, a))) return rc;
   for (int d = 0; d < 8; ++d) {
-    int w, hh, c0, r0;
-    halo_region(a, d, false, w, hh, c0, r0);
-    count[d] = (int64_t)w * hh * a.narr * a.kk;
+    count[d] = (int64_t)halo_count(a, d);
   }
   return 0;
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
 #include <utility>
 #include <vector>
 
@@ -31,6 +32,11 @@ struct hycom_tsadvc_handle {
   int64_t launches = 0;
   bool have_static = false;
   uint8_t* mask = nullptr;
+  std::vector<uint8_t> mask_host;   // the same bytes on the host (row segments of the FCT2 launch)
+  // row segments of the marching launch per (part, cells per lane, chunk rows): device arrays of
+  // MarchSeg, [0] the all-sea segments, [1] the rest (tsadvc_abi.cu, march_segments)
+  struct SegLists { void* d[2] = {nullptr, nullptr}; long n[2] = {0, 0}; };
+  std::map<long, SegLists> seg_cache;
   double *scp2 = nullptr, *scp2i = nullptr, *scuy = nullptr, *scvx = nullptr, *aspux = nullptr,
          *aspvy = nullptr;
   tsadvc::Mirror temp, saln, th3d, dp, uflx, vflx;

@@ -17,6 +17,9 @@ struct MarchRect {
   long unit0;            // first unit: unit = unit0 + job + njobs*(strip + nstrips*chunk)
 };
 
+// a run of rows of one strip (instead of the regular chunks of a rectangle)
+struct MarchSeg { int strip, j0, j1, pad; };
+
 struct MarchParams {
   FieldDesc fld[kMaxFields];
   int nfld;
@@ -35,6 +38,10 @@ struct MarchParams {
   int nrect;
   MarchRect rect[4];
   long nunits;      // sum over rectangles of njobs*nstrips*nchunks
+  // alternatively the launch covers a list of row segments: unit = job + njobs*segment
+  const MarchSeg* seg;
+  long nseg;
+  int allsea;       // every staged cell of every segment is sea (mask byte 0xff): mask-free body
 };
 
 // scheme: 1 = MPDATA, 2 = FCT2 (advtyp of blkdat.input, mod_tsadvc.F90:87-90)
@@ -63,6 +70,11 @@ struct HaloArrays {
   int kk;
   long slab;
   int pitch, nrows, nbdy, ii, jj, mh, nh;
+  // tile of the top row of a global grid across the arctic (nreg=2, mod_xc_mp.h:4114-4662): the
+  // directions N, NW, NE carry the tripole fold instead of a plain strip.  itype is xctilr's grid and
+  // field type of each array (1 p-grid scalar, 13 u-grid vector, 14 v-grid vector, mod_xc.F90:41-44)
+  int fold;
+  int itype[kMaxHaloArrays];
 };
 struct HaloBufs {
   double* buf[8];     // per direction (W,E,S,N,SW,SE,NW,NE); nullptr: skip (pack) / vland (unpack)
@@ -83,6 +95,30 @@ __host__ __device__ inline void halo_region(const HaloArrays& a, int d, bool rec
   if (ys == 0) { h = a.jj; r0 = nb; }
   else if (ys < 0) { h = a.nh; r0 = recv ? nb - a.nh : nb; }
   else { h = a.nh; r0 = recv ? nb + a.jj : nb + a.jj - a.nh; }
+}
+
+// Fold messages (directions N=3, NW=6, NE=7 of a top-row arctic tile; all top-row tiles have the
+// same ii).  The tile T' = twin of the receiver sends all ii columns (N), the tile east of T' its first
+// mh+1 columns (NW) and the tile west of T' its last mh columns (NE); per array the rows are
+// jj-1-j (p,u grid) or jj-j (q,v grid), j=1..nh, and the sender applies the sign rule of
+// mod_xc_mp.h:4263-4372 (vector fields change sign unless the value is vland).  The receiver
+// mirrors: column c of T' lands at i = ii+1+s-c (s = 1 on the u,q grids whose mirror is shifted by
+// one column, mod_xc_mp.h:4283-4331) in row jj+j; cells that fall outside 1-mh..ii+mh are dropped.
+__host__ __device__ inline bool halo_is_fold(const HaloArrays& a, int d) {
+  return a.fold && (d == 3 || d == 6 || d == 7);
+}
+__host__ __device__ inline void halo_fold_region(const HaloArrays& a, int d, int& w, int& h, int& c1) {
+  h = a.nh;
+  if (d == 3) { w = a.ii; c1 = 1; }
+  else if (d == 6) { w = a.mh + 1; c1 = 1; }
+  else { w = a.mh; c1 = a.ii - a.mh + 1; }
+}
+// doubles of the message in direction d
+__host__ __device__ inline long halo_count(const HaloArrays& a, int d) {
+  int w, h, c0, r0;
+  if (halo_is_fold(a, d)) halo_fold_region(a, d, w, h, c0);
+  else halo_region(a, d, false, w, h, c0, r0);
+  return (long)w * h * a.narr * a.kk;
 }
 
 int launch_halo_pack(const HaloArrays& a, const HaloBufs& b, cudaStream_t stream);

@@ -133,12 +133,12 @@ def bigrid_masks(sea: np.ndarray, g: TileGeom):
 
 
 def _bigrid_masks_arctic(sea: np.ndarray, g: TileGeom):
-    """nreg=2 (global grid across the arctic, single tile): periodic in i, land south of row 1,
-    and the rows above jtdm are the tripole fold ip(i,jtdm+j) = ip(itdm+1-i, jtdm-1-j)
-    (bigrid.F90:116-131 + xctilr halo_ps of mod_xc_sm.h:1215-1232).  iu/iv follow from ip: for a
+    """nreg=2 (global grid across the arctic): periodic in i, land south of row 1, and the rows
+    above jtdm are the tripole fold ip(i,jtdm+j) = ip(itdm+1-i, jtdm-1-j) (bigrid.F90:116-131 +
+    xctilr halo_ps of mod_xc_sm.h:1215-1232 / mod_xc_mp.h:4263-4281).  iu/iv follow from ip: for a
     depth array that is itself fold-consistent in row jtdm this equals the reference's
-    halo_us/halo_vs updates of the interior iu/iv."""
-    assert g.ipr == 1 and g.jpr == 1, "arctic masks: single tile only"
+    halo_us/halo_vs updates of the interior iu/iv.  A tile is a window of the padded global map
+    (the tiles of the top row see the fold in their northern halo)."""
     nb, ni, nj = g.nbdy, g.itdm, g.jtdm
     ipg = np.zeros((nj + 2 * nb + 1, ni + 2 * nb + 1), dtype=np.int32)   # one extra cell west/south
     jj = np.arange(-nb, nj + nb + 1)       # Fortran j of every row (from 1-nb-1)
@@ -156,6 +156,11 @@ def _bigrid_masks_arctic(sea: np.ndarray, g: TileGeom):
     ip = ipg[1:, 1:]
     iu = ip & ipg[1:, :-1]
     iv = ip & ipg[:-1, 1:]
+    if g.ipr * g.jpr > 1:
+        win = (slice(g.j0, g.j0 + g.nrows), slice(g.i0, g.i0 + g.ncols))
+        live = np.zeros((g.nrows, g.ncols), dtype=bool)     # bigrid fills 1-nbdy..ii+nbdy only
+        live[: g.jj + 2 * nb, : g.ii + 2 * nb] = True
+        ip, iu, iv = (np.where(live, a[win], 0) for a in (ip, iu, iv))
     return (np.ascontiguousarray(ip, dtype=np.int32), np.ascontiguousarray(iu, dtype=np.int32),
             np.ascontiguousarray(iv, dtype=np.int32))
 

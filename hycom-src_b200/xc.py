@@ -27,11 +27,28 @@ DIR_DXY = ((-1, 0), (1, 0), (0, -1), (0, 1), (-1, -1), (1, -1), (-1, 1), (1, 1))
 OPP = (1, 0, 3, 2, 7, 6, 5, 4)
 
 
+def arctic_fold(g: TileGeom) -> bool:
+    """a tile of the top row of a multi-tile global grid across the arctic (nreg=2): its northern
+    exchange is the tripole fold with the twin tiles (mod_xc_mp.h:2830, :4263-4428)"""
+    return g.nreg == 2 and g.ipr * g.jpr > 1 and g.nproc == g.jpr
+
+
+def opp_dir(g: TileGeom, d: int) -> int:
+    """the direction in which the peer sent the message that arrives from direction d: the
+    opposite one, except across the fold where N, NW, NE pair with themselves (both twins look
+    north at each other)"""
+    return d if arctic_fold(g) and DIR_DXY[d][1] > 0 else OPP[d]
+
+
 def neighbors(g: TileGeom) -> List[int]:
     """0-based tile index (mproc-1 + ipr*(nproc-1)) of the eight neighbours, -1 at a closed
-    edge (mod_xc.F90:25-31: nreg 1,3 periodic in i; nreg 3,4 periodic in j)."""
+    edge (mod_xc.F90:25-31: nreg 1,3 periodic in i; nreg 3,4 periodic in j).  Across the arctic
+    the top row faces its twins: idproc(m,jpr+1) = idproc(ipr+1-m,jpr) (mod_xc_mp.h:2830)."""
     out = []
     for dx, dy in DIR_DXY:
+        if arctic_fold(g) and dy > 0:
+            out.append((g.ipr - 1 - (g.mproc - 1 + dx) % g.ipr) + g.ipr * (g.nproc - 1))
+            continue
         mp, np_ = g.mproc - 1 + dx, g.nproc - 1 + dy
         if not 0 <= mp < g.ipr:
             if not g.periodic_i:
@@ -48,11 +65,14 @@ def neighbors(g: TileGeom) -> List[int]:
 
 
 def halo_counts(g: TileGeom, nslab: int, mh: int = 5, nh: int = 5) -> List[int]:
-    """doubles per direction of one message of ``nslab`` slabs"""
+    """doubles per direction of one message of ``nslab`` slabs (fold messages: all ii columns to
+    the twin, mh+1 columns north-west and mh north-east, see csrc/tsadvc_launch.h)"""
     out = []
     for dx, dy in DIR_DXY:
         w = g.ii if dx == 0 else mh
         h = g.jj if dy == 0 else nh
+        if arctic_fold(g) and dy > 0 and dx < 0:
+            w = mh + 1
         out.append(w * h * nslab)
     return out
 
@@ -180,7 +200,7 @@ class XcExchange:
                     continue
                 # a periodic edge that wraps onto this tile: what leaves in the opposite
                 # direction is what arrives here
-                recv[d] = send[OPP[d]] if self.nbr[d] == self.rank else self.backend.alloc(c)
+                recv[d] = send[opp_dir(self.geom, d)] if self.nbr[d] == self.rank else self.backend.alloc(c)
             self._bufs[key] = (send, recv, self.ops(send, recv))
         return self._bufs[key]
 
@@ -193,8 +213,9 @@ class XcExchange:
             peer = self.nbr[d]
             if peer >= 0 and peer != self.rank:
                 ops.append(P2POp(dist.isend, send[d], self._global(peer), group=self.group, tag=d))
-        for d in range(8):
-            e = OPP[d]          # the peer sent this message in ITS direction d
+        # receives in the order of the SENDER's direction d; a top-row arctic tile may hear from the
+        # same d twice (d=3: from the tile below it and, folded, from its twin)
+        for d, e in sorted((opp_dir(self.geom, e), e) for e in range(8)):
             peer = self.nbr[e]
             if peer >= 0 and peer != self.rank:
                 ops.append(P2POp(dist.irecv, recv[e], self._global(peer), group=self.group, tag=d))
@@ -285,7 +306,7 @@ class XcExchange:
             recv: List = [None] * 8
             for d, c in enumerate(cnt):
                 if self.nbr[d] >= 0:
-                    recv[d] = send[OPP[d]] if self.nbr[d] == self.rank else self.backend.alloc(c)
+                    recv[d] = send[opp_dir(self.geom, d)] if self.nbr[d] == self.rank else self.backend.alloc(c)
             self._bufs[key] = (send, recv, self.ops(send, recv))
         send, recv, ops = self._bufs[key]
         cs = self.comm_stream
@@ -328,7 +349,7 @@ class XcExchange:
             recv: List = [None] * 8
             for d, c in enumerate(cnt):
                 if self.nbr[d] >= 0:
-                    recv[d] = send[OPP[d]] if self.nbr[d] == self.rank else self.backend.alloc(c)
+                    recv[d] = send[opp_dir(self.geom, d)] if self.nbr[d] == self.rank else self.backend.alloc(c)
             self._bufs[key] = (send, recv, self.ops(send, recv))
         send, recv, ops = self._bufs[key]
         cs = self.comm_stream

@@ -83,7 +83,7 @@ typedef struct hycom_tsadvc_dims {
   int32_t i0, j0;               /* offset of the tile in the global grid */
   int32_t itdm, jtdm;           /* global extents */
   int32_t nreg;                 /* mod_xc.F90:25-31: 0 closed, 1 periodic in i, 2 global grid
-                                   across the arctic (tripole fold, one tile only for now),
+                                   across the arctic (tripole fold of the top row),
                                    3 periodic in i and j (f-plane), 4 closed f-plane */
   int32_t ipr, jpr;             /* number of tiles in i and j */
   int32_t mproc, nproc;         /* 1-based tile coordinates */
@@ -189,7 +189,12 @@ enum {
   HYCOM_TSADVC_PART_FRAME = 2     /* the rest, after unpack; completes the step */
 };
 /* 0-based index (mproc-1 + ipr*(nproc-1)) of the neighbour tile per direction, -1 at a
- * closed edge; periodic edges wrap (possibly onto the tile itself) */
+ * closed edge; periodic edges wrap (possibly onto the tile itself).  nreg=2: the tiles of the
+ * top row face their twins across the arctic, idproc(m,jpr+1) = idproc(ipr+1-m,jpr)
+ * (mod_xc_mp.h:2830): N is the twin of the tile, NW / NE the twins of its western / eastern
+ * neighbour, and a message sent in one of those directions is received from the SAME direction
+ * (both twins look north).  Fold messages carry ii, mh+1 and mh columns of nh mirrored rows
+ * (mod_xc_mp.h:4263-4372; the u-grid mirror is shifted by one column, :4283-4331). */
 int hycom_tsadvc_halo_neighbors(const hycom_tsadvc_handle *h, int32_t nbr[8]);
 /* doubles per direction of one message (send and receive sizes are equal for the uniform
  * tilings of hycom-src_b200/geometry.py: tiles of one row share jj, of one column ii) */

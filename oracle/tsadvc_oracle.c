@@ -265,9 +265,22 @@ void orc_xctilr_type(const orc_tile *t, double *a, int l1, int ld_, int mh, int 
  * neighbour leaves vland (:4786-4787, :4914-4915). */
 void orc_world_xctilr(int ipr, int jpr, orc_tile *const *tiles,
                       double *const *a, int l1, int ld_, int mh, int nh) {
+  orc_world_xctilr_type(ipr, jpr, tiles, a, l1, ld_, mh, nh, 1); /* halo_ps */
+}
+
+/* The ARCTIC version (mod_xc_mp.h:4114-4662) differs for the tiles of the top row (nproc = jpr):
+ * their northern neighbour is the twin tile idproc(ipr+1-m,jpr) (:2830), which sends its rows
+ * below jj mirrored in i, with the sign flipped for vector fields unless the value is vland
+ * (:4263-4372).  On the u and q grids the mirror is shifted by one column (io = ii+2-i), so the
+ * first column arrives separately from tile mod(ipr+1-mproc,ipr)+1 (buffer aia, :4319-4331,
+ * :4419-4428, :4521-4532). */
+void orc_world_xctilr_type(int ipr, int jpr, orc_tile *const *tiles,
+                           double *const *a, int l1, int ld_, int mh, int nh, int itype) {
   const double vland = 0.0;
   const int nreg = tiles[0]->nreg;
   const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg > 2;
+  const int grid = itype % 10;
+  const double sarc = itype < 10 ? 1.0 : -1.0; /* :4211-4215 */
   /* phase 1: north/south */
   for (int n = 0; n < jpr; n++)
     for (int m = 0; m < ipr; m++) {
@@ -296,6 +309,22 @@ void orc_world_xctilr(int ipr, int jpr, orc_tile *const *tiles,
               const double *an = a[m + ipr * nn] +
                                  (size_t)orc_slab(tn) * (size_t)(k - 1);
               vn = an[(size_t)(i + nb - 1) + ldn * (size_t)(j + nb - 1)];
+            } else if (nreg == 2 && n == jpr - 1) { /* arctic */
+              /* what the twin packed for this i (the twin's own loop index is i as well: its
+               * ai(l,1) for index i holds a(io,jo) of the twin, :4263-4372) */
+              int mt = ipr - 1 - m, io, jo;
+              if (grid == 1 || grid == 4) io = ii + 1 - i; /* p,v: ii:1:-1   */
+              else io = ii + 2 - i;                        /* u,q: ii+1:2:-1 */
+              jo = (grid == 1 || grid == 3) ? jj - 1 - j : jj - j;
+              if (io == ii + 1) { /* aia: a(1,jo) of tile mod(ipr+1-mproc,ipr)+1 */
+                mt = (ipr - m) % ipr;
+                io = 1;
+              }
+              const orc_tile *tt = tiles[mt + ipr * n];
+              const size_t ldt = (size_t)(tt->idm + 2 * nb);
+              const double *at = a[mt + ipr * n] + (size_t)orc_slab(tt) * (size_t)(k - 1);
+              const double v = at[(size_t)(io + nb - 1) + ldt * (size_t)(jo + nb - 1)];
+              vn = (v != vland) ? sarc * v : vland;
             }
             ak[IX(i, 1 - j)] = vs;
             ak[IX(i, jj + j)] = vn;

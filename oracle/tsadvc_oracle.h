@@ -94,6 +94,9 @@ void orc_xctilr_type(const orc_tile *t, double *a, int l1, int ld, int mh, int n
  * address space: a[m + ipr*n] is the same field on tile (m,n), 0-based. */
 void orc_world_xctilr(int ipr, int jpr, orc_tile *const *tiles,
                       double *const *a, int l1, int ld, int mh, int nh);
+/* the same for a grid/field type (mod_xc.F90:41-44); nreg=2: the ARCTIC version of mod_xc_mp.h */
+void orc_world_xctilr_type(int ipr, int jpr, orc_tile *const *tiles,
+                           double *const *a, int l1, int ld, int mh, int nh, int itype);
 
 /* bigrid.F90:116-386; depth is a P-sized slab whose interior 1..ii,1..jj is set.
  * stage1: halo of depth must be current; builds ip and interior iu/iv/iq and

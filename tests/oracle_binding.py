@@ -153,6 +153,9 @@ class Oracle:
         lib.orc_world_xctilr.restype = None
         lib.orc_world_xctilr.argtypes = [C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp),
                                          C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.orc_world_xctilr_type.restype = None
+        lib.orc_world_xctilr_type.argtypes = [C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp),
+                                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         lib.orc_bigrid.argtypes = [_vp, _vp]
         lib.orc_bigrid_stage1.argtypes = [_vp, _vp]
         lib.orc_bigrid_stage2.argtypes = [_vp]
@@ -187,8 +190,8 @@ class Oracle:
     def tile(self, geom, ntracr=0):
         return OracleTile(self, geom, ntracr)
 
-    def world_xctilr(self, ipr, jpr, tiles, arrays, l1, ld, mh, nh):
+    def world_xctilr(self, ipr, jpr, tiles, arrays, l1, ld, mh, nh, itype=1):
         n = ipr * jpr
         T = (_vp * n)(*[t.t for t in tiles])
         A = (_vp * n)(*[a.ctypes.data_as(_vp) for a in arrays])
-        self.lib.orc_world_xctilr(ipr, jpr, T, A, l1, ld, mh, nh)
+        self.lib.orc_world_xctilr_type(ipr, jpr, T, A, l1, ld, mh, nh, itype)

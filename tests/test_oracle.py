@@ -7,6 +7,8 @@ import importlib
 import sys
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -183,6 +185,40 @@ def test_tiling_invariance_2x2(oracle):
             sea_t = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
             assert np.array_equal(np.where(sea_t, loc, 0), np.where(sea_t, glb, 0)), (name, g.mproc, g.nproc)
         ot.close()
+
+
+@pytest.mark.parametrize("ipr,jpr", [(2, 1), (2, 2), (4, 2), (1, 2)])
+@pytest.mark.parametrize("itype", [1, 13, 14, 2, 3])
+def test_arctic_world_xctilr_matches_single_tile(oracle, ipr, jpr, itype):
+    """the ARCTIC xctilr of mod_xc_mp.h over ipr x jpr tiles leaves the halo the single-tile version
+    of mod_xc_sm.h leaves on the global array (the two differ only in the sign of a folded zero of a
+    vector field: the tiled version keeps vland, :4270-4274)"""
+    itdm, jtdm, kk = 48, 36, 2
+    rng = np.random.default_rng(4)
+    g1 = pkg.partition(itdm, jtdm, kk, 1, 1, 2)[0]
+    nb = g1.nbdy
+    glob = np.full((kk, g1.nrows, g1.ncols), np.nan)
+    core = rng.standard_normal((kk, jtdm, itdm))
+    core[rng.random(core.shape) < 0.1] = 0.0            # vland inside the field
+    glob[:, nb:nb + jtdm, nb:nb + itdm] = core
+    o1 = oracle.tile(g1, 0)
+    oracle.lib.orc_xctilr_type(o1.t, glob.ctypes.data_as(C.c_void_p), 1, kk, 5, 5, itype)
+    tiles = pkg.partition(itdm, jtdm, kk, ipr, jpr, 2)
+    ots = [oracle.tile(g, 0) for g in tiles]
+    arrs = []
+    for g in tiles:
+        a = np.full((kk, g.nrows, g.ncols), np.nan)
+        a[:, nb:nb + g.jj, nb:nb + g.ii] = core[:, g.j0:g.j0 + g.jj, g.i0:g.i0 + g.ii]
+        arrs.append(a)
+    oracle.world_xctilr(ipr, jpr, ots, arrs, 1, kk, 5, 5, itype)
+    for g, a in zip(tiles, arrs):
+        win = (slice(None), slice(g.j0 + nb - 5, g.j0 + nb + g.jj + 5), slice(g.i0 + nb - 5, g.i0 + nb + g.ii + 5))
+        loc = a[:, nb - 5:nb + g.jj + 5, nb - 5:nb + g.ii + 5]
+        assert not np.isnan(loc).any()
+        assert np.array_equal(loc, glob[win]), (g.mproc, g.nproc)     # -0.0 == 0.0
+        assert np.isnan(a[:, 0]).all()                                   # sixth halo line untouched
+    for o in ots + [o1]:
+        o.close()
 
 
 def test_periodic_shift_invariance(oracle):

@@ -270,7 +270,7 @@ def _exchange_in_process(tss, m, n):
         nbrs.append(nbr)
         ts.synchronize()
     for t, ts in enumerate(tss):
-        recv = [sends[nbrs[t][d]][xc.OPP[d]] if nbrs[t][d] >= 0 else None for d in range(8)]
+        recv = [sends[nbrs[t][d]][xc.opp_dir(ts.cb.geom, d)] if nbrs[t][d] >= 0 else None for d in range(8)]
         xc.DeviceHaloBackend(ts).unpack(m, n, recv)
         ts.synchronize()
 
@@ -413,7 +413,7 @@ def test_diffusion_tiling_invariance_on_device(oracle, ipr, jpr, nreg, ntracr, s
         sends.append(send); nbrs.append(nbr)
         ts.synchronize()
     for t, ts in enumerate(tss):
-        recv = [sends[nbrs[t][d]][xc.OPP[d]] if nbrs[t][d] >= 0 else None for d in range(8)]
+        recv = [sends[nbrs[t][d]][xc.opp_dir(ts.cb.geom, d)] if nbrs[t][d] >= 0 else None for d in range(8)]
         xc.DeviceHaloBackend(ts).diff_unpack(n, recv)
         p = ts.cb.params()
         ts._ck(ts.lib.hycom_tsadvc_diffuse_device(ts.h, m, n, C.byref(p)))
@@ -541,7 +541,7 @@ def test_fct2c_tiling_invariance_on_device(oracle, ipr, jpr, nreg, ntracr, kdm):
                 sends.append(send)
                 ts.synchronize()
             for t, ts in enumerate(tss):
-                recv = [sends[nbrs[t][d]][xc.OPP[d]] if nbrs[t][d] >= 0 else None for d in range(8)]
+                recv = [sends[nbrs[t][d]][xc.opp_dir(ts.cb.geom, d)] if nbrs[t][d] >= 0 else None for d in range(8)]
                 bes[t].fct2c_unpack(m, n, b, recv)
                 ts.synchronize()
         stage(b, 2)
@@ -600,6 +600,101 @@ def test_arctic_device_halo_matches_xctilr(oracle):
         assert np.array_equal(dev[win], a3[win], equal_nan=True), name
     ts.close()
     ot.close()
+
+
+# nreg=2 on several tiles: the tiles of the top row exchange the fold with their twins
+# (mod_xc_mp.h:4114-4662)
+@pytest.mark.parametrize("ipr,jpr", [(2, 1), (2, 2), (4, 2), (1, 2)])
+def test_arctic_tiles_device_exchange_matches_xctilr(oracle, ipr, jpr):
+    """device pack/unpack of the folded exchange == the single-tile arctic xctilr on the global array,
+    per grid type: scalars (halo_ps), uflx (halo_uv), vflx (halo_vv)"""
+    m, n = 1, 2
+    cfg, sea, g1, cb1 = util.make_arctic_case(96, 60, 2, seed=3, m=m, n=n)
+    ot = util.oracle_tile_from_cb(oracle, cb1, sea)
+    nb = g1.nbdy
+    ref = {}
+    for name, itype in (("saln", 1), ("temp", 1), ("uflx", 13), ("vflx", 14)):
+        a = ot.f64(name)
+        a3 = a.reshape((-1,) + a.shape[-2:])
+        ot.lib.orc_xctilr_type(ot.t, a3.ctypes.data_as(C.c_void_p), 1, a3.shape[0], 5, 5, itype)
+        ref[name] = a.copy()
+    ot.close()
+    tss = []
+    for cb in util.make_arctic_tiles(cfg, sea, cb1, ipr, jpr, m, n):
+        ts = pkg.Tsadvc(cb)
+        ts.upload_state(m, n)
+        tss.append(ts)
+    _exchange_in_process(tss, m, n)
+    for ts in tss:
+        g = ts.cb.geom
+        loc = (slice(None), slice(nb - 5, nb + g.jj + 5), slice(nb - 5, nb + g.ii + 5))
+        glb = (slice(None), slice(g.j0 + nb - 5, g.j0 + nb + g.jj + 5), slice(g.i0 + nb - 5, g.i0 + nb + g.ii + 5))
+        for fld, name, slots in ((cabi.F_SALN, "saln", (1, 2)), (cabi.F_TEMP, "temp", (1, 2)),
+                                 (cabi.F_UFLX, "uflx", (1,)), (cabi.F_VFLX, "vflx", (1,))):
+            for slot in slots:
+                dev = ts.download(fld, slot)[loc]
+                r = ref[name][slot - 1] if ref[name].ndim == 4 else ref[name]
+                assert np.array_equal(dev, r[glb]), (name, slot, g.mproc, g.nproc)
+        ts.close()
+
+
+@pytest.mark.parametrize("itdm,jtdm,kdm,ipr,jpr,ntracr,advtyp,temdf2", [
+    (128, 70, 2, 2, 2, 0, 2, 0.0),     # FCT2 on 2x2 tiles, fold in the top row
+    (192, 64, 2, 4, 2, 1, 2, 0.0),     # 4x2 (the 8-GPU tiling): the shifted u-grid column comes from a third tile
+    (128, 70, 2, 2, 1, 0, 1, 0.0),     # MPDATA, 2x1: NW/NE fold onto the tile itself
+    (96, 80, 2, 1, 2, 0, 2, 0.0),      # 1x2: the top tile is its own twin
+    (128, 70, 2, 2, 2, 1, 2, 0.02),    # with the diffusion exchange (width 2) and the EOS tail
+])
+def test_arctic_tiling_invariance_on_device(oracle, itdm, jtdm, kdm, ipr, jpr, ntracr, advtyp, temdf2):
+    """tsadvc on N tiles of a global grid across the arctic == the oracle on the single global tile"""
+    m, n = 1, 2
+    xc = __import__("importlib").import_module("hycom-src_b200.xc")
+    extra = dict(advtyp=advtyp, nstep=3)
+    if temdf2 > 0.0:    # temp & saln diffused, th3d = sig(T,S) - thbase from the 17-term sigma-2 fit
+        extra.update(temdf2=temdf2, temdfc=1.0, sigver=6, thbase=34.0)
+    cfg, sea, g1, cb1 = util.make_arctic_case(itdm, jtdm, kdm, ntracr=ntracr, seed=29, m=m, n=n, **extra)
+    ref = util.run_oracle(oracle, cb1, sea, m, n)
+    tss = []
+    nb = g1.nbdy
+    for cb in util.make_arctic_tiles(cfg, sea, cb1, ipr, jpr, m, n, **extra):
+        ts = pkg.Tsadvc(cb)
+        ts.upload_state(m, n)
+        tss.append(ts)
+    _exchange_in_process(tss, m, n)
+    for ts in tss:
+        p = ts.cb.params()
+        xm, xx = ts.xmin.ctypes.data_as(C.c_void_p), ts.xmax.ctypes.data_as(C.c_void_p)
+        ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_INTERIOR, None, None))
+        ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_FRAME, xm, xx))
+        ts.synchronize()
+    if temdf2 > 0.0:
+        sends, nbrs = [], []
+        for ts in tss:
+            be = xc.DeviceHaloBackend(ts)
+            nbr = xc.neighbors(ts.cb.geom)
+            cnt = be.diff_counts(n)
+            send = [be.alloc(c) if nbr[d] >= 0 else None for d, c in enumerate(cnt)]
+            be.diff_pack(n, send)
+            sends.append(send); nbrs.append(nbr)
+            ts.synchronize()
+        for t, ts in enumerate(tss):
+            recv = [sends[nbrs[t][d]][xc.opp_dir(ts.cb.geom, d)] if nbrs[t][d] >= 0 else None for d in range(8)]
+            xc.DeviceHaloBackend(ts).diff_unpack(n, recv)
+            p = ts.cb.params()
+            ts._ck(ts.lib.hycom_tsadvc_diffuse_device(ts.h, m, n, C.byref(p)))
+            ts.synchronize()
+    for ts in tss:
+        g = ts.cb.geom
+        sea_t = ts.cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
+        glob = (slice(None), slice(nb + g.j0, nb + g.j0 + g.jj), slice(nb + g.i0, nb + g.i0 + g.ii))
+        pairs = [(cabi.F_TEMP, 0, ref["temp"][n - 1]), (cabi.F_SALN, 0, ref["saln"][n - 1])]
+        pairs += [(cabi.F_TRACER, q + 1, ref["tracer"][q, n - 1]) for q in range(ntracr)]
+        if temdf2 > 0.0:
+            pairs.append((cabi.F_TH3D, 0, ref["th3d"][n - 1]))
+        for fld, ktr, r in pairs:
+            dev = ts.download(fld, n, ktr=ktr)[:, nb:nb + g.jj, nb:nb + g.ii]
+            assert np.array_equal(dev[:, sea_t], r[glob][:, sea_t]), (g.mproc, g.nproc, fld)
+        ts.close()
 
 
 # ---------------------------------------------------------------------------------------

@@ -26,20 +26,30 @@ def _field(ig, jg, k, a):
     return 1000.0 * a + 100.0 * k + ig + 0.001 * jg
 
 
-def _expected(g, a, kk, mh=5, nh=5):
-    """what xctilr must leave in the tile (interior + halo of width 5; NaN elsewhere)"""
+def _expected(g, a, kk, mh=5, nh=5, itype=1):
+    """what xctilr must leave in the tile (interior + halo of width 5; NaN elsewhere).  nreg=2: rows
+    above jtdm image the tripole fold of the global array (mod_xc_sm.h:1215-1320 / mod_xc_mp.h:4263-
+    4372): mirrored in i (shifted by one column on the u grid), rows jtdm-1-j (p,u) or jtdm-j (v),
+    vector fields with the sign flipped"""
     nb = g.nbdy
     out = np.full((kk, g.nrows, g.ncols), np.nan)
+    grid = itype % 10
     for r in range(nb - nh, nb + g.jj + nh):
         for c in range(nb - mh, nb + g.ii + mh):
             ig, jg = g.i0 + c + 1 - nb, g.j0 + r + 1 - nb
+            sgn = 1.0
             if g.periodic_i:
                 ig = (ig - 1) % g.itdm + 1
             if g.periodic_j:
                 jg = (jg - 1) % g.jtdm + 1
+            if g.nreg == 2 and jg > g.jtdm:
+                j = jg - g.jtdm
+                ig = g.itdm - (ig - 1) % g.itdm if grid in (1, 4) else (g.itdm - (ig - 1)) % g.itdm + 1
+                jg = g.jtdm - 1 - j if grid in (1, 3) else g.jtdm - j
+                sgn = -1.0 if itype > 10 else 1.0
             inside = 1 <= ig <= g.itdm and 1 <= jg <= g.jtdm
             for k in range(kk):
-                out[k, r, c] = _field(ig, jg, k, a) if inside else 0.0
+                out[k, r, c] = sgn * _field(ig, jg, k, a) if inside else 0.0
     return out
 
 
@@ -59,13 +69,14 @@ def _worker(rank, world, port, itdm, jtdm, ipr, jpr, nreg, q):
                 jj_, ii_ = np.meshgrid(np.arange(1, g.jj + 1), np.arange(1, g.ii + 1), indexing="ij")
                 arr[k, nb:nb + g.jj, nb:nb + g.ii] = _field(g.i0 + ii_, g.j0 + jj_, k, a)
             arrays.append(arr)
-        be = np_halo.NumpyHaloBackend(g, arrays)
+        itypes = [1, 13, 14] if nreg == 2 else [1, 1, 1]   # halo_ps, halo_uv, halo_vv
+        be = np_halo.NumpyHaloBackend(g, arrays, itypes)
         ex = pkg.XcExchange(None, dist, backend=be)
         for _ in range(2):               # twice: buffers are reused
             ex.xctilr(1, 2)
         ok = True
         for a in range(narr):
-            exp = _expected(g, a, kk)
+            exp = _expected(g, a, kk, itype=itypes[a])
             live = ~np.isnan(exp)
             ok = ok and np.array_equal(arrays[a][live], exp[live])
             # the sixth halo line is not touched by a width-5 exchange
@@ -123,7 +134,8 @@ def _worker_staged(rank, world, port, itdm, jtdm, ipr, jpr, nreg, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,itdm,jtdm,ipr,jpr,nreg", [(2, 57, 41, 2, 1, 0), (2, 44, 36, 1, 2, 3), (4, 45, 38, 2, 2, 3)])
+@pytest.mark.parametrize("world,itdm,jtdm,ipr,jpr,nreg", [(2, 57, 41, 2, 1, 0), (2, 44, 36, 1, 2, 3), (4, 45, 38, 2, 2, 3),
+                                                          (4, 48, 38, 2, 2, 2)])
 def test_staged_exchanges_over_gloo(world, itdm, jtdm, ipr, jpr, nreg):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -145,6 +157,10 @@ CASES = [
     (2, 44, 36, 2, 1, 3),   # 2x1 doubly periodic: both E and W neighbour are the other rank
     (4, 45, 38, 2, 2, 3),   # 2x2 doubly periodic: every neighbour pair exchanges 4 messages
     (4, 61, 33, 4, 1, 0),   # 4x1 closed
+    (2, 44, 36, 2, 1, 2),   # arctic, 2x1: each tile's twin is the other rank, NW/NE fold onto itself
+    (4, 48, 38, 2, 2, 2),   # arctic, 2x2: fold in the top row, closed south
+    (4, 64, 30, 4, 1, 2),   # arctic, 4x1: twins 0-3 and 1-2, shifted u-grid column from a third tile
+    (2, 40, 36, 1, 2, 2),   # arctic, 1x2: the top tile is its own twin
 ]
 
 
@@ -178,4 +194,4 @@ def test_neighbour_tables():
     for t in tiles:
         cnt, nbr = xc.halo_counts(t, 7), xc.neighbors(t)
         for d in range(8):
-            assert cnt[d] == xc.halo_counts(tiles[nbr[d]], 7)[xc.OPP[d]]
+            assert cnt[d] == xc.halo_counts(tiles[nbr[d]], 7)[xc.opp_dir(t, d)]

@@ -133,6 +133,22 @@ def make_arctic_case(itdm, jtdm, kdm, ntracr=0, seed=1, m=1, n=2, **scalars):
     return cfg, sea, g, cb
 
 
+def make_arctic_tiles(cfg, sea, cb1, ipr, jpr, m=1, n=2, **scalars):
+    """the tiles of an arctic case: every tile is generated from the global function like any other
+    tiling; the arrays that must arrive with a valid halo (dp, oneta, metrics) are windows of the
+    single-tile arrays, whose halo make_arctic_case filled with the fold of their grid"""
+    g1 = cb1.geom
+    cbs = []
+    for g in pkg.partition(g1.itdm, g1.jtdm, g1.kdm, ipr, jpr, 2):
+        cb = syn.build_cb_arrays(cfg, g, sea, m, n, **scalars)
+        win = (slice(g.j0, g.j0 + g.nrows), slice(g.i0, g.i0 + g.ncols))
+        for name in ("dp", "oneta", "scp2", "scp2i", "scuy", "aspux", "scvx", "aspvy"):
+            src = getattr(cb1, name)
+            setattr(cb, name, np.ascontiguousarray(src[(Ellipsis,) + win]))
+        cbs.append(cb)
+    return cbs
+
+
 def add_asselin(cfg, sea, g, cb, m, n, sigver=6, seed=77):
     """operands of mod_asselin.F90 on top of a case: dpo both slots (a perturbed dp), pbot/pbavg so
     that oneta = 1 + O(1e-3), the saved t-1 fields o* (a perturbed copy of slot n), dp of both slots"""

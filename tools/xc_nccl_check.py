@@ -28,7 +28,12 @@ def main():
     cases = [(150, 150, 4, 0, 0, 2, {}), (301, 203, 3, 3, 1, 2, {}), (180, 120, 2, 1, 1, 1, {}),
              # temdf2 > 0: second exchange (width 2) + tsdff + EOS; btrmas: advem_fct2c with five exchanges
              (150, 150, 3, 0, 1, 2, {"diffusion": (6, 1.0)}), (301, 203, 2, 3, 0, 2, {"diffusion": (8, 0.5)}),
-             (150, 150, 10, 0, 1, 2, {"btrmas": True}), (301, 203, 2, 3, 0, 2, {"btrmas": True})]
+             (150, 150, 10, 0, 1, 2, {"btrmas": True}), (301, 203, 2, 3, 0, 2, {"btrmas": True}),
+             # nreg=2: the top row exchanges the tripole fold with its twin tiles (mod_xc_mp.h:4114-4662)
+             (192, 120, 3, 2, 1, 2, {"arctic": True}), (256, 96, 2, 2, 0, 1, {"arctic": True})]
+    only = os.environ.get("XC_CHECK_CASES", "")       # e.g. "arctic": run the cases carrying that key only
+    if only:
+        cases = [c for c in cases if only in c[6]]
     for (itdm, jtdm, kdm, nreg, ntracr, advtyp, extra) in cases:
         m, n = 1, 2
         scal = dict(advtyp=advtyp)
@@ -39,12 +44,17 @@ def main():
             cfg, sea, g1, cb1 = util.make_diffusion_case(itdm, jtdm, kdm, sigver, temdfc, nreg=nreg, ntracr=ntracr,
                                                          seed=9, **scal)
             scal.update(temdf2=cb1.temdf2, temdfc=temdfc, sigver=sigver, thbase=cb1.thbase)
+        elif "arctic" in extra:
+            cfg, sea, g1, cb1 = util.make_arctic_case(itdm, jtdm, kdm, ntracr=ntracr, seed=9, m=m, n=n, **scal)
         else:
             cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=9, m=m, n=n, **scal)
         orc = oracle_binding.Oracle(os.path.join(ROOT, "oracle", "_build", "liboracle.so"))
         ot = util.oracle_tile_from_cb(orc, cb1, sea)
         g = pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)[rank]
-        cb = syn.build_cb_arrays(cfg, g, sea, m, n, **scal)
+        if "arctic" in extra:   # dp, oneta and the metrics arrive with the fold in their halo
+            cb = util.make_arctic_tiles(cfg, sea, cb1, ipr, jpr, m, n, **scal)[rank]
+        else:
+            cb = syn.build_cb_arrays(cfg, g, sea, m, n, **scal)
         if "diffusion" in extra:   # this tile's window of the single-tile th3d/theta (both slots)
             nbd = g.nbdy
             win = (Ellipsis, slice(g.j0, g.j0 + g.nrows), slice(g.i0, g.i0 + g.ncols))
