@@ -12,6 +12,9 @@
 // definite; fldc is not used.  Land values of fld and dp are read as 0 where the stencil
 // touches them (the reference never reads them; any finite stand-in gives the same sea
 // results because every flux that multiplies them is coast-zeroed).
+// Every register ring has period 3 and the ring slots of the staged rows rotate at run time (loop
+// unrolled three times, march_tma_common.cuh kPeriod); SEA = 1 is the mask-free instantiation for
+// row segments whose staged window is sea throughout (tsadvc_abi.cu, march_segments).
 #pragma once
 #include "march_tma_common.cuh"
 
@@ -19,22 +22,24 @@ namespace tsadvc {
 
 template <int NC>
 struct MpdataT {
-  double TX1[2][NC], TY1[2][NC];            // [row&1]   A(row r) -> B(row r, next iteration)
-  double DFLX[2][NC], FLY[2][NC];           // [row&1]   low-order flux divergence pieces
-  double FDV[2][NC], FCO[2][NC];            // [row&1]   flxdiv, fco of rows r-1, r-2
+  // all rings are indexed by row mod 3; the two-row ones die one row earlier
+  double TX1[3][NC], TY1[3][NC];            // A(row r) -> B(row r, next iteration)
+  double DFLX[3][NC], FLY[3][NC];           // low-order flux divergence pieces
+  double FDV[3][NC], FCO[3][NC];            // flxdiv, fco of rows r-1, r-2
   double FCN[3][NC];                        // [row%3]   rows r-1, r-2, r-3
   double LO[3][NC], MX[3][NC], MN[3][NC];   // [row%3]   fldlo, fmx, fmn
-  double FLX2[2][NC], FLX2E[2][NC], FLY2[2][NC];   // [row&1]  M3 fluxes (own face, east face)
-  double RP[2][NC], RM[2][NC];              // [row&1]
-  double DFLX3[2][NC], FLY3[2][NC];         // [row&1]   limited fluxes
+  double FLX2[3][NC], FLX2E[3][NC], FLY2[3][NC];   // M3 fluxes (own face, east face)
+  double RP[3][NC], RM[3][NC];
+  double DFLX3[3][NC], FLY3[3][NC];         // limited fluxes
   unsigned m1, m2, m3;
 };
 
-template <int NC>
+template <int NC, int SEA = 0>
 struct MpdataScheme {
   typedef MpdataT<NC> State;
   static constexpr bool kNeedC = false;
-  static constexpr int kPeriod = 6;
+  static constexpr int kPeriod = 3;
+  static constexpr bool ALLSEA = (SEA != 0);
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll
@@ -42,7 +47,7 @@ struct MpdataScheme {
 #pragma unroll
       for (int q = 0; q < 3; ++q) { s.FCN[q][c] = 0.0; s.LO[q][c] = 0.0; s.MX[q][c] = 0.0; s.MN[q][c] = 0.0; }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 3; ++q) {
         s.TX1[q][c] = 0.0; s.TY1[q][c] = 0.0; s.DFLX[q][c] = 0.0; s.FLY[q][c] = 0.0;
         s.FDV[q][c] = 0.0; s.FCO[q][c] = 0.0; s.FLX2[q][c] = 0.0; s.FLX2E[q][c] = 0.0;
         s.FLY2[q][c] = 0.0; s.RP[q][c] = 0.0; s.RM[q][c] = 0.0; s.DFLX3[q][c] = 0.0; s.FLY3[q][c] = 0.0;
@@ -53,19 +58,19 @@ struct MpdataScheme {
 
   // fld / dp with land cells read as zero
   template <int ARR>
-  static __device__ __forceinline__ void ld_sea(const RingPtr& p, int slot, unsigned m, double (&x)[NC]) {
+  static __device__ __forceinline__ void ld_sea(const RingPtr& p, Off slot, unsigned m, double (&x)[NC]) {
     ld_own<NC, ARR>(p, slot, x);
+    if (ALLSEA) return;
 #pragma unroll
     for (int c = 0; c < NC; ++c) x[c] = (mk(m, c) & M_IP) ? x[c] : 0.0;
   }
 
   template <int PH, bool SAFE>
   static __device__ __forceinline__ void step(State& s, const TmaCtx& x, const RingPtr& p, const int r,
-                                              bool& bad) {
+                                              const SlotOff& so, bool& bad) {
     typedef Ring<NC> R;
-    constexpr int p2 = PH & 1, q2 = p2 ^ 1;                           // rows r (r-2), r-1 (r-3)
     constexpr int a3 = PH % 3, b3 = (PH + 2) % 3, c3 = (PH + 1) % 3;  // rows r (r-3), r-1, r-2
-    constexpr int s0 = PH % 6, s1 = (PH + 5) % 6, s2 = (PH + 4) % 6, s3 = (PH + 3) % 6;
+    const Off s0 = so.s0, s1 = so.s1, s2 = so.s2, s3 = so.s3;
     const double onemu = 9806.e-12;  // :236
     const double dt2 = x.dt2;
     const double posdef = x.posdef;
@@ -83,21 +88,21 @@ struct MpdataScheme {
         // west neighbour of the first own cell, zero if land (its ip is this cell's M_PW)
         double fw[NC];
         ld_west<NC, R::F>(p, s0, F0, fw);
-        FW[0] = (mk(m0, 0) & M_PW) ? fw[0] : 0.0;
+        FW[0] = (ALLSEA || (mk(m0, 0) & M_PW)) ? fw[0] : 0.0;
         if (NC == 2) FW[NC - 1] = F0[0];
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const unsigned mc = mk(m0, c);
         const double F = F0[c], U = U0[c], V = V0[c];
-        s.TX1[p2][c] = .5 * fabs(U) * (F - FW[c]);                 // :254
-        s.TY1[p2][c] = .5 * fabs(V) * (F - F1[c]);                 // :262
+        s.TX1[a3][c] = .5 * fabs(U) * (F - FW[c]);                 // :254
+        s.TY1[a3][c] = .5 * fabs(V) * (F - F1[c]);                 // :262
         const double qx = (U >= 0.0) ? FW[c] : F;                  // :255-259
         const double qy = (V >= 0.0) ? F1[c] : F;                  // :263-267
-        flx[c] = (mc & M_IU) ? U * (qx + posdef) : 0.0;
-        s.FLY[p2][c] = (mc & M_IV) ? V * (qy + posdef) : 0.0;
+        flx[c] = (ALLSEA || (mc & M_IU)) ? U * (qx + posdef) : 0.0;
+        s.FLY[a3][c] = (ALLSEA || (mc & M_IV)) ? V * (qy + posdef) : 0.0;
       }
-      ediff<NC>(flx, s.DFLX[p2]);
+      ediff<NC>(flx, s.DFLX[a3]);
     }
 
     // ---- stage B: row r-1
@@ -123,17 +128,24 @@ struct MpdataScheme {
         const double Fc = F1[c];
         // 5-point sea-only extrema of fld (:272-281), then + posdef
         double mx, mn;
-        maxmin_first(mx, mn, Fc, Fc, Fw[c], Fw[c], m1, M_PW << (8 * c));
-        maxmin_if(mx, mn, Fe[c], Fe[c], m1, M_PE << (8 * c));
-        maxmin_if(mx, mn, F2[c], F2[c], m1, M_PS << (8 * c));
-        maxmin_if(mx, mn, F0[c], F0[c], m1, M_PN << (8 * c));
+        if (ALLSEA) {
+          mx = fmax2(Fw[c], Fc);    mn = fmin2(Fw[c], Fc);
+          mx = fmax2(Fe[c], mx);    mn = fmin2(Fe[c], mn);
+          mx = fmax2(F2[c], mx);    mn = fmin2(F2[c], mn);
+          mx = fmax2(F0[c], mx);    mn = fmin2(F0[c], mn);
+        } else {
+          maxmin_first(mx, mn, Fc, Fc, Fw[c], Fw[c], m1, M_PW << (8 * c));
+          maxmin_if(mx, mn, Fe[c], Fe[c], m1, M_PE << (8 * c));
+          maxmin_if(mx, mn, F2[c], F2[c], m1, M_PS << (8 * c));
+          maxmin_if(mx, mn, F0[c], F0[c], m1, M_PN << (8 * c));
+        }
         const double MX = mx + posdef, MN = mn + posdef;
         // tsadvc prolog :1934-1938
         const double fdp = ((UE[c] - U1[c]) + (V0[c] - V1[c])) * dt2 * SCI1[c];
         FCO[c] = fmax2(D1[c] + fdp, 0.0);
         FCN[c] = fmax2(D1[c], 0.0);
         // M2 :346-354
-        FDV[c] = ((s.DFLX[q2][c]) + (s.FLY[p2][c] - s.FLY[q2][c])) * dt2 * SCI1[c];
+        FDV[c] = ((s.DFLX[b3][c]) + (s.FLY[a3][c] - s.FLY[b3][c])) * dt2 * SCI1[c];
         const double q = (Fc + posdef) * (FCO[c] + onemu) - FDV[c];
         const double b = FCN[c] + onemu;
         const double lo = div_flag<SAFE>(q, b, SAFE ? 0.0 : rcp_nr(b), bad);
@@ -152,27 +164,27 @@ struct MpdataScheme {
         const unsigned mc = mk(m1, c);
         const double ax = U1[c] * (FDV[c] + FDVW[c]);
         const double bx = ((FCO[c] + FCOW[c]) + (FCN[c] + FCNW[c])) + onemu;
-        const double ay = V1[c] * (FDV[c] + s.FDV[p2][c]);
-        const double by = ((FCO[c] + s.FCO[p2][c]) + (FCN[c] + s.FCN[c3][c])) + onemu;
-        const double fx = s.TX1[q2][c] - div_flag<SAFE>(ax, bx, SAFE ? 0.0 : rcp_nr(bx), bad);
-        const double fy = s.TY1[q2][c] - div_flag<SAFE>(ay, by, SAFE ? 0.0 : rcp_nr(by), bad);
-        flx2[c] = (mc & M_IU) ? fx : 0.0;
-        s.FLY2[q2][c] = (mc & M_IV) ? fy : 0.0;
+        const double ay = V1[c] * (FDV[c] + s.FDV[c3][c]);
+        const double by = ((FCO[c] + s.FCO[c3][c]) + (FCN[c] + s.FCN[c3][c])) + onemu;
+        const double fx = s.TX1[b3][c] - div_flag<SAFE>(ax, bx, SAFE ? 0.0 : rcp_nr(bx), bad);
+        const double fy = s.TY1[b3][c] - div_flag<SAFE>(ay, by, SAFE ? 0.0 : rcp_nr(by), bad);
+        flx2[c] = (ALLSEA || (mc & M_IU)) ? fx : 0.0;
+        s.FLY2[b3][c] = (ALLSEA || (mc & M_IV)) ? fy : 0.0;
       }
 #pragma unroll
-      for (int c = 0; c < NC; ++c) { s.FLX2[q2][c] = flx2[c]; s.FDV[q2][c] = FDV[c]; s.FCO[q2][c] = FCO[c]; }
-      east_of<NC>(flx2, s.FLX2E[q2]);
+      for (int c = 0; c < NC; ++c) { s.FLX2[b3][c] = flx2[c]; s.FDV[b3][c] = FDV[c]; s.FCO[b3][c] = FCO[c]; }
+      east_of<NC>(flx2, s.FLX2E[b3]);
     }
 
-    // ---- stage C: row r-2 (M4, M5).  FLX2/FLY2 of row r-2 sit in ring slot p2, of row r-1 in q2
+    // ---- stage C: row r-2 (M4, M5).  FLX2/FLY2 of row r-2 sit in ring slot c3, of row r-1 in b3
     {
       const unsigned m2 = s.m2;
       double SC2[NC];
       ld_own<NC, R::SC>(p, s2, SC2);
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const double fxc = s.FLX2[p2][c], fxe = s.FLX2E[p2][c];
-        const double fyc = s.FLY2[p2][c], fyn = s.FLY2[q2][c];
+        const double fxc = s.FLX2[c3][c], fxe = s.FLX2E[c3][c];
+        const double fyc = s.FLY2[c3][c], fyn = s.FLY2[b3][c];
         const double flxdp = fmin2(0.0, fxe) - fmax2(0.0, fxc);     // :412-415
         const double flxdn = fmax2(0.0, fxe) - fmin2(0.0, fxc);
         const double flydp = fmin2(0.0, fyn) - fmax2(0.0, fyc);
@@ -180,25 +192,25 @@ struct MpdataScheme {
         const double w = s.FCN[c3][c] * SC2[c];
         const double ap = (s.MX[c3][c] - s.LO[c3][c]) * w, bp = (onemu - (flxdp + flydp)) * dt2;   // :416-417
         const double am = (s.LO[c3][c] - s.MN[c3][c]) * w, bm = (onemu + (flxdn + flydn)) * dt2;   // :418-419
-        s.RP[p2][c] = div_flag<SAFE>(ap, bp, SAFE ? 0.0 : rcp_nr(bp), bad);
-        s.RM[p2][c] = div_flag<SAFE>(am, bm, SAFE ? 0.0 : rcp_nr(bm), bad);
+        s.RP[c3][c] = div_flag<SAFE>(ap, bp, SAFE ? 0.0 : rcp_nr(bp), bad);
+        s.RM[c3][c] = div_flag<SAFE>(am, bm, SAFE ? 0.0 : rcp_nr(bm), bad);
       }
       double RPW[NC], RMW[NC], flx3[NC];
-      west_of<NC>(s.RP[p2], RPW);
-      west_of<NC>(s.RM[p2], RMW);
+      west_of<NC>(s.RP[c3], RPW);
+      west_of<NC>(s.RM[c3], RMW);
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const unsigned mc = mk(m2, c);
-        const double fxc = s.FLX2[p2][c], fyc = s.FLY2[p2][c];
-        const double RP = s.RP[p2][c], RM = s.RM[p2][c];
+        const double fxc = s.FLX2[c3][c], fyc = s.FLY2[c3][c];
+        const double RP = s.RP[c3][c], RM = s.RM[c3][c];
         const double x3 = fmax2(0.0, fxc) * fmin2(fmin2(1.0, RP), RMW[c]) +          // :439-441
                           fmin2(0.0, fxc) * fmin2(fmin2(1.0, RPW[c]), RM);
-        const double y3 = fmax2(0.0, fyc) * fmin2(fmin2(1.0, RP), s.RM[q2][c]) +     // :443-445
-                          fmin2(0.0, fyc) * fmin2(fmin2(1.0, s.RP[q2][c]), RM);
-        flx3[c] = (mc & M_IU) ? x3 : 0.0;
-        s.FLY3[p2][c] = (mc & M_IV) ? y3 : 0.0;
+        const double y3 = fmax2(0.0, fyc) * fmin2(fmin2(1.0, RP), s.RM[a3][c]) +     // :443-445
+                          fmin2(0.0, fyc) * fmin2(fmin2(1.0, s.RP[a3][c]), RM);
+        flx3[c] = (ALLSEA || (mc & M_IU)) ? x3 : 0.0;
+        s.FLY3[c3][c] = (ALLSEA || (mc & M_IV)) ? y3 : 0.0;
       }
-      ediff<NC>(flx3, s.DFLX3[p2]);
+      ediff<NC>(flx3, s.DFLX3[c3]);
     }
 
     // ---- stage E: row r-3, M6 (:475-480) and store
@@ -209,7 +221,7 @@ struct MpdataScheme {
       ld_own<NC, R::F>(p, s3, OLD3);
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const double flxdiv = ((s.DFLX3[q2][c]) + (s.FLY3[p2][c] - s.FLY3[q2][c])) * dt2 * SCI3[c];
+        const double flxdiv = ((s.DFLX3[a3][c]) + (s.FLY3[c3][c] - s.FLY3[a3][c])) * dt2 * SCI3[c];
         const double b = s.FCN[a3][c] + onemu;
         const double d = div_flag<SAFE>(flxdiv, b, SAFE ? 0.0 : rcp_nr(b), bad);
         const double f = fmax2(s.MN[a3][c], fmin2(s.MX[a3][c], s.LO[a3][c] - d));
@@ -220,7 +232,8 @@ struct MpdataScheme {
         Vec<NC> old;
 #pragma unroll
         for (int c = 0; c < NC; ++c) old.v[c] = OLD3[c];
-        store_vec<NC>(x.out, (long)r3 * x.pitch + col, x.lane, s.m3, old, nv);
+        store_vec<NC>(x.out, (long)r3 * x.pitch + col, x.lane, ALLSEA ? ((NC == 2) ? 0xffffu : 0xffu) : s.m3, old,
+                      nv);
       }
     }
     s.m3 = s.m2; s.m2 = s.m1; s.m1 = m0;

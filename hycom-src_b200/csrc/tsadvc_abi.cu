@@ -590,7 +590,7 @@ int neighbour(const hycom_tsadvc_dims& d, int dir) {
   return mp + d.ipr * np;
 }
 
-// Row segments of an FCT2 launch.  Every (strip, row) of the rectangles of P is assigned to a run of
+// Row segments of an FCT2 or MPDATA launch.  Every (strip, row) of the rectangles of P is assigned to a run of
 // rows: runs whose staged window (32*nc columns, rows j0-3 .. j1+2) holds nothing but mask bytes 0xff
 // (sea, interior, sea on all four sides) are marched by the mask-free instantiation of the kernel, the
 // rest by the general one.  The marching loop works in rounds of six rows, so the all-sea runs are cut
@@ -770,10 +770,10 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     else { CU(h, cudaEventCreate(&ev.first)); CU(h, cudaEventCreate(&ev.second)); }
     CU(h, cudaEventRecord(ev.first, lst));
   }
-  // FCT2: the all-sea row segments go to the mask-free instantiation, the rest to the general one
-  // (HYCOM_TSADVC_SPLIT=0: one general launch over the regular chunks)
+  // FCT2, MPDATA: the all-sea row segments go to the mask-free instantiation, the rest to the general
+  // one (HYCOM_TSADVC_SPLIT=0: one general launch over the regular chunks)
   const char* cs = getenv("HYCOM_TSADVC_SPLIT");
-  if (aadv == 2 && !p.btrmas && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
+  if ((aadv == 2 || aadv == 1) && !p.btrmas && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
     const hycom_tsadvc_handle::SegLists* L = nullptr;
     if ((rc = march_segments(h, P, part, chunk_rows, &L))) return rc;
     rc = 0;
