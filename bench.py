@@ -273,11 +273,15 @@ def run_b200(args):
     cells = idm * jdm * kdm
     value = cells / (ms_step * 1e-3)
 
-    # roofline of the dominant kernel (k_tsadvc_march): algorithmic bytes of this rank's tile
+    # roofline of the dominant kernel (k_tsadvc_march_tma; FCT2 and MPDATA run it as two launches per
+    # call, the mask-free instantiation over the all-sea row segments and the general one over the
+    # rest - timed together, events around the pair): algorithmic bytes of this rank's tile
     peak, peak_src = _peaks()
     alg = alg_bytes_per_call(g.ii, g.jj, kdm, args.advtyp, args.ntracr)
     achieved = alg / (march_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_tsadvc_march", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_tsadvc_march_tma (general + all-sea launch of one call)" if
+                args.advtyp in (1, 2) and os.environ.get("HYCOM_TSADVC_SPLIT", "1") != "0" else "k_tsadvc_march_tma",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "alg_bytes_per_launch": alg, "kernel_ms": march_avg, "peak_source": peak_src,
                 "kernel_share_of_step": march_avg / ms_step}
