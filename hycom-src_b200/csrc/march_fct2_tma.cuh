@@ -54,6 +54,7 @@ struct Fct2Scheme {
   typedef Fct2T<NC> State;
   static constexpr bool kNeedC = true;
   static constexpr int kPeriod = 3;
+  static constexpr bool kNeedM = (SEA == 0);   // the mask plane is staged for the general body only
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll
@@ -186,10 +187,13 @@ struct Fct2Scheme {
       // 5-point sea-only extrema of fld (:709-716)
       double mx, mn;
       if (ALLSEA) {
-        mx = fmax2(Fw[c], Fc);    mn = fmin2(Fw[c], Fc);
-        mx = fmax2(Fe[c], mx);    mn = fmin2(Fe[c], mn);
-        mx = fmax2(F2[c], mx);    mn = fmin2(F2[c], mn);
-        mx = fmax2(F0[c], mx);    mn = fmin2(F0[c], mn);
+        // max and min of the same pair share the compare (max/min are exact: any order gives the
+        // reference's value; only the sign of a zero among equal zeros may differ)
+        const bool gwe = Fw[c] > Fe[c], gsn = F2[c] > F0[c];
+        const double xwe = gwe ? Fw[c] : Fe[c], nwe = gwe ? Fe[c] : Fw[c];
+        const double xsn = gsn ? F2[c] : F0[c], nsn = gsn ? F0[c] : F2[c];
+        mx = fmax2(xwe, Fc);      mn = fmin2(nwe, Fc);
+        mx = fmax2(xsn, mx);      mn = fmin2(nsn, mn);
       } else {
         maxmin_first(mx, mn, Fc, Fc, Fw[c], Fw[c], m1, M_PW << (8 * c));
         maxmin_if(mx, mn, Fe[c], Fe[c], m1, M_PE << (8 * c));

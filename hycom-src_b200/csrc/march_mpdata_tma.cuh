@@ -39,6 +39,7 @@ struct MpdataScheme {
   typedef MpdataT<NC> State;
   static constexpr bool kNeedC = false;
   static constexpr int kPeriod = 3;
+  static constexpr bool kNeedM = (SEA == 0);   // the mask plane is staged for the general body only
   static constexpr bool ALLSEA = (SEA != 0);
 
   static __device__ __forceinline__ void init(State& s) {
@@ -128,11 +129,12 @@ struct MpdataScheme {
         const double Fc = F1[c];
         // 5-point sea-only extrema of fld (:272-281), then + posdef
         double mx, mn;
-        if (ALLSEA) {
-          mx = fmax2(Fw[c], Fc);    mn = fmin2(Fw[c], Fc);
-          mx = fmax2(Fe[c], mx);    mn = fmin2(Fe[c], mn);
-          mx = fmax2(F2[c], mx);    mn = fmin2(F2[c], mn);
-          mx = fmax2(F0[c], mx);    mn = fmin2(F0[c], mn);
+        if (ALLSEA) {   // max and min of the same pair share the compare
+          const bool gwe = Fw[c] > Fe[c], gsn = F2[c] > F0[c];
+          const double xwe = gwe ? Fw[c] : Fe[c], nwe = gwe ? Fe[c] : Fw[c];
+          const double xsn = gsn ? F2[c] : F0[c], nsn = gsn ? F0[c] : F2[c];
+          mx = fmax2(xwe, Fc);      mn = fmin2(nwe, Fc);
+          mx = fmax2(xsn, mx);      mn = fmin2(nsn, mn);
         } else {
           maxmin_first(mx, mn, Fc, Fc, Fw[c], Fw[c], m1, M_PW << (8 * c));
           maxmin_if(mx, mn, Fe[c], Fe[c], m1, M_PE << (8 * c));

@@ -17,6 +17,7 @@ struct PcmScheme {
   typedef PcmT<NC> State;
   static constexpr bool kNeedC = false;
   static constexpr int kPeriod = 6;
+  static constexpr bool kNeedM = true;
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll

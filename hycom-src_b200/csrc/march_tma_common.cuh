@@ -96,13 +96,13 @@ struct TmaCtx {
 };
 
 // request row r of every staged array into slot `slot` (one lane)
-template <int NC, bool NEED_C>
+template <int NC, bool NEED_C, bool NEED_M = true>
 __device__ __forceinline__ void issue_row(const TmaCtx& x, int r, int slot) {
   typedef Ring<NC> R;
   const uint32_t bar = x.bar_s + 8u * slot;
   const uint32_t dst = x.ring_s + (uint32_t)(slot * R::SLOT);
   const long off = (long)max(0, min(r, x.nrows - 1)) * x.pitch;
-  mbar_expect_tx(bar, NEED_C ? R::TX : R::TX - R::RB);
+  mbar_expect_tx(bar, R::TX - (NEED_C ? 0 : R::RB) - (NEED_M ? 0 : R::RB));
   bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
   if (NEED_C) bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
   bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
@@ -110,7 +110,7 @@ __device__ __forceinline__ void issue_row(const TmaCtx& x, int r, int slot) {
   bulk_g2s(dst + R::D * R::RB, x.dp + off, R::RB, bar);
   bulk_g2s(dst + R::SCI * R::RB, x.sci + off, R::RB, bar);
   bulk_g2s(dst + R::SC * R::RB, x.sc + off, R::RB, bar);
-  bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);
+  if (NEED_M) bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);   // the mask-free bodies never read it
 }
 
 // per-lane views of the ring: own columns, west neighbour of the first own column, east
@@ -243,9 +243,9 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     __syncwarp();
   }
   if (elect_one()) {
-    issue_row<NC, S::kNeedC>(x, r0, 0);
-    issue_row<NC, S::kNeedC>(x, r0 + 1, 1);
-    issue_row<NC, S::kNeedC>(x, r0 + 2, 2);
+    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0, 0);
+    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 1, 1);
+    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 2, 2);
   }
   if constexpr (S::kPeriod == 3) {
     int slot = 0;                        // slot of row r; rows r-1..r-3 sit in slot-1..slot-3 (mod 6)
@@ -258,7 +258,7 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     __syncwarp();                                                                         \
     const int slot3 = slot >= 3 ? slot - 3 : slot + 3;   /* row r-3: free now */           \
     if (t + (PH) + 3 < niter && elect_one())                                              \
-      issue_row<NC, S::kNeedC>(x, r0 + t + (PH) + 3, slot3);                              \
+      issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + t + (PH) + 3, slot3);                              \
     so.s3 = so.s2; so.s2 = so.s1; so.s1 = so.s0;                                          \
     slot = slot == 5 ? 0 : slot + 1;                                                      \
     par ^= (slot == 0) ? 1u : 0u;                                                         \
@@ -276,7 +276,7 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     /* the slot of row r-3 is free now: request row r+3 into it */                        \
     __syncwarp();                                                                         \
     if (t + (PH) + 3 < niter && elect_one())                                              \
-      issue_row<NC, S::kNeedC>(x, r0 + t + (PH) + 3, ((PH) + 3) % 6);                     \
+      issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + t + (PH) + 3, ((PH) + 3) % 6);                     \
   }
   for (int t = 0; t < niter; t += 6) {
     TSADVC_PHASE(0) TSADVC_PHASE(1) TSADVC_PHASE(2) TSADVC_PHASE(3) TSADVC_PHASE(4) TSADVC_PHASE(5)
