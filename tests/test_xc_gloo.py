@@ -189,6 +189,20 @@ def test_neighbour_tables():
     assert xc.neighbors(t) == [4, 6, 1, -1, 0, 2, -1, -1]
     tiles = pkg.partition(100, 80, 1, 4, 2, 1)   # periodic in i
     assert xc.neighbors(tiles[0]) == [3, 1, -1, 4, -1, -1, 7, 5]
+    # arctic: the top row faces its twins (N = twin, NW/NE = twins of the W/E neighbours), the fold
+    # directions pair with themselves, the bottom row is closed to the south
+    tiles = pkg.partition(96, 60, 1, 4, 2, 2)
+    assert xc.neighbors(tiles[4]) == [7, 5, 0, 7, 3, 1, 4, 6]
+    assert xc.neighbors(tiles[5]) == [4, 6, 1, 6, 0, 2, 7, 5]
+    assert xc.neighbors(tiles[1]) == [0, 2, -1, 5, -1, -1, 4, 6]
+    assert [xc.opp_dir(tiles[4], d) for d in range(8)] == [1, 0, 3, 3, 7, 6, 6, 7]
+    assert [xc.opp_dir(tiles[1], d) for d in range(8)] == list(xc.OPP)
+    for t in tiles:
+        cnt, nbr = xc.halo_counts(t, 3), xc.neighbors(t)
+        for d in range(8):
+            if nbr[d] >= 0:
+                assert cnt[d] == xc.halo_counts(tiles[nbr[d]], 3)[xc.opp_dir(t, d)]
+                assert xc.neighbors(tiles[nbr[d]])[xc.opp_dir(t, d)] == t.mproc - 1 + t.ipr * (t.nproc - 1)
     # message sizes: send size of a tile == receive size of its neighbour
     tiles = pkg.partition(103, 81, 1, 4, 2, 3)
     for t in tiles:
