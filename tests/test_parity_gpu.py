@@ -188,6 +188,27 @@ def test_constant_field_preserved_on_device():
     assert (got["saln"][1][:, msk] == 35.25).all()
 
 
+@pytest.mark.parametrize("advtyp", [2, 1])
+def test_all_sea_segments_equal_general_launch(oracle, advtyp, monkeypatch):
+    """FCT2 / MPDATA as the launch pair (all-sea row segments on the mask-free instantiation + the rest)
+    == the single general launch == the oracle, bit for bit, on a grid with wide open water"""
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(420, 360, 2, nreg=0, ntracr=1, seed=12, m=m, n=n, advtyp=advtyp)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    out = {}
+    for split in ("1", "0"):
+        monkeypatch.setenv("HYCOM_TSADVC_SPLIT", split)
+        cbx = syn.build_cb_arrays(cfg, g, sea, m, n, advtyp=advtyp)
+        got, _, launches = _run_host_path(cbx, m, n)
+        out[split] = (got, launches)
+        _compare(cbx, g, got, ref, n, ["saln", "temp"])
+        _compare(cbx, g, {"t": got["tracer"][0]}, {"t": ref["tracer"][0]}, n, ["t"])
+    # the pair really ran: one marching launch more per call of run_march than the general launch alone
+    assert out["1"][1] > out["0"][1], (out["1"][1], out["0"][1])
+    for name in ("temp", "saln"):
+        assert np.array_equal(out["1"][0][name], out["0"][0][name], equal_nan=True)
+
+
 @pytest.mark.parametrize("advtyp,ntracr", [(2, 0), (1, 1)])
 def test_full_size_glb_layers_match_oracle(oracle, advtyp, ntracr):
     """BASELINE configs[1]/[2] at the full GLBb0.08 horizontal size (4500x3298) on the
