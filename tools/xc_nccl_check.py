@@ -24,6 +24,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ipr, jpr = {2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
+    if os.environ.get("XC_CHECK_TILES"):          # e.g. "4x1": another tiling of the same world size
+        ipr, jpr = (int(v) for v in os.environ["XC_CHECK_TILES"].split("x"))
+        assert ipr * jpr == world
     ok_all = True
     cases = [(150, 150, 4, 0, 0, 2, {}), (301, 203, 3, 3, 1, 2, {}), (180, 120, 2, 1, 1, 1, {}),
              # temdf2 > 0: second exchange (width 2) + tsdff + EOS; btrmas: advem_fct2c with five exchanges
