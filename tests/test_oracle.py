@@ -221,6 +221,58 @@ def test_arctic_world_xctilr_matches_single_tile(oracle, ipr, jpr, itype):
         o.close()
 
 
+@pytest.mark.parametrize("ipr,jpr,nreg", [(4, 2, 2), (2, 2, 2), (2, 1, 2), (1, 2, 2), (2, 2, 3), (4, 1, 0)])
+def test_exchange_schedule_matches_oracle_world_xctilr(oracle, ipr, jpr, nreg):
+    """the product's exchange schedule (xc.neighbors / opp_dir / halo_counts: who sends what to whom,
+    which message a tile reads for which direction) with the numpy pack/unpack of tests/np_halo.py,
+    run between the tiles of one process, fills every halo exactly like the C oracle's xctilr over
+    tiles (mod_xc_mp.h), per grid type: scalar p-grid, u-grid vector, v-grid vector"""
+    import np_halo
+    xc = importlib.import_module("hycom-src_b200.xc")
+    itdm, jtdm, kk = 64, 46, 2
+    rng = np.random.default_rng(7)
+    tiles = pkg.partition(itdm, jtdm, kk, ipr, jpr, nreg)
+    nb = tiles[0].nbdy
+    itypes = [1, 13, 14]
+    cores = [rng.standard_normal((kk, jtdm, itdm)) for _ in itypes]
+    for c in cores:
+        c[rng.random(c.shape) < 0.1] = 0.0
+
+    def tile_arrays():
+        out = []
+        for g in tiles:
+            arrs = []
+            for c in cores:
+                a = np.full((kk, g.nrows, g.ncols), np.nan)
+                a[:, nb:nb + g.jj, nb:nb + g.ii] = c[:, g.j0:g.j0 + g.jj, g.i0:g.i0 + g.ii]
+                arrs.append(a)
+            out.append(arrs)
+        return out
+    # the oracle
+    ref = tile_arrays()
+    ots = [oracle.tile(g, 0) for g in tiles]
+    for q, it in enumerate(itypes):
+        oracle.world_xctilr(ipr, jpr, ots, [ref[t][q] for t in range(len(tiles))], 1, kk, 5, 5, it)
+    for o in ots:
+        o.close()
+    # the product's schedule
+    got = tile_arrays()
+    bes = [np_halo.NumpyHaloBackend(g, got[t], itypes) for t, g in enumerate(tiles)]
+    sends, nbrs = [], []
+    for t, g in enumerate(tiles):
+        nbr = xc.neighbors(g)
+        cnt = bes[t].counts(1, 2)
+        send = [bes[t].alloc(c) if nbr[d] >= 0 else None for d, c in enumerate(cnt)]
+        bes[t].pack(1, 2, send)
+        sends.append(send); nbrs.append(nbr)
+    for t, g in enumerate(tiles):
+        recv = [sends[nbrs[t][d]][xc.opp_dir(g, d)] if nbrs[t][d] >= 0 else None for d in range(8)]
+        bes[t].unpack(1, 2, recv)
+    for t, g in enumerate(tiles):
+        for q in range(len(itypes)):
+            assert np.array_equal(got[t][q], ref[t][q], equal_nan=True), (g.mproc, g.nproc, itypes[q])
+
+
 def test_periodic_shift_invariance(oracle):
     """PIPE_SHIFT (mod_pipe.F90:56-61): on a doubly periodic domain shifting every
     input by (si,sj) shifts the output by the same amount, bit for bit"""
