@@ -245,9 +245,10 @@ int hycom_tsadvc_create(const hycom_tsadvc_dims* dims, hycom_tsadvc_handle** out
   if (d.nreg == 2 && d.ipr * d.jpr != 1) {
     if (d.ipr > 1 && d.ipr % 2 != 0)
       return fail(nullptr, HYCOM_TSADVC_EINVAL, "Error in xcspmd (arctic) - ipr must be even (ipr=%d)", d.ipr);
-    if (d.nproc == d.jpr && (d.itdm % d.ipr != 0 || d.ii != d.itdm / d.ipr))
-      return fail(nullptr, HYCOM_TSADVC_EINVAL, "error - arctic patch tiles should have ii = %d (ii=%d)",
-                  d.itdm / d.ipr, d.ii);
+    // (every rank refuses an uneven split, not only the top row: the call is collective)
+    if (d.itdm % d.ipr != 0 || (d.nproc == d.jpr && d.ii != d.itdm / d.ipr))
+      return fail(nullptr, HYCOM_TSADVC_EINVAL, "error - arctic patch tiles should have ii = %d (ii=%d, itdm=%d, ipr=%d)",
+                  d.itdm / d.ipr, d.ii, d.itdm, d.ipr);
   }
   if (d.nreg < 0 || d.nreg > 4) return fail(nullptr, HYCOM_TSADVC_EINVAL, "bad nreg %d", d.nreg);
   int ndev = 0;
