@@ -110,6 +110,18 @@ PROTOTYPES = {
                                                      C.c_double]),
     "hycom_tsadvc_set_timing": (C.c_int, [_vp, C.c_int32]),
     "hycom_tsadvc_get_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "hycom_tsadvc_comm_unique_id": (C.c_int, [C.POINTER(C.c_char * 128)]),
+    "hycom_tsadvc_comm_init": (C.c_int, [_vp, C.POINTER(C.c_char * 128)]),
+    "hycom_tsadvc_comm_version": (C.c_int, [C.POINTER(C.c_int32)]),
+    "hycom_tsadvc_local_group_create": (C.c_int, [C.c_int32, C.POINTER(_vp)]),
+    "hycom_tsadvc_local_group_destroy": (C.c_int, [_vp]),
+    "hycom_tsadvc_comm_attach_local": (C.c_int, [_vp, _vp]),
+    "hycom_tsadvc_comm_detach": (C.c_int, [_vp]),
+    "hycom_tsadvc_set_overlap": (C.c_int, [_vp, C.c_int32]),
+    "hycom_tsadvc_xctilr": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "hycom_tsadvc_set_deferred_range": (C.c_int, [_vp, C.c_int32]),
+    "hycom_tsadvc_saln_range": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_int32)]),
+    "hycom_tsadvc_checksum": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     "hycom_synth_sea_mask": (C.c_int, [C.POINTER(SynthCfg), _vp]),
     "hycom_synth_fill_host": (C.c_int, [C.POINTER(SynthCfg), C.POINTER(SynthTile), _vp,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -15,6 +15,7 @@
 #include "tsadvc_dev.h"
 #include "tsadvc_handle.h"
 #include "tsadvc_launch.h"
+#include "xc_comm.h"
 
 using namespace tsadvc;
 
@@ -24,7 +25,7 @@ char g_err[512] = "";
 
 }  // namespace
 
-namespace {
+namespace tsadvc {
 
 int fail(hycom_tsadvc_handle* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -37,13 +38,11 @@ int fail(hycom_tsadvc_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
-#define CU(h, call)                                                                        \
-  do {                                                                                     \
-    cudaError_t e_ = (call);                                                               \
-    if (e_ != cudaSuccess)                                                                 \
-      return fail(h, HYCOM_TSADVC_ECUDA, "%s failed: %s (%s:%d)", #call,                   \
-                  cudaGetErrorString(e_), __FILE__, __LINE__);                             \
-  } while (0)
+}  // namespace tsadvc
+
+namespace {
+
+#define CU(h, call) TSADVC_CU(h, call)
 
 int dalloc(hycom_tsadvc_handle* h, void** p, size_t nbytes, bool zero) {
   CU(h, cudaSetDevice(h->d.device));
@@ -176,6 +175,36 @@ __device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
   }
 }
 
+// SplitMix64 finaliser
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+
+// sum over the cells tsadvc writes (M_OUT: interior sea points) of mix64(bits ^ mix64(global index)):
+// independent of the summation order and of the tiling (hycom_tsadvc_checksum)
+__global__ void __launch_bounds__(256) k_checksum(const double* __restrict__ fld, const uint8_t* __restrict__ mask,
+                                                   long slab, int pitch, int nrows, int nbdy, int i0, int j0,
+                                                   int itdm, int jtdm, int nk, unsigned long long* out) {
+  const long per = (long)pitch * nrows, total = per * nk;
+  unsigned long long acc = 0;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int k = (int)(t / per);
+    const long q = t - (long)k * per;
+    if (!(mask[q] & M_OUT)) continue;
+    const int r = (int)(q / pitch), c = (int)(q - (long)r * pitch);
+    const long gi = i0 + (c - nbdy), gj = j0 + (r - nbdy);   // 0-based global cell
+    const unsigned long long cell = (unsigned long long)(gi + (long)itdm * (gj + (long)jtdm * k));
+    const double v = fld[slab * k + q];
+    const unsigned long long bits = v == 0.0 ? 0ull : (unsigned long long)__double_as_longlong(v);   // -0.0 == 0.0
+    acc += mix64(bits ^ mix64(cell));
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 __global__ void k_minmax_init(double* mm, int kk) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < kk) {
@@ -277,6 +306,11 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->d.device);
   cudaDeviceSynchronize();
+  xc_detach(h);
+  if (h->range_host) cudaFreeHost(h->range_host);
+  if (h->ev_range) cudaEventDestroy(h->ev_range);
+  if (h->ev_xc) cudaEventDestroy(h->ev_xc);
+  cudaFree(h->d_cksum);
   for (void* raw : h->raw_allocs) cudaFree(raw);  // field mirrors, flux block, static block
   cudaFree(h->mask); cudaFree(h->scuy); cudaFree(h->scvx);
   for (auto& kv : h->seg_cache) { cudaFree(kv.second.d[0]); cudaFree(kv.second.d[1]); }
@@ -545,12 +579,6 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   return 0;
 }
 
-// a tile of the top row of a multi-tile global grid across the arctic: its northern exchange is the
-// tripole fold (mod_xc_mp.h:4263-4372, :4400-4428)
-inline int arctic_fold(const hycom_tsadvc_dims& d) {
-  return (d.nreg == 2 && d.ipr * d.jpr > 1 && d.nproc == d.jpr) ? 1 : 0;
-}
-
 // the arrays xctilr is called on at mod_tsadvc.F90:1829-1836 (th3d is exchanged by the
 // reference too but not read when advflg=0 and temdf2=0: left out of the multi-tile messages)
 int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, HaloArrays& a) {
@@ -570,25 +598,6 @@ int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, H
   a.ii = h->d.ii; a.jj = h->d.jj; a.mh = mbdy; a.nh = mbdy;
   a.fold = arctic_fold(h->d);
   return 0;
-}
-
-// 0-based tile index of the neighbour in direction d, -1 at a closed edge
-// (mod_xc.F90:25-31: nreg 1,3 periodic in i; nreg 3,4 periodic in j).  Across the arctic (nreg=2)
-// the tiles of the top row face their twins: idproc(m,jpr+1) = idproc(ipr+1-m,jpr)
-// (mod_xc_mp.h:2830), so N is the twin of this tile, NW the twin of the western and NE the twin of
-// the eastern neighbour.
-int neighbour(const hycom_tsadvc_dims& d, int dir) {
-  static const int dx[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
-  static const int dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};
-  const bool per_i = !(d.nreg == 0 || d.nreg == 4), per_j = d.nreg > 2;
-  if (arctic_fold(d) && dy[dir] > 0) {
-    const int mw = ((d.mproc - 1 + dx[dir]) % d.ipr + d.ipr) % d.ipr;
-    return (d.ipr - 1 - mw) + d.ipr * (d.nproc - 1);
-  }
-  int mp = d.mproc - 1 + dx[dir], np = d.nproc - 1 + dy[dir];
-  if (mp < 0 || mp >= d.ipr) { if (!per_i) return -1; mp = (mp + d.ipr) % d.ipr; }
-  if (np < 0 || np >= d.jpr) { if (!per_j) return -1; np = (np + d.jpr) % d.jpr; }
-  return mp + d.ipr * np;
 }
 
 // Row segments of an FCT2 or MPDATA launch.  Every (strip, row) of the rectangles of P is assigned to a run of
@@ -914,12 +923,14 @@ void fct2c_halo_arrays(const hycom_tsadvc_handle* h, const Fct2cParams& P, HaloA
   a.fold = arctic_fold(h->d);
 }
 
-// the whole scheme on a single tile
+// the whole scheme: on a single tile the halo kernels stand for the five xctilr(hloc), xctilr(fldlo)
+// of :1186-1187, on several tiles the attached communicator moves them
 int run_fct2c(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
               const std::vector<Adv>& adv) {
   const int kk = h->d.kdm, nb = fct2c_batch_layers(h);
   const int nreg = h->d.nreg;
   const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg == 2 ? 101 : nreg > 2;   // halo_ps
+  const bool single = h->d.ipr * h->d.jpr == 1;
   int rc;
   for (int batch = 0; batch * nb < kk; ++batch) {
     Fct2cParams P;
@@ -927,6 +938,12 @@ int run_fct2c(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     if ((rc = fct2c_stage(h, P, 0))) return rc;
     for (int iter = 1; iter <= 5; ++iter) {   // :1088
       if ((rc = fct2c_stage(h, P, 1))) return rc;
+      if (!single) {
+        HaloArrays a;
+        fct2c_halo_arrays(h, P, a);
+        if ((rc = xc_exchange(h, a, false, h->stream))) return rc;
+        continue;
+      }
       // xctilr(hloc), xctilr(fldlo): hloc and the fldlo stack are contiguous slabs
       for (int q = 0; q < 2; ++q) {
         int r2 = launch_halo_local(q ? P.fldlo : P.hloc, h->slab, q ? P.nb * P.nf : P.nb, h->pitch, h->d.nbdy,
@@ -960,7 +977,8 @@ int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
     mi->lev[n - 1] = mi->spare;
     mi->spare = t;
   }
-  if (xmin && xmax && ((p.nstep % 3 == 0) || p.diagno)) {
+  const bool want = h->deferred_range || (xmin && xmax);
+  if (want && ((p.nstep % 3 == 0) || p.diagno)) {
     double* dpn;
     if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
     if (!h->d_minmax && (rc = dalloc(h, (void**)&h->d_minmax, sizeof(double) * 2 * kk, false))) return rc;
@@ -969,10 +987,20 @@ int finish_step(hycom_tsadvc_handle* h, int32_t n, const hycom_tsadvc_params& p,
     k_saln_minmax<<<grid, 256, 0, h->stream>>>(h->saln.lev[n - 1], dpn, h->mask, h->slab, p.onemm,
                                                h->d_minmax, kk);
     h->launches += 2;
-    std::vector<double> mm(2 * kk);
-    CU(h, cudaMemcpyAsync(mm.data(), h->d_minmax, sizeof(double) * 2 * kk, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    for (int k = 0; k < kk; ++k) { xmin[k] = mm[k]; xmax[k] = mm[kk + k]; }
+    // :2093-2094 xcminr, xcmaxr (a host-owned transport reduces the tile values itself)
+    if (h->xc && (rc = xc_minmax(h, h->d_minmax, kk, h->stream))) return rc;
+    if (!h->range_host) {
+      CU(h, cudaMallocHost((void**)&h->range_host, sizeof(double) * 2 * kk));
+      CU(h, cudaEventCreateWithFlags(&h->ev_range, cudaEventDisableTiming));
+    }
+    CU(h, cudaMemcpyAsync(h->range_host, h->d_minmax, sizeof(double) * 2 * kk, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaEventRecord(h->ev_range, h->stream));
+    h->range_nstep = p.nstep;
+    if (!h->deferred_range) {
+      CU(h, cudaEventSynchronize(h->ev_range));
+      for (int k = 0; k < kk; ++k) { xmin[k] = h->range_host[k]; xmax[k] = h->range_host[kk + k]; }
+      h->range_nstep = -1;
+    }
   }
   CU(h, cudaGetLastError());
   return 0;
@@ -1141,6 +1169,10 @@ int hycom_tsadvc_diffuse_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
       if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_Q2, 0, n, mdf, mdf))) return rc;
       if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_Q2L, 0, n, mdf, mdf))) return rc;
     }
+  } else if (h->xc) {   // the same exchange through the communicator (a host-owned transport has done it)
+    HaloArrays a;
+    if ((rc = diff_halo_arrays(h, n, prm->mxlmy != 0, a))) return rc;
+    if ((rc = xc_exchange(h, a, false, h->stream))) return rc;
   }
   return run_diffuse(h, n, *prm);
 }
@@ -1269,6 +1301,18 @@ int hycom_tsadvc_asselin_save_device(hycom_tsadvc_handle* h, int32_t m, int32_t 
   if (h->d.ipr * h->d.jpr == 1) {   // :77-78 xctilr(oneta|onetao, 1,2, 6,6, halo_ps)
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_ONETA, 0, 0, 6, 6))) return rc;
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_ONETAO, 0, 0, 6, 6))) return rc;
+  } else if (h->xc) {
+    HaloArrays a;
+    memset(&a, 0, sizeof a);
+    for (int f : {HYCOM_F_ONETA, HYCOM_F_ONETAO})
+      for (int t = 1; t <= 2; ++t) {
+        if ((rc = slot(h, f, 0, t, &a.base[a.narr]))) return rc;
+        a.itype[a.narr++] = 1;
+      }
+    a.kk = 1; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+    a.ii = h->d.ii; a.jj = h->d.jj; a.mh = std::min(6, h->d.nbdy); a.nh = a.mh;
+    a.fold = arctic_fold(h->d);
+    if ((rc = xc_exchange(h, a, false, h->stream))) return rc;
   }
   return 0;
 }
@@ -1357,8 +1401,51 @@ int hycom_tsadvc_diff_halo_unpack(hycom_tsadvc_handle* h, int32_t n, const hycom
   return diff_halo_xfer(h, n, prm, recvbuf, cuda_stream, false);
 }
 
+// tsadvc(m,n) on the device mirrors of an ipr x jpr tile: the exchange of :1829-1836 through the attached
+// communicator, overlapped with the march over the tile interior,
+//     exchange stream : pack -> send/recv -> unpack -> march(frame)
+//     handle stream   : march(interior) ............................ join -> time-level switch, ...
+// (the frame depends on the unpacked halos only, so it runs next to the interior launch and fills its
+// tail).  advem_fct2c and isopyc read halos from their first kernel on: exchange first, no overlap.
+static int step_device_tiles(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params* prm,
+                             double* xmin, double* xmax) {
+  std::vector<Adv> adv;
+  int mbdy = 0, rc;
+  if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  if (!h->xc)
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED,
+                "tsadvc on %d x %d tiles needs a communicator (hycom_tsadvc_comm_init) or a host-driven "
+                "exchange (hycom_tsadvc_halo_pack/unpack + hycom_tsadvc_step_device_part)", h->d.ipr, h->d.jpr);
+  CU(h, cudaSetDevice(h->d.device));
+  HaloArrays a;
+  if ((rc = halo_arrays(h, adv, mbdy, a))) return rc;
+  const bool fct2c = prm->btrmas && abs(prm->advtyp) == 2;
+  if (fct2c || prm->isopyc || !h->overlap) {
+    if ((rc = xc_exchange(h, a, true, h->stream))) return rc;
+    if (fct2c) rc = run_fct2c(h, m, n, *prm, adv);
+    else rc = advect_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_ALL);
+    if (rc) return rc;
+  } else {
+    cudaStream_t cs = xc_stream(h);
+    if (!h->ev_xc) CU(h, cudaEventCreateWithFlags(&h->ev_xc, cudaEventDisableTiming));
+    CU(h, cudaEventRecord(h->ev_xc, h->stream));     // the strips are packed from the finished previous step
+    CU(h, cudaStreamWaitEvent(cs, h->ev_xc, 0));
+    if ((rc = xc_exchange(h, a, true, cs))) return rc;
+    if ((rc = run_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_INTERIOR))) return rc;
+    cudaStream_t keep = h->frame_stream;
+    h->frame_stream = cs;
+    rc = run_march(h, m, n, *prm, adv, HYCOM_TSADVC_PART_FRAME);   // the handle's stream joins behind it
+    h->frame_stream = keep;
+    if (rc) return rc;
+  }
+  if ((rc = finish_step(h, n, *prm, adv, xmin, xmax))) return rc;
+  if (prm->temdf2 > 0.0) return hycom_tsadvc_diffuse_device(h, m, n, prm);   // :2138-2230
+  return 0;
+}
+
 int hycom_tsadvc_step_device(hycom_tsadvc_handle* h, int32_t m, int32_t n,
                              const hycom_tsadvc_params* prm, double* xmin, double* xmax) {
+  if (h && h->d.ipr * h->d.jpr > 1) return step_device_tiles(h, m, n, prm, xmin, xmax);
   return hycom_tsadvc_step_device_part(h, m, n, prm, HYCOM_TSADVC_PART_ALL, xmin, xmax);
 }
 
@@ -1425,6 +1512,9 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   std::vector<Adv> adv;
   int mbdy = 0, rc;
   if ((rc = plan_step(h, m, n, prm, adv, mbdy))) return rc;
+  if (h->d.ipr * h->d.jpr > 1 && !h->xc)   // never a step with the exchanges left out
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED,
+                "tsadvc on %d x %d tiles needs a communicator: hycom_tsadvc_comm_init", h->d.ipr, h->d.jpr);
   const int kk = h->d.kdm;
   const size_t fs = (size_t)h->ncols * h->nrows;  // Fortran slab
   const bool adv_th3d = prm->advflg != 0;
@@ -1473,6 +1563,8 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   CU(h, cudaStreamSynchronize(h->stream));   // allocations zero-fill on h->stream
 
   const bool single = h->d.ipr * h->d.jpr == 1;
+  HaloArrays xa;   // the arrays of the first exchange (:1829-1836), all layers
+  if (!single && (rc = halo_arrays(h, adv, mbdy, xa))) return rc;
   const int nb = h->d.nbdy;
   auto host_of = [&](int field) { return field == HYCOM_F_SALN ? saln : field == HYCOM_F_TH3D ? th3d : temp; };
   auto resident = [](const Adv& a) { return a.field == HYCOM_F_Q2 || a.field == HYCOM_F_Q2L; };
@@ -1506,8 +1598,13 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
     if ((rc = upload_on(h, HYCOM_F_VFLX, 0, 1, k0 + 1, nk, vflx + fs * k0, h->up_stream))) return rc;
     CU(h, cudaEventRecord(h->ev_chunk[2 * c], h->up_stream));
     CU(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c], 0));
-    // ---- :1827-1836 halos (single tile; a multi-tile host program hands over valid halos)
-    if (single) {
+    // ---- :1827-1836 halos: the layers of this chunk (layers are independent, so is their exchange)
+    if (!single) {
+      HaloArrays a = xa;
+      for (int q = 0; q < a.narr; ++q) a.base[q] += h->slab * k0;
+      a.kk = nk;
+      if ((rc = xc_exchange(h, a, true, h->stream))) return rc;
+    } else {
       for (const Adv& a : adv) {
         if (k0 >= a.nlay) continue;
         const int na = (k0 + nk <= a.nlay) ? nk : a.nlay - k0;
@@ -1552,7 +1649,7 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
     bool other_advected = false;   // isopyc: th3d is advected in layer 1 and already in its mirror
     for (const Adv& a : adv) other_advected = other_advected || a.field == ofield;
     if (!other_advected && (rc = upload_on(h, ofield, 0, n, 1, kk, h4(other, n, 0), h->stream))) return rc;
-    if (single && (rc = hycom_tsadvc_diffuse_device(h, m, n, prm))) return rc;
+    if ((rc = hycom_tsadvc_diffuse_device(h, m, n, prm))) return rc;
     auto back_all = [&](int field, int ktr, double* host_n) -> int {
       double* base;
       int r2 = slot(h, field, ktr, n, &base);
@@ -1566,6 +1663,70 @@ int hycom_tsadvc_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_
   }
   CU(h, cudaStreamSynchronize(h->down_stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int hycom_tsadvc_xctilr(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev, int32_t mh, int32_t nh,
+                        int32_t itype) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  if (h->d.ipr * h->d.jpr == 1) return hycom_tsadvc_halo_local(h, field, ktr, tlev, mh, nh);
+  if (!h->xc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "xctilr on %d x %d tiles needs a communicator", h->d.ipr, h->d.jpr);
+  if (mh < 0 || nh < 0 || mh > h->d.nbdy || nh > h->d.nbdy) return fail(h, HYCOM_TSADVC_EINVAL, "xctilr: bad halo width %d,%d", mh, nh);
+  CU(h, cudaSetDevice(h->d.device));
+  HaloArrays a;
+  memset(&a, 0, sizeof a);
+  const int t0 = is3d(field) ? 1 : (tlev == 0 ? 1 : tlev), t1 = is3d(field) ? 1 : (tlev == 0 ? 2 : tlev);
+  int rc;
+  for (int t = t0; t <= t1; ++t) {
+    if ((rc = slot(h, field, ktr, t, &a.base[a.narr]))) return rc;
+    a.itype[a.narr++] = itype;
+  }
+  a.kk = nlayers_of(h, field); a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+  a.ii = h->d.ii; a.jj = h->d.jj; a.mh = mh; a.nh = nh;
+  a.fold = arctic_fold(h->d);
+  return xc_exchange(h, a, false, h->stream);
+}
+
+int hycom_tsadvc_set_deferred_range(hycom_tsadvc_handle* h, int32_t enable) {
+  if (!h) return fail(nullptr, HYCOM_TSADVC_EINVAL, "null handle");
+  h->deferred_range = enable != 0;
+  return 0;
+}
+
+int hycom_tsadvc_saln_range(hycom_tsadvc_handle* h, double* xmin, double* xmax, int32_t* nstep) {
+  if (!h || !xmin || !xmax) return fail(h, HYCOM_TSADVC_EINVAL, "saln_range: null argument");
+  if (nstep) *nstep = h->range_nstep;
+  if (h->range_nstep < 0 || !h->range_host) return 0;
+  CU(h, cudaEventSynchronize(h->ev_range));
+  const int kk = h->d.kdm;
+  for (int k = 0; k < kk; ++k) { xmin[k] = h->range_host[k]; xmax[k] = h->range_host[kk + k]; }
+  h->range_nstep = -1;
+  return 0;
+}
+
+int hycom_tsadvc_checksum(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, int32_t tlev, int32_t global,
+                          uint64_t* sum) {
+  if (!h || !sum) return fail(h, HYCOM_TSADVC_EINVAL, "checksum: null argument");
+  if (!h->have_static) return fail(h, HYCOM_TSADVC_EINVAL, "checksum: set_static has not been called");
+  CU(h, cudaSetDevice(h->d.device));
+  double* base;
+  int rc = slot(h, field, ktr, tlev, &base);
+  if (rc) return rc;
+  if (!h->d_cksum && (rc = dalloc(h, (void**)&h->d_cksum, sizeof(unsigned long long), false))) return rc;
+  CU(h, cudaMemsetAsync(h->d_cksum, 0, sizeof(unsigned long long), h->stream));
+  const int nk = h->d.kdm;   // the model layers 1..kdm (q2, q2l: slabs 1..kdm of 0:kdm+1)
+  k_checksum<<<148 * 8, 256, 0, h->stream>>>(base + h->slab * layer1_of(field), h->mask, h->slab, h->pitch, h->nrows,
+                                             h->d.nbdy, h->d.i0, h->d.j0, h->d.itdm, h->d.jtdm, nk, h->d_cksum);
+  h->launches += 1;
+  CU(h, cudaGetLastError());
+  if (global && h->d.ipr * h->d.jpr > 1) {
+    if (!h->xc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "checksum over all tiles needs a communicator");
+    if ((rc = xc_sum_u64(h, h->d_cksum, 1, h->stream))) return rc;
+  }
+  unsigned long long v = 0;
+  CU(h, cudaMemcpyAsync(&v, h->d_cksum, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  *sum = (uint64_t)v;
   return 0;
 }
 

@@ -10,6 +10,7 @@
 #include "../../include/hycom_tsadvc_b200.h"
 
 namespace tsadvc {
+struct XcComm;   // communicator of a multi-tile run (xc_comm.cu)
 struct Mirror {
   double* lev[2] = {nullptr, nullptr};  // time slots 1,2 (3-D fields: lev[0] only)
   double* spare = nullptr;              // ping-pong target of the next step
@@ -69,5 +70,29 @@ struct hycom_tsadvc_handle {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
   double march_ms = 0.0;
   int64_t march_n = 0;
+  // multi-tile runs: the transport between tiles (NCCL or in-process), its stream and staging
+  // buffers (xc_comm.cu); null: the host program moves the packed strips itself
+  tsadvc::XcComm* xc = nullptr;
+  bool overlap = true;          // exchange overlapped with the tile interior (hycom_tsadvc_set_overlap)
+  // salinity range of the last diagnostic step: device -> pinned host, fetched by
+  // hycom_tsadvc_saln_range (deferred mode: the step itself never waits for the device)
+  bool deferred_range = false;
+  double* range_host = nullptr;   // pinned, 2*kdm
+  cudaEvent_t ev_range = nullptr;
+  int32_t range_nstep = -1;
+  unsigned long long* d_cksum = nullptr;
+  cudaEvent_t ev_xc = nullptr;    // handle stream -> exchange stream
   char err[512];
 };
+
+// error reporting shared by the translation units of the library
+namespace tsadvc {
+int fail(hycom_tsadvc_handle* h, int code, const char* fmt, ...);
+}
+#define TSADVC_CU(h, call)                                                                 \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return tsadvc::fail(h, HYCOM_TSADVC_ECUDA, "%s failed: %s (%s:%d)", #call,           \
+                          cudaGetErrorString(e_), __FILE__, __LINE__);                     \
+  } while (0)

@@ -167,6 +167,50 @@ class Tsadvc:
         self._ck(self.lib.hycom_tsadvc_get_timing(self.h, C.byref(ms), C.byref(nl), int(reset)))
         return ms.value, nl.value
 
+    # -- multi-tile runs: the communicator lives in the handle (mod_xc's role) ---------
+    def comm_init_nccl(self, dist, group=None):
+        """attach an NCCL communicator: rank 0 of the torch.distributed group draws the id, the group
+        broadcasts the 128 bytes (the only thing the host program contributes)"""
+        import torch
+        g = self.cb.geom
+        rank = dist.get_rank(group)
+        if rank != g.mproc - 1 + g.ipr * (g.nproc - 1):
+            raise ValueError("tiles are placed row-major: rank = mproc-1 + ipr*(nproc-1)")
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            self._ck(self.lib.hycom_tsadvc_comm_unique_id(C.byref(buf)))
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        src = 0 if group is None else dist.get_global_rank(group, 0)
+        dist.broadcast(t, src=src, group=group)
+        buf.raw = bytes(t.cpu().numpy().tobytes())
+        self._ck(self.lib.hycom_tsadvc_comm_init(self.h, C.byref(buf)))
+
+    def comm_attach_local(self, group_handle):
+        self._ck(self.lib.hycom_tsadvc_comm_attach_local(self.h, group_handle))
+
+    def set_overlap(self, enable: bool = True):
+        self._ck(self.lib.hycom_tsadvc_set_overlap(self.h, int(enable)))
+
+    def set_deferred_range(self, enable: bool = True):
+        self._ck(self.lib.hycom_tsadvc_set_deferred_range(self.h, int(enable)))
+
+    def saln_range(self):
+        """(nstep, xmin, xmax) of the last diagnostic step in deferred mode; nstep -1: nothing pending"""
+        ns = C.c_int32(-1)
+        self._ck(self.lib.hycom_tsadvc_saln_range(self.h, _ptr(self.xmin), _ptr(self.xmax), C.byref(ns)))
+        return ns.value, self.xmin, self.xmax
+
+    def checksum(self, fld: int, tlev: int = 1, ktr: int = 0, all_tiles: bool = True) -> int:
+        """tiling-invariant checksum of the interior sea points of one mirror (PIPE_CHECK analogue)"""
+        out = C.c_uint64(0)
+        self._ck(self.lib.hycom_tsadvc_checksum(self.h, fld, ktr, tlev, int(all_tiles), C.byref(out)))
+        return int(out.value)
+
+    def xctilr(self, fld: int, tlev: int = 0, ktr: int = 0, mh: int = 5, nh: int = 5, itype: int = 1):
+        self._ck(self.lib.hycom_tsadvc_xctilr(self.h, fld, ktr, tlev, mh, nh, itype))
+
     def set_static(self):
         cb = self.cb
         self._ck(self.lib.hycom_tsadvc_set_static(

@@ -29,8 +29,26 @@ def shape_cfg(name: str, nreg=0, ntracr=0, seed=1) -> SynthCfg:
     return make_cfg(idm, jdm, kdm, nreg=nreg, ntracr=ntracr, seed=seed, dx0=dx, delt1=2.0 * baclin)
 
 
+_host_lib = None
+
+
+def use_host_library(path: str) -> None:
+    """take hycom_synth_sea_mask / hycom_synth_fill_host from a CUDA-free build of the same source
+    (oracle/_build/libsynth_host.so): the reference arm of bench.py then maps nothing of the product"""
+    global _host_lib
+    lib = C.CDLL(path)
+    for name in ("hycom_synth_sea_mask", "hycom_synth_fill_host"):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = cabi.PROTOTYPES[name]
+    _host_lib = lib
+
+
+def _hostlib():
+    return _host_lib if _host_lib is not None else load_library()
+
+
 def sea_mask(cfg: SynthCfg) -> np.ndarray:
-    lib = load_library()
+    lib = _hostlib()
     sea = np.zeros((cfg.jtdm, cfg.itdm), dtype=np.uint8)
     rc = lib.hycom_synth_sea_mask(C.byref(cfg), sea.ctypes.data_as(C.c_void_p))
     if rc:
@@ -44,7 +62,7 @@ def _tile(g: TileGeom) -> SynthTile:
 
 def fill_host(cfg: SynthCfg, g: TileGeom, sea: np.ndarray, field: int, ktr: int = 0, lev: int = 0,
               k0: int = 1, nk: int = 1, halo_mode: int = 0, fill: float = np.nan) -> np.ndarray:
-    lib = load_library()
+    lib = _hostlib()
     out = np.empty((nk, g.nrows, g.ncols))
     t = _tile(g)
     rc = lib.hycom_synth_fill_host(C.byref(cfg), C.byref(t), sea.ctypes.data_as(C.c_void_p), field,

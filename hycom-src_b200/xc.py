@@ -1,10 +1,12 @@
 """Multi-tile halo exchange of the tsadvc path: the host side of ``xctilr``.
 
 mod_xc (mod_xc_mp.h:4664-4987) owns the communicator and moves the packed edge strips with
-MPI/SHMEM.  Here one process drives one GPU (= one tile, placed exactly as mod_xc places
-tiles: ``geometry.partition``), the edge strips are packed and unpacked on the device by the
-C library (``hycom_tsadvc_halo_pack/unpack``) and travel between GPUs as NCCL send/recv over
-NVLink (``torch.distributed`` is the plumbing).  All eight neighbours are addressed in one
+MPI/SHMEM.  The product path keeps the communicator INSIDE the C library (csrc/xc_comm.cu:
+``Tsadvc.comm_init_nccl`` + one ``hycom_tsadvc_step_device`` call per step).  This module is the
+alternative a host program uses when it wants to own the byte moving: one process drives one GPU
+(= one tile, placed exactly as mod_xc places tiles: ``geometry.partition``), the edge strips are
+packed and unpacked on the device by the C library (``hycom_tsadvc_halo_pack/unpack``) and travel
+between GPUs as NCCL send/recv over NVLink issued by ``torch.distributed``.  All eight neighbours are addressed in one
 round, and the exchange overlaps the interior of the tile:
 
     comm stream   : pack -> send/recv -> unpack
@@ -189,10 +191,11 @@ class XcExchange:
     def _buffers(self, m, n):
         """(send, recv, ops) of an exchange with these leapfrog slots; built once and reused
         (the per-step host work is what limits the 8-GPU step, not the bytes)"""
-        key = (m, n, self.ts.cb.ntracr if self.ts is not None else 0,
-               self.ts.cb.advflg if self.ts is not None else 0)
+        # the message layout depends on every scalar that selects the exchanged arrays and the halo
+        # width (advtyp: mbdy 2 or 5; mxlmy: q2, q2l; advflg/isopyc/nhybrd: th3d): key on the counts
+        cnt = self.backend.counts(m, n)
+        key = (m, n, tuple(cnt))
         if key not in self._bufs:
-            cnt = self.backend.counts(m, n)
             send = [self.backend.alloc(c) if self.nbr[d] >= 0 else None for d, c in enumerate(cnt)]
             recv: List = [None] * 8
             for d, c in enumerate(cnt):
@@ -273,7 +276,9 @@ class XcExchange:
             self.finish(m, n, pending)
             self._fct2c(m, n, p)
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_ALL, xm, xx))
-        elif overlap:
+        elif overlap and not ts.cb.isopyc:
+            # (isopyc: the flux smoothing and the march of layer 1 read the halo from their first kernel on
+            # and run on the handle's stream - exchange first, like advem_fct2c)
             ts._ck(ts.lib.hycom_tsadvc_step_device_part(ts.h, m, n, C.byref(p), cabi.PART_INTERIOR, None, None))
             if self.comm_stream is not None and self.frame_concurrent:
                 # the frame runs on the comm stream right behind the unpack, next to the interior
@@ -371,8 +376,9 @@ class XcExchange:
         """xcminr / xcmaxr of the per-layer salinity range (mod_tsadvc.F90:2093-2094):
         element-wise min/max over all tiles, in place"""
         torch = self.torch
-        dev = self.backend.dev if self.comm_stream is not None else "cpu"
         import numpy as np
+        nccl = self.dist.get_backend(self.group) == "nccl"
+        dev = getattr(self.backend, "dev", "cuda") if nccl else "cpu"
         kk = xmin.shape[0]
         both = torch.from_numpy(np.concatenate([xmin, -xmax])).to(dev)   # max = -min(-x): one collective
         self.dist.all_reduce(both, op=self.dist.ReduceOp.MIN, group=self.group)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define HYCOM_TSADVC_ABI_VERSION 2
+#define HYCOM_TSADVC_ABI_VERSION 3
 #define HYCOM_TSADVC_MXTRCR 16
 
 enum {
@@ -171,12 +171,57 @@ int hycom_tsadvc_device_slab(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
 int hycom_tsadvc_halo_local(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
                             int32_t tlev_or_0_for_both, int32_t mh, int32_t nh);
 
-/* ---- multi-tile runs (ipr*jpr > 1): the device side of xctilr --------------------------
+/* ---- multi-tile runs (ipr*jpr > 1): the communicator ------------------------------------
+ * The reference's xctilr / xcminr / xcmaxr live in mod_xc, which owns MPI_COMM_HYCOM
+ * (mod_xc_mp.h:2317-3288, :4664-4987, :6091-6389).  Here the HANDLE owns the transport: once a
+ * communicator is attached, hycom_tsadvc_step and hycom_tsadvc_step_device are complete on
+ * ipr x jpr tiles - first exchange (mod_tsadvc.F90:1829-1836) overlapped with the tile
+ * interior, the width-2 diffusion exchange (:2140-2151), the five exchanges inside
+ * advem_fct2c (:1186-1187), xcminr/xcmaxr of the salinity range (:2093-2094).  Calls are
+ * collective over all tiles, like the reference routine.  Without a communicator those two
+ * entries return HYCOM_TSADVC_EUNSUPPORTED on a multi-tile handle (they never skip work).
+ *   NCCL: one process per GPU.  Rank 0 obtains the 128-byte id, the host program broadcasts it
+ *   (MPI_Bcast(id,128,MPI_BYTE,0,mpi_comm_hycom) in the Fortran shim), every tile calls
+ *   hycom_tsadvc_comm_init; rank = mproc-1 + ipr*(nproc-1), ranks = ipr*jpr.  libnccl.so.2 is
+ *   loaded at run time (HYCOM_TSADVC_NCCL_LIB overrides the name).
+ *   In-process: several handles of ONE process, each driven by its own host thread (tests). */
+#define HYCOM_TSADVC_COMM_ID_BYTES 128
+typedef struct hycom_tsadvc_local_group hycom_tsadvc_local_group;
+int hycom_tsadvc_comm_unique_id(char id[HYCOM_TSADVC_COMM_ID_BYTES]);
+int hycom_tsadvc_comm_init(hycom_tsadvc_handle *h, const char id[HYCOM_TSADVC_COMM_ID_BYTES]);
+int hycom_tsadvc_comm_version(int32_t *nccl_version_code);
+int hycom_tsadvc_local_group_create(int32_t nranks, hycom_tsadvc_local_group **out);
+int hycom_tsadvc_local_group_destroy(hycom_tsadvc_local_group *g);
+int hycom_tsadvc_comm_attach_local(hycom_tsadvc_handle *h, hycom_tsadvc_local_group *g);
+int hycom_tsadvc_comm_detach(hycom_tsadvc_handle *h);
+/* 1 (default): the first exchange runs next to the march over the tile interior, the frame
+ * follows the unpack; 0: exchange first, then the whole tile (comparison runs) */
+int hycom_tsadvc_set_overlap(hycom_tsadvc_handle *h, int32_t enable);
+/* xctilr(a(1-nbdy,1-nbdy,1[,tlev]),1,nk, mh,nh, itype) of one mirror through the attached
+ * communicator (single tile: hycom_tsadvc_halo_local); tlev 0: both time slots;
+ * itype 1 halo_ps, 13 halo_uv, 14 halo_vv (mod_xc.F90:41-44) */
+int hycom_tsadvc_xctilr(hycom_tsadvc_handle *h, int32_t field, int32_t ktr,
+                        int32_t tlev_or_0_for_both, int32_t mh, int32_t nh, int32_t itype);
+/* Deferred diagnostics: with enable != 0 a step never waits for the device; the salinity range
+ * of a diagnostic step (mod(nstep,3)==0 or diagno) stays in pinned memory until
+ * hycom_tsadvc_saln_range fetches it (waits for that step only).  *nstep receives the step the
+ * range belongs to, -1 if none is pending. */
+int hycom_tsadvc_set_deferred_range(hycom_tsadvc_handle *h, int32_t enable);
+int hycom_tsadvc_saln_range(hycom_tsadvc_handle *h, double *xmin, double *xmax, int32_t *nstep);
+/* Tiling-invariant checksum of one mirror, the analogue of the reference's PIPE_CHECK hash
+ * (mod_pipe.F90:724-757: MurmurHash3 over the gathered array on the first tile).  Here every
+ * interior sea cell (1<=i<=ii, 1<=j<=jj, ip) of every layer contributes
+ * mix64(bits(a(i,j,k)) ^ mix64(global cell index)) to a sum modulo 2**64 - independent of the
+ * order of summation and of the tiling; global != 0: summed over all tiles (collective). */
+int hycom_tsadvc_checksum(hycom_tsadvc_handle *h, int32_t field, int32_t ktr, int32_t tlev,
+                          int32_t global, uint64_t *sum);
+
+/* ---- multi-tile runs with a HOST-owned transport: the device side of xctilr --------------
  * mod_xc_mp.h:4664-4987 packs the mh x nh wide edge strips of a (..,..,ld) array, moves them
- * with MPI/SHMEM and unpacks them into the neighbour's halo.  Here the library packs and
- * unpacks on the device; the TRANSPORT between tiles stays with the host program, as it
- * does in the reference (mod_xc owns the communicator): NCCL send/recv or CUDA-aware MPI on
- * the device buffers, torch.distributed in this repository's Python host.
+ * with MPI/SHMEM and unpacks them into the neighbour's halo.  A host program that wants to keep
+ * the byte moving to itself (CUDA-aware MPI, torch.distributed: hycom-src_b200/xc.py) uses the
+ * pack / unpack entries below and drives the step in parts; the library then performs no
+ * exchange of its own.
  * Directions: 0 W, 1 E, 2 S, 3 N, 4 SW, 5 SE, 6 NW, 7 NE.  All eight neighbours are
  * addressed in one round; a corner message comes from the diagonal tile (the reference
  * gets the same values in two hops, N/S then E/W including the fresh N/S lines).

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_abi_version(pkg):
     lib = cabi.load_library()
-    assert lib.hycom_tsadvc_abi_version() == 2
+    assert lib.hycom_tsadvc_abi_version() == 3
 
 
 def test_struct_layout_matches_header(pkg):

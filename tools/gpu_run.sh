@@ -1,0 +1,80 @@
+#!/bin/bash
+# One parameterised GPU session (replaces the round-1 one-off scripts).
+#   gpurun [--gpus N] --timeout T -- 'bash tools/gpu_run.sh TAG STEP [STEP ...]'
+# Steps (each writes under gpurun_out/TAG/):
+#   env        toolchain probe (gfortran & co), nvidia-smi, NCCL version
+#   tests      python -m pytest tests -m gpu
+#   smoke      __graft_entry__.smoke()
+#   bench      bench.py at N = $NGPU (default 1), driver flags
+#   benchq     bench.py quick (5 steps, no e2e / cpu / extra)
+#   ref        bench.py --impl reference
+#   launches   ncu launch list of a short bench run (N=1)
+#   ncu        ncu --set full + source of the marching kernel (N=1, reduced kdm)
+#   tma        the tensor-map TMA probe, every variant in its own process
+#   nccl       tools/xc_nccl_check.py under torchrun (N = $NGPU >= 2)
+#   scale      bench.py at N=1,2,4,8 as far as $NGPU allows (no e2e/cpu)
+#   fortran    fortran/build_ref.sh if a Fortran compiler exists
+#   variants   kernel variant timings (env knobs listed in $VARIANTS, ';'-separated)
+TAG=${1:?tag}; shift
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+NGPU=${NGPU:-1}
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29533"
+for STEP in "$@"; do
+  echo "=== $STEP"
+  case $STEP in
+    env)
+      { for c in gfortran flang flang-new nvfortran ifort ifx lfortran f2c mpif90 mpirun; do printf "%s: " $c; which $c || echo none; done
+        nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,memory.total --format=csv
+        nproc; free -g | head -2
+        python -c "import importlib,ctypes as C; p=importlib.import_module('hycom-src_b200'); l=p.load_library(); v=C.c_int32(0); print('nccl rc', l.hycom_tsadvc_comm_version(C.byref(v)), 'version', v.value)"
+      } > $OUT/env.txt 2>&1; cat $OUT/env.txt ;;
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "rc=$?" >> $OUT/pytest_gpu.log; tail -5 $OUT/pytest_gpu.log ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "rc=$?" >> $OUT/smoke.log; tail -3 $OUT/smoke.log ;;
+    bench)
+      if [ $NGPU -gt 1 ]; then L="$TR --nproc-per-node $NGPU"; else L=python; fi
+      timeout 900 $L bench.py --gpus $NGPU --steps 20 --warmup 5 $BENCH_ARGS > $OUT/bench_n$NGPU.json 2> $OUT/bench_n$NGPU.err; echo "rc=$?"; cut -c1-1800 $OUT/bench_n$NGPU.json; tail -3 $OUT/bench_n$NGPU.err ;;
+    benchq)
+      timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --no-extra $BENCH_ARGS > $OUT/benchq.json 2> $OUT/benchq.err; echo "rc=$?"; cut -c1-900 $OUT/benchq.json; tail -3 $OUT/benchq.err ;;
+    ref)
+      timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/ref.json 2> $OUT/ref.err; echo "rc=$?"; cut -c1-1500 $OUT/ref.json; tail -3 $OUT/ref.err ;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extra > $OUT/launches_run.log 2>&1; echo "rc=$?"; tail -2 $OUT/launches_run.log | cut -c1-300 ;;
+    ncu)
+      # general launch first, all-sea second in every step: skip the 3 warm-up steps
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_tsadvc_march -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} -f -o $OUT/prof \
+        python bench.py --kdm ${NCU_KDM:-6} --steps 1 --warmup 3 --no-e2e --no-cpu --no-extra $BENCH_ARGS > $OUT/ncu_run.log 2>&1; echo "rc=$?"; tail -2 $OUT/ncu_run.log | cut -c1-300
+      ls -la $OUT/prof.ncu-rep ;;
+    tma)
+      (cd tools/probe && nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe4 tma_probe4.cu -lcuda 2>/dev/null)
+      for v in 0 1 2 3 4; do timeout 60 tools/probe/tma_probe4 $v; echo "exit=$?"; done > $OUT/tma_probe4.txt 2>&1; cat $OUT/tma_probe4.txt ;;
+    nccl)
+      timeout 900 $TR --nproc-per-node $NGPU tools/xc_nccl_check.py > $OUT/xc_nccl_check_n$NGPU.log 2>&1; echo "rc=$?" >> $OUT/xc_nccl_check_n$NGPU.log; grep -v "^W\|^\[W\|warn" $OUT/xc_nccl_check_n$NGPU.log | tail -8
+      if [ -n "$XC_TILES" ]; then XC_CHECK_TILES=$XC_TILES XC_CHECK_CASES=arctic timeout 600 $TR --nproc-per-node $NGPU tools/xc_nccl_check.py > $OUT/xc_nccl_check_$XC_TILES.log 2>&1; echo "rc=$?" >> $OUT/xc_nccl_check_$XC_TILES.log; tail -3 $OUT/xc_nccl_check_$XC_TILES.log; fi ;;
+    scale)
+      for n in 1 2 4 8; do
+        [ $n -gt $NGPU ] && break
+        if [ $n -gt 1 ]; then L="$TR --nproc-per-node $n"; else L=python; fi
+        timeout 600 $L bench.py --gpus $n --steps 20 --warmup 5 --no-cpu $SCALE_ARGS > $OUT/scale_n$n.json 2> $OUT/scale_n$n.err; echo "n=$n rc=$?"; cut -c1-700 $OUT/scale_n$n.json; tail -2 $OUT/scale_n$n.err
+      done ;;
+    fortran)
+      if which gfortran > /dev/null 2>&1; then bash fortran/build_ref.sh > $OUT/fortran_ref.log 2>&1; tail -5 $OUT/fortran_ref.log; else echo "no gfortran on this box" | tee $OUT/fortran_ref.log; fi ;;
+    variants)
+      IFS=';' read -ra VS <<< "$VARIANTS"
+      for v in "${VS[@]}"; do
+        name=$(echo "$v" | tr ' =/' '___')
+        env $v timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-extra > $OUT/var_$name.json 2> $OUT/var_$name.err
+        python - "$v" $OUT/var_$name.json <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    print(f"{sys.argv[1]:60s} ms/step {d['ms_per_step']:.3f} kernel {d['roofline']['kernel_ms']:.3f} frac {d['roofline']['frac']:.4f} cks {d['checksum']['value']}")
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+PY
+      done | tee $OUT/variants.txt ;;
+    *) echo "unknown step $STEP" ;;
+  esac
+done
