@@ -54,6 +54,7 @@ struct Fct2Scheme {
   typedef Fct2T<NC> State;
   static constexpr bool kNeedC = true;
   static constexpr int kPeriod = 3;
+  static constexpr int kLag = 3;               // the row finished in iteration r is row r-3
   static constexpr bool kNeedM = (SEA == 0);   // the mask plane is staged for the general body only
 
   static __device__ __forceinline__ void init(State& s) {
@@ -304,7 +305,6 @@ struct Fct2Scheme {
 
   // ---- stage E: row r-3, S6 (:968-980) and store
   {
-    const int r3 = r - 3;
     double SCI3[NC], OLD3[NC], nv[NC];
     ld_own<NC, R::SCI>(p, s3, SCI3);
     ld_own<NC, R::F>(p, s3, OLD3);
@@ -314,13 +314,8 @@ struct Fct2Scheme {
       const double d = div_flag<SAFE>(a, s.FCN[a3][c] + onemu, s.Y[a3][c], bad);
       nv[c] = fmax2(s.QMN[a3][c], fmin2(s.QMX[a3][c], s.LO[a3][c] - d));
     }
-    const int col = x.w0 + NC * x.lane;
-    if ((unsigned)col < (unsigned)x.pitch && r3 >= x.j0 && r3 < x.j1) {
-      Vec<NC> old;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) old.v[c] = OLD3[c];
-      store_vec<NC>(x.out, (long)r3 * x.pitch + col, x.lane, ALLSEA ? ((NC == 2) ? 0xffffu : 0xffu) : s.m3, old, nv);
-    }
+    if (ALLSEA) store_cells<NC>(p, nv);
+    else store_row_masked<NC>(p, s.m3, OLD3, nv);
   }
   s.m3 = s.m2; s.m2 = s.m1; s.m1 = m0;
   }

@@ -39,6 +39,7 @@ struct MpdataScheme {
   typedef MpdataT<NC> State;
   static constexpr bool kNeedC = false;
   static constexpr int kPeriod = 3;
+  static constexpr int kLag = 3;
   static constexpr bool kNeedM = (SEA == 0);   // the mask plane is staged for the general body only
   static constexpr bool ALLSEA = (SEA != 0);
 
@@ -217,7 +218,6 @@ struct MpdataScheme {
 
     // ---- stage E: row r-3, M6 (:475-480) and store
     {
-      const int r3 = r - 3;
       double SCI3[NC], OLD3[NC], nv[NC];
       ld_own<NC, R::SCI>(p, s3, SCI3);
       ld_own<NC, R::F>(p, s3, OLD3);
@@ -229,14 +229,8 @@ struct MpdataScheme {
         const double f = fmax2(s.MN[a3][c], fmin2(s.MX[a3][c], s.LO[a3][c] - d));
         nv[c] = f - posdef;
       }
-      const int col = x.w0 + NC * x.lane;
-      if ((unsigned)col < (unsigned)x.pitch && r3 >= x.j0 && r3 < x.j1) {
-        Vec<NC> old;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) old.v[c] = OLD3[c];
-        store_vec<NC>(x.out, (long)r3 * x.pitch + col, x.lane, ALLSEA ? ((NC == 2) ? 0xffffu : 0xffu) : s.m3, old,
-                      nv);
-      }
+      if (ALLSEA) store_cells<NC>(p, nv);
+      else store_row_masked<NC>(p, s.m3, OLD3, nv);
     }
     s.m3 = s.m2; s.m2 = s.m1; s.m1 = m0;
   }

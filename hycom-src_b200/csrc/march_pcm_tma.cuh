@@ -17,6 +17,7 @@ struct PcmScheme {
   typedef PcmT<NC> State;
   static constexpr bool kNeedC = false;
   static constexpr int kPeriod = 6;
+  static constexpr int kLag = 1;               // the row finished in iteration r is row r-1
   static constexpr bool kNeedM = true;
 
   static __device__ __forceinline__ void init(State& s) {
@@ -86,14 +87,7 @@ struct PcmScheme {
         const double lo = div_flag<SAFE>(q, b, SAFE ? 0.0 : rcp_nr(b), bad);
         nv[c] = fmax2(mn, fmin2(mx, lo));
       }
-      const int r1 = r - 1;
-      const int col = x.w0 + NC * x.lane;
-      if ((unsigned)col < (unsigned)x.pitch && r1 >= x.j0 && r1 < x.j1) {
-        Vec<NC> old;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) old.v[c] = F1[c];
-        store_vec<NC>(x.out, (long)r1 * x.pitch + col, x.lane, m1, old, nv);
-      }
+      store_row_masked<NC>(p, m1, F1, nv);
     }
     s.m1 = m0;
   }

@@ -2,23 +2,31 @@
 //
 // Row pipeline: stage A works on row r, B on row r-1, C/D on row r-2, E on row r-3.
 // The RAW rows (fld, fldc, uflx, vflx, dp, scp2i, scp2, masks) are not carried in registers:
-// each warp owns a ring of six row slots in shared memory that the TMA engine fills
-// (cp.async.bulk global->shared, SASS UBLKCP: one 256*NC-byte request per array and row,
-// completion counted in bytes on one mbarrier per slot).  Row r+3 is requested at the end of iteration r, into the slot of row r-3 that
-// iteration r has just finished with, so three rows are always in flight and the prefetch
-// distance does not depend on the instruction scheduler.  i-neighbours of raw data are
-// plain shared-memory reads at lane-1 / lane+1; j-neighbours are older slots.  Rows outside
-// the slab (apron of the first/last chunk) are clamped to the nearest row; the window of the
-// first/last strip may start 4 columns before / end after its row, i.e. in the neighbouring
-// row or in the guard row every buffer is allocated with: real, finite data that only ever
-// feeds apron lanes (dependency radius 3 < nbdy).  Nothing is predicated.  Only computed
-// intermediates stay in register rings indexed by (row mod 2) or (row mod 3); the loop is
-// unrolled six times with the phase as a template parameter, so every ring and slot index
-// is a compile-time constant and nothing is ever rotated.
-// (The tensor-map form cp.async.bulk.tensor / UTMALDG raises "illegal instruction" on this
-// pool's B200 boxes even for the CUDA programming guide's own example - tools/probe/ -
-// so the rows are fetched with the descriptor-less bulk copy.)
+// each warp owns a ring of six row slots in shared memory that the TMA engine fills from 3-D
+// tensor maps (col, row, layer) - cp.async.bulk.tensor, SASS UTMALDG: one 32*NC-column box per
+// array and row, coordinates instead of 64-bit address arithmetic, completion counted in bytes
+// on one mbarrier per slot.  Row r+3 is requested at the end of iteration r, into the slot of
+// row r-3 that iteration r has just finished with, so three rows are always in flight and the
+// prefetch distance does not depend on the instruction scheduler.  i-neighbours of raw data are
+// plain shared-memory reads at lane-1 / lane+1; j-neighbours are older slots.  Rows and columns
+// outside the slab (apron of the first/last chunk or strip) are zero-filled by the TMA engine:
+// finite data that only ever feeds apron lanes (dependency radius 3 < nbdy).  Nothing is
+// predicated.  Only computed intermediates stay in register rings indexed by (row mod 2) or
+// (row mod 3).
+// The finished row is stored straight from registers through one per-lane pointer that advances by
+// a row per iteration (predicated 16-byte stores, no branches, no per-row 64-bit index arithmetic).
+// (A TMA store of the row was tried first: the strip interior starts at the odd column w0+3, and a
+// box whose first element is not 16-byte aligned in global memory raises "illegal instruction" -
+// loads and stores alike, which is also what round 1's probe hit with its column 3;
+// profiles/r02c_tma_probe5.txt.  Loads start at the even column w0.)
+// (Round 1 believed the tensor-map form traps on this pool: its probe fetched
+// cuTensorMapEncodeTiled with the default driver entry point, which on the CUDA 13 driver of the
+// boxes is not the CUDA 12 ABI the runtime headers describe; with
+// cudaGetDriverEntryPointByVersion(..., 12000) every variant works: profiles/r02a_tma_probe4.txt.
+// Per-instruction stall samples of the old address arithmetic: profiles/r02a_*_stalls.txt.)
 #pragma once
+#include <cuda.h>
+
 #include "march_common.cuh"
 #include "tsadvc_launch.h"
 
@@ -33,7 +41,6 @@ struct Ring {
   static constexpr int SLOT = NARR * RB;
   static constexpr int NSLOT = 6;
   static constexpr int BYTES = NSLOT * SLOT;           // per warp
-  static constexpr int TX = SLOT;                      // bytes the requests of one row deliver
   enum { F = 0, C = 1, U = 2, V = 3, D = 4, SCI = 5, SC = 6, MSK = 7 };
 };
 
@@ -51,6 +58,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint32_t bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
@@ -64,53 +74,67 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// wait for the row in a slot; a request that never completes (bad descriptor) traps instead
-// of hanging the device
+// wait for the row in a slot (one try site); a request that never completes (bad descriptor)
+// traps instead of hanging the device
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  for (int spin = 0; !mbar_try(bar, parity); ++spin)
-    if (spin > (1 << 16)) __trap();
+  int spin = 0;
+  while (!mbar_try(bar, parity))
+    if (++spin > (1 << 16)) __trap();
 }
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned),
-// completion on the mbarrier
+// descriptor-less global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned),
+// completion on the mbarrier (SASS UBLKCP; the diffusion kernel still stages its rows this way)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// one box of a 3-D tensor map (col, row, layer) global -> shared, completion on the mbarrier
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tmap_acquire(const CUtensorMap* map) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
+}
 
 struct TmaCtx {
-  // slabs of this (field, layer): element (row 0, column w0) of each staged array
-  const double *fld, *fldc, *u, *v, *dp, *sci, *sc, *msk;
-  double* __restrict__ out;
+  // tensor maps (device global memory) of the staged arrays and of the output slab, and the layer
+  // coordinate of this unit in each of them
+  const CUtensorMap *m_fld, *m_fldc, *m_u, *m_v, *m_dp, *m_sci, *m_sc, *m_msk;
+  int kf, kuv, kdp;      // layer of fld/fldc, of uflx/vflx, of dp
+  double* out;           // the output slab (ping-pong buffer) of this layer
+  int pitch;
   unsigned char* ring;   // this warp's ring (generic pointer into shared memory)
   uint32_t ring_s;       // same, shared-window address
   uint32_t bar_s;        // six mbarriers of this warp
-  int pitch, nrows;
-  int w0;                // first staged column (even: 16-byte aligned requests)
+  int w0;                // first staged column (even: 16-byte aligned rows)
   int lane;
   int j0, j1;
   double dt2, qdt2x2;
   double posdef;         // MPDATA offset (mod_tsadvc.F90:1762)
 };
 
-// request row r of every staged array into slot `slot` (one lane)
+// request row r of every staged array into the slot at byte offset `soff` of the ring (one lane)
 template <int NC, bool NEED_C, bool NEED_M = true>
-__device__ __forceinline__ void issue_row(const TmaCtx& x, int r, int slot) {
+__device__ __forceinline__ void issue_row(const TmaCtx& x, int r, uint32_t soff, uint32_t bar) {
   typedef Ring<NC> R;
-  const uint32_t bar = x.bar_s + 8u * slot;
-  const uint32_t dst = x.ring_s + (uint32_t)(slot * R::SLOT);
-  const long off = (long)max(0, min(r, x.nrows - 1)) * x.pitch;
-  mbar_expect_tx(bar, R::TX - (NEED_C ? 0 : R::RB) - (NEED_M ? 0 : R::RB));
-  bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
-  if (NEED_C) bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
-  bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
-  bulk_g2s(dst + R::V * R::RB, x.v + off, R::RB, bar);
-  bulk_g2s(dst + R::D * R::RB, x.dp + off, R::RB, bar);
-  bulk_g2s(dst + R::SCI * R::RB, x.sci + off, R::RB, bar);
-  bulk_g2s(dst + R::SC * R::RB, x.sc + off, R::RB, bar);
-  if (NEED_M) bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);   // the mask-free bodies never read it
+  const uint32_t dst = x.ring_s + soff;
+  mbar_expect_tx(bar, R::SLOT - (NEED_C ? 0 : R::RB) - (NEED_M ? 0 : R::RB));
+  tma_load(dst + R::F * R::RB, x.m_fld, x.w0, r, x.kf, bar);
+  if (NEED_C) tma_load(dst + R::C * R::RB, x.m_fldc, x.w0, r, x.kf, bar);
+  tma_load(dst + R::U * R::RB, x.m_u, x.w0, r, x.kuv, bar);
+  tma_load(dst + R::V * R::RB, x.m_v, x.w0, r, x.kuv, bar);
+  tma_load(dst + R::D * R::RB, x.m_dp, x.w0, r, x.kdp, bar);
+  tma_load(dst + R::SCI * R::RB, x.m_sci, x.w0, r, 0, bar);
+  tma_load(dst + R::SC * R::RB, x.m_sc, x.w0, r, 0, bar);
+  if (NEED_M) tma_load(dst + R::MSK * R::RB, x.m_msk, x.w0, r, 0, bar);   // the mask-free bodies never read it
 }
 
 // per-lane views of the ring: own columns, west neighbour of the first own column, east
@@ -118,7 +142,36 @@ __device__ __forceinline__ void issue_row(const TmaCtx& x, int r, int slot) {
 struct RingPtr {
   const unsigned char *c, *w, *e;
   const unsigned char* w2;   // two columns west of the first own column (advem_fct4)
+  // output: this lane's first cell in the row being finished, and what the lane may store there
+  double* outp;
+  bool rowok;                // the finished row lies inside j0..j1-1 (warp-uniform)
+  bool st2, stx, sty;        // both cells / only the first / only the second belong to the strip interior
 };
+
+// The finished row: new values on the cells tsadvc writes (M_OUT), the old value everywhere else
+// (land, halo ring), so the ping-pong slab is complete.  Only the strip interior (columns w0+3 ..
+// w0+32*NC-4, inside the slab) is written by this warp: lanes with both cells inside store 16 bytes,
+// the two edge lanes 8.
+template <int NC>
+__device__ __forceinline__ void store_cells(const RingPtr& p, const double (&o)[NC]) {
+  if (p.rowok) {
+    if (NC == 2) {
+      if (p.st2) asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p.outp), "d"(o[0]), "d"(o[NC - 1]) : "memory");
+      if (p.stx) asm volatile("st.global.f64 [%0], %1;" ::"l"(p.outp), "d"(o[0]) : "memory");
+      if (p.sty) asm volatile("st.global.f64 [%0+8], %1;" ::"l"(p.outp), "d"(o[NC - 1]) : "memory");
+    } else {
+      if (p.stx) asm volatile("st.global.f64 [%0], %1;" ::"l"(p.outp), "d"(o[0]) : "memory");
+    }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void store_row_masked(const RingPtr& p, unsigned m, const double (&old)[NC],
+                                                 const double (&nv)[NC]) {
+  double o[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) o[c] = (mk(m, c) & M_OUT) ? nv[c] : old[c];
+  store_cells<NC>(p, o);
+}
 
 template <int NC, int ARR>
 __device__ __forceinline__ void ld_own(const RingPtr& p, int slot, double (&x)[NC]) {
@@ -164,6 +217,7 @@ __device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, int slot) {
   if (NC == 2) m |= *reinterpret_cast<const unsigned*>(a + 8) << 8;
   return m;
 }
+
 
 
 // The same accessors for a slot given by its byte offset in the ring at run time (a scheme whose
@@ -235,56 +289,78 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
   bool bad = false;
   const int r0 = x.j0 - 3;
   const int niter = ((x.j1 - x.j0) + 6 + 5) / 6 * 6;   // rows j0-3 .. j1+2, whole rounds of six
+  const int nstore = x.j1 - x.j0;
   // rows r0-3..r0-1 are "below the chunk": zeros with an all-land mask (never stored)
   {
     double* z = reinterpret_cast<double*>(x.ring + 3 * R::SLOT);
     for (int i = x.lane; i < 3 * R::SLOT / 8; i += 32) z[i] = 0.0;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_proxy_async();
     __syncwarp();
   }
   if (elect_one()) {
-    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0, 0);
-    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 1, 1);
-    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 2, 2);
+    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0, 0, x.bar_s);
+    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 1, R::SLOT, x.bar_s + 8);
+    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 2, 2 * R::SLOT, x.bar_s + 16);
   }
+  // this lane's output pointer walks down the slab one row per iteration (row r - kLag)
+  RingPtr q = p;
+  q.outp = x.out + ((long)(r0 - S::kLag) * x.pitch + x.w0 + NC * x.lane);
+  const long ostep = x.pitch;
+  // after step(row r): request row r+3 into the slot row r-3 has left (no end-of-chunk test: the three
+  // rows past the chunk are drained below)
+#define TSADVC_ROW_TAIL(ROW, SOFF3, BAR3)                                                      \
+  __syncwarp();                                                                              \
+  if (elect_one()) issue_row<NC, S::kNeedC, S::kNeedM>(x, (ROW) + 3, SOFF3, BAR3);           \
+  q.outp += ostep;
+#define TSADVC_ROW_HEAD(ROW) q.rowok = (unsigned)((ROW) - S::kLag - x.j0) < (unsigned)nstore;
   if constexpr (S::kPeriod == 3) {
-    int slot = 0;                        // slot of row r; rows r-1..r-3 sit in slot-1..slot-3 (mod 6)
-    uint32_t par = round & 1u;           // parity the barrier of that slot completes next
-    SlotOff so{{0}, {5 * R::SLOT}, {4 * R::SLOT}, {3 * R::SLOT}};
-#define TSADVC_PHASE3(PH)                                                                 \
-  {                                                                                       \
-    mbar_wait(x.bar_s + 8u * slot, par);                                                  \
-    S::template step<PH, SAFE>(s, x, p, r0 + t + (PH), so, bad);                          \
-    __syncwarp();                                                                         \
-    const int slot3 = slot >= 3 ? slot - 3 : slot + 3;   /* row r-3: free now */           \
-    if (t + (PH) + 3 < niter && elect_one())                                              \
-      issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + t + (PH) + 3, slot3);                              \
-    so.s3 = so.s2; so.s2 = so.s1; so.s1 = so.s0;                                          \
-    slot = slot == 5 ? 0 : slot + 1;                                                      \
-    par ^= (slot == 0) ? 1u : 0u;                                                         \
-    so.s0.b = slot * R::SLOT;                                                             \
+    // The loop is unrolled three times over a ring of six slots: in one trip the rows r sit in slots
+    // PH + 3*half, the older rows partly in the other half.  Two warp-uniform byte offsets (hb: this
+    // half, hc: the other) that swap once per trip make every slot address "register + constant".
+    uint32_t hb = 0, hc = 3 * R::SLOT;         // ring offsets of slot 0 / 3 of the two halves
+    uint32_t bb = x.bar_s, bc = x.bar_s + 24;  // mbarriers of the two halves
+    uint32_t par = round & 1u;                 // parity the barriers of this round complete with
+#define TSADVC_PHASE3(PH)                                                                     \
+  {                                                                                           \
+    const SlotOff so{{(int)(hb + (PH) * R::SLOT)},                                            \
+                     {(int)((PH) >= 1 ? hb + ((PH) - 1) * R::SLOT : hc + 2 * R::SLOT)},       \
+                     {(int)((PH) == 2 ? hb : hc + ((PH) + 1) * R::SLOT)},                     \
+                     {(int)(hc + (PH) * R::SLOT)}};                                           \
+    TSADVC_ROW_HEAD(r0 + t + (PH))                                                            \
+    mbar_wait(bb + 8u * (PH), par);                                                           \
+    S::template step<PH, SAFE>(s, x, q, r0 + t + (PH), so, bad);                              \
+    TSADVC_ROW_TAIL(r0 + t + (PH), hc + (PH) * R::SLOT, bc + 8u * (PH))                       \
   }
-    for (int t = 0; t < niter; t += 3) { TSADVC_PHASE3(0) TSADVC_PHASE3(1) TSADVC_PHASE3(2) }
+    for (int t = 0; t < niter; t += 3) {
+      TSADVC_PHASE3(0) TSADVC_PHASE3(1) TSADVC_PHASE3(2)
+      par ^= (hb != 0) ? 1u : 0u;               // the second half closes a round of six
+      const uint32_t th = hb; hb = hc; hc = th;
+      const uint32_t tb = bb; bb = bc; bc = tb;
+    }
 #undef TSADVC_PHASE3
     round += (uint32_t)(niter / 6);
-    return bad;
   } else {
 #define TSADVC_PHASE(PH)                                                                  \
   {                                                                                       \
+    TSADVC_ROW_HEAD(r0 + t + (PH))                                                        \
     mbar_wait(x.bar_s + 8u * (PH), round & 1u); /* row r has landed in slot PH */          \
-    S::template step<PH, SAFE>(s, x, p, r0 + t + (PH), bad);                              \
-    /* the slot of row r-3 is free now: request row r+3 into it */                        \
-    __syncwarp();                                                                         \
-    if (t + (PH) + 3 < niter && elect_one())                                              \
-      issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + t + (PH) + 3, ((PH) + 3) % 6);                     \
+    S::template step<PH, SAFE>(s, x, q, r0 + t + (PH), bad);                              \
+    TSADVC_ROW_TAIL(r0 + t + (PH), (((PH) + 3) % 6) * R::SLOT, x.bar_s + 8u * (((PH) + 3) % 6)) \
   }
-  for (int t = 0; t < niter; t += 6) {
-    TSADVC_PHASE(0) TSADVC_PHASE(1) TSADVC_PHASE(2) TSADVC_PHASE(3) TSADVC_PHASE(4) TSADVC_PHASE(5)
-    ++round;
-  }
+    for (int t = 0; t < niter; t += 6) {
+      TSADVC_PHASE(0) TSADVC_PHASE(1) TSADVC_PHASE(2) TSADVC_PHASE(3) TSADVC_PHASE(4) TSADVC_PHASE(5)
+      ++round;
+    }
 #undef TSADVC_PHASE
-  return bad;
   }
+#undef TSADVC_ROW_TAIL
+#undef TSADVC_ROW_HEAD
+  // rows niter .. niter+2 were requested past the end of the chunk (no test in the loop): let them land
+  // before the ring is reused; the three barriers are then one phase ahead of the other three
+  mbar_wait(x.bar_s, round & 1u);
+  mbar_wait(x.bar_s + 8, round & 1u);
+  mbar_wait(x.bar_s + 16, round & 1u);
+  return bad;
 }
 
 // the whole chunk again with the compiler's a/b: taken by a warp only when one of its lanes
@@ -292,6 +368,20 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
 template <class S, int NC>
 __device__ __noinline__ void march_tma_safe(const TmaCtx x, const RingPtr p, uint32_t round) {
   march_tma_pass<S, NC, true>(x, p, round);
+}
+
+template <int NC>
+__device__ __forceinline__ void ring_barriers_init(const TmaCtx& x, bool again) {
+  typedef Ring<NC> R;
+  if (x.lane == 0) {
+#pragma unroll
+    for (int q = 0; q < R::NSLOT; ++q) {
+      if (again) mbar_inval(x.bar_s + 8u * q);
+      mbar_init(x.bar_s + 8u * q, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
 }
 
 template <class S, int NC>
@@ -303,15 +393,25 @@ __device__ void march_tma(const TmaCtx& x) {
   p.w = x.ring + 8 * max(l0 - 1, 0);
   p.e = x.ring + 8 * min(l0 + NC, 32 * NC - 1);
   p.w2 = x.ring + 8 * max(l0 - 2, 0);
-  if (x.lane == 0) {
-#pragma unroll
-    for (int q = 0; q < R::NSLOT; ++q) mbar_init(x.bar_s + 8u * q, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {  // which of this lane's cells belong to the strip interior and to the slab
+    const int lo = kApron, hi = 32 * NC - kApron;                  // interior columns [lo, hi) of the window
+    const bool in0 = l0 >= lo && l0 < hi && (unsigned)(x.w0 + l0) < (unsigned)x.pitch;
+    const bool in1 = NC == 2 && l0 + 1 >= lo && l0 + 1 < hi && (unsigned)(x.w0 + l0 + 1) < (unsigned)x.pitch;
+    p.st2 = in0 && in1; p.stx = in0 && !in1; p.sty = in1 && !in0;
+    p.outp = nullptr; p.rowok = false;
+  }
+  ring_barriers_init<NC>(x, false);
+  if (x.lane == 0) {   // descriptors were written by the host before the launch
+    tmap_acquire(x.m_fld); tmap_acquire(x.m_fldc); tmap_acquire(x.m_u); tmap_acquire(x.m_v); tmap_acquire(x.m_dp);
+    tmap_acquire(x.m_sci); tmap_acquire(x.m_sc); tmap_acquire(x.m_msk);
   }
   __syncwarp();
   uint32_t round = 0;
   const bool bad = march_tma_pass<S, NC, false>(x, p, round);
-  if (__any_sync(TSADVC_FULLMASK, bad)) march_tma_safe<S, NC>(x, p, round);
+  if (__any_sync(TSADVC_FULLMASK, bad)) {
+    ring_barriers_init<NC>(x, true);
+    march_tma_safe<S, NC>(x, p, 0u);
+  }
 }
 
 }  // namespace tsadvc

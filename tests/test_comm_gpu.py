@@ -143,7 +143,7 @@ HOST_CASES = [
     (2, 1, 3, 0, 2, {"temdf2": 0.02, "temdfc": 0.5, "sigver": 8}),
     (2, 2, 0, 1, 2, {"btrmas": True}),                                   # advem_fct2c: five in-scheme exchanges
     (1, 2, 1, 0, 2, {"btrmas": True}),
-    (2, 2, 0, 0, 2, {"isopyc": True}),                                   # smoothed layer-1 fluxes read the halo
+    (2, 2, 0, 0, 2, {"isopyc": True, "hybrid": False, "nhybrd": 0}),     # smoothed layer-1 fluxes read the halo
 ]
 
 
@@ -178,6 +178,8 @@ def test_host_array_step_on_tiles(oracle, ipr, jpr, nreg, ntracr, advtyp, extra,
     run_tiles(tss, lambda ts, r: ts.tsadvc(m, n))
     nb = g1.nbdy
     names = ["temp", "saln"] + (["th3d"] if diff else [])
+    if extra.get("isopyc"):
+        names = ["saln", "th3d"]        # th3d & saln in layer 1 on the smoothed fluxes, saln only below
     for ts in tss:   # the host arrays hold the result on 1:ii,1:jj
         g, cb = ts.cb.geom, ts.cb
         sea_t = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0

@@ -50,6 +50,9 @@ for STEP in "$@"; do
     tma)
       (cd tools/probe && nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe4 tma_probe4.cu -lcuda 2>/dev/null)
       for v in 0 1 2 3 4; do timeout 60 tools/probe/tma_probe4 $v; echo "exit=$?"; done > $OUT/tma_probe4.txt 2>&1; cat $OUT/tma_probe4.txt ;;
+    tma5)
+      (cd tools/probe && nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe5 tma_probe5.cu -lcuda 2>/dev/null)
+      for args in "0 2 58 0" "0 18 58 0" "0 34 58 0" "0 2 64 0" "0 2 32 0" "0 2 58 1" "0 2 58 2" "0 2 64 2" "0 3 64 1"; do timeout 60 tools/probe/tma_probe5 $args; echo "exit=$?"; done > $OUT/tma_probe5.txt 2>&1; cat $OUT/tma_probe5.txt ;;
     nccl)
       timeout 900 $TR --nproc-per-node $NGPU tools/xc_nccl_check.py > $OUT/xc_nccl_check_n$NGPU.log 2>&1; echo "rc=$?" >> $OUT/xc_nccl_check_n$NGPU.log; grep -v "^W\|^\[W\|warn" $OUT/xc_nccl_check_n$NGPU.log | tail -8
       if [ -n "$XC_TILES" ]; then XC_CHECK_TILES=$XC_TILES XC_CHECK_CASES=arctic timeout 600 $TR --nproc-per-node $NGPU tools/xc_nccl_check.py > $OUT/xc_nccl_check_$XC_TILES.log 2>&1; echo "rc=$?" >> $OUT/xc_nccl_check_$XC_TILES.log; tail -3 $OUT/xc_nccl_check_$XC_TILES.log; fi ;;

@@ -54,7 +54,7 @@ def main():
         if "btrmas" in extra:
             scal["btrmas"] = True
         if "isopyc" in extra:
-            scal["isopyc"] = True
+            scal.update(isopyc=True, hybrid=False, nhybrd=0)
         if "diffusion_arctic" in extra:
             scal.update(temdf2=0.02, temdfc=1.0, sigver=6, thbase=34.0)
         if "diffusion" in extra:
@@ -122,7 +122,7 @@ def main():
                 print(f"rank {rank}: MISMATCH xmin/xmax step {step} case {(itdm, jtdm, nreg, advtyp, extra)}", flush=True)
             sea_t = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
             glob = (slice(None), slice(nb + g.j0, nb + g.j0 + g.jj), slice(nb + g.i0, nb + g.i0 + g.ii))
-            flds = ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")) + (((cabi.F_TH3D, "th3d"),) if ("diffusion" in extra or "diffusion_arctic" in extra) else ())
+            flds = ((cabi.F_TH3D, "th3d"), (cabi.F_SALN, "saln")) if "isopyc" in extra else ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")) + (((cabi.F_TH3D, "th3d"),) if ("diffusion" in extra or "diffusion_arctic" in extra) else ())
             for fld, name in flds:
                 src = getattr(cb, name)[nn - 1] if "host" in extra else ts.download(fld, nn)
                 dev = src[:, nb:nb + g.jj, nb:nb + g.ii]
