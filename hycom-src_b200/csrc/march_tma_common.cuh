@@ -2,31 +2,33 @@
 //
 // Row pipeline: stage A works on row r, B on row r-1, C/D on row r-2, E on row r-3.
 // The RAW rows (fld, fldc, uflx, vflx, dp, scp2i, scp2, masks) are not carried in registers:
-// each warp owns a ring of six row slots in shared memory that the TMA engine fills from 3-D
-// tensor maps (col, row, layer) - cp.async.bulk.tensor, SASS UTMALDG: one 32*NC-column box per
-// array and row, coordinates instead of 64-bit address arithmetic, completion counted in bytes
-// on one mbarrier per slot.  Row r+3 is requested at the end of iteration r, into the slot of
-// row r-3 that iteration r has just finished with, so three rows are always in flight and the
-// prefetch distance does not depend on the instruction scheduler.  i-neighbours of raw data are
-// plain shared-memory reads at lane-1 / lane+1; j-neighbours are older slots.  Rows and columns
-// outside the slab (apron of the first/last chunk or strip) are zero-filled by the TMA engine:
-// finite data that only ever feeds apron lanes (dependency radius 3 < nbdy).  Nothing is
-// predicated.  Only computed intermediates stay in register rings indexed by (row mod 2) or
+// each warp owns a ring of six row slots in shared memory that the TMA engine fills
+// (cp.async.bulk global->shared, SASS UBLKCP: one 256*NC-byte request per array and row,
+// completion counted in bytes on one mbarrier per slot).  Row r+3 is requested at the end of
+// iteration r, into the slot of row r-3 that iteration r has just finished with, so three rows
+// are always in flight and the prefetch distance does not depend on the instruction scheduler.
+// The source addresses are eight slab pointers plus one warp-uniform offset that advances by one
+// row per request (no per-row index arithmetic).  i-neighbours of raw data are plain shared-memory reads at lane-1 /
+// lane+1; j-neighbours are older slots.  Rows outside the slab (apron of the first/last chunk)
+// are clamped to the nearest row; the window of the first/last strip may start 4 columns before /
+// end after its row, i.e. in the neighbouring row or in the guard row every buffer is allocated
+// with: real, finite data that only ever feeds apron lanes (dependency radius 3 < nbdy).  Nothing
+// is predicated.  Only computed intermediates stay in register rings indexed by (row mod 2) or
 // (row mod 3).
 // The finished row is stored straight from registers through one per-lane pointer that advances by
 // a row per iteration (predicated 16-byte stores, no branches, no per-row 64-bit index arithmetic).
-// (A TMA store of the row was tried first: the strip interior starts at the odd column w0+3, and a
-// box whose first element is not 16-byte aligned in global memory raises "illegal instruction" -
-// loads and stores alike, which is also what round 1's probe hit with its column 3;
-// profiles/r02c_tma_probe5.txt.  Loads start at the even column w0.)
-// (Round 1 believed the tensor-map form traps on this pool: its probe fetched
-// cuTensorMapEncodeTiled with the default driver entry point, which on the CUDA 13 driver of the
-// boxes is not the CUDA 12 ABI the runtime headers describe; with
-// cudaGetDriverEntryPointByVersion(..., 12000) every variant works: profiles/r02a_tma_probe4.txt.
-// Per-instruction stall samples of the old address arithmetic: profiles/r02a_*_stalls.txt.)
+//
+// What was measured on the way (profiles/r02a_*, r02c_*, r02e_*):
+//  * the tensor-map form of TMA (cp.async.bulk.tensor, UTMALDG) does work on this pool - round 1's
+//    "illegal instruction" came from a box whose first element is not 16-byte aligned in global
+//    memory (its probe started at column 3; fp64 boxes must start at an even column, loads and
+//    stores alike) - but it is the more expensive way to fetch single rows: per-instruction stall
+//    samples put 19 % of the warps' time on the seven UTMALDG of a row and the uniform-register
+//    hand-over behind them (635 samples per UTMALDG against 105 per UBLKCP and 57 per FSEL), and
+//    the kernel was no faster than with UBLKCP although it issued 9 % fewer instructions;
+//  * a TMA store of the finished row needs the strip interior to start at an even column (it
+//    starts at w0+3): not possible without giving up 2 of the 58 useful columns.
 #pragma once
-#include <cuda.h>
-
 #include "march_common.cuh"
 #include "tsadvc_launch.h"
 
@@ -89,52 +91,54 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-// one box of a 3-D tensor map (col, row, layer) global -> shared, completion on the mbarrier
-__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                         uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void tmap_acquire(const CUtensorMap* map) {
-  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
-}
-
 struct TmaCtx {
-  // tensor maps (device global memory) of the staged arrays and of the output slab, and the layer
-  // coordinate of this unit in each of them
-  const CUtensorMap *m_fld, *m_fldc, *m_u, *m_v, *m_dp, *m_sci, *m_sc, *m_msk;
-  int kf, kuv, kdp;      // layer of fld/fldc, of uflx/vflx, of dp
+  // slabs of this (field, layer): element (row 0, column w0) of each staged array
+  const double *fld, *fldc, *u, *v, *dp, *sci, *sc, *msk;
   double* out;           // the output slab (ping-pong buffer) of this layer
-  int pitch;
   unsigned char* ring;   // this warp's ring (generic pointer into shared memory)
   uint32_t ring_s;       // same, shared-window address
   uint32_t bar_s;        // six mbarriers of this warp
-  int w0;                // first staged column (even: 16-byte aligned rows)
+  int pitch, nrows;
+  int w0;                // first staged column (even: 16-byte aligned requests)
   int lane;
   int j0, j1;
   double dt2, qdt2x2;
   double posdef;         // MPDATA offset (mod_tsadvc.F90:1762)
 };
 
-// request row r of every staged array into the slot at byte offset `soff` of the ring (one lane)
+// the source row of the next request: one warp-uniform element offset that walks down the slabs
+struct RowSrc {
+  long off;              // offset of row clamp(r, 0, nrows-1) from row 0
+  int r;
+};
+__device__ __forceinline__ RowSrc row_src(const TmaCtx& x, int r) {
+  return RowSrc{(long)max(0, min(r, x.nrows - 1)) * x.pitch, r};
+}
+
+// request the row of `g` into the slot at byte offset `soff` of the ring (one lane)
 template <int NC, bool NEED_C, bool NEED_M = true>
-__device__ __forceinline__ void issue_row(const TmaCtx& x, int r, uint32_t soff, uint32_t bar) {
+__device__ __forceinline__ void issue_row(const TmaCtx& x, const RowSrc& g, uint32_t soff, uint32_t bar) {
   typedef Ring<NC> R;
   const uint32_t dst = x.ring_s + soff;
+  const long off = g.off;
   mbar_expect_tx(bar, R::SLOT - (NEED_C ? 0 : R::RB) - (NEED_M ? 0 : R::RB));
-  tma_load(dst + R::F * R::RB, x.m_fld, x.w0, r, x.kf, bar);
-  if (NEED_C) tma_load(dst + R::C * R::RB, x.m_fldc, x.w0, r, x.kf, bar);
-  tma_load(dst + R::U * R::RB, x.m_u, x.w0, r, x.kuv, bar);
-  tma_load(dst + R::V * R::RB, x.m_v, x.w0, r, x.kuv, bar);
-  tma_load(dst + R::D * R::RB, x.m_dp, x.w0, r, x.kdp, bar);
-  tma_load(dst + R::SCI * R::RB, x.m_sci, x.w0, r, 0, bar);
-  tma_load(dst + R::SC * R::RB, x.m_sc, x.w0, r, 0, bar);
-  if (NEED_M) tma_load(dst + R::MSK * R::RB, x.m_msk, x.w0, r, 0, bar);   // the mask-free bodies never read it
+  bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
+  if (NEED_C) bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
+  bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
+  bulk_g2s(dst + R::V * R::RB, x.v + off, R::RB, bar);
+  bulk_g2s(dst + R::D * R::RB, x.dp + off, R::RB, bar);
+  bulk_g2s(dst + R::SCI * R::RB, x.sci + off, R::RB, bar);
+  bulk_g2s(dst + R::SC * R::RB, x.sc + off, R::RB, bar);
+  if (NEED_M) bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);   // the mask-free bodies never read it
+}
+// step to the next row (every lane: the offset stays warp-uniform); rows outside the slab repeat the
+// nearest one
+__device__ __forceinline__ void next_row(const TmaCtx& x, RowSrc& g) {
+  g.off += ((unsigned)g.r < (unsigned)(x.nrows - 1)) ? (long)x.pitch : 0L;
+  g.r += 1;
 }
 
 // per-lane views of the ring: own columns, west neighbour of the first own column, east
@@ -297,10 +301,11 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     fence_proxy_async();
     __syncwarp();
   }
-  if (elect_one()) {
-    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0, 0, x.bar_s);
-    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 1, R::SLOT, x.bar_s + 8);
-    issue_row<NC, S::kNeedC, S::kNeedM>(x, r0 + 2, 2 * R::SLOT, x.bar_s + 16);
+  RowSrc g = row_src(x, r0);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (elect_one()) issue_row<NC, S::kNeedC, S::kNeedM>(x, g, q * R::SLOT, x.bar_s + 8u * q);
+    next_row(x, g);
   }
   // this lane's output pointer walks down the slab one row per iteration (row r - kLag)
   RingPtr q = p;
@@ -310,7 +315,8 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
   // rows past the chunk are drained below)
 #define TSADVC_ROW_TAIL(ROW, SOFF3, BAR3)                                                      \
   __syncwarp();                                                                              \
-  if (elect_one()) issue_row<NC, S::kNeedC, S::kNeedM>(x, (ROW) + 3, SOFF3, BAR3);           \
+  if (elect_one()) issue_row<NC, S::kNeedC, S::kNeedM>(x, g, SOFF3, BAR3);                   \
+  next_row(x, g);                                                      \
   q.outp += ostep;
 #define TSADVC_ROW_HEAD(ROW) q.rowok = (unsigned)((ROW) - S::kLag - x.j0) < (unsigned)nstore;
   if constexpr (S::kPeriod == 3) {
@@ -401,11 +407,6 @@ __device__ void march_tma(const TmaCtx& x) {
     p.outp = nullptr; p.rowok = false;
   }
   ring_barriers_init<NC>(x, false);
-  if (x.lane == 0) {   // descriptors were written by the host before the launch
-    tmap_acquire(x.m_fld); tmap_acquire(x.m_fldc); tmap_acquire(x.m_u); tmap_acquire(x.m_v); tmap_acquire(x.m_dp);
-    tmap_acquire(x.m_sci); tmap_acquire(x.m_sc); tmap_acquire(x.m_msk);
-  }
-  __syncwarp();
   uint32_t round = 0;
   const bool bad = march_tma_pass<S, NC, false>(x, p, round);
   if (__any_sync(TSADVC_FULLMASK, bad)) {

@@ -145,51 +145,6 @@ int spare_of(hycom_tsadvc_handle* h, Mirror* mi, double** out) {
   return 0;
 }
 
-// index of the tensor map of `nlay` slabs starting at `base`, box = boxw columns x 1 row x 1 layer.
-// cuTensorMapEncodeTiled is taken from the driver by version (12000: the ABI of this toolkit's cuda.h;
-// the boxes run a CUDA 13 driver whose default entry point is a newer one) - no link against libcuda.
-typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int tmap_of(hycom_tsadvc_handle* h, const double* base, int nlay, int boxw, int* idx) {
-  const auto key = std::make_tuple((const void*)base, nlay, boxw);
-  auto it = h->tmap_index.find(key);
-  if (it != h->tmap_index.end()) { *idx = it->second; return 0; }
-  static TmapEncodeFn enc = nullptr;
-  if (!enc) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &q);
-    if (e != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess)
-      return fail(h, HYCOM_TSADVC_ECUDA, "cuTensorMapEncodeTiled is not available from the driver: %s",
-                  e != cudaSuccess ? cudaGetErrorString(e) : "symbol not found");
-    enc = (TmapEncodeFn)fn;
-  }
-  if ((int)h->tmap_host.size() >= hycom_tsadvc_handle::kMaxTmaps)
-    return fail(h, HYCOM_TSADVC_ENOMEM, "tensor-map table full (%d)", hycom_tsadvc_handle::kMaxTmaps);
-  if (!h->tmap_dev) {
-    int rc = dalloc(h, (void**)&h->tmap_dev, sizeof(CUtensorMap) * hycom_tsadvc_handle::kMaxTmaps, false);
-    if (rc) return rc;
-    h->tmap_host.reserve(hycom_tsadvc_handle::kMaxTmaps);   // entries never move: async copies read them
-  }
-  alignas(64) CUtensorMap m;
-  const cuuint64_t gd[3] = {(cuuint64_t)h->pitch, (cuuint64_t)h->nrows, (cuuint64_t)nlay};
-  const cuuint64_t gs[2] = {(cuuint64_t)h->pitch * 8, (cuuint64_t)h->slab * 8};
-  const cuuint32_t box[3] = {(cuuint32_t)boxw, 1, 1}, es[3] = {1, 1, 1};
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(h, HYCOM_TSADVC_ECUDA, "cuTensorMapEncodeTiled failed: %d (base %p, %d x %d x %d, box %d)", (int)r,
-                (const void*)base, h->pitch, h->nrows, nlay, boxw);
-  const int i = (int)h->tmap_host.size();
-  h->tmap_host.push_back(m);
-  // ordered before the launches that use it: every stream of the handle is synchronised behind this copy
-  CU(h, cudaMemcpy(h->tmap_dev + i, &h->tmap_host[i], sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  h->tmap_index[key] = i;
-  *idx = i;
-  return 0;
-}
-
 int up2d(hycom_tsadvc_handle* h, double** dst, const double* src) {
   if (!*dst) {
     int rc = dalloc(h, (void**)dst, sizeof(double) * (size_t)h->slab, true);
@@ -745,17 +700,16 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   // (profiles/r01p_variants.txt): FCT2 and MPDATA 2 cells per lane at 2 blocks per SM (11.8 warp-
   // instructions per useful cell against 15.4 with one cell per lane), FCT4 and PCM 1 cell per lane
   P.nc = (aadv == 0 || aadv == 4) ? 1 : cn ? (atoi(cn) == 2 ? 2 : 1) : 2;
-  const int boxw = 32 * P.nc;
+  const long koff = h->slab * k0;
   for (int f = 0; f < P.nfld; ++f) {
     double *in, *ctr, *out;
     if ((rc = slot(h, adv[f].field, adv[f].ktr, n, &in))) return rc;
     if ((rc = slot(h, adv[f].field, adv[f].ktr, m, &ctr))) return rc;
     if ((rc = spare_of(h, mirror_of(h, adv[f].field, adv[f].ktr), &out))) return rc;
-    const int nsl = nlayers_of(h, adv[f].field);
-    if ((rc = tmap_of(h, in, nsl, boxw, &P.fld[f].map_in))) return rc;
-    if ((rc = tmap_of(h, ctr, nsl, boxw, &P.fld[f].map_ctr))) return rc;
-    P.fld[f].kbase = k0 + adv[f].koff;
-    P.fld[f].out = out + h->slab * (k0 + adv[f].koff);
+    const long kf = koff + h->slab * adv[f].koff;
+    P.fld[f].fld = in + kf;
+    P.fld[f].fldc = ctr + kf;
+    P.fld[f].out = out + kf;
     P.fld[f].posdef = adv[f].posdef;
     const int nl = adv[f].nlay - k0;
     P.fld[f].nlay = nl < 0 ? 0 : (nl > kk ? kk : nl);
@@ -764,18 +718,8 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   if ((rc = slot(h, HYCOM_F_UFLX, 0, 1, &u))) return rc;
   if ((rc = slot(h, HYCOM_F_VFLX, 0, 1, &v))) return rc;
   if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
-  if (u_over) {   // isopyc layer 1: the smoothed fluxes, prolog included (:1930-1932); one slab each
-    if ((rc = tmap_of(h, u_over, 1, boxw, &P.map_u)) || (rc = tmap_of(h, v_over, 1, boxw, &P.map_v))) return rc;
-    P.k_uv = 0;
-  } else {
-    if ((rc = tmap_of(h, u, h->d.kdm, boxw, &P.map_u)) || (rc = tmap_of(h, v, h->d.kdm, boxw, &P.map_v))) return rc;
-    P.k_uv = k0;
-  }
-  if ((rc = tmap_of(h, dpn, h->d.kdm, boxw, &P.map_dp))) return rc;
-  P.k_dp = k0;
-  if ((rc = tmap_of(h, h->scp2i, 1, boxw, &P.map_sci)) || (rc = tmap_of(h, h->scp2, 1, boxw, &P.map_sc)) ||
-      (rc = tmap_of(h, h->static_block + 2 * h->slab, 1, boxw, &P.map_msk))) return rc;
-  P.maps = h->tmap_dev;
+  P.u = u + koff; P.v = v + koff; P.dp = dpn + koff;
+  if (u_over) { P.u = u_over; P.v = v_over; }   // isopyc layer 1: the smoothed fluxes, prolog included (:1930-1932)
   P.slab = h->slab;
   P.njobs = P.nfld * kk;
   P.g.pitch = h->pitch; P.g.ncols = h->ncols; P.g.nrows = h->nrows; P.g.nbdy = h->d.nbdy;

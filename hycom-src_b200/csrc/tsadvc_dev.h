@@ -25,15 +25,13 @@ enum MaskBits : unsigned {
 };
 
 // one advected field: every layer k < nlay is one call of advem
-// (mod_tsadvc.F90:1969-2034).  The slabs are addressed through 3-D tensor maps (col, row, layer) of
-// the handle's table: (:,:,:,n) on entry = time level t-1, (:,:,:,m) = t (unused by MPDATA/PCM); the
-// ping-pong buffer that receives t+1 is written with ordinary stores.
+// (mod_tsadvc.F90:1969-2034)
 struct FieldDesc {
-  int map_in, map_ctr;            // indices into MarchParams::maps
-  int kbase;                      // layer coordinate of the launch's first layer in those buffers
-  double* out;                    // slab of that layer in the ping-pong buffer
-  double posdef;                  // MPDATA offset (mod_tsadvc.F90:1762)
-  int nlay;                       // layers 1..nlay are advected (temp: nhybrd, :1855)
+  const double* fld;   // (:,:,1,n) on entry: time level t-1
+  const double* fldc;  // (:,:,1,m): time level t (unused by MPDATA/PCM)
+  double* out;         // (:,:,1,n) of the ping-pong buffer: time level t+1
+  double posdef;       // MPDATA offset (mod_tsadvc.F90:1762)
+  int nlay;            // layers 1..nlay are advected (temp: nhybrd, :1855)
   int pad;
 };
 constexpr int kMaxFields = 2 + 16;

@@ -1,6 +1,5 @@
 // private: the handle behind hycom_tsadvc_handle* (shared by tsadvc_abi.cu and synth.cu)
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -72,12 +71,6 @@ struct hycom_tsadvc_handle {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
   double march_ms = 0.0;
   int64_t march_n = 0;
-  // tensor maps of the slabs the marching kernels stage through the TMA engine: one 3-D map
-  // (col, row, layer) per (buffer, box width), encoded once, kept in device global memory
-  static constexpr int kMaxTmaps = 1024;
-  CUtensorMap* tmap_dev = nullptr;
-  std::vector<CUtensorMap> tmap_host;
-  std::map<std::tuple<const void*, int, int>, int> tmap_index;
   // multi-tile runs: the transport between tiles (NCCL or in-process), its stream and staging
   // buffers (xc_comm.cu); null: the host program moves the packed strips itself
   tsadvc::XcComm* xc = nullptr;

@@ -1,6 +1,5 @@
 // host <-> kernel launch contract of the marching kernels
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "eos.cuh"
@@ -25,10 +24,9 @@ struct MarchParams {
   FieldDesc fld[kMaxFields];
   int nfld;
   int kk;
-  const CUtensorMap* maps;   // the handle's tensor-map table (device global memory)
-  int map_u, map_v, map_dp;  // uflx, vflx, dp(:,:,:,n)
-  int map_sci, map_sc, map_msk;   // scp2i, scp2, mask words (one layer each)
-  int k_uv, k_dp;    // layer coordinate of the launch's first layer in uflx/vflx and in dp
+  const double* u;   // uflx(:,:,1)
+  const double* v;   // vflx(:,:,1)
+  const double* dp;  // dp(:,:,1,n)
   long slab;         // doubles per 2-D slab (pitch*nrows)
   int njobs;         // nfld*kk; job = field + nfld*(k-1): T and S of a layer adjacent
   Geo g;
