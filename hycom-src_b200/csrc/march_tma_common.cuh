@@ -36,10 +36,10 @@ namespace tsadvc {
 
 // One row slot = eight staged rows of 32*NC doubles: fld(n), fld(m), uflx, vflx, dp(n),
 // scp2i, scp2 and the mask word plane of the static block.
-template <int NC>
+template <int NC, int NA = 8>
 struct Ring {
   static constexpr int RB = 256 * NC;   // bytes of one staged row of doubles (32*NC columns)
-  static constexpr int NARR = 8;
+  static constexpr int NARR = NA;       // 7: the mask plane (the last array) is not staged
   static constexpr int SLOT = NARR * RB;
   static constexpr int NSLOT = 6;
   static constexpr int BYTES = NSLOT * SLOT;           // per warp
@@ -121,10 +121,10 @@ __device__ __forceinline__ RowSrc row_src(const TmaCtx& x, int r) {
 // request the row of `g` into the slot at byte offset `soff` of the ring (one lane)
 template <int NC, bool NEED_C, bool NEED_M = true>
 __device__ __forceinline__ void issue_row(const TmaCtx& x, const RowSrc& g, uint32_t soff, uint32_t bar) {
-  typedef Ring<NC> R;
+  typedef Ring<NC, NEED_M ? 8 : 7> R;
   const uint32_t dst = x.ring_s + soff;
   const long off = g.off;
-  mbar_expect_tx(bar, R::SLOT - (NEED_C ? 0 : R::RB) - (NEED_M ? 0 : R::RB));
+  mbar_expect_tx(bar, R::SLOT - (NEED_C ? 0 : R::RB));
   bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
   if (NEED_C) bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
   bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
@@ -287,7 +287,7 @@ __device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, Off o) {
 // ---------------------------------------------------------------------------------------
 template <class S, int NC, bool SAFE>
 __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p, uint32_t& round) {
-  typedef Ring<NC> R;
+  typedef Ring<NC, S::kNeedM ? 8 : 7> R;
   typename S::State s;
   S::init(s);
   bool bad = false;
