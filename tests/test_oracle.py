@@ -574,3 +574,65 @@ def test_asselin_conserves_constants(oracle):
     msk = util.interior_sea(cb)
     assert np.all(ot.f64("tracer")[0, m - 1][:, msk] == 0.625)
     ot.close()
+
+
+# ---------------------------------------------------------------------------------------
+# the pin: digests produced by the REFERENCE itself (fortran/build_ref.sh, needs gfortran)
+# ---------------------------------------------------------------------------------------
+_REF_FIXTURE = os.path.join(os.path.dirname(__file__), "golden", "from_reference.json")
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_FIXTURE),
+                    reason="tests/golden/from_reference.json absent: no Fortran compiler has produced it yet "
+                           "(fortran/build_ref.sh); parity stays unpinned")
+def test_reference_fixture(oracle):
+    """the oracle reproduces the bits of the reference's own tsadvc on the golden cases"""
+    import json
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden
+    ref = json.load(open(_REF_FIXTURE))
+    for name in sorted(ref):
+        got, _ = make_golden.run_oracle_case(oracle, name)
+        assert got == ref[name], name
+
+
+def test_reference_case_io_roundtrip(oracle, tmp_path):
+    """fortran/ref_case.py: the files it writes hold the case in the Fortran layout, and its digest of
+    out_*.bin files equals the frozen golden digest when those files hold the oracle's result - so the
+    only untested link of the pin is the Fortran compiler"""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    sys.path.insert(0, os.path.join(root, "fortran"))
+    import make_golden
+    import ref_case
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tsadvc_golden.json")))
+    for name in ("box_fct2", "periodic_mpdata_tracers"):
+        d = tmp_path / ("case_" + name)
+        ref_case.write(name, str(d))
+        kind, kw = make_golden.CASES[name]
+        cfg, sea, g, cb = make_golden.build(kind, kw)
+        back = np.fromfile(str(d / "saln.bin"), dtype="<f8").reshape(cb.saln.shape)
+        assert np.array_equal(back, cb.saln, equal_nan=True)
+        hdr = open(str(d / "case.txt")).read().split()
+        assert [int(v) for v in hdr[:3]] == [g.itdm, g.jtdm, g.kdm] and float(hdr[16]) == cb.delt1
+        out = util.run_oracle(oracle, cb, sea, 1, 2)
+        for nm in ("temp", "saln", "th3d"):
+            out[nm].astype("<f8").tofile(str(d / f"out_{nm}.bin"))
+        if cb.ntracr:
+            out["tracer"].astype("<f8").tofile(str(d / "out_tracer.bin"))
+    here = os.getcwd()
+    fixture = os.path.join(root, "tests", "golden", "from_reference.json")
+    keep = open(fixture).read() if os.path.exists(fixture) else None
+    try:
+        ref_case.digest(str(tmp_path), ["box_fct2", "periodic_mpdata_tracers"])
+        got = json.load(open(fixture))
+    finally:
+        if keep is None:
+            os.remove(fixture)
+        else:
+            open(fixture, "w").write(keep)
+        os.chdir(here)
+    for name in got:
+        assert got[name] == gold[name], name
