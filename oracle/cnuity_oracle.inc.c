@@ -1,0 +1,300 @@
+/*
+ * oracle/cnuity_oracle.inc.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (included by tsadvc_oracle.c).
+ *
+ * CPU restatement of HYCOM's continuity equation cnuity(m,n) (cnuity.F90), the producer of the
+ * dp(:,:,:,n), uflx, vflx that tsadvc(m,n) consumes, sweep by sweep with
+ * the Fortran loop ranges and operation order.  Scope (everything else is refused with an error):
+ *   .not.btrmas, thkdf2 = thkdf4 = 0 (no interface smoothing, :760-1124), no open-boundary faces
+ *   (iuopn = ivopn = 0, :170-229, :327-358), no STOKES drift, not (hybrid .and. mxlkta) (:1148-1324),
+ *   not (synflt .and. wvelfl) (:1128-1142).
+ * PARITY UNPINNED like the rest of the oracle (no Fortran compiler in this image); a second, independent
+ * restatement in numpy (oracle/np_restatement.py: cnuity) must agree with it bit for bit.
+ */
+
+/* arrays cnuity needs on top of the tsadvc tile, allocated on first use (r_init = NaN) */
+int orc_cnuity_alloc(orc_tile *t) {
+  if (t->u) return 0;
+  const size_t P = (size_t)orc_slab(t), K = (size_t)t->kdm;
+  t->u = alloc_r(P * K * 2); t->v = alloc_r(P * K * 2);
+  t->dpu = alloc_r(P * K * 2); t->dpv = alloc_r(P * K * 2);
+  t->ubavg = alloc_r(P * 3); t->vbavg = alloc_r(P * 3);
+  t->depthu = alloc_r(P); t->depthv = alloc_r(P);
+  t->p = alloc_r(P * (K + 1));
+  t->utotn = alloc_r(P); t->vtotn = alloc_r(P); t->utotm = alloc_r(P); t->vtotm = alloc_r(P);
+  t->util3 = alloc_r(P);
+  t->dpmixl = alloc_r(P * 2); t->dpmold = alloc_r(P);
+  t->uflxav = alloc_r(P * K); t->vflxav = alloc_r(P * K); t->dpav = alloc_r(P * K);
+  t->dpkmin = alloc_r(2 * K);
+  if (!t->u || !t->v || !t->dpu || !t->dpv || !t->ubavg || !t->vbavg || !t->depthu || !t->depthv || !t->p ||
+      !t->utotn || !t->vtotn || !t->utotm || !t->vtotm || !t->util3 || !t->dpmixl || !t->dpmold ||
+      !t->uflxav || !t->vflxav || !t->dpav || !t->dpkmin)
+    return 1;
+  /* geopar.F90:822-871: the flux scratch is zero on the land faces that bound sea segments and is never
+   * written there again; p(:,:,1) = 0 (the surface) */
+  for (size_t q = 0; q < P; q++) {
+    t->uflux[q] = t->vflux[q] = t->uflux2[q] = t->vflux2[q] = 0.0;
+    t->p[q] = 0.0;
+  }
+  return 0;
+}
+
+/* cnuity.F90:100-107: the single-tile xctilr calls, width 6, with their grid types */
+static void cnuity_halo(orc_tile *t, int m, int n) {
+  const size_t P = (size_t)orc_slab(t), K = (size_t)t->kdm;
+  const int kk = t->kk;
+  orc_xctilr_type(t, t->dpmixl + P * (size_t)(n - 1), 1, 1, 6, 6, 1);
+  orc_xctilr_type(t, t->dp, 1, 2 * kk, 6, 6, 1);
+  orc_xctilr_type(t, t->dpu + P * K * (size_t)(m - 1), 1, kk, 6, 6, 3);   /* halo_us */
+  orc_xctilr_type(t, t->dpv + P * K * (size_t)(m - 1), 1, kk, 6, 6, 4);   /* halo_vs */
+  orc_xctilr_type(t, t->u + P * K * (size_t)(m - 1), 1, kk, 6, 6, 13);    /* halo_uv */
+  orc_xctilr_type(t, t->v + P * K * (size_t)(m - 1), 1, kk, 6, 6, 14);    /* halo_vv */
+  orc_xctilr_type(t, t->ubavg + P * (size_t)(m - 1), 1, 1, 6, 6, 13);
+  orc_xctilr_type(t, t->vbavg + P * (size_t)(m - 1), 1, 1, 6, 6, 14);
+}
+
+/* cnuity.F90:14-1422.  do_halo as orc_tsadvc.  Returns 0, or an error for an unsupported option. */
+int orc_cnuity(orc_tile *t, int m, int n, int do_halo) {
+  GEOM(t); MASKS(t);
+  const size_t P = (size_t)orc_slab(t), K = (size_t)t->kdm;
+  const int kk = t->kk;
+  if (orc_cnuity_alloc(t)) return seterr("cnuity: out of memory");
+  if (t->btrmas) return seterr("cnuity: btrmas is not restated");
+  if (t->thkdf2 != 0.0 || t->thkdf4 != 0.0) return seterr("cnuity: interface smoothing (thkdf2/thkdf4) is not restated");
+  const double delt1 = t->delt1, epsil = 1.0e-11;   /* mod_cb_arrays.F90:853 */
+  const int nthr = nthr_of(t), jblk = jblk_of(t, nthr);
+  (void)jblk;
+  double *dpn = t->dp + P * K * (size_t)(n - 1), *dpm = t->dp + P * K * (size_t)(m - 1);
+  double *dpon = t->dpo + P * K * (size_t)(n - 1), *dpom = t->dpo + P * K * (size_t)(m - 1);
+  const double *um = t->u + P * K * (size_t)(m - 1), *vm = t->v + P * K * (size_t)(m - 1);
+  const double *dpum = t->dpu + P * K * (size_t)(m - 1), *dpvm = t->dpv + P * K * (size_t)(m - 1);
+  const double *ubm = t->ubavg + P * (size_t)(m - 1), *vbm = t->vbavg + P * (size_t)(m - 1);
+  double *onmn = t->onetamas + P * (size_t)(n - 1);
+  double *uflux = t->uflux, *vflux = t->vflux, *uflux2 = t->uflux2, *vflux2 = t->vflux2;
+  double *util1 = t->util1, *util2 = t->util2, *util3 = t->util3;
+  double *utotn = t->utotn, *vtotn = t->vtotn, *utotm = t->utotm, *vtotm = t->vtotm;
+  int mbdy = 6, margin;
+  if (do_halo) cnuity_halo(t, m, n);
+
+  /* :116-156 (use dp'): onetamas = oneta_u = oneta_v = 1.0 */
+  margin = mbdy;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int i = 1 - margin; i <= ii + margin; i++) {
+      const size_t c = IX(i, j);
+      t->onetamas[c] = 1.0; t->onetamas[c + P] = 1.0;
+      utotn[c] = 0.0; vtotn[c] = 0.0; util3[c] = 0.0;
+      t->dpmold[c] = t->dpmixl[c + P * (size_t)(n - 1)];
+      for (int k = 1; k <= kk; k++) dpon[c + P * (size_t)(k - 1)] = dpn[c + P * (size_t)(k - 1)];
+    }
+
+  for (int k = 1; k <= kk; k++) {   /* loop 76 */
+    const size_t ko = P * (size_t)(k - 1);
+    double *dpk = dpn + ko;
+    /* :236-283 low-order fluxes at the old time level and antidiffusive fluxes */
+    margin = mbdy - 1;
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++) {
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_U) {
+          const size_t c = IX(i, j);
+          double q;
+          utotm[c] = (um[c + ko] + ubm[c]) * t->scuy[c];
+          if (utotm[c] >= 0.0)
+            q = MIN2(dpk[IX(i - 1, j)], MAX2(0.0, t->depthu[c] - util3[IX(i - 1, j)])) * onmn[IX(i - 1, j)];
+          else
+            q = MIN2(dpk[c], MAX2(0.0, t->depthu[c] - util3[c])) * onmn[c];
+          uflux[c] = utotm[c] * q;
+          uflux2[c] = utotm[c] * dpum[c + ko] * 1.0 - uflux[c];   /* oneta_u = 1.0 */
+          t->uflx[c + ko] = uflux[c];
+        }
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_V) {
+          const size_t c = IX(i, j);
+          double q;
+          vtotm[c] = (vm[c + ko] + vbm[c]) * t->scvx[c];
+          if (vtotm[c] >= 0.0)
+            q = MIN2(dpk[IX(i, j - 1)], MAX2(0.0, t->depthv[c] - util3[IX(i, j - 1)])) * onmn[IX(i, j - 1)];
+          else
+            q = MIN2(dpk[c], MAX2(0.0, t->depthv[c] - util3[c])) * onmn[c];
+          vflux[c] = vtotm[c] * q;
+          vflux2[c] = vtotm[c] * dpvm[c + ko] * 1.0 - vflux[c];
+          t->vflx[c + ko] = vflux[c];
+        }
+    }
+    /* :293-311 advance dp with the low-order fluxes (loop 19) */
+    margin = mbdy - 2;
+    {
+      double dpmn[4096 + 64];
+      double *mn = (size_t)(t->jdm + 2 * nb) <= sizeof dpmn / sizeof dpmn[0] ? dpmn
+                                                                            : (double *)malloc(sizeof(double) * (size_t)(t->jdm + 2 * nb));
+      OMP_J
+      for (int j = 1 - margin; j <= jj + margin; j++) {
+        double dpmin = 999.0;
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_P) {
+            const size_t c = IX(i, j);
+            util3[c] = util3[c] + dpk[c];
+            dpk[c] = dpk[c] * onmn[c] -
+                     ((uflux[IX(i + 1, j)] - uflux[c]) + (vflux[IX(i, j + 1)] - vflux[c])) * delt1 * t->scp2i[c];
+            dpom[c + ko] = dpk[c];
+            dpmin = MIN2(dpmin, dpk[c]);
+          }
+        mn[j + nb - 1] = dpmin;
+      }
+      double dpmin = 999.0;
+      for (int j = 1; j <= jj; j++) dpmin = MIN2(dpmin, mn[j + nb - 1]);
+      t->dpkmin[k - 1] = dpmin;
+      if (mn != dpmn) free(mn);
+    }
+    /* :378-400 ratios of the largest permissible change to the sum of incoming / outgoing fluxes */
+    margin = mbdy - 2;
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++)
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_P) {
+          const size_t c = IX(i, j);
+          const int ia = t->ipim1[c], ib = t->ipip1[c], ja = t->ipjm1[c], jb = t->ipjp1[c];
+          const double d0 = dpk[c], d1 = dpk[IX(ia, j)], d2 = dpk[IX(ib, j)], d3 = dpk[IX(i, ja)], d4 = dpk[IX(i, jb)];
+          double u1 = MAX5(d0, d1, d2, d3, d4);
+          double u2 = MAX2(0.0, MIN5(d0, d1, d2, d3, d4));
+          u1 = (u1 - d0) /
+               (((MAX2(0.0, uflux2[c]) - MIN2(0.0, uflux2[IX(i + 1, j)])) +
+                 (MAX2(0.0, vflux2[c]) - MIN2(0.0, vflux2[IX(i, j + 1)])) + epsil) * delt1 * t->scp2i[c]);
+          u2 = (u2 - d0) /
+               (((MIN2(0.0, uflux2[c]) - MAX2(0.0, uflux2[IX(i + 1, j)])) +
+                 (MIN2(0.0, vflux2[c]) - MAX2(0.0, vflux2[IX(i, j + 1)])) - epsil) * delt1 * t->scp2i[c]);
+          util1[c] = u1; util2[c] = u2;
+        }
+    /* :414-441 limit the antidiffusive fluxes; utotn, vtotn keep what was clipped */
+    margin = mbdy - 3;
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++) {
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_U) {
+          const size_t c = IX(i, j);
+          double clip;
+          if (uflux2[c] >= 0.0) clip = MIN3(1.0, util1[c], util2[IX(i - 1, j)]);
+          else clip = MIN3(1.0, util2[c], util1[IX(i - 1, j)]);
+          utotn[c] = utotn[c] + uflux2[c] * (1.0 - clip);
+          uflux[c] = uflux2[c] * clip;
+          t->uflx[c + ko] = t->uflx[c + ko] + uflux[c];
+        }
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_V) {
+          const size_t c = IX(i, j);
+          double clip;
+          if (vflux2[c] >= 0.0) clip = MIN3(1.0, util1[c], util2[IX(i, j - 1)]);
+          else clip = MIN3(1.0, util2[c], util1[IX(i, j - 1)]);
+          vtotn[c] = vtotn[c] + vflux2[c] * (1.0 - clip);
+          vflux[c] = vflux2[c] * clip;
+          t->vflx[c + ko] = t->vflx[c + ko] + vflux[c];
+        }
+    }
+    /* :449-469 effect of the clipped antidiffusive fluxes on dp (loop 15) */
+    margin = mbdy - 4;
+    {
+      double dpmin = 999.0;
+      for (int j = 1 - margin; j <= jj + margin; j++) {
+        double dmj = 999.0;
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_P) {
+            const size_t c = IX(i, j);
+            dpk[c] = dpk[c] - ((uflux[IX(i + 1, j)] - uflux[c]) + (vflux[IX(i, j + 1)] - vflux[c])) * delt1 * t->scp2i[c];
+            t->p[c + P * (size_t)k] = t->p[c + P * (size_t)(k - 1)] + dpk[c];
+            dmj = MIN2(dmj, dpk[c]);
+          }
+        if (j >= 1 && j <= jj) dpmin = MIN2(dpmin, dmj);
+      }
+      t->dpkmin[kk + k - 1] = dpmin;
+    }
+  }
+
+  /* :580-683 (not btrmas) restore the nondivergence of the vertically integrated flow */
+  for (int k = 1; k <= kk; k++) {   /* loop 77 */
+    const size_t ko = P * (size_t)(k - 1);
+    double *dpk = dpn + ko;
+    const double *pb = t->p + P * (size_t)kk;   /* p(:,:,kk+1) */
+    margin = mbdy - 5;
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++) {
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_U) {
+          const size_t c = IX(i, j);
+          double q;
+          if (utotn[c] >= 0.0) q = dpk[IX(i - 1, j)] / pb[IX(i - 1, j)];
+          else q = dpk[c] / pb[c];
+          uflux[c] = utotn[c] * q;
+          t->uflx[c + ko] = t->uflx[c + ko] + uflux[c];
+        }
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_V) {
+          const size_t c = IX(i, j);
+          double q;
+          if (vtotn[c] >= 0.0) q = dpk[IX(i, j - 1)] / pb[IX(i, j - 1)];
+          else q = dpk[c] / pb[c];
+          vflux[c] = vtotn[c] * q;
+          t->vflx[c + ko] = t->vflx[c + ko] + vflux[c];
+        }
+    }
+    margin = mbdy - 6;
+    {
+      double dpmin = 999.0;
+      for (int j = 1 - margin; j <= jj + margin; j++)
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_P) {
+            const size_t c = IX(i, j);
+            dpk[c] = dpk[c] - ((uflux[IX(i + 1, j)] - uflux[c]) + (vflux[IX(i, j + 1)] - vflux[c])) * delt1 * t->scp2i[c];
+            t->p[c + P * (size_t)k] = t->p[c + P * (size_t)(k - 1)] + dpk[c];
+            dpmin = MIN2(dpmin, dpk[c]);
+          }
+      t->dpkmin[k - 1] = dpmin;   /* loop 14 (the loop-19 values of :505-535 are overwritten, like the Fortran) */
+    }
+  }
+  /* NOTE the Fortran updates p(:,:,k+1) inside loop 77 while q of the layers below still reads p(:,:,kk+1):
+   * p(kk+1) changes only when k = kk, after its last use (:684-706). */
+
+  /* :716-733 bottom-pressure restoring term */
+  margin = mbdy - 6;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int i = 1 - margin; i <= ii + margin; i++)
+      if (SEA_P) {
+        const size_t c = IX(i, j);
+        const double q = t->pbot[c] / t->p[c + P * (size_t)kk];
+        for (int k = 1; k <= kk; k++) {
+          dpn[c + P * (size_t)(k - 1)] = dpn[c + P * (size_t)(k - 1)] * q;
+          t->p[c + P * (size_t)k] = t->p[c + P * (size_t)(k - 1)] + dpn[c + P * (size_t)(k - 1)];
+        }
+        if (t->isopyc) t->dpmixl[c + P * (size_t)(n - 1)] = dpn[c];
+      }
+
+  /* :1326-1350 cumulative fluxes */
+  margin = 0;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int k = 1; k <= kk; k++)
+      for (int i = 1 - margin; i <= ii + margin; i++) {
+        const size_t c = IX(i, j), ck = c + P * (size_t)(k - 1);
+        if (SEA_U) t->uflxav[ck] = t->uflxav[ck] + t->uflx[ck];
+        if (SEA_V) t->vflxav[ck] = t->vflxav[ck] + t->vflx[ck];
+        if (SEA_P) t->dpav[ck] = t->dpav[ck] + dpn[ck];
+      }
+
+  /* :1396-1422 Robert-Asselin time filter of the thickness field */
+  if (do_halo) orc_xctilr_type(t, dpn, 1, kk, 6, 6, 1);
+  margin = mbdy;
+  OMP_J
+  for (int j = 1 - margin; j <= jj + margin; j++)
+    for (int i = 1 - margin; i <= ii + margin; i++)
+      if (SEA_P) {
+        const size_t c = IX(i, j);
+        for (int k = 1; k <= kk; k++) {
+          const size_t ck = c + P * (size_t)(k - 1);
+          const double dpold = dpon[ck], dpmid = dpm[ck], dpnew = dpn[ck];
+          const double q = 0.5 * t->ra2fac * (dpold + dpnew - 2.0 * dpmid);
+          dpom[ck] = dpm[ck];
+          dpm[ck] = dpmid + q;
+        }
+      }
+  return 0;
+}

@@ -638,3 +638,127 @@ def asselin_filter(cb, m, n):
                     R = (dpsmid + 0.5 * ra * (dpsold + dpsnew - 2.0 * dpsmid)) * qd
                     arr[m - 1, k + 1] = np.where(go, R, arr[m - 1, k + 1])
     return dict(oneta=oneta, dp=dp, temp=temp, saln=saln, th3d=th3d, tracer=tracer, q2=q2, q2l=q2l)
+
+
+# -----------------------------------------------------------------------------------------
+# cnuity(m,n) (cnuity.F90), second restatement: whole-array expressions, fluxes by the rule
+# "zero unless an iu / iv point", layer coupling through a running sum of the old thicknesses.
+# Scope as oracle/cnuity_oracle.inc.c (not btrmas, no interface smoothing, no open boundaries).
+# -----------------------------------------------------------------------------------------
+EPSIL = 1.0e-11   # mod_cb_arrays.F90:853
+
+
+def cnuity(geom, st, m, n, ip, iu, iv, scuy, scvx, scp2i, depthu, depthv, pbot, delt1, ra2fac, isopyc=False):
+    """st: dict of arrays in the Fortran layout with halos valid to width 6 (the caller did the xctilr of
+    cnuity.F90:100-107): dp, dpo (2,kk,..), u, v, dpu, dpv (2,kk,..), ubavg, vbavg (3,..), dpmixl (2,..),
+    uflx, vflx, uflxav, vflxav, dpav (kk,..).  Updated in place; returns p (kk+1,..), utotn, vtotn, dpkmin.
+    The halo refresh of dp(:,:,:,n) before the Robert-Asselin filter (:1400) is the caller's `halo` callback."""
+    kk = geom.kdm
+    dp, dpo = st["dp"], st["dpo"]
+    n_, m_ = n - 1, m - 1
+    shape = (geom.nrows, geom.ncols)
+    R = {mg: _region(geom, mg) for mg in range(0, 7)}
+    sea_p, sea_u, sea_v = ip != 0, iu != 0, iv != 0
+    utotn, vtotn, util3 = np.zeros(shape), np.zeros(shape), np.zeros(shape)
+    dpmold = st["dpmixl"][n_].copy()
+    dpo[n_][:, R[6]] = dp[n_][:, R[6]]
+    p = np.full((kk + 1,) + shape, np.nan)
+    p[0] = 0.0
+    dpkmin = np.full(2 * kk, np.nan)
+    inner = R[0]
+    with np.errstate(all="ignore"):
+        for k in range(kk):
+            d = dp[n_][k]
+            # low-order and antidiffusive fluxes (:236-283), margin 5
+            utotm = (st["u"][m_][k] + st["ubavg"][m_]) * scuy
+            qu = np.where(utotm >= 0.0,
+                          _fmin(_sh(d, -1, 0), _fmax(0.0, depthu - _sh(util3, -1, 0))),
+                          _fmin(d, _fmax(0.0, depthu - util3)))
+            fu = np.where(sea_u & R[5], utotm * qu, 0.0)
+            fu2 = np.where(sea_u & R[5], utotm * st["dpu"][m_][k] - fu, 0.0)
+            vtotm = (st["v"][m_][k] + st["vbavg"][m_]) * scvx
+            qv = np.where(vtotm >= 0.0,
+                          _fmin(_sh(d, 0, -1), _fmax(0.0, depthv - _sh(util3, 0, -1))),
+                          _fmin(d, _fmax(0.0, depthv - util3)))
+            fv = np.where(sea_v & R[5], vtotm * qv, 0.0)
+            fv2 = np.where(sea_v & R[5], vtotm * st["dpv"][m_][k] - fv, 0.0)
+            uflx_k = np.where(sea_u & R[5], fu, st["uflx"][k])
+            vflx_k = np.where(sea_v & R[5], fv, st["vflx"][k])
+            # low-order thickness (:293-311), margin 4
+            r4 = sea_p & R[4]
+            util3 = np.where(r4, util3 + d, util3)
+            dlo = d - ((_sh(fu, 1, 0) - fu) + (_sh(fv, 0, 1) - fv)) * delt1 * scp2i
+            d = np.where(r4, dlo, d)
+            rows = np.where(r4, d, 999.0).min(axis=1)           # dpmn(j): all columns of the margin
+            nb = geom.nbdy
+            dpkmin[k] = min(999.0, rows[nb:nb + geom.jj].min())
+            # ratios (:378-400), margin 4
+            mx, mn = _extrema5(d, ip)
+            mn = _fmax(0.0, mn)
+            pos = lambda a: _fmax(0.0, a)   # noqa: E731
+            neg = lambda a: _fmin(0.0, a)   # noqa: E731
+            u1 = (mx - d) / (((pos(fu2) - neg(_sh(fu2, 1, 0))) + (pos(fv2) - neg(_sh(fv2, 0, 1))) + EPSIL) * delt1 * scp2i)
+            u2 = (mn - d) / (((neg(fu2) - pos(_sh(fu2, 1, 0))) + (neg(fv2) - pos(_sh(fv2, 0, 1))) - EPSIL) * delt1 * scp2i)
+            u1 = np.where(r4, u1, np.nan)
+            u2 = np.where(r4, u2, np.nan)
+            # limiter (:414-441), margin 3
+            cu = np.where(fu2 >= 0.0, _fmin(_fmin(1.0, u1), _sh(u2, -1, 0)), _fmin(_fmin(1.0, u2), _sh(u1, -1, 0)))
+            cv = np.where(fv2 >= 0.0, _fmin(_fmin(1.0, u1), _sh(u2, 0, -1)), _fmin(_fmin(1.0, u2), _sh(u1, 0, -1)))
+            r3u, r3v = sea_u & R[3], sea_v & R[3]
+            utotn = np.where(r3u, utotn + fu2 * (1.0 - cu), utotn)
+            vtotn = np.where(r3v, vtotn + fv2 * (1.0 - cv), vtotn)
+            fuc = np.where(r3u, fu2 * cu, fu)      # outside margin 3 uflux keeps the low-order value (never used)
+            fvc = np.where(r3v, fv2 * cv, fv)
+            uflx_k = np.where(r3u, uflx_k + fuc, uflx_k)
+            vflx_k = np.where(r3v, vflx_k + fvc, vflx_k)
+            # antidiffusive update (:449-469), margin 2
+            r2 = sea_p & R[2]
+            d = np.where(r2, d - ((_sh(fuc, 1, 0) - fuc) + (_sh(fvc, 0, 1) - fvc)) * delt1 * scp2i, d)
+            p[k + 1] = np.where(r2, p[k] + d, p[k + 1])
+            rows = np.where(r2, d, 999.0).min(axis=1)
+            dpkmin[kk + k] = min(999.0, rows[nb:nb + geom.jj].min())
+            dp[n_][k] = d
+            st["uflx"][k], st["vflx"][k] = uflx_k, vflx_k
+        # loop 77 (:588-683): the clipped fluxes go back in proportion to the layer thickness
+        pb = p[kk].copy()
+        for k in range(kk):
+            d = dp[n_][k]
+            r1u, r1v = sea_u & R[1], sea_v & R[1]
+            qu = np.where(utotn >= 0.0, _sh(d, -1, 0) / _sh(pb, -1, 0), d / pb)
+            qv = np.where(vtotn >= 0.0, _sh(d, 0, -1) / _sh(pb, 0, -1), d / pb)
+            fu = np.where(r1u, utotn * qu, 0.0)
+            fv = np.where(r1v, vtotn * qv, 0.0)
+            st["uflx"][k] = np.where(r1u, st["uflx"][k] + fu, st["uflx"][k])
+            st["vflx"][k] = np.where(r1v, st["vflx"][k] + fv, st["vflx"][k])
+            r0 = sea_p & inner
+            d = np.where(r0, d - ((_sh(fu, 1, 0) - fu) + (_sh(fv, 0, 1) - fv)) * delt1 * scp2i, d)
+            p[k + 1] = np.where(r0, p[k] + d, p[k + 1])
+            dpkmin[k] = min(999.0, np.where(r0, d, 999.0).min())
+            dp[n_][k] = d
+        # bottom-pressure restoring (:716-733)
+        r0 = sea_p & inner
+        q = pbot / p[kk]
+        for k in range(kk):
+            dp[n_][k] = np.where(r0, dp[n_][k] * q, dp[n_][k])
+            p[k + 1] = np.where(r0, p[k] + dp[n_][k], p[k + 1])
+        if isopyc:
+            st["dpmixl"][n_] = np.where(r0, dp[n_][0], st["dpmixl"][n_])
+        # cumulative fluxes (:1326-1350)
+        for k in range(kk):
+            st["uflxav"][k] = np.where(sea_u & inner, st["uflxav"][k] + st["uflx"][k], st["uflxav"][k])
+            st["vflxav"][k] = np.where(sea_v & inner, st["vflxav"][k] + st["vflx"][k], st["vflxav"][k])
+            st["dpav"][k] = np.where(r0, st["dpav"][k] + dp[n_][k], st["dpav"][k])
+    return p, utotn, vtotn, dpkmin, dpmold
+
+
+def cnuity_asselin(geom, st, m, n, ip, ra2fac):
+    """the Robert-Asselin tail of cnuity (:1396-1422); dp(:,:,:,n) halo valid to width 6"""
+    n_, m_ = n - 1, m - 1
+    r6 = (ip != 0) & _region(geom, 6)
+    dp, dpo = st["dp"], st["dpo"]
+    with np.errstate(all="ignore"):
+        for k in range(geom.kdm):
+            q = 0.5 * ra2fac * (dpo[n_][k] + dp[n_][k] - 2.0 * dp[m_][k])
+            mid = dp[m_][k].copy()
+            dpo[m_][k] = np.where(r6, mid, dpo[m_][k])
+            dp[m_][k] = np.where(r6, mid + q, dp[m_][k])

@@ -136,7 +136,9 @@ void orc_tile_destroy(orc_tile *t) {
                   t->fldlo, t->fmxlo, t->fmnlo, t->fax, t->fay, t->rp, t->rm,
                   t->flxdiv, t->tx1, t->ty1, t->fldao, t->fldan, t->xmin,
                   t->xmax, t->theta, t->q2, t->q2l, t->dpo, t->onetao, t->pbavg, t->pbot,
-                  t->otemp, t->osaln, t->oth3d, t->otracer, t->oq2, t->oq2l};
+                  t->otemp, t->osaln, t->oth3d, t->otracer, t->oq2, t->oq2l,
+                  t->u, t->v, t->dpu, t->dpv, t->ubavg, t->vbavg, t->depthu, t->depthv, t->p, t->utotn, t->vtotn,
+                  t->utotm, t->vtotm, t->util3, t->dpmixl, t->dpmold, t->uflxav, t->vflxav, t->dpav, t->dpkmin};
   for (size_t q = 0; q < sizeof(ptrs) / sizeof(ptrs[0]); q++) free(ptrs[q]);
   free(t);
 }
@@ -151,6 +153,8 @@ double *orc_f64(orc_tile *t, const char *name) {
   F(rp); F(rm); F(flxdiv); F(tx1); F(ty1); F(fldao); F(fldan);
   F(xmin); F(xmax); F(theta); F(q2); F(q2l);
   F(dpo); F(onetao); F(pbavg); F(pbot); F(otemp); F(osaln); F(oth3d); F(otracer); F(oq2); F(oq2l);
+  F(u); F(v); F(dpu); F(dpv); F(ubavg); F(vbavg); F(depthu); F(depthv); F(p); F(utotn); F(vtotn); F(utotm); F(vtotm);
+  F(util3); F(dpmixl); F(dpmold); F(uflxav); F(vflxav); F(dpav); F(dpkmin);
 #undef F
   return NULL;
 }
@@ -180,7 +184,7 @@ int orc_get_i(const orc_tile *t, const char *name) {
 }
 int orc_set_d(orc_tile *t, const char *name, double v) {
 #define S(n) if (!strcmp(name, #n)) { t->n = v; return 0; }
-  S(delt1) S(temdf2) S(temdfc) S(thbase) S(onemm) S(ra2fac) S(oneta0)
+  S(delt1) S(temdf2) S(temdfc) S(thbase) S(onemm) S(ra2fac) S(oneta0) S(thkdf2) S(thkdf4)
 #undef S
   return 1;
 }
@@ -1738,3 +1742,9 @@ int orc_tsadvc(orc_tile *t, int m, int n, int do_halo) {
   }
   return 0;
 }
+
+static int seterr(const char *msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return 1;
+}
+#include "cnuity_oracle.inc.c"

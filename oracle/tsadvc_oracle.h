@@ -70,6 +70,12 @@ typedef struct orc_tile {
   int xminmax_valid;
   /* OpenMP threads used by the sweeps (0 = runtime default) */
   int nthreads;
+  /* cnuity.F90 operands, allocated by orc_cnuity_alloc:
+   * u, v, dpu, dpv (P,kdm,2); ubavg, vbavg (P,3); depthu, depthv (P); p (P,kdm+1); utotn, vtotn, utotm, vtotm,
+   * util3 (P); dpmixl (P,2); dpmold (P); uflxav, vflxav, dpav (P,kdm); dpkmin (2*kdm) */
+  double *u, *v, *dpu, *dpv, *ubavg, *vbavg, *depthu, *depthv, *p, *utotn, *vtotn, *utotm, *vtotm, *util3,
+      *dpmixl, *dpmold, *uflxav, *vflxav, *dpav, *dpkmin;
+  double thkdf2, thkdf4;
 } orc_tile;
 
 orc_tile *orc_tile_create(int idm, int jdm, int kdm, int nbdy, int ii, int jj,
@@ -128,6 +134,11 @@ double orc_tofsig(int sigver, double r, double s);
  * do_halo=0: the caller has already refreshed the halos (multi-tile emulation,
  *            orc_tsadvc_halo_list + orc_world_xctilr). Returns 0 or an error. */
 int orc_tsadvc(orc_tile *t, int m, int n, int do_halo);
+
+/* cnuity.F90:14-1422 within the scope stated in cnuity_oracle.inc.c; orc_cnuity_alloc adds its operands to
+ * the tile (idempotent) */
+int orc_cnuity_alloc(orc_tile *t);
+int orc_cnuity(orc_tile *t, int m, int n, int do_halo);
 
 /* mod_asselin.F90:28-82 and :84-286 */
 void orc_asselin_save(orc_tile *t, int m, int n, int do_halo);

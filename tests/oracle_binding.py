@@ -38,7 +38,9 @@ class OracleTile:
     _SHAPES = {"temp": 4, "saln": 4, "th3d": 4, "dp": 4, "tracer": 5, "uflx": 3, "vflx": 3,
                "oneta": -2, "onetamas": -2, "xmin": 1, "xmax": 1, "theta": 3, "q2": 6, "q2l": 6,
                "dpo": 4, "onetao": -2, "pbavg": -3, "otemp": 3, "osaln": 3, "oth3d": 3, "otracer": 7,
-               "oq2": 8, "oq2l": 8}
+               "oq2": 8, "oq2l": 8,
+               "u": 4, "v": 4, "dpu": 4, "dpv": 4, "ubavg": -3, "vbavg": -3, "dpmixl": -2, "p": 9,
+               "uflxav": 3, "vflxav": 3, "dpav": 3, "dpkmin": 10}
 
     def f64(self, name):
         g = self.geom
@@ -50,7 +52,7 @@ class OracleTile:
                  4: (2, g.kdm, g.nrows, g.ncols), 5: (self.ntracr, 2, g.kdm, g.nrows, g.ncols),
                  -2: (2, g.nrows, g.ncols), 1: (g.kdm,), 6: (2, g.kdm + 2, g.nrows, g.ncols),
                  -3: (3, g.nrows, g.ncols), 7: (self.ntracr, g.kdm, g.nrows, g.ncols),
-                 8: (g.kdm + 2, g.nrows, g.ncols)}[kind]
+                 8: (g.kdm + 2, g.nrows, g.ncols), 9: (g.kdm + 1, g.nrows, g.ncols), 10: (2 * g.kdm,)}[kind]
         n = int(np.prod(shape))
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,)).reshape(shape)
 
@@ -102,6 +104,14 @@ class OracleTile:
         rc = self.lib.orc_tsadvc(self.t, m, n, do_halo)
         if rc:
             raise RuntimeError(f"orc_tsadvc rc={rc}: {self.orc.last_error()}")
+
+    def cnuity_alloc(self):
+        assert self.lib.orc_cnuity_alloc(self.t) == 0
+
+    def cnuity(self, m, n, do_halo=1):
+        rc = self.lib.orc_cnuity(self.t, m, n, do_halo)
+        if rc:
+            raise RuntimeError(f"orc_cnuity rc={rc}: {self.orc.last_error()}")
 
     def asselin_save(self, m, n, do_halo=1):
         self.lib.orc_asselin_save(self.t, m, n, do_halo)
@@ -164,6 +174,8 @@ class Oracle:
         lib.orc_advem.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp,
                                   C.c_double, C.c_int]
         lib.orc_tsadvc.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+        lib.orc_cnuity_alloc.argtypes = [_vp]
+        lib.orc_cnuity.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
         lib.orc_asselin_save.restype = None
         lib.orc_asselin_save.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
         lib.orc_asselin_filter.restype = None

@@ -636,3 +636,69 @@ def test_reference_case_io_roundtrip(oracle, tmp_path):
         os.chdir(here)
     for name in got:
         assert got[name] == gold[name], name
+
+
+# ---------------------------------------------------------------------------------------
+# cnuity(m,n) (cnuity.F90): C restatement == numpy restatement
+# ---------------------------------------------------------------------------------------
+def _np_cnuity(cb, g, st, m, n, ra2fac=0.125, isopyc=False):
+    """the numpy path with the single-tile xctilr calls of cnuity.F90:100-107 and :1400"""
+    st = {k: v.copy() for k, v in st.items()}
+    nb = g.nbdy
+    H = lambda a, it: npr.halo_single_tile(g, a, 6, 6, it)   # noqa: E731
+    st["dpmixl"][n - 1] = H(st["dpmixl"][n - 1], 1)
+    st["dp"] = H(st["dp"], 1)
+    st["dpu"][m - 1] = H(st["dpu"][m - 1], 3)
+    st["dpv"][m - 1] = H(st["dpv"][m - 1], 4)
+    st["u"][m - 1] = H(st["u"][m - 1], 13)
+    st["v"][m - 1] = H(st["v"][m - 1], 14)
+    st["ubavg"][m - 1] = H(st["ubavg"][m - 1], 13)
+    st["vbavg"][m - 1] = H(st["vbavg"][m - 1], 14)
+    p, utotn, vtotn, dpkmin, dpmold = npr.cnuity(g, st, m, n, cb.ip, cb.iu, cb.iv, cb.scuy, cb.scvx, cb.scp2i,
+                                                 st["depthu"], st["depthv"], st["pbot"], cb.delt1, ra2fac, isopyc)
+    st["dp"][n - 1] = H(st["dp"][n - 1], 1)
+    npr.cnuity_asselin(g, st, m, n, cb.ip, ra2fac)
+    st.update(p=p, utotn=utotn, vtotn=vtotn, dpkmin=dpkmin)
+    return st
+
+
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,m,n,isopyc", [
+    (90, 70, 4, 0, 1, 2, False),      # closed basin with islands
+    (131, 77, 3, 3, 2, 1, False),     # doubly periodic, slots swapped
+    (64, 90, 3, 1, 1, 2, True),       # periodic in i, isopyc: dpmixl(n) = dp(1,n)
+    (70, 45, 2, 4, 1, 2, False),      # closed f-plane (periodic in j)
+])
+def test_cnuity_c_oracle_equals_numpy(oracle, itdm, jtdm, kdm, nreg, m, n, isopyc):
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=23, m=m, n=n)
+    st = util.add_cnuity(cfg, sea, g, cb, m, n)
+    want = _np_cnuity(cb, g, st, m, n, isopyc=isopyc)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    util.oracle_load_cnuity(ot, st)
+    ot.set_i("isopyc", int(isopyc))
+    ot.cnuity(m, n, 1)
+    nb = g.nbdy
+    inner = util.interior_sea(cb)
+    sea6 = cb.ip != 0
+    iu_in = np.zeros_like(inner); iv_in = np.zeros_like(inner)
+    iu_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iu[nb:nb + g.jj, nb:nb + g.ii] != 0
+    iv_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iv[nb:nb + g.jj, nb:nb + g.ii] != 0
+    for k in range(kdm):
+        assert np.array_equal(ot.f64("dp")[n - 1, k][inner], want["dp"][n - 1, k][inner]), ("dp.n", k)
+        assert np.array_equal(ot.f64("dp")[m - 1, k][sea6], want["dp"][m - 1, k][sea6]), ("dp.m", k)
+        assert np.array_equal(ot.f64("dpo")[m - 1, k][sea6], want["dpo"][m - 1, k][sea6]), ("dpo.m", k)
+        assert np.array_equal(ot.f64("dpo")[n - 1, k], want["dpo"][n - 1, k], equal_nan=True), ("dpo.n", k)
+        assert np.array_equal(ot.f64("uflx")[k][iu_in], want["uflx"][k][iu_in]), ("uflx", k)
+        assert np.array_equal(ot.f64("vflx")[k][iv_in], want["vflx"][k][iv_in]), ("vflx", k)
+        assert np.array_equal(ot.f64("p")[k + 1][inner], want["p"][k + 1][inner]), ("p", k)
+        assert np.array_equal(ot.f64("dpav")[k][inner], want["dpav"][k][inner]), ("dpav", k)
+        assert np.array_equal(ot.f64("uflxav")[k][iu_in], want["uflxav"][k][iu_in]), ("uflxav", k)
+    assert np.array_equal(ot.f64("utotn")[iu_in], want["utotn"][iu_in])
+    assert np.array_equal(ot.f64("vtotn")[iv_in], want["vtotn"][iv_in])
+    assert np.array_equal(ot.f64("dpkmin"), want["dpkmin"])
+    if isopyc:
+        assert np.array_equal(ot.f64("dpmixl")[n - 1][inner], want["dpmixl"][n - 1][inner])
+    # the column still sums to pbot after the restoring term, and the thicknesses moved
+    colsum = ot.f64("dp")[n - 1].sum(axis=0)
+    assert np.allclose(colsum[inner], st["pbot"][inner], rtol=1e-12)
+    assert not np.array_equal(ot.f64("dp")[n - 1, 0][inner], st["dp"][n - 1, 0][inner])
+    ot.close()

@@ -174,3 +174,68 @@ def add_asselin(cfg, sea, g, cb, m, n, sigver=6, seed=77):
         for k in range(kk):
             cb.theta[k] = 1.0 + 0.1 * k
     return cb
+
+
+def add_cnuity(cfg, sea, g, cb, m, n, seed=91):
+    """operands of cnuity(m,n) (cnuity.F90) on top of a case, as a dict of arrays in the Fortran layout.
+    Halos of the arrays cnuity exchanges itself (:100-107) are NaN, like every exchanged array; pbot, depthu,
+    depthv arrive with valid halos.  u, v are O(0.3 m/s) smooth fields (both signs), zero off the iu / iv
+    points; dp(:,:,:,m) is a perturbed dp(:,:,:,n); pbot is the column sum of dp(m); depthu/depthv the
+    shallower neighbour; dpu/dpv the thickness of layer k on the faces (dpudpv.F90's definition)."""
+    rng = np.random.default_rng(seed)
+    kk, shp = g.kdm, (g.nrows, g.ncols)
+    nb = g.nbdy
+    full = lambda fld, ktr=0, lev=0: syn.fill_host(cfg, g, sea, fld, ktr, lev, 1, kk, 1)   # noqa: E731
+    dpn = syn.fill_host(cfg, g, sea, cabi.F_DP, 0, 0, 1, kk, 1)
+    dpm = syn.fill_host(cfg, g, sea, cabi.F_DP, 0, 1, 1, kk, 1)
+    sea_h = np.zeros(shp, dtype=bool)           # sea map on the padded tile (periodic image or land)
+    js = (np.arange(g.nrows) - nb + g.j0) % g.jtdm if g.periodic_j else np.arange(g.nrows) - nb + g.j0
+    is_ = (np.arange(g.ncols) - nb + g.i0) % g.itdm if g.periodic_i else np.arange(g.ncols) - nb + g.i0
+    okj, oki = (js >= 0) & (js < g.jtdm), (is_ >= 0) & (is_ < g.itdm)
+    sea_h[np.ix_(okj, oki)] = sea[np.ix_(js[okj], is_[oki])] != 0
+    dpn = np.where(sea_h, dpn, 0.0)
+    dpm = np.where(sea_h, dpm, 0.0)
+    pbot = dpm.sum(axis=0)
+    pbot = np.where(sea_h, np.maximum(pbot, 9806.0), 0.0)
+    west = np.roll(pbot, 1, axis=1); south = np.roll(pbot, 1, axis=0)
+    depthu, depthv = np.minimum(pbot, west), np.minimum(pbot, south)
+    pint = np.concatenate([np.zeros((1,) + shp), np.cumsum(dpm, axis=0)])       # interfaces of dp(m)
+    def face_thk(shift_axis, depth):
+        lo = 0.5 * (pint + np.roll(pint, 1, axis=shift_axis))
+        return np.maximum(0.0, np.minimum(depth, lo[1:]) - np.minimum(depth, lo[:-1]))
+    dpu, dpv = face_thk(2, depthu), face_thk(1, depthv)
+    uf = syn.fill_host(cfg, g, sea, cabi.F_UFLX, 0, 0, 1, kk, 1)
+    vf = syn.fill_host(cfg, g, sea, cabi.F_VFLX, 0, 0, 1, kk, 1)
+    u = 0.3 * uf / max(np.abs(uf).max(), 1e-30)
+    v = 0.3 * vf / max(np.abs(vf).max(), 1e-30)
+    u = np.where(cb.iu != 0, u, 0.0); v = np.where(cb.iv != 0, v, 0.0)
+    ub = 0.1 * u.mean(axis=0); vb = 0.1 * v.mean(axis=0)
+    nanhalo = np.ones(shp, dtype=bool)
+    nanhalo[nb:nb + g.jj, nb:nb + g.ii] = False
+
+    def halo_nan(a):
+        a = np.array(a, dtype=np.float64)
+        a[..., nanhalo] = np.nan
+        return np.ascontiguousarray(a)
+    st = dict(
+        dp=halo_nan(np.stack([dpm, dpn] if n == 2 else [dpn, dpm])),
+        dpo=np.full((2, kk) + shp, np.nan),
+        u=halo_nan(np.stack([u, u * 0.9]) if m == 1 else np.stack([u * 0.9, u])),
+        v=halo_nan(np.stack([v, v * 0.9]) if m == 1 else np.stack([v * 0.9, v])),
+        dpu=halo_nan(np.stack([dpu, dpu]) ), dpv=halo_nan(np.stack([dpv, dpv])),
+        ubavg=halo_nan(np.stack([ub, ub, ub])), vbavg=halo_nan(np.stack([vb, vb, vb])),
+        dpmixl=halo_nan(np.stack([dpn[0] * 0.5, dpn[0] * 0.6])),
+        uflx=np.full((kk,) + shp, np.nan), vflx=np.full((kk,) + shp, np.nan),
+        uflxav=np.zeros((kk,) + shp), vflxav=np.zeros((kk,) + shp), dpav=np.zeros((kk,) + shp),
+        pbot=np.ascontiguousarray(pbot), depthu=np.ascontiguousarray(depthu), depthv=np.ascontiguousarray(depthv))
+    # geopar.F90:822-871: uflx, vflx are zero on the land faces that bound sea segments
+    st["uflx"][:, cb.iu == 0] = 0.0
+    st["vflx"][:, cb.iv == 0] = 0.0
+    return st
+
+
+def oracle_load_cnuity(ot, st):
+    ot.cnuity_alloc()
+    for name in ("dp", "dpo", "u", "v", "dpu", "dpv", "ubavg", "vbavg", "dpmixl", "uflx", "vflx", "uflxav", "vflxav",
+                 "dpav", "pbot", "depthu", "depthv"):
+        ot.f64(name)[...] = st[name]
