@@ -15,6 +15,8 @@ MXTRCR = 16
 
 F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER, F_ONETA, F_THETA, F_Q2, F_Q2L = range(11)
 (F_DPO, F_ONETAO, F_PBAVG, F_PBOT, F_OTEMP, F_OSALN, F_OTH3D, F_OTRACER, F_OQ2, F_OQ2L) = range(11, 21)
+(F_U, F_V, F_DPU, F_DPV, F_UBAVG, F_VBAVG, F_DEPTHU, F_DEPTHV, F_P, F_DPMIXL, F_UFLXAV, F_VFLXAV, F_DPAV, F_UTOTN,
+ F_VTOTN, F_DPMOLD) = range(21, 37)
 S_SCPX, S_SCPY, S_SCUX, S_SCUY, S_SCVX, S_SCVY, S_ONETA = range(10, 17)
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENBDY, EADVTYP, ENOMEM = range(7)
@@ -46,6 +48,11 @@ class Params(C.Structure):
         ("trcflg", C.c_int32 * MXTRCR), ("sigver", C.c_int32),
         ("delt1", C.c_double), ("temdf2", C.c_double), ("temdfc", C.c_double),
         ("thbase", C.c_double), ("onemm", C.c_double)]
+
+
+class CnuityParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("btrmas", "isopyc", "hybrid", "mxlkta", "nstep", "pad")] + [
+        (n, C.c_double) for n in ("delt1", "ra2fac", "thkdf2", "thkdf4")]
 
 
 class SynthCfg(C.Structure):
@@ -122,6 +129,7 @@ PROTOTYPES = {
     "hycom_tsadvc_set_deferred_range": (C.c_int, [_vp, C.c_int32]),
     "hycom_tsadvc_saln_range": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_int32)]),
     "hycom_tsadvc_checksum": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "hycom_tsadvc_cnuity_device": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(CnuityParams), _vp]),
     "hycom_synth_sea_mask": (C.c_int, [C.POINTER(SynthCfg), _vp]),
     "hycom_synth_fill_host": (C.c_int, [C.POINTER(SynthCfg), C.POINTER(SynthTile), _vp,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

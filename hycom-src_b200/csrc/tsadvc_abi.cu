@@ -93,17 +93,38 @@ Mirror* mirror_of(hycom_tsadvc_handle* h, int field, int ktr) {
     case HYCOM_F_OTRACER:
       if (ktr >= 1 && ktr <= h->d.ntracr) return &h->otracer[ktr - 1];
       return nullptr;
+    case HYCOM_F_U: return &h->u;
+    case HYCOM_F_V: return &h->v;
+    case HYCOM_F_DPU: return &h->dpu;
+    case HYCOM_F_DPV: return &h->dpv;
+    case HYCOM_F_UBAVG: return &h->ubavg;
+    case HYCOM_F_VBAVG: return &h->vbavg;
+    case HYCOM_F_DEPTHU: return &h->depthu;
+    case HYCOM_F_DEPTHV: return &h->depthv;
+    case HYCOM_F_P: return &h->p;
+    case HYCOM_F_DPMIXL: return &h->dpmixl;
+    case HYCOM_F_UFLXAV: return &h->uflxav;
+    case HYCOM_F_VFLXAV: return &h->vflxav;
+    case HYCOM_F_DPAV: return &h->dpav;
+    case HYCOM_F_UTOTN: return &h->utotn;
+    case HYCOM_F_VTOTN: return &h->vtotn;
+    case HYCOM_F_DPMOLD: return &h->dpmold;
   }
   return nullptr;
 }
 bool is3d(int field) {   // one time level only
   return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX || field == HYCOM_F_THETA || field == HYCOM_F_PBAVG ||
-         field == HYCOM_F_PBOT || (field >= HYCOM_F_OTEMP && field <= HYCOM_F_OQ2L);
+         field == HYCOM_F_PBOT || (field >= HYCOM_F_OTEMP && field <= HYCOM_F_OQ2L) ||
+         (field >= HYCOM_F_UBAVG && field <= HYCOM_F_P) || (field >= HYCOM_F_UFLXAV && field <= HYCOM_F_DPMOLD);
 }
 // slabs per time slot of a mirror
 int nlayers_of(const hycom_tsadvc_handle* h, int field) {
-  if (field == HYCOM_F_ONETA || field == HYCOM_F_ONETAO || field == HYCOM_F_PBOT) return 1;
-  if (field == HYCOM_F_PBAVG) return 3;
+  if (field == HYCOM_F_ONETA || field == HYCOM_F_ONETAO || field == HYCOM_F_PBOT || field == HYCOM_F_DEPTHU ||
+      field == HYCOM_F_DEPTHV || field == HYCOM_F_DPMIXL || field == HYCOM_F_UTOTN || field == HYCOM_F_VTOTN ||
+      field == HYCOM_F_DPMOLD)
+    return 1;
+  if (field == HYCOM_F_PBAVG || field == HYCOM_F_UBAVG || field == HYCOM_F_VBAVG) return 3;
+  if (field == HYCOM_F_P) return h->d.kdm + 1;
   if (field == HYCOM_F_Q2 || field == HYCOM_F_Q2L || field == HYCOM_F_OQ2 || field == HYCOM_F_OQ2L)
     return h->d.kdm + 2;   // layers 0..kk+1
   return h->d.kdm;
@@ -310,7 +331,7 @@ int hycom_tsadvc_destroy(hycom_tsadvc_handle* h) {
   if (h->range_host) cudaFreeHost(h->range_host);
   if (h->ev_range) cudaEventDestroy(h->ev_range);
   if (h->ev_xc) cudaEventDestroy(h->ev_xc);
-  cudaFree(h->d_cksum);
+  cudaFree(h->d_cksum); cudaFree(h->d_dpkmin);
   for (void* raw : h->raw_allocs) cudaFree(raw);  // field mirrors, flux block, static block
   cudaFree(h->mask); cudaFree(h->scuy); cudaFree(h->scvx);
   for (auto& kv : h->seg_cache) { cudaFree(kv.second.d[0]); cudaFree(kv.second.d[1]); }
@@ -504,7 +525,9 @@ static int halo_local_range(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, 
   const int nreg = h->d.nreg;
   // xctilr's itype (mod_tsadvc.F90:1829-1836): halo_ps = 1 for scalars, halo_uv = 13 / halo_vv = 14 for
   // the mass fluxes; it only matters across the arctic (nreg = 2)
-  const int itype = field == HYCOM_F_UFLX ? 13 : field == HYCOM_F_VFLX ? 14 : 1;
+  const int itype = (field == HYCOM_F_UFLX || field == HYCOM_F_U || field == HYCOM_F_UBAVG) ? 13
+                    : (field == HYCOM_F_VFLX || field == HYCOM_F_V || field == HYCOM_F_VBAVG) ? 14
+                    : field == HYCOM_F_DPU ? 3 : field == HYCOM_F_DPV ? 4 : 1;   // halo_uv, halo_vv, halo_us, halo_vs, halo_ps
   const int per_i = !(nreg == 0 || nreg == 4), per_j = nreg == 2 ? 100 + itype : nreg > 2;
   const int t0 = is3d(field) ? 1 : (tlev == 0 ? 1 : tlev);
   const int t1 = is3d(field) ? 1 : (tlev == 0 ? 2 : tlev);
@@ -1731,6 +1754,100 @@ int hycom_tsadvc_checksum(hycom_tsadvc_handle* h, int32_t field, int32_t ktr, in
   CU(h, cudaMemcpyAsync(&v, h->d_cksum, sizeof v, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   *sum = (uint64_t)v;
+  return 0;
+}
+
+// ---- cnuity(m,n) on the device mirrors (cnuity.F90) ------------------------------------------------
+int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_cnuity_params* prm,
+                               double* dpkmin) {
+  if (!h || !prm) return fail(h, HYCOM_TSADVC_EINVAL, "cnuity: null argument");
+  if (!h->have_static) return fail(h, HYCOM_TSADVC_EINVAL, "cnuity: set_static has not been called");
+  if (m < 1 || m > 2 || n < 1 || n > 2 || m == n) return fail(h, HYCOM_TSADVC_EINVAL, "cnuity: bad leapfrog slots m=%d n=%d", m, n);
+  if (h->d.nbdy < 6) return fail(h, HYCOM_TSADVC_ENBDY, "error: cnuity needs nbdy >= 6 (mbdy = 6, cnuity.F90:98)");
+  if (prm->btrmas) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity with btrmas (oneta_u, oneta_v, onetacnt) is not built");
+  if (prm->thkdf2 != 0.0 || prm->thkdf4 != 0.0)
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity: interface smoothing (thkdf2/thkdf4, cnuity.F90:760-1124) is not built");
+  if (prm->hybrid && prm->mxlkta)
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity: vertical advection of dpmixl (hybrid & mxlkta, :1148-1324) is not built");
+  if (!h->scuy || !h->scvx) return fail(h, HYCOM_TSADVC_EINVAL, "cnuity needs scuy, scvx (set_static)");
+  CU(h, cudaSetDevice(h->d.device));
+  const int kk = h->d.kdm;
+  const bool single = h->d.ipr * h->d.jpr == 1;
+  if (!single && !h->xc) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity on %d x %d tiles needs a communicator", h->d.ipr, h->d.jpr);
+  int rc;
+  CnuityParams P;
+  memset(&P, 0, sizeof P);
+  double *um, *vm, *dpum, *dpvm, *ub, *vb, *du, *dv, *pb, *uflx, *vflx;
+  if ((rc = slot(h, HYCOM_F_DP, 0, n, &P.dp_n)) || (rc = slot(h, HYCOM_F_DP, 0, m, &P.dp_m)) ||
+      (rc = slot(h, HYCOM_F_DPO, 0, n, &P.dpo_n)) || (rc = slot(h, HYCOM_F_DPO, 0, m, &P.dpo_m)) ||
+      (rc = slot(h, HYCOM_F_U, 0, m, &um)) || (rc = slot(h, HYCOM_F_V, 0, m, &vm)) ||
+      (rc = slot(h, HYCOM_F_DPU, 0, m, &dpum)) || (rc = slot(h, HYCOM_F_DPV, 0, m, &dpvm)) ||
+      (rc = slot(h, HYCOM_F_UBAVG, 0, 1, &ub)) || (rc = slot(h, HYCOM_F_VBAVG, 0, 1, &vb)) ||
+      (rc = slot(h, HYCOM_F_DEPTHU, 0, 1, &du)) || (rc = slot(h, HYCOM_F_DEPTHV, 0, 1, &dv)) ||
+      (rc = slot(h, HYCOM_F_PBOT, 0, 1, &pb)) || (rc = slot(h, HYCOM_F_UFLX, 0, 1, &uflx)) ||
+      (rc = slot(h, HYCOM_F_VFLX, 0, 1, &vflx)) || (rc = slot(h, HYCOM_F_P, 0, 1, &P.p)) ||
+      (rc = slot(h, HYCOM_F_DPMIXL, 0, n, &P.dpmixl_n)) || (rc = slot(h, HYCOM_F_DPMOLD, 0, 1, &P.dpmold)) ||
+      (rc = slot(h, HYCOM_F_UTOTN, 0, 1, &P.utotn)) || (rc = slot(h, HYCOM_F_VTOTN, 0, 1, &P.vtotn)))
+    return rc;
+  P.u_m = um; P.v_m = vm; P.dpu_m = dpum; P.dpv_m = dpvm;
+  P.ubavg_m = ub + h->slab * (m - 1); P.vbavg_m = vb + h->slab * (m - 1);
+  P.depthu = du; P.depthv = dv; P.pbot = pb; P.uflx = uflx; P.vflx = vflx;
+  P.uflxav = h->uflxav.lev[0]; P.vflxav = h->vflxav.lev[0]; P.dpav = h->dpav.lev[0];
+  if (!h->cnuity_scratch && (rc = dalloc_field(h, &h->cnuity_scratch, 9 * (size_t)kk * h->slab))) return rc;
+  if (!h->d_dpkmin && (rc = dalloc(h, (void**)&h->d_dpkmin, sizeof(double) * 2 * kk, false))) return rc;
+  const long L = (long)kk * h->slab;
+  double* s0 = h->cnuity_scratch;
+  P.u3 = s0; P.uf = s0 + L; P.vf = s0 + 2 * L; P.uf2 = s0 + 3 * L; P.vf2 = s0 + 4 * L; P.r1 = s0 + 5 * L;
+  P.r2 = s0 + 6 * L; P.tnu = s0 + 7 * L; P.tnv = s0 + 8 * L;
+  P.dpkmin = h->d_dpkmin;
+  P.pitch = h->pitch; P.nrows = h->nrows; P.nbdy = h->d.nbdy; P.ii = h->d.ii; P.jj = h->d.jj; P.kk = kk;
+  P.slab = h->slab; P.mask = h->mask; P.scuy = h->scuy; P.scvx = h->scvx; P.scp2i = h->scp2i;
+  P.delt1 = prm->delt1; P.ra2fac = prm->ra2fac; P.isopyc = prm->isopyc;
+  // :100-107 the eight xctilr calls, width 6
+  if (single) {
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_DPMIXL, 0, n, 6, 6)) || (rc = hycom_tsadvc_halo_local(h, HYCOM_F_DP, 0, 0, 6, 6)) ||
+        (rc = hycom_tsadvc_halo_local(h, HYCOM_F_DPU, 0, m, 6, 6)) || (rc = hycom_tsadvc_halo_local(h, HYCOM_F_DPV, 0, m, 6, 6)) ||
+        (rc = hycom_tsadvc_halo_local(h, HYCOM_F_U, 0, m, 6, 6)) || (rc = hycom_tsadvc_halo_local(h, HYCOM_F_V, 0, m, 6, 6)) ||
+        (rc = halo_local_range(h, HYCOM_F_UBAVG, 0, 1, 6, 6, m - 1, 1)) || (rc = halo_local_range(h, HYCOM_F_VBAVG, 0, 1, 6, 6, m - 1, 1)))
+      return rc;
+  } else {
+    // one exchange of kk-layer arrays (dp both slots, dpu, dpv, u, v) and one of the 2-D arrays
+    HaloArrays a;
+    memset(&a, 0, sizeof a);
+    double* b3[6] = {P.dp_n, P.dp_m, dpum, dpvm, um, vm};
+    const int t3[6] = {1, 1, 3, 4, 13, 14};
+    for (int q = 0; q < 6; ++q) { a.base[a.narr] = b3[q]; a.itype[a.narr++] = t3[q]; }
+    a.kk = kk; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+    a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 6; a.nh = 6; a.fold = arctic_fold(h->d);
+    if ((rc = xc_exchange(h, a, false, h->stream))) return rc;
+    HaloArrays b = a;
+    b.narr = 0;
+    double* b2[3] = {P.dpmixl_n, ub + h->slab * (m - 1), vb + h->slab * (m - 1)};
+    const int t2[3] = {1, 13, 14};
+    for (int q = 0; q < 3; ++q) { b.base[b.narr] = b2[q]; b.itype[b.narr++] = t2[q]; }
+    b.kk = 1;
+    if ((rc = xc_exchange(h, b, false, h->stream))) return rc;
+  }
+  if ((rc = launch_cnuity(0, P, h->stream))) return fail(h, HYCOM_TSADVC_ECUDA, "cnuity kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  h->launches += 10;
+  // :1400 xctilr(dp(:,:,:,n), 1,kk, 6,6, halo_ps), then the Robert-Asselin filter
+  if (single) {
+    if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_DP, 0, n, 6, 6))) return rc;
+  } else {
+    HaloArrays a;
+    memset(&a, 0, sizeof a);
+    a.base[0] = P.dp_n; a.itype[0] = 1; a.narr = 1;
+    a.kk = kk; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+    a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 6; a.nh = 6; a.fold = arctic_fold(h->d);
+    if ((rc = xc_exchange(h, a, false, h->stream))) return rc;
+  }
+  if ((rc = launch_cnuity(1, P, h->stream))) return fail(h, HYCOM_TSADVC_ECUDA, "cnuity kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  h->launches += 1;
+  if (dpkmin && prm->nstep % 3 == 0) {   // :513-516: evaluated every third step
+    CU(h, cudaMemcpyAsync(dpkmin, h->d_dpkmin, sizeof(double) * 2 * kk, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  CU(h, cudaGetLastError());
   return 0;
 }
 

@@ -49,6 +49,11 @@ struct hycom_tsadvc_handle {
   // otemp/osaln/oth3d/otracer (kdm), oq2/oq2l (kdm+2)
   tsadvc::Mirror dpo, onetao, pbavg, pbot, otemp, osaln, oth3d, oq2, oq2l;
   tsadvc::Mirror otracer[HYCOM_TSADVC_MXTRCR];
+  // cnuity.F90 operands: u, v, dpu, dpv (kdm per slot), ubavg, vbavg (3 slabs), depthu, depthv (1), p (kdm+1),
+  // dpmixl (1 per slot), uflxav, vflxav, dpav (kdm), utotn, vtotn, dpmold (1)
+  tsadvc::Mirror u, v, dpu, dpv, ubavg, vbavg, depthu, depthv, p, dpmixl, uflxav, vflxav, dpav, utotn, vtotn, dpmold;
+  double* cnuity_scratch = nullptr;   // 9*kdm slabs
+  double* d_dpkmin = nullptr;         // 2*kdm
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
   // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)]
   double* flux_block = nullptr;

@@ -209,3 +209,26 @@ struct AsselinParams {
 int launch_asselin(int stage, const AsselinParams& P, cudaStream_t stream);
 
 }  // namespace tsadvc
+
+// ---- cnuity(m,n) on the device mirrors (cnuity.cu; cnuity.F90) ---------------------------------
+namespace tsadvc {
+
+struct CnuityParams {
+  int pitch, nrows, nbdy, ii, jj, kk;
+  long slab;
+  const uint8_t* mask;
+  const double *scuy, *scvx, *scp2i, *depthu, *depthv, *pbot;
+  double *dp_n, *dp_m, *dpo_n, *dpo_m;          // (:,:,1,n|m)
+  const double *u_m, *v_m, *dpu_m, *dpv_m;      // (:,:,1,m)
+  const double *ubavg_m, *vbavg_m;              // (:,:,m)
+  double *dpmixl_n, *dpmold;
+  double *uflx, *vflx, *p, *utotn, *vtotn;
+  double *uflxav, *vflxav, *dpav;               // may be null: not accumulated
+  double *u3, *uf, *vf, *uf2, *vf2, *r1, *r2, *tnu, *tnv;   // scratch, kk slabs each
+  double* dpkmin;                               // 2*kk (device)
+  double delt1, ra2fac;
+  int isopyc;
+};
+int launch_cnuity(int stage, const CnuityParams& P, cudaStream_t stream);
+
+}  // namespace tsadvc

@@ -225,7 +225,9 @@ class Tsadvc:
         g = self.cb.geom
         if nk is None:
             nlay = {cabi.F_ONETA: 1, cabi.F_ONETAO: 1, cabi.F_PBOT: 1, cabi.F_PBAVG: 3, cabi.F_Q2: g.kdm + 2,
-                    cabi.F_Q2L: g.kdm + 2, cabi.F_OQ2: g.kdm + 2, cabi.F_OQ2L: g.kdm + 2}.get(fld, g.kdm)
+                    cabi.F_Q2L: g.kdm + 2, cabi.F_OQ2: g.kdm + 2, cabi.F_OQ2L: g.kdm + 2, cabi.F_UBAVG: 3,
+                    cabi.F_VBAVG: 3, cabi.F_DEPTHU: 1, cabi.F_DEPTHV: 1, cabi.F_P: g.kdm + 1, cabi.F_DPMIXL: 1,
+                    cabi.F_UTOTN: 1, cabi.F_VTOTN: 1, cabi.F_DPMOLD: 1}.get(fld, g.kdm)
             nk = nlay - k0 + 1
         out = np.empty((nk, g.nrows, g.ncols))
         self._ck(self.lib.hycom_tsadvc_download(self.h, fld, ktr, tlev, k0, nk, _ptr(out)))
@@ -299,6 +301,35 @@ class Tsadvc:
         p = self.cb.params()
         self._ck(self.lib.hycom_tsadvc_asselin_filter_device(self.h, m, n, C.byref(p), self.cb.ra2fac,
                                                             self.cb.oneta0))
+
+    # -- upstream of the path: cnuity.F90 on the device mirrors ------------------
+    _CN_NLAY = None
+
+    def upload_cnuity_state(self, st: dict, m: int, n: int):
+        """every operand of cnuity(m,n) (a dict of arrays in the Fortran layout, tests/util.add_cnuity)"""
+        for t in (1, 2):
+            self.upload(cabi.F_DP, st["dp"][t - 1], t)
+        for fld, nm in ((cabi.F_U, "u"), (cabi.F_V, "v"), (cabi.F_DPU, "dpu"), (cabi.F_DPV, "dpv")):
+            self.upload(fld, st[nm][m - 1], m)
+        self.upload(cabi.F_UBAVG, st["ubavg"], 1)
+        self.upload(cabi.F_VBAVG, st["vbavg"], 1)
+        for t in (1, 2):
+            self.upload(cabi.F_DPMIXL, st["dpmixl"][t - 1], t)
+        for fld, nm in ((cabi.F_DEPTHU, "depthu"), (cabi.F_DEPTHV, "depthv"), (cabi.F_PBOT, "pbot")):
+            self.upload(fld, st[nm], 1)
+        for fld, nm in ((cabi.F_UFLX, "uflx"), (cabi.F_VFLX, "vflx"), (cabi.F_UFLXAV, "uflxav"), (cabi.F_VFLXAV, "vflxav"),
+                        (cabi.F_DPAV, "dpav")):
+            self.upload(fld, st[nm], 1)
+
+    def cnuity_device(self, m: int, n: int, ra2fac: float = 0.125, thkdf2: float = 0.0, thkdf4: float = 0.0,
+                      mxlkta: bool = False):
+        """cnuity(m,n), cnuity.F90, on the device mirrors; returns dpkmin (2*kdm) when mod(nstep,3) == 0"""
+        cb = self.cb
+        p = cabi.CnuityParams(btrmas=int(cb.btrmas), isopyc=int(cb.isopyc), hybrid=int(cb.hybrid), mxlkta=int(mxlkta),
+                              nstep=cb.nstep, pad=0, delt1=cb.delt1, ra2fac=ra2fac, thkdf2=thkdf2, thkdf4=thkdf4)
+        out = np.full(2 * cb.geom.kdm, np.nan)
+        self._ck(self.lib.hycom_tsadvc_cnuity_device(self.h, m, n, C.byref(p), _ptr(out)))
+        return out
 
     # -- the path ---------------------------------------------------------
     def tsadvc(self, m: int, n: int):

@@ -73,7 +73,24 @@ enum {
   HYCOM_F_OTH3D = 17,
   HYCOM_F_OTRACER = 18,
   HYCOM_F_OQ2 = 19,     /* oq2, oq2l (:,:,0:kdm+1) */
-  HYCOM_F_OQ2L = 20
+  HYCOM_F_OQ2L = 20,
+  /* operands of cnuity (cnuity.F90), see hycom_tsadvc_cnuity_device below */
+  HYCOM_F_U = 21,       /* u, v, dpu, dpv (:,:,kdm,tlev) */
+  HYCOM_F_V = 22,
+  HYCOM_F_DPU = 23,
+  HYCOM_F_DPV = 24,
+  HYCOM_F_UBAVG = 25,   /* ubavg, vbavg (:,:,3), 3-D: tlev ignored, layer k0 = time slot 1..3 */
+  HYCOM_F_VBAVG = 26,
+  HYCOM_F_DEPTHU = 27,  /* depthu, depthv (:,:), one slab */
+  HYCOM_F_DEPTHV = 28,
+  HYCOM_F_P = 29,       /* p(:,:,kdm+1): kdm+1 slabs, 3-D */
+  HYCOM_F_DPMIXL = 30,  /* dpmixl(:,:,tlev): one slab per slot */
+  HYCOM_F_UFLXAV = 31,  /* uflxav, vflxav, dpav (:,:,kdm), 3-D */
+  HYCOM_F_VFLXAV = 32,
+  HYCOM_F_DPAV = 33,
+  HYCOM_F_UTOTN = 34,   /* utotn, vtotn, dpmold (:,:), one slab */
+  HYCOM_F_VTOTN = 35,
+  HYCOM_F_DPMOLD = 36
 };
 
 /* mod_dimensions.F90:33,45-49 + mod_xc tile geometry (mod_xc_mp.h:2317-3288) */
@@ -327,6 +344,26 @@ int hycom_tsadvc_asselin_save_device(hycom_tsadvc_handle *h, int32_t m, int32_t 
 int hycom_tsadvc_asselin_filter_device(hycom_tsadvc_handle *h, int32_t m, int32_t n,
                                        const hycom_tsadvc_params *prm, double ra2fac,
                                        double oneta0);
+
+/* ---- upstream of tsadvc in the time step: cnuity(m,n), the continuity
+ * equation (cnuity.F90), on the device mirrors.  It produces what tsadvc consumes - dp(:,:,:,n), uflx, vflx -
+ * so a device-resident step keeps them out of the host<->device traffic.
+ *   on entry : dp both slots, u, v, dpu, dpv (:,:,:,m), ubavg, vbavg (:,:,m), dpmixl(:,:,n), depthu, depthv,
+ *              pbot in their mirrors (hycom_tsadvc_upload); uflx, vflx zero on land faces (geopar.F90:822-871)
+ *   on exit  : dp(:,:,:,n) = t+1, dp(:,:,:,m) Robert-Asselin filtered, dpo both slots, uflx, vflx, p, utotn,
+ *              vtotn, dpmold (, dpmixl(:,:,n) if isopyc); uflxav, vflxav, dpav accumulated when their mirrors
+ *              exist (uploaded once)
+ * The xctilr calls of :100-107 and :1400 (width 6) are done here (single tile: locally; several tiles: through
+ * the communicator).  dpkmin (2*kdm reals, may be NULL) receives the per-layer minima of loops 14 and 15
+ * (:471, :679) of this tile when mod(nstep,3) == 0, as the reference evaluates them.
+ * Scope: .not.btrmas, thkdf2 = thkdf4 = 0 (no interface smoothing), no open-boundary faces, no Stokes
+ * drift, not (hybrid .and. mxlkta), not (synflt .and. wvelfl): anything else returns EUNSUPPORTED. */
+typedef struct hycom_cnuity_params {
+  int32_t btrmas, isopyc, hybrid, mxlkta, nstep, pad;
+  double delt1, ra2fac, thkdf2, thkdf4;
+} hycom_cnuity_params;
+int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle *h, int32_t m, int32_t n,
+                               const hycom_cnuity_params *prm, double *dpkmin);
 
 /* number of kernels this library launched on the handle since creation */
 int64_t hycom_tsadvc_launch_count(const hycom_tsadvc_handle *h);

@@ -1,0 +1,103 @@
+"""cnuity(m,n) (cnuity.F90) on the device mirrors through the C ABI against the CPU
+oracle, bit for bit: one tile, and ipr x jpr tiles through the library's communicator (the eight xctilr calls
+of :100-107 and the one of :1400 inside the call)."""
+import numpy as np
+import pytest
+
+import util
+from util import pkg, syn, cabi
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ts, g, cb, ref, m, n, kdm, g1=None, isopyc=False):
+    """device mirrors of one tile against the (single-tile) oracle result"""
+    nb = g.nbdy
+    g1 = g1 or g
+    win = (slice(g.j0, g.j0 + g.nrows), slice(g.i0, g.i0 + g.ncols)) if g1 is not g else (slice(None), slice(None))
+    inner = util.interior_sea(cb)
+    iu_in = np.zeros_like(inner); iv_in = np.zeros_like(inner)
+    iu_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iu[nb:nb + g.jj, nb:nb + g.ii] != 0
+    iv_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iv[nb:nb + g.jj, nb:nb + g.ii] != 0
+
+    def W(a):   # the tile's window of a single-tile array (..., nrows, ncols)
+        out = np.full(a.shape[:-2] + (g.nrows, g.ncols), np.nan)
+        src = a[(Ellipsis,) + win]
+        out[..., :src.shape[-2], :src.shape[-1]] = src
+        return out
+    dpn, dpm = ts.download(cabi.F_DP, n), ts.download(cabi.F_DP, m)
+    dpom = ts.download(cabi.F_DPO, m)
+    uflx, vflx = ts.download(cabi.F_UFLX, 1), ts.download(cabi.F_VFLX, 1)
+    p = ts.download(cabi.F_P, 1)
+    for k in range(kdm):
+        assert np.array_equal(dpn[k][inner], W(ref["dp"][n - 1, k])[inner]), ("dp.n", k)
+        assert np.array_equal(dpm[k][inner], W(ref["dp"][m - 1, k])[inner]), ("dp.m", k)
+        assert np.array_equal(dpom[k][inner], W(ref["dpo"][m - 1, k])[inner]), ("dpo.m", k)
+        assert np.array_equal(uflx[k][iu_in], W(ref["uflx"][k])[iu_in]), ("uflx", k)
+        assert np.array_equal(vflx[k][iv_in], W(ref["vflx"][k])[iv_in]), ("vflx", k)
+        assert np.array_equal(p[k + 1][inner], W(ref["p"][k + 1])[inner]), ("p", k)
+    assert np.array_equal(ts.download(cabi.F_UTOTN, 1)[0][iu_in], W(ref["utotn"])[iu_in])
+    assert np.array_equal(ts.download(cabi.F_VTOTN, 1)[0][iv_in], W(ref["vtotn"])[iv_in])
+    assert np.array_equal(ts.download(cabi.F_DPAV, 1)[0][inner], W(ref["dpav"][0])[inner])
+    assert np.array_equal(ts.download(cabi.F_UFLXAV, 1)[kdm - 1][iu_in], W(ref["uflxav"][kdm - 1])[iu_in])
+    if isopyc:
+        assert np.array_equal(ts.download(cabi.F_DPMIXL, n)[0][inner], W(ref["dpmixl"][n - 1])[inner])
+
+
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,m,n,isopyc", [
+    (150, 150, 6, 0, 1, 2, False),     # BASELINE configs[0] basin
+    (131, 77, 3, 3, 2, 1, False),      # doubly periodic, slots swapped
+    (64, 90, 3, 1, 1, 2, True),        # periodic in i; isopyc: dpmixl(n) = dp(1,n)
+    (70, 45, 2, 4, 1, 2, False),
+])
+def test_cnuity_device_matches_oracle(oracle, itdm, jtdm, kdm, nreg, m, n, isopyc):
+    extra = dict(isopyc=True, hybrid=False, nhybrd=0) if isopyc else {}
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=23, m=m, n=n, nstep=3, **extra)
+    st = util.add_cnuity(cfg, sea, g, cb, m, n)
+    ref = util.run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=isopyc)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_cnuity_state(st, m, n)
+    l0 = ts.launch_count
+    dpkmin = ts.cnuity_device(m, n)
+    assert ts.launch_count - l0 >= 11
+    _check(ts, g, cb, ref, m, n, kdm, isopyc=isopyc)
+    assert np.array_equal(dpkmin, ref["dpkmin"])
+    ts.close()
+
+
+def test_cnuity_refuses_what_is_not_built():
+    cfg, sea, g, cb = util.make_case(40, 30, 2, seed=3)
+    st = util.add_cnuity(cfg, sea, g, cb, 1, 2)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_cnuity_state(st, 1, 2)
+    for kw in (dict(thkdf4=0.01), dict(thkdf2=0.01), dict(mxlkta=True)):
+        with pytest.raises(cabi.TsadvcError) as e:
+            ts.cnuity_device(1, 2, **kw)
+        assert e.value.code == cabi.EUNSUPPORTED
+    cb.btrmas = True
+    with pytest.raises(cabi.TsadvcError) as e:
+        ts.cnuity_device(1, 2)
+    assert e.value.code == cabi.EUNSUPPORTED
+    ts.close()
+
+
+@pytest.mark.parametrize("ipr,jpr,nreg", [(2, 2, 0), (2, 1, 3), (4, 2, 0)])
+def test_cnuity_on_tiles(oracle, ipr, jpr, nreg):
+    """ipr x jpr tiles through the library's communicator == the oracle on one tile"""
+    from test_comm_gpu import make_tiles, run_tiles, close_tiles
+    m, n = 1, 2
+    itdm, jtdm, kdm = 160, 120, 3
+    cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=23, m=m, n=n, nstep=3)
+    st1 = util.add_cnuity(cfg, sea, g1, cb1, m, n)
+    ref = util.run_oracle_cnuity(oracle, cb1, sea, st1, m, n)
+    cbs = [syn.build_cb_arrays(cfg, g, sea, m, n, nstep=3) for g in pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)]
+    sts = [util.add_cnuity(cfg, sea, cb.geom, cb, m, n, uscale=st1["_uscale"]) for cb in cbs]
+    grp, tss = make_tiles(cfg, sea, itdm, jtdm, kdm, ipr, jpr, nreg, m, n, cbs=cbs)
+
+    def go(ts, r):
+        ts.upload_cnuity_state(sts[r], m, n)
+        ts.cnuity_device(m, n)
+    run_tiles(tss, go)
+    for ts, cb in zip(tss, cbs):
+        _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1)
+    close_tiles(grp, tss)

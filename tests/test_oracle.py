@@ -643,7 +643,7 @@ def test_reference_case_io_roundtrip(oracle, tmp_path):
 # ---------------------------------------------------------------------------------------
 def _np_cnuity(cb, g, st, m, n, ra2fac=0.125, isopyc=False):
     """the numpy path with the single-tile xctilr calls of cnuity.F90:100-107 and :1400"""
-    st = {k: v.copy() for k, v in st.items()}
+    st = {k: v.copy() for k, v in st.items() if not k.startswith("_")}
     nb = g.nbdy
     H = lambda a, it: npr.halo_single_tile(g, a, 6, 6, it)   # noqa: E731
     st["dpmixl"][n - 1] = H(st["dpmixl"][n - 1], 1)

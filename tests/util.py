@@ -176,7 +176,7 @@ def add_asselin(cfg, sea, g, cb, m, n, sigver=6, seed=77):
     return cb
 
 
-def add_cnuity(cfg, sea, g, cb, m, n, seed=91):
+def add_cnuity(cfg, sea, g, cb, m, n, seed=91, uscale=None):
     """operands of cnuity(m,n) (cnuity.F90) on top of a case, as a dict of arrays in the Fortran layout.
     Halos of the arrays cnuity exchanges itself (:100-107) are NaN, like every exchanged array; pbot, depthu,
     depthv arrive with valid halos.  u, v are O(0.3 m/s) smooth fields (both signs), zero off the iu / iv
@@ -206,8 +206,10 @@ def add_cnuity(cfg, sea, g, cb, m, n, seed=91):
     dpu, dpv = face_thk(2, depthu), face_thk(1, depthv)
     uf = syn.fill_host(cfg, g, sea, cabi.F_UFLX, 0, 0, 1, kk, 1)
     vf = syn.fill_host(cfg, g, sea, cabi.F_VFLX, 0, 0, 1, kk, 1)
-    u = 0.3 * uf / max(np.abs(uf).max(), 1e-30)
-    v = 0.3 * vf / max(np.abs(vf).max(), 1e-30)
+    if uscale is None:      # tiles of one case pass the single-tile value: the fields are functions of (i,j,k) only
+        uscale = (0.3 / max(np.abs(uf).max(), 1e-30), 0.3 / max(np.abs(vf).max(), 1e-30))
+    u = uscale[0] * uf
+    v = uscale[1] * vf
     u = np.where(cb.iu != 0, u, 0.0); v = np.where(cb.iv != 0, v, 0.0)
     ub = 0.1 * u.mean(axis=0); vb = 0.1 * v.mean(axis=0)
     nanhalo = np.ones(shp, dtype=bool)
@@ -228,6 +230,7 @@ def add_cnuity(cfg, sea, g, cb, m, n, seed=91):
         uflx=np.full((kk,) + shp, np.nan), vflx=np.full((kk,) + shp, np.nan),
         uflxav=np.zeros((kk,) + shp), vflxav=np.zeros((kk,) + shp), dpav=np.zeros((kk,) + shp),
         pbot=np.ascontiguousarray(pbot), depthu=np.ascontiguousarray(depthu), depthv=np.ascontiguousarray(depthv))
+    st["_uscale"] = uscale
     # geopar.F90:822-871: uflx, vflx are zero on the land faces that bound sea segments
     st["uflx"][:, cb.iu == 0] = 0.0
     st["vflx"][:, cb.iv == 0] = 0.0
@@ -239,3 +242,15 @@ def oracle_load_cnuity(ot, st):
     for name in ("dp", "dpo", "u", "v", "dpu", "dpv", "ubavg", "vbavg", "dpmixl", "uflx", "vflx", "uflxav", "vflxav",
                  "dpav", "pbot", "depthu", "depthv"):
         ot.f64(name)[...] = st[name]
+
+
+def run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=False):
+    """CPU oracle cnuity(m,n) on a private copy; returns the arrays it updates"""
+    ot = oracle_tile_from_cb(oracle, cb, sea)
+    oracle_load_cnuity(ot, st)
+    ot.set_i("isopyc", int(isopyc))
+    ot.cnuity(m, n, 1)
+    out = {k: ot.f64(k).copy() for k in ("dp", "dpo", "uflx", "vflx", "p", "utotn", "vtotn", "dpkmin", "dpmixl",
+                                         "uflxav", "vflxav", "dpav", "dpmold")}
+    ot.close()
+    return out
