@@ -364,8 +364,70 @@ class Run:
         return {"ms_step": ms_step, "value": cells / (ms_step * 1e-3), "roofline": roofline, "launches": int(launches),
                 "clocks": clocks, "alg": alg, "checksum": cks, "total_steps": self.nsteps, "slot": n}
 
+    def cnuity_timing(self, steps=3, warmup=1):
+        """cnuity(m,n) (cnuity.F90, the producer of dp(n), uflx, vflx) on the same device-resident state: its
+        operands are fabricated on the device from the synthetic generator (u, v of O(0.3 m/s) from the mass-flux
+        fields, dpu = dpv = dp(m), no depth limiting) - a timing of the sweeps, not a parity case (those are
+        tests/test_cnuity_gpu.py)."""
+        torch, ts, cabi, cfg = self.torch, self.ts, self.cabi, self.cfg
+        lib, C = ts.lib, cabi.C
+        kk = self.kdm
+        su = 1.0 / (cfg.dx0 * 150.0 * 9806.0)
+        m, n = 1, 2
+
+        def fill(gen, lev, scale, dst, tlev, nk, halo=1):
+            ts._ck(lib.hycom_tsadvc_synth_fill_to(ts.h, C.byref(cfg), gen, 0, lev, halo, scale, dst, tlev, 1, nk))
+        fill(cabi.F_UFLX, 0, su, cabi.F_U, m, kk)
+        fill(cabi.F_VFLX, 0, su, cabi.F_V, m, kk)
+        fill(cabi.F_DP, 1, 1.0, cabi.F_DPU, m, kk)
+        fill(cabi.F_DP, 1, 1.0, cabi.F_DPV, m, kk)
+        fill(cabi.F_UFLX, 0, 0.0, cabi.F_UBAVG, 1, 3)
+        fill(cabi.F_VFLX, 0, 0.0, cabi.F_VBAVG, 1, 3)
+        for dst in (cabi.F_DEPTHU, cabi.F_DEPTHV, cabi.F_PBOT):
+            fill(cabi.S_ONETA, 0, 1.0e9, dst, 1, 1)
+        for t in (1, 2):
+            fill(cabi.F_DP, 0, 0.5, cabi.F_DPMIXL, t, 1)
+        ts.synchronize()
+        l0 = ts.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for s in range(warmup + steps):
+            if s == warmup:
+                self.barrier()
+                e0.record(self.stream)
+                l0 = ts.launch_count
+            self.cb.nstep = s + 1
+            ts.cnuity_device(m, n)
+        e1.record(self.stream)
+        self.barrier()
+        ms = self.maxr(e0.elapsed_time(e1)) / steps
+        peak, _ = _peaks()
+        alg = self.g.ii * self.g.jj * kk * 104
+        return {"what": "cnuity(m,n) on the device mirrors (cnuity.F90), synthetic operands", "ms_per_call": ms,
+                "value": self.idm * self.jdm * kk / (ms * 1e-3), "unit": UNIT, "steps": steps,
+                "alg_bytes_per_call": alg, "alg_bytes_note": "104 B per layer-cell: read dp(n), dp(m), u, v, dpu, dpv; "
+                "write dp(n), dp(m), dpo(n), dpo(m), uflx, vflx, p", "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak, "gpu_launches": int(ts.launch_count - l0)}
+
     def close(self):
         self.ts.close()
+
+
+def _bind_to_gpu_numa_node(index):
+    """run this rank (and first-touch its pinned host arrays) on the CPUs next to its GPU: with eight ranks
+    uploading at once, host arrays on the far socket cap the per-rank H2D rate well below PCIe"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def run_b200(args):
@@ -382,22 +444,32 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the tsadvc path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = _bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     run = Run(args, args.workload, args.advtyp, args.ntracr, temdf2=args.temdf2, kdm_override=args.kdm)
+    run.numa = numa
     r = run.timed(args.steps, args.warmup)
     e2e = None
     if not args.no_e2e and not args.py_transport:
         e2e = run_e2e(args, run)
     g, idm, jdm, kdm = run.g, run.idm, run.jdm, run.kdm
+    cn = None
+    if not args.no_extra and world == 1 and not args.kdm:
+        try:
+            cn = run.cnuity_timing()
+        except Exception as e:  # noqa: BLE001
+            cn = {"failed": repr(e)[:300]}
     run.close()
     del run
     torch.cuda.empty_cache()
 
     # the other configurations BASELINE.json names, each with its own roofline, as `extra`
     extra = {}
+    if cn is not None:
+        extra["cnuity"] = cn
     if not args.no_extra and args.workload == "GLBb0.08" and args.advtyp == 2 and args.ntracr == 0 and not args.kdm:
         todo = []
         if world == 1:
@@ -515,7 +587,7 @@ def run_e2e(args, run):
     sec = run.maxr(sum(times) / len(times))
     return {"value": run.idm * run.jdm * kk / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": sec * 1e3, "steps": steps,
-            "h2d_gbs_per_rank": h2d / sec / 1e9,
+            "h2d_gbs_per_rank": h2d / sec / 1e9, "cpus_near_gpu": getattr(run, "numa", None),
             "api": "hycom_tsadvc_step (pinned host arrays, Fortran layout"
                    + (", NCCL halo exchange inside the call)" if run.world > 1 else ")")}
 

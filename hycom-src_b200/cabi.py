@@ -137,6 +137,8 @@ PROTOTYPES = {
     "hycom_tsadvc_synth_set_sea": (C.c_int, [_vp, C.POINTER(SynthCfg), _vp]),
     "hycom_tsadvc_synth_fill": (C.c_int, [_vp, C.POINTER(SynthCfg), C.c_int32, C.c_int32,
                                           C.c_int32, C.c_int32, C.c_int32, C.c_double]),
+    "hycom_tsadvc_synth_fill_to": (C.c_int, [_vp, C.POINTER(SynthCfg), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
 }
 
 _lib = None

@@ -73,4 +73,32 @@ int hycom_tsadvc_synth_fill(hycom_tsadvc_handle* h, const hycom_synth_cfg* cfg, 
   return 0;
 }
 
+// values of generator field `gen` (all layers of the destination, time level `lev`), times `scale`, written into
+// ANY mirror: how bench.py fabricates the operands of cnuity (u, v, dpu, dpv, ...) on the device for its timing
+namespace {
+__global__ void k_scale(double* a, long n, double s) {
+  for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long)gridDim.x * blockDim.x) a[q] = a[q] * s;
+}
+}  // namespace
+
+int hycom_tsadvc_synth_fill_to(hycom_tsadvc_handle* h, const hycom_synth_cfg* cfg, int32_t gen, int32_t ktr,
+                               int32_t lev, int32_t halo_mode, double scale, int32_t dst_field, int32_t dst_tlev,
+                               int32_t k0, int32_t nk) {
+  if (!h || !cfg || !h->d_sea) return HYCOM_TSADVC_EINVAL;
+  void* base;
+  int64_t pitch;
+  int rc = hycom_tsadvc_device_slab(h, dst_field, 0, dst_tlev, k0, &base, &pitch);
+  if (rc) return rc;
+  const synth::Cfg c = to_cfg(*cfg);
+  synth::Tile t;
+  t.idm = h->d.idm; t.jdm = h->d.jdm; t.nbdy = h->d.nbdy; t.ii = h->d.ii; t.jj = h->d.jj;
+  t.i0 = h->d.i0; t.j0 = h->d.j0; t.pad = 0;
+  k_synth_fill<<<148 * 8, 256, 0, h->stream>>>(c, t, h->d_sea, gen, ktr, lev, 1, nk, halo_mode, 0.0, (double*)base,
+                                                (int)pitch, h->slab);
+  if (scale != 1.0) k_scale<<<148 * 8, 256, 0, h->stream>>>((double*)base, h->slab * nk, scale);
+  h->launches += 2;
+  if (cudaGetLastError() != cudaSuccess) return HYCOM_TSADVC_ECUDA;
+  return 0;
+}
+
 }  // extern "C"

@@ -60,6 +60,12 @@ int hycom_tsadvc_synth_fill(hycom_tsadvc_handle *h, const hycom_synth_cfg *cfg,
                             int32_t field, int32_t ktr, int32_t tlev, int32_t lev,
                             int32_t halo_mode, double fill);
 
+/* layers k0 .. k0+nk-1 of ANY mirror `dst_field` filled with generator field `gen` (its layers 1..nk) times
+ * `scale`: bench.py fabricates the operands of cnuity (u, v, dpu, dpv, ...) this way for its timing */
+int hycom_tsadvc_synth_fill_to(hycom_tsadvc_handle *h, const hycom_synth_cfg *cfg, int32_t gen,
+                               int32_t ktr, int32_t lev, int32_t halo_mode, double scale,
+                               int32_t dst_field, int32_t dst_tlev, int32_t k0, int32_t nk);
+
 #ifdef __cplusplus
 }
 #endif
