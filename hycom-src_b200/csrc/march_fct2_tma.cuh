@@ -148,24 +148,30 @@ struct Fct2Scheme {
     ld_east<NC, R::C>(p, s1, Cc, Ce);
     unsigned mw[NC], me[NC];
     Cww[0] = ld_at<NC, R::C>(p.w2, s1);
-    mw[0] = ld_mask_at<NC>(p.w, s1);
-    me[NC - 1] = ld_mask_at<NC>(p.e, s1);
-    if (NC == 2) { Cww[NC - 1] = Cw[0]; mw[NC - 1] = mk(m1, 0); me[0] = mk(m1, 1); }
+    if (NC == 2) Cww[NC - 1] = Cw[0];
+    if (!ALLSEA) {   // (the mask plane is not staged for the mask-free body)
+      mw[0] = ld_mask_at<NC>(p.w, s1);
+      me[NC - 1] = ld_mask_at<NC>(p.e, s1);
+      if (NC == 2) { mw[NC - 1] = mk(m1, 0); me[0] = mk(m1, 1); }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { mw[c] = 0xffu; me[c] = 0xffu; }
+    }
     const double ft14 = 7.0 / 12.0, ft24 = -1.0 / 12.0;              // :1398-1399
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const unsigned mc = mk(m1, c);
       const double U = U1[c], V = V1[c];
-      const bool lowx = !(mw[c] & M_IU) || !(me[c] & M_IU);         // iu(i-1)==0 .or. iu(i+1)==0
-      const bool lowy = !(mk(s.m2, c) & M_IV) || !(mk(m0, c) & M_IV);
+      const bool lowx = !ALLSEA && (!(mw[c] & M_IU) || !(me[c] & M_IU));         // iu(i-1)==0 .or. iu(i+1)==0
+      const bool lowy = !ALLSEA && (!(mk(s.m2, c) & M_IV) || !(mk(m0, c) & M_IV));
       const double fhx2 = U * 0.5 * (Cc[c] + Cw[c]);
       const double fhx4 = U * (ft14 * (Cc[c] + Cw[c]) + ft24 * (Ce[c] + Cww[c]));
       const double fhy2 = V * 0.5 * (Cc[c] + Cs[c]);
       const double fhy4 = V * (ft14 * (Cc[c] + Cs[c]) + ft24 * (Cn[c] + Css[c]));
       const double fhx = lowx ? fhx2 : fhx4;
       const double fhy = lowy ? fhy2 : fhy4;
-      s.FAX[b3][c] = (mc & M_IU) ? fhx - s.FLXR[b3][c] : 0.0;
-      s.FAY[b3][c] = (mc & M_IV) ? fhy - s.FLY[b3][c] : 0.0;
+      s.FAX[b3][c] = (ALLSEA || (mc & M_IU)) ? fhx - s.FLXR[b3][c] : 0.0;
+      s.FAY[b3][c] = (ALLSEA || (mc & M_IV)) ? fhy - s.FLY[b3][c] : 0.0;
     }
   }
 

@@ -810,7 +810,7 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   // FCT2, MPDATA: the all-sea row segments go to the mask-free instantiation, the rest to the general
   // one (HYCOM_TSADVC_SPLIT=0: one general launch over the regular chunks)
   const char* cs = getenv("HYCOM_TSADVC_SPLIT");
-  if ((aadv == 2 || aadv == 1) && !p.btrmas && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
+  if ((aadv == 2 || aadv == 1 || aadv == 4) && !p.btrmas && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
     const hycom_tsadvc_handle::SegLists* L = nullptr;
     if ((rc = march_segments(h, P, part, chunk_rows, &L))) return rc;
     rc = 0;

@@ -188,9 +188,9 @@ def test_constant_field_preserved_on_device():
     assert (got["saln"][1][:, msk] == 35.25).all()
 
 
-@pytest.mark.parametrize("advtyp", [2, 1])
+@pytest.mark.parametrize("advtyp", [2, 1, 4])
 def test_all_sea_segments_equal_general_launch(oracle, advtyp, monkeypatch):
-    """FCT2 / MPDATA as the launch pair (all-sea row segments on the mask-free instantiation + the rest)
+    """FCT2 / MPDATA / FCT4 as the launch pair (all-sea row segments on the mask-free instantiation + the rest)
     == the single general launch == the oracle, bit for bit, on a grid with wide open water"""
     m, n = 1, 2
     cfg, sea, g, cb = util.make_case(420, 360, 2, nreg=0, ntracr=1, seed=12, m=m, n=n, advtyp=advtyp)
