@@ -49,13 +49,15 @@ struct Fct2T {                                       // computed intermediates o
   unsigned m1, m2, m3;                               // masks of rows r-1, r-2, r-3
 };
 
-template <int NC, int ORDER = 2, int SEA = 0>
+template <int NC, int ORDER = 2, int SEA = 0, int ISO = 0>
 struct Fct2Scheme {
   typedef Fct2T<NC> State;
   static constexpr bool kNeedC = true;
   static constexpr int kPeriod = 3;
   static constexpr int kLag = 3;               // the row finished in iteration r is row r-3
   static constexpr bool kNeedM = (SEA == 0);   // the mask plane is staged for the general body only
+  // ISO: the prolog is built from its own pair of mass fluxes (ring arrays U2, V2; isopyc layer 1)
+  static constexpr int kArrays = ISO ? 10 : (kNeedM ? 8 : 7);
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll
@@ -182,9 +184,18 @@ struct Fct2Scheme {
     ld_west<NC, R::F>(p, s1, F1, Fw);
     ld_east<NC, R::F>(p, s1, F1, Fe);
     ld_own<NC, R::F>(p, s2, F2);
-    ld_own<NC, R::U>(p, s1, U1);
-    ld_east<NC, R::U>(p, s1, U1, UE);
-    ld_own<NC, R::V>(p, s1, V1);
+    // mass fluxes of the prolog: rows r-1 (own and east face) and r
+    constexpr int PU = ISO ? (int)R::U2 : (int)R::U, PV = ISO ? (int)R::V2 : (int)R::V;
+    double VP0[NC];
+    ld_own<NC, PU>(p, s1, U1);
+    ld_east<NC, PU>(p, s1, U1, UE);
+    ld_own<NC, PV>(p, s1, V1);
+    if (ISO) {
+      ld_own<NC, PV>(p, s0, VP0);
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) VP0[c] = V0[c];
+    }
     ld_own<NC, R::D>(p, s1, D1);
     ld_own<NC, R::SCI>(p, s1, SCI1);
     double q[NC], b[NC], y[NC], fmx[NC], fmn[NC];
@@ -209,7 +220,7 @@ struct Fct2Scheme {
       }
       fmx[c] = mx; fmn[c] = mn;
       // tsadvc prolog :1934-1938 (onetamas(:,:,m) = 1.0 when .not.btrmas, :1809)
-      const double fdp = ((UE[c] - U1[c]) + (V0[c] - V1[c])) * dt2 * SCI1[c];
+      const double fdp = ((UE[c] - U1[c]) + (VP0[c] - V1[c])) * dt2 * SCI1[c];
       const double Dc = D1[c];
       const double fco = pos_part(Dc + fdp);
       const double fcn = pos_part(Dc);

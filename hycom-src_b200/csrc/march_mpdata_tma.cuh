@@ -34,13 +34,15 @@ struct MpdataT {
   unsigned m1, m2, m3;
 };
 
-template <int NC, int SEA = 0>
+template <int NC, int SEA = 0, int ISO = 0>
 struct MpdataScheme {
   typedef MpdataT<NC> State;
   static constexpr bool kNeedC = false;
   static constexpr int kPeriod = 3;
   static constexpr int kLag = 3;
   static constexpr bool kNeedM = (SEA == 0);   // the mask plane is staged for the general body only
+  // ISO: the prolog is built from its own pair of mass fluxes (ring arrays U2, V2; isopyc layer 1)
+  static constexpr int kArrays = ISO ? 10 : (kNeedM ? 8 : 7);
   static constexpr bool ALLSEA = (SEA != 0);
 
   static __device__ __forceinline__ void init(State& s) {
@@ -124,6 +126,17 @@ struct MpdataScheme {
       ld_own<NC, R::V>(p, s1, V1);
       ld_sea<R::D>(p, s1, m1, D1);
       ld_own<NC, R::SCI>(p, s1, SCI1);
+      // mass fluxes of the prolog (U1, V1 stay the advecting ones: M3 below)
+      double UP1[NC], UPE[NC], VP1[NC], VP0[NC];
+      if (ISO) {
+        ld_own<NC, R::U2>(p, s1, UP1);
+        ld_east<NC, R::U2>(p, s1, UP1, UPE);
+        ld_own<NC, R::V2>(p, s1, VP1);
+        ld_own<NC, R::V2>(p, s0, VP0);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { UP1[c] = U1[c]; UPE[c] = UE[c]; VP1[c] = V1[c]; VP0[c] = V0[c]; }
+      }
       double FDV[NC], FCO[NC], FCN[NC];
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
@@ -144,7 +157,7 @@ struct MpdataScheme {
         }
         const double MX = mx + posdef, MN = mn + posdef;
         // tsadvc prolog :1934-1938
-        const double fdp = ((UE[c] - U1[c]) + (V0[c] - V1[c])) * dt2 * SCI1[c];
+        const double fdp = ((UPE[c] - UP1[c]) + (VP0[c] - VP1[c])) * dt2 * SCI1[c];
         FCO[c] = fmax2(D1[c] + fdp, 0.0);
         FCN[c] = fmax2(D1[c], 0.0);
         // M2 :346-354

@@ -12,13 +12,15 @@ struct PcmT {
   unsigned m1;
 };
 
-template <int NC>
+template <int NC, int ISO = 0>
 struct PcmScheme {
   typedef PcmT<NC> State;
   static constexpr bool kNeedC = false;
   static constexpr int kPeriod = 6;
   static constexpr int kLag = 1;               // the row finished in iteration r is row r-1
   static constexpr bool kNeedM = true;
+  // ISO: the prolog is built from its own pair of mass fluxes (ring arrays U2, V2; isopyc layer 1)
+  static constexpr int kArrays = ISO ? 10 : 8;
 
   static __device__ __forceinline__ void init(State& s) {
 #pragma unroll
@@ -31,9 +33,9 @@ struct PcmScheme {
   template <int PH, bool SAFE>
   static __device__ __forceinline__ void step(State& s, const TmaCtx& x, const RingPtr& p, const int r,
                                               bool& bad) {
-    typedef Ring<NC> R;
+    typedef Ring<NC, kArrays> R;
     constexpr int p2 = PH & 1, q2 = p2 ^ 1;
-    constexpr int s0 = PH % 6, s1 = (PH + 5) % 6, s2 = (PH + 4) % 6;
+    const Off s0{(PH % 6) * R::SLOT}, s1{((PH + 5) % 6) * R::SLOT}, s2{((PH + 4) % 6) * R::SLOT};
     const double onemu = 9806.e-12;  // :519
     const double dt2 = x.dt2;
 
@@ -65,9 +67,17 @@ struct PcmScheme {
       ld_west<NC, R::F>(p, s1, F1, Fw);
       ld_east<NC, R::F>(p, s1, F1, Fe);
       ld_own<NC, R::F>(p, s2, F2);
-      ld_own<NC, R::U>(p, s1, U1);
-      ld_east<NC, R::U>(p, s1, U1, UE);
-      ld_own<NC, R::V>(p, s1, V1);
+      constexpr int PU = ISO ? (int)R::U2 : (int)R::U, PV = ISO ? (int)R::V2 : (int)R::V;
+      double VP0[NC];
+      ld_own<NC, PU>(p, s1, U1);
+      ld_east<NC, PU>(p, s1, U1, UE);
+      ld_own<NC, PV>(p, s1, V1);
+      if (ISO) {
+        ld_own<NC, PV>(p, s0, VP0);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) VP0[c] = V0[c];
+      }
       ld_own<NC, R::D>(p, s1, D1);
       ld_own<NC, R::SCI>(p, s1, SCI1);
 #pragma unroll
@@ -78,7 +88,7 @@ struct PcmScheme {
         maxmin_if(mx, mn, Fe[c], Fe[c], m1, M_PE << (8 * c));
         maxmin_if(mx, mn, F2[c], F2[c], m1, M_PS << (8 * c));
         maxmin_if(mx, mn, F0[c], F0[c], m1, M_PN << (8 * c));
-        const double fdp = ((UE[c] - U1[c]) + (V0[c] - V1[c])) * dt2 * SCI1[c];   // :1934-1938
+        const double fdp = ((UE[c] - U1[c]) + (VP0[c] - V1[c])) * dt2 * SCI1[c];   // :1934-1938
         const double fco = fmax2(D1[c] + fdp, 0.0);
         const double fcn = fmax2(D1[c], 0.0);
         const double flxdiv = ((s.DFLX[q2][c]) + (s.FLY[p2][c] - s.FLY[q2][c])) * dt2 * SCI1[c];

@@ -43,7 +43,9 @@ struct Ring {
   static constexpr int SLOT = NARR * RB;
   static constexpr int NSLOT = 6;
   static constexpr int BYTES = NSLOT * SLOT;           // per warp
-  enum { F = 0, C = 1, U = 2, V = 3, D = 4, SCI = 5, SC = 6, MSK = 7 };
+  // U2, V2: the mass fluxes of the prolog where they differ from the advecting ones (isopyc, layer 1:
+  // fco is built from the smoothed fluxes, the tracers are advected by uflx, vflx; NA = 10)
+  enum { F = 0, C = 1, U = 2, V = 3, D = 4, SCI = 5, SC = 6, MSK = 7, U2 = 8, V2 = 9 };
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -91,12 +93,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
+  uint64_t n, l, f;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(n));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(f));
+  return kind == 1 ? l : kind == 2 ? f : n;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 struct TmaCtx {
   // slabs of this (field, layer): element (row 0, column w0) of each staged array
   const double *fld, *fldc, *u, *v, *dp, *sci, *sc, *msk;
+  const double *u2, *v2;   // prolog fluxes (ten-array ring only)
   double* out;           // the output slab (ping-pong buffer) of this layer
   unsigned char* ring;   // this warp's ring (generic pointer into shared memory)
   uint32_t ring_s;       // same, shared-window address
@@ -107,7 +125,18 @@ struct TmaCtx {
   int j0, j1;
   double dt2, qdt2x2;
   double posdef;         // MPDATA offset (mod_tsadvc.F90:1762)
+  // the warps of this block that march the same rows of the same layer (T and S, tracers) meet at a
+  // named barrier every six rows, so that the rows of uflx, vflx, dp one of them fetched are still
+  // in L2 when the others ask for them (free-running warps drift apart by more than L2 holds: 63 % of
+  // those reads came from DRAM twice, profiles/r02p)
+  int grp_bar, grp_threads;   // barrier id (1..) and threads of the group; 0 threads: alone
+  // L2 eviction priority of the requests: the field rows are read once, the 2-D metrics and masks
+  // by every layer and field of the strip
+  uint64_t pol_fld, pol_flux, pol_static;
 };
+__device__ __forceinline__ void group_sync(const TmaCtx& x) {
+  if (x.grp_threads) asm volatile("bar.sync %0, %1;" ::"r"(x.grp_bar), "r"(x.grp_threads) : "memory");
+}
 
 // the source row of the next request: one warp-uniform element offset that walks down the slabs
 struct RowSrc {
@@ -119,20 +148,25 @@ __device__ __forceinline__ RowSrc row_src(const TmaCtx& x, int r) {
 }
 
 // request the row of `g` into the slot at byte offset `soff` of the ring (one lane)
-template <int NC, bool NEED_C, bool NEED_M = true>
+template <int NC, bool NEED_C, int NA = 8>
 __device__ __forceinline__ void issue_row(const TmaCtx& x, const RowSrc& g, uint32_t soff, uint32_t bar) {
-  typedef Ring<NC, NEED_M ? 8 : 7> R;
+  typedef Ring<NC, NA> R;
+  constexpr bool NEED_M = NA >= 8;
   const uint32_t dst = x.ring_s + soff;
   const long off = g.off;
   mbar_expect_tx(bar, R::SLOT - (NEED_C ? 0 : R::RB));
-  bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
-  if (NEED_C) bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
-  bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
-  bulk_g2s(dst + R::V * R::RB, x.v + off, R::RB, bar);
-  bulk_g2s(dst + R::D * R::RB, x.dp + off, R::RB, bar);
-  bulk_g2s(dst + R::SCI * R::RB, x.sci + off, R::RB, bar);
-  bulk_g2s(dst + R::SC * R::RB, x.sc + off, R::RB, bar);
-  if (NEED_M) bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);   // the mask-free bodies never read it
+  bulk_g2s_hint(dst + R::F * R::RB, x.fld + off, R::RB, bar, x.pol_fld);
+  if (NEED_C) bulk_g2s_hint(dst + R::C * R::RB, x.fldc + off, R::RB, bar, x.pol_fld);
+  bulk_g2s_hint(dst + R::U * R::RB, x.u + off, R::RB, bar, x.pol_flux);
+  bulk_g2s_hint(dst + R::V * R::RB, x.v + off, R::RB, bar, x.pol_flux);
+  bulk_g2s_hint(dst + R::D * R::RB, x.dp + off, R::RB, bar, x.pol_flux);
+  bulk_g2s_hint(dst + R::SCI * R::RB, x.sci + off, R::RB, bar, x.pol_static);
+  bulk_g2s_hint(dst + R::SC * R::RB, x.sc + off, R::RB, bar, x.pol_static);
+  if (NEED_M) bulk_g2s_hint(dst + R::MSK * R::RB, x.msk + off, R::RB, bar, x.pol_static);   // the mask-free bodies never read it
+  if (NA == 10) {
+    bulk_g2s_hint(dst + R::U2 * R::RB, x.u2 + off, R::RB, bar, x.pol_flux);
+    bulk_g2s_hint(dst + R::V2 * R::RB, x.v2 + off, R::RB, bar, x.pol_flux);
+  }
 }
 // step to the next row (every lane: the offset stays warp-uniform); rows outside the slab repeat the
 // nearest one
@@ -177,56 +211,8 @@ __device__ __forceinline__ void store_row_masked(const RingPtr& p, unsigned m, c
   store_cells<NC>(p, o);
 }
 
-template <int NC, int ARR>
-__device__ __forceinline__ void ld_own(const RingPtr& p, int slot, double (&x)[NC]) {
-  typedef Ring<NC> R;
-  const unsigned char* a = p.c + slot * R::SLOT + ARR * R::RB;
-  if (NC == 2) {
-    const double2 v = *reinterpret_cast<const double2*>(a);
-    x[0] = v.x; x[NC - 1] = v.y;
-  } else {
-    x[0] = *reinterpret_cast<const double*>(a);
-  }
-}
-template <int NC, int ARR>
-__device__ __forceinline__ void ld_west(const RingPtr& p, int slot, const double (&own)[NC],
-                                        double (&w)[NC]) {
-  typedef Ring<NC> R;
-  w[0] = *reinterpret_cast<const double*>(p.w + slot * R::SLOT + ARR * R::RB);
-  if (NC == 2) w[NC - 1] = own[0];
-}
-template <int NC, int ARR>
-__device__ __forceinline__ void ld_east(const RingPtr& p, int slot, const double (&own)[NC],
-                                        double (&e)[NC]) {
-  typedef Ring<NC> R;
-  e[NC - 1] = *reinterpret_cast<const double*>(p.e + slot * R::SLOT + ARR * R::RB);
-  if (NC == 2) e[0] = own[NC - 1];
-}
-// value of array ARR / mask byte at the column a per-lane pointer (p.w, p.e, p.w2) addresses
-template <int NC, int ARR>
-__device__ __forceinline__ double ld_at(const unsigned char* q, int slot) {
-  typedef Ring<NC> R;
-  return *reinterpret_cast<const double*>(q + slot * R::SLOT + ARR * R::RB);
-}
-template <int NC>
-__device__ __forceinline__ unsigned ld_mask_at(const unsigned char* q, int slot) {
-  typedef Ring<NC> R;
-  return *reinterpret_cast<const unsigned*>(q + slot * R::SLOT + R::MSK * R::RB);
-}
-template <int NC>
-__device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, int slot) {
-  typedef Ring<NC> R;
-  const unsigned char* a = p.c + slot * R::SLOT + R::MSK * R::RB;   // low word of the mask plane
-  unsigned m = *reinterpret_cast<const unsigned*>(a);
-  if (NC == 2) m |= *reinterpret_cast<const unsigned*>(a + 8) << 8;
-  return m;
-}
-
-
-
-// The same accessors for a slot given by its byte offset in the ring at run time (a scheme whose
-// register rings all have period 3 is unrolled three times, not six, so the slot of a row is no
-// longer a compile-time constant; the offset is warp-uniform).
+// Accessors of the staged rows; a slot is named by its byte offset in the ring (a compile-time constant
+// for a scheme unrolled six times, a warp-uniform register for one unrolled three times).
 struct Off { int b; };
 struct SlotOff { Off s0, s1, s2, s3; };   // slots of rows r, r-1, r-2, r-3
 template <int NC, int ARR>
@@ -287,7 +273,7 @@ __device__ __forceinline__ unsigned ld_mask_s(const RingPtr& p, Off o) {
 // ---------------------------------------------------------------------------------------
 template <class S, int NC, bool SAFE>
 __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p, uint32_t& round) {
-  typedef Ring<NC, S::kNeedM ? 8 : 7> R;
+  typedef Ring<NC, S::kArrays> R;
   typename S::State s;
   S::init(s);
   bool bad = false;
@@ -304,7 +290,7 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
   RowSrc g = row_src(x, r0);
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
-    if (elect_one()) issue_row<NC, S::kNeedC, S::kNeedM>(x, g, q * R::SLOT, x.bar_s + 8u * q);
+    if (elect_one()) issue_row<NC, S::kNeedC, S::kArrays>(x, g, q * R::SLOT, x.bar_s + 8u * q);
     next_row(x, g);
   }
   // this lane's output pointer walks down the slab one row per iteration (row r - kLag)
@@ -315,7 +301,7 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
   // rows past the chunk are drained below)
 #define TSADVC_ROW_TAIL(ROW, SOFF3, BAR3)                                                      \
   __syncwarp();                                                                              \
-  if (elect_one()) issue_row<NC, S::kNeedC, S::kNeedM>(x, g, SOFF3, BAR3);                   \
+  if (elect_one()) issue_row<NC, S::kNeedC, S::kArrays>(x, g, SOFF3, BAR3);                   \
   next_row(x, g);                                                      \
   q.outp += ostep;
 #define TSADVC_ROW_HEAD(ROW) q.rowok = (unsigned)((ROW) - S::kLag - x.j0) < (unsigned)nstore;
@@ -340,6 +326,7 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     for (int t = 0; t < niter; t += 3) {
       TSADVC_PHASE3(0) TSADVC_PHASE3(1) TSADVC_PHASE3(2)
       par ^= (hb != 0) ? 1u : 0u;               // the second half closes a round of six
+      if (!SAFE && hb != 0) group_sync(x);
       const uint32_t th = hb; hb = hc; hc = th;
       const uint32_t tb = bb; bb = bc; bc = tb;
     }
@@ -356,6 +343,7 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     for (int t = 0; t < niter; t += 6) {
       TSADVC_PHASE(0) TSADVC_PHASE(1) TSADVC_PHASE(2) TSADVC_PHASE(3) TSADVC_PHASE(4) TSADVC_PHASE(5)
       ++round;
+      if (!SAFE) group_sync(x);
     }
 #undef TSADVC_PHASE
   }

@@ -579,9 +579,8 @@ int plan_step(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   if (p.isopyc && (p.nhybrd != 0 || p.hybrid))
     return fail(h, HYCOM_TSADVC_EINVAL, "isopyc needs nhybrd = 0 and hybrid = .false. (blkdat.F90:1485): nhybrd=%d hybrid=%d",
                 p.nhybrd, p.hybrid);
-  if (p.isopyc && (h->d.ntracr > 0 || p.mxlmy || p.btrmas))
-    return fail(h, HYCOM_TSADVC_EUNSUPPORTED,
-                "isopyc with tracers, mxlmy or btrmas: layer 1 then mixes smoothed thickness changes with unsmoothed fluxes");
+  if (p.isopyc && p.btrmas)
+    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "isopyc with btrmas: advem_fct2c on smoothed layer-1 fluxes is not built");
   if (p.temdf2 > 0.0) {
     if (p.sigver < 1 || p.sigver > 8)
       return fail(h, HYCOM_TSADVC_EINVAL, "temdf2>0 needs the equation of state: sigver=%d not in 1..8", p.sigver);
@@ -635,17 +634,22 @@ int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, H
 // rows of pipeline fill and stay with the general kernel.  Built once per (part, nc, chunk rows).
 static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part, int chunk_rows,
                           const hycom_tsadvc_handle::SegLists** out) {
-  const long key = ((long)part << 40) | ((long)P.nc << 32) | (long)chunk_rows;
+  const long key = ((long)part << 40) | ((long)P.nc << 32) | (long)chunk_rows;   // (the band is fixed per process)
   auto it = h->seg_cache.find(key);
   if (it != h->seg_cache.end()) { *out = &it->second; return 0; }
   const int use = strip_use(P.nc), lead = strip_lead(P.nc), wid = 32 * P.nc;
   const int pitch = h->pitch, nrows = h->nrows;
   const int kMinRows = 48;
+  const char* cbnd = getenv("HYCOM_TSADVC_SEG_BAND");
+  // 256 rows: DRAM traffic of the launch pair 58.4 -> 53.8 GB at GLBb0.08 (the 64-column windows are not
+  // 128-byte aligned: a strip whose neighbour is elsewhere in j fetches 624 bytes per row and array for
+  // 464 useful ones; the regular chunks of a single launch reach 47.5 GB), profiles/r02u
+  const int band = std::max(48, std::min(cbnd ? atoi(cbnd) : 256, chunk_rows));
   std::vector<MarchSeg> seg[2];
   std::vector<char> good(nrows + 8), taken(nrows);
   for (int q = 0; q < P.nrect; ++q) {
     const MarchRect& R = P.rect[q];
-    const int fast_piece = (R.chunk_rows / 6) * 6;
+    const int fast_piece = (std::min(R.chunk_rows, band) / 6) * 6;
     for (int st = R.strip0; st < R.strip0 + R.nstrips; ++st) {
       const int w0 = st * use - lead;
       const bool cols_ok = w0 >= 0 && w0 + wid <= pitch;
@@ -667,10 +671,16 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
           int j0 = std::max(r + 3, R.row0), j1 = std::min(b - 3, R.row1);
           int len = ((j1 - j0) / 6) * 6;
           if (len >= kMinRows) {
-            for (int a = j0; a < j0 + len; a += fast_piece) {
-              const int e = std::min(a + fast_piece, j0 + len);
+            // pieces end at the common band boundaries (to within six rows), so that neighbouring strips
+            // march the same rows at the same time and share the 128-byte lines their windows overlap in
+            for (int a = j0; a < j0 + len;) {
+              int e = a + ((((a / band) + 1) * band - a) + 5) / 6 * 6;
+              if (e - a < 24) e += band / 6 * 6;
+              if (j0 + len - e < 24) e = j0 + len;
+              e = std::min(e, j0 + len);
               seg[0].push_back(MarchSeg{st, a, e, 0});
               for (int t = a; t < e; ++t) taken[t] = 1;
+              a = e;
             }
           }
           r = b;
@@ -680,7 +690,7 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
       while (r < R.row1) {
         if (taken[r]) { ++r; continue; }
         int b = r;
-        while (b < R.row1 && !taken[b] && b - r < R.chunk_rows) ++b;
+        while (b < R.row1 && !taken[b] && (b == r || b % band != 0)) ++b;
         seg[1].push_back(MarchSeg{st, r, b, 0});
         r = b;
       }
@@ -690,7 +700,7 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
   for (int c = 0; c < 2; ++c) {
     // neighbouring strips of the same rows next to each other: they share their aprons through L2
     std::stable_sort(seg[c].begin(), seg[c].end(), [&](const MarchSeg& a, const MarchSeg& b) {
-      const int ba = a.j0 / (chunk_rows > 0 ? chunk_rows : 1), bb = b.j0 / (chunk_rows > 0 ? chunk_rows : 1);
+      const int ba = (a.j0 + 12) / band, bb = (b.j0 + 12) / band;
       return ba != bb ? ba < bb : a.strip < b.strip;
     });
     L.n[c] = (long)seg[c].size();
@@ -708,7 +718,8 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
 // layers k0 .. k0+nk-1 (0-based; nk < 0: all)
 int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_params& p,
               const std::vector<Adv>& adv, int part, int k0 = 0, int nk = -1,
-              const double* u_over = nullptr, const double* v_over = nullptr) {
+              const double* u_over = nullptr, const double* v_over = nullptr,
+              const double* u_prolog = nullptr, const double* v_prolog = nullptr) {
   // the frame of a multi-tile step may run on its own stream (hycom_tsadvc_set_frame_stream), next
   // to the interior launch instead of behind it: it depends on the unpacked halos only
   cudaStream_t lst = (part == HYCOM_TSADVC_PART_FRAME && h->frame_stream) ? h->frame_stream : h->stream;
@@ -722,7 +733,7 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   // cells per lane (tuning knobs HYCOM_TSADVC_NC / _MINB / _CHUNK_ROWS).  Defaults measured on B200
   // (profiles/r01p_variants.txt): FCT2 and MPDATA 2 cells per lane at 2 blocks per SM (11.8 warp-
   // instructions per useful cell against 15.4 with one cell per lane), FCT4 and PCM 1 cell per lane
-  P.nc = (aadv == 0 || aadv == 4) ? 1 : cn ? (atoi(cn) == 2 ? 2 : 1) : 2;
+  P.nc = (aadv == 0 || aadv == 4 || u_prolog) ? 1 : cn ? (atoi(cn) == 2 ? 2 : 1) : 2;
   const long koff = h->slab * k0;
   for (int f = 0; f < P.nfld; ++f) {
     double *in, *ctr, *out;
@@ -743,6 +754,8 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   if ((rc = slot(h, HYCOM_F_DP, 0, n, &dpn))) return rc;
   P.u = u + koff; P.v = v + koff; P.dp = dpn + koff;
   if (u_over) { P.u = u_over; P.v = v_over; }   // isopyc layer 1: the smoothed fluxes, prolog included (:1930-1932)
+  // isopyc layer 1, tracers and q2, q2l: advected by uflx, vflx (:2016-2048) with the fco of the smoothed fluxes
+  P.u2 = u_prolog; P.v2 = v_prolog;
   P.slab = h->slab;
   P.njobs = P.nfld * kk;
   P.g.pitch = h->pitch; P.g.ncols = h->ncols; P.g.nrows = h->nrows; P.g.nbdy = h->d.nbdy;
@@ -750,8 +763,19 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   P.g.mask = h->mask; P.g.scp2 = h->scp2; P.g.scp2i = h->scp2i;
   P.g.mask64 = h->static_block + 2 * h->slab;
   P.g.delt1 = p.delt1; P.g.onemm = p.onemm;
+  if (const char* ca = getenv("HYCOM_TSADVC_DIAG_ALIAS")) {   // traffic diagnostics only: results are garbage
+    const int a = atoi(ca);
+    if (a & 1) P.g.scp2 = P.g.scp2i;
+    if (a & 2) { P.v = P.u; P.dp = P.u; }
+    if (a & 4) P.g.scp2 = P.g.scp2i = P.u;
+  }
+  const char* cg = getenv("HYCOM_TSADVC_GRPSYNC");
+  P.grpsync = cg ? atoi(cg) : 0;
+  const char* cl = getenv("HYCOM_TSADVC_L2HINT");
+  P.l2hint = cl ? atoi(cl) : 1;
   const char* cb = getenv("HYCOM_TSADVC_MINB");
   P.minb = cb ? atoi(cb) : (P.nc == 2 ? 2 : 3);
+  if (u_prolog) P.minb = 2;
   // rows one warp marches: long chunks amortise the 6 rows of pipeline fill (1024: 0.6 %), but the
   // launch needs about ten waves of blocks to hide the tail - small tiles get shorter chunks
   const char* ce = getenv("HYCOM_TSADVC_CHUNK_ROWS");
@@ -810,14 +834,14 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   // FCT2, MPDATA: the all-sea row segments go to the mask-free instantiation, the rest to the general
   // one (HYCOM_TSADVC_SPLIT=0: one general launch over the regular chunks)
   const char* cs = getenv("HYCOM_TSADVC_SPLIT");
-  if ((aadv == 2 || aadv == 1 || aadv == 4) && !p.btrmas && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
+  if ((aadv == 2 || aadv == 1 || aadv == 4) && !p.btrmas && !u_prolog && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
     const hycom_tsadvc_handle::SegLists* L = nullptr;
     if ((rc = march_segments(h, P, part, chunk_rows, &L))) return rc;
     rc = 0;
     for (int c = 1; c >= 0 && !rc; --c) {       // the general segments first: the long launch hides their tail
       if (!L->n[c]) continue;
       MarchParams Q = P;
-      Q.seg = (const MarchSeg*)L->d[c]; Q.nseg = L->n[c]; Q.allsea = (c == 0);
+      Q.seg = (const MarchSeg*)L->d[c]; Q.nseg = L->n[c]; Q.allsea = (c == 0) && !(cs && atoi(cs) == 2);
       Q.nunits = (long)Q.njobs * Q.nseg;
       rc = launch_march_tma(aadv, Q, lst);
       h->launches += 1;
@@ -856,7 +880,14 @@ int advect_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadv
                             h->d.nbdy, h->d.ii, h->d.jj, mbdy - 1, h->stream);
   h->launches += 1;
   if (rc) return fail(h, HYCOM_TSADVC_ECUDA, "isopyc smoothing launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-  if ((rc = run_march(h, m, n, p, adv, HYCOM_TSADVC_PART_ALL, 0, 1, h->isopyc_flux, h->isopyc_flux + h->slab))) return rc;
+  // layer 1: the thermodynamic fields on the smoothed fluxes (:1992-2005), every other field on uflx, vflx
+  // with the prolog of the smoothed ones (:1930-1932, :2016-2048)
+  std::vector<Adv> thermo, other;
+  for (const Adv& a : adv)
+    (a.field == HYCOM_F_TEMP || a.field == HYCOM_F_TH3D || a.field == HYCOM_F_SALN ? thermo : other).push_back(a);
+  double *us = h->isopyc_flux, *vs = h->isopyc_flux + h->slab;
+  if ((rc = run_march(h, m, n, p, thermo, HYCOM_TSADVC_PART_ALL, 0, 1, us, vs))) return rc;
+  if (!other.empty() && (rc = run_march(h, m, n, p, other, HYCOM_TSADVC_PART_ALL, 0, 1, nullptr, nullptr, us, vs))) return rc;
   if (h->d.kdm > 1 && (rc = run_march(h, m, n, p, adv, HYCOM_TSADVC_PART_ALL, 1, h->d.kdm - 1))) return rc;
   return 0;
 }

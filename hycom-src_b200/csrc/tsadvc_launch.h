@@ -27,6 +27,10 @@ struct MarchParams {
   const double* u;   // uflx(:,:,1)
   const double* v;   // vflx(:,:,1)
   const double* dp;  // dp(:,:,1,n)
+  // the mass fluxes the prolog (fco, mod_tsadvc.F90:1930-1938) is built from where they are not the
+  // advecting ones: isopyc, tracers and q2, q2l of layer 1 (:2016-2048).  nullptr otherwise
+  const double* u2;
+  const double* v2;
   long slab;         // doubles per 2-D slab (pitch*nrows)
   int njobs;         // nfld*kk; job = field + nfld*(k-1): T and S of a layer adjacent
   Geo g;
@@ -42,6 +46,8 @@ struct MarchParams {
   const MarchSeg* seg;
   long nseg;
   int allsea;       // every staged cell of every segment is sea (mask byte 0xff): mask-free body
+  int l2hint;       // L2 eviction priority of the row requests, decimal digits fld|flux|static: 0 normal, 1 last, 2 first
+  int grpsync;      // warps of a block on the same rows of a layer meet every six rows (march_tma_common.cuh)
 };
 
 // scheme: 1 = MPDATA, 2 = FCT2 (advtyp of blkdat.input, mod_tsadvc.F90:87-90)

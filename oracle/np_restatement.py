@@ -332,25 +332,29 @@ def tsadvc(cb, m, n):
     oem = cb.oneta[n - 1] if cb.btrmas else np.ones((g.nrows, g.ncols))
     ip, iu, iv = cb.ip, cb.iu, cb.iv
 
-    def adv(fld_n, fld_m, k, posdef, fco, fcn):
-        a = (g, fld_n, fld_m, uflx[k], vflx[k], fco, fcn, cb.scp2, cb.scp2i, cb.delt1, ip, iu, iv)
+    def adv(fld_n, fld_m, k, posdef, fco, fcn, uf=None, vf=None):
+        uk = uflx[k] if uf is None else uf
+        vk = vflx[k] if vf is None else vf
+        a = (g, fld_n, fld_m, uk, vk, fco, fcn, cb.scp2, cb.scp2i, cb.delt1, ip, iu, iv)
         if cb.advtyp == 2 and cb.btrmas:
-            return advem_fct2c(g, fld_n, fld_m, uflx[k], vflx[k], fco, cb.scp2, cb.scp2i, cb.delt1, ip, iu, iv)[0]
+            return advem_fct2c(g, fld_n, fld_m, uk, vk, fco, cb.scp2, cb.scp2i, cb.delt1, ip, iu, iv)[0]
         if cb.advtyp == 2:
             return advem_fct(a[0], 2, *a[1:])[0]
         if cb.advtyp == 4:
             return advem_fct(a[0], 4, *a[1:])[0]
         if cb.advtyp == 1:
-            return advem_mpdata(g, fld_n, uflx[k], vflx[k], fco, fcn, posdef, cb.scp2, cb.scp2i,
+            return advem_mpdata(g, fld_n, uk, vk, fco, fcn, posdef, cb.scp2, cb.scp2i,
                                 cb.delt1, ip, iu, iv)[0]
         if cb.advtyp == 0:
-            return advem_pcm(g, fld_n, uflx[k], vflx[k], fco, fcn, cb.scp2, cb.scp2i, cb.delt1,
+            return advem_pcm(g, fld_n, uk, vk, fco, fcn, cb.scp2, cb.scp2i, cb.delt1,
                              ip, iu, iv)[0]
         raise ValueError(cb.advtyp)
 
+    usm = vsm = None
     if cb.isopyc:
-        # :1859-1897 layer 1 runs on laterally smoothed mass fluxes (0.0 off the iu/iv points and
-        # outside margin mbdy-1, :1812-1813); a private copy so that the tracers keep uflx(:,:,1)
+        # :1859-1897 layer 1: th3d and saln run on laterally smoothed mass fluxes (0.0 off the iu/iv points
+        # and outside margin mbdy-1, :1812-1813) and so does the prolog (:1930-1932); the tracers and
+        # q2, q2l keep uflx(:,:,1) (:2016-2048)
         reg = _region(g, mbdy - 1)
         u1, v1 = uflx[0], vflx[0]
         vfa = np.where(_sh(iv, -1, 0) != 0, _sh(v1, -1, 0), v1)
@@ -360,18 +364,19 @@ def tsadvc(cb, m, n):
         with np.errstate(all="ignore"):
             usm = np.where(reg & (iu != 0), .5 * u1 + .25 * (ufa + ufb), 0.0)
             vsm = np.where(reg & (iv != 0), .5 * v1 + .25 * (vfa + vfb), 0.0)
-        uflx, vflx = uflx.copy(), vflx.copy()
-        uflx[0], vflx[0] = usm, vsm
     for k in range(kk):
-        fco, fcn = prolog(g, uflx[k], vflx[k], cb.dp[n - 1, k], oem, cb.delt1, cb.scp2i, ip, mbdy - 1)
+        smooth = cb.isopyc and k == 0
+        fco, fcn = prolog(g, usm if smooth else uflx[k], vsm if smooth else vflx[k], cb.dp[n - 1, k], oem,
+                          cb.delt1, cb.scp2i, ip, mbdy - 1)
+        ts = (usm, vsm) if smooth else (None, None)     # fluxes of the thermodynamic fields
         if cb.isopyc and k == 0 and not (cb.advflg == 1 and nhyb > 0):
-            th3d[n - 1, k] = adv(th3d[n - 1, k], th3d[m - 1, k], k, 32.0, fco, fcn)
+            th3d[n - 1, k] = adv(th3d[n - 1, k], th3d[m - 1, k], k, 32.0, fco, fcn, *ts)
         if k + 1 <= nhyb:
             if cb.advflg == 0:
                 temp[n - 1, k] = adv(temp[n - 1, k], temp[m - 1, k], k, 256.0, fco, fcn)
             else:
                 th3d[n - 1, k] = adv(th3d[n - 1, k], th3d[m - 1, k], k, 32.0, fco, fcn)
-        saln[n - 1, k] = adv(saln[n - 1, k], saln[m - 1, k], k, 0.0, fco, fcn)
+        saln[n - 1, k] = adv(saln[n - 1, k], saln[m - 1, k], k, 0.0, fco, fcn, *ts)
         for q in range(cb.ntracr):
             pd = 256.0 if (q < len(cb.trcflg) and cb.trcflg[q] == 2) else 0.0
             tracer[q, n - 1, k] = adv(tracer[q, n - 1, k], tracer[q, m - 1, k], k, pd, fco, fcn)

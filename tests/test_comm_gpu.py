@@ -144,6 +144,7 @@ HOST_CASES = [
     (2, 2, 0, 1, 2, {"btrmas": True}),                                   # advem_fct2c: five in-scheme exchanges
     (1, 2, 1, 0, 2, {"btrmas": True}),
     (2, 2, 0, 0, 2, {"isopyc": True, "hybrid": False, "nhybrd": 0}),     # smoothed layer-1 fluxes read the halo
+    (2, 1, 1, 2, 1, {"isopyc": True, "hybrid": False, "nhybrd": 0}),     # + tracers: two pairs of fluxes in layer 1
 ]
 
 

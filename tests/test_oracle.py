@@ -505,6 +505,29 @@ def test_isopyc_c_oracle_equals_numpy_restatement(oracle, advtyp, nreg):
     assert _sea_eq(ref["saln"][n - 1, 1], ref2["saln"][n - 1, 1], msk)                     # ... and only layer 1
 
 
+# isopyc with tracers and mxlmy: the tracers and q2, q2l of layer 1 keep uflx(:,:,1) while the prolog
+# (fco, fcn) is built from the smoothed fluxes (:1930-1932 against :2016-2048)
+@pytest.mark.parametrize("advtyp,nreg,mxlmy", [(2, 0, True), (1, 3, False), (4, 0, False), (0, 0, True)])
+def test_isopyc_with_tracers_c_oracle_equals_numpy_restatement(oracle, advtyp, nreg, mxlmy):
+    kw = dict(nreg=nreg, seed=9, advtyp=advtyp, isopyc=True, hybrid=False, nhybrd=0, ntracr=2, trcflg=[2, 0])
+    m, n = 2, 1
+    cfg, sea, g, cb = util.make_case(57, 44, 3, m=m, n=n, **kw)
+    if mxlmy:
+        util.add_q2(cfg, sea, g, cb, m, n)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    alt = npr.tsadvc(cb, m, n)
+    msk = util.interior_sea(cb)
+    for k in range(g.kdm):
+        assert _sea_eq(ref["saln"][n - 1, k], alt["saln"][n - 1, k], msk), ("saln", k)
+        assert _sea_eq(ref["th3d"][n - 1, k], alt["th3d"][n - 1, k], msk), ("th3d", k)
+        for q in range(2):
+            assert _sea_eq(ref["tracer"][q, n - 1, k], alt["tracer"][q, n - 1, k], msk), ("tracer", q, k)
+        if mxlmy:
+            assert _sea_eq(ref["q2"][n - 1, k + 1], alt["q2"][n - 1, k + 1], msk), ("q2", k)
+            assert _sea_eq(ref["q2l"][n - 1, k + 1], alt["q2l"][n - 1, k + 1], msk), ("q2l", k)
+    assert not _sea_eq(ref["tracer"][1, n - 1, 0], cb.tracer[1, n - 1, 0], msk)
+
+
 # ---- frozen vectors (tests/golden): the oracle and the numpy restatement reproduce them ---------
 import json as _json
 import os as _os

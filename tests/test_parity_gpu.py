@@ -764,8 +764,38 @@ def test_isopyc_host_path_matches_oracle(oracle, advtyp, nreg, temdf2):
     assert np.array_equal(got["xmin"], ref["xmin"]) and np.array_equal(got["xmax"], ref["xmax"])
 
 
-def test_isopyc_with_tracers_is_refused():
-    cfg, sea, g, cb = util.make_case(40, 30, 2, ntracr=1, advtyp=2, isopyc=True, hybrid=False, nhybrd=0)
+@pytest.mark.parametrize("advtyp,nreg,mxlmy,temdf2", [(2, 0, True, 0.0), (1, 3, False, 0.0), (4, 0, False, 0.0),
+                                                        (0, 1, True, 0.0), (2, 0, False, 0.02)])
+def test_isopyc_with_tracers_matches_oracle(oracle, advtyp, nreg, mxlmy, temdf2):
+    """isopyc with tracers / mxlmy (mod_tsadvc.F90:2016-2048): in layer 1 the tracers and q2, q2l are advected
+    by uflx, vflx against the fco of the smoothed fluxes (:1930-1932) - the ten-array ring of the march"""
+    m, n = 2, 1
+    kw = dict(nreg=nreg, seed=41, advtyp=advtyp, nstep=3, isopyc=True, hybrid=False, nhybrd=0, ntracr=2,
+              trcflg=[2, 0])
+    if temdf2 > 0:
+        cfg, sea, g, cb = util.make_diffusion_case(90, 61, 4, 8, 0.0, m=m, n=n, **kw)
+    else:
+        cfg, sea, g, cb = util.make_case(90, 61, 4, m=m, n=n, **kw)
+    if mxlmy:
+        util.add_q2(cfg, sea, g, cb, m, n)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    tr_before = cb.tracer.copy()
+    got, before, launches = _run_host_path(cb, m, n)
+    _compare(cb, g, got, ref, n, ["saln", "th3d"])
+    msk = util.interior_sea(cb)
+    for q in range(2):
+        for k in range(g.kdm):
+            assert np.array_equal(cb.tracer[q, n - 1, k][msk], ref["tracer"][q, n - 1, k][msk]), ("tracer", q, k)
+    assert not np.array_equal(cb.tracer[1, n - 1, 0][msk], tr_before[1, n - 1, 0][msk])
+    if mxlmy:
+        for name in ("q2", "q2l"):
+            for k in range(1, g.kdm + 1):
+                assert np.array_equal(getattr(cb, name)[n - 1, k][msk], ref[name][n - 1, k][msk]), (name, k)
+    assert np.array_equal(got["xmin"], ref["xmin"]) and np.array_equal(got["xmax"], ref["xmax"])
+
+
+def test_isopyc_with_btrmas_is_refused():
+    cfg, sea, g, cb = util.make_case(40, 30, 2, advtyp=2, isopyc=True, hybrid=False, nhybrd=0, btrmas=True)
     ts = pkg.Tsadvc(cb)
     ts.upload_state(1, 2)
     with pytest.raises(cabi.TsadvcError, match="isopyc"):

@@ -9,6 +9,7 @@
 #   benchq     bench.py quick (5 steps, no e2e / cpu / extra)
 #   ref        bench.py --impl reference
 #   launches   ncu launch list of a short bench run (N=1)
+#   traffic    DRAM bytes + L2 hit rate of the marching launches of one full-size step
 #   ncu        ncu --set full + source of the marching kernel (N=1, reduced kdm)
 #   tma        the tensor-map TMA probe, every variant in its own process
 #   nccl       tools/xc_nccl_check.py under torchrun (N = $NGPU >= 2)
@@ -47,6 +48,23 @@ for STEP in "$@"; do
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_tsadvc_march -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} -f -o $OUT/prof \
         python bench.py --kdm ${NCU_KDM:-6} --steps 1 --warmup 3 --no-e2e --no-cpu --no-extra $BENCH_ARGS > $OUT/ncu_run.log 2>&1; echo "rc=$?"; tail -2 $OUT/ncu_run.log | cut -c1-300
       ls -la $OUT/prof.ncu-rep ;;
+    traffic)
+      # DRAM bytes of the two marching launches of one full-size step (few counters: one replay pass)
+      timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none \
+        -k regex:k_tsadvc_march -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} --csv --log-file $OUT/traffic${TRAFFIC_TAG}.csv \
+        python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-extra $BENCH_ARGS > $OUT/traffic_run.log 2>&1; echo "rc=$?"
+      python - $OUT/traffic${TRAFFIC_TAG}.csv <<'PY'
+import csv, sys
+rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
+hdr = rows[0]; ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+tot = 0.0
+for r in rows[1:]:
+    print(r[ik][:60], r[im], r[iv], r[iu])
+    if r[im].startswith("dram__bytes"):
+        tot += float(r[iv].replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[r[iu]]
+print("dram total %.3f GB" % (tot / 1e9))
+PY
+      ;;
     tma)
       (cd tools/probe && nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe4 tma_probe4.cu -lcuda 2>/dev/null)
       for v in 0 1 2 3 4; do timeout 60 tools/probe/tma_probe4 $v; echo "exit=$?"; done > $OUT/tma_probe4.txt 2>&1; cat $OUT/tma_probe4.txt ;;
