@@ -93,21 +93,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-// the same with an L2 eviction-priority hint (createpolicy)
-__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
-                                              uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
-  uint64_t n, l, f;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(n));
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l));
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(f));
-  return kind == 1 ? l : kind == 2 ? f : n;
-}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -125,18 +110,7 @@ struct TmaCtx {
   int j0, j1;
   double dt2, qdt2x2;
   double posdef;         // MPDATA offset (mod_tsadvc.F90:1762)
-  // the warps of this block that march the same rows of the same layer (T and S, tracers) meet at a
-  // named barrier every six rows, so that the rows of uflx, vflx, dp one of them fetched are still
-  // in L2 when the others ask for them (free-running warps drift apart by more than L2 holds: 63 % of
-  // those reads came from DRAM twice, profiles/r02p)
-  int grp_bar, grp_threads;   // barrier id (1..) and threads of the group; 0 threads: alone
-  // L2 eviction priority of the requests: the field rows are read once, the 2-D metrics and masks
-  // by every layer and field of the strip
-  uint64_t pol_fld, pol_flux, pol_static;
 };
-__device__ __forceinline__ void group_sync(const TmaCtx& x) {
-  if (x.grp_threads) asm volatile("bar.sync %0, %1;" ::"r"(x.grp_bar), "r"(x.grp_threads) : "memory");
-}
 
 // the source row of the next request: one warp-uniform element offset that walks down the slabs
 struct RowSrc {
@@ -155,17 +129,17 @@ __device__ __forceinline__ void issue_row(const TmaCtx& x, const RowSrc& g, uint
   const uint32_t dst = x.ring_s + soff;
   const long off = g.off;
   mbar_expect_tx(bar, R::SLOT - (NEED_C ? 0 : R::RB));
-  bulk_g2s_hint(dst + R::F * R::RB, x.fld + off, R::RB, bar, x.pol_fld);
-  if (NEED_C) bulk_g2s_hint(dst + R::C * R::RB, x.fldc + off, R::RB, bar, x.pol_fld);
-  bulk_g2s_hint(dst + R::U * R::RB, x.u + off, R::RB, bar, x.pol_flux);
-  bulk_g2s_hint(dst + R::V * R::RB, x.v + off, R::RB, bar, x.pol_flux);
-  bulk_g2s_hint(dst + R::D * R::RB, x.dp + off, R::RB, bar, x.pol_flux);
-  bulk_g2s_hint(dst + R::SCI * R::RB, x.sci + off, R::RB, bar, x.pol_static);
-  bulk_g2s_hint(dst + R::SC * R::RB, x.sc + off, R::RB, bar, x.pol_static);
-  if (NEED_M) bulk_g2s_hint(dst + R::MSK * R::RB, x.msk + off, R::RB, bar, x.pol_static);   // the mask-free bodies never read it
+  bulk_g2s(dst + R::F * R::RB, x.fld + off, R::RB, bar);
+  if (NEED_C) bulk_g2s(dst + R::C * R::RB, x.fldc + off, R::RB, bar);
+  bulk_g2s(dst + R::U * R::RB, x.u + off, R::RB, bar);
+  bulk_g2s(dst + R::V * R::RB, x.v + off, R::RB, bar);
+  bulk_g2s(dst + R::D * R::RB, x.dp + off, R::RB, bar);
+  bulk_g2s(dst + R::SCI * R::RB, x.sci + off, R::RB, bar);
+  bulk_g2s(dst + R::SC * R::RB, x.sc + off, R::RB, bar);
+  if (NEED_M) bulk_g2s(dst + R::MSK * R::RB, x.msk + off, R::RB, bar);   // the mask-free bodies never read it
   if (NA == 10) {
-    bulk_g2s_hint(dst + R::U2 * R::RB, x.u2 + off, R::RB, bar, x.pol_flux);
-    bulk_g2s_hint(dst + R::V2 * R::RB, x.v2 + off, R::RB, bar, x.pol_flux);
+    bulk_g2s(dst + R::U2 * R::RB, x.u2 + off, R::RB, bar);
+    bulk_g2s(dst + R::V2 * R::RB, x.v2 + off, R::RB, bar);
   }
 }
 // step to the next row (every lane: the offset stays warp-uniform); rows outside the slab repeat the
@@ -326,7 +300,6 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     for (int t = 0; t < niter; t += 3) {
       TSADVC_PHASE3(0) TSADVC_PHASE3(1) TSADVC_PHASE3(2)
       par ^= (hb != 0) ? 1u : 0u;               // the second half closes a round of six
-      if (!SAFE && hb != 0) group_sync(x);
       const uint32_t th = hb; hb = hc; hc = th;
       const uint32_t tb = bb; bb = bc; bc = tb;
     }
@@ -343,7 +316,6 @@ __device__ __forceinline__ bool march_tma_pass(const TmaCtx& x, const RingPtr& p
     for (int t = 0; t < niter; t += 6) {
       TSADVC_PHASE(0) TSADVC_PHASE(1) TSADVC_PHASE(2) TSADVC_PHASE(3) TSADVC_PHASE(4) TSADVC_PHASE(5)
       ++round;
-      if (!SAFE) group_sync(x);
     }
 #undef TSADVC_PHASE
   }

@@ -763,16 +763,6 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   P.g.mask = h->mask; P.g.scp2 = h->scp2; P.g.scp2i = h->scp2i;
   P.g.mask64 = h->static_block + 2 * h->slab;
   P.g.delt1 = p.delt1; P.g.onemm = p.onemm;
-  if (const char* ca = getenv("HYCOM_TSADVC_DIAG_ALIAS")) {   // traffic diagnostics only: results are garbage
-    const int a = atoi(ca);
-    if (a & 1) P.g.scp2 = P.g.scp2i;
-    if (a & 2) { P.v = P.u; P.dp = P.u; }
-    if (a & 4) P.g.scp2 = P.g.scp2i = P.u;
-  }
-  const char* cg = getenv("HYCOM_TSADVC_GRPSYNC");
-  P.grpsync = cg ? atoi(cg) : 0;
-  const char* cl = getenv("HYCOM_TSADVC_L2HINT");
-  P.l2hint = cl ? atoi(cl) : 1;
   const char* cb = getenv("HYCOM_TSADVC_MINB");
   P.minb = cb ? atoi(cb) : (P.nc == 2 ? 2 : 3);
   if (u_prolog) P.minb = 2;
@@ -841,7 +831,7 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
     for (int c = 1; c >= 0 && !rc; --c) {       // the general segments first: the long launch hides their tail
       if (!L->n[c]) continue;
       MarchParams Q = P;
-      Q.seg = (const MarchSeg*)L->d[c]; Q.nseg = L->n[c]; Q.allsea = (c == 0) && !(cs && atoi(cs) == 2);
+      Q.seg = (const MarchSeg*)L->d[c]; Q.nseg = L->n[c]; Q.allsea = (c == 0);
       Q.nunits = (long)Q.njobs * Q.nseg;
       rc = launch_march_tma(aadv, Q, lst);
       h->launches += 1;

@@ -46,8 +46,6 @@ struct MarchParams {
   const MarchSeg* seg;
   long nseg;
   int allsea;       // every staged cell of every segment is sea (mask byte 0xff): mask-free body
-  int l2hint;       // L2 eviction priority of the row requests, decimal digits fld|flux|static: 0 normal, 1 last, 2 first
-  int grpsync;      // warps of a block on the same rows of a layer meet every six rows (march_tma_common.cuh)
 };
 
 // scheme: 1 = MPDATA, 2 = FCT2 (advtyp of blkdat.input, mod_tsadvc.F90:87-90)

@@ -40,6 +40,8 @@ def main():
              (256, 96, 2, 2, 0, 2, {"arctic": True, "diffusion_arctic": True}),
              # isopyc: layer 1 on laterally smoothed fluxes, which read the halo (no interior overlap)
              (150, 150, 3, 0, 0, 2, {"isopyc": True}),
+             # ... with a tracer: layer 1 advected by uflx with the prolog of the smoothed fluxes (ten-array ring)
+             (150, 150, 3, 0, 1, 1, {"isopyc": True}),
              # the drop-in entry on HOST arrays: upload, exchange per layer chunk, advect, download
              (150, 150, 5, 0, 1, 2, {"host": True}), (150, 150, 3, 0, 0, 2, {"host": True, "diffusion": (6, 1.0)})]
     py_transport = os.environ.get("XC_CHECK_PY", "0") == "1"
@@ -131,6 +133,13 @@ def main():
                 ok_all = ok_all and ok
                 if not ok:
                     print(f"rank {rank}: MISMATCH {name} step {step} case {(itdm, jtdm, nreg, advtyp, extra)}", flush=True)
+            for q in range(ntracr if "host" not in extra else 0):
+                dev = ts.download(cabi.F_TRACER, nn, ktr=q + 1)[:, nb:nb + g.jj, nb:nb + g.ii]
+                ref = ot.f64("tracer")[q, nn - 1][glob]
+                ok = np.array_equal(dev[:, sea_t], ref[:, sea_t])
+                ok_all = ok_all and ok
+                if not ok:
+                    print(f"rank {rank}: MISMATCH tracer {q} step {step} case {(itdm, jtdm, nreg, advtyp, extra)}", flush=True)
             if xc is None and "host" not in extra:   # PIPE_CHECK analogue: one number for all tiles
                 import test_comm_gpu
                 want = test_comm_gpu.np_checksum(ot.f64("saln")[nn - 1], cb1.ip, g1, kdm)
