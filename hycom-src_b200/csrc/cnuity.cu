@@ -4,29 +4,27 @@
 //
 // The reference runs loop 76 serially over the layers: layer k needs util3 = the sum of the OLD
 // thicknesses above it (depth-limited donor thickness, :236-283), and utotn/vtotn/p accumulate over k.
-// Those are prefix sums and reductions of quantities that do not depend on the transport itself, so
-// here every sweep covers ALL layers at once:
-//   init    :116-156   dpo(:,:,:,n) = dp(:,:,:,n); U3(k) = sum of the old dp above k (columns, in k order)
-//   flux    :236-283   low-order fluxes uflux, vflux and antidiffusive uflux2, vflux2 (margin 5)
-//   low     :293-311   dp advanced with the low-order fluxes (margin 4)
-//   ratio   :378-400   util1, util2 (5-point sea-only extrema of the low-order dp)
-//   limit   :414-441   clipped antidiffusive fluxes; the clipped-off part per layer (margin 3)
-//   update  :449-469   dp with the clipped fluxes (margin 2)
-//   column  (:437-441, :459) utotn, vtotn = sums over k IN ORDER of the clipped-off parts; p(:,:,k+1)
-//   f77     :588-651   loop 77: the lost flux goes back in proportion dp/p(kk+1) (margin 1)
-//   u77     :657-683   dp, p (margin 0)
-//   bottom  :716-733   bottom-pressure restoring, :1326-1350 cumulative fluxes
-//   asselin :1396-1422 Robert-Asselin filter of dp behind one more exchange of dp(:,:,:,n)
+// Here a thread block owns a tile of the horizontal plane and walks down the layers itself:
+//   k_cn_loop76  :116-511  per layer: dpo = dp; low-order and antidiffusive fluxes (margin 5); loop 19, the
+//                          low-order step (margin 4); util1, util2; the limiter (margin 3: the clipped-off
+//                          part joins utotn, vtotn IN k ORDER); loop 15 (margin 2); p(kk+1)
+//   k_cn_loop77  :588-733  loop 77: the lost flux goes back in proportion dp/p(kk+1) (margin 1), dp (margin
+//                :1326-1350 0); bottom-pressure restoring; cumulative fluxes
+//   k_cn_asselin :1396-1422 Robert-Asselin filter of dp behind one more exchange of dp(:,:,:,n)
 // Arithmetic is the Fortran's, expression by expression (-fmad=false, IEEE division); fluxes are zero
 // off the iu / iv points (geopar.F90:822-871 zeroes them there once, cnuity never writes them).
 // Scope: .not.btrmas, thkdf2 = thkdf4 = 0, no open-boundary faces, no Stokes drift, not (hybrid .and.
 // mxlkta), not (synflt .and. wvelfl) - everything else is refused by the caller (tsadvc_abi.cu).
-// These are streaming sweeps (HBM bound, about 10 passes over the 3-D state); the marching form of the
-// advection kernels is the next step for loop 76.
+// Measured at GLBb0.08 (profiles/r02x-z): ten streaming sweeps over all layers (the first version, 64
+// passes over a 3-D field through nine scratch fields) 66 ms; the tile kernel with its operands loaded
+// where they are used 60 ms (47 % of the warps' time waiting for them); operands of layer k+1 requested
+// while layer k is finished, 2-D metrics in shared memory 44.5 ms; donor cells by select instead of
+// branches, zero dividends on the fast division path 40.4 ms.
 #include <cuda_runtime.h>
 
 #include "tsadvc_dev.h"
 #include "tsadvc_launch.h"
+#include "march_common.cuh"
 
 namespace tsadvc {
 
@@ -63,196 +61,280 @@ __device__ __forceinline__ void layer_min(double* addr, double v) {
   const bool inside = c < P.pitch && r < P.nrows;                                \
   const long q = (long)r * P.pitch + c
 
-// ---- init: columns, margin 6 -------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cn_init(const CnuityParams P) {
+// ---- Robert-Asselin filter of dp, margin 6 (:1404-1420) ---------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cn_asselin(const CnuityParams P) {
   CN_CELL;
-  if (blockIdx.x == 0 && blockIdx.y == 0)   // per-layer minima of loops 19/14 and 15 start at 999. (:295, :451)
-    for (int k = threadIdx.y * 32 + threadIdx.x; k < 2 * P.kk; k += 256) P.dpkmin[k] = 999.0;
-  if (!inside || !in_margin(P, c, r, 6)) return;
-  const bool acc = (P.mask[q] & M_IP) && in_margin(P, c, r, 4);   // where :300 advances util3
-  double u3 = 0.0;
-  P.dpmold[q] = P.dpmixl_n[q];
-  for (int k = 0; k < P.kk; ++k) {
-    const long qk = q + (long)k * P.slab;
-    const double d = P.dp_n[qk];
-    P.dpo_n[qk] = d;
-    P.u3[qk] = u3;
-    if (acc) u3 = u3 + d;
-  }
-}
-
-// ---- low-order and antidiffusive fluxes, margin 5 ------------------------------------------------
-__global__ void __launch_bounds__(256) k_cn_flux(const CnuityParams P) {
-  CN_CELL;
-  if (!inside) return;
+  if (!inside || !in_margin(P, c, r, 6) || !(P.mask[q] & M_IP)) return;
   const int k = blockIdx.z;
   const long qk = q + (long)k * P.slab;
-  const bool m5 = in_margin(P, c, r, 5);
-  const unsigned mk = P.mask[q];
-  double fu = 0.0, fu2 = 0.0, fv = 0.0, fv2 = 0.0;
-  if (m5 && (mk & M_IU)) {
-    const double utotm = (P.u_m[qk] + P.ubavg_m[q]) * P.scuy[q];
-    double qq;
-    if (utotm >= 0.0) qq = cmin(P.dpo_n[qk - 1], cmax(0.0, P.depthu[q] - P.u3[qk - 1]));
-    else qq = cmin(P.dpo_n[qk], cmax(0.0, P.depthu[q] - P.u3[qk]));
-    fu = utotm * qq;
-    fu2 = utotm * P.dpu_m[qk] - fu;
-    P.uflx[qk] = fu;
-  }
-  if (m5 && (mk & M_IV)) {
-    const double vtotm = (P.v_m[qk] + P.vbavg_m[q]) * P.scvx[q];
-    double qq;
-    if (vtotm >= 0.0) qq = cmin(P.dpo_n[qk - P.pitch], cmax(0.0, P.depthv[q] - P.u3[qk - P.pitch]));
-    else qq = cmin(P.dpo_n[qk], cmax(0.0, P.depthv[q] - P.u3[qk]));
-    fv = vtotm * qq;
-    fv2 = vtotm * P.dpv_m[qk] - fv;
-    P.vflx[qk] = fv;
-  }
-  P.uf[qk] = fu; P.uf2[qk] = fu2; P.vf[qk] = fv; P.vf2[qk] = fv2;
+  const double dpold = P.dpo_n[qk], dpmid = P.dp_m[qk], dpnew = P.dp_n[qk];
+  const double qq = 0.5 * P.ra2fac * (dpold + dpnew - 2.0 * dpmid);
+  P.dpo_m[qk] = dpmid;
+  P.dp_m[qk] = dpmid + qq;
 }
 
-// ---- dp -= div(uf, vf)*delt1*scp2i on sea cells of a margin; min over rows 1..jj into dpkmin[slot] -----
-// src: the thickness the update starts from (dpo(n) for the low-order step, dp(n) itself afterwards)
-template <bool LOW>
-__global__ void __launch_bounds__(256) k_cn_update(const CnuityParams P, int margin, int minslot) {
-  CN_CELL;
-  const int k = blockIdx.z;
-  double seen = 999.0;
-  if (inside && in_margin(P, c, r, margin) && (P.mask[q] & M_IP)) {
-    const long qk = q + (long)k * P.slab;
-    const double d0 = LOW ? P.dpo_n[qk] : P.dp_n[qk];
-    const double d = d0 - ((P.uf[qk + 1] - P.uf[qk]) + (P.vf[qk + P.pitch] - P.vf[qk])) * P.delt1 * P.scp2i[q];
-    P.dp_n[qk] = d;
-    const int j = r + 1 - P.nbdy;
-    if (j >= 1 && j <= P.jj) seen = d;
-  }
-  if (minslot >= 0) layer_min(&P.dpkmin[minslot * P.kk + k], seen);
+
+// =====================================================================================================
+// Loop 76 (fluxes, low-order step, ratios, limiter, update) of ALL layers in one kernel:
+// a block owns a tile of 58 x 26 cells, stages a window of 64 x 32 (dependency radius 3) in shared
+// memory and walks down the layers, so that the prefix sum util3 of the old thicknesses and the column
+// sums utotn, vtotn, p(kk+1) run in registers / shared memory in the reference's k order and no
+// intermediate (u3, uf, vf, uf2, vf2, r1, r2, tnu, tnv of the sweeps above) ever reaches HBM.  The new
+// thickness goes to a scratch field (the neighbouring tiles still read the old one).
+// Loop 77, the bottom-pressure restoring and the cumulative fluxes follow as one column kernel that
+// recomputes the four face fluxes of a cell from the 5-point stencil of that scratch field.
+// HBM passes over a 3-D field: 64 (sweeps) -> about 30.
+// =====================================================================================================
+constexpr int CW = 64, CH = 32, CHALO = 3, CUX = CW - 2 * CHALO, CUY = CH - 2 * CHALO;
+constexpr int CTY = 16, CCELL = (CW / 32) * (CH / CTY);   // block 32 x 16 threads, four cells each
+constexpr int CN76_ARRAYS = 12;
+
+__global__ void k_cn_reset(const CnuityParams P) {
+  for (int k = threadIdx.x; k < 2 * P.kk; k += blockDim.x) P.dpkmin[k] = 999.0;
 }
 
-// ---- util1, util2, margin 4 -----------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cn_ratio(const CnuityParams P) {
-  CN_CELL;
-  if (!inside || !in_margin(P, c, r, 4)) return;
-  const unsigned mk = P.mask[q];
-  if (!(mk & M_IP)) return;
-  const int k = blockIdx.z;
-  const long qk = q + (long)k * P.slab;
-  const double* d = P.dp_n;
-  const double d0 = d[qk];
-  const double d1 = (mk & M_PW) ? d[qk - 1] : d0, d2 = (mk & M_PE) ? d[qk + 1] : d0;
-  const double d3 = (mk & M_PS) ? d[qk - P.pitch] : d0, d4 = (mk & M_PN) ? d[qk + P.pitch] : d0;
-  double u1 = cmax(cmax(cmax(cmax(d0, d1), d2), d3), d4);
-  double u2 = cmax(0.0, cmin(cmin(cmin(cmin(d0, d1), d2), d3), d4));
-  const double a = P.uf2[qk], b = P.uf2[qk + 1], e = P.vf2[qk], f = P.vf2[qk + P.pitch];
+// One block per SM (192 KB of shared memory: six work arrays and the six 2-D metrics of the fluxes).  The
+// 3-D operands of layer k+1 are requested into registers as soon as the fluxes of layer k are formed, so
+// their latency hides behind the other four stages (per-instruction samples of the first version: 47 % of
+// the warps' time waited for these loads, profiles/r02x).
+__global__ void __launch_bounds__(32 * CTY, 1) k_cn_loop76(const CnuityParams P) {
+  extern __shared__ double cn_smem[];
+  constexpr int N = CW * CH;
+  double* D = cn_smem;          // dpo, then the low-order dp
+  double* U3 = D + N;           // running sum of the old thicknesses above the layer
+  double* A = U3 + N;           // uflux, then util1
+  double* B = A + N;            // vflux, then util2
+  double* E = B + N;            // uflux2, then the clipped flux
+  double* F = E + N;            // vflux2, then the clipped flux
+  double* SCUY = F + N; double* UBAV = SCUY + N; double* DEPU = UBAV + N;
+  double* SCVX = DEPU + N; double* VBAV = SCVX + N; double* DEPV = VBAV + N;
+  const int c0 = blockIdx.x * CUX - CHALO, r0 = blockIdx.y * CUY - CHALO;
   const double epsil = 1.0e-11;   // mod_cb_arrays.F90:853
-  u1 = (u1 - d0) / (((cmax(0.0, a) - cmin(0.0, b)) + (cmax(0.0, e) - cmin(0.0, f)) + epsil) * P.delt1 * P.scp2i[q]);
-  u2 = (u2 - d0) / (((cmin(0.0, a) - cmax(0.0, b)) + (cmin(0.0, e) - cmax(0.0, f)) - epsil) * P.delt1 * P.scp2i[q]);
-  P.r1[qk] = u1; P.r2[qk] = u2;
-}
-
-// ---- limiter, margin 3: uf, vf := clipped antidiffusive flux; tn := the clipped-off part -----------------
-__global__ void __launch_bounds__(256) k_cn_limit(const CnuityParams P) {
-  CN_CELL;
-  if (!inside) return;
-  const int k = blockIdx.z;
-  const long qk = q + (long)k * P.slab;
-  const bool m3 = in_margin(P, c, r, 3);
-  const unsigned mk = P.mask[q];
-  double tu = 0.0, tv = 0.0;
-  if (m3 && (mk & M_IU)) {
-    const double f2 = P.uf2[qk];
-    double clip;
-    if (f2 >= 0.0) clip = cmin(cmin(1.0, P.r1[qk]), P.r2[qk - 1]);
-    else clip = cmin(cmin(1.0, P.r2[qk]), P.r1[qk - 1]);
-    tu = f2 * (1.0 - clip);
-    const double fc = f2 * clip;
-    P.uf[qk] = fc;
-    P.uflx[qk] = P.uflx[qk] + fc;
+  // this thread's cells of the window: cell e sits at window column threadIdx.x + 32*(e&1), row threadIdx.y +
+  // CTY*(e>>1); its flags share a word with its mask byte
+  const long qb = (long)(r0 + (int)threadIdx.y) * P.pitch + (c0 + (int)threadIdx.x);
+  const long qrow = (long)CTY * P.pitch;
+#define CN_Q(e) (qb + 32 * ((e) & 1) + ((e) >> 1) * qrow)
+#define CN_S(e) ((threadIdx.y + CTY * ((e) >> 1)) * CW + threadIdx.x + 32 * ((e) & 1))
+  double sci[CCELL], un[CCELL], vn[CCELL], pk[CCELL];
+  unsigned flags[CCELL];
+  // stage predicates of a cell, formed once: flux faces, low-order cell, ratio cell, limiter faces, updated cell,
+  // uflx / vflx written, row counts for dpkmin
+  enum { VALID = 0x100, OWN = 0x200, FXF = 0x400, FYF = 0x800, SEA4 = 0x1000, LOW = 0x2000, RAT = 0x4000,
+         CLX = 0x8000, CLY = 0x10000, UPD = 0x20000, WRU = 0x40000, WRV = 0x80000, JIN = 0x100000 };
+#pragma unroll
+  for (int e = 0; e < CCELL; ++e) {
+    const int sx = threadIdx.x + 32 * (e & 1), sy = threadIdx.y + CTY * (e >> 1), s = CN_S(e);
+    const int c = c0 + sx, r = r0 + sy;
+    const bool valid = c >= 0 && c < P.pitch && r >= 0 && r < P.nrows;
+    const long q = CN_Q(e);
+    sci[e] = valid ? P.scp2i[q] : 0.0;
+    un[e] = vn[e] = pk[e] = 0.0;
+    unsigned f = valid ? (VALID | P.mask[q]) : 0u;
+    const bool own = valid && sx >= CHALO && sx < CW - CHALO && sy >= CHALO && sy < CH - CHALO;
+    if (own) f |= OWN;
+    if (valid) {
+      const bool m5 = in_margin(P, c, r, 5), m4 = in_margin(P, c, r, 4), m3 = in_margin(P, c, r, 3), m2 = in_margin(P, c, r, 2);
+      const bool inner = sx >= 1 && sx < CW - 1 && sy >= 1 && sy < CH - 1;
+      if (m5 && (f & M_IU) && sx >= 1) f |= FXF;
+      if (m5 && (f & M_IV) && sy >= 1) f |= FYF;
+      if (m4 && (f & M_IP)) f |= SEA4;
+      if (m4 && (f & M_IP) && sx < CW - 1 && sy < CH - 1) f |= LOW;
+      if (m4 && (f & M_IP) && inner) f |= RAT;
+      if (m3 && (f & M_IU) && sx >= 2) f |= CLX;
+      if (m3 && (f & M_IV) && sy >= 2) f |= CLY;
+      if (own && m2 && (f & M_IP)) f |= UPD;
+      if (own && m5 && (f & M_IU)) f |= WRU;
+      if (own && m5 && (f & M_IV)) f |= WRV;
+      const int j = r + 1 - P.nbdy;
+      if (j >= 1 && j <= P.jj) f |= JIN;
+    }
+    flags[e] = f;
+    U3[s] = 0.0;
+    SCUY[s] = valid ? P.scuy[q] : 0.0; UBAV[s] = valid ? P.ubavg_m[q] : 0.0; DEPU[s] = valid ? P.depthu[q] : 0.0;
+    SCVX[s] = valid ? P.scvx[q] : 0.0; VBAV[s] = valid ? P.vbavg_m[q] : 0.0; DEPV[s] = valid ? P.depthv[q] : 0.0;
+    if ((f & OWN)) { P.dpmold[q] = P.dpmixl_n[q]; P.p[q] = 0.0; }
   }
-  if (m3 && (mk & M_IV)) {
-    const double f2 = P.vf2[qk];
-    double clip;
-    if (f2 >= 0.0) clip = cmin(cmin(1.0, P.r1[qk]), P.r2[qk - P.pitch]);
-    else clip = cmin(cmin(1.0, P.r2[qk]), P.r1[qk - P.pitch]);
-    tv = f2 * (1.0 - clip);
-    const double fc = f2 * clip;
-    P.vf[qk] = fc;
-    P.vflx[qk] = P.vflx[qk] + fc;
+  // the 3-D operands of the layer at hand
+  double od[CCELL], ou[CCELL], ov[CCELL], odu[CCELL], odv[CCELL];
+#pragma unroll
+  for (int e = 0; e < CCELL; ++e) {
+    const bool v = flags[e] & VALID;
+    const long qk = CN_Q(e);
+    od[e] = v ? P.dp_n[qk] : 0.0; ou[e] = v ? P.u_m[qk] : 0.0; ov[e] = v ? P.v_m[qk] : 0.0;
+    odu[e] = v ? P.dpu_m[qk] : 0.0; odv[e] = v ? P.dpv_m[qk] : 0.0;
   }
-  P.tnu[qk] = tu; P.tnv[qk] = tv;
+  for (int k = 0; k < P.kk; ++k) {
+    const long ko = (long)k * P.slab;
+    // ---- the old thickness of the window; dpo(:,:,k,n) = dp(:,:,k,n) (:116-156)
+    double fu_own[CCELL], fv_own[CCELL];
+#pragma unroll
+    for (int e = 0; e < CCELL; ++e) {
+      D[CN_S(e)] = od[e];
+      if (flags[e] & OWN) P.dpo_n[CN_Q(e) + ko] = od[e];
+    }
+    __syncthreads();
+    // ---- low-order and antidiffusive fluxes at the west and south face of every cell (:236-283)
+#pragma unroll
+    for (int e = 0; e < CCELL; ++e) {
+      const int s = CN_S(e);
+      double fu = 0.0, fu2 = 0.0, fv = 0.0, fv2 = 0.0;
+      if (flags[e] & FXF) {   // the donor cell by the sign of the transport
+        const double utotm = (ou[e] + UBAV[s]) * SCUY[s];
+        const int sd = (utotm >= 0.0) ? s - 1 : s;
+        const double qq = cmin(D[sd], cmax(0.0, DEPU[s] - U3[sd]));
+        fu = utotm * qq;
+        fu2 = utotm * odu[e] - fu;
+      }
+      if (flags[e] & FYF) {
+        const double vtotm = (ov[e] + VBAV[s]) * SCVX[s];
+        const int sd = (vtotm >= 0.0) ? s - CW : s;
+        const double qq = cmin(D[sd], cmax(0.0, DEPV[s] - U3[sd]));
+        fv = vtotm * qq;
+        fv2 = vtotm * odv[e] - fv;
+      }
+      A[s] = fu; E[s] = fu2; B[s] = fv; F[s] = fv2;
+      fu_own[e] = fu; fv_own[e] = fv;
+    }
+    // the operands of the next layer: in flight while this one is finished
+    if (k + 1 < P.kk) {
+#pragma unroll
+      for (int e = 0; e < CCELL; ++e) {
+        const bool v = flags[e] & VALID;
+        const long qk = CN_Q(e) + ko + P.slab;
+        od[e] = v ? P.dp_n[qk] : 0.0; ou[e] = v ? P.u_m[qk] : 0.0; ov[e] = v ? P.v_m[qk] : 0.0;
+        odu[e] = v ? P.dpu_m[qk] : 0.0; odv[e] = v ? P.dpv_m[qk] : 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- loop 19: the low-order step (:293-311); util3 moves on to the next layer (:300)
+#pragma unroll
+    for (int e = 0; e < CCELL; ++e) {
+      const int s = CN_S(e);
+      const double d0 = D[s];
+      if (flags[e] & SEA4) U3[s] = U3[s] + d0;
+      if (flags[e] & LOW) D[s] = d0 - ((A[s + 1] - A[s]) + (B[s + CW] - B[s])) * P.delt1 * sci[e];
+    }
+    __syncthreads();
+    // ---- util1, util2 (:378-400) into A, B
+#pragma unroll
+    for (int e = 0; e < CCELL; ++e) {
+      const int s = CN_S(e);
+      if (flags[e] & RAT) {
+        const unsigned m = flags[e];
+        const double d0 = D[s];
+        const double d1 = (m & M_PW) ? D[s - 1] : d0, d2 = (m & M_PE) ? D[s + 1] : d0;
+        const double d3 = (m & M_PS) ? D[s - CW] : d0, d4 = (m & M_PN) ? D[s + CW] : d0;
+        double u1 = cmax(cmax(cmax(cmax(d0, d1), d2), d3), d4);
+        double u2 = cmax(0.0, cmin(cmin(cmin(cmin(d0, d1), d2), d3), d4));
+        const double a = E[s], b = E[s + 1], ee = F[s], f = F[s + CW];
+        // (zero dividends - a cell at a local extremum - are common: div_rn takes them on its fast path)
+        u1 = div_rn(u1 - d0, ((cmax(0.0, a) - cmin(0.0, b)) + (cmax(0.0, ee) - cmin(0.0, f)) + epsil) * P.delt1 * sci[e]);
+        u2 = div_rn(u2 - d0, ((cmin(0.0, a) - cmax(0.0, b)) + (cmin(0.0, ee) - cmax(0.0, f)) - epsil) * P.delt1 * sci[e]);
+        A[s] = u1; B[s] = u2;
+      }
+    }
+    __syncthreads();
+    // ---- the limiter (:414-441): E, F := clipped fluxes; the clipped-off part joins utotn, vtotn in k order
+#pragma unroll
+    for (int e = 0; e < CCELL; ++e) {
+      const int s = CN_S(e);
+      const long qk = CN_Q(e) + ko;
+      double fcu = 0.0, fcv = 0.0;
+      const bool fx = flags[e] & CLX, fy = flags[e] & CLY;
+      if (fx) {
+        const double f2 = E[s];
+        const bool pos = f2 >= 0.0;
+        const double clip = cmin(cmin(1.0, pos ? A[s] : B[s]), pos ? B[s - 1] : A[s - 1]);
+        un[e] = un[e] + f2 * (1.0 - clip);
+        fcu = f2 * clip;
+      }
+      if (fy) {
+        const double f2 = F[s];
+        const bool pos = f2 >= 0.0;
+        const double clip = cmin(cmin(1.0, pos ? A[s] : B[s]), pos ? B[s - CW] : A[s - CW]);
+        vn[e] = vn[e] + f2 * (1.0 - clip);
+        fcv = f2 * clip;
+      }
+      E[s] = fcu; F[s] = fcv;
+      if (flags[e] & WRU) P.uflx[qk] = fx ? fu_own[e] + fcu : fu_own[e];
+      if (flags[e] & WRV) P.vflx[qk] = fy ? fv_own[e] + fcv : fv_own[e];
+    }
+    __syncthreads();
+    // ---- loop 15: dp with the clipped fluxes (:449-469), into the scratch field; p(k+1)
+    double seen = 999.0;
+#pragma unroll
+    for (int e = 0; e < CCELL; ++e) {
+      if (!(flags[e] & OWN)) continue;
+      const int s = CN_S(e);
+      double d = D[s];
+      if (flags[e] & UPD) {
+        d = d - ((E[s + 1] - E[s]) + (F[s + CW] - F[s])) * P.delt1 * sci[e];
+        pk[e] = pk[e] + d;
+        if (flags[e] & JIN) seen = cmin(seen, d);
+      }
+      P.dnew[CN_Q(e) + ko] = d;
+    }
+    layer_min(&P.dpkmin[P.kk + k], seen);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < CCELL; ++e)
+    if (flags[e] & OWN) {
+      P.utotn[CN_Q(e)] = un[e]; P.vtotn[CN_Q(e)] = vn[e];
+      if (flags[e] & UPD) P.p[CN_Q(e) + (long)P.kk * P.slab] = pk[e];
+    }
 }
+#undef CN_Q
+#undef CN_S
 
-// ---- columns: utotn, vtotn (sums over k in order) and p(:,:,k+1) after loop 76 ---------------------------
-__global__ void __launch_bounds__(256) k_cn_column(const CnuityParams P) {
-  CN_CELL;
-  if (blockIdx.x == 0 && blockIdx.y == 0)   // loop 14 reuses dpkmin(1:kk) (:679)
-    for (int k = threadIdx.y * 32 + threadIdx.x; k < P.kk; k += 256) P.dpkmin[k] = 999.0;
-  if (!inside) return;
-  const unsigned mk = P.mask[q];
-  const bool m3 = in_margin(P, c, r, 3);
-  const bool cell = in_margin(P, c, r, 2) && (mk & M_IP);
-  double un = 0.0, vn = 0.0, pk = 0.0;
-  P.p[q] = 0.0;
+// ---- loop 77 (:588-683), bottom-pressure restoring (:716-733), cumulative fluxes (:1326-1350): columns ---------
+__global__ void __launch_bounds__(256) k_cn_loop77(const CnuityParams P) {
+  const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+  const bool inside = c < P.pitch && r < P.nrows;
+  const long q = inside ? (long)r * P.pitch + c : 0;
+  const unsigned mk = inside ? P.mask[q] : 0u;
+  const bool out = mk & M_OUT;                                      // sea cell of 1..ii x 1..jj
+  const bool m1 = inside && in_margin(P, c, r, 1);
+  const bool fw = m1 && (mk & M_IU), fs = m1 && (mk & M_IV);        // own faces: uflx, vflx are updated there
+  const bool fe = out && (P.mask[q + 1] & M_IU), fn = out && (P.mask[q + P.pitch] & M_IV);
+  const double* pb = P.p + (long)P.kk * P.slab;                     // p(:,:,kk+1) as loop 76 left it
+  // per face: the lost transport, the donor cell by its sign (:600-640), that column's p(kk+1) and its reciprocal
+  const double un_w = fw ? P.utotn[q] : 0.0, un_e = fe ? P.utotn[q + 1] : 0.0;
+  const double vn_s = fs ? P.vtotn[q] : 0.0, vn_n = fn ? P.vtotn[q + P.pitch] : 0.0;
+  const long ow = (un_w >= 0.0) ? -1 : 0, oe = (un_e >= 0.0) ? 0 : 1;
+  const long os = (vn_s >= 0.0) ? -(long)P.pitch : 0, on = (vn_n >= 0.0) ? 0 : (long)P.pitch;
+  const double pw = fw ? pb[q + ow] : 1.0, pe = fe ? pb[q + oe] : 1.0;
+  const double ps = fs ? pb[q + os] : 1.0, pn = fn ? pb[q + on] : 1.0;
+  const double yw = rcp_nr(pw), ye = rcp_nr(pe), ys = rcp_nr(ps), yn = rcp_nr(pn);
+  const double sci = inside ? P.scp2i[q] : 0.0;
+  const int i = c + 1 - P.nbdy, j = r + 1 - P.nbdy;
+  const bool col = inside && i >= 1 && i <= P.ii && j >= 1 && j <= P.jj;
+  double psum = 0.0;
   for (int k = 0; k < P.kk; ++k) {
     const long qk = q + (long)k * P.slab;
-    if (m3 && (mk & M_IU)) un = un + P.tnu[qk];
-    if (m3 && (mk & M_IV)) vn = vn + P.tnv[qk];
-    if (cell) { pk = pk + P.dp_n[qk]; P.p[qk + P.slab] = pk; }
+    double seen = 999.0;
+    if (inside) {
+      const double dc = P.dnew[qk];
+      double d = dc;
+      double fuw = 0.0, fue = 0.0, fvs = 0.0, fvn = 0.0;
+      if (fw) { fuw = un_w * div_y(P.dnew[qk + ow], pw, yw); P.uflx[qk] = P.uflx[qk] + fuw; }
+      if (fs) { fvs = vn_s * div_y(P.dnew[qk + os], ps, ys); P.vflx[qk] = P.vflx[qk] + fvs; }
+      if (out) {
+        if (fe) fue = un_e * div_y(P.dnew[qk + oe], pe, ye);
+        if (fn) fvn = vn_n * div_y(P.dnew[qk + on], pn, yn);
+        d = dc - ((fue - fuw) + (fvn - fvs)) * P.delt1 * sci;
+        seen = d;
+      }
+      P.dp_n[qk] = d;
+      if (col && (mk & M_IP)) psum = psum + d;
+    }
+    layer_min(&P.dpkmin[k], seen);
   }
-  P.utotn[q] = un; P.vtotn[q] = vn;
-}
-
-// ---- loop 77 fluxes, margin 1 -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cn_f77(const CnuityParams P) {
-  CN_CELL;
-  if (!inside) return;
-  const int k = blockIdx.z;
-  const long qk = q + (long)k * P.slab;
-  const bool m1 = in_margin(P, c, r, 1);
-  const unsigned mk = P.mask[q];
-  const double* pb = P.p + (long)P.kk * P.slab;   // p(:,:,kk+1) as loop 76 left it
-  double fu = 0.0, fv = 0.0;
-  if (m1 && (mk & M_IU)) {
-    const double un = P.utotn[q];
-    const double qq = (un >= 0.0) ? P.dp_n[qk - 1] / pb[q - 1] : P.dp_n[qk] / pb[q];
-    fu = un * qq;
-    P.uflx[qk] = P.uflx[qk] + fu;
-  }
-  if (m1 && (mk & M_IV)) {
-    const double vn = P.vtotn[q];
-    const double qq = (vn >= 0.0) ? P.dp_n[qk - P.pitch] / pb[q - P.pitch] : P.dp_n[qk] / pb[q];
-    fv = vn * qq;
-    P.vflx[qk] = P.vflx[qk] + fv;
-  }
-  P.uf2[qk] = fu; P.vf2[qk] = fv;   // (uf, vf still feed nothing; uf2, vf2 are free: no read-write overlap with u77)
-}
-
-// ---- loop 77 update, margin 0: reads the fluxes of f77 from uf2, vf2 ------------------------------------------
-__global__ void __launch_bounds__(256) k_cn_u77(const CnuityParams P) {
-  CN_CELL;
-  const int k = blockIdx.z;
-  double seen = 999.0;
-  if (inside && (P.mask[q] & M_OUT)) {
-    const long qk = q + (long)k * P.slab;
-    const double d = P.dp_n[qk] - ((P.uf2[qk + 1] - P.uf2[qk]) + (P.vf2[qk + P.pitch] - P.vf2[qk])) * P.delt1 * P.scp2i[q];
-    P.dp_n[qk] = d;
-    seen = d;
-  }
-  layer_min(&P.dpkmin[k], seen);
-}
-
-// ---- bottom-pressure restoring (:716-733) and cumulative fluxes (:1326-1350), columns of 1:ii,1:jj -----------
-__global__ void __launch_bounds__(256) k_cn_bottom(const CnuityParams P) {
-  CN_CELL;
-  if (!inside) return;
-  const int i = c + 1 - P.nbdy, j = r + 1 - P.nbdy;
-  if (i < 1 || i > P.ii || j < 1 || j > P.jj) return;
-  const unsigned mk = P.mask[q];
+  if (!col) return;
   if (mk & M_IP) {
+    const double qq = P.pbot[q] / psum;
     double pk = 0.0;
-    for (int k = 0; k < P.kk; ++k) pk = pk + P.dp_n[q + (long)k * P.slab];   // p(kk+1) after loop 77
-    const double qq = P.pbot[q] / pk;
-    pk = 0.0;
     for (int k = 0; k < P.kk; ++k) {
       const long qk = q + (long)k * P.slab;
       const double d = P.dp_n[qk] * qq;
@@ -269,18 +351,6 @@ __global__ void __launch_bounds__(256) k_cn_bottom(const CnuityParams P) {
     for (int k = 0; k < P.kk; ++k) { const long qk = q + (long)k * P.slab; P.vflxav[qk] = P.vflxav[qk] + P.vflx[qk]; }
 }
 
-// ---- Robert-Asselin filter of dp, margin 6 (:1404-1420) ---------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cn_asselin(const CnuityParams P) {
-  CN_CELL;
-  if (!inside || !in_margin(P, c, r, 6) || !(P.mask[q] & M_IP)) return;
-  const int k = blockIdx.z;
-  const long qk = q + (long)k * P.slab;
-  const double dpold = P.dpo_n[qk], dpmid = P.dp_m[qk], dpnew = P.dp_n[qk];
-  const double qq = 0.5 * P.ra2fac * (dpold + dpnew - 2.0 * dpmid);
-  P.dpo_m[qk] = dpmid;
-  P.dp_m[qk] = dpmid + qq;
-}
-
 }  // namespace
 
 // stage 0: everything up to the exchange of dp(:,:,:,n) (:1400); stage 1: the Robert-Asselin filter
@@ -290,16 +360,17 @@ int launch_cnuity(int stage, const CnuityParams& P, cudaStream_t st) {
     k_cn_asselin<<<g3, block, 0, st>>>(P);
     return (int)cudaGetLastError();
   }
-  k_cn_init<<<g2, block, 0, st>>>(P);
-  k_cn_flux<<<g3, block, 0, st>>>(P);
-  k_cn_update<true><<<g3, block, 0, st>>>(P, 4, 0);     // loop 19
-  k_cn_ratio<<<g3, block, 0, st>>>(P);
-  k_cn_limit<<<g3, block, 0, st>>>(P);
-  k_cn_update<false><<<g3, block, 0, st>>>(P, 2, 1);    // loop 15
-  k_cn_column<<<g2, block, 0, st>>>(P);
-  k_cn_f77<<<g3, block, 0, st>>>(P);
-  k_cn_u77<<<g3, block, 0, st>>>(P);                    // loop 14 (overwrites the loop-19 minima, like the Fortran)
-  k_cn_bottom<<<g2, block, 0, st>>>(P);
+  static bool attr_set = false;
+  const int bytes = CN76_ARRAYS * CW * CH * (int)sizeof(double);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_cn_loop76, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  k_cn_reset<<<1, 256, 0, st>>>(P);
+  const dim3 gt((P.pitch + CUX - 1) / CUX, (P.nrows + CUY - 1) / CUY);
+  k_cn_loop76<<<gt, dim3(32, CTY), bytes, st>>>(P);
+  k_cn_loop77<<<g2, block, 0, st>>>(P);
   return (int)cudaGetLastError();
 }
 

@@ -1814,12 +1814,9 @@ int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, con
   P.ubavg_m = ub + h->slab * (m - 1); P.vbavg_m = vb + h->slab * (m - 1);
   P.depthu = du; P.depthv = dv; P.pbot = pb; P.uflx = uflx; P.vflx = vflx;
   P.uflxav = h->uflxav.lev[0]; P.vflxav = h->vflxav.lev[0]; P.dpav = h->dpav.lev[0];
-  if (!h->cnuity_scratch && (rc = dalloc_field(h, &h->cnuity_scratch, 9 * (size_t)kk * h->slab))) return rc;
+  if (!h->cnuity_scratch && (rc = dalloc_field(h, &h->cnuity_scratch, (size_t)kk * h->slab))) return rc;
   if (!h->d_dpkmin && (rc = dalloc(h, (void**)&h->d_dpkmin, sizeof(double) * 2 * kk, false))) return rc;
-  const long L = (long)kk * h->slab;
-  double* s0 = h->cnuity_scratch;
-  P.u3 = s0; P.uf = s0 + L; P.vf = s0 + 2 * L; P.uf2 = s0 + 3 * L; P.vf2 = s0 + 4 * L; P.r1 = s0 + 5 * L;
-  P.r2 = s0 + 6 * L; P.tnu = s0 + 7 * L; P.tnv = s0 + 8 * L;
+  P.dnew = h->cnuity_scratch;
   P.dpkmin = h->d_dpkmin;
   P.pitch = h->pitch; P.nrows = h->nrows; P.nbdy = h->d.nbdy; P.ii = h->d.ii; P.jj = h->d.jj; P.kk = kk;
   P.slab = h->slab; P.mask = h->mask; P.scuy = h->scuy; P.scvx = h->scvx; P.scp2i = h->scp2i;
@@ -1850,7 +1847,7 @@ int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, con
     if ((rc = xc_exchange(h, b, false, h->stream))) return rc;
   }
   if ((rc = launch_cnuity(0, P, h->stream))) return fail(h, HYCOM_TSADVC_ECUDA, "cnuity kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-  h->launches += 10;
+  h->launches += 3;
   // :1400 xctilr(dp(:,:,:,n), 1,kk, 6,6, halo_ps), then the Robert-Asselin filter
   if (single) {
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_DP, 0, n, 6, 6))) return rc;

@@ -52,7 +52,7 @@ struct hycom_tsadvc_handle {
   // cnuity.F90 operands: u, v, dpu, dpv (kdm per slot), ubavg, vbavg (3 slabs), depthu, depthv (1), p (kdm+1),
   // dpmixl (1 per slot), uflxav, vflxav, dpav (kdm), utotn, vtotn, dpmold (1)
   tsadvc::Mirror u, v, dpu, dpv, ubavg, vbavg, depthu, depthv, p, dpmixl, uflxav, vflxav, dpav, utotn, vtotn, dpmold;
-  double* cnuity_scratch = nullptr;   // 9*kdm slabs
+  double* cnuity_scratch = nullptr;   // kdm slabs: dp after loop 76
   double* d_dpkmin = nullptr;         // 2*kdm
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];
   // one allocation [dp(:,:,:,1) | uflx | vflx | dp(:,:,:,2)]

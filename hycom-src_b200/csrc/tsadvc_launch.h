@@ -228,7 +228,7 @@ struct CnuityParams {
   double *dpmixl_n, *dpmold;
   double *uflx, *vflx, *p, *utotn, *vtotn;
   double *uflxav, *vflxav, *dpav;               // may be null: not accumulated
-  double *u3, *uf, *vf, *uf2, *vf2, *r1, *r2, *tnu, *tnv;   // scratch, kk slabs each
+  double* dnew;                                 // scratch: dp after loop 76 (kk slabs)
   double* dpkmin;                               // 2*kk (device)
   double delt1, ra2fac;
   int isopyc;

@@ -9,6 +9,7 @@
 #   benchq     bench.py quick (5 steps, no e2e / cpu / extra)
 #   ref        bench.py --impl reference
 #   launches   ncu launch list of a short bench run (N=1)
+#   cnuity     cnuity parity tests + timing at GLBb0.08; cnuity_launches / cnuity_ncu: per-kernel times, full capture
 #   traffic    DRAM bytes + L2 hit rate of the marching launches of one full-size step
 #   ncu        ncu --set full + source of the marching kernel (N=1, reduced kdm)
 #   tma        the tensor-map TMA probe, every variant in its own process
@@ -65,6 +66,27 @@ for r in rows[1:]:
 print("dram total %.3f GB" % (tot / 1e9))
 PY
       ;;
+    cnuity)
+      timeout 900 python -m pytest tests/test_cnuity_gpu.py -x -q > $OUT/pytest_cnuity.log 2>&1; echo "rc=$?" >> $OUT/pytest_cnuity.log; tail -4 $OUT/pytest_cnuity.log
+      timeout 600 python tools/cnuity_timing.py 2>&1 | tail -1 | tee -a $OUT/cnuity_timing.txt ;;
+    cnuity_launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_cn_\|k_halo -c 400 --csv --log-file $OUT/cnuity_launches.csv \
+        python tools/cnuity_timing.py 1 1 > $OUT/cnuity_launches_run.log 2>&1; echo "rc=$?"
+      python - $OUT/cnuity_launches.csv <<'PY'
+import csv, sys, collections
+rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
+hdr = rows[0]; ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+t = collections.OrderedDict()
+for r in rows[1:]:
+    v = float(r[iv].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6}.get(r[iu], 1e-6)
+    n, s = t.get(r[ik][:70], (0, 0.0)); t[r[ik][:70]] = (n + 1, s + v)
+for k, (n, s) in t.items():
+    print(f"{s:9.3f} ms {n:4d}x  {k}")
+PY
+      ;;
+    cnuity_ncu)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:${CN_KERNEL:-k_cn_loop76} -c 1 -f -o $OUT/cnuity_prof \
+        python tools/cnuity_timing.py 1 0 > $OUT/cnuity_ncu_run.log 2>&1; echo "rc=$?"; tail -2 $OUT/cnuity_ncu_run.log | cut -c1-200 ;;
     tma)
       (cd tools/probe && nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe4 tma_probe4.cu -lcuda 2>/dev/null)
       for v in 0 1 2 3 4; do timeout 60 tools/probe/tma_probe4 $v; echo "exit=$?"; done > $OUT/tma_probe4.txt 2>&1; cat $OUT/tma_probe4.txt ;;
