@@ -58,7 +58,7 @@ int dalloc(hycom_tsadvc_handle* h, void** p, size_t nbytes, bool zero) {
 // field buffers: one zeroed guard row on each side (see tsadvc_handle.h)
 int dalloc_field(hycom_tsadvc_handle* h, double** p, size_t ndoubles) {
   void* raw = nullptr;
-  const size_t g = (size_t)h->pitch;
+  const size_t g = (size_t)(h->pitch > 64 ? h->pitch : 64);   // at least one 64-column window
   int rc = dalloc(h, &raw, sizeof(double) * (ndoubles + 2 * g), true);
   if (rc) return rc;
   h->raw_allocs.push_back(raw);

@@ -78,6 +78,10 @@ __global__ void __launch_bounds__(256) k_isopyc_smooth(const double* __restrict_
 // face of row r-1 is the south face of row r (carried in a register), the east face of column i
 // is the west face of column i+1 (one shuffle) - two harmonc divisions per cell instead of four -
 // and every operand is read from HBM once.  Dependency radius 1: a strip yields 30 columns.
+// Two cells per lane were measured (profiles/r03b-h): 18-24 % fewer instructions per cell, but with all nine
+// operands staged the ring allows two warps per scheduler instead of four (5.7 ms against 3.8 at kdm=12),
+// and with the five 2-D operands fetched by plain loads one row ahead ptxas copies the freshly loaded
+// registers at the loop head, so every row waits out a full load latency (4.1 ms): not adopted.
 //   ring slot = [fld_0 .. fld_NF-1 | dp | oneta | au | av | scp2 | mask words], 256 B each
 // ---------------------------------------------------------------------------------------------
 template <int NF>
@@ -87,13 +91,12 @@ struct DRing {
 };
 constexpr int kDiffUse = 30;   // columns a strip yields; its first staged column is 30*s - 2 (even)
 
+// request the row at element offset `off` into the slot at byte offset `soff` of the ring (one lane)
 template <int NF>
-__device__ __forceinline__ void diff_issue_row(const DiffMarchParams& P, const double* const (&src)[NF + 6],
-                                               int nrows, int pitch, int r, uint32_t ring_s, uint32_t bar_s,
-                                               int slot) {
+__device__ __forceinline__ void diff_issue_row(const double* const (&src)[NF + 6], long off, uint32_t ring_s,
+                                               uint32_t soff, uint32_t bar) {
   typedef DRing<NF> R;
-  const uint32_t bar = bar_s + 8u * slot, dst = ring_s + (uint32_t)(slot * R::SLOT);
-  const long off = (long)max(0, min(r, nrows - 1)) * pitch;
+  const uint32_t dst = ring_s + soff;
   mbar_expect_tx(bar, R::SLOT);
 #pragma unroll
   for (int a = 0; a < R::NARR; ++a) bulk_g2s(dst + a * R::RB, src[a] + off, R::RB, bar);
@@ -130,41 +133,53 @@ __global__ void __launch_bounds__(128, 4) k_tsdff_march(const DiffMarchParams P)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  const int r0 = j0 - 1;                                   // two warm-up rows: see the header of the loop
-  const int niter = ((j1 - j0) + 2 + 5) / 6 * 6;
-  {   // rows r0-2, r0-1 ("below the chunk"): zeros, all land
+  // step t: row r = r0+t is the NORTH row, r-1 the centre (stored when inside the chunk), r-2 the south
+  // row; t = 0,1 only build the carried values for the first stored row
+  const int r0 = j0 - 1;
+  const int niter = (j1 - j0) + 2;
+  const int nstore = j1 - j0;
+  {   // rows r0-2, r0-1 ("below the chunk", slots 4 and 5): zeros, all land
     double* z = reinterpret_cast<double*>(const_cast<unsigned char*>(ring) + 4 * R::SLOT);
     for (int i = lane; i < 2 * R::SLOT / 8; i += 32) z[i] = 0.0;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
   }
-  if (elect_one()) {
-    diff_issue_row<NF>(P, src, P.nrows, P.pitch, r0, ring_s, bar_s, 0);
-    diff_issue_row<NF>(P, src, P.nrows, P.pitch, r0 + 1, ring_s, bar_s, 1);
-    diff_issue_row<NF>(P, src, P.nrows, P.pitch, r0 + 2, ring_s, bar_s, 2);
+  // the source row of the next request: one warp-uniform offset that walks down the slabs (rows outside
+  // the slab repeat the nearest one)
+  long goff = (long)max(0, min(r0, P.nrows - 1)) * P.pitch;
+  int grow = r0;
+#define TSDFF_NEXT_ROW goff += ((unsigned)grow < (unsigned)(P.nrows - 1)) ? (long)P.pitch : 0L; grow += 1;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (elect_one()) diff_issue_row<NF>(src, goff, ring_s, q * R::SLOT, bar_s + 8u * q);
+    TSDFF_NEXT_ROW
   }
   const unsigned char* pc = ring + 8 * lane;
   const unsigned char* pw = ring + 8 * max(lane - 1, 0);
   const unsigned char* pe = ring + 8 * min(lane + 1, 31);
-  auto at = [](const unsigned char* q, int slot, int arr) {
-    return *reinterpret_cast<const double*>(q + slot * R::SLOT + arr * R::RB);
+  auto at = [](const unsigned char* q, uint32_t so, int arr) {
+    return *reinterpret_cast<const double*>(q + so + arr * R::RB);
   };
-  auto mask_at = [](const unsigned char* q, int slot) {
-    return *reinterpret_cast<const unsigned*>(q + slot * R::SLOT + R::MSK * R::RB);
+  auto mask_at = [](const unsigned char* q, uint32_t so) {
+    return *reinterpret_cast<const unsigned*>(q + so + R::MSK * R::RB);
   };
+  // this lane's output cell walks down the slab one row per iteration (the row finished in iteration t is
+  // r0+t-1); lanes 1..30 of the window inside the slab store
+  const int col = w0 + lane;
+  const bool mine = lane >= 1 && lane <= kDiffUse && (unsigned)col < (unsigned)P.pitch;
+  long oq = (long)k0 * P.slab + (long)(r0 - 1) * P.pitch + col;
   // carried from the previous row: dp*oneta and the mask of the centre row, its south face factor
   double hc = 0.0, gs = 0.0;
   unsigned mc = 0u;
-  uint32_t round = 0;
+  // the ring slots of the north, centre and south row rotate as three warp-uniform byte offsets
+  uint32_t sn = 0, sc_ = 5 * R::SLOT, ss = 4 * R::SLOT;
+  uint32_t bn = bar_s, par = 0;
   const int k = k0 + 1;
   const bool ldtemp = k <= P.nhybrd && P.temdfc > 0.0;                               // :2170
   const bool ldth3d = (k <= P.nhybrd && P.temdfc < 1.0) || (k == 1 && P.isopyc);     // :2171-2172
-  // step t: row r = r0+t is the NORTH row (slot t%6), r-1 the centre (stored when inside the
-  // chunk), r-2 the south row.  t = 0,1 only build the carried values for the first stored row.
+#pragma unroll 1
   for (int t = 0; t < niter; ++t) {
-    const int sn = t % 6, sc_ = (t + 5) % 6, ss = (t + 4) % 6;
-    mbar_wait(bar_s + 8u * sn, round & 1u);
-    const int r = r0 + t, rc = r - 1;
+    mbar_wait(bn, par);
     const unsigned mn = mask_at(pc, sn);
     const double hn = at(pc, sn, R::DPA) * at(pc, sn, R::ON);
     // east and north face factors of the centre cell (west = east of the lane to the left, south =
@@ -189,9 +204,7 @@ __global__ void __launch_bounds__(128, 4) k_tsdff_march(const DiffMarchParams P)
       old[f] = x;
       v[f] = on_ ? x + util : x;
     }
-    const int col = w0 + lane;
-    if (lane >= 1 && lane <= kDiffUse && (unsigned)col < (unsigned)P.pitch && rc >= j0 && rc < j1) {
-      const long qk = (long)k0 * P.slab + (long)rc * P.pitch + col;
+    if (mine && (unsigned)(t - 2) < (unsigned)nstore) {
       const bool wr = mc & M_OUT;
       if (EOS) {   // :2199-2229
         double tt = v[0], s = v[1], h = v[NF - 1];
@@ -205,24 +218,32 @@ __global__ void __launch_bounds__(128, 4) k_tsdff_march(const DiffMarchParams P)
           } else if (ldth3d) {
             tt = eos::tofsig(P.eosc, h + P.thbase, s);
           } else {
-            h = P.theta[qk];
+            h = P.theta[oq];
             tt = eos::tofsig(P.eosc, h + P.thbase, s);
           }
         }
-        P.out[0][qk] = wr ? tt : old[0];
-        P.out[1][qk] = wr ? s : old[1];
-        P.out[NF - 1][qk] = wr ? h : old[NF - 1];
+        P.out[0][oq] = wr ? tt : old[0];
+        P.out[1][oq] = wr ? s : old[1];
+        P.out[NF - 1][oq] = wr ? h : old[NF - 1];
       } else {
 #pragma unroll
-        for (int f = 0; f < NF; ++f) P.out[f][qk] = wr ? v[f] : old[f];
+        for (int f = 0; f < NF; ++f) P.out[f][oq] = wr ? v[f] : old[f];
       }
     }
     hc = hn; gs = gn; mc = mn;
     __syncwarp();
-    if (t + 3 < niter && elect_one())
-      diff_issue_row<NF>(P, src, P.nrows, P.pitch, r + 3, ring_s, bar_s, (t + 3) % 6);
-    if (sn == 5) ++round;
+    // row r+3 goes into the slot of row r-3 (the south row of the previous iteration); the slots rotate
+    const uint32_t fill = sn >= 3 * R::SLOT ? sn - 3 * R::SLOT : sn + 3 * R::SLOT;
+    const uint32_t bfill = sn >= 3 * R::SLOT ? bn - 24u : bn + 24u;
+    if (t + 3 < niter && elect_one()) diff_issue_row<NF>(src, goff, ring_s, fill, bfill);
+    TSDFF_NEXT_ROW
+    ss = sc_; sc_ = sn;
+    sn = (sn == 5 * R::SLOT) ? 0u : sn + R::SLOT;
+    par ^= (sn == 0) ? 1u : 0u;               // slot 5 closes a round of six
+    bn = (sn == 0) ? bar_s : bn + 8u;
+    oq += P.pitch;
   }
+#undef TSDFF_NEXT_ROW
 }
 
 template <int NF, bool EOS>

@@ -46,7 +46,7 @@ for STEP in "$@"; do
         python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extra > $OUT/launches_run.log 2>&1; echo "rc=$?"; tail -2 $OUT/launches_run.log | cut -c1-300 ;;
     ncu)
       # general launch first, all-sea second in every step: skip the 3 warm-up steps
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_tsadvc_march -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} -f -o $OUT/prof \
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-k_tsadvc_march} -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-2} -f -o $OUT/prof \
         python bench.py --kdm ${NCU_KDM:-6} --steps 1 --warmup 3 --no-e2e --no-cpu --no-extra $BENCH_ARGS > $OUT/ncu_run.log 2>&1; echo "rc=$?"; tail -2 $OUT/ncu_run.log | cut -c1-300
       ls -la $OUT/prof.ncu-rep ;;
     traffic)
