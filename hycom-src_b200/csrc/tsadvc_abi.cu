@@ -640,11 +640,17 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
   const int use = strip_use(P.nc), lead = strip_lead(P.nc), wid = 32 * P.nc;
   const int pitch = h->pitch, nrows = h->nrows;
   const int kMinRows = 48;
+  // The 64-column windows are not 128-byte aligned: a strip whose neighbour is elsewhere in j fetches 624
+  // bytes per row and array for 464 useful ones.  Pieces that start on common band boundaries let
+  // neighbouring strips march the same rows at the same time and share those lines through L2.  DRAM traffic of
+  // the launch pair at GLBb0.08 (algorithmic 44.2 GB; profiles/r02q-u, r03j): maximal all-sea runs cut per
+  // strip 58.4 GB; cut at common 256-row bands 53.8 GB; all-sea pieces = whole 252-row bands only 50.7 GB (the
+  // default: 27 % instead of 76 % of the rows then take the mask-free body, +0.8 % time); one general launch 47.5
   const char* cbnd = getenv("HYCOM_TSADVC_SEG_BAND");
-  // 256 rows: DRAM traffic of the launch pair 58.4 -> 53.8 GB at GLBb0.08 (the 64-column windows are not
-  // 128-byte aligned: a strip whose neighbour is elsewhere in j fetches 624 bytes per row and array for
-  // 464 useful ones; the regular chunks of a single launch reach 47.5 GB), profiles/r02u
-  const int band = std::max(48, std::min(cbnd ? atoi(cbnd) : 256, chunk_rows));
+  const char* cwh = getenv("HYCOM_TSADVC_SEG_WHOLE");
+  const bool whole = !(cwh && atoi(cwh) == 0);
+  int band = std::max(48, std::min(cbnd ? atoi(cbnd) : (whole ? 252 : 256), chunk_rows));
+  if (whole) band = band / 6 * 6;
   std::vector<MarchSeg> seg[2];
   std::vector<char> good(nrows + 8), taken(nrows);
   for (int q = 0; q < P.nrect; ++q) {
@@ -662,7 +668,16 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
         good[r] = g;
         taken[r] = 0;
       }
-      if (fast_piece >= kMinRows) {
+      if (whole) {
+        for (int a = R.row0 / band * band; a < R.row1; a += band) {
+          const int lo = std::max(a, R.row0), hi = std::min(a + band, R.row1);
+          bool ok = (hi - lo) % 6 == 0 && hi - lo >= kMinRows && lo - 3 >= 0 && hi + 3 <= nrows;
+          for (int t = lo - 3; ok && t < hi + 3; ++t) ok = good[t];
+          if (!ok) continue;
+          seg[0].push_back(MarchSeg{st, lo, hi, 0});
+          for (int t = lo; t < hi; ++t) taken[t] = 1;
+        }
+      } else if (fast_piece >= kMinRows) {
         int r = 0;
         while (r < nrows) {
           if (!good[r]) { ++r; continue; }
