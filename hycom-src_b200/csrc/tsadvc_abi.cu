@@ -632,9 +632,11 @@ int halo_arrays(hycom_tsadvc_handle* h, const std::vector<Adv>& adv, int mbdy, H
 // rest by the general one.  The marching loop works in rounds of six rows, so the all-sea runs are cut
 // to a multiple of six rows (no row beyond the run is ever computed); short runs are not worth the six
 // rows of pipeline fill and stay with the general kernel.  Built once per (part, nc, chunk rows).
-static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part, int chunk_rows,
+static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part, int chunk_rows, bool whole_default,
                           const hycom_tsadvc_handle::SegLists** out) {
-  const long key = ((long)part << 40) | ((long)P.nc << 32) | (long)chunk_rows;   // (the band is fixed per process)
+  const char* cwh = getenv("HYCOM_TSADVC_SEG_WHOLE");
+  const bool whole = cwh ? atoi(cwh) != 0 : whole_default;
+  const long key = ((long)whole << 44) | ((long)part << 40) | ((long)P.nc << 32) | (long)chunk_rows;   // (the band is fixed per process)
   auto it = h->seg_cache.find(key);
   if (it != h->seg_cache.end()) { *out = &it->second; return 0; }
   const int use = strip_use(P.nc), lead = strip_lead(P.nc), wid = 32 * P.nc;
@@ -645,10 +647,9 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
   // neighbouring strips march the same rows at the same time and share those lines through L2.  DRAM traffic of
   // the launch pair at GLBb0.08 (algorithmic 44.2 GB; profiles/r02q-u, r03j): maximal all-sea runs cut per
   // strip 58.4 GB; cut at common 256-row bands 53.8 GB; all-sea pieces = whole 252-row bands only 50.7 GB (the
-  // default: 27 % instead of 76 % of the rows then take the mask-free body, +0.8 % time); one general launch 47.5
+  // default of FCT2/FCT4: 27 % instead of 76 % of the rows then take the mask-free body, +0.8 % time; MPDATA, whose
+  // mask-free body saves more, keeps the maximal runs: 90.2 against 94.7 ms with 8 tracers); one general launch 47.5
   const char* cbnd = getenv("HYCOM_TSADVC_SEG_BAND");
-  const char* cwh = getenv("HYCOM_TSADVC_SEG_WHOLE");
-  const bool whole = !(cwh && atoi(cwh) == 0);
   int band = std::max(48, std::min(cbnd ? atoi(cbnd) : (whole ? 252 : 256), chunk_rows));
   if (whole) band = band / 6 * 6;
   std::vector<MarchSeg> seg[2];
@@ -841,7 +842,8 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   const char* cs = getenv("HYCOM_TSADVC_SPLIT");
   if ((aadv == 2 || aadv == 1 || aadv == 4) && !p.btrmas && !u_prolog && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
     const hycom_tsadvc_handle::SegLists* L = nullptr;
-    if ((rc = march_segments(h, P, part, chunk_rows, &L))) return rc;
+    // (whole-band all-sea pieces on one tile only: on the tiles of a 2x2 tiling the march is 3-4 % slower with them)
+    if ((rc = march_segments(h, P, part, chunk_rows, aadv != 1 && h->d.ipr * h->d.jpr == 1, &L))) return rc;
     rc = 0;
     for (int c = 1; c >= 0 && !rc; --c) {       // the general segments first: the long launch hides their tail
       if (!L->n[c]) continue;

@@ -196,17 +196,26 @@ def test_all_sea_segments_equal_general_launch(oracle, advtyp, monkeypatch):
     cfg, sea, g, cb = util.make_case(420, 360, 2, nreg=0, ntracr=1, seed=12, m=m, n=n, advtyp=advtyp)
     ref = util.run_oracle(oracle, cb, sea, m, n)
     out = {}
-    for split in ("1", "0"):
-        monkeypatch.setenv("HYCOM_TSADVC_SPLIT", split)
+    # the pair with all-sea pieces = whole bands (the default, short bands so that several fit), with maximal
+    # all-sea runs cut at the band boundaries, and the single general launch
+    for key, env in (("whole", {"HYCOM_TSADVC_SPLIT": "1", "HYCOM_TSADVC_SEG_WHOLE": "1", "HYCOM_TSADVC_SEG_BAND": "96"}),
+                     ("runs", {"HYCOM_TSADVC_SPLIT": "1", "HYCOM_TSADVC_SEG_WHOLE": "0", "HYCOM_TSADVC_SEG_BAND": "128"}),
+                     ("one", {"HYCOM_TSADVC_SPLIT": "0"})):
+        for name in ("HYCOM_TSADVC_SPLIT", "HYCOM_TSADVC_SEG_WHOLE", "HYCOM_TSADVC_SEG_BAND"):
+            monkeypatch.delenv(name, raising=False)
+        for name, val in env.items():
+            monkeypatch.setenv(name, val)
         cbx = syn.build_cb_arrays(cfg, g, sea, m, n, advtyp=advtyp)
         got, _, launches = _run_host_path(cbx, m, n)
-        out[split] = (got, launches)
+        out[key] = (got, launches)
         _compare(cbx, g, got, ref, n, ["saln", "temp"])
         _compare(cbx, g, {"t": got["tracer"][0]}, {"t": ref["tracer"][0]}, n, ["t"])
     # the pair really ran: one marching launch more per call of run_march than the general launch alone
-    assert out["1"][1] > out["0"][1], (out["1"][1], out["0"][1])
+    assert out["whole"][1] > out["one"][1], (out["whole"][1], out["one"][1])
+    assert out["runs"][1] > out["one"][1], (out["runs"][1], out["one"][1])
     for name in ("temp", "saln"):
-        assert np.array_equal(out["1"][0][name], out["0"][0][name], equal_nan=True)
+        assert np.array_equal(out["whole"][0][name], out["one"][0][name], equal_nan=True)
+        assert np.array_equal(out["runs"][0][name], out["one"][0][name], equal_nan=True)
 
 
 @pytest.mark.parametrize("advtyp,ntracr", [(2, 0), (1, 1)])
