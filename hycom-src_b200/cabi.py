@@ -16,7 +16,7 @@ MXTRCR = 16
 F_TEMP, F_SALN, F_TH3D, F_DP, F_UFLX, F_VFLX, F_TRACER, F_ONETA, F_THETA, F_Q2, F_Q2L = range(11)
 (F_DPO, F_ONETAO, F_PBAVG, F_PBOT, F_OTEMP, F_OSALN, F_OTH3D, F_OTRACER, F_OQ2, F_OQ2L) = range(11, 21)
 (F_U, F_V, F_DPU, F_DPV, F_UBAVG, F_VBAVG, F_DEPTHU, F_DEPTHV, F_P, F_DPMIXL, F_UFLXAV, F_VFLXAV, F_DPAV, F_UTOTN,
- F_VTOTN, F_DPMOLD) = range(21, 37)
+ F_VTOTN, F_DPMOLD, F_THKDF4U, F_THKDF4V) = range(21, 39)
 S_SCPX, S_SCPY, S_SCUX, S_SCUY, S_SCVX, S_SCVY, S_ONETA = range(10, 17)
 
 OK, EINVAL, ECUDA, EUNSUPPORTED, ENBDY, EADVTYP, ENOMEM = range(7)

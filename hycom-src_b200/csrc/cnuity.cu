@@ -13,8 +13,10 @@
 //   k_cn_asselin :1396-1422 Robert-Asselin filter of dp behind one more exchange of dp(:,:,:,n)
 // Arithmetic is the Fortran's, expression by expression (-fmad=false, IEEE division); fluxes are zero
 // off the iu / iv points (geopar.F90:822-871 zeroes them there once, cnuity never writes them).
-// Scope: .not.btrmas, thkdf2 = thkdf4 = 0, no open-boundary faces, no Stokes drift, not (hybrid .and.
-// mxlkta), not (synflt .and. wvelfl) - everything else is refused by the caller (tsadvc_abi.cu).
+//   k_thk_*      :745-1124 interface-depth diffusion, biharmonic (thkdf4) or Laplacian (thkdf2): three kernels per
+//                          interface, behind their own exchange of dpmixl(n), dp(n), p
+// Scope: .not.btrmas, no open-boundary faces, no Stokes drift, not (hybrid .and. mxlkta), not (synflt .and.
+// wvelfl) - everything else is refused by the caller (tsadvc_abi.cu).
 // Measured at GLBb0.08 (profiles/r02x-z): ten streaming sweeps over all layers (the first version, 64
 // passes over a 3-D field through nine scratch fields) 66 ms; the tile kernel with its operands loaded
 // where they are used 60 ms (47 % of the warps' time waiting for them); operands of layer k+1 requested
@@ -341,14 +343,132 @@ __global__ void __launch_bounds__(256) k_cn_loop77(const CnuityParams P) {
       P.dp_n[qk] = d;
       pk = pk + d;
       P.p[qk + P.slab] = pk;
-      if (P.dpav) P.dpav[qk] = P.dpav[qk] + d;
+      if (P.dpav && !P.defer_av) P.dpav[qk] = P.dpav[qk] + d;
     }
     if (P.isopyc) P.dpmixl_n[q] = P.dp_n[q];
   }
+  if (P.defer_av) return;
   if (P.uflxav && (mk & M_IU))
     for (int k = 0; k < P.kk; ++k) { const long qk = q + (long)k * P.slab; P.uflxav[qk] = P.uflxav[qk] + P.uflx[qk]; }
   if (P.vflxav && (mk & M_IV))
     for (int k = 0; k < P.kk; ++k) { const long qk = q + (long)k * P.slab; P.vflxav[qk] = P.vflxav[qk] + P.vflx[qk]; }
+}
+
+
+// =====================================================================================================
+// Biharmonic (:745-963) and Laplacian (:973-1124) thickness diffusion - literally, interface depth diffusion.
+// The interfaces p(:,:,2..kk) are moved one after the other (the biharmonic form limits the flux of an
+// interface against the one of the interface before and walks downward or upward in alternate steps), so the
+// reference's three sweeps per interface stay three kernels per interface: coupling between interfaces rules
+// out the all-layers form, and the halo each sweep consumes rules out one kernel per column.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_thk_init(const CnuityParams P, int iflip) {
+  CN_CELL;
+  if (!inside) return;
+  P.fu[q] = 0.0; P.fv[q] = 0.0; P.t1[q] = 0.0; P.t2[q] = 0.0;
+  P.pold[q] = (iflip == 1 && (P.mask[q] & M_IP)) ? P.p[q + (long)P.kk * P.slab] : 0.0;
+}
+
+// util1, util2 of interface k (1-based), margin 5 (:796-833)
+__global__ void __launch_bounds__(256) k_thk_util(const CnuityParams P, int k) {
+  CN_CELL;
+  if (!inside || !in_margin(P, c, r, 5)) return;
+  const unsigned mk = P.mask[q];
+  if (!(mk & M_IP)) return;
+  const double onecm = 9806.0 * 0.01;   // mod_cb_arrays.F90:850
+  const double* pk = P.p + (long)(k - 1) * P.slab;
+  const double* dk = P.dp_n + (long)(k - 1) * P.slab;
+  const double* dm = P.dp_n + (long)(k - 2) * P.slab;
+  double u1 = 0.0, u2 = 0.0;
+  if (!(cmin(dk[q], dm[q]) < onecm)) {
+    // bigrid.F90:343-372: i-1 if sea; else i+1 if sea; otherwise i
+    const long ia = (mk & M_PW) ? q - 1 : ((mk & M_PE) ? q + 1 : q);
+    const long ib = (mk & M_PE) ? q + 1 : ((mk & M_PW) ? q - 1 : q);
+    const long ja = (mk & M_PS) ? q - P.pitch : ((mk & M_PN) ? q + P.pitch : q);
+    const long jb = (mk & M_PN) ? q + P.pitch : ((mk & M_PS) ? q - P.pitch : q);
+    u1 = pk[q] - .5 * (pk[ia] + pk[ib]);
+    u2 = pk[q] - .5 * (pk[ja] + pk[jb]);
+    if (u1 > 0.0) { if (cmin(dk[ia], dk[ib]) < onecm) u1 = 0.0; }
+    else          { if (cmin(dm[ia], dm[ib]) < onecm) u1 = 0.0; }
+    if (u2 > 0.0) { if (cmin(dk[ja], dk[jb]) < onecm) u2 = 0.0; }
+    else          { if (cmin(dm[ja], dm[jb]) < onecm) u2 = 0.0; }
+  }
+  P.t1[q] = u1; P.t2[q] = u2;
+}
+
+// the limited fluxes of interface k at the u and v points, margin 4 (:835-906, :1029-1061); uflx, vflx of the
+// layers above and below take them up
+template <bool BIH>
+__global__ void __launch_bounds__(256) k_thk_flux(const CnuityParams P, int k, int iflip, double dtinv) {
+  CN_CELL;
+  if (!inside || !in_margin(P, c, r, 4)) return;
+  const unsigned mk = P.mask[q];
+  const double* pk = P.p + (long)(k - 1) * P.slab;
+  const double* pb = P.p + (long)P.kk * P.slab;
+  const long ka = q + (long)(k - 2) * P.slab, kb = q + (long)(k - 1) * P.slab;
+#define THK_FACE(LO, FLUX, COEF, UTIL, OUT)                                                        \
+  {                                                                                                \
+    const long w = (LO);                                                                           \
+    double flxhi = .25 * (pb[q] - pk[q]) * P.scp2[q];                                              \
+    double flxlo = -.25 * (pb[w] - pk[w]) * P.scp2[w];                                             \
+    double want;                                                                                   \
+    if (BIH) {                                                                                     \
+      if (iflip == 0) { /* downward k loop */                                                      \
+        flxhi = cmin(flxhi, FLUX[q] + .25 * (pk[w] - P.pold[w]) * P.scp2[w]);                      \
+        flxlo = cmax(flxlo, FLUX[q] - .25 * (pk[q] - P.pold[q]) * P.scp2[q]);                      \
+      } else {          /* upward k loop */                                                        \
+        flxhi = cmin(flxhi, FLUX[q] + .25 * (P.pold[q] - pk[q]) * P.scp2[q]);                      \
+        flxlo = cmax(flxlo, FLUX[q] - .25 * (P.pold[w] - pk[w]) * P.scp2[w]);                      \
+      }                                                                                            \
+      want = (P.delt1 * COEF[q]) * (UTIL[w] - UTIL[q]);                                            \
+    } else {                                                                                       \
+      want = (P.delt1 * COEF[q]) * (pk[w] - pk[q]);                                                \
+    }                                                                                              \
+    const double f = cmin(flxhi, cmax(flxlo, want));                                               \
+    FLUX[q] = f;                                                                                   \
+    OUT[ka] = OUT[ka] + f * dtinv;                                                                 \
+    OUT[kb] = OUT[kb] - f * dtinv;                                                                 \
+  }
+  if (mk & M_IU) THK_FACE(q - 1, P.fu, P.thku, P.t1, P.uflx)
+  if (mk & M_IV) THK_FACE(q - P.pitch, P.fv, P.thkv, P.t2, P.vflx)
+#undef THK_FACE
+}
+
+// pold = p(k); p(k) moves with the divergence of the limited fluxes, margin 4 (:908-922, :1063-1078)
+__global__ void __launch_bounds__(256) k_thk_cell(const CnuityParams P, int k) {
+  CN_CELL;
+  if (!inside || !in_margin(P, c, r, 4) || !(P.mask[q] & M_IP)) return;
+  double* pk = P.p + (long)(k - 1) * P.slab;
+  const double v = pk[q];
+  P.pold[q] = v;
+  pk[q] = v - ((P.fu[q + 1] - P.fu[q]) + (P.fv[q + P.pitch] - P.fv[q])) * P.scp2i[q];
+}
+
+// interfaces may not cross; dp(:,:,:,n) from them, margin 4 (:937-962, :1092-1114); then the cumulative fluxes
+// of :1326-1350 that the diffusion postponed
+__global__ void __launch_bounds__(256) k_thk_final(const CnuityParams P) {
+  CN_CELL;
+  if (!inside) return;
+  const unsigned mk = P.mask[q];
+  if (in_margin(P, c, r, 4) && (mk & M_IP)) {
+    double pa = P.p[q];
+    for (int k = 1; k <= P.kk; ++k) {
+      const long qk = q + (long)k * P.slab;
+      double pbk = P.p[qk];
+      if (pbk < pa) { pbk = pa; P.p[qk] = pbk; }
+      P.dp_n[qk - P.slab] = pbk - pa;
+      pa = pbk;
+    }
+    if (P.isopyc) P.dpmixl_n[q] = P.dp_n[q];
+  }
+  const int i = c + 1 - P.nbdy, j = r + 1 - P.nbdy;
+  if (i < 1 || i > P.ii || j < 1 || j > P.jj) return;
+  for (int k = 0; k < P.kk; ++k) {
+    const long qk = q + (long)k * P.slab;
+    if (P.uflxav && (mk & M_IU)) P.uflxav[qk] = P.uflxav[qk] + P.uflx[qk];
+    if (P.vflxav && (mk & M_IV)) P.vflxav[qk] = P.vflxav[qk] + P.vflx[qk];
+    if (P.dpav && (mk & M_IP)) P.dpav[qk] = P.dpav[qk] + P.dp_n[qk];
+  }
 }
 
 }  // namespace
@@ -372,6 +492,28 @@ int launch_cnuity(int stage, const CnuityParams& P, cudaStream_t st) {
   k_cn_loop76<<<gt, dim3(32, CTY), bytes, st>>>(P);
   k_cn_loop77<<<g2, block, 0, st>>>(P);
   return (int)cudaGetLastError();
+}
+
+int launch_cnuity_thkdf(const CnuityParams& P, int bih, int nstep, cudaStream_t st) {
+  const dim3 block(32, 8), g2((P.pitch + 31) / 32, (P.nrows + 7) / 8);
+  const int iflip = nstep % 2;        // :766
+  const double dtinv = 1. / P.delt1;  // :765
+  int n = 0;
+  k_thk_init<<<g2, block, 0, st>>>(P, iflip); ++n;
+  // :790 alternate between upward and downward direction in the k loop (biharmonic); :1013 k = 2,kk (Laplacian)
+  const int k0 = bih ? 2 * (1 - iflip) + P.kk * iflip : 2, k1 = bih ? P.kk * (1 - iflip) + 2 * iflip : P.kk;
+  const int kstep = bih ? 1 - 2 * iflip : 1;
+  for (int k = k0; kstep > 0 ? k <= k1 : k >= k1; k += kstep) {
+    if (bih) {
+      k_thk_util<<<g2, block, 0, st>>>(P, k); ++n;
+      k_thk_flux<true><<<g2, block, 0, st>>>(P, k, iflip, dtinv); ++n;
+    } else {
+      k_thk_flux<false><<<g2, block, 0, st>>>(P, k, iflip, dtinv); ++n;
+    }
+    k_thk_cell<<<g2, block, 0, st>>>(P, k); ++n;
+  }
+  k_thk_final<<<g2, block, 0, st>>>(P); ++n;
+  return cudaGetLastError() == cudaSuccess ? n : -1;
 }
 
 }  // namespace tsadvc

@@ -109,19 +109,21 @@ Mirror* mirror_of(hycom_tsadvc_handle* h, int field, int ktr) {
     case HYCOM_F_UTOTN: return &h->utotn;
     case HYCOM_F_VTOTN: return &h->vtotn;
     case HYCOM_F_DPMOLD: return &h->dpmold;
+    case HYCOM_F_THKDF4U: return &h->thkdf4u;
+    case HYCOM_F_THKDF4V: return &h->thkdf4v;
   }
   return nullptr;
 }
 bool is3d(int field) {   // one time level only
   return field == HYCOM_F_UFLX || field == HYCOM_F_VFLX || field == HYCOM_F_THETA || field == HYCOM_F_PBAVG ||
          field == HYCOM_F_PBOT || (field >= HYCOM_F_OTEMP && field <= HYCOM_F_OQ2L) ||
-         (field >= HYCOM_F_UBAVG && field <= HYCOM_F_P) || (field >= HYCOM_F_UFLXAV && field <= HYCOM_F_DPMOLD);
+         (field >= HYCOM_F_UBAVG && field <= HYCOM_F_P) || (field >= HYCOM_F_UFLXAV && field <= HYCOM_F_THKDF4V);
 }
 // slabs per time slot of a mirror
 int nlayers_of(const hycom_tsadvc_handle* h, int field) {
   if (field == HYCOM_F_ONETA || field == HYCOM_F_ONETAO || field == HYCOM_F_PBOT || field == HYCOM_F_DEPTHU ||
       field == HYCOM_F_DEPTHV || field == HYCOM_F_DPMIXL || field == HYCOM_F_UTOTN || field == HYCOM_F_VTOTN ||
-      field == HYCOM_F_DPMOLD)
+      field == HYCOM_F_DPMOLD || field == HYCOM_F_THKDF4U || field == HYCOM_F_THKDF4V)
     return 1;
   if (field == HYCOM_F_PBAVG || field == HYCOM_F_UBAVG || field == HYCOM_F_VBAVG) return 3;
   if (field == HYCOM_F_P) return h->d.kdm + 1;
@@ -1803,8 +1805,11 @@ int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, con
   if (m < 1 || m > 2 || n < 1 || n > 2 || m == n) return fail(h, HYCOM_TSADVC_EINVAL, "cnuity: bad leapfrog slots m=%d n=%d", m, n);
   if (h->d.nbdy < 6) return fail(h, HYCOM_TSADVC_ENBDY, "error: cnuity needs nbdy >= 6 (mbdy = 6, cnuity.F90:98)");
   if (prm->btrmas) return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity with btrmas (oneta_u, oneta_v, onetacnt) is not built");
-  if (prm->thkdf2 != 0.0 || prm->thkdf4 != 0.0)
-    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity: interface smoothing (thkdf2/thkdf4, cnuity.F90:760-1124) is not built");
+  if (prm->thkdf2 != 0.0 && prm->thkdf4 != 0.0)
+    return fail(h, HYCOM_TSADVC_EINVAL, "cnuity: only one of thkdf2 and thkdf4 is non-zero (cnuity.F90:758)");
+  const bool thk = prm->thkdf2 != 0.0 || prm->thkdf4 != 0.0;
+  if (thk && (!h->thkdf4u.lev[0] || !h->thkdf4v.lev[0]))
+    return fail(h, HYCOM_TSADVC_EINVAL, "cnuity with thkdf2/thkdf4 reads thkdf4u, thkdf4v: upload HYCOM_F_THKDF4U/_THKDF4V first");
   if (prm->hybrid && prm->mxlkta)
     return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity: vertical advection of dpmixl (hybrid & mxlkta, :1148-1324) is not built");
   if (!h->scuy || !h->scvx) return fail(h, HYCOM_TSADVC_EINVAL, "cnuity needs scuy, scvx (set_static)");
@@ -1834,6 +1839,12 @@ int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, con
   if (!h->cnuity_scratch && (rc = dalloc_field(h, &h->cnuity_scratch, (size_t)kk * h->slab))) return rc;
   if (!h->d_dpkmin && (rc = dalloc(h, (void**)&h->d_dpkmin, sizeof(double) * 2 * kk, false))) return rc;
   P.dnew = h->cnuity_scratch;
+  if (thk) {   // the interface-depth diffusion of :745-1124 and the cumulative fluxes behind it
+    if (!h->thk_scratch && (rc = dalloc_field(h, &h->thk_scratch, 5 * (size_t)h->slab))) return rc;
+    P.pold = h->thk_scratch; P.t1 = P.pold + h->slab; P.t2 = P.t1 + h->slab; P.fu = P.t2 + h->slab; P.fv = P.fu + h->slab;
+    P.thku = h->thkdf4u.lev[0]; P.thkv = h->thkdf4v.lev[0]; P.scp2 = h->scp2;
+    P.defer_av = 1;
+  }
   P.dpkmin = h->d_dpkmin;
   P.pitch = h->pitch; P.nrows = h->nrows; P.nbdy = h->d.nbdy; P.ii = h->d.ii; P.jj = h->d.jj; P.kk = kk;
   P.slab = h->slab; P.mask = h->mask; P.scuy = h->scuy; P.scvx = h->scvx; P.scp2i = h->scp2i;
@@ -1865,6 +1876,26 @@ int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, con
   }
   if ((rc = launch_cnuity(0, P, h->stream))) return fail(h, HYCOM_TSADVC_ECUDA, "cnuity kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   h->launches += 3;
+  if (thk) {   // :761-763 / :981-983 xctilr of dpmixl(n), dp(n), p(2:kk+1), width 6
+    if (single) {
+      if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_DPMIXL, 0, n, 6, 6)) || (rc = hycom_tsadvc_halo_local(h, HYCOM_F_DP, 0, n, 6, 6)) ||
+          (rc = halo_local_range(h, HYCOM_F_P, 0, 1, 6, 6, 1, kk)))
+        return rc;
+    } else {
+      HaloArrays a;
+      memset(&a, 0, sizeof a);
+      a.base[0] = P.dp_n; a.base[1] = P.p + h->slab; a.itype[0] = a.itype[1] = 1; a.narr = 2;
+      a.kk = kk; a.slab = h->slab; a.pitch = h->pitch; a.nrows = h->nrows; a.nbdy = h->d.nbdy;
+      a.ii = h->d.ii; a.jj = h->d.jj; a.mh = 6; a.nh = 6; a.fold = arctic_fold(h->d);
+      if ((rc = xc_exchange(h, a, false, h->stream))) return rc;
+      HaloArrays b = a;
+      b.narr = 1; b.base[0] = P.dpmixl_n; b.kk = 1;
+      if ((rc = xc_exchange(h, b, false, h->stream))) return rc;
+    }
+    const int nl = launch_cnuity_thkdf(P, prm->thkdf4 != 0.0, prm->nstep, h->stream);
+    if (nl < 0) return fail(h, HYCOM_TSADVC_ECUDA, "cnuity thickness-diffusion launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += nl;
+  }
   // :1400 xctilr(dp(:,:,:,n), 1,kk, 6,6, halo_ps), then the Robert-Asselin filter
   if (single) {
     if ((rc = hycom_tsadvc_halo_local(h, HYCOM_F_DP, 0, n, 6, 6))) return rc;

@@ -52,6 +52,8 @@ struct hycom_tsadvc_handle {
   // cnuity.F90 operands: u, v, dpu, dpv (kdm per slot), ubavg, vbavg (3 slabs), depthu, depthv (1), p (kdm+1),
   // dpmixl (1 per slot), uflxav, vflxav, dpav (kdm), utotn, vtotn, dpmold (1)
   tsadvc::Mirror u, v, dpu, dpv, ubavg, vbavg, depthu, depthv, p, dpmixl, uflxav, vflxav, dpav, utotn, vtotn, dpmold;
+  tsadvc::Mirror thkdf4u, thkdf4v;     // coefficients of the interface-depth diffusion (1 slab)
+  double* thk_scratch = nullptr;       // pold, util1, util2, uflux, vflux of cnuity.F90:745-1124 (5 slabs)
   double* cnuity_scratch = nullptr;   // kdm slabs: dp after loop 76
   double* d_dpkmin = nullptr;         // 2*kdm
   tsadvc::Mirror tracer[HYCOM_TSADVC_MXTRCR];

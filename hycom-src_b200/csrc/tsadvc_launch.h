@@ -229,10 +229,16 @@ struct CnuityParams {
   double *uflx, *vflx, *p, *utotn, *vtotn;
   double *uflxav, *vflxav, *dpav;               // may be null: not accumulated
   double* dnew;                                 // scratch: dp after loop 76 (kk slabs)
+  // interface-depth diffusion (:745-1124): coefficients at the u / v points, scp2, and five scratch slabs
+  const double *thku, *thkv, *scp2;
+  double *pold, *t1, *t2, *fu, *fv;
+  int defer_av;                                 // the cumulative fluxes (:1326-1350) follow the diffusion
   double* dpkmin;                               // 2*kk (device)
   double delt1, ra2fac;
   int isopyc;
 };
 int launch_cnuity(int stage, const CnuityParams& P, cudaStream_t stream);
+// the interface-depth diffusion behind its three exchanges; bih: thkdf4, else thkdf2; returns launches (< 0: error)
+int launch_cnuity_thkdf(const CnuityParams& P, int bih, int nstep, cudaStream_t stream);
 
 }  // namespace tsadvc

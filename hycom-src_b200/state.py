@@ -227,7 +227,8 @@ class Tsadvc:
             nlay = {cabi.F_ONETA: 1, cabi.F_ONETAO: 1, cabi.F_PBOT: 1, cabi.F_PBAVG: 3, cabi.F_Q2: g.kdm + 2,
                     cabi.F_Q2L: g.kdm + 2, cabi.F_OQ2: g.kdm + 2, cabi.F_OQ2L: g.kdm + 2, cabi.F_UBAVG: 3,
                     cabi.F_VBAVG: 3, cabi.F_DEPTHU: 1, cabi.F_DEPTHV: 1, cabi.F_P: g.kdm + 1, cabi.F_DPMIXL: 1,
-                    cabi.F_UTOTN: 1, cabi.F_VTOTN: 1, cabi.F_DPMOLD: 1}.get(fld, g.kdm)
+                    cabi.F_UTOTN: 1, cabi.F_VTOTN: 1, cabi.F_DPMOLD: 1, cabi.F_THKDF4U: 1,
+                    cabi.F_THKDF4V: 1}.get(fld, g.kdm)
             nk = nlay - k0 + 1
         out = np.empty((nk, g.nrows, g.ncols))
         self._ck(self.lib.hycom_tsadvc_download(self.h, fld, ktr, tlev, k0, nk, _ptr(out)))
@@ -320,6 +321,9 @@ class Tsadvc:
         for fld, nm in ((cabi.F_UFLX, "uflx"), (cabi.F_VFLX, "vflx"), (cabi.F_UFLXAV, "uflxav"), (cabi.F_VFLXAV, "vflxav"),
                         (cabi.F_DPAV, "dpav")):
             self.upload(fld, st[nm], 1)
+        if "thkdf4u" in st:
+            self.upload(cabi.F_THKDF4U, st["thkdf4u"], 1)
+            self.upload(cabi.F_THKDF4V, st["thkdf4v"], 1)
 
     def cnuity_device(self, m: int, n: int, ra2fac: float = 0.125, thkdf2: float = 0.0, thkdf4: float = 0.0,
                       mxlkta: bool = False):

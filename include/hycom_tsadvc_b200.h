@@ -90,7 +90,9 @@ enum {
   HYCOM_F_DPAV = 33,
   HYCOM_F_UTOTN = 34,   /* utotn, vtotn, dpmold (:,:), one slab */
   HYCOM_F_VTOTN = 35,
-  HYCOM_F_DPMOLD = 36
+  HYCOM_F_DPMOLD = 36,
+  HYCOM_F_THKDF4U = 37, /* thkdf4u, thkdf4v (:,:), one slab: the coefficients of the interface-depth diffusion at the */
+  HYCOM_F_THKDF4V = 38  /* u and v points (forfun.F90:2541-2568; they hold the thkdf2 ones when thkdf4 = 0)          */
 };
 
 /* mod_dimensions.F90:33,45-49 + mod_xc tile geometry (mod_xc_mp.h:2317-3288) */
@@ -356,8 +358,10 @@ int hycom_tsadvc_asselin_filter_device(hycom_tsadvc_handle *h, int32_t m, int32_
  * The xctilr calls of :100-107 and :1400 (width 6) are done here (single tile: locally; several tiles: through
  * the communicator).  dpkmin (2*kdm reals, may be NULL) receives the per-layer minima of loops 14 and 15
  * (:471, :679) of this tile when mod(nstep,3) == 0, as the reference evaluates them.
- * Scope: .not.btrmas, thkdf2 = thkdf4 = 0 (no interface smoothing), no open-boundary faces, no Stokes
- * drift, not (hybrid .and. mxlkta), not (synflt .and. wvelfl): anything else returns EUNSUPPORTED. */
+ * thkdf4 != 0 (biharmonic) or thkdf2 != 0 (Laplacian) applies the interface-depth diffusion of :745-1124 with the
+ * coefficients in the mirrors HYCOM_F_THKDF4U / _THKDF4V (uploaded once, valid halos) and its three xctilr calls.
+ * Scope: .not.btrmas, no open-boundary faces, no Stokes drift, not (hybrid .and. mxlkta), not (synflt .and.
+ * wvelfl): anything else returns EUNSUPPORTED. */
 typedef struct hycom_cnuity_params {
   int32_t btrmas, isopyc, hybrid, mxlkta, nstep, pad;
   double delt1, ra2fac, thkdf2, thkdf4;

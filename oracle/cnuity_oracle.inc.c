@@ -4,8 +4,7 @@
  * CPU restatement of HYCOM's continuity equation cnuity(m,n) (cnuity.F90), the producer of the
  * dp(:,:,:,n), uflx, vflx that tsadvc(m,n) consumes, sweep by sweep with
  * the Fortran loop ranges and operation order.  Scope (everything else is refused with an error):
- *   .not.btrmas, thkdf2 = thkdf4 = 0 (no interface smoothing, :760-1124), no open-boundary faces
- *   (iuopn = ivopn = 0, :170-229, :327-358), no STOKES drift, not (hybrid .and. mxlkta) (:1148-1324),
+ *   .not.btrmas, no open-boundary faces (iuopn = ivopn = 0, :170-229, :327-358), no STOKES drift, not (hybrid .and. mxlkta) (:1148-1324),
  *   not (synflt .and. wvelfl) (:1128-1142).
  * PARITY UNPINNED like the rest of the oracle (no Fortran compiler in this image); a second, independent
  * restatement in numpy (oracle/np_restatement.py: cnuity) must agree with it bit for bit.
@@ -25,6 +24,9 @@ int orc_cnuity_alloc(orc_tile *t) {
   t->dpmixl = alloc_r(P * 2); t->dpmold = alloc_r(P);
   t->uflxav = alloc_r(P * K); t->vflxav = alloc_r(P * K); t->dpav = alloc_r(P * K);
   t->dpkmin = alloc_r(2 * K);
+  t->thkdf4u = alloc_r(P); t->thkdf4v = alloc_r(P); t->pold = alloc_r(P);
+  if (!t->thkdf4u || !t->thkdf4v || !t->pold) return 1;
+  for (size_t q = 0; q < P; q++) { t->thkdf4u[q] = 0.0; t->thkdf4v[q] = 0.0; }
   if (!t->u || !t->v || !t->dpu || !t->dpv || !t->ubavg || !t->vbavg || !t->depthu || !t->depthv || !t->p ||
       !t->utotn || !t->vtotn || !t->utotm || !t->vtotm || !t->util3 || !t->dpmixl || !t->dpmold ||
       !t->uflxav || !t->vflxav || !t->dpav || !t->dpkmin)
@@ -59,7 +61,7 @@ int orc_cnuity(orc_tile *t, int m, int n, int do_halo) {
   const int kk = t->kk;
   if (orc_cnuity_alloc(t)) return seterr("cnuity: out of memory");
   if (t->btrmas) return seterr("cnuity: btrmas is not restated");
-  if (t->thkdf2 != 0.0 || t->thkdf4 != 0.0) return seterr("cnuity: interface smoothing (thkdf2/thkdf4) is not restated");
+  if (t->thkdf2 != 0.0 && t->thkdf4 != 0.0) return seterr("cnuity: only one of thkdf2 and thkdf4 is non-zero (:758)");
   const double delt1 = t->delt1, epsil = 1.0e-11;   /* mod_cb_arrays.F90:853 */
   const int nthr = nthr_of(t), jblk = jblk_of(t, nthr);
   (void)jblk;
@@ -267,6 +269,144 @@ int orc_cnuity(orc_tile *t, int m, int n, int do_halo) {
         }
         if (t->isopyc) t->dpmixl[c + P * (size_t)(n - 1)] = dpn[c];
       }
+
+  /* :745-963 biharmonic and :973-1124 Laplacian thickness diffusion (literally, interface depth diffusion) */
+  if (t->thkdf4 != 0.0 || t->thkdf2 != 0.0) {
+    const int bih = t->thkdf4 != 0.0;
+    const double onecm = 9806.0 * 0.01;   /* mod_cb_arrays.F90:850 */
+    double *pold = t->pold;
+    const double *thku = t->thkdf4u, *thkv = t->thkdf4v;   /* (the thkdf2 coefficients live in the same arrays) */
+    mbdy = 6;
+    if (do_halo) {   /* :761-763, :981-983 */
+      orc_xctilr_type(t, t->dpmixl + P * (size_t)(n - 1), 1, 1, 6, 6, 1);
+      orc_xctilr_type(t, dpn, 1, kk, 6, 6, 1);
+      orc_xctilr_type(t, t->p + P, 1, kk, 6, 6, 1);
+    }
+    const double dtinv = 1. / delt1;
+    const int iflip = t->nstep % 2;   /* :766 (the Laplacian block does not use it beyond pold) */
+    margin = mbdy;
+    for (int j = 1 - margin; j <= jj + margin; j++)
+      for (int i = 1 - margin; i <= ii + margin; i++) {
+        const size_t c = IX(i, j);
+        if (SEA_U) uflux[c] = 0.;
+        if (SEA_V) vflux[c] = 0.;
+        if (SEA_P) {
+          if (!bih) vflux[c] = 0.;   /* :1003 */
+          pold[c] = iflip == 1 ? t->p[c + P * (size_t)kk] : 0.;
+        }
+      }
+    /* :790 alternate between upward and downward direction in the k loop (biharmonic); :1013 k = 2,kk */
+    const int k0 = bih ? 2 * (1 - iflip) + kk * iflip : 2, k1 = bih ? kk * (1 - iflip) + 2 * iflip : kk;
+    const int kstep = bih ? 1 - 2 * iflip : 1;
+    for (int k = k0; kstep > 0 ? k <= k1 : k >= k1; k += kstep) {
+      double *pk = t->p + P * (size_t)(k - 1);          /* p(:,:,k) */
+      const double *pb = t->p + P * (size_t)kk;         /* p(:,:,kk+1) */
+      if (bih) {   /* :796-833 */
+        const double *dk = dpn + P * (size_t)(k - 1), *dkm = dpn + P * (size_t)(k - 2);
+        margin = mbdy - 1;
+        OMP_J
+        for (int j = 1 - margin; j <= jj + margin; j++)
+          for (int i = 1 - margin; i <= ii + margin; i++)
+            if (SEA_P) {
+              const size_t c = IX(i, j);
+              if (MIN2(dk[c], dkm[c]) < onecm) {
+                util1[c] = 0.0;
+                util2[c] = 0.0;
+              } else {
+                /* bigrid.F90:343-372: i-1 if sea; else i+1 if sea; otherwise i */
+                const int ia = ip[IX(i - 1, j)] != 0 ? i - 1 : (ip[IX(i + 1, j)] != 0 ? i + 1 : i);
+                const int ib = ip[IX(i + 1, j)] != 0 ? i + 1 : (ip[IX(i - 1, j)] != 0 ? i - 1 : i);
+                const int ja = ip[IX(i, j - 1)] != 0 ? j - 1 : (ip[IX(i, j + 1)] != 0 ? j + 1 : j);
+                const int jb = ip[IX(i, j + 1)] != 0 ? j + 1 : (ip[IX(i, j - 1)] != 0 ? j - 1 : j);
+                util1[c] = pk[c] - .5 * (pk[IX(ia, j)] + pk[IX(ib, j)]);
+                util2[c] = pk[c] - .5 * (pk[IX(i, ja)] + pk[IX(i, jb)]);
+                if (util1[c] > 0.0) {
+                  if (MIN2(dk[IX(ia, j)], dk[IX(ib, j)]) < onecm) util1[c] = 0.0;
+                } else {
+                  if (MIN2(dkm[IX(ia, j)], dkm[IX(ib, j)]) < onecm) util1[c] = 0.0;
+                }
+                if (util2[c] > 0.0) {
+                  if (MIN2(dk[IX(i, ja)], dk[IX(i, jb)]) < onecm) util2[c] = 0.0;
+                } else {
+                  if (MIN2(dkm[IX(i, ja)], dkm[IX(i, jb)]) < onecm) util2[c] = 0.0;
+                }
+              }
+            }
+      }
+      /* :835-906, :1029-1061 limit fluxes to avoid intertwining interfaces */
+      margin = mbdy - 2;
+      OMP_J
+      for (int j = 1 - margin; j <= jj + margin; j++) {
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_U) {
+            const size_t c = IX(i, j), w = IX(i - 1, j);
+            double flxhi = .25 * (pb[c] - pk[c]) * t->scp2[c];
+            double flxlo = -.25 * (pb[w] - pk[w]) * t->scp2[w];
+            double want;
+            if (bih) {
+              if (iflip == 0) {   /* downward k loop */
+                flxhi = MIN2(flxhi, uflux[c] + .25 * (pk[w] - pold[w]) * t->scp2[w]);
+                flxlo = MAX2(flxlo, uflux[c] - .25 * (pk[c] - pold[c]) * t->scp2[c]);
+              } else {            /* upward k loop */
+                flxhi = MIN2(flxhi, uflux[c] + .25 * (pold[c] - pk[c]) * t->scp2[c]);
+                flxlo = MAX2(flxlo, uflux[c] - .25 * (pold[w] - pk[w]) * t->scp2[w]);
+              }
+              want = (delt1 * thku[c]) * (util1[w] - util1[c]);
+            } else {
+              want = (delt1 * thku[c]) * (pk[w] - pk[c]);
+            }
+            uflux[c] = MIN2(flxhi, MAX2(flxlo, want));
+            t->uflx[c + P * (size_t)(k - 2)] = t->uflx[c + P * (size_t)(k - 2)] + uflux[c] * dtinv;
+            t->uflx[c + P * (size_t)(k - 1)] = t->uflx[c + P * (size_t)(k - 1)] - uflux[c] * dtinv;
+          }
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_V) {
+            const size_t c = IX(i, j), s_ = IX(i, j - 1);
+            double flxhi = .25 * (pb[c] - pk[c]) * t->scp2[c];
+            double flxlo = -.25 * (pb[s_] - pk[s_]) * t->scp2[s_];
+            double want;
+            if (bih) {
+              if (iflip == 0) {
+                flxhi = MIN2(flxhi, vflux[c] + .25 * (pk[s_] - pold[s_]) * t->scp2[s_]);
+                flxlo = MAX2(flxlo, vflux[c] - .25 * (pk[c] - pold[c]) * t->scp2[c]);
+              } else {
+                flxhi = MIN2(flxhi, vflux[c] + .25 * (pold[c] - pk[c]) * t->scp2[c]);
+                flxlo = MAX2(flxlo, vflux[c] - .25 * (pold[s_] - pk[s_]) * t->scp2[s_]);
+              }
+              want = (delt1 * thkv[c]) * (util2[s_] - util2[c]);
+            } else {
+              want = (delt1 * thkv[c]) * (pk[s_] - pk[c]);
+            }
+            vflux[c] = MIN2(flxhi, MAX2(flxlo, want));
+            t->vflx[c + P * (size_t)(k - 2)] = t->vflx[c + P * (size_t)(k - 2)] + vflux[c] * dtinv;
+            t->vflx[c + P * (size_t)(k - 1)] = t->vflx[c + P * (size_t)(k - 1)] - vflux[c] * dtinv;
+          }
+      }
+      /* :908-922, :1063-1078 */
+      margin = mbdy - 2;
+      OMP_J
+      for (int j = 1 - margin; j <= jj + margin; j++)
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_P) {
+            const size_t c = IX(i, j);
+            pold[c] = pk[c];
+            pk[c] = pk[c] - ((uflux[IX(i + 1, j)] - uflux[c]) + (vflux[IX(i, j + 1)] - vflux[c])) * t->scp2i[c];
+          }
+    }
+    /* :937-962, :1092-1114 */
+    margin = mbdy - 2;
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++)
+      for (int k = 1; k <= kk; k++)
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_P) {
+            const size_t c = IX(i, j);
+            double *pa = t->p + c + P * (size_t)(k - 1), *pbk = t->p + c + P * (size_t)k;
+            if (*pbk < *pa) *pbk = *pa;
+            dpn[c + P * (size_t)(k - 1)] = *pbk - *pa;
+            if (t->isopyc && k == 1) t->dpmixl[c + P * (size_t)(n - 1)] = dpn[c];
+          }
+  }
 
   /* :1326-1350 cumulative fluxes */
   margin = 0;

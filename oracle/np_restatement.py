@@ -653,11 +653,14 @@ def asselin_filter(cb, m, n):
 EPSIL = 1.0e-11   # mod_cb_arrays.F90:853
 
 
-def cnuity(geom, st, m, n, ip, iu, iv, scuy, scvx, scp2i, depthu, depthv, pbot, delt1, ra2fac, isopyc=False):
+def cnuity(geom, st, m, n, ip, iu, iv, scuy, scvx, scp2i, depthu, depthv, pbot, delt1, ra2fac, isopyc=False, thk=None):
     """st: dict of arrays in the Fortran layout with halos valid to width 6 (the caller did the xctilr of
     cnuity.F90:100-107): dp, dpo (2,kk,..), u, v, dpu, dpv (2,kk,..), ubavg, vbavg (3,..), dpmixl (2,..),
     uflx, vflx, uflxav, vflxav, dpav (kk,..).  Updated in place; returns p (kk+1,..), utotn, vtotn, dpkmin.
-    The halo refresh of dp(:,:,:,n) before the Robert-Asselin filter (:1400) is the caller's `halo` callback."""
+    The halo refresh of dp(:,:,:,n) before the Robert-Asselin filter (:1400) is the caller's.
+    thk: interface-depth diffusion (:745-1124), a dict with thkdf4u, thkdf4v (the coefficients at the u and v
+    points), bih (True: biharmonic, thkdf4; False: Laplacian, thkdf2), nstep, scp2 and halo(a, itype), the
+    xctilr of width 6 of :761-763."""
     kk = geom.kdm
     dp, dpo = st["dp"], st["dpo"]
     n_, m_ = n - 1, m - 1
@@ -748,12 +751,98 @@ def cnuity(geom, st, m, n, ip, iu, iv, scuy, scvx, scp2i, depthu, depthv, pbot, 
             p[k + 1] = np.where(r0, p[k] + dp[n_][k], p[k + 1])
         if isopyc:
             st["dpmixl"][n_] = np.where(r0, dp[n_][0], st["dpmixl"][n_])
+        if thk is not None:
+            cnuity_thkdf(geom, st, p, n, ip, iu, iv, thk["scp2"], scp2i, delt1, thk["thkdf4u"], thk["thkdf4v"],
+                         thk["bih"], thk["nstep"], isopyc, thk["halo"])
         # cumulative fluxes (:1326-1350)
         for k in range(kk):
             st["uflxav"][k] = np.where(sea_u & inner, st["uflxav"][k] + st["uflx"][k], st["uflxav"][k])
             st["vflxav"][k] = np.where(sea_v & inner, st["vflxav"][k] + st["vflx"][k], st["vflxav"][k])
             st["dpav"][k] = np.where(r0, st["dpav"][k] + dp[n_][k], st["dpav"][k])
     return p, utotn, vtotn, dpkmin, dpmold
+
+
+def cnuity_thkdf(geom, st, p, n, ip, iu, iv, scp2, scp2i, delt1, thku, thkv, bih, nstep, isopyc, halo):
+    """biharmonic (:745-963) or Laplacian (:973-1124) thickness diffusion - literally, interface depth diffusion:
+    the interfaces p(:,:,2..kk) are moved by fluxes limited so that interfaces do not intertwine; the biharmonic
+    form walks through the interfaces downward or upward in alternate time steps and limits each flux against
+    the one of the interface before.  Whole-array form; p, dp(:,:,:,n), uflx, vflx are updated in place."""
+    kk = geom.kdm
+    n_ = n - 1
+    dp = st["dp"]
+    onecm = 9806.0 * 0.01
+    st["dpmixl"][n_] = halo(st["dpmixl"][n_], 1)
+    dp[n_] = halo(dp[n_], 1)
+    p[1:] = halo(p[1:], 1)
+    dtinv = 1. / delt1
+    iflip = nstep % 2
+    sea_p, sea_u, sea_v = ip != 0, iu != 0, iv != 0
+    r5, r4 = _region(geom, 5), _region(geom, 4)
+    shape = (geom.nrows, geom.ncols)
+    uflux, vflux = np.zeros(shape), np.zeros(shape)
+    pold = p[kk].copy() if iflip == 1 else np.zeros(shape)
+    w_sea, e_sea = _sh(ip, -1, 0) != 0, _sh(ip, 1, 0) != 0
+    s_sea, n_sea = _sh(ip, 0, -1) != 0, _sh(ip, 0, 1) != 0
+
+    def xa(a):   # at ipim1x: i-1 if sea; else i+1 if sea; otherwise i (bigrid.F90:343-372)
+        return np.where(w_sea, _sh(a, -1, 0), np.where(e_sea, _sh(a, 1, 0), a))
+
+    def xb(a):
+        return np.where(e_sea, _sh(a, 1, 0), np.where(w_sea, _sh(a, -1, 0), a))
+
+    def ya(a):
+        return np.where(s_sea, _sh(a, 0, -1), np.where(n_sea, _sh(a, 0, 1), a))
+
+    def yb(a):
+        return np.where(n_sea, _sh(a, 0, 1), np.where(s_sea, _sh(a, 0, -1), a))
+
+    order = range(2, kk + 1) if (not bih or iflip == 0) else range(kk, 1, -1)
+    u1, u2 = np.zeros(shape), np.zeros(shape)
+    with np.errstate(all="ignore"):
+        for k in order:
+            pk, pb = p[k - 1], p[kk]
+            if bih:
+                dk, dkm = dp[n_][k - 1], dp[n_][k - 2]
+                a1 = pk - .5 * (xa(pk) + xb(pk))
+                a2 = pk - .5 * (ya(pk) + yb(pk))
+                a1 = np.where(a1 > 0.0, np.where(np.minimum(xa(dk), xb(dk)) < onecm, 0.0, a1),
+                              np.where(np.minimum(xa(dkm), xb(dkm)) < onecm, 0.0, a1))
+                a2 = np.where(a2 > 0.0, np.where(np.minimum(ya(dk), yb(dk)) < onecm, 0.0, a2),
+                              np.where(np.minimum(ya(dkm), yb(dkm)) < onecm, 0.0, a2))
+                thin = np.minimum(dk, dkm) < onecm
+                cell5 = sea_p & r5
+                u1 = np.where(cell5, np.where(thin, 0.0, a1), u1)
+                u2 = np.where(cell5, np.where(thin, 0.0, a2), u2)
+            for d, (flux, coef, util, sea_f, key) in enumerate(((uflux, thku, u1, sea_u, "uflx"),
+                                                                (vflux, thkv, u2, sea_v, "vflx"))):
+                di, dj = (-1, 0) if d == 0 else (0, -1)
+                lo_ = lambda a: _sh(a, di, dj)   # noqa: E731  the cell on the low side of the face
+                flxhi = .25 * (pb - pk) * scp2
+                flxlo = -.25 * (lo_(pb) - lo_(pk)) * lo_(scp2)
+                if bih:
+                    if iflip == 0:   # downward k loop
+                        flxhi = np.minimum(flxhi, flux + .25 * (lo_(pk) - lo_(pold)) * lo_(scp2))
+                        flxlo = np.maximum(flxlo, flux - .25 * (pk - pold) * scp2)
+                    else:            # upward k loop
+                        flxhi = np.minimum(flxhi, flux + .25 * (pold - pk) * scp2)
+                        flxlo = np.maximum(flxlo, flux - .25 * (lo_(pold) - lo_(pk)) * lo_(scp2))
+                    want = (delt1 * coef) * (lo_(util) - util)
+                else:
+                    want = (delt1 * coef) * (lo_(pk) - pk)
+                face = sea_f & r4
+                new = np.where(face, np.minimum(flxhi, np.maximum(flxlo, want)), flux)
+                flux[...] = new
+                st[key][k - 2] = np.where(face, st[key][k - 2] + new * dtinv, st[key][k - 2])
+                st[key][k - 1] = np.where(face, st[key][k - 1] - new * dtinv, st[key][k - 1])
+            cell = sea_p & r4
+            pold = np.where(cell, pk, pold)
+            p[k - 1] = np.where(cell, pk - ((_sh(uflux, 1, 0) - uflux) + (_sh(vflux, 0, 1) - vflux)) * scp2i, pk)
+        cell = sea_p & r4
+        for k in range(1, kk + 1):
+            p[k] = np.where(cell & (p[k] < p[k - 1]), p[k - 1], p[k])
+            dp[n_][k - 1] = np.where(cell, p[k] - p[k - 1], dp[n_][k - 1])
+        if isopyc:
+            st["dpmixl"][n_] = np.where(cell, dp[n_][0], st["dpmixl"][n_])
 
 
 def cnuity_asselin(geom, st, m, n, ip, ra2fac):

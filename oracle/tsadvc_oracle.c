@@ -138,7 +138,8 @@ void orc_tile_destroy(orc_tile *t) {
                   t->xmax, t->theta, t->q2, t->q2l, t->dpo, t->onetao, t->pbavg, t->pbot,
                   t->otemp, t->osaln, t->oth3d, t->otracer, t->oq2, t->oq2l,
                   t->u, t->v, t->dpu, t->dpv, t->ubavg, t->vbavg, t->depthu, t->depthv, t->p, t->utotn, t->vtotn,
-                  t->utotm, t->vtotm, t->util3, t->dpmixl, t->dpmold, t->uflxav, t->vflxav, t->dpav, t->dpkmin};
+                  t->utotm, t->vtotm, t->util3, t->dpmixl, t->dpmold, t->uflxav, t->vflxav, t->dpav, t->dpkmin,
+                  t->thkdf4u, t->thkdf4v, t->pold};
   for (size_t q = 0; q < sizeof(ptrs) / sizeof(ptrs[0]); q++) free(ptrs[q]);
   free(t);
 }
@@ -154,7 +155,7 @@ double *orc_f64(orc_tile *t, const char *name) {
   F(xmin); F(xmax); F(theta); F(q2); F(q2l);
   F(dpo); F(onetao); F(pbavg); F(pbot); F(otemp); F(osaln); F(oth3d); F(otracer); F(oq2); F(oq2l);
   F(u); F(v); F(dpu); F(dpv); F(ubavg); F(vbavg); F(depthu); F(depthv); F(p); F(utotn); F(vtotn); F(utotm); F(vtotm);
-  F(util3); F(dpmixl); F(dpmold); F(uflxav); F(vflxav); F(dpav); F(dpkmin);
+  F(util3); F(dpmixl); F(dpmold); F(uflxav); F(vflxav); F(dpav); F(dpkmin); F(thkdf4u); F(thkdf4v);
 #undef F
   return NULL;
 }

@@ -75,6 +75,8 @@ typedef struct orc_tile {
    * util3 (P); dpmixl (P,2); dpmold (P); uflxav, vflxav, dpav (P,kdm); dpkmin (2*kdm) */
   double *u, *v, *dpu, *dpv, *ubavg, *vbavg, *depthu, *depthv, *p, *utotn, *vtotn, *utotm, *vtotm, *util3,
       *dpmixl, *dpmold, *uflxav, *vflxav, *dpav, *dpkmin;
+  /* interface-depth diffusion (cnuity.F90:745-1124): coefficients at the u and v points (forfun.F90:2541-2568), scratch */
+  double *thkdf4u, *thkdf4v, *pold;
   double thkdf2, thkdf4;
 } orc_tile;
 

@@ -70,10 +70,14 @@ def test_cnuity_refuses_what_is_not_built():
     st = util.add_cnuity(cfg, sea, g, cb, 1, 2)
     ts = pkg.Tsadvc(cb)
     ts.upload_cnuity_state(st, 1, 2)
-    for kw in (dict(thkdf4=0.01), dict(thkdf2=0.01), dict(mxlkta=True)):
+    with pytest.raises(cabi.TsadvcError) as e:
+        ts.cnuity_device(1, 2, mxlkta=True)
+    assert e.value.code == cabi.EUNSUPPORTED
+    # the interface-depth diffusion needs its coefficients, and only one of thkdf2 / thkdf4 (cnuity.F90:758)
+    for kw in (dict(thkdf4=0.01), dict(thkdf2=0.01), dict(thkdf2=0.01, thkdf4=0.01)):
         with pytest.raises(cabi.TsadvcError) as e:
             ts.cnuity_device(1, 2, **kw)
-        assert e.value.code == cabi.EUNSUPPORTED
+        assert e.value.code == cabi.EINVAL
     cb.btrmas = True
     with pytest.raises(cabi.TsadvcError) as e:
         ts.cnuity_device(1, 2)
@@ -97,6 +101,53 @@ def test_cnuity_on_tiles(oracle, ipr, jpr, nreg):
     def go(ts, r):
         ts.upload_cnuity_state(sts[r], m, n)
         ts.cnuity_device(m, n)
+    run_tiles(tss, go)
+    for ts, cb in zip(tss, cbs):
+        _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1)
+    close_tiles(grp, tss)
+
+
+# interface-depth diffusion inside cnuity (cnuity.F90:745-1124): biharmonic in both sweep directions (nstep even:
+# downward, odd: upward) and Laplacian
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,bih,nstep,isopyc", [
+    (150, 150, 6, 0, True, 4, False),
+    (150, 150, 6, 0, True, 7, False),
+    (64, 90, 4, 1, True, 3, True),
+    (131, 77, 3, 3, False, 2, False),
+    (70, 45, 4, 4, False, 5, False),
+])
+def test_cnuity_thickness_diffusion_matches_oracle(oracle, itdm, jtdm, kdm, nreg, bih, nstep, isopyc):
+    m, n = 1, 2
+    extra = dict(isopyc=True, hybrid=False, nhybrd=0) if isopyc else {}
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=29, m=m, n=n, nstep=nstep, **extra)
+    thk = 0.01 if bih else 0.02
+    st = util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=thk, bih=bih)
+    ref = util.run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=isopyc)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_cnuity_state(st, m, n)
+    l0 = ts.launch_count
+    ts.cnuity_device(m, n, **({"thkdf4": thk} if bih else {"thkdf2": thk}))
+    assert ts.launch_count - l0 >= 4 + (3 if bih else 2) * (kdm - 1)
+    _check(ts, g, cb, ref, m, n, kdm, isopyc=isopyc)
+    ts.close()
+
+
+@pytest.mark.parametrize("ipr,jpr,nreg,bih,nstep", [(2, 2, 0, True, 5), (2, 1, 3, True, 2), (4, 2, 0, False, 3)])
+def test_cnuity_thickness_diffusion_on_tiles(oracle, ipr, jpr, nreg, bih, nstep):
+    from test_comm_gpu import make_tiles, run_tiles, close_tiles
+    m, n = 1, 2
+    itdm, jtdm, kdm = 160, 120, 4
+    thk = 0.01 if bih else 0.02
+    cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=23, m=m, n=n, nstep=nstep)
+    st1 = util.add_cnuity(cfg, sea, g1, cb1, m, n, thkdf=thk, bih=bih)
+    ref = util.run_oracle_cnuity(oracle, cb1, sea, st1, m, n)
+    cbs = [syn.build_cb_arrays(cfg, g, sea, m, n, nstep=nstep) for g in pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)]
+    sts = [util.add_cnuity(cfg, sea, cb.geom, cb, m, n, uscale=st1["_uscale"], thkdf=thk, bih=bih) for cb in cbs]
+    grp, tss = make_tiles(cfg, sea, itdm, jtdm, kdm, ipr, jpr, nreg, m, n, cbs=cbs)
+
+    def go(ts, r):
+        ts.upload_cnuity_state(sts[r], m, n)
+        ts.cnuity_device(m, n, **({"thkdf4": thk} if bih else {"thkdf2": thk}))
     run_tiles(tss, go)
     for ts, cb in zip(tss, cbs):
         _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1)

@@ -666,6 +666,7 @@ def test_reference_case_io_roundtrip(oracle, tmp_path):
 # ---------------------------------------------------------------------------------------
 def _np_cnuity(cb, g, st, m, n, ra2fac=0.125, isopyc=False):
     """the numpy path with the single-tile xctilr calls of cnuity.F90:100-107 and :1400"""
+    thkdf = st.get("_thkdf")
     st = {k: v.copy() for k, v in st.items() if not k.startswith("_")}
     nb = g.nbdy
     H = lambda a, it: npr.halo_single_tile(g, a, 6, 6, it)   # noqa: E731
@@ -677,8 +678,11 @@ def _np_cnuity(cb, g, st, m, n, ra2fac=0.125, isopyc=False):
     st["v"][m - 1] = H(st["v"][m - 1], 14)
     st["ubavg"][m - 1] = H(st["ubavg"][m - 1], 13)
     st["vbavg"][m - 1] = H(st["vbavg"][m - 1], 14)
+    thk = None
+    if "thkdf4u" in st:
+        thk = dict(thkdf4u=st["thkdf4u"], thkdf4v=st["thkdf4v"], bih=thkdf[1], nstep=cb.nstep, scp2=cb.scp2, halo=H)
     p, utotn, vtotn, dpkmin, dpmold = npr.cnuity(g, st, m, n, cb.ip, cb.iu, cb.iv, cb.scuy, cb.scvx, cb.scp2i,
-                                                 st["depthu"], st["depthv"], st["pbot"], cb.delt1, ra2fac, isopyc)
+                                                 st["depthu"], st["depthv"], st["pbot"], cb.delt1, ra2fac, isopyc, thk)
     st["dp"][n - 1] = H(st["dp"][n - 1], 1)
     npr.cnuity_asselin(g, st, m, n, cb.ip, ra2fac)
     st.update(p=p, utotn=utotn, vtotn=vtotn, dpkmin=dpkmin)
@@ -724,4 +728,48 @@ def test_cnuity_c_oracle_equals_numpy(oracle, itdm, jtdm, kdm, nreg, m, n, isopy
     colsum = ot.f64("dp")[n - 1].sum(axis=0)
     assert np.allclose(colsum[inner], st["pbot"][inner], rtol=1e-12)
     assert not np.array_equal(ot.f64("dp")[n - 1, 0][inner], st["dp"][n - 1, 0][inner])
+    ot.close()
+
+
+# interface-depth diffusion inside cnuity (cnuity.F90:745-1124): biharmonic in both sweep directions (nstep even:
+# downward, odd: upward) and Laplacian
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,bih,nstep,isopyc", [
+    (90, 70, 5, 0, True, 4, False),
+    (90, 70, 5, 0, True, 7, False),
+    (64, 90, 4, 1, True, 3, True),
+    (131, 77, 3, 3, False, 2, False),
+    (70, 45, 4, 4, False, 5, False),
+])
+def test_cnuity_thickness_diffusion_c_oracle_equals_numpy(oracle, itdm, jtdm, kdm, nreg, bih, nstep, isopyc):
+    m, n = 1, 2
+    extra = dict(isopyc=True, hybrid=False, nhybrd=0) if isopyc else {}
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=29, m=m, n=n, nstep=nstep, **extra)
+    st = util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=0.01 if bih else 0.02, bih=bih)
+    want = _np_cnuity(cb, g, st, m, n, isopyc=isopyc)
+    plain = _np_cnuity(cb, g, {k: v for k, v in st.items() if k not in ("thkdf4u", "thkdf4v", "_thkdf")}, m, n,
+                       isopyc=isopyc)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    util.oracle_load_cnuity(ot, st)
+    ot.set_i("isopyc", int(isopyc))
+    ot.cnuity(m, n, 1)
+    nb = g.nbdy
+    inner = util.interior_sea(cb)
+    iu_in = np.zeros_like(inner); iv_in = np.zeros_like(inner)
+    iu_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iu[nb:nb + g.jj, nb:nb + g.ii] != 0
+    iv_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iv[nb:nb + g.jj, nb:nb + g.ii] != 0
+    for k in range(kdm):
+        assert np.array_equal(ot.f64("dp")[n - 1, k][inner], want["dp"][n - 1, k][inner]), ("dp.n", k)
+        assert np.array_equal(ot.f64("dp")[m - 1, k][inner], want["dp"][m - 1, k][inner]), ("dp.m", k)
+        assert np.array_equal(ot.f64("uflx")[k][iu_in], want["uflx"][k][iu_in]), ("uflx", k)
+        assert np.array_equal(ot.f64("vflx")[k][iv_in], want["vflx"][k][iv_in]), ("vflx", k)
+        assert np.array_equal(ot.f64("p")[k + 1][inner], want["p"][k + 1][inner]), ("p", k)
+        assert np.array_equal(ot.f64("dpav")[k][inner], want["dpav"][k][inner]), ("dpav", k)
+        assert np.array_equal(ot.f64("uflxav")[k][iu_in], want["uflxav"][k][iu_in]), ("uflxav", k)
+    if isopyc:
+        assert np.array_equal(ot.f64("dpmixl")[n - 1][inner], want["dpmixl"][n - 1][inner])
+    # the diffusion moved interfaces (and only interfaces: the column still sums to pbot), layers stay non-negative
+    got = ot.f64("dp")[n - 1]
+    assert not np.array_equal(got[1][inner], plain["dp"][n - 1, 1][inner])
+    assert np.allclose(got.sum(axis=0)[inner], st["pbot"][inner], rtol=1e-12)
+    assert (got[:, inner] >= 0.0).all()
     ot.close()

@@ -176,7 +176,7 @@ def add_asselin(cfg, sea, g, cb, m, n, sigver=6, seed=77):
     return cb
 
 
-def add_cnuity(cfg, sea, g, cb, m, n, seed=91, uscale=None):
+def add_cnuity(cfg, sea, g, cb, m, n, seed=91, uscale=None, thkdf=0.0, bih=True):
     """operands of cnuity(m,n) (cnuity.F90) on top of a case, as a dict of arrays in the Fortran layout.
     Halos of the arrays cnuity exchanges itself (:100-107) are NaN, like every exchanged array; pbot, depthu,
     depthv arrive with valid halos.  u, v are O(0.3 m/s) smooth fields (both signs), zero off the iu / iv
@@ -231,6 +231,16 @@ def add_cnuity(cfg, sea, g, cb, m, n, seed=91, uscale=None):
         uflxav=np.zeros((kk,) + shp), vflxav=np.zeros((kk,) + shp), dpav=np.zeros((kk,) + shp),
         pbot=np.ascontiguousarray(pbot), depthu=np.ascontiguousarray(depthu), depthv=np.ascontiguousarray(depthv))
     st["_uscale"] = uscale
+    if thkdf:
+        # forfun.F90:2541-2568: thkdf4u = thkdf4*aspux**3*scuy (biharmonic) or thkdf2*aspux*scuy (Laplacian) at
+        # the u points, 0.0 elsewhere (aspux = aspvy = 1 on the synthetic grids); a smooth variation on top
+        # (a function of the global cell, wrapped like the grid, so that every tiling sees the same halos)
+        ig = is_[None, :] + 0.0 * js[:, None]
+        jg = js[:, None] + 0.0 * is_[None, :]
+        var = 1.0 + 0.2 * np.sin(2.0 * np.pi * 3.0 * ig / g.itdm) * np.cos(2.0 * np.pi * 2.0 * jg / g.jtdm)
+        st["thkdf4u"] = np.ascontiguousarray(np.where(cb.iu != 0, thkdf * var * cb.scuy, 0.0))
+        st["thkdf4v"] = np.ascontiguousarray(np.where(cb.iv != 0, thkdf * var * cb.scvx, 0.0))
+        st["_thkdf"] = (thkdf, bih)
     # geopar.F90:822-871: uflx, vflx are zero on the land faces that bound sea segments
     st["uflx"][:, cb.iu == 0] = 0.0
     st["vflx"][:, cb.iv == 0] = 0.0
@@ -242,6 +252,10 @@ def oracle_load_cnuity(ot, st):
     for name in ("dp", "dpo", "u", "v", "dpu", "dpv", "ubavg", "vbavg", "dpmixl", "uflx", "vflx", "uflxav", "vflxav",
                  "dpav", "pbot", "depthu", "depthv"):
         ot.f64(name)[...] = st[name]
+    if "thkdf4u" in st:
+        ot.f64("thkdf4u")[...] = st["thkdf4u"]
+        ot.f64("thkdf4v")[...] = st["thkdf4v"]
+        ot.set_d("thkdf4" if st["_thkdf"][1] else "thkdf2", st["_thkdf"][0])
 
 
 def run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=False):
