@@ -10,6 +10,7 @@
 #   ref        bench.py --impl reference
 #   launches   ncu launch list of a short bench run (N=1)
 #   cnuity     cnuity parity tests + timing at GLBb0.08; cnuity_launches / cnuity_ncu: per-kernel times, full capture
+#   sanitize   compute-sanitizer memcheck + racecheck on small cases of the newer kernels
 #   traffic    DRAM bytes + L2 hit rate of the marching launches of one full-size step
 #   ncu        ncu --set full + source of the marching kernel (N=1, reduced kdm)
 #   tma        the tensor-map TMA probe, every variant in its own process
@@ -87,6 +88,11 @@ PY
     cnuity_ncu)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:${CN_KERNEL:-k_cn_loop76} -c 1 -f -o $OUT/cnuity_prof \
         python tools/cnuity_timing.py 1 0 > $OUT/cnuity_ncu_run.log 2>&1; echo "rc=$?"; tail -2 $OUT/cnuity_ncu_run.log | cut -c1-200 ;;
+    sanitize)
+      # memcheck and racecheck (shared-memory hazards) of the newer kernels on small cases
+      SEL=${SANITIZE_SEL:-"cnuity_device_matches_oracle or thickness_diffusion_matches_oracle or isopyc_with_tracers"}
+      timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_cnuity_gpu.py tests/test_parity_gpu.py -x -q -k "$SEL" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/memcheck.log; grep -c "Invalid\|ERROR SUMMARY" $OUT/memcheck.log; tail -3 $OUT/memcheck.log
+      timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_cnuity_gpu.py -x -q -k "cnuity_device_matches_oracle" > $OUT/racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/racecheck.log; tail -3 $OUT/racecheck.log ;;
     tma)
       (cd tools/probe && nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe4 tma_probe4.cu -lcuda 2>/dev/null)
       for v in 0 1 2 3 4; do timeout 60 tools/probe/tma_probe4 $v; echo "exit=$?"; done > $OUT/tma_probe4.txt 2>&1; cat $OUT/tma_probe4.txt ;;
