@@ -844,8 +844,9 @@ int run_march(hycom_tsadvc_handle* h, int32_t m, int32_t n, const hycom_tsadvc_p
   const char* cs = getenv("HYCOM_TSADVC_SPLIT");
   if ((aadv == 2 || aadv == 1 || aadv == 4) && !p.btrmas && !u_prolog && !(cs && atoi(cs) == 0) && !h->mask_host.empty()) {
     const hycom_tsadvc_handle::SegLists* L = nullptr;
-    // (whole-band all-sea pieces on one tile only: on the tiles of a 2x2 tiling the march is 3-4 % slower with them)
-    if ((rc = march_segments(h, P, part, chunk_rows, aadv != 1 && h->d.ipr * h->d.jpr == 1, &L))) return rc;
+    // (whole-band all-sea pieces for FCT2 / FCT4, on tiles as well: 8 x B200 on one box 2.79 ms per step with them,
+    // 2.84 with maximal runs - profiles/r03v; MPDATA keeps the maximal runs)
+    if ((rc = march_segments(h, P, part, chunk_rows, aadv != 1, &L))) return rc;
     rc = 0;
     for (int c = 1; c >= 0 && !rc; --c) {       // the general segments first: the long launch hides their tail
       if (!L->n[c]) continue;
