@@ -15,8 +15,9 @@
 // off the iu / iv points (geopar.F90:822-871 zeroes them there once, cnuity never writes them).
 //   k_thk_*      :745-1124 interface-depth diffusion, biharmonic (thkdf4) or Laplacian (thkdf2): three kernels per
 //                          interface, behind their own exchange of dpmixl(n), dp(n), p
-// Scope: .not.btrmas, no open-boundary faces, no Stokes drift, not (hybrid .and. mxlkta), not (synflt .and.
-// wvelfl) - everything else is refused by the caller (tsadvc_abi.cu).
+//   k_mxl_*      :1144-1324 hybrid .and. mxlkta: vertical advection and thickness diffusion of dpmixl
+// Scope: .not.btrmas, no open-boundary faces, no Stokes drift, not (synflt .and. wvelfl) - everything else is
+// refused by the caller (tsadvc_abi.cu).
 // Measured at GLBb0.08 (profiles/r02x-z): ten streaming sweeps over all layers (the first version, 64
 // passes over a 3-D field through nine scratch fields) 66 ms; the tile kernel with its operands loaded
 // where they are used 60 ms (47 % of the warps' time waiting for them); operands of layer k+1 requested
@@ -471,6 +472,69 @@ __global__ void __launch_bounds__(256) k_thk_final(const CnuityParams P) {
   }
 }
 
+
+// =====================================================================================================
+// hybrid .and. mxlkta (:1144-1324): dpmixl(:,:,n) follows the vertical excursion of the coordinates immediately
+// above and below the mixed-layer base (found in the OLD thicknesses), then is diffused like an interface.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_mxl_vert(const CnuityParams P) {
+  CN_CELL;
+  if (!inside || !in_margin(P, c, r, 4) || !(P.mask[q] & M_IP)) return;
+  const double onemm = 9806.0 * 0.001;   // mod_cb_arrays.F90:851
+  double above = 0., below = 0., mx = P.dpmixl_n[q];
+  for (int k = 0; k < P.kk; ++k) {
+    const long qk = q + (long)k * P.slab;
+    const double dpok = P.dpo_n[qk];
+    above = below;
+    below = below + dpok;
+    if (below >= mx && above < mx) {
+      const double dpup = P.p[qk] - above;
+      const double dpdn = P.p[qk + P.slab] - below;
+      const double qq = (below - mx) / cmax(onemm, dpok);
+      mx = mx + (dpdn + qq * (dpup - dpdn));
+    }
+  }
+  P.dpmixl_n[q] = mx;
+}
+
+// biharmonic: util1, util2 of dpmixl, margin 2 (:1206-1225)
+__global__ void __launch_bounds__(256) k_mxl_util(const CnuityParams P) {
+  CN_CELL;
+  if (!inside) return;
+  const unsigned mk = P.mask[q];
+  double u1 = 0.0, u2 = 0.0;
+  if (in_margin(P, c, r, 2) && (mk & M_IP)) {
+    const double* d = P.dpmixl_n;
+    const long ia = (mk & M_PW) ? q - 1 : ((mk & M_PE) ? q + 1 : q);
+    const long ib = (mk & M_PE) ? q + 1 : ((mk & M_PW) ? q - 1 : q);
+    const long ja = (mk & M_PS) ? q - P.pitch : ((mk & M_PN) ? q + P.pitch : q);
+    const long jb = (mk & M_PN) ? q + P.pitch : ((mk & M_PS) ? q - P.pitch : q);
+    u1 = d[q] - 0.5 * (d[ia] + d[ib]);
+    u2 = d[q] - 0.5 * (d[ja] + d[jb]);
+  }
+  P.t1[q] = u1; P.t2[q] = u2;
+}
+
+// fluxes at the u and v points: biharmonic from util1, util2 (margin 1, :1227-1243), Laplacian from dpmixl
+// (margin 2, :1285-1301); zero everywhere else (:1190-1203)
+template <bool BIH>
+__global__ void __launch_bounds__(256) k_mxl_flux(const CnuityParams P) {
+  CN_CELL;
+  if (!inside) return;
+  const unsigned mk = P.mask[q];
+  const bool in = in_margin(P, c, r, BIH ? 1 : 2);
+  double fu = 0.0, fv = 0.0;
+  if (in && (mk & M_IU)) fu = (P.delt1 * P.thku[q]) * (BIH ? P.t1[q - 1] - P.t1[q] : P.dpmixl_n[q - 1] - P.dpmixl_n[q]);
+  if (in && (mk & M_IV)) fv = (P.delt1 * P.thkv[q]) * (BIH ? P.t2[q - P.pitch] - P.t2[q] : P.dpmixl_n[q - P.pitch] - P.dpmixl_n[q]);
+  P.fu[q] = fu; P.fv[q] = fv;
+}
+
+__global__ void __launch_bounds__(256) k_mxl_update(const CnuityParams P) {   // margin 0 (:1245-1262, :1303-1320)
+  CN_CELL;
+  if (!inside || !(P.mask[q] & M_OUT)) return;
+  P.dpmixl_n[q] = P.dpmixl_n[q] - ((P.fu[q + 1] - P.fu[q]) + (P.fv[q + P.pitch] - P.fv[q])) * P.scp2i[q];
+}
+
 }  // namespace
 
 // stage 0: everything up to the exchange of dp(:,:,:,n) (:1400); stage 1: the Robert-Asselin filter
@@ -513,6 +577,21 @@ int launch_cnuity_thkdf(const CnuityParams& P, int bih, int nstep, cudaStream_t 
     k_thk_cell<<<g2, block, 0, st>>>(P, k); ++n;
   }
   k_thk_final<<<g2, block, 0, st>>>(P); ++n;
+  return cudaGetLastError() == cudaSuccess ? n : -1;
+}
+
+// mode: 0 no diffusion of dpmixl (thkdf2 = thkdf4 = 0), 1 biharmonic, 2 Laplacian; returns launches (< 0: error)
+int launch_cnuity_mxlkta(const CnuityParams& P, int mode, cudaStream_t st) {
+  const dim3 block(32, 8), g2((P.pitch + 31) / 32, (P.nrows + 7) / 8);
+  int n = 0;
+  k_mxl_vert<<<g2, block, 0, st>>>(P); ++n;
+  if (mode == 1) {
+    k_mxl_util<<<g2, block, 0, st>>>(P); ++n;
+    k_mxl_flux<true><<<g2, block, 0, st>>>(P); ++n;
+  } else if (mode == 2) {
+    k_mxl_flux<false><<<g2, block, 0, st>>>(P); ++n;
+  }
+  if (mode) { k_mxl_update<<<g2, block, 0, st>>>(P); ++n; }
   return cudaGetLastError() == cudaSuccess ? n : -1;
 }
 

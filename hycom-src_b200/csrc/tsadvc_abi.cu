@@ -1811,8 +1811,6 @@ int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, con
   const bool thk = prm->thkdf2 != 0.0 || prm->thkdf4 != 0.0;
   if (thk && (!h->thkdf4u.lev[0] || !h->thkdf4v.lev[0]))
     return fail(h, HYCOM_TSADVC_EINVAL, "cnuity with thkdf2/thkdf4 reads thkdf4u, thkdf4v: upload HYCOM_F_THKDF4U/_THKDF4V first");
-  if (prm->hybrid && prm->mxlkta)
-    return fail(h, HYCOM_TSADVC_EUNSUPPORTED, "cnuity: vertical advection of dpmixl (hybrid & mxlkta, :1148-1324) is not built");
   if (!h->scuy || !h->scvx) return fail(h, HYCOM_TSADVC_EINVAL, "cnuity needs scuy, scvx (set_static)");
   CU(h, cudaSetDevice(h->d.device));
   const int kk = h->d.kdm;
@@ -1895,6 +1893,11 @@ int hycom_tsadvc_cnuity_device(hycom_tsadvc_handle* h, int32_t m, int32_t n, con
     }
     const int nl = launch_cnuity_thkdf(P, prm->thkdf4 != 0.0, prm->nstep, h->stream);
     if (nl < 0) return fail(h, HYCOM_TSADVC_ECUDA, "cnuity thickness-diffusion launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->launches += nl;
+  }
+  if (prm->hybrid && prm->mxlkta) {   // :1144-1324 dpmixl follows the coordinates around its base, then diffuses
+    const int nl = launch_cnuity_mxlkta(P, prm->thkdf4 != 0.0 ? 1 : prm->thkdf2 != 0.0 ? 2 : 0, h->stream);
+    if (nl < 0) return fail(h, HYCOM_TSADVC_ECUDA, "cnuity dpmixl launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->launches += nl;
   }
   // :1400 xctilr(dp(:,:,:,n), 1,kk, 6,6, halo_ps), then the Robert-Asselin filter

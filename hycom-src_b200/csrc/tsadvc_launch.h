@@ -240,5 +240,7 @@ struct CnuityParams {
 int launch_cnuity(int stage, const CnuityParams& P, cudaStream_t stream);
 // the interface-depth diffusion behind its three exchanges; bih: thkdf4, else thkdf2; returns launches (< 0: error)
 int launch_cnuity_thkdf(const CnuityParams& P, int bih, int nstep, cudaStream_t stream);
+// hybrid .and. mxlkta (:1144-1324); mode 0: dpmixl is only advected, 1: + biharmonic, 2: + Laplacian diffusion
+int launch_cnuity_mxlkta(const CnuityParams& P, int mode, cudaStream_t stream);
 
 }  // namespace tsadvc

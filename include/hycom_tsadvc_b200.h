@@ -360,8 +360,9 @@ int hycom_tsadvc_asselin_filter_device(hycom_tsadvc_handle *h, int32_t m, int32_
  * (:471, :679) of this tile when mod(nstep,3) == 0, as the reference evaluates them.
  * thkdf4 != 0 (biharmonic) or thkdf2 != 0 (Laplacian) applies the interface-depth diffusion of :745-1124 with the
  * coefficients in the mirrors HYCOM_F_THKDF4U / _THKDF4V (uploaded once, valid halos) and its three xctilr calls.
- * Scope: .not.btrmas, no open-boundary faces, no Stokes drift, not (hybrid .and. mxlkta), not (synflt .and.
- * wvelfl): anything else returns EUNSUPPORTED. */
+ * hybrid .and. mxlkta (Kraus-Turner mixed layer) advects and diffuses dpmixl(:,:,n) as :1144-1324 do.
+ * Scope: .not.btrmas, no open-boundary faces, no Stokes drift, not (synflt .and. wvelfl): anything else returns
+ * EUNSUPPORTED. */
 typedef struct hycom_cnuity_params {
   int32_t btrmas, isopyc, hybrid, mxlkta, nstep, pad;
   double delt1, ra2fac, thkdf2, thkdf4;

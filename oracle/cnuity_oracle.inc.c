@@ -4,7 +4,7 @@
  * CPU restatement of HYCOM's continuity equation cnuity(m,n) (cnuity.F90), the producer of the
  * dp(:,:,:,n), uflx, vflx that tsadvc(m,n) consumes, sweep by sweep with
  * the Fortran loop ranges and operation order.  Scope (everything else is refused with an error):
- *   .not.btrmas, no open-boundary faces (iuopn = ivopn = 0, :170-229, :327-358), no STOKES drift, not (hybrid .and. mxlkta) (:1148-1324),
+ *   .not.btrmas, no open-boundary faces (iuopn = ivopn = 0, :170-229, :327-358), no STOKES drift,
  *   not (synflt .and. wvelfl) (:1128-1142).
  * PARITY UNPINNED like the rest of the oracle (no Fortran compiler in this image); a second, independent
  * restatement in numpy (oracle/np_restatement.py: cnuity) must agree with it bit for bit.
@@ -406,6 +406,83 @@ int orc_cnuity(orc_tile *t, int m, int n, int do_halo) {
             dpn[c + P * (size_t)(k - 1)] = *pbk - *pa;
             if (t->isopyc && k == 1) t->dpmixl[c + P * (size_t)(n - 1)] = dpn[c];
           }
+  }
+
+  /* :1144-1324 vertical advection of dpmixl: the excursions of the coordinates immediately above and below the
+   * mixed-layer base, interpolated to dpmixl; then thickness diffusion of the mixed layer */
+  if (t->hybrid && t->mxlkta) {
+    double *dpmx = t->dpmixl + P * (size_t)(n - 1);
+    const double *thku = t->thkdf4u, *thkv = t->thkdf4v;
+    mbdy = 6;
+    margin = mbdy - 2;
+    OMP_J
+    for (int j = 1 - margin; j <= jj + margin; j++) {
+      for (int i = 1 - margin; i <= ii + margin; i++)
+        if (SEA_P) { util1[IX(i, j)] = 0.; util2[IX(i, j)] = 0.; }
+      for (int k = 1; k <= kk; k++)
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_P) {
+            const size_t c = IX(i, j);
+            const double dpok = dpon[c + P * (size_t)(k - 1)];
+            util1[c] = util2[c];
+            util2[c] = util2[c] + dpok;
+            if (util2[c] >= dpmx[c] && util1[c] < dpmx[c]) {
+              const double dpup = t->p[c + P * (size_t)(k - 1)] - util1[c];
+              const double dpdn = t->p[c + P * (size_t)k] - util2[c];
+              const double q = (util2[c] - dpmx[c]) / MAX2(t->onemm, dpok);
+              dpmx[c] = dpmx[c] + (dpdn + q * (dpup - dpdn));
+            }
+          }
+    }
+    if (t->thkdf4 != 0. || t->thkdf2 != 0.) {
+      const int bih = t->thkdf4 != 0.;
+      margin = mbdy - 3;
+      for (int j = 1 - margin; j <= jj + margin; j++)
+        for (int i = 1 - margin; i <= ii + margin; i++) {
+          if (SEA_U) uflux[IX(i, j)] = 0.;
+          if (SEA_V) vflux[IX(i, j)] = 0.;
+        }
+      if (bih) {   /* :1206-1243 */
+        margin = mbdy - 4;
+        OMP_J
+        for (int j = 1 - margin; j <= jj + margin; j++)
+          for (int i = 1 - margin; i <= ii + margin; i++)
+            if (SEA_P) {
+              const size_t c = IX(i, j);
+              const int ia = ip[IX(i - 1, j)] != 0 ? i - 1 : (ip[IX(i + 1, j)] != 0 ? i + 1 : i);
+              const int ib = ip[IX(i + 1, j)] != 0 ? i + 1 : (ip[IX(i - 1, j)] != 0 ? i - 1 : i);
+              const int ja = ip[IX(i, j - 1)] != 0 ? j - 1 : (ip[IX(i, j + 1)] != 0 ? j + 1 : j);
+              const int jb = ip[IX(i, j + 1)] != 0 ? j + 1 : (ip[IX(i, j - 1)] != 0 ? j - 1 : j);
+              util1[c] = dpmx[c] - 0.5 * (dpmx[IX(ia, j)] + dpmx[IX(ib, j)]);
+              util2[c] = dpmx[c] - 0.5 * (dpmx[IX(i, ja)] + dpmx[IX(i, jb)]);
+            }
+        margin = mbdy - 5;
+        OMP_J
+        for (int j = 1 - margin; j <= jj + margin; j++)
+          for (int i = 1 - margin; i <= ii + margin; i++) {
+            const size_t c = IX(i, j);
+            if (SEA_U) uflux[c] = (delt1 * thku[c]) * (util1[IX(i - 1, j)] - util1[c]);
+            if (SEA_V) vflux[c] = (delt1 * thkv[c]) * (util2[IX(i, j - 1)] - util2[c]);
+          }
+      } else {     /* :1285-1301 */
+        margin = mbdy - 4;
+        OMP_J
+        for (int j = 1 - margin; j <= jj + margin; j++)
+          for (int i = 1 - margin; i <= ii + margin; i++) {
+            const size_t c = IX(i, j);
+            if (SEA_U) uflux[c] = (delt1 * thku[c]) * (dpmx[IX(i - 1, j)] - dpmx[c]);
+            if (SEA_V) vflux[c] = (delt1 * thkv[c]) * (dpmx[IX(i, j - 1)] - dpmx[c]);
+          }
+      }
+      margin = mbdy - 6;
+      OMP_J
+      for (int j = 1 - margin; j <= jj + margin; j++)
+        for (int i = 1 - margin; i <= ii + margin; i++)
+          if (SEA_P) {
+            const size_t c = IX(i, j);
+            dpmx[c] = dpmx[c] - ((uflux[IX(i + 1, j)] - uflux[c]) + (vflux[IX(i, j + 1)] - vflux[c])) * t->scp2i[c];
+          }
+    }
   }
 
   /* :1326-1350 cumulative fluxes */

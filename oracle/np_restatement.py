@@ -653,14 +653,15 @@ def asselin_filter(cb, m, n):
 EPSIL = 1.0e-11   # mod_cb_arrays.F90:853
 
 
-def cnuity(geom, st, m, n, ip, iu, iv, scuy, scvx, scp2i, depthu, depthv, pbot, delt1, ra2fac, isopyc=False, thk=None):
+def cnuity(geom, st, m, n, ip, iu, iv, scuy, scvx, scp2i, depthu, depthv, pbot, delt1, ra2fac, isopyc=False, thk=None,
+           mxlkta=None):
     """st: dict of arrays in the Fortran layout with halos valid to width 6 (the caller did the xctilr of
     cnuity.F90:100-107): dp, dpo (2,kk,..), u, v, dpu, dpv (2,kk,..), ubavg, vbavg (3,..), dpmixl (2,..),
     uflx, vflx, uflxav, vflxav, dpav (kk,..).  Updated in place; returns p (kk+1,..), utotn, vtotn, dpkmin.
     The halo refresh of dp(:,:,:,n) before the Robert-Asselin filter (:1400) is the caller's.
     thk: interface-depth diffusion (:745-1124), a dict with thkdf4u, thkdf4v (the coefficients at the u and v
     points), bih (True: biharmonic, thkdf4; False: Laplacian, thkdf2), nstep, scp2 and halo(a, itype), the
-    xctilr of width 6 of :761-763."""
+    xctilr of width 6 of :761-763.  mxlkta: hybrid .and. mxlkta (:1144-1324), a dict with onemm."""
     kk = geom.kdm
     dp, dpo = st["dp"], st["dpo"]
     n_, m_ = n - 1, m - 1
@@ -754,12 +755,72 @@ def cnuity(geom, st, m, n, ip, iu, iv, scuy, scvx, scp2i, depthu, depthv, pbot, 
         if thk is not None:
             cnuity_thkdf(geom, st, p, n, ip, iu, iv, thk["scp2"], scp2i, delt1, thk["thkdf4u"], thk["thkdf4v"],
                          thk["bih"], thk["nstep"], isopyc, thk["halo"])
+        if mxlkta is not None:
+            cnuity_mxlkta(geom, st, p, n, ip, iu, iv, scp2i, delt1, mxlkta["onemm"],
+                          thk["thkdf4u"] if thk else None, thk["thkdf4v"] if thk else None, thk["bih"] if thk else True)
         # cumulative fluxes (:1326-1350)
         for k in range(kk):
             st["uflxav"][k] = np.where(sea_u & inner, st["uflxav"][k] + st["uflx"][k], st["uflxav"][k])
             st["vflxav"][k] = np.where(sea_v & inner, st["vflxav"][k] + st["vflx"][k], st["vflxav"][k])
             st["dpav"][k] = np.where(r0, st["dpav"][k] + dp[n_][k], st["dpav"][k])
     return p, utotn, vtotn, dpkmin, dpmold
+
+
+def _extended_neighbours(ip):
+    """array -> array at ipim1x / ipip1x / ipjm1x / ipjp1x (bigrid.F90:343-372): i-1 if sea; else i+1 if sea;
+    otherwise i - and likewise for the other three"""
+    w_sea, e_sea = _sh(ip, -1, 0) != 0, _sh(ip, 1, 0) != 0
+    s_sea, n_sea = _sh(ip, 0, -1) != 0, _sh(ip, 0, 1) != 0
+
+    def xa(a):
+        return np.where(w_sea, _sh(a, -1, 0), np.where(e_sea, _sh(a, 1, 0), a))
+
+    def xb(a):
+        return np.where(e_sea, _sh(a, 1, 0), np.where(w_sea, _sh(a, -1, 0), a))
+
+    def ya(a):
+        return np.where(s_sea, _sh(a, 0, -1), np.where(n_sea, _sh(a, 0, 1), a))
+
+    def yb(a):
+        return np.where(n_sea, _sh(a, 0, 1), np.where(s_sea, _sh(a, 0, -1), a))
+    return xa, xb, ya, yb
+
+
+def cnuity_mxlkta(geom, st, p, n, ip, iu, iv, scp2i, delt1, onemm, thku=None, thkv=None, bih=True):
+    """hybrid .and. mxlkta (cnuity.F90:1144-1324): dpmixl(:,:,n) follows the vertical excursion of the coordinates
+    immediately above and below the mixed-layer base (found in the OLD thicknesses dpo(:,:,:,n)), then is
+    diffused like an interface (biharmonic with thkdf4, Laplacian with thkdf2; thku None: no diffusion)"""
+    kk = geom.kdm
+    n_ = n - 1
+    dpo = st["dpo"][n_]
+    dpmx = st["dpmixl"][n_]
+    sea_p, sea_u, sea_v = ip != 0, iu != 0, iv != 0
+    r4 = sea_p & _region(geom, 4)
+    shape = (geom.nrows, geom.ncols)
+    above, below = np.zeros(shape), np.zeros(shape)
+    with np.errstate(all="ignore"):
+        for k in range(kk):
+            above = below
+            below = below + dpo[k]
+            base_here = r4 & (below >= dpmx) & (above < dpmx)
+            dpup = p[k] - above
+            dpdn = p[k + 1] - below
+            q = (below - dpmx) / np.maximum(onemm, dpo[k])
+            dpmx = np.where(base_here, dpmx + (dpdn + q * (dpup - dpdn)), dpmx)
+        if thku is not None:
+            if bih:
+                xa, xb, ya, yb = _extended_neighbours(ip)
+                cell2 = sea_p & _region(geom, 2)
+                t1 = np.where(cell2, dpmx - 0.5 * (xa(dpmx) + xb(dpmx)), 0.0)
+                t2 = np.where(cell2, dpmx - 0.5 * (ya(dpmx) + yb(dpmx)), 0.0)
+                fu = np.where(sea_u & _region(geom, 1), (delt1 * thku) * (_sh(t1, -1, 0) - t1), 0.0)
+                fv = np.where(sea_v & _region(geom, 1), (delt1 * thkv) * (_sh(t2, 0, -1) - t2), 0.0)
+            else:
+                fu = np.where(sea_u & _region(geom, 2), (delt1 * thku) * (_sh(dpmx, -1, 0) - dpmx), 0.0)
+                fv = np.where(sea_v & _region(geom, 2), (delt1 * thkv) * (_sh(dpmx, 0, -1) - dpmx), 0.0)
+            cell0 = sea_p & _region(geom, 0)
+            dpmx = np.where(cell0, dpmx - ((_sh(fu, 1, 0) - fu) + (_sh(fv, 0, 1) - fv)) * scp2i, dpmx)
+    st["dpmixl"][n_] = dpmx
 
 
 def cnuity_thkdf(geom, st, p, n, ip, iu, iv, scp2, scp2i, delt1, thku, thkv, bih, nstep, isopyc, halo):
@@ -781,20 +842,7 @@ def cnuity_thkdf(geom, st, p, n, ip, iu, iv, scp2, scp2i, delt1, thku, thkv, bih
     shape = (geom.nrows, geom.ncols)
     uflux, vflux = np.zeros(shape), np.zeros(shape)
     pold = p[kk].copy() if iflip == 1 else np.zeros(shape)
-    w_sea, e_sea = _sh(ip, -1, 0) != 0, _sh(ip, 1, 0) != 0
-    s_sea, n_sea = _sh(ip, 0, -1) != 0, _sh(ip, 0, 1) != 0
-
-    def xa(a):   # at ipim1x: i-1 if sea; else i+1 if sea; otherwise i (bigrid.F90:343-372)
-        return np.where(w_sea, _sh(a, -1, 0), np.where(e_sea, _sh(a, 1, 0), a))
-
-    def xb(a):
-        return np.where(e_sea, _sh(a, 1, 0), np.where(w_sea, _sh(a, -1, 0), a))
-
-    def ya(a):
-        return np.where(s_sea, _sh(a, 0, -1), np.where(n_sea, _sh(a, 0, 1), a))
-
-    def yb(a):
-        return np.where(n_sea, _sh(a, 0, 1), np.where(s_sea, _sh(a, 0, -1), a))
+    xa, xb, ya, yb = _extended_neighbours(ip)
 
     order = range(2, kk + 1) if (not bih or iflip == 0) else range(kk, 1, -1)
     u1, u2 = np.zeros(shape), np.zeros(shape)

@@ -117,7 +117,7 @@ orc_tile *orc_tile_create(int idm, int jdm, int kdm, int nbdy, int ii, int jj,
   t->fldan = alloc_r(P);
   t->xmin = alloc_r(K); t->xmax = alloc_r(K);
   /* blkdat defaults of the benchmark configuration */
-  t->advtyp = 2; t->advflg = 0; t->btrmas = 0; t->nhybrd = kdm; t->hybrid = 1;
+  t->advtyp = 2; t->advflg = 0; t->btrmas = 0; t->nhybrd = kdm; t->hybrid = 1; t->mxlkta = 0;
   t->isopyc = 0; t->mxlmy = 0; t->nstep = 1; t->diagno = 0;
   t->delt1 = 480.0; t->temdf2 = 0.0; t->temdfc = 1.0; t->thbase = 34.0;
   t->onemm = 9806.0 * 0.001; /* mod_cb_arrays.F90:842-857 */
@@ -170,14 +170,14 @@ int *orc_i32(orc_tile *t, const char *name) {
 
 int orc_set_i(orc_tile *t, const char *name, int v) {
 #define S(n) if (!strcmp(name, #n)) { t->n = v; return 0; }
-  S(advtyp) S(advflg) S(btrmas) S(nhybrd) S(hybrid) S(isopyc) S(mxlmy) S(ntracr)
+  S(advtyp) S(advflg) S(btrmas) S(nhybrd) S(hybrid) S(isopyc) S(mxlmy) S(ntracr) S(mxlkta)
   S(nstep) S(diagno) S(nreg) S(nthreads) S(kk) S(sigver)
 #undef S
   return 1;
 }
 int orc_get_i(const orc_tile *t, const char *name) {
 #define G(n) if (!strcmp(name, #n)) return t->n;
-  G(advtyp) G(advflg) G(btrmas) G(nhybrd) G(hybrid) G(isopyc) G(mxlmy) G(ntracr)
+  G(advtyp) G(advflg) G(btrmas) G(nhybrd) G(hybrid) G(isopyc) G(mxlmy) G(ntracr) G(mxlkta)
   G(nstep) G(diagno) G(nreg) G(nthreads) G(kk) G(ms) G(xminmax_valid) G(sigver)
   G(idm) G(jdm) G(kdm) G(nbdy) G(ii) G(jj) G(i0) G(j0) G(itdm) G(jtdm)
 #undef G

@@ -57,6 +57,7 @@ typedef struct orc_tile {
   double *oneta, *onetamas;          /* (P,2) */
   double *uflux, *vflux, *uflux2, *vflux2, *util1, *util2; /* (P) */
   /* run-time scalars (blkdat) */
+  int mxlkta;   /* Kraus-Turner mixed layer: cnuity advects and diffuses dpmixl (cnuity.F90:1148-1324) */
   int advtyp, advflg, btrmas, nhybrd, hybrid, isopyc, mxlmy, ntracr, nstep,
       diagno;
   int trcflg[ORC_MXTRCR];

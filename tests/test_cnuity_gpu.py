@@ -10,7 +10,7 @@ from util import pkg, syn, cabi
 pytestmark = pytest.mark.gpu
 
 
-def _check(ts, g, cb, ref, m, n, kdm, g1=None, isopyc=False):
+def _check(ts, g, cb, ref, m, n, kdm, g1=None, isopyc=False, dpmixl=False):
     """device mirrors of one tile against the (single-tile) oracle result"""
     nb = g.nbdy
     g1 = g1 or g
@@ -40,7 +40,7 @@ def _check(ts, g, cb, ref, m, n, kdm, g1=None, isopyc=False):
     assert np.array_equal(ts.download(cabi.F_VTOTN, 1)[0][iv_in], W(ref["vtotn"])[iv_in])
     assert np.array_equal(ts.download(cabi.F_DPAV, 1)[0][inner], W(ref["dpav"][0])[inner])
     assert np.array_equal(ts.download(cabi.F_UFLXAV, 1)[kdm - 1][iu_in], W(ref["uflxav"][kdm - 1])[iu_in])
-    if isopyc:
+    if isopyc or dpmixl:
         assert np.array_equal(ts.download(cabi.F_DPMIXL, n)[0][inner], W(ref["dpmixl"][n - 1])[inner])
 
 
@@ -70,9 +70,6 @@ def test_cnuity_refuses_what_is_not_built():
     st = util.add_cnuity(cfg, sea, g, cb, 1, 2)
     ts = pkg.Tsadvc(cb)
     ts.upload_cnuity_state(st, 1, 2)
-    with pytest.raises(cabi.TsadvcError) as e:
-        ts.cnuity_device(1, 2, mxlkta=True)
-    assert e.value.code == cabi.EUNSUPPORTED
     # the interface-depth diffusion needs its coefficients, and only one of thkdf2 / thkdf4 (cnuity.F90:758)
     for kw in (dict(thkdf4=0.01), dict(thkdf2=0.01), dict(thkdf2=0.01, thkdf4=0.01)):
         with pytest.raises(cabi.TsadvcError) as e:
@@ -151,4 +148,50 @@ def test_cnuity_thickness_diffusion_on_tiles(oracle, ipr, jpr, nreg, bih, nstep)
     run_tiles(tss, go)
     for ts, cb in zip(tss, cbs):
         _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1)
+    close_tiles(grp, tss)
+
+
+# hybrid .and. mxlkta (cnuity.F90:1144-1324): dpmixl follows the coordinates around the mixed-layer base and is
+# diffused like an interface
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,mode,nstep", [
+    (150, 150, 6, 0, "bih", 4),
+    (64, 90, 4, 1, "lap", 3),
+    (131, 77, 4, 3, None, 2),
+])
+def test_cnuity_mxlkta_matches_oracle(oracle, itdm, jtdm, kdm, nreg, mode, nstep):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=31, m=m, n=n, nstep=nstep)
+    thk = {"bih": 0.01, "lap": 0.02, None: 0.0}[mode]
+    st = util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=thk, bih=mode != "lap")
+    util.deepen_dpmixl(st, n)
+    ref = util.run_oracle_cnuity(oracle, cb, sea, st, m, n, mxlkta=True)
+    plain = util.run_oracle_cnuity(oracle, cb, sea, st, m, n, mxlkta=False)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_cnuity_state(st, m, n)
+    kw = {"bih": {"thkdf4": thk}, "lap": {"thkdf2": thk}, None: {}}[mode]
+    ts.cnuity_device(m, n, mxlkta=True, **kw)
+    _check(ts, g, cb, ref, m, n, kdm, dpmixl=True)
+    inner = util.interior_sea(cb)
+    assert not np.array_equal(ts.download(cabi.F_DPMIXL, n)[0][inner], plain["dpmixl"][n - 1][inner])
+    ts.close()
+
+
+def test_cnuity_mxlkta_on_tiles(oracle):
+    from test_comm_gpu import make_tiles, run_tiles, close_tiles
+    m, n = 1, 2
+    itdm, jtdm, kdm, ipr, jpr, nreg, nstep = 160, 120, 4, 2, 2, 0, 5
+    cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=23, m=m, n=n, nstep=nstep)
+    st1 = util.deepen_dpmixl(util.add_cnuity(cfg, sea, g1, cb1, m, n, thkdf=0.01, bih=True), n)
+    ref = util.run_oracle_cnuity(oracle, cb1, sea, st1, m, n, mxlkta=True)
+    cbs = [syn.build_cb_arrays(cfg, g, sea, m, n, nstep=nstep) for g in pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)]
+    sts = [util.deepen_dpmixl(util.add_cnuity(cfg, sea, cb.geom, cb, m, n, uscale=st1["_uscale"], thkdf=0.01, bih=True), n)
+           for cb in cbs]
+    grp, tss = make_tiles(cfg, sea, itdm, jtdm, kdm, ipr, jpr, nreg, m, n, cbs=cbs)
+
+    def go(ts, r):
+        ts.upload_cnuity_state(sts[r], m, n)
+        ts.cnuity_device(m, n, thkdf4=0.01, mxlkta=True)
+    run_tiles(tss, go)
+    for ts, cb in zip(tss, cbs):
+        _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1, dpmixl=True)
     close_tiles(grp, tss)

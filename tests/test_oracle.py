@@ -664,7 +664,7 @@ def test_reference_case_io_roundtrip(oracle, tmp_path):
 # ---------------------------------------------------------------------------------------
 # cnuity(m,n) (cnuity.F90): C restatement == numpy restatement
 # ---------------------------------------------------------------------------------------
-def _np_cnuity(cb, g, st, m, n, ra2fac=0.125, isopyc=False):
+def _np_cnuity(cb, g, st, m, n, ra2fac=0.125, isopyc=False, mxlkta=False):
     """the numpy path with the single-tile xctilr calls of cnuity.F90:100-107 and :1400"""
     thkdf = st.get("_thkdf")
     st = {k: v.copy() for k, v in st.items() if not k.startswith("_")}
@@ -682,7 +682,8 @@ def _np_cnuity(cb, g, st, m, n, ra2fac=0.125, isopyc=False):
     if "thkdf4u" in st:
         thk = dict(thkdf4u=st["thkdf4u"], thkdf4v=st["thkdf4v"], bih=thkdf[1], nstep=cb.nstep, scp2=cb.scp2, halo=H)
     p, utotn, vtotn, dpkmin, dpmold = npr.cnuity(g, st, m, n, cb.ip, cb.iu, cb.iv, cb.scuy, cb.scvx, cb.scp2i,
-                                                 st["depthu"], st["depthv"], st["pbot"], cb.delt1, ra2fac, isopyc, thk)
+                                                 st["depthu"], st["depthv"], st["pbot"], cb.delt1, ra2fac, isopyc, thk,
+                                                 dict(onemm=cb.onemm) if mxlkta else None)
     st["dp"][n - 1] = H(st["dp"][n - 1], 1)
     npr.cnuity_asselin(g, st, m, n, cb.ip, ra2fac)
     st.update(p=p, utotn=utotn, vtotn=vtotn, dpkmin=dpkmin)
@@ -772,4 +773,33 @@ def test_cnuity_thickness_diffusion_c_oracle_equals_numpy(oracle, itdm, jtdm, kd
     assert not np.array_equal(got[1][inner], plain["dp"][n - 1, 1][inner])
     assert np.allclose(got.sum(axis=0)[inner], st["pbot"][inner], rtol=1e-12)
     assert (got[:, inner] >= 0.0).all()
+    ot.close()
+
+
+# hybrid .and. mxlkta (cnuity.F90:1144-1324): dpmixl follows the coordinates around the mixed-layer base and is
+# diffused like an interface
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,mode,nstep", [
+    (90, 70, 5, 0, "bih", 4),
+    (64, 90, 4, 1, "lap", 3),
+    (131, 77, 4, 3, None, 2),
+])
+def test_cnuity_mxlkta_c_oracle_equals_numpy(oracle, itdm, jtdm, kdm, nreg, mode, nstep):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=31, m=m, n=n, nstep=nstep)
+    st = util.add_cnuity(cfg, sea, g, cb, m, n, thkdf={"bih": 0.01, "lap": 0.02, None: 0.0}[mode], bih=mode != "lap")
+    util.deepen_dpmixl(st, n)
+    want = _np_cnuity(cb, g, st, m, n, mxlkta=True)
+    plain = _np_cnuity(cb, g, st, m, n, mxlkta=False)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    util.oracle_load_cnuity(ot, st)
+    ot.set_i("mxlkta", 1)
+    ot.cnuity(m, n, 1)
+    inner = util.interior_sea(cb)
+    got = ot.f64("dpmixl")[n - 1]
+    assert np.array_equal(got[inner], want["dpmixl"][n - 1][inner])
+    assert not np.array_equal(got[inner], plain["dpmixl"][n - 1][inner])
+    for k in range(kdm):   # nothing else moves
+        assert np.array_equal(ot.f64("dp")[n - 1, k][inner], plain["dp"][n - 1, k][inner])
+    # the base of the mixed layer sits below layer 1 somewhere: more than one layer is exercised
+    assert (st["dpmixl"][n - 1][inner] > st["dp"][n - 1, 0][inner]).any()
     ot.close()

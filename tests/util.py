@@ -247,6 +247,16 @@ def add_cnuity(cfg, sea, g, cb, m, n, seed=91, uscale=None, thkdf=0.0, bih=True)
     return st
 
 
+def deepen_dpmixl(st, n):
+    """a mixed-layer base that wanders through the upper layers (add_cnuity keeps it inside layer 1): 30 % .. 230 %
+    of the first layer, as a function of the thickness fields (so every tiling sees the same values)"""
+    d = st["dp"]
+    for t in (0, 1):
+        frac = 0.3 + 2.0 * (np.nan_to_num(d[t][0]) % 7.0) / 7.0
+        st["dpmixl"][t] = np.where(np.isnan(st["dpmixl"][t]), np.nan, frac * np.nan_to_num(d[t][0]) + 1.0)
+    return st
+
+
 def oracle_load_cnuity(ot, st):
     ot.cnuity_alloc()
     for name in ("dp", "dpo", "u", "v", "dpu", "dpv", "ubavg", "vbavg", "dpmixl", "uflx", "vflx", "uflxav", "vflxav",
@@ -258,11 +268,12 @@ def oracle_load_cnuity(ot, st):
         ot.set_d("thkdf4" if st["_thkdf"][1] else "thkdf2", st["_thkdf"][0])
 
 
-def run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=False):
+def run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=False, mxlkta=False):
     """CPU oracle cnuity(m,n) on a private copy; returns the arrays it updates"""
     ot = oracle_tile_from_cb(oracle, cb, sea)
     oracle_load_cnuity(ot, st)
     ot.set_i("isopyc", int(isopyc))
+    ot.set_i("mxlkta", int(mxlkta))
     ot.cnuity(m, n, 1)
     out = {k: ot.f64(k).copy() for k in ("dp", "dpo", "uflx", "vflx", "p", "utotn", "vtotn", "dpkmin", "dpmixl",
                                          "uflxav", "vflxav", "dpav", "dpmold")}
