@@ -652,7 +652,8 @@ static int march_segments(hycom_tsadvc_handle* h, const MarchParams& P, int part
   // default of FCT2/FCT4: 27 % instead of 76 % of the rows then take the mask-free body, +0.8 % time; MPDATA, whose
   // mask-free body saves more, keeps the maximal runs: 90.2 against 94.7 ms with 8 tracers); one general launch 47.5
   const char* cbnd = getenv("HYCOM_TSADVC_SEG_BAND");
-  int band = std::max(48, std::min(cbnd ? atoi(cbnd) : (whole ? 252 : 256), chunk_rows));
+  // (maximal runs - MPDATA - are cut chunk-long: 90.9 ms with 8 tracers against 92.6 at 256-row bands, profiles/r03y)
+  int band = std::max(48, std::min(cbnd ? atoi(cbnd) : (whole ? 252 : chunk_rows), chunk_rows));
   if (whole) band = band / 6 * 6;
   std::vector<MarchSeg> seg[2];
   std::vector<char> good(nrows + 8), taken(nrows);
