@@ -51,7 +51,7 @@ def oracle():
     """the CPU oracle (test infrastructure)"""
     odir = os.path.join(ROOT, "oracle")
     lib = os.path.join(odir, "_build", "liboracle.so")
-    src = [os.path.join(odir, f) for f in ("tsadvc_oracle.c", "tsadvc_oracle.h", "Makefile")]
+    src = [os.path.join(odir, f) for f in ("tsadvc_oracle.c", "cnuity_oracle.inc.c", "tsadvc_oracle.h", "Makefile")]
     if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in src):
         subprocess.run(["make", "-C", odir], check=True, capture_output=True)
     import oracle_binding

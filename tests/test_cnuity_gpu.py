@@ -195,3 +195,35 @@ def test_cnuity_mxlkta_on_tiles(oracle):
     for ts, cb in zip(tss, cbs):
         _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1, dpmixl=True)
     close_tiles(grp, tss)
+
+
+@pytest.mark.parametrize("nreg,advtyp,thk", [(0, 2, 0.01), (3, 1, 0.0)])
+def test_cnuity_then_tsadvc_device_chain_matches_oracle_chain(oracle, nreg, advtyp, thk):
+    """the producer and its consumer back to back on the device mirrors - cnuity(m,n) leaves dp(:,:,:,n), uflx, vflx
+    where tsadvc(m,n) reads them, nothing crosses PCIe in between - against the same chain in the oracle"""
+    m, n = 1, 2
+    itdm, jtdm, kdm = 150, 120, 5
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=1, seed=43, m=m, n=n, nstep=4, advtyp=advtyp)
+    st = util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=thk, bih=True)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    util.oracle_load_cnuity(ot, st)
+    ot.cnuity(m, n, 1)
+    ot.tsadvc(m, n, 1)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_state(m, n)
+    ts.upload_cnuity_state(st, m, n)
+    ts.cnuity_device(m, n, **({"thkdf4": thk} if thk else {}))
+    ts.tsadvc_device(m, n)
+    inner = util.interior_sea(cb)
+    for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+        dev = ts.download(fld, n)
+        for k in range(kdm):
+            assert np.array_equal(dev[k][inner], ot.f64(name)[n - 1, k][inner]), (name, k)
+    tr = ts.download(cabi.F_TRACER, n, ktr=1)
+    for k in range(kdm):
+        assert np.array_equal(tr[k][inner], ot.f64("tracer")[0, n - 1, k][inner]), ("tracer", k)
+    # the advection really ran on what cnuity produced: not what tsadvc gives on the uploaded fluxes
+    ot2 = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot2.tsadvc(m, n, 1)
+    assert not np.array_equal(ot2.f64("saln")[n - 1, 0][inner], ot.f64("saln")[n - 1, 0][inner])
+    ot.close(); ot2.close(); ts.close()
