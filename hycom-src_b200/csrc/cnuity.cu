@@ -361,7 +361,9 @@ __global__ void __launch_bounds__(256) k_cn_loop77(const CnuityParams P) {
 // The interfaces p(:,:,2..kk) are moved one after the other (the biharmonic form limits the flux of an
 // interface against the one of the interface before and walks downward or upward in alternate steps), so the
 // reference's three sweeps per interface stay three kernels per interface: coupling between interfaces rules
-// out the all-layers form, and the halo each sweep consumes rules out one kernel per column.
+// out the all-layers form, and the halo each sweep consumes rules out one kernel per column.  (Forming util1,
+// util2 inside the flux kernel and completing one layer of uflx, vflx per interface - two kernels, 22 instead
+// of 31 passes over a slab per interface - was measured no faster: 74.8 against 73.4 ms per call, r04a.)
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_thk_init(const CnuityParams P, int iflip) {
   CN_CELL;
