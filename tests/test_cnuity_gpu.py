@@ -227,3 +227,42 @@ def test_cnuity_then_tsadvc_device_chain_matches_oracle_chain(oracle, nreg, advt
     ot2.tsadvc(m, n, 1)
     assert not np.array_equal(ot2.f64("saln")[n - 1, 0][inner], ot.f64("saln")[n - 1, 0][inner])
     ot.close(); ot2.close(); ts.close()
+
+
+def test_cnuity_across_the_arctic_matches_oracle(oracle):
+    """nreg=2 on one tile: every xctilr of cnuity through the tripole fold with its grid type"""
+    m, n, kdm = 1, 2, 4
+    cfg, sea, g, cb = util.make_arctic_case(96, 70, kdm, seed=17, m=m, n=n, nstep=4)
+    st = util.arctic_halos_cnuity(g, util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=0.01, bih=True))
+    ref = util.run_oracle_cnuity(oracle, cb, sea, st, m, n)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_cnuity_state(st, m, n)
+    ts.cnuity_device(m, n, thkdf4=0.01)
+    _check(ts, g, cb, ref, m, n, kdm)
+    ts.close()
+
+
+def test_cnuity_across_the_arctic_on_tiles(oracle):
+    """nreg=2 on 2 x 2 tiles: the top row exchanges the fold of every cnuity operand with its twin tiles"""
+    from test_comm_gpu import make_tiles, run_tiles, close_tiles
+    from test_parity_gpu import _tile_window
+    m, n = 1, 2
+    itdm, jtdm, kdm, ipr, jpr = 128, 70, 3, 2, 2
+    cfg, sea, g1, cb1 = util.make_arctic_case(itdm, jtdm, kdm, seed=17, m=m, n=n, nstep=4)
+    st1 = util.arctic_halos_cnuity(g1, util.add_cnuity(cfg, sea, g1, cb1, m, n, thkdf=0.01, bih=True))
+    ref = util.run_oracle_cnuity(oracle, cb1, sea, st1, m, n)
+    cbs = util.make_arctic_tiles(cfg, sea, cb1, ipr, jpr, m, n, nstep=4)
+    sts = []
+    for cb in cbs:   # every operand is the tile's window of the single-tile array
+        g = cb.geom
+        sts.append({k: (np.ascontiguousarray(_tile_window(v, g1, g, 2)) if isinstance(v, np.ndarray) else v)
+                    for k, v in st1.items()})
+    grp, tss = make_tiles(cfg, sea, itdm, jtdm, kdm, ipr, jpr, 2, m, n, cbs=cbs)
+
+    def go(ts, r):
+        ts.upload_cnuity_state(sts[r], m, n)
+        ts.cnuity_device(m, n, thkdf4=0.01)
+    run_tiles(tss, go)
+    for ts, cb in zip(tss, cbs):
+        _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1)
+    close_tiles(grp, tss)

@@ -803,3 +803,31 @@ def test_cnuity_mxlkta_c_oracle_equals_numpy(oracle, itdm, jtdm, kdm, nreg, mode
     # the base of the mixed layer sits below layer 1 somewhere: more than one layer is exercised
     assert (st["dpmixl"][n - 1][inner] > st["dp"][n - 1, 0][inner]).any()
     ot.close()
+
+
+def test_cnuity_across_the_arctic_c_oracle_equals_numpy(oracle):
+    """nreg=2: every xctilr of cnuity goes through the tripole fold with its grid type (halo_ps, halo_us, halo_vs,
+    halo_uv, halo_vv: mod_xc.F90:41-44), the interface-depth diffusion included"""
+    m, n, kdm = 1, 2, 4
+    cfg, sea, g, cb = util.make_arctic_case(96, 70, kdm, seed=17, m=m, n=n, nstep=4)
+    st = util.arctic_halos_cnuity(g, util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=0.01, bih=True))
+    want = _np_cnuity(cb, g, st, m, n)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    util.oracle_load_cnuity(ot, st)
+    ot.cnuity(m, n, 1)
+    nb = g.nbdy
+    inner = util.interior_sea(cb)
+    iu_in = np.zeros_like(inner); iv_in = np.zeros_like(inner)
+    iu_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iu[nb:nb + g.jj, nb:nb + g.ii] != 0
+    iv_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iv[nb:nb + g.jj, nb:nb + g.ii] != 0
+    for k in range(kdm):
+        assert np.array_equal(ot.f64("dp")[n - 1, k][inner], want["dp"][n - 1, k][inner]), ("dp.n", k)
+        assert np.array_equal(ot.f64("dp")[m - 1, k][inner], want["dp"][m - 1, k][inner]), ("dp.m", k)
+        assert np.array_equal(ot.f64("uflx")[k][iu_in], want["uflx"][k][iu_in]), ("uflx", k)
+        assert np.array_equal(ot.f64("vflx")[k][iv_in], want["vflx"][k][iv_in]), ("vflx", k)
+        assert np.array_equal(ot.f64("p")[k + 1][inner], want["p"][k + 1][inner]), ("p", k)
+    # the top rows feel the fold: the last interior row of dp(n) differs from a run on the same data as a
+    # closed basin would give only through the halo, so just require finite, non-negative thicknesses there
+    top = ot.f64("dp")[n - 1][:, nb + g.jj - 1, nb:nb + g.ii]
+    assert np.isfinite(top).all() and (top >= 0.0).all()
+    ot.close()

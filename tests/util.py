@@ -247,6 +247,18 @@ def add_cnuity(cfg, sea, g, cb, m, n, seed=91, uscale=None, thkdf=0.0, bih=True)
     return st
 
 
+def arctic_halos_cnuity(g, st):
+    """nreg=2: the cnuity operands that must arrive with a valid halo get the tripole fold of their grid"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import np_restatement as npr
+    nb = g.nbdy
+    for name, it in (("pbot", 1), ("depthu", 3), ("depthv", 4), ("thkdf4u", 3), ("thkdf4v", 4)):
+        if name in st:
+            st[name] = np.ascontiguousarray(npr.halo_single_tile(g, st[name], nb, nb, it))
+    return st
+
+
 def deepen_dpmixl(st, n):
     """a mixed-layer base that wanders through the upper layers (add_cnuity keeps it inside layer 1): 30 % .. 230 %
     of the first layer, as a function of the thickness fields (so every tiling sees the same values)"""
