@@ -59,7 +59,7 @@ def _worker(rank, world, port, itdm, jtdm, ipr, jpr, nreg, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import np_halo
-        kk, narr = 2, 3
+        kk, narr = 2, (5 if nreg == 2 else 3)
         g = pkg.partition(itdm, jtdm, kk, ipr, jpr, nreg)[rank]
         nb = g.nbdy
         arrays = []
@@ -69,7 +69,8 @@ def _worker(rank, world, port, itdm, jtdm, ipr, jpr, nreg, q):
                 jj_, ii_ = np.meshgrid(np.arange(1, g.jj + 1), np.arange(1, g.ii + 1), indexing="ij")
                 arr[k, nb:nb + g.jj, nb:nb + g.ii] = _field(g.i0 + ii_, g.j0 + jj_, k, a)
             arrays.append(arr)
-        itypes = [1, 13, 14] if nreg == 2 else [1, 1, 1]   # halo_ps, halo_uv, halo_vv
+        # halo_ps, halo_uv, halo_vv of tsadvc; halo_us, halo_vs as cnuity exchanges dpu, dpv (cnuity.F90:102-103)
+        itypes = [1, 13, 14, 3, 4] if nreg == 2 else [1, 1, 1]
         be = np_halo.NumpyHaloBackend(g, arrays, itypes)
         ex = pkg.XcExchange(None, dist, backend=be)
         for _ in range(2):               # twice: buffers are reused
