@@ -1,0 +1,700 @@
+"""oracle/fortran_exec.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Runs subroutines of the REFERENCE'S OWN Fortran source text (HYCOM-src: mod_tsadvc.F90, bigrid.F90, ...) without
+a Fortran compiler: the structured subset of Fortran 90 those files use is translated, statement by statement,
+into Python source and executed on numpy-backed arrays that keep the Fortran bounds and index order.  Nothing
+about the algorithms is restated here - the translator only knows the language (do/if blocks, assignments,
+expressions, calls) - so what it computes is what the reference text says, in IEEE double precision without
+FMA contraction (Python floats), i.e. what a `-fdefault-real-8 -ffp-contract=off` build computes.
+
+It exists to PIN the CPU oracle (oracle/tsadvc_oracle.c): tests/test_reference_text.py executes the reference
+routines on small seeded cases and demands bit equality with the oracle; tests/golden/from_reference_text.json
+keeps digests of those runs for machines where /root/reference is absent.
+
+Supported: fixed/free form with `&` continuations, `!` comments, cpp (#if defined / #elif / #else / #endif /
+#define NAME text), do / labelled do ... continue, block and one-line if, assignment (scalars, array elements,
+whole arrays), call, return, parameter constants in declarations, intrinsics min max abs mod sign sqrt real int
+nint float dble exp log atan2 cos sin, integer division, array-element actual arguments (sequence association:
+the callee sees the array from that element on).  Not supported (raises): goto, where, derived types, I/O
+(write/print/read/open/close/flush are skipped), modules as such (module variables are entries of the
+environment dictionary the caller supplies).
+"""
+from __future__ import annotations
+
+import keyword
+import math
+import re
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------------------
+# arrays with Fortran bounds.  Storage is a numpy array in C order with the index order reversed - a(i,j,k) is
+# store[k-lk, j-lj, i-li] - i.e. exactly the layout of the test arrays (nrows, ncols), which are wrapped, not copied
+# ---------------------------------------------------------------------------------------------------------
+class FArray:
+    __slots__ = ("a", "lo", "rank", "isint")
+
+    def __init__(self, store, lower):
+        self.a = store
+        self.lo = tuple(lower)
+        self.rank = len(self.lo)
+        assert store.ndim == self.rank, (store.shape, lower)
+        self.isint = store.dtype.kind in "iub"
+
+    @classmethod
+    def zeros(cls, bounds, dtype=np.float64, fill=0):
+        """bounds: ((lo, hi), ...) in Fortran order"""
+        shape = tuple(hi - lo + 1 for lo, hi in reversed(bounds))
+        return cls(np.full(shape, fill, dtype=dtype), [lo for lo, _ in bounds])
+
+    def __getitem__(self, idx):
+        if self.rank == 1:
+            v = self.a[idx - self.lo[0]]
+        elif self.rank == 2:
+            v = self.a[idx[1] - self.lo[1], idx[0] - self.lo[0]]
+        else:
+            v = self.a[tuple(i - l for i, l in zip(reversed(idx), reversed(self.lo)))]
+        return int(v) if self.isint else float(v)
+
+    def __setitem__(self, idx, v):
+        if self.rank == 1:
+            self.a[idx - self.lo[0]] = v
+        elif self.rank == 2:
+            self.a[idx[1] - self.lo[1], idx[0] - self.lo[0]] = v
+        else:
+            self.a[tuple(i - l for i, l in zip(reversed(idx), reversed(self.lo)))] = v
+
+    def fill(self, v):
+        self.a[...] = v
+
+    def from_element(self, idx, rank):
+        """sequence association: the array a callee sees when the actual argument is the element a(idx) and the
+        dummy has `rank` dimensions - the trailing dimensions are fixed at idx, the leading ones keep their bounds
+        (the element must be the first of its slab, as in `temp(1-nbdy,1-nbdy,k,n)`)"""
+        idx = tuple(idx) if isinstance(idx, tuple) else (idx,)
+        assert all(i == l for i, l in zip(idx[:rank], self.lo[:rank])), "element is not the start of a slab"
+        sel = tuple(i - l for i, l in zip(reversed(idx[rank:]), reversed(self.lo[rank:])))
+        return FArray(self.a[sel], self.lo[:rank])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# source handling
+# ---------------------------------------------------------------------------------------------------------
+def _strip_comment(line):
+    out, q = [], None
+    for ch in line:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif ch == "!":
+            break
+        else:
+            out.append(ch)
+    return "".join(out).rstrip()
+
+
+def load_source(path, defines=(), include_dirs=()):
+    """logical, lower-cased statements of a Fortran file after cpp: list of (label or None, text)"""
+    import os
+    defined = {d: "" for d in defines}
+    macros = {}
+    raw = open(path, errors="replace").read().split("\n")
+    out_lines, stack = [], []   # stack of [taking_now, any_branch_taken]
+
+    def active():
+        return all(s[0] for s in stack)
+    i = 0
+    while i < len(raw):
+        ln = raw[i]
+        i += 1
+        s = ln.strip()
+        if s.startswith("#"):
+            d = s[1:].strip()
+            m = re.match(r"(if|elif)\s+defined\s*\(\s*(\w+)\s*\)", d) or re.match(r"(ifdef)\s+(\w+)", d)
+            if m and m.group(1) in ("if", "ifdef"):
+                t = m.group(2) in defined or m.group(2) in macros
+                stack.append([t, t])
+            elif m and m.group(1) == "elif":
+                t = (not stack[-1][1]) and (m.group(2) in defined or m.group(2) in macros)
+                stack[-1][0] = t
+                stack[-1][1] = stack[-1][1] or t
+            elif d.startswith("if"):
+                raise NotImplementedError(f"cpp: {s}")
+            elif d.startswith("else"):
+                stack[-1][0] = not stack[-1][1]
+                stack[-1][1] = True
+            elif d.startswith("endif"):
+                stack.pop()
+            elif d.startswith("define") and active():
+                m = re.match(r"define\s+(\w+)\s*(.*)", d)
+                macros[m.group(1)] = m.group(2).strip()
+            elif d.startswith("include") and active():
+                m = re.search(r'"([^"]+)"', d)
+                for dd in (os.path.dirname(path),) + tuple(include_dirs):
+                    f = os.path.join(dd, m.group(1))
+                    if os.path.exists(f):
+                        raw[i:i] = open(f, errors="replace").read().split("\n")
+                        break
+            continue
+        if not active():
+            continue
+        out_lines.append(ln)
+    # comments, continuations (free form: trailing &; the next line may start with &)
+    stmts, cur = [], ""
+    for ln in out_lines:
+        ln = _strip_comment(ln)
+        if not ln.strip():
+            continue
+        body = ln.strip()
+        if cur:
+            if body.startswith("&"):
+                body = body[1:].lstrip()
+            cur += " " + body
+        else:
+            cur = body
+        if cur.endswith("&"):
+            cur = cur[:-1].rstrip()
+            continue
+        stmts.append(cur)
+        cur = ""
+    # macro substitution, lower case (strings are never needed), labels
+    res = []
+    for st in stmts:
+        for name, text in macros.items():
+            st = re.sub(r"\b%s\b" % re.escape(name), text, st)
+        st = re.sub(r"'[^']*'|\"[^\"]*\"", "''", st).lower()
+        m = re.match(r"^(\d+)\s+(.*)$", st)
+        res.append((int(m.group(1)), m.group(2)) if m else (None, st))
+    return res
+
+
+def extract_unit(stmts, name):
+    """(dummy argument names, body statements) of `subroutine name(...)`"""
+    name = name.lower()
+    for k, (_, st) in enumerate(stmts):
+        m = re.match(r"^(?:recursive\s+)?subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$", st)
+        if m and m.group(1) == name:
+            args = [a.strip() for a in (m.group(2) or "").split(",") if a.strip()]
+            body = []
+            for lab, s2 in stmts[k + 1:]:
+                if re.match(r"^end\s*(subroutine(\s+\w+)?)?\s*$", s2):
+                    return args, body
+                body.append((lab, s2))
+    raise KeyError(name)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# expressions: tokenizer + precedence climbing -> Python source
+# ---------------------------------------------------------------------------------------------------------
+_TOK = re.compile(r"""\s*(?:
+    (?P<str>'') |
+    (?P<num>(?:\d+\.(?!(?:and|or|not|eq|ne|lt|le|gt|ge|eqv|neqv|true|false)\.)\d*|\.\d+|\d+)(?:[ed][+-]?\d+)?(?:_\w+)?) |
+    (?P<dotop>\.(?:and|or|not|eq|ne|lt|le|gt|ge|true|false|eqv|neqv)\.) |
+    (?P<name>[a-z_]\w*) |
+    (?P<op>\*\*|==|/=|<=|>=|//|[-+*/(),<>:=])
+)""", re.X)
+
+_INTRINSIC = {
+    "max": "_max", "min": "_min", "amax1": "_max", "amin1": "_min", "dmax1": "_max", "dmin1": "_min", "max0": "_max",
+    "min0": "_min", "abs": "abs", "dabs": "abs", "iabs": "abs", "mod": "_mod", "sign": "_sign", "sqrt": "_sqrt",
+    "dsqrt": "_sqrt", "real": "float", "float": "float", "dble": "float", "int": "_int", "nint": "_nint",
+    "exp": "_exp", "log": "_log", "alog": "_log", "atan2": "_atan2", "cos": "_cos", "sin": "_sin", "atan": "_atan",
+    "tan": "_tan", "acos": "_acos", "asin": "_asin",
+}
+_REL = {".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", "==": "==", "/=": "!=",
+        "<": "<", "<=": "<=", ">": ">", ">=": ">="}
+
+
+def _pyname(n):
+    return n + "_" if keyword.iskeyword(n) or n in ("print", "len", "id", "type", "sum", "all", "any") else n
+
+
+def tokenize(s):
+    pos, toks = 0, []
+    s = s.strip()
+    while pos < len(s):
+        m = _TOK.match(s, pos)
+        if not m or m.end() == pos:
+            raise SyntaxError(f"cannot tokenize {s[pos:]!r} in {s!r}")
+        pos = m.end()
+        kind = m.lastgroup
+        toks.append((kind, m.group(kind)))
+    return toks
+
+
+class ExprParser:
+    """Fortran expression -> Python source.  `arrays`: names indexed with [] (everything else followed by '(' is a
+    call); `rank`: rank of known arrays (for array-element actual arguments)"""
+
+    def __init__(self, toks, arrays, funcs=()):
+        self.t, self.p, self.arrays, self.funcs = toks, 0, arrays, funcs
+
+    def peek(self):
+        return self.t[self.p] if self.p < len(self.t) else (None, None)
+
+    def take(self, val=None):
+        k, v = self.peek()
+        if val is not None and v != val:
+            raise SyntaxError(f"expected {val!r}, got {v!r} in {self.t}")
+        self.p += 1
+        return k, v
+
+    def parse(self):
+        e = self.p_or()
+        return e
+
+    def p_or(self):
+        e = self.p_and()
+        while self.peek()[1] in (".or.",):
+            self.take()
+            e = f"({e} or {self.p_and()})"
+        return e
+
+    def p_and(self):
+        e = self.p_not()
+        while self.peek()[1] == ".and.":
+            self.take()
+            e = f"({e} and {self.p_not()})"
+        return e
+
+    def p_not(self):
+        if self.peek()[1] == ".not.":
+            self.take()
+            return f"(not {self.p_not()})"
+        return self.p_rel()
+
+    def p_rel(self):
+        e = self.p_add()
+        if self.peek()[1] in _REL:
+            op = _REL[self.take()[1]]
+            e = f"({e} {op} {self.p_add()})"
+        return e
+
+    def p_add(self):
+        k, v = self.peek()
+        if v in ("+", "-"):
+            self.take()
+            e = self.p_mul()
+            e = f"(-{e})" if v == "-" else e
+        else:
+            e = self.p_mul()
+        while self.peek()[1] in ("+", "-"):
+            op = self.take()[1]
+            e = f"({e} {op} {self.p_mul()})"
+        return e
+
+    def p_mul(self):
+        e = self.p_pow()
+        while self.peek()[1] in ("*", "/"):
+            op = self.take()[1]
+            r = self.p_pow()
+            e = f"({e} * {r})" if op == "*" else f"_div({e}, {r})"
+        return e
+
+    def p_pow(self):
+        b = self.p_atom()
+        if self.peek()[1] == "**":
+            self.take()
+            k, v = self.peek()
+            if v in ("+", "-"):
+                self.take()
+                ex = self.p_pow()
+                ex = f"(-{ex})" if v == "-" else ex
+            else:
+                ex = self.p_pow()
+            return f"_pow({b}, {ex})"
+        return b
+
+    def args(self):
+        """comma list up to the closing parenthesis (consumed); ':' sections come back as the string ':'"""
+        out = []
+        if self.peek()[1] == ")":
+            self.take()
+            return out
+        while True:
+            if self.peek()[1] == ":":
+                self.take()
+                out.append(":")
+            else:
+                e = self.p_or()
+                if self.peek()[1] == ":":
+                    raise NotImplementedError("array sections with bounds")
+                out.append(e)
+            k, v = self.take()
+            if v == ")":
+                return out
+            if v != ",":
+                raise SyntaxError(f"expected , or ) got {v!r} in {self.t}")
+
+    def p_atom(self):
+        k, v = self.take()
+        if k == "str":
+            return "''"
+        if k == "num":
+            v = re.sub(r"_\w+$", "", v).replace("d", "e")
+            return v if re.search(r"[.e]", v) else v.lstrip("0") or "0"
+        if v == ".true.":
+            return "True"
+        if v == ".false.":
+            return "False"
+        if v == "(":
+            e = self.p_or()
+            self.take(")")
+            return f"({e})"
+        if k == "name":
+            if self.peek()[1] == "(":
+                self.take()
+                a = self.args()
+                if v in self.arrays:
+                    return f"{_pyname(v)}[{', '.join(a)}]" if len(a) > 1 else f"{_pyname(v)}[{a[0]}]"
+                if v in _INTRINSIC and v not in self.funcs:
+                    return f"{_INTRINSIC[v]}({', '.join(a)})"
+                return f"{_pyname(v)}({', '.join(a)})"
+            return _pyname(v)
+        raise SyntaxError(f"unexpected {v!r} in {self.t}")
+
+
+def expr(s, arrays, funcs=()):
+    p = ExprParser(tokenize(s), arrays, funcs)
+    e = p.parse()
+    if p.p != len(p.t):
+        raise SyntaxError(f"trailing tokens in {s!r}")
+    return e
+
+
+# ---------------------------------------------------------------------------------------------------------
+# run-time helpers the generated code calls
+# ---------------------------------------------------------------------------------------------------------
+def _div(a, b):
+    if isinstance(a, int) and isinstance(b, int) and not isinstance(a, bool):
+        q = abs(a) // abs(b)
+        return q if (a >= 0) == (b >= 0) else -q
+    return a / b if b != 0 else (math.copysign(math.inf, a) * math.copysign(1.0, b) if a != 0 and a == a else math.nan)
+
+
+def _pow(a, b):
+    if isinstance(b, int):
+        r = 1 if isinstance(a, int) else 1.0
+        for _ in range(abs(b)):
+            r = r * a
+        return r if b >= 0 else 1.0 / r
+    return math.pow(a, b)
+
+
+def _max(*a):
+    m = a[0]
+    for x in a[1:]:
+        if x > m:
+            m = x
+    return m
+
+
+def _min(*a):
+    m = a[0]
+    for x in a[1:]:
+        if x < m:
+            m = x
+    return m
+
+
+def _mod(a, b):
+    if isinstance(a, int) and isinstance(b, int):
+        return a - b * _div(a, b)
+    return math.fmod(a, b)
+
+
+def _sign(a, b):
+    return abs(a) if (b > 0 or (b == 0 and math.copysign(1.0, b) > 0)) else -abs(a)
+
+
+def _int(a):
+    return int(a)
+
+
+def _nint(a):
+    return int(math.floor(a + 0.5)) if a >= 0 else -int(math.floor(-a + 0.5))
+
+
+def _frange(a, b, c=1):
+    return range(a, b + 1, c) if c > 0 else range(a, b - 1, c)
+
+
+class FortranStop(Exception):
+    pass
+
+
+RUNTIME = dict(np=np, _div=_div, _pow=_pow, _max=_max, _min=_min, _mod=_mod, _sign=_sign, _int=_int, _nint=_nint,
+               _frange=_frange, _sqrt=math.sqrt, _exp=math.exp, _log=math.log, _atan2=math.atan2, _cos=math.cos,
+               _sin=math.sin, _atan=math.atan, _tan=math.tan, _acos=math.acos, _asin=math.asin, FArray=FArray,
+               FortranStop=FortranStop)
+
+_DECL = re.compile(r"^(real|integer|logical|character|double\s*precision|implicit|use|save|external|intrinsic|"
+                   r"dimension|private|public|data|common|parameter|type|include|allocatable|intent)\b")
+_IO = re.compile(r"^(write|print|read|open|close|flush|rewind|format|call\s+flush)\b")
+
+
+def _split_top(s, sep=","):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+        if ch == sep and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    out.append(cur)
+    return [x.strip() for x in out]
+
+
+def _match_paren(s, start):
+    depth = 0
+    for k in range(start, len(s)):
+        if s[k] == "(":
+            depth += 1
+        elif s[k] == ")":
+            depth -= 1
+            if depth == 0:
+                return k
+    raise SyntaxError(s)
+
+
+class Translator:
+    """one subroutine -> Python source.  `env_arrays`: rank of every array visible to the unit (dummies included);
+    `module_scalars`: module variables the unit may assign (declared global); `callee_ranks`: for a subroutine
+    called from here, the ranks of its dummy arrays by position (None for scalars) so that array-element actual
+    arguments become views; `skip_calls`: calls to drop; `inout_calls`: `call f(x)` that means x = f(x)"""
+
+    def __init__(self, name, args, body, env_arrays, module_scalars=(), callee_ranks=None, skip_calls=(),
+                 inout_calls=(), funcs=(), drop_blocks=()):
+        self.name, self.args, self.body = name, args, body
+        self.arr = dict(env_arrays)
+        self.modsc = set(module_scalars)
+        self.callee = callee_ranks or {}
+        self.skip = set(skip_calls)
+        self.inout = set(inout_calls)
+        self.funcs = set(funcs)
+        self.drop = [re.compile(r) for r in drop_blocks]   # block-ifs (diagnostic output) to leave out entirely
+        self.lines, self.ind = [], 1
+        self.assigned = set()
+        self.do_labels = []   # stack of labels of open labelled do loops (None for unlabelled)
+
+    def emit(self, s):
+        self.lines.append("    " * self.ind + s)
+
+    def ex(self, s):
+        return expr(s, self.arr, self.funcs)
+
+    def stmt(self, st):
+        if re.match(r"^(go\s*to|where|forall|select|cycle|exit)\b", st):
+            raise NotImplementedError(st)
+        if _IO.match(st) or st in ("continue",):
+            self.emit("pass")
+            return
+        m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*?)::(.*)$", st)
+        if ((m and "parameter" in m.group(2)) or re.match(r"^parameter\s*\(", st)) and getattr(self, "params_done", False):
+            return            # emitted ahead of the local arrays by declarations()
+        if m and "parameter" in m.group(2):
+            for item in _split_top(m.group(3)):
+                if "=" in item:
+                    n, v = item.split("=", 1)
+                    if "(/" in v:
+                        raise NotImplementedError(st)
+                    self.emit(f"{_pyname(n.strip())} = {self.ex(v)}")
+            return
+        m = re.match(r"^parameter\s*\((.*)\)$", st)
+        if m:
+            for item in _split_top(m.group(1)):
+                n, v = item.split("=", 1)
+                self.emit(f"{_pyname(n.strip())} = {self.ex(v)}")
+            return
+        if _DECL.match(st):
+            return
+        if st == "return":
+            self.emit("return")
+            return
+        if st.startswith("stop"):
+            self.emit("raise FortranStop()")
+            return
+        m = re.match(r"^do\s+(?:(\d+)\s+)?(\w+)\s*=\s*(.*)$", st)
+        if m:
+            parts = _split_top(m.group(3))
+            rng = ", ".join(self.ex(p) for p in parts)
+            self.emit(f"for {_pyname(m.group(2))} in _frange({rng}):")
+            self.ind += 1
+            self.emit("pass")
+            self.do_labels.append(int(m.group(1)) if m.group(1) else None)
+            return
+        if re.match(r"^end\s*do$", st):
+            self.ind -= 1
+            self.do_labels.pop()
+            return
+        m = re.match(r"^(else\s*if|elseif|if)\s*\(", st)
+        if m and m.group(1) == "if" and "if" in self.arr:
+            e0 = _match_paren(st, st.index("("))
+            if re.match(r"^\s*=[^=]", st[e0 + 1:]):
+                m = None          # an array called `if` (bigrid.F90: indxi) is being assigned
+        if m:
+            start = st.index("(", m.end() - 1)
+            end = _match_paren(st, start)
+            cond, rest = st[start + 1:end], st[end + 1:].strip()
+            kw = "if" if m.group(1) == "if" else "elif"
+            if rest == "then":
+                if kw == "elif":
+                    self.ind -= 1
+                self.emit(f"{kw} {self.ex(cond)}:")
+                self.ind += 1
+                self.emit("pass")
+            else:
+                assert kw == "if", st
+                self.emit(f"if {self.ex(cond)}:")
+                self.ind += 1
+                self.stmt(rest)
+                self.ind -= 1
+            return
+        if st == "else":
+            self.ind -= 1
+            self.emit("else:")
+            self.ind += 1
+            self.emit("pass")
+            return
+        if re.match(r"^end\s*if$", st):
+            self.ind -= 1
+            return
+        m = re.match(r"^call\s+(\w+)\s*(?:\((.*)\))?$", st)
+        if m:
+            f, a = m.group(1), (_split_top(m.group(2)) if m.group(2) else [])
+            if f in self.skip:
+                self.emit("pass")
+                return
+            if f in self.inout:
+                self.emit(f"{_pyname(a[0])} = {f}({', '.join(self.ex(x) for x in a)})")
+                self.assigned.add(a[0])
+                return
+            ranks = self.callee.get(f)
+            out = []
+            for k, x in enumerate(a):
+                mm = re.match(r"^(\w+)\s*\((.*)\)$", x)
+                if mm and mm.group(1) in self.arr and ranks is not None and k < len(ranks) and ranks[k]:
+                    idx = ", ".join(self.ex(y) for y in _split_top(mm.group(2)))
+                    out.append(f"{_pyname(mm.group(1))}.from_element(({idx},), {ranks[k]})")
+                else:
+                    out.append(self.ex(x))
+            self.emit(f"{_pyname(f)}({', '.join(out)})")
+            return
+        # assignment
+        depth, eq = 0, -1
+        for k, ch in enumerate(st):
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "=" and depth == 0 and st[k - 1] not in "<>/=" and st[k + 1:k + 2] != "=":
+                eq = k
+                break
+        if eq < 0:
+            raise NotImplementedError(st)
+        lhs, rhs = st[:eq].strip(), st[eq + 1:].strip()
+        m = re.match(r"^(\w+)\s*\((.*)\)$", lhs)
+        if m:
+            n, idx = m.group(1), _split_top(m.group(2))
+            if n not in self.arr:
+                raise NotImplementedError(f"assignment to unknown array {n}: {st}")
+            if all(i == ":" for i in idx):
+                self.emit(f"{_pyname(n)}.fill({self.ex(rhs)})")
+            else:
+                ii = ", ".join(self.ex(i) for i in idx)
+                self.emit(f"{_pyname(n)}[{ii}] = {self.ex(rhs)}")
+        elif lhs in self.arr:
+            self.emit(f"{_pyname(lhs)}.fill({self.ex(rhs)})")
+        else:
+            self.assigned.add(lhs)
+            self.emit(f"{_pyname(lhs)} = {self.ex(rhs)}")
+
+    def declarations(self):
+        """arrays declared in the unit: dummies get their rank; locals with explicit bounds are allocated (after the
+        parameter constants, which may size them)"""
+        self.params_done = True
+        for _, st in self.body:
+            m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*?)::(.*)$", st)
+            if (m and "parameter" in m.group(2)) or re.match(r"^parameter\s*\(", st):
+                self.params_done = False
+                self.stmt(st)
+        self.params_done = True
+        for _, st in self.body:
+            m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*)$", st)
+            if not m or "parameter" in m.group(2).split("::")[0]:
+                continue
+            isint = m.group(1) in ("integer", "logical")
+            rest = m.group(2)
+            if "::" in rest:
+                attrs, ents = rest.split("::", 1)
+            else:
+                attrs, ents = "", rest
+            dim = None
+            md = re.search(r"dimension\s*\(", attrs)
+            if md:
+                end = _match_paren(attrs, md.end() - 1)
+                dim = _split_top(attrs[md.end():end])
+            for ent in _split_top(ents):
+                me = re.match(r"^(\w+)\s*(?:\((.*)\))?(?:\s*\*\s*\d+)?$", ent.split("=")[0].strip())
+                if not me:
+                    continue
+                n, own = me.group(1), me.group(2)
+                bounds = _split_top(own) if own else dim
+                if not bounds:
+                    continue
+                self.arr[n] = len(bounds)
+                if n not in self.args and "allocatable" not in attrs and all(":" not in b or b.count(":") == 1 for b in bounds) \
+                        and not any(b.strip() in (":", "*") for b in bounds):
+                    bb = []
+                    for b in bounds:
+                        lo, hi = (b.split(":") + [None])[:2] if ":" in b else ("1", b)
+                        bb.append(f"({self.ex(lo)}, {self.ex(hi)})")
+                    self.emit(f"{_pyname(n)} = FArray.zeros(({', '.join(bb)},), dtype={'np.int64' if isint else 'np.float64'})")
+
+    def source(self):
+        self.declarations()
+        skipping = 0
+        for lab, st in self.body:
+            if skipping:
+                if re.match(r"^if\s*\(.*\)\s*then$", st):
+                    skipping += 1
+                elif re.match(r"^end\s*if$", st):
+                    skipping -= 1
+                continue
+            if any(r.search(st) for r in self.drop) and re.match(r"^if\s*\(.*\)\s*then$", st):
+                skipping = 1
+                continue
+            self.stmt(st)
+            while lab is not None and self.do_labels and self.do_labels[-1] == lab:
+                self.ind -= 1
+                self.do_labels.pop()
+        glob = sorted(_pyname(n) for n in self.assigned if n in self.modsc and n not in self.args)
+        head = [f"def {self.name}({', '.join(_pyname(a) for a in self.args)}):"]
+        if glob:
+            head.append("    global " + ", ".join(glob))
+        return "\n".join(head + ["    pass"] + self.lines) + "\n"
+
+
+def compile_unit(path, name, env, defines=("RELO",), extra_arrays=None, **kw):
+    """translate `subroutine name` of the file and define it in `env` (a dict that holds the module variables:
+    FArray objects and scalars); returns the Python source (for inspection)"""
+    stmts = load_source(path, defines)
+    args, body = extract_unit(stmts, name)
+    arrays = {k: v.rank for k, v in env.items() if isinstance(v, FArray)}
+    arrays.update(extra_arrays or {})
+    t = Translator(name.lower(), args, body, arrays, module_scalars=[k for k, v in env.items() if not isinstance(v, FArray)],
+                   **kw)
+    src = t.source()
+    for k, v in RUNTIME.items():
+        env.setdefault(k, v)
+    exec(compile(src, f"<{name} of {path}>", "exec"), env)
+    return src

@@ -1,0 +1,137 @@
+"""The CPU oracle against the REFERENCE'S OWN SOURCE TEXT, executed here without a Fortran compiler:
+oracle/fortran_exec.py translates the structured Fortran of /root/reference/bigrid.F90 and mod_tsadvc.F90
+statement by statement into Python (it knows the language, not the algorithms) and runs it in IEEE double
+precision; the oracle (oracle/tsadvc_oracle.c) must reproduce every result bit for bit.
+
+  * bigrid: ip, iu, iv, iq, the sea-only neighbour indices and the segment tables ifp/ilp/isp, jfp/jlp/jsp
+  * advem_pcm, advem_mpdata, advem_fct2, advem_fct4 on small basins with islands and on periodic domains
+
+The live tests need /root/reference (present in the build container, absent on the GPU box: they skip there);
+tests/golden/from_reference_text.json keeps the digests of the same runs (make_reference_text_vectors.py), which
+the oracle must reproduce everywhere."""
+import ctypes as C
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import reference_text as rt  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "from_reference_text.json")
+
+# itdm, jtdm, nreg, seed
+GRIDS = [(26, 22, 0, 3), (24, 20, 1, 5), (22, 24, 3, 7), (20, 26, 4, 9)]
+SCHEMES = [0, 1, 2, 4]
+
+
+def build_case(itdm, jtdm, nreg, seed):
+    """a small case of the usual generator + its depth array (100 m on sea) as bigrid wants it"""
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, 2, nreg=nreg, seed=seed)
+    nb = g.nbdy
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+    return cfg, sea, g, cb, depth
+
+
+def oracle_advem(ot, advtyp, fld, fldc, u, v, fco, fcn, posdef, scal, scali, dt2):
+    P = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    rc = ot.lib.orc_advem(ot.t, advtyp, P(fld), P(fldc), P(u), P(v), P(fco), P(fcn), posdef, P(scal), P(scali), dt2, 0)
+    assert rc == 0
+    return fld
+
+
+def advem_inputs(g, cb, seed):
+    """operands of one advem call with valid halos (width nbdy): the case's fields of layer 1, halo-refreshed the
+    way tsadvc does before it calls advem, and the prolog's fco, fcn"""
+    import np_restatement as npr
+    nb = g.nbdy
+    H = lambda a, it=1: npr.halo_single_tile(g, np.array(a, dtype=np.float64), nb, nb, it)   # noqa: E731
+    fld = H(cb.saln[1, 0])
+    fldc = H(cb.saln[0, 0])
+    u, v = H(cb.uflx[0], 13), H(cb.vflx[0], 14)
+    dp = np.nan_to_num(H(cb.dp[1, 0]))
+    with np.errstate(all="ignore"):
+        flxdiv = ((np.roll(u, -1, 1) - u) + (np.roll(v, -1, 0) - v)) * cb.delt1 * cb.scp2i
+    fco = np.maximum(dp + np.nan_to_num(flxdiv), 0.0)
+    fcn = np.maximum(dp, 0.0)
+    clean = lambda a: np.ascontiguousarray(np.nan_to_num(a))   # noqa: E731
+    return [clean(x) for x in (fld, fldc, u, v, fco, fcn)] + [np.ascontiguousarray(cb.scp2), np.ascontiguousarray(cb.scp2i)]
+
+
+def digest(a, mask):
+    return hashlib.sha256(np.ascontiguousarray(a[mask]).astype("<f8").tobytes()).hexdigest()[:24]
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("itdm,jtdm,nreg,seed", GRIDS)
+def test_bigrid_of_the_reference_text_equals_oracle(oracle, itdm, jtdm, nreg, seed):
+    cfg, sea, g, cb, depth = build_case(itdm, jtdm, nreg, seed)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    env = rt.make_env(g.ii, g.jj)
+    rt.run_bigrid(env, depth.copy(), mapflg=4 if nreg in (3, 4) else 0)
+    assert env["nreg"] == nreg
+    nb = g.nbdy
+    for name in ("ip", "iu", "iv", "iq"):
+        assert np.array_equal(env[name].a, ot.i32(name)), name
+    inner = np.zeros((g.nrows, g.ncols), dtype=bool)
+    inner[1:-1, 1:-1] = True         # the neighbour indices are defined one line inside the array (bigrid.F90:318)
+    jj_, ii_ = np.meshgrid(np.arange(g.nrows) - nb + 1, np.arange(g.ncols) - nb + 1, indexing="ij")
+    for name in ("ipim1", "ipip1", "ipjm1", "ipjp1"):
+        assert np.array_equal(env[name].a[inner], ot.i32(name)[inner]), name
+    # segment tables: the oracle stores (ms, nrows) / (ms, ncols)
+    ms = min(env["ms"], ot.get_i("ms"))
+    assert np.array_equal(env["isp"].a, ot.i32("isp")) and np.array_equal(env["jsp"].a, ot.i32("jsp"))
+    assert env["isp"].a.max() <= ms and env["jsp"].a.max() <= ms
+    for a, b in (("ifp", "ifp"), ("ilp", "ilp"), ("jfp", "jfp"), ("jlp", "jlp")):
+        assert np.array_equal(env[a].a[:ms], ot.i32(b)[:ms]), a
+    ot.close()
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("advtyp", SCHEMES)
+@pytest.mark.parametrize("itdm,jtdm,nreg,seed", GRIDS)
+def test_advem_of_the_reference_text_equals_oracle(oracle, itdm, jtdm, nreg, seed, advtyp):
+    cfg, sea, g, cb, depth = build_case(itdm, jtdm, nreg, seed)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    env = rt.make_env(g.ii, g.jj)
+    rt.run_bigrid(env, depth.copy(), mapflg=4 if nreg in (3, 4) else 0)
+    ops = advem_inputs(g, cb, seed)
+    posdef = 0.0 if advtyp != 1 else 256.0
+    want = rt.run_advem(env, advtyp, ops[0].copy(), *[o.copy() for o in ops[1:6]], posdef, ops[6], ops[7], cb.delt1)
+    got = oracle_advem(ot, advtyp, ops[0].copy(), *[o.copy() for o in ops[1:6]], posdef, ops[6].copy(), ops[7].copy(), cb.delt1)
+    inner = util.interior_sea(cb)
+    assert np.isfinite(want[inner]).all()
+    assert not np.array_equal(want[inner], ops[0][inner])          # the field moved
+    assert np.array_equal(got[inner], want[inner]), np.abs(got - want)[inner].max()
+    gold = json.load(open(GOLD)) if os.path.exists(GOLD) else {}
+    key = f"advem{advtyp}:{itdm}x{jtdm}:nreg{nreg}:seed{seed}"
+    if key in gold:
+        assert gold[key] == digest(want, inner), key
+    ot.close()
+
+
+def test_oracle_reproduces_the_digests_of_the_reference_text(oracle):
+    """everywhere (also where the reference tree is absent): the committed digests of the runs above"""
+    if not os.path.exists(GOLD):
+        pytest.skip("tests/golden/from_reference_text.json has not been generated")
+    gold = json.load(open(GOLD))
+    assert len(gold) >= len(GRIDS) * len(SCHEMES)
+    for itdm, jtdm, nreg, seed in GRIDS:
+        cfg, sea, g, cb, depth = build_case(itdm, jtdm, nreg, seed)
+        ot = util.oracle_tile_from_cb(oracle, cb, sea)
+        ops = advem_inputs(g, cb, seed)
+        inner = util.interior_sea(cb)
+        for advtyp in SCHEMES:
+            posdef = 0.0 if advtyp != 1 else 256.0
+            got = oracle_advem(ot, advtyp, ops[0].copy(), *[o.copy() for o in ops[1:6]], posdef, ops[6].copy(),
+                               ops[7].copy(), cb.delt1)
+            key = f"advem{advtyp}:{itdm}x{jtdm}:nreg{nreg}:seed{seed}"
+            assert gold[key] == digest(got, inner), key
+        ot.close()
