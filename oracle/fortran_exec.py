@@ -68,14 +68,34 @@ class FArray:
     def fill(self, v):
         self.a[...] = v
 
+    def section(self, idx):
+        """numpy view of a(lo:hi, :, k, ...): `idx` holds ints (the dimension is dropped) or (lo, hi) pairs with
+        None for an open end (the dimension stays); the view keeps the storage order (last Fortran dimension first)"""
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        sel = []
+        for d in range(self.rank - 1, -1, -1):
+            x, l = idx[d], self.lo[d]
+            if isinstance(x, tuple):
+                lo, hi = x
+                sel.append(slice(None if lo is None else lo - l, None if hi is None else hi - l + 1))
+            else:
+                sel.append(x - l)
+        return self.a[tuple(sel)]
+
     def from_element(self, idx, rank):
-        """sequence association: the array a callee sees when the actual argument is the element a(idx) and the
-        dummy has `rank` dimensions - the trailing dimensions are fixed at idx, the leading ones keep their bounds
-        (the element must be the first of its slab, as in `temp(1-nbdy,1-nbdy,k,n)`)"""
+        """sequence association: the array a callee with a `rank`-dimensional dummy sees when the actual argument is
+        the element a(idx).  The first rank-1 dimensions keep their extent (the element must start them), everything
+        from dimension `rank` on is one long last dimension that begins at the element - so that, as in Fortran,
+        `call xctilr(saln(1-nbdy,1-nbdy,1,1),1,2*kk,..)` reaches both time levels.  The last dimension is numbered
+        from the element's own index (callees that number it from 1 are told so by the harness)."""
         idx = tuple(idx) if isinstance(idx, tuple) else (idx,)
-        assert all(i == l for i, l in zip(idx[:rank], self.lo[:rank])), "element is not the start of a slab"
-        sel = tuple(i - l for i, l in zip(reversed(idx[rank:]), reversed(self.lo[rank:])))
-        return FArray(self.a[sel], self.lo[:rank])
+        lead = rank - 1
+        assert all(i == l for i, l in zip(idx[:lead], self.lo[:lead])), "element is not the start of a slab"
+        R = self.rank
+        flat = self.a.reshape((-1,) + self.a.shape[R - lead:])
+        tail = tuple(i - l for i, l in zip(reversed(idx[lead:]), reversed(self.lo[lead:])))
+        start = int(np.ravel_multi_index(tail, self.a.shape[:R - lead]))
+        return FArray(flat[start:], self.lo[:lead] + (idx[lead],))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -115,16 +135,23 @@ def load_source(path, defines=(), include_dirs=()):
         s = ln.strip()
         if s.startswith("#"):
             d = s[1:].strip()
-            m = re.match(r"(if|elif)\s+defined\s*\(\s*(\w+)\s*\)", d) or re.match(r"(ifdef)\s+(\w+)", d)
-            if m and m.group(1) in ("if", "ifdef"):
-                t = m.group(2) in defined or m.group(2) in macros
+            m = re.match(r"(ifdef|ifndef|if|elif)\b\s*(.*)$", d)
+
+            def cpp_true(e):
+                # defined (X), (X), X joined by || && ! : an identifier is true when it is defined
+                e = re.sub(r"defined\s*\(\s*(\w+)\s*\)", lambda q: " 1 " if (q.group(1) in defined or q.group(1) in macros) else " 0 ", e)
+                e = re.sub(r"defined\s+(\w+)", lambda q: " 1 " if (q.group(1) in defined or q.group(1) in macros) else " 0 ", e)
+                e = re.sub(r"[A-Za-z_]\w*", lambda q: " 1 " if (q.group(0) in defined or q.group(0) in macros) else " 0 ", e)
+                e = e.replace("||", " or ").replace("&&", " and ").replace("!", " not ")
+                return bool(eval(e, {"__builtins__": {}}))
+            if m and m.group(1) in ("if", "ifdef", "ifndef"):
+                t = cpp_true(m.group(2))
+                t = (not t) if m.group(1) == "ifndef" else t
                 stack.append([t, t])
             elif m and m.group(1) == "elif":
-                t = (not stack[-1][1]) and (m.group(2) in defined or m.group(2) in macros)
+                t = (not stack[-1][1]) and cpp_true(m.group(2))
                 stack[-1][0] = t
                 stack[-1][1] = stack[-1][1] or t
-            elif d.startswith("if"):
-                raise NotImplementedError(f"cpp: {s}")
             elif d.startswith("else"):
                 stack[-1][0] = not stack[-1][1]
                 stack[-1][1] = True
@@ -174,17 +201,35 @@ def load_source(path, defines=(), include_dirs=()):
 
 
 def extract_unit(stmts, name):
-    """(dummy argument names, body statements) of `subroutine name(...)`"""
+    """(dummy argument names, body statements, internal procedures) of `subroutine name(...)`; the internal
+    procedures (after `contains`) come back as a list of (name, args, body)"""
     name = name.lower()
+    head = re.compile(r"^(?:recursive\s+)?subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$")
+    tail = re.compile(r"^end\s*(subroutine(\s+\w+)?)?\s*$")
     for k, (_, st) in enumerate(stmts):
-        m = re.match(r"^(?:recursive\s+)?subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$", st)
+        m = head.match(st)
         if m and m.group(1) == name:
             args = [a.strip() for a in (m.group(2) or "").split(",") if a.strip()]
-            body = []
+            body, internals, cur, inside = [], [], None, False
             for lab, s2 in stmts[k + 1:]:
-                if re.match(r"^end\s*(subroutine(\s+\w+)?)?\s*$", s2):
-                    return args, body
-                body.append((lab, s2))
+                if not inside:
+                    if s2 == "contains":
+                        inside = True
+                        continue
+                    if tail.match(s2):
+                        return args, body, internals
+                    body.append((lab, s2))
+                else:
+                    m2 = head.match(s2)
+                    if cur is None and m2:
+                        cur = (m2.group(1), [a.strip() for a in (m2.group(2) or "").split(",") if a.strip()], [])
+                    elif cur is not None and tail.match(s2):
+                        internals.append(cur)
+                        cur = None
+                    elif cur is not None:
+                        cur[2].append((lab, s2))
+                    elif tail.match(s2):
+                        return args, body, internals
     raise KeyError(name)
 
 
@@ -204,7 +249,7 @@ _INTRINSIC = {
     "min0": "_min", "abs": "abs", "dabs": "abs", "iabs": "abs", "mod": "_mod", "sign": "_sign", "sqrt": "_sqrt",
     "dsqrt": "_sqrt", "real": "float", "float": "float", "dble": "float", "int": "_int", "nint": "_nint",
     "exp": "_exp", "log": "_log", "alog": "_log", "atan2": "_atan2", "cos": "_cos", "sin": "_sin", "atan": "_atan",
-    "tan": "_tan", "acos": "_acos", "asin": "_asin",
+    "tan": "_tan", "acos": "_acos", "asin": "_asin", "minval": "_minval", "maxval": "_maxval",
 }
 _REL = {".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", "==": "==", "/=": "!=",
         "<": "<", "<=": "<=", ">": ">", ">=": ">="}
@@ -311,20 +356,24 @@ class ExprParser:
         return b
 
     def args(self):
-        """comma list up to the closing parenthesis (consumed); ':' sections come back as the string ':'"""
+        """comma list up to the closing parenthesis (consumed); a section lo:hi comes back as ('sec', lo, hi) with
+        None for an open end"""
         out = []
         if self.peek()[1] == ")":
             self.take()
             return out
         while True:
+            lo = None
+            if self.peek()[1] != ":":
+                lo = self.p_or()
             if self.peek()[1] == ":":
                 self.take()
-                out.append(":")
+                hi = None
+                if self.peek()[1] not in (",", ")"):
+                    hi = self.p_or()
+                out.append(("sec", lo, hi))
             else:
-                e = self.p_or()
-                if self.peek()[1] == ":":
-                    raise NotImplementedError("array sections with bounds")
-                out.append(e)
+                out.append(lo)
             k, v = self.take()
             if v == ")":
                 return out
@@ -351,6 +400,9 @@ class ExprParser:
                 self.take()
                 a = self.args()
                 if v in self.arrays:
+                    if any(isinstance(x, tuple) for x in a):
+                        parts = [f"({x[1]}, {x[2]})" if isinstance(x, tuple) else x for x in a]
+                        return f"{_pyname(v)}.section(({', '.join(parts)},))"
                     return f"{_pyname(v)}[{', '.join(a)}]" if len(a) > 1 else f"{_pyname(v)}[{a[0]}]"
                 if v in _INTRINSIC and v not in self.funcs:
                     return f"{_INTRINSIC[v]}({', '.join(a)})"
@@ -428,7 +480,7 @@ class FortranStop(Exception):
     pass
 
 
-RUNTIME = dict(np=np, _div=_div, _pow=_pow, _max=_max, _min=_min, _mod=_mod, _sign=_sign, _int=_int, _nint=_nint,
+RUNTIME = dict(np=np, _minval=lambda a: float(np.min(a)), _maxval=lambda a: float(np.max(a)), _div=_div, _pow=_pow, _max=_max, _min=_min, _mod=_mod, _sign=_sign, _int=_int, _nint=_nint,
                _frange=_frange, _sqrt=math.sqrt, _exp=math.exp, _log=math.log, _atan2=math.atan2, _cos=math.cos,
                _sin=math.sin, _atan=math.atan, _tan=math.tan, _acos=math.acos, _asin=math.asin, FArray=FArray,
                FortranStop=FortranStop)
@@ -473,7 +525,7 @@ class Translator:
     arguments become views; `skip_calls`: calls to drop; `inout_calls`: `call f(x)` that means x = f(x)"""
 
     def __init__(self, name, args, body, env_arrays, module_scalars=(), callee_ranks=None, skip_calls=(),
-                 inout_calls=(), funcs=(), drop_blocks=()):
+                 inout_calls=(), funcs=(), drop_blocks=(), internals=(), host=None):
         self.name, self.args, self.body = name, args, body
         self.arr = dict(env_arrays)
         self.modsc = set(module_scalars)
@@ -482,6 +534,8 @@ class Translator:
         self.inout = set(inout_calls)
         self.funcs = set(funcs)
         self.drop = [re.compile(r) for r in drop_blocks]   # block-ifs (diagnostic output) to leave out entirely
+        self.internals, self.host = list(internals), host
+        self.kw = dict(callee_ranks=callee_ranks, skip_calls=skip_calls, inout_calls=inout_calls, drop_blocks=drop_blocks)
         self.lines, self.ind = [], 1
         self.assigned = set()
         self.do_labels = []   # stack of labels of open labelled do loops (None for unlabelled)
@@ -606,9 +660,16 @@ class Translator:
         if m:
             n, idx = m.group(1), _split_top(m.group(2))
             if n not in self.arr:
+                if all(re.match(r"^[a-z_]\w*$", i) for i in idx):   # a statement function: name(dummies) = expression
+                    self.funcs.add(n)
+                    self.emit(f"def {_pyname(n)}({', '.join(_pyname(i) for i in idx)}):")
+                    self.emit(f"    return {self.ex(rhs)}")
+                    return
                 raise NotImplementedError(f"assignment to unknown array {n}: {st}")
             if all(i == ":" for i in idx):
                 self.emit(f"{_pyname(n)}.fill({self.ex(rhs)})")
+            elif any(":" in i for i in idx):
+                self.emit(f"{self.ex(lhs)}[...] = {self.ex(rhs)}")
             else:
                 ii = ", ".join(self.ex(i) for i in idx)
                 self.emit(f"{_pyname(n)}[{ii}] = {self.ex(rhs)}")
@@ -650,9 +711,12 @@ class Translator:
                 n, own = me.group(1), me.group(2)
                 bounds = _split_top(own) if own else dim
                 if not bounds:
+                    if n in self.arr and n not in self.args and self.host is None:
+                        del self.arr[n]       # a local scalar that hides a module array of the same name
                     continue
+                known = n in self.arr
                 self.arr[n] = len(bounds)
-                if n not in self.args and "allocatable" not in attrs and all(":" not in b or b.count(":") == 1 for b in bounds) \
+                if not known and n not in self.args and "allocatable" not in attrs and all(":" not in b or b.count(":") == 1 for b in bounds) \
                         and not any(b.strip() in (":", "*") for b in bounds):
                     bb = []
                     for b in bounds:
@@ -677,22 +741,40 @@ class Translator:
             while lab is not None and self.do_labels and self.do_labels[-1] == lab:
                 self.ind -= 1
                 self.do_labels.pop()
+        if self.host is not None:
+            return None
+        # internal procedures (host association): nested functions that see the host's variables; what they assign
+        # and the host assigns too is the host's variable
+        inner_src = []
+        for iname, iargs, ibody in self.internals:
+            t = Translator(iname, iargs, ibody, self.arr, module_scalars=self.modsc, funcs=self.funcs, host=self, **self.kw)
+            t.ind = 2
+            t.source()
+            shared = sorted(_pyname(n) for n in t.assigned if (n in self.assigned or n in self.args) and n not in iargs)
+            inner_src.append(f"    def {_pyname(iname)}({', '.join(_pyname(a) for a in iargs)}):")
+            if shared:
+                inner_src.append("        nonlocal " + ", ".join(shared))
+            inner_src.append("        pass")
+            inner_src += t.lines
+            self.assigned |= {n for n in t.assigned if n in self.modsc}
         glob = sorted(_pyname(n) for n in self.assigned if n in self.modsc and n not in self.args)
         head = [f"def {self.name}({', '.join(_pyname(a) for a in self.args)}):"]
         if glob:
             head.append("    global " + ", ".join(glob))
-        return "\n".join(head + ["    pass"] + self.lines) + "\n"
+        # statement functions and parameters come first in self.lines; internal procedures may use them, so they go
+        # after the declarations block: Python resolves the names when the internal procedure is called
+        return "\n".join(head + ["    pass"] + inner_src + self.lines) + "\n"
 
 
 def compile_unit(path, name, env, defines=("RELO",), extra_arrays=None, **kw):
     """translate `subroutine name` of the file and define it in `env` (a dict that holds the module variables:
     FArray objects and scalars); returns the Python source (for inspection)"""
     stmts = load_source(path, defines)
-    args, body = extract_unit(stmts, name)
+    args, body, internals = extract_unit(stmts, name)
     arrays = {k: v.rank for k, v in env.items() if isinstance(v, FArray)}
     arrays.update(extra_arrays or {})
     t = Translator(name.lower(), args, body, arrays, module_scalars=[k for k, v in env.items() if not isinstance(v, FArray)],
-                   **kw)
+                   internals=internals, **kw)
     src = t.source()
     for k, v in RUNTIME.items():
         env.setdefault(k, v)

@@ -33,7 +33,8 @@ def _xctilr_factory(env):
         per_j = env["nreg"] in (3, 4)
         if env["nreg"] == 2:
             raise NotImplementedError("arctic xctilr is not provided to the reference text")
-        st = a.a if a.rank == 2 else a.a[l1 - a.lo[2]:l1 - a.lo[2] + ld]
+        # (a 3-D argument is the view from the element the caller passed on: its first slab is l1 = 1)
+        st = a.a if a.rank == 2 else a.a[l1 - 1:l1 - 1 + ld]
         st = st.reshape((-1,) + st.shape[-2:])
         mh, nh = min(mh, nb), min(nh, nb)
         r0, c0 = nb, nb           # store index of (i,j) = (1,1)
@@ -146,3 +147,78 @@ def run_advem(env, advtyp, fld, fldc, u, v, fco, fcn, posdef, scal, scali, dt2):
     else:
         raise ValueError(advtyp)
     return fld
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the driver tsadvc(m,n) itself (mod_tsadvc.F90:1708-2258) with its internal procedures tsdff_1x / tsdff_2x and the
+# statement functions of stmt_fns.h
+# ---------------------------------------------------------------------------------------------------------
+_EOS_DEFINES = {1: ("EOS_SIG0", "EOS_7T"), 2: ("EOS_SIG2", "EOS_7T"), 3: ("EOS_SIG0", "EOS_9T"), 4: ("EOS_SIG2", "EOS_9T"),
+                5: ("EOS_SIG0", "EOS_17T"), 6: ("EOS_SIG2", "EOS_17T"), 7: ("EOS_SIG0", "EOS_12T"), 8: ("EOS_SIG2", "EOS_12T")}
+
+
+def add_cb_arrays(env, cb):
+    """mod_cb_arrays variables that tsadvc touches, wrapping the arrays of a test case (no copies: the routine
+    updates cb in place, as the reference updates its module arrays)"""
+    g = cb.geom
+    nb, kk = g.nbdy, g.kdm
+    lo2 = (1 - nb, 1 - nb)
+    W = lambda a, lo: fx.FArray(np.ascontiguousarray(a) if not a.flags["C_CONTIGUOUS"] else a, lo)   # noqa: E731
+    env.update(kdm=kk, kk=kk)
+    for name in ("temp", "saln", "th3d", "dp"):
+        env[name] = W(getattr(cb, name), lo2 + (1, 1))
+    env["uflx"], env["vflx"] = W(cb.uflx, lo2 + (1,)), W(cb.vflx, lo2 + (1,))
+    env["oneta"] = W(cb.oneta, lo2 + (1,))
+    env["onetamas"] = fx.FArray.zeros(((1 - nb, g.ii + nb), (1 - nb, g.jj + nb), (1, 2)), fill=np.nan)
+    if cb.ntracr:
+        env["tracer"] = W(cb.tracer, lo2 + (1, 1, 1))
+    else:
+        env["tracer"] = fx.FArray.zeros(((1 - nb, g.ii + nb), (1 - nb, g.jj + nb), (1, kk), (1, 2), (1, 1)))
+    if getattr(cb, "mxlmy", False):
+        env["q2"], env["q2l"] = W(cb.q2, lo2 + (0, 1)), W(cb.q2l, lo2 + (0, 1))
+    else:
+        z = ((1 - nb, g.ii + nb), (1 - nb, g.jj + nb), (0, kk + 1), (1, 2))
+        env["q2"], env["q2l"] = fx.FArray.zeros(z), fx.FArray.zeros(z)
+    if getattr(cb, "theta", None) is not None:
+        env["theta"] = W(cb.theta, lo2 + (1,))
+    else:
+        env["theta"] = fx.FArray.zeros(((1 - nb, g.ii + nb), (1 - nb, g.jj + nb), (1, kk)))
+    for name in ("scp2", "scp2i", "scuy", "scvx", "aspux", "aspvy"):
+        env[name] = W(getattr(cb, name), lo2)
+    b2 = ((1 - nb, g.ii + nb), (1 - nb, g.jj + nb))
+    for name in ("util1", "util2", "util3", "uflux", "vflux", "uflux2", "vflux2", "sold", "told", "q2old", "q2lold"):
+        env[name] = fx.FArray.zeros(b2, fill=np.nan)
+    # geopar.F90:822-871: the flux scratch is zero on the land faces that bound sea segments
+    for name in ("uflux", "vflux", "uflux2", "vflux2"):
+        env[name].fill(0.0)
+    env["trold"] = fx.FArray.zeros(b2 + ((1, max(cb.ntracr, 1)),), fill=np.nan)
+    env["xmin"], env["xmax"] = fx.FArray.zeros(((1, kk),), fill=np.nan), fx.FArray.zeros(((1, kk),), fill=np.nan)
+    trc = np.zeros(max(cb.ntracr, 1), dtype=np.int64)
+    for q, v in enumerate(list(cb.trcflg)[:cb.ntracr]):
+        trc[q] = v
+    env["trcflg"] = fx.FArray(trc, (1,))
+    env.update(advtyp=int(cb.advtyp), advflg=int(cb.advflg), btrmas=bool(cb.btrmas), nhybrd=int(cb.nhybrd if cb.nhybrd >= 0 else kk),
+               hybrid=bool(cb.hybrid), isopyc=bool(cb.isopyc), mxlmy=bool(getattr(cb, "mxlmy", False)), ntracr=int(cb.ntracr),
+               nstep=int(cb.nstep), diagno=bool(cb.diagno), delt1=float(cb.delt1), temdf2=float(cb.temdf2),
+               temdfc=float(cb.temdfc), thbase=float(cb.thbase), onemm=float(cb.onemm), r_init=float("nan"),
+               mxtrcr=max(cb.ntracr, 1), lpipe_tsadvc=False)
+    return env
+
+
+def compile_tsadvc(env, sigver=6):
+    path = os.path.join(REF, "mod_tsadvc.F90")
+    defines = ("RELO",) + _EOS_DEFINES[sigver]
+    compile_advem(env)
+    ranks = {"xctilr": (3, None, None, None, None, None),
+             "advem": (None, 2, 2, 2, 2, 2, 2, None, 2, 2, None, None),
+             "tsdff_1x": (2,), "tsdff_2x": (2, 2)}
+    skip = _SKIP + ("xcminr", "xcmaxr")
+    fx.compile_unit(path, "advem", env, defines=defines, skip_calls=skip, callee_ranks=ranks,
+                    drop_blocks=(r"allocated", r"lconserve"))
+    return fx.compile_unit(path, "tsadvc", env, defines=defines, skip_calls=skip, callee_ranks=ranks,
+                           drop_blocks=(r"allocated",))
+
+
+def run_tsadvc(env, m, n):
+    env["tsadvc"](m, n)
+    return env

@@ -135,3 +135,55 @@ def test_oracle_reproduces_the_digests_of_the_reference_text(oracle):
             key = f"advem{advtyp}:{itdm}x{jtdm}:nreg{nreg}:seed{seed}"
             assert gold[key] == digest(got, inner), key
         ot.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the driver tsadvc(m,n) itself (mod_tsadvc.F90:1708-2258): halo refresh, prolog, field selection, advem dispatch,
+# salinity range, diffusion (internal procedures tsdff_1x / tsdff_2x) and the equation-of-state sweep
+# (statement functions of stmt_fns.h) - the reference text against the oracle's orc_tsadvc
+# ---------------------------------------------------------------------------------------------------------
+DRIVER_CASES = [
+    # itdm, jtdm, kdm, nreg, ntracr, advtyp, extra
+    (26, 22, 3, 0, 1, 2, {}),                                    # FCT2, T + S + tracer, closed basin
+    (24, 20, 2, 1, 2, 1, {"trcflg": [0, 2]}),                    # MPDATA, a temperature tracer, periodic in i
+    (22, 24, 2, 3, 0, 4, {}),                                    # FCT4, doubly periodic
+    (20, 26, 2, 4, 1, 0, {}),                                    # PCM
+    (26, 22, 4, 0, 1, 2, {"nhybrd": 2}),                         # isopycnal layers below nhybrd: saln only
+    (24, 20, 3, 1, 0, 2, {"advflg": 1}),                         # advect th3d and S
+    (26, 22, 3, 0, 0, 2, {"isopyc": True, "hybrid": False, "nhybrd": 0}),   # layer 1 on smoothed fluxes
+    (26, 22, 3, 0, 2, 1, {"isopyc": True, "hybrid": False, "nhybrd": 0}),   # ... with tracers on uflx, vflx
+]
+
+
+def _run_reference_driver(cb, sea, g, m, n, sigver=6):
+    nb = g.nbdy
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+    env = rt.make_env(g.ii, g.jj, g.kdm)
+    rt.run_bigrid(env, depth, mapflg=4 if g.nreg in (3, 4) else 0)
+    rt.add_cb_arrays(env, cb)
+    rt.compile_tsadvc(env, sigver)
+    rt.run_tsadvc(env, m, n)
+    return env
+
+
+def _same(a, b, mask):
+    return np.array_equal(a[..., mask], b[..., mask])
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,ntracr,advtyp,extra", DRIVER_CASES)
+def test_tsadvc_of_the_reference_text_equals_oracle(oracle, itdm, jtdm, kdm, nreg, ntracr, advtyp, extra):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=11, m=m, n=n, advtyp=advtyp,
+                                     nstep=3, **extra)
+    ref = util.run_oracle(oracle, cb, sea, m, n)          # the oracle works on its own copy
+    before = cb.saln.copy()
+    env = _run_reference_driver(cb, sea, g, m, n)          # the reference text updates cb in place
+    inner = util.interior_sea(cb)
+    for name in ("temp", "saln", "th3d"):
+        assert _same(getattr(cb, name)[n - 1], ref[name][n - 1], inner), name
+    for q in range(ntracr):
+        assert _same(cb.tracer[q, n - 1], ref["tracer"][q, n - 1], inner), ("tracer", q)
+    assert np.array_equal(env["xmin"].a, ref["xmin"]) and np.array_equal(env["xmax"].a, ref["xmax"])
+    assert not _same(cb.saln[n - 1], before[n - 1], inner)
