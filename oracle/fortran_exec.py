@@ -559,8 +559,11 @@ class Translator:
             for item in _split_top(m.group(3)):
                 if "=" in item:
                     n, v = item.split("=", 1)
-                    if "(/" in v:
-                        raise NotImplementedError(st)
+                    if "(/" in v:       # a constant vector: real, parameter, dimension(7) :: c = (/ .. /)
+                        vals = _split_top(v[v.index("(/") + 2:v.rindex("/)")])
+                        self.arr[n.strip()] = 1
+                        self.emit(f"{_pyname(n.strip())} = FArray(np.array([{', '.join(self.ex(x) for x in vals)}], dtype=np.float64), (1,))")
+                        continue
                     self.emit(f"{_pyname(n.strip())} = {self.ex(v)}")
             return
         m = re.match(r"^parameter\s*\((.*)\)$", st)

@@ -187,3 +187,42 @@ def test_tsadvc_of_the_reference_text_equals_oracle(oracle, itdm, jtdm, kdm, nre
         assert _same(cb.tracer[q, n - 1], ref["tracer"][q, n - 1], inner), ("tracer", q)
     assert np.array_equal(env["xmin"].a, ref["xmin"]) and np.array_equal(env["xmax"].a, ref["xmax"])
     assert not _same(cb.saln[n - 1], before[n - 1], inner)
+
+
+# diffusion + equation of state (temdf2 > 0): tsdff_1x / tsdff_2x and the sig / tofsig statement functions of the
+# family the executable is compiled with (cpp: EOS_SIG0|EOS_SIG2 x EOS_7T|9T|12T|17T); mxlmy adds q2, q2l
+DIFF_CASES = [
+    # sigver, temdfc, nreg, ntracr, nhybrd, mxlmy
+    (6, 1.0, 0, 1, -1, False),     # 17-term sigma-2, temp diffused, th3d from sig(t,s)
+    (8, 0.5, 0, 0, -1, False),     # 12-term sigma-2: temp and th3d combined in density space, tofsig
+    (7, 0.0, 1, 2, -1, False),     # 12-term sigma-0: th3d diffused, temp from tofsig
+    (2, 1.0, 3, 0, 2, False),      # 7-term sigma-2, exactly isopycnal layers below nhybrd: th3d = theta
+    (4, 1.0, 0, 1, -1, True),      # 9-term sigma-2 with Mellor-Yamada fields
+]
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("sigver,temdfc,nreg,ntracr,nhybrd,mxlmy", DIFF_CASES)
+def test_tsadvc_with_diffusion_of_the_reference_text_equals_oracle(oracle, sigver, temdfc, nreg, ntracr, nhybrd, mxlmy):
+    m, n = 1, 2
+    itdm, jtdm, kdm = 24, 20, 3
+    cfg, sea, g, cb = util.make_diffusion_case(itdm, jtdm, kdm, sigver, temdfc, nreg=nreg, ntracr=ntracr, nhybrd=nhybrd,
+                                               seed=13, nstep=3, m=m, n=n)
+    if mxlmy:
+        util.add_q2(cfg, sea, g, cb, m, n)
+    ref = util.run_oracle(oracle, cb, sea, m, n)
+    env = _run_reference_driver(cb, sea, g, m, n, sigver)
+    inner = util.interior_sea(cb)
+    # sig of every family and tofsig of the 12-term family are bit-exact; tofsig of the 7/9-term families goes through
+    # atan2 / cos, whose last bit depends on the maths library (python's libm here, the C library in the oracle)
+    libm = sigver <= 4 and (temdfc < 1.0 or (0 <= nhybrd < kdm))
+    for name in ("temp", "saln", "th3d"):
+        a, b = getattr(cb, name)[n - 1], ref[name][n - 1]
+        if libm and name != "saln":
+            assert np.allclose(a[..., inner], b[..., inner], rtol=1e-12, atol=0), name
+        else:
+            assert _same(a, b, inner), name
+    for q in range(ntracr):
+        assert _same(cb.tracer[q, n - 1], ref["tracer"][q, n - 1], inner), ("tracer", q)
+    if mxlmy:
+        assert _same(cb.q2[n - 1, 1:-1], ref["q2"][n - 1, 1:-1], inner) and _same(cb.q2l[n - 1, 1:-1], ref["q2l"][n - 1, 1:-1], inner)
