@@ -90,6 +90,9 @@ class FArray:
         from the element's own index (callees that number it from 1 are told so by the harness)."""
         idx = tuple(idx) if isinstance(idx, tuple) else (idx,)
         lead = rank - 1
+        if len(idx) == lead and self.rank == lead:      # a 2-D array handed to xctilr(a(1-nbdy,1-nbdy),1,1,..): one slab
+            assert idx == self.lo
+            return FArray(self.a[None], self.lo + (1,))
         assert all(i == l for i, l in zip(idx[:lead], self.lo[:lead])), "element is not the start of a slab"
         R = self.rank
         flat = self.a.reshape((-1,) + self.a.shape[R - lead:])
@@ -196,7 +199,10 @@ def load_source(path, defines=(), include_dirs=()):
             st = re.sub(r"\b%s\b" % re.escape(name), text, st)
         st = re.sub(r"'[^']*'|\"[^\"]*\"", "''", st).lower()
         m = re.match(r"^(\d+)\s+(.*)$", st)
-        res.append((int(m.group(1)), m.group(2)) if m else (None, st))
+        lab, st = (int(m.group(1)), m.group(2)) if m else (None, st)
+        parts = [p.strip() for p in st.split(";") if p.strip()]     # several statements on one line
+        for k, p in enumerate(parts):
+            res.append((lab if k == len(parts) - 1 else None, p))
     return res
 
 
@@ -476,11 +482,21 @@ def _frange(a, b, c=1):
     return range(a, b + 1, c) if c > 0 else range(a, b - 1, c)
 
 
+def _dummy(a, bounds):
+    if not isinstance(a, FArray) or a.rank != len(bounds):
+        return a
+    lo = tuple(b[0] for b in bounds)
+    n = bounds[-1][1] - bounds[-1][0] + 1
+    if a.a.shape[0] > n > 0 or lo != a.lo:
+        return FArray(a.a[:n] if a.a.shape[0] > n > 0 else a.a, lo)
+    return a
+
+
 class FortranStop(Exception):
     pass
 
 
-RUNTIME = dict(np=np, _minval=lambda a: float(np.min(a)), _maxval=lambda a: float(np.max(a)), _div=_div, _pow=_pow, _max=_max, _min=_min, _mod=_mod, _sign=_sign, _int=_int, _nint=_nint,
+RUNTIME = dict(np=np, _dummy=_dummy, _minval=lambda a: float(np.min(a)), _maxval=lambda a: float(np.max(a)), _div=_div, _pow=_pow, _max=_max, _min=_min, _mod=_mod, _sign=_sign, _int=_int, _nint=_nint,
                _frange=_frange, _sqrt=math.sqrt, _exp=math.exp, _log=math.log, _atan2=math.atan2, _cos=math.cos,
                _sin=math.sin, _atan=math.atan, _tan=math.tan, _acos=math.acos, _asin=math.asin, FArray=FArray,
                FortranStop=FortranStop)
@@ -719,6 +735,15 @@ class Translator:
                     continue
                 known = n in self.arr
                 self.arr[n] = len(bounds)
+                explicit = all(":" not in b or b.count(":") == 1 for b in bounds) and not any(b.strip() in (":", "*") for b in bounds)
+                if n in self.args and explicit and self.host is None:
+                    # a dummy array has the bounds ITS declaration gives it: lower bounds, and the extent of the last
+                    # dimension (the actual argument may be a longer sequence-associated view)
+                    bb = []
+                    for b in bounds:
+                        lo, hi = (b.split(":") + [None])[:2] if ":" in b else ("1", b)
+                        bb.append(f"({self.ex(lo)}, {self.ex(hi)})")
+                    self.emit(f"{_pyname(n)} = _dummy({_pyname(n)}, ({', '.join(bb)},))")
                 if not known and n not in self.args and "allocatable" not in attrs and all(":" not in b or b.count(":") == 1 for b in bounds) \
                         and not any(b.strip() in (":", "*") for b in bounds):
                     bb = []

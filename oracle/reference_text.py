@@ -6,8 +6,8 @@ tile: bigrid (masks, sea-only neighbour indices, segment tables) and the advecti
 tests/golden/make_reference_text_vectors.py to pin the CPU oracle against what the reference text computes.
 
 The only things supplied from outside the reference text are the module variables (dimensions, arrays) and the
-communication calls of mod_xc on ONE tile: xctilr for a closed or periodic domain (fill with vland = 0 beyond a
-closed edge, wrap across a periodic one: mod_xc_sm.h:1337-1428), xcmaxr/xcminr (identity), xcsync/xcstop.
+trivial communication calls of mod_xc on ONE tile: xcmaxr/xcminr (identity), xcsync/xcstop.  xctilr is the
+reference's own single-tile text (mod_xc_sm.h), compiled with ARCTIC for nreg = 2.
 """
 from __future__ import annotations
 
@@ -26,36 +26,26 @@ def available():
 
 
 def _xctilr_factory(env):
+    """xctilr of the reference's own mod_xc_sm.h (the single-tile mod_xc: closed / periodic :1337-1428, with the
+    arctic fold :1172-1335 when the executable is compiled with ARCTIC, i.e. for nreg = 2), translated on first use.
+    It reads nbdy, idm, jdm, ii, jj, nreg and vland from the module variables."""
+    text = {}
+
     def xctilr(a, l1, ld, mh, nh, itype):
-        """single tile, closed (vland = 0 outside) or periodic (wrap); `a` is a 2-D or 3-D FArray"""
-        nb, ii, jj = env["nbdy"], env["ii"], env["jj"]
-        per_i = env["nreg"] in (1, 3)
-        per_j = env["nreg"] in (3, 4)
-        if env["nreg"] == 2:
-            raise NotImplementedError("arctic xctilr is not provided to the reference text")
-        # (a 3-D argument is the view from the element the caller passed on: its first slab is l1 = 1)
-        st = a.a if a.rank == 2 else a.a[l1 - 1:l1 - 1 + ld]
-        st = st.reshape((-1,) + st.shape[-2:])
-        mh, nh = min(mh, nb), min(nh, nb)
-        r0, c0 = nb, nb           # store index of (i,j) = (1,1)
-        for s in st:
-            # north / south
-            for h in range(1, nh + 1):
-                if per_j:
-                    s[r0 - h, c0:c0 + ii] = s[r0 + jj - h, c0:c0 + ii]
-                    s[r0 + jj - 1 + h, c0:c0 + ii] = s[r0 + h - 1, c0:c0 + ii]
-                else:
-                    s[r0 - h, c0:c0 + ii] = 0.0
-                    s[r0 + jj - 1 + h, c0:c0 + ii] = 0.0
-            # east / west over the rows just filled
-            for h in range(1, mh + 1):
-                rows = slice(r0 - nh, r0 + jj + nh)
-                if per_i:
-                    s[rows, c0 - h] = s[rows, c0 + ii - h]
-                    s[rows, c0 + ii - 1 + h] = s[rows, c0 + h - 1]
-                else:
-                    s[rows, c0 - h] = 0.0
-                    s[rows, c0 + ii - 1 + h] = 0.0
+        arctic = env["nreg"] == 2
+        if arctic not in text:
+            sub = {k: env[k] for k in ("nbdy", "idm", "jdm", "ii", "jj")}
+            sub.update(nreg=env["nreg"], vland=0.0)              # vland: mod_xc.F90 (real, save :: vland = 0.0)
+            fx.compile_unit(os.path.join(REF, "mod_xc_sm.h"), "xctilr", sub, defines=("RELO",) + (("ARCTIC",) if arctic else ()),
+                            skip_calls=("xctmr0", "xctmr1"))
+            text[arctic] = sub
+        sub = text[arctic]
+        sub["nreg"] = env["nreg"]
+        if a.rank == 2:
+            a = fx.FArray(a.a[None], a.lo + (1,))
+        elif a.lo[2] != 1:                                        # the dummy a(:,:,ld) numbers its slabs from 1
+            a = fx.FArray(a.a, a.lo[:2] + (1,))
+        sub["xctilr"](a, l1, ld, mh, nh, itype)
     return xctilr
 
 
@@ -125,9 +115,10 @@ def run_bigrid(env, depth, mapflg=0):
 
 def compile_advem(env):
     path = os.path.join(REF, "mod_tsadvc.F90")
-    for name in ("advem_pcm", "advem_mpdata", "advem_fct2", "advem_fct4"):
+    for name in ("advem_pcm", "advem_mpdata", "advem_fct2", "advem_fct4", "advem_fct2c"):
         if name not in env:
-            fx.compile_unit(path, name, env, skip_calls=_SKIP, inout_calls=("xcmaxr", "xcminr"))
+            fx.compile_unit(path, name, env, skip_calls=_SKIP, inout_calls=("xcmaxr", "xcminr"),
+                            callee_ranks={"xctilr": (3, None, None, None, None, None)}, drop_blocks=(r"allocated",))
 
 
 def run_advem(env, advtyp, fld, fldc, u, v, fco, fcn, posdef, scal, scali, dt2):

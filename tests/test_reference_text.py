@@ -152,6 +152,10 @@ DRIVER_CASES = [
     (24, 20, 3, 1, 0, 2, {"advflg": 1}),                         # advect th3d and S
     (26, 22, 3, 0, 0, 2, {"isopyc": True, "hybrid": False, "nhybrd": 0}),   # layer 1 on smoothed fluxes
     (26, 22, 3, 0, 2, 1, {"isopyc": True, "hybrid": False, "nhybrd": 0}),   # ... with tracers on uflx, vflx
+    (26, 22, 2, 0, 1, 2, {"btrmas": True}),                      # advem_fct2c: five sub-cycled iterations, onetamas
+    (24, 20, 2, 1, 0, 2, {"btrmas": True}),
+    (28, 24, 2, 2, 1, 2, {}),                                    # across the arctic: xctilr of mod_xc_sm.h with ARCTIC
+    (28, 24, 2, 2, 0, 1, {}),
 ]
 
 
@@ -175,8 +179,12 @@ def _same(a, b, mask):
 @pytest.mark.parametrize("itdm,jtdm,kdm,nreg,ntracr,advtyp,extra", DRIVER_CASES)
 def test_tsadvc_of_the_reference_text_equals_oracle(oracle, itdm, jtdm, kdm, nreg, ntracr, advtyp, extra):
     m, n = 1, 2
-    cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=11, m=m, n=n, advtyp=advtyp,
-                                     nstep=3, **extra)
+    if nreg == 2:
+        cfg, sea, g, cb = util.make_arctic_case(itdm, jtdm, kdm, ntracr=ntracr, seed=11, m=m, n=n, advtyp=advtyp, nstep=3,
+                                                **extra)
+    else:
+        cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=11, m=m, n=n, advtyp=advtyp,
+                                         nstep=3, **extra)
     ref = util.run_oracle(oracle, cb, sea, m, n)          # the oracle works on its own copy
     before = cb.saln.copy()
     env = _run_reference_driver(cb, sea, g, m, n)          # the reference text updates cb in place
