@@ -213,3 +213,40 @@ def compile_tsadvc(env, sigver=6):
 def run_tsadvc(env, m, n):
     env["tsadvc"](m, n)
     return env
+
+
+# ---------------------------------------------------------------------------------------------------------
+# mod_asselin.F90: asselin_save(m,n) :28-82 and asselin_filter(m,n) :84-286 (with stmt_fns.h)
+# ---------------------------------------------------------------------------------------------------------
+def add_asselin_arrays(env, cb):
+    """module arrays of mod_cb_arrays that mod_asselin touches on top of add_cb_arrays (wrapped, not copied)"""
+    g = cb.geom
+    nb, kk = g.nbdy, g.kdm
+    lo2 = (1 - nb, 1 - nb)
+    W = lambda a, lo: fx.FArray(a, lo)   # noqa: E731
+    for name in ("dpo",):
+        env[name] = W(getattr(cb, name), lo2 + (1, 1))
+    for name in ("onetao", "pbavg"):
+        env[name] = W(getattr(cb, name), lo2 + (1,))
+    env["pbot"] = W(cb.pbot, lo2)
+    for name in ("otemp", "osaln", "oth3d"):
+        env[name] = W(getattr(cb, name), lo2 + (1,))
+    if cb.ntracr:
+        env["otracer"] = W(cb.otracer, lo2 + (1, 1))
+    else:
+        env["otracer"] = fx.FArray.zeros(((1 - nb, g.ii + nb), (1 - nb, g.jj + nb), (1, kk), (1, 1)))
+    if getattr(cb, "mxlmy", False):
+        env["oq2"], env["oq2l"] = W(cb.oq2, lo2 + (0,)), W(cb.oq2l, lo2 + (0,))
+    else:
+        z = ((1 - nb, g.ii + nb), (1 - nb, g.jj + nb), (0, kk + 1))
+        env["oq2"], env["oq2l"] = fx.FArray.zeros(z), fx.FArray.zeros(z)
+    env.update(oneta0=float(cb.oneta0), ra2fac=float(cb.ra2fac), onem=9806.0)
+    return env
+
+
+def compile_asselin(env, sigver=6):
+    path = os.path.join(REF, "mod_asselin.F90")
+    defines = ("RELO",) + _EOS_DEFINES[sigver]
+    ranks = {"xctilr": (3, None, None, None, None, None)}
+    for name in ("asselin_save", "asselin_filter"):
+        fx.compile_unit(path, name, env, defines=defines, skip_calls=_SKIP, callee_ranks=ranks)

@@ -234,3 +234,61 @@ def test_tsadvc_with_diffusion_of_the_reference_text_equals_oracle(oracle, sigve
         assert _same(cb.tracer[q, n - 1], ref["tracer"][q, n - 1], inner), ("tracer", q)
     if mxlmy:
         assert _same(cb.q2[n - 1, 1:-1], ref["q2"][n - 1, 1:-1], inner) and _same(cb.q2l[n - 1, 1:-1], ref["q2l"][n - 1, 1:-1], inner)
+
+
+# mod_asselin.F90: asselin_save and asselin_filter of the reference text
+ASSELIN_CASES = [(6, 2, {}, True), (8, 0, {"advflg": 1}, False), (2, 1, {"nhybrd": 1}, False),
+                 (7, 0, {"isopyc": True, "hybrid": False, "nhybrd": 0}, False)]
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("sigver,ntracr,extra,mxlmy", ASSELIN_CASES)
+def test_asselin_of_the_reference_text_equals_oracle(oracle, sigver, ntracr, extra, mxlmy):
+    import copy
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(26, 22, 3, nreg=0, ntracr=ntracr, seed=5, **extra)
+    if mxlmy:
+        util.add_q2(cfg, sea, g, cb, m, n)
+    util.add_asselin(cfg, sea, g, cb, m, n, sigver=sigver)
+    msk = util.interior_sea(cb)
+    nb = g.nbdy
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+
+    def reference(which):
+        c = copy.deepcopy(cb)
+        env = rt.make_env(g.ii, g.jj, g.kdm)
+        rt.run_bigrid(env, depth.copy())
+        rt.add_cb_arrays(env, c)
+        rt.add_asselin_arrays(env, c)
+        rt.compile_asselin(env, sigver)
+        env[which](m, n)
+        return c, env
+
+    # asselin_save
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot.asselin_save(m, n, 1)
+    c, env = reference("asselin_save")
+    for name in ("oneta", "onetao"):
+        assert np.array_equal(ot.f64(name), getattr(c, name), equal_nan=True), name
+    for name in ("otemp", "osaln", "oth3d") + (("otracer",) if ntracr else ()) + (("oq2", "oq2l") if mxlmy else ()):
+        a, b = ot.f64(name), getattr(c, name)
+        if name in ("oq2", "oq2l"):
+            a, b = a[1:-1], b[1:-1]
+        assert np.array_equal(a[..., msk], b[..., msk]), name
+    ot.close()
+    # asselin_filter from the same starting state
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot.asselin_filter(m, n)
+    c, env = reference("asselin_filter")
+    libm = sigver <= 4 and ("nhybrd" in extra or extra.get("advflg") == 1 or extra.get("isopyc"))
+    for name in ("oneta", "dp", "temp", "saln", "th3d") + (("tracer",) if ntracr else ()) + (("q2", "q2l") if mxlmy else ()):
+        a, b = ot.f64(name), getattr(c, name)
+        if name in ("q2", "q2l"):
+            a, b = a[:, 1:-1], b[:, 1:-1]
+        if libm and name == "temp":
+            assert util.rel_err(a[m - 1], b[m - 1], msk) < 1e-13, name
+        else:
+            assert np.array_equal(a[..., msk], b[..., msk], equal_nan=True), name
+    assert not np.array_equal(c.saln[m - 1, 0][msk], cb.saln[m - 1, 0][msk])
+    ot.close()
