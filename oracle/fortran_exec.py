@@ -15,7 +15,7 @@ Supported: fixed/free form with `&` continuations, `!` comments, cpp (#if define
 #define NAME text), do / labelled do ... continue, block and one-line if, assignment (scalars, array elements,
 whole arrays), call, return, parameter constants in declarations, intrinsics min max abs mod sign sqrt real int
 nint float dble exp log atan2 cos sin, integer division, array-element actual arguments (sequence association:
-the callee sees the array from that element on).  Not supported (raises): goto, where, derived types, I/O
+the callee sees the array from that element on).  `if (c) go to L` forward to `L continue` at the same block level.  Not supported (raises): other goto, where, derived types, I/O
 (write/print/read/open/close/flush are skipped), modules as such (module variables are entries of the
 environment dictionary the caller supplies).
 """
@@ -555,6 +555,8 @@ class Translator:
         self.lines, self.ind = [], 1
         self.assigned = set()
         self.do_labels = []   # stack of labels of open labelled do loops (None for unlabelled)
+        self.declared = set()  # scalars the unit declares itself (locals of an internal procedure, not the host's)
+        self.goto_labels = []  # stack of (label, indentation) of open forward jumps
 
     def emit(self, s):
         self.lines.append("    " * self.ind + s)
@@ -563,6 +565,15 @@ class Translator:
         return expr(s, self.arr, self.funcs)
 
     def stmt(self, st):
+        m = re.match(r"^if\s*\((.*)\)\s*go\s*to\s*(\d+)$", st)
+        if m:
+            # a forward jump over the statements up to `label continue` at the same block level (cnuity.F90:749, 978):
+            # they become the body of `if not (condition)`
+            self.emit(f"if not {self.ex(m.group(1))}:")
+            self.ind += 1
+            self.emit("pass")
+            self.goto_labels.append((int(m.group(2)), self.ind))
+            return
         if re.match(r"^(go\s*to|where|forall|select|cycle|exit)\b", st):
             raise NotImplementedError(st)
         if _IO.match(st) or st in ("continue",):
@@ -701,6 +712,18 @@ class Translator:
     def declarations(self):
         """arrays declared in the unit: dummies get their rank; locals with explicit bounds are allocated (after the
         parameter constants, which may size them)"""
+        # an undefined local scalar may be read in Fortran (cnuity.F90:1006 reads iflip, which is only set when thkdf4
+        # is used, to fill an array nobody reads): NaN / a sentinel instead of a Python error.  Ahead of the parameter
+        # constants, which overwrite the entry of a name that is typed first and given its value later.
+        for _, st in self.body:
+            m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*)$", st)
+            if not m or "parameter" in m.group(2).split("::")[0] or "dimension" in m.group(2).split("::")[0]:
+                continue
+            undef = "-987654321" if m.group(1) == "integer" else ("False" if m.group(1) == "logical" else "float('nan')")
+            for ent in _split_top(m.group(2).split("::", 1)[-1]):
+                self.declared.add(ent)
+                if re.match(r"^[a-z_]\w*$", ent) and ent not in self.args and (ent not in self.arr or self.host is None):
+                    self.emit(f"{_pyname(ent)} = {undef}")
         self.params_done = True
         for _, st in self.body:
             m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*?)::(.*)$", st)
@@ -769,6 +792,10 @@ class Translator:
             while lab is not None and self.do_labels and self.do_labels[-1] == lab:
                 self.ind -= 1
                 self.do_labels.pop()
+            if lab is not None and self.goto_labels and self.goto_labels[-1][0] == lab:
+                assert self.goto_labels[-1][1] == self.ind, "a jump into or out of a block"
+                self.ind -= 1
+                self.goto_labels.pop()
         if self.host is not None:
             return None
         # internal procedures (host association): nested functions that see the host's variables; what they assign
@@ -778,7 +805,7 @@ class Translator:
             t = Translator(iname, iargs, ibody, self.arr, module_scalars=self.modsc, funcs=self.funcs, host=self, **self.kw)
             t.ind = 2
             t.source()
-            shared = sorted(_pyname(n) for n in t.assigned if (n in self.assigned or n in self.args) and n not in iargs)
+            shared = sorted(_pyname(n) for n in t.assigned if (n in self.assigned or n in self.args) and n not in iargs and n not in t.declared)
             inner_src.append(f"    def {_pyname(iname)}({', '.join(_pyname(a) for a in iargs)}):")
             if shared:
                 inner_src.append("        nonlocal " + ", ".join(shared))

@@ -250,3 +250,48 @@ def compile_asselin(env, sigver=6):
     ranks = {"xctilr": (3, None, None, None, None, None)}
     for name in ("asselin_save", "asselin_filter"):
         fx.compile_unit(path, name, env, defines=defines, skip_calls=_SKIP, callee_ranks=ranks)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cnuity(m,n) (cnuity.F90:14-1424)
+# ---------------------------------------------------------------------------------------------------------
+def add_cnuity_arrays(env, cb, st, mxlkta=False):
+    """module variables cnuity touches on top of add_cb_arrays: `st` is the dictionary of tests/util.add_cnuity
+    (arrays in the Fortran layout; wrapped, not copied, so cnuity updates them in place).  Scratch that the
+    reference allocates on its first call (masku .. dpmn) and module scratch (utotm .. p) start as r_init = NaN."""
+    g = cb.geom
+    nb, kk = g.nbdy, g.kdm
+    lo2 = (1 - nb, 1 - nb)
+    b2 = ((1 - nb, g.ii + nb), (1 - nb, g.jj + nb))
+    W = lambda a, lo: fx.FArray(a, lo)   # noqa: E731
+    for name in ("dp", "dpo", "u", "v", "dpu", "dpv"):
+        env[name] = W(st[name], lo2 + (1, 1))
+    for name in ("ubavg", "vbavg", "dpmixl", "uflx", "vflx", "uflxav", "vflxav", "dpav"):
+        env[name] = W(st[name], lo2 + (1,))
+    for name in ("pbot", "depthu", "depthv"):
+        env[name] = W(st[name], lo2)
+    for name in ("thkdf4u", "thkdf4v"):
+        env[name] = W(st[name], lo2) if name in st else fx.FArray.zeros(b2)
+    for name in ("utotm", "vtotm", "utotn", "vtotn", "util1", "util2", "util3", "uflux", "vflux", "uflux2", "vflux2",
+                 "pold", "oneta_u", "oneta_v", "dpmold", "onetacnt"):
+        env[name] = fx.FArray.zeros(b2, fill=np.nan)
+    # geopar.F90:822-871: the flux scratch is zero on the land faces that bound sea segments
+    for name in ("uflux", "vflux", "uflux2", "vflux2", "utotm", "vtotm"):
+        env[name].fill(0.0)
+    for name in ("masku", "maskv", "iuopn", "ivopn"):
+        env[name] = fx.FArray.zeros(b2, dtype=np.int64)
+    env["dpmn"] = fx.FArray.zeros(((1 - nb, g.jj + nb),), fill=np.nan)
+    env["p"] = fx.FArray.zeros(b2 + ((1, kk + 1),), fill=np.nan)
+    env["p"].a[0] = 0.0                                        # p(:,:,1) = 0 always (geopar / inicon)
+    env["wveli"] = fx.FArray.zeros(b2 + ((1, kk + 1),))         # mod_floats (synflt = .false.: never touched)
+    env["onetamas"] = fx.FArray.zeros(b2 + ((1, 2),), fill=np.nan)
+    thk = st.get("_thkdf")
+    env.update(mxlkta=bool(mxlkta), synflt=False, wvelfl=False, onem=9806.0, onecm=98.06, qonem=1.0 / 9806.0,
+               epsil=1.0e-11, ra2fac=0.125, lpipe_cnuity=False,
+               thkdf4=float(thk[0]) if thk and thk[1] else 0.0, thkdf2=float(thk[0]) if thk and not thk[1] else 0.0)
+    return env
+
+
+def compile_cnuity(env):
+    return fx.compile_unit(os.path.join(REF, "cnuity.F90"), "cnuity", env, skip_calls=_SKIP + ("xcminr", "xcmaxr"),
+                           callee_ranks={"xctilr": (3, None, None, None, None, None)}, drop_blocks=(r"allocated",))

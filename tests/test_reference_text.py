@@ -292,3 +292,70 @@ def test_asselin_of_the_reference_text_equals_oracle(oracle, sigver, ntracr, ext
             assert np.array_equal(a[..., msk], b[..., msk], equal_nan=True), name
     assert not np.array_equal(c.saln[m - 1, 0][msk], cb.saln[m - 1, 0][msk])
     ot.close()
+
+
+# cnuity(m,n) of cnuity.F90: loop 76 (FCT of dp), loop 77 + bottom restoring, the
+# interface-depth diffusion (thkdf4 in both sweep directions, thkdf2), mxlkta, the Asselin tail
+CNUITY_CASES = [
+    # itdm, jtdm, kdm, nreg, m, n, isopyc, thkdf, bih, nstep, mxlkta
+    (30, 24, 4, 0, 1, 2, False, 0.0, True, 3, False),      # closed basin with islands
+    (26, 22, 3, 3, 2, 1, False, 0.0, True, 3, False),      # doubly periodic, slots swapped
+    (24, 28, 3, 1, 1, 2, True, 0.0, True, 3, False),       # periodic in i, isopyc: dpmixl(n) = dp(1,n)
+    (26, 20, 2, 4, 1, 2, False, 0.0, True, 3, False),      # closed f-plane (periodic in j)
+    (30, 24, 5, 0, 1, 2, False, 0.01, True, 4, False),     # biharmonic interface-depth diffusion, downward sweep
+    (30, 24, 5, 0, 1, 2, False, 0.01, True, 7, False),     # ... upward sweep
+    (24, 28, 4, 1, 1, 2, True, 0.01, True, 3, True),       # ... with isopyc (mxlkta is then irrelevant)
+    (26, 22, 3, 3, 1, 2, False, 0.02, False, 2, False),    # Laplacian
+    (30, 24, 5, 0, 1, 2, False, 0.01, True, 4, True),      # hybrid .and. mxlkta: dpmixl follows the coordinates
+    (30, 26, 3, 2, 1, 2, False, 0.0, True, 3, False),      # across the arctic
+    (30, 26, 4, 2, 1, 2, False, 0.01, True, 4, False),     # ... with the interface-depth diffusion
+]
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,m,n,isopyc,thkdf,bih,nstep,mxlkta", CNUITY_CASES)
+def test_cnuity_of_the_reference_text_equals_oracle(oracle, itdm, jtdm, kdm, nreg, m, n, isopyc, thkdf, bih, nstep, mxlkta):
+    extra = dict(isopyc=True, hybrid=False, nhybrd=0) if isopyc else {}
+    if nreg == 2:
+        cfg, sea, g, cb = util.make_arctic_case(itdm, jtdm, kdm, seed=23, m=m, n=n, nstep=nstep, **extra)
+        st = util.arctic_halos_cnuity(g, util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=thkdf, bih=bih))
+    else:
+        cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, seed=23, m=m, n=n, nstep=nstep, **extra)
+        st = util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=thkdf, bih=bih)
+    if mxlkta:
+        util.deepen_dpmixl(st, n)
+    got = util.run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=isopyc, mxlkta=mxlkta)     # on its own copy
+    before = st["dp"].copy()
+    nb = g.nbdy
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+    env = rt.make_env(g.ii, g.jj, g.kdm)
+    rt.run_bigrid(env, depth, mapflg=4 if nreg in (3, 4) else 0)
+    assert env["nreg"] == nreg
+    rt.add_cb_arrays(env, cb)
+    rt.add_cnuity_arrays(env, cb, st, mxlkta=mxlkta)
+    rt.compile_cnuity(env)
+    env["cnuity"](m, n)                                                                       # updates st in place
+    inner = util.interior_sea(cb)
+    sea6 = cb.ip != 0
+    iu_in, iv_in = np.zeros_like(inner), np.zeros_like(inner)
+    iu_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iu[nb:nb + g.jj, nb:nb + g.ii] != 0
+    iv_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iv[nb:nb + g.jj, nb:nb + g.ii] != 0
+    for k in range(kdm):
+        assert np.array_equal(got["dp"][n - 1, k][inner], st["dp"][n - 1, k][inner]), ("dp.n", k)
+        assert np.array_equal(got["dp"][m - 1, k][inner], st["dp"][m - 1, k][inner]), ("dp.m", k)
+        assert np.array_equal(got["dpo"][m - 1, k][inner], st["dpo"][m - 1, k][inner]), ("dpo.m", k)
+        assert np.array_equal(got["dpo"][n - 1, k][inner], st["dpo"][n - 1, k][inner]), ("dpo.n", k)
+        assert np.array_equal(got["uflx"][k][iu_in], st["uflx"][k][iu_in]), ("uflx", k)
+        assert np.array_equal(got["vflx"][k][iv_in], st["vflx"][k][iv_in]), ("vflx", k)
+        assert np.array_equal(got["p"][k + 1][inner], env["p"].a[k + 1][inner]), ("p", k)
+        assert np.array_equal(got["dpav"][k][inner], st["dpav"][k][inner]), ("dpav", k)
+        assert np.array_equal(got["uflxav"][k][iu_in], st["uflxav"][k][iu_in]), ("uflxav", k)
+        assert np.array_equal(got["vflxav"][k][iv_in], st["vflxav"][k][iv_in]), ("vflxav", k)
+    assert np.array_equal(got["utotn"][iu_in], env["utotn"].a[iu_in])
+    assert np.array_equal(got["vtotn"][iv_in], env["vtotn"].a[iv_in])
+    assert np.array_equal(got["dpmixl"][..., inner], st["dpmixl"][..., inner])
+    assert np.array_equal(got["dpmold"][inner], env["dpmold"].a[inner])
+    assert not np.array_equal(before[n - 1, 0][inner], st["dp"][n - 1, 0][inner])
+    if thkdf:
+        assert not np.array_equal(before[n - 1, kdm - 1][inner], st["dp"][n - 1, kdm - 1][inner])
