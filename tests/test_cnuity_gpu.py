@@ -266,3 +266,30 @@ def test_cnuity_across_the_arctic_on_tiles(oracle):
     for ts, cb in zip(tss, cbs):
         _check(ts, cb.geom, cb, ref, m, n, kdm, g1=g1)
     close_tiles(grp, tss)
+
+
+# the device against the REFERENCE'S OWN SOURCE TEXT: tests/golden/from_reference_text.json holds digests of what
+# cnuity.F90 computes when executed as written (oracle/fortran_exec.py, tests/golden/make_reference_text_vectors.py)
+# on the configurations of the tests above
+import json as _json
+import os as _os
+
+import reftext_cases as _rc
+
+_REFTEXT = _json.load(open(_os.path.join(_os.path.dirname(__file__), "golden", "from_reference_text.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_rc.CNUITY))
+def test_cnuity_device_reproduces_the_reference_text(name):
+    cfg, sea, g, cb, st, m, n, isopyc, mxlkta = _rc.cnuity_case(name)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_cnuity_state(st, m, n)
+    kw = {}
+    if "_thkdf" in st:
+        kw["thkdf4" if st["_thkdf"][1] else "thkdf2"] = st["_thkdf"][0]
+    ts.cnuity_device(m, n, mxlkta=mxlkta, **kw)
+    dp = np.stack([ts.download(cabi.F_DP, 1), ts.download(cabi.F_DP, 2)])
+    d = _rc.cnuity_digest(cb, m, n, dp, ts.download(cabi.F_UFLX, 1), ts.download(cabi.F_VFLX, 1), ts.download(cabi.F_P, 1),
+                          ts.download(cabi.F_DPMIXL, n)[0] if (isopyc or mxlkta) else None)
+    ts.close()
+    assert d == _REFTEXT[name], name

@@ -892,3 +892,28 @@ def test_asselin_device_matches_oracle(oracle, sigver, ntracr, nreg, extra):
                 assert np.array_equal(dev[:, msk], ref[:, msk]), (name, slot)
     assert not np.array_equal(ts.download(cabi.F_SALN, m)[0][msk], cb.saln[m - 1, 0][msk])
     ts.close(); ot.close()
+
+
+# ---------------------------------------------------------------------------------------
+# the device against the REFERENCE'S OWN SOURCE TEXT: tests/golden/from_reference_text.json holds digests of what
+# mod_asselin.F90 computes when executed as written (oracle/fortran_exec.py, tests/golden/make_reference_text_vectors.py)
+# on the configurations of test_asselin_device_matches_oracle
+# ---------------------------------------------------------------------------------------
+import reftext_cases as _rc
+
+_REFTEXT = _json.load(open(_os.path.join(_os.path.dirname(__file__), "golden", "from_reference_text.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_rc.ASSELIN))
+def test_asselin_device_reproduces_the_reference_text(name):
+    cfg, sea, g, cb, m, n = _rc.asselin_case(name)
+    ts = pkg.Tsadvc(cb)
+    ts.upload_asselin_state(m, n)
+    ts.asselin_filter_device(m, n)
+    flds = {nm: np.stack([ts.download(fld, 1), ts.download(fld, 2)])
+            for fld, nm in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln"), (cabi.F_TH3D, "th3d"), (cabi.F_DP, "dp"))}
+    if cb.ntracr:
+        flds["tracer"] = np.stack([np.stack([ts.download(cabi.F_TRACER, 1, ktr=q + 1), ts.download(cabi.F_TRACER, 2, ktr=q + 1)])
+                                   for q in range(cb.ntracr)])
+    ts.close()
+    assert _rc.asselin_digest(cb, m, flds) == _REFTEXT[name], name

@@ -359,3 +359,101 @@ def test_cnuity_of_the_reference_text_equals_oracle(oracle, itdm, jtdm, kdm, nre
     assert not np.array_equal(before[n - 1, 0][inner], st["dp"][n - 1, 0][inner])
     if thkdf:
         assert not np.array_equal(before[n - 1, kdm - 1][inner], st["dp"][n - 1, kdm - 1][inner])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the frozen vectors of tests/golden/tsadvc_golden.json - the ones the CUDA path must reproduce in
+# tests/test_parity_gpu.py::test_golden_vectors_on_device - are what the REFERENCE TEXT computes
+# ---------------------------------------------------------------------------------------------------------
+def _golden_cases():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden
+    return make_golden
+
+
+def reference_text_digest_of_golden_case(name):
+    mg = _golden_cases()
+    kind, kw = mg.CASES[name]
+    cfg, sea, g, cb = mg.build(kind, kw)
+    _run_reference_driver(cb, sea, g, 1, 2, int(getattr(cb, "sigver", 6)))     # updates cb in place
+    flds = dict(temp=cb.temp, saln=cb.saln, th3d=cb.th3d, tracer=cb.tracer if cb.ntracr else None)
+    return mg.digest(flds, util.interior_sea(cb), 2)
+
+
+def _reference_asselin_filter(name):
+    import reftext_cases as rc
+    cfg, sea, g, cb, m, n = rc.asselin_case(name)
+    nb = g.nbdy
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+    env = rt.make_env(g.ii, g.jj, g.kdm)
+    rt.run_bigrid(env, depth, mapflg=4 if g.nreg in (3, 4) else 0)
+    rt.add_cb_arrays(env, cb)
+    rt.add_asselin_arrays(env, cb)
+    rt.compile_asselin(env, int(cb.sigver))
+    env["asselin_filter"](m, n)
+    return rc.asselin_digest(cb, m, dict(temp=cb.temp, saln=cb.saln, th3d=cb.th3d, dp=cb.dp, tracer=cb.tracer))
+
+
+def _reference_cnuity(name):
+    import reftext_cases as rc
+    cfg, sea, g, cb, st, m, n, isopyc, mxlkta = rc.cnuity_case(name)
+    nb = g.nbdy
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+    env = rt.make_env(g.ii, g.jj, g.kdm)
+    rt.run_bigrid(env, depth, mapflg=4 if g.nreg in (3, 4) else 0)
+    rt.add_cb_arrays(env, cb)
+    rt.add_cnuity_arrays(env, cb, st, mxlkta=mxlkta)
+    rt.compile_cnuity(env)
+    env["cnuity"](m, n)
+    return rc.cnuity_digest(cb, m, n, st["dp"], st["uflx"], st["vflx"], env["p"].a,
+                            st["dpmixl"][n - 1] if (isopyc or mxlkta) else None)
+
+
+def more_reference_vectors():
+    """for tests/golden/make_reference_text_vectors.py: digests of the reference text on the frozen-vector cases of
+    tsadvc and on the asselin / cnuity cases of tests/reftext_cases.py"""
+    import reftext_cases as rc
+    out = {"golden:" + name: reference_text_digest_of_golden_case(name) for name in sorted(_golden_cases().CASES)}
+    out.update({name: _reference_asselin_filter(name) for name in rc.ASSELIN})
+    out.update({name: _reference_cnuity(name) for name in rc.CNUITY})
+    return out
+
+
+def test_oracle_reproduces_the_asselin_and_cnuity_digests_of_the_reference_text(oracle):
+    """everywhere (also where the reference tree is absent)"""
+    import reftext_cases as rc
+    gold = json.load(open(GOLD))
+    for name in rc.ASSELIN:
+        cfg, sea, g, cb, m, n = rc.asselin_case(name)
+        ot = util.oracle_tile_from_cb(oracle, cb, sea)
+        ot.asselin_filter(m, n)
+        flds = {k: ot.f64(k).copy() for k in ("temp", "saln", "th3d", "dp")}
+        flds["tracer"] = ot.f64("tracer").copy() if cb.ntracr else None
+        assert rc.asselin_digest(cb, m, flds) == gold[name], name
+        ot.close()
+    for name in rc.CNUITY:
+        cfg, sea, g, cb, st, m, n, isopyc, mxlkta = rc.cnuity_case(name)
+        got = util.run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=isopyc, mxlkta=mxlkta)
+        d = rc.cnuity_digest(cb, m, n, got["dp"], got["uflx"], got["vflx"], got["p"],
+                             got["dpmixl"][n - 1] if (isopyc or mxlkta) else None)
+        assert d == gold[name], name
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("name", ["box_fct2", "periodic_mpdata_tracers", "fct2c_btrmas", "diffusion_12t_mixed", "arctic_fct2"])
+def test_frozen_vectors_equal_the_reference_text_live(name):
+    frozen = json.load(open(os.path.join(os.path.dirname(GOLD), "tsadvc_golden.json")))
+    assert reference_text_digest_of_golden_case(name) == frozen[name]
+
+
+def test_frozen_vectors_equal_the_committed_digests_of_the_reference_text():
+    """everywhere: tsadvc_golden.json (checked on the device by test_golden_vectors_on_device and on the oracle by
+    test_oracle.py) holds exactly the digests the reference text produced (from_reference_text.json, `golden:` keys)"""
+    frozen = json.load(open(os.path.join(os.path.dirname(GOLD), "tsadvc_golden.json")))
+    gold = json.load(open(GOLD))
+    names = [k[len("golden:"):] for k in gold if k.startswith("golden:")]
+    assert sorted(names) == sorted(frozen)
+    for name in names:
+        assert gold["golden:" + name] == frozen[name], name
