@@ -1,8 +1,10 @@
 """oracle/reference_text.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 Executes routines of the reference's own source text (/root/reference/*.F90) through oracle/fortran_exec.py on one
-tile: bigrid (masks, sea-only neighbour indices, segment tables) and the advection schemes of mod_tsadvc.F90
-(advem_pcm, advem_mpdata, advem_fct2, advem_fct4).  Used by tests/test_reference_text.py and
+tile: bigrid (masks, sea-only neighbour indices, segment tables), xctilr of mod_xc_sm.h (closed, periodic, ARCTIC),
+the advection schemes of mod_tsadvc.F90 (advem_pcm, advem_mpdata, advem_fct2, advem_fct4, advem_fct2c), its driver
+tsadvc(m,n) with tsdff_1x/2x and the statement functions of stmt_fns.h (all eight EOS families), asselin_save /
+asselin_filter of mod_asselin.F90 and cnuity(m,n) of cnuity.F90.  Used by tests/test_reference_text.py and
 tests/golden/make_reference_text_vectors.py to pin the CPU oracle against what the reference text computes.
 
 The only things supplied from outside the reference text are the module variables (dimensions, arrays) and the

@@ -1,7 +1,7 @@
 /*
  * oracle/tsadvc_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
- * PARITY UNPINNED (see tsadvc_oracle.h): no golden vectors exist upstream and
- * no Fortran compiler exists here; fidelity is by construction + invariants.
+ * PARITY PINNED AGAINST THE REFERENCE'S SOURCE TEXT executed by oracle/fortran_exec.py
+ * (see tsadvc_oracle.h; no reference binary: no Fortran compiler exists here).
  *
  * Sweep-by-sweep C99 restatement of /root/reference/mod_tsadvc.F90 and the
  * pieces of bigrid.F90 / mod_xc_sm.h / mod_xc_mp.h / geopar.F90 that path

@@ -6,14 +6,22 @@
  *   advem_fct4, tsdff_1x/2x), bigrid.F90 (masks, sea-only neighbours, segment
  *   tables), mod_xc_sm.h / mod_xc_mp.h (xctilr), geopar.F90:311-340 (metrics).
  *
- * PARITY UNPINNED: the reference ships no golden vectors, no tests and no input
- * decks, and no Fortran compiler exists in this image, so this restatement
- * cannot be checked against the reference binary.  Its fidelity is argued by
- * construction (same sweeps, same margins, same operation order, same scratch
- * arrays, each function citing the Fortran lines it follows), by an independent
- * second restatement in numpy (oracle/np_restatement.py) that must agree with
- * it bit-for-bit, and by the invariants the reference itself relies on
- * (SURVEY.md section 4).
+ * PARITY PINNED AGAINST THE REFERENCE'S SOURCE TEXT, not against a reference
+ * binary: the reference ships no golden vectors, no tests and no input decks,
+ * and no Fortran compiler exists in this image or on the GPU boxes, so there is
+ * no oracle/_ref.  Instead oracle/fortran_exec.py translates the Fortran of
+ * /root/reference (bigrid.F90, mod_xc_sm.h xctilr incl. ARCTIC, mod_tsadvc.F90
+ * with stmt_fns.h, mod_asselin.F90, cnuity.F90) statement by statement into
+ * Python - it knows the language, not the algorithms - and
+ * tests/test_reference_text.py demands that this restatement reproduce what the
+ * reference text computes BIT FOR BIT (unfused IEEE double, i.e. a
+ * -ffp-contract=off build; tofsig of the 7/9-term fits to 1e-12 because of
+ * libm's atan2/cos); tests/golden/from_reference_text.json keeps digests of
+ * those runs for machines without /root/reference.  On top: an independent
+ * second restatement in numpy (oracle/np_restatement.py) that must agree bit
+ * for bit, and the invariants the reference relies on.
+ * A compiled-reference pin is one `bash fortran/build_ref.sh` away on any
+ * machine with gfortran (tests/golden/from_reference.json).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.

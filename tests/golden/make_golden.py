@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Regenerates tests/golden/tsadvc_golden.json (TEST INFRASTRUCTURE).
 
-The reference ships no golden vectors and cannot be compiled here (no Fortran compiler), so these
-are NOT reference outputs: they freeze the bits of the CPU oracle (oracle/tsadvc_oracle.c) on small
-seeded cases at a moment when it agreed bit-for-bit with the independent numpy restatement
-(oracle/np_restatement.py).  They guard against silent drift of the oracle, of the synthetic
-generator and - through tests/test_parity_gpu.py::test_golden_vectors_on_device - of the CUDA path.
+The reference ships no golden vectors and cannot be compiled here (no Fortran compiler).  These digests freeze
+the bits of the CPU oracle (oracle/tsadvc_oracle.c) on small seeded cases - and they ARE what the reference's own
+source text computes on those cases: tests/golden/make_reference_text_vectors.py executes mod_tsadvc.F90 as written
+(oracle/fortran_exec.py) on every case below and tests/test_reference_text.py demands that its digests
+(from_reference_text.json, `golden:` keys) equal this file, live where /root/reference exists and from the committed
+file everywhere.  Through tests/test_parity_gpu.py::test_golden_vectors_on_device the CUDA path must reproduce them.
 
     python tests/golden/make_golden.py        # rewrites the json next to this file
 """

@@ -607,7 +607,7 @@ _REF_FIXTURE = os.path.join(os.path.dirname(__file__), "golden", "from_reference
 
 @pytest.mark.skipif(not os.path.exists(_REF_FIXTURE),
                     reason="tests/golden/from_reference.json absent: no Fortran compiler has produced it yet "
-                           "(fortran/build_ref.sh); parity stays unpinned")
+                           "(fortran/build_ref.sh); the pin is the executed reference text (tests/test_reference_text.py)")
 def test_reference_fixture(oracle):
     """the oracle reproduces the bits of the reference's own tsadvc on the golden cases"""
     import json

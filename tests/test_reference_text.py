@@ -206,6 +206,9 @@ DIFF_CASES = [
     (7, 0.0, 1, 2, -1, False),     # 12-term sigma-0: th3d diffused, temp from tofsig
     (2, 1.0, 3, 0, 2, False),      # 7-term sigma-2, exactly isopycnal layers below nhybrd: th3d = theta
     (4, 1.0, 0, 1, -1, True),      # 9-term sigma-2 with Mellor-Yamada fields
+    (1, 0.5, 0, 0, -1, False),     # 7-term sigma-0, temp and th3d combined: sig and tofsig
+    (3, 0.0, 1, 0, -1, False),     # 9-term sigma-0, th3d diffused: tofsig
+    (5, 1.0, 4, 1, -1, False),     # 17-term sigma-0
 ]
 
 
