@@ -611,14 +611,17 @@ class Translator:
         if m:
             parts = _split_top(m.group(3))
             rng = ", ".join(self.ex(p) for p in parts)
-            self.emit(f"for {_pyname(m.group(2))} in _frange({rng}):")
+            self.nloops = getattr(self, "nloops", 0) + 1
+            rname, var = f"_r{self.nloops}", _pyname(m.group(2))
+            self.emit(f"{rname} = _frange({rng})")
+            self.emit(f"for {var} in {rname}:")
             self.ind += 1
             self.emit("pass")
-            self.do_labels.append(int(m.group(1)) if m.group(1) else None)
+            self.assigned.add(m.group(2))
+            self.do_labels.append((int(m.group(1)) if m.group(1) else None, var, rname))
             return
         if re.match(r"^end\s*do$", st):
-            self.ind -= 1
-            self.do_labels.pop()
+            self.close_do()
             return
         m = re.match(r"^(else\s*if|elseif|if)\s*\(", st)
         if m and m.group(1) == "if" and "if" in self.arr:
@@ -709,6 +712,12 @@ class Translator:
             self.assigned.add(lhs)
             self.emit(f"{_pyname(lhs)} = {self.ex(rhs)}")
 
+    def close_do(self):
+        """end of a do loop: the variable is left one step past the last iteration, as in Fortran"""
+        _, var, rname = self.do_labels.pop()
+        self.ind -= 1
+        self.emit(f"{var} = {rname}.start + len({rname}) * {rname}.step")
+
     def declarations(self):
         """arrays declared in the unit: dummies get their rank; locals with explicit bounds are allocated (after the
         parameter constants, which may size them)"""
@@ -789,9 +798,8 @@ class Translator:
                 skipping = 1
                 continue
             self.stmt(st)
-            while lab is not None and self.do_labels and self.do_labels[-1] == lab:
-                self.ind -= 1
-                self.do_labels.pop()
+            while lab is not None and self.do_labels and self.do_labels[-1][0] == lab:
+                self.close_do()
             if lab is not None and self.goto_labels and self.goto_labels[-1][0] == lab:
                 assert self.goto_labels[-1][1] == self.ind, "a jump into or out of a block"
                 self.ind -= 1
@@ -805,7 +813,7 @@ class Translator:
             t = Translator(iname, iargs, ibody, self.arr, module_scalars=self.modsc, funcs=self.funcs, host=self, **self.kw)
             t.ind = 2
             t.source()
-            shared = sorted(_pyname(n) for n in t.assigned if (n in self.assigned or n in self.args) and n not in iargs and n not in t.declared)
+            shared = sorted(_pyname(n) for n in t.assigned if (n in self.assigned or n in self.args or n in self.declared) and n not in iargs and n not in t.declared)
             inner_src.append(f"    def {_pyname(iname)}({', '.join(_pyname(a) for a in iargs)}):")
             if shared:
                 inner_src.append("        nonlocal " + ", ".join(shared))

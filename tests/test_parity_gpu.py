@@ -917,3 +917,13 @@ def test_asselin_device_reproduces_the_reference_text(name):
                                    for q in range(cb.ntracr)])
     ts.close()
     assert _rc.asselin_digest(cb, m, flds) == _REFTEXT[name], name
+
+
+def test_config1_on_device_reproduces_the_reference_text():
+    """BASELINE.json configs[0] at full size (150 x 150 x 22 box basin, FCT2 T + S, one tile) through the host-array
+    entry against the digest of the executed reference text"""
+    import test_reference_text as T
+    cfg, sea, g, cb = T.config1_case()
+    got, before, launches = _run_host_path(cb, 1, 2)
+    assert launches > 0
+    assert T.config1_digest(cb, got["temp"], got["saln"]) == _REFTEXT[T.CONFIG1]

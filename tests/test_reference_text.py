@@ -383,6 +383,34 @@ def reference_text_digest_of_golden_case(name):
     return mg.digest(flds, util.interior_sea(cb), 2)
 
 
+# BASELINE.json configs[0] at its full size: the 150 x 150 x 22 box basin, FCT2 T + S, one tile - the first case of
+# tests/test_parity_gpu.py::CASES (75 s of executed reference text: generated once, not run live)
+CONFIG1 = "config1:box_150x150x22_fct2"
+
+
+def config1_case():
+    m, n = 1, 2
+    return util.make_case(150, 150, 22, nreg=0, ntracr=0, seed=13, m=m, n=n, advtyp=2, nstep=3)
+
+
+def config1_digest(cb, temp, saln):
+    mg = _golden_cases()
+    return mg.digest(dict(temp=temp, saln=saln), util.interior_sea(cb), 2)
+
+
+def reference_text_digest_of_config1():
+    cfg, sea, g, cb = config1_case()
+    _run_reference_driver(cb, sea, g, 1, 2)
+    return config1_digest(cb, cb.temp, cb.saln)
+
+
+def test_oracle_reproduces_config1_of_the_reference_text(oracle):
+    gold = json.load(open(GOLD))
+    cfg, sea, g, cb = config1_case()
+    ref = util.run_oracle(oracle, cb, sea, 1, 2)
+    assert config1_digest(cb, ref["temp"], ref["saln"]) == gold[CONFIG1]
+
+
 def _reference_asselin_filter(name):
     import reftext_cases as rc
     cfg, sea, g, cb, m, n = rc.asselin_case(name)
@@ -419,6 +447,7 @@ def more_reference_vectors():
     tsadvc and on the asselin / cnuity cases of tests/reftext_cases.py"""
     import reftext_cases as rc
     out = {"golden:" + name: reference_text_digest_of_golden_case(name) for name in sorted(_golden_cases().CASES)}
+    out[CONFIG1] = reference_text_digest_of_config1()
     out.update({name: _reference_asselin_filter(name) for name in rc.ASSELIN})
     out.update({name: _reference_cnuity(name) for name in rc.CNUITY})
     return out
