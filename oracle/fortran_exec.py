@@ -137,7 +137,7 @@ def load_source(path, defines=(), include_dirs=()):
         i += 1
         s = ln.strip()
         if s.startswith("#"):
-            d = s[1:].strip()
+            d = re.sub(r"/\*.*?\*/", "", s[1:]).strip()
             m = re.match(r"(ifdef|ifndef|if|elif)\b\s*(.*)$", d)
 
             def cpp_true(e):
@@ -195,8 +195,12 @@ def load_source(path, defines=(), include_dirs=()):
     # macro substitution, lower case (strings are never needed), labels
     res = []
     for st in stmts:
-        for name, text in macros.items():
-            st = re.sub(r"\b%s\b" % re.escape(name), text, st)
+        for _ in range(4):            # a macro may expand to another macro (BARRIER_MP -> BARRIER -> call ...)
+            before = st
+            for name, text in macros.items():
+                st = re.sub(r"\b%s\b" % re.escape(name), text, st)
+            if st == before:
+                break
         st = re.sub(r"'[^']*'|\"[^\"]*\"", "''", st).lower()
         m = re.match(r"^(\d+)\s+(.*)$", st)
         lab, st = (int(m.group(1)), m.group(2)) if m else (None, st)
@@ -724,6 +728,14 @@ class Translator:
         # an undefined local scalar may be read in Fortran (cnuity.F90:1006 reads iflip, which is only set when thkdf4
         # is used, to fill an array nobody reads): NaN / a sentinel instead of a Python error.  Ahead of the parameter
         # constants, which overwrite the entry of a name that is typed first and given its value later.
+        saved = set()          # `save a, b` / `integer, save :: a`: such a variable lives in the environment the caller
+        for _, st in self.body:    # supplies (with the value its `data` statement gives it) and is never reset here
+            m = re.match(r"^save\s+(.*)$", st)
+            if m:
+                saved |= {x.strip() for x in m.group(1).split(",")}
+            m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*?)::(.*)$", st)
+            if m and re.search(r"\bsave\b", m.group(2)):
+                saved |= {re.sub(r"\(.*", "", x).strip() for x in _split_top(m.group(3))}
         for _, st in self.body:
             m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*)$", st)
             if not m or "parameter" in m.group(2).split("::")[0] or "dimension" in m.group(2).split("::")[0]:
@@ -731,7 +743,8 @@ class Translator:
             undef = "-987654321" if m.group(1) == "integer" else ("False" if m.group(1) == "logical" else "float('nan')")
             for ent in _split_top(m.group(2).split("::", 1)[-1]):
                 self.declared.add(ent)
-                if re.match(r"^[a-z_]\w*$", ent) and ent not in self.args and (ent not in self.arr or self.host is None):
+                if re.match(r"^[a-z_]\w*$", ent) and ent not in self.args and ent not in saved and \
+                        (ent not in self.arr or self.host is None):
                     self.emit(f"{_pyname(ent)} = {undef}")
         self.params_done = True
         for _, st in self.body:
@@ -827,6 +840,23 @@ class Translator:
         # statement functions and parameters come first in self.lines; internal procedures may use them, so they go
         # after the declarations block: Python resolves the names when the internal procedure is called
         return "\n".join(head + ["    pass"] + inner_src + self.lines) + "\n"
+
+
+def compile_slice(path, unit, first, last, name, env, defines=("RELO",), **kw):
+    """a run of statements of `subroutine unit` as a parameterless subroutine `name`: from the first statement that
+    matches the regular expression `first` up to (not including) the first later statement that matches `last`.
+    For routines whose head cannot be executed (xcspmd: file input, MPI start-up) but whose tail is plain Fortran."""
+    stmts = load_source(path, defines)
+    _, body, _ = extract_unit(stmts, unit)
+    k0 = next(k for k, (_, st) in enumerate(body) if re.search(first, st))
+    k1 = next(k for k, (_, st) in enumerate(body) if k > k0 and re.search(last, st))
+    arrays = {k: v.rank for k, v in env.items() if isinstance(v, FArray)}
+    t = Translator(name.lower(), [], body[k0:k1], arrays, module_scalars=[k for k, v in env.items() if not isinstance(v, FArray)], **kw)
+    src = t.source()
+    for k, v in RUNTIME.items():
+        env.setdefault(k, v)
+    exec(compile(src, f"<{name}: part of {unit} of {path}>", "exec"), env)
+    return src
 
 
 def compile_unit(path, name, env, defines=("RELO",), extra_arrays=None, **kw):

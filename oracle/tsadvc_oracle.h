@@ -10,7 +10,8 @@
  * binary: the reference ships no golden vectors, no tests and no input decks,
  * and no Fortran compiler exists in this image or on the GPU boxes, so there is
  * no oracle/_ref.  Instead oracle/fortran_exec.py translates the Fortran of
- * /root/reference (bigrid.F90, mod_xc_sm.h xctilr incl. ARCTIC, mod_tsadvc.F90
+ * /root/reference (bigrid.F90, xctilr of mod_xc_sm.h and - on threads - of
+ * mod_xc_mp.h incl. ARCTIC, mod_tsadvc.F90
  * with stmt_fns.h, mod_asselin.F90, cnuity.F90) statement by statement into
  * Python - it knows the language, not the algorithms - and
  * tests/test_reference_text.py demands that this restatement reproduce what the

@@ -489,3 +489,71 @@ def test_frozen_vectors_equal_the_committed_digests_of_the_reference_text():
     assert sorted(names) == sorted(frozen)
     for name in names:
         assert gold["golden:" + name] == frozen[name], name
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the MULTI-TILE xctilr of mod_xc_mp.h (:4664-4987; ARCTIC :4114-4662) as written, one thread per tile in the
+# reference's SHMEM flavour, its neighbour tables from the reference's own xcspmd text (oracle/reference_text_mp.py):
+# the oracle's orc_world_xctilr - against which the product's exchange schedule and its device pack / unpack are
+# tested (tests/test_oracle.py, tests/test_parity_gpu.py) - leaves the same halos, and both leave what the
+# single-tile text of mod_xc_sm.h leaves on the global array
+# ---------------------------------------------------------------------------------------------------------
+MP_CASES = [
+    # ipr, jpr, nreg, itdm, jtdm, itypes, flavour
+    (2, 2, 0, 48, 36, (1,), "MPI"),            # closed
+    (2, 2, 0, 48, 36, (1,), "SHMEM"),
+    (4, 2, 1, 48, 36, (1,), "MPI"),            # periodic in i
+    (4, 2, 1, 48, 36, (1,), "SHMEM"),
+    (3, 1, 3, 45, 30, (1,), "MPI"),            # f-plane: periodic in both, jpr = 1, ragged in i
+    (3, 1, 3, 45, 30, (1,), "SHMEM"),
+    (2, 3, 0, 47, 41, (1,), "MPI"),            # ragged in both
+    (2, 2, 2, 48, 36, (1, 13, 14, 2, 3), "MPI"),   # across the arctic: the top row exchanges the fold with its twin tiles
+    (4, 2, 2, 48, 36, (1, 13, 14), "MPI"),
+    (2, 1, 2, 48, 36, (1, 13, 14), "MPI"),
+]
+
+
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("ipr,jpr,nreg,itdm,jtdm,itypes,flavour", MP_CASES)
+def test_multi_tile_xctilr_of_the_reference_text_equals_oracle(oracle, ipr, jpr, nreg, itdm, jtdm, itypes, flavour):
+    import reference_text_mp as rmp
+    pkg = util.pkg
+    kk, mh, nh = 3, 5, 5
+    rng = np.random.default_rng(4)
+    tiles = pkg.partition(itdm, jtdm, kk, ipr, jpr, nreg)
+    g1 = pkg.partition(itdm, jtdm, kk, 1, 1, nreg)[0]
+    nb = g1.nbdy
+    world = rmp.World(tiles, ipr, jpr, nreg, itdm, jtdm, kk, flavour=flavour)
+    ots = [oracle.tile(g, 0) for g in tiles]
+    o1 = oracle.tile(g1, 0)
+    for itype in itypes:
+        core = rng.standard_normal((kk, jtdm, itdm))
+        core[rng.random(core.shape) < 0.1] = 0.0            # vland inside the field
+        def fresh():
+            out = []
+            for g in tiles:
+                a = np.full((kk, g.nrows, g.ncols), np.nan)
+                a[:, nb:nb + g.jj, nb:nb + g.ii] = core[:, g.j0:g.j0 + g.jj, g.i0:g.i0 + g.ii]
+                out.append(a)
+            return out
+        ref, got = fresh(), fresh()
+        world.xctilr(ref, 1, kk, mh, nh, itype)                               # the reference text on the tiles
+        oracle.world_xctilr(ipr, jpr, ots, got, 1, kk, mh, nh, itype)         # the oracle on the tiles
+        # the reference's single-tile text on the global array
+        glob = np.full((kk, g1.nrows, g1.ncols), np.nan)
+        glob[:, nb:nb + jtdm, nb:nb + itdm] = core
+        env = rt.make_env(g1.ii, g1.jj, kk, nreg=nreg)
+        env["xctilr"](fx_array3(glob, nb), 1, kk, mh, nh, itype)
+        for g, a, b in zip(tiles, ref, got):
+            assert np.array_equal(a, b, equal_nan=True), (itype, g.mproc, g.nproc)     # incl. what stays untouched
+            loc = a[:, nb - nh:nb + g.jj + nh, nb - mh:nb + g.ii + mh]
+            assert not np.isnan(loc).any()
+            win = glob[:, g.j0 + nb - nh:g.j0 + nb + g.jj + nh, g.i0 + nb - mh:g.i0 + nb + g.ii + mh]
+            assert np.array_equal(loc, win), (itype, g.mproc, g.nproc, "tiling invariance of the reference text")
+    for o in ots + [o1]:
+        o.close()
+
+
+def fx_array3(a, nb):
+    import fortran_exec as fx
+    return fx.FArray(a, (1 - nb, 1 - nb, 1))
