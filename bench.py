@@ -164,7 +164,7 @@ class CpuOracle:
         if ntracr:
             cb.tracer = np.stack([f4(cabi.F_TRACER, ktr=q + 1) for q in range(ntracr)])
         self.ot = util.oracle_tile_from_cb(orc, cb, sea)
-        del cb
+        self.cb, self.sea, self.geom = cb, sea, g
         self.calls = 0
 
     def run(self, calls, threads):
@@ -181,6 +181,39 @@ class CpuOracle:
 
     def close(self):
         self.ot.close()
+
+
+def reference_text_rate(o, calls, threads):
+    """the REFERENCE'S OWN SOURCE TEXT, compiled (oracle/fortran_to_c.py: mod_tsadvc.F90, bigrid.F90 and xctilr of
+    mod_xc_sm.h translated statement by statement to C, `!$OMP PARALLEL DO ... SCHEDULE(STATIC,jblk)` carried over;
+    oracle/_ref/libref_text_*_omp.so, built where /root/reference exists and shipped with the snapshot), on the
+    sample the port was just timed on: seconds per tsadvc(m,n) call"""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import reference_text as rt
+    import reference_text_c as rc
+    so = rc.RefTextC.so_path(6, False, True)
+    if not rt.available() and not (os.path.exists(so) and os.path.exists(so[:-3] + ".json")):
+        raise FileNotFoundError("oracle/_ref holds no compiled reference text (build() makes it where /root/reference exists)")
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    lib = rc.RefTextC(6, False, openmp=True, flags=rc.RefTextC.TIMED_FLAGS)
+    g, cb, sea = o.geom, o.cb, o.sea
+    nb = g.nbdy
+    env = rt.make_env(g.ii, g.jj, g.kdm)
+    env["jblk"] = (g.jj + 2 * nb + threads - 1) // threads            # mod_dimensions.F90:143
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+    u = [np.zeros_like(depth) for _ in range(3)]
+    lib.run(env, "bigrid", depth, 0, *u)
+    cb.nstep = 1
+    rt.add_cb_arrays(env, cb)
+    out = []
+    for c in range(calls + 1):
+        m, n = (1, 2) if c % 2 == 0 else (2, 1)
+        t0 = time.perf_counter()
+        lib.run(env, "tsadvc", m, n)
+        out.append(time.perf_counter() - t0)
+    return out[1:]
 
 
 def run_reference(args):
@@ -200,9 +233,25 @@ def run_reference(args):
     sec = sum(timed) / len(timed)
     value = idm * jdm * nlay / sec
     one = o.run(2, 1)[-1]                             # relo_one analogue: one thread, same sample
-    o.close()
     extra = {"one_thread": {"value": idm * jdm * nlay / one, "unit": UNIT, "cores": 1,
                             "sample": f"{nlay} of {kdm} layers, 1 timed call after 1 warm-up"}}
+    kind, impl_note = "port", "C oracle -O2 -fopenmp schedule(static,jblk)"
+    port_value = value
+    try:
+        tt = reference_text_rate(o, min(args.steps, 5), cores)
+        tsec = sum(tt) / len(tt)
+        extra["reference_text"] = {"value": idm * jdm * nlay / tsec, "unit": UNIT, "cores": cores, "kind": "reference",
+                                   "ms_per_step": tsec * 1e3,
+                                   "sample": f"{nlay} of {kdm} layers, {len(tt)} timed tsadvc calls after 1 warm-up: mod_tsadvc.F90 "
+                                             f"as written, translated statement by statement to C with its OpenMP directives "
+                                             f"(oracle/fortran_to_c.py), gcc -O2 -march=x86-64-v3 -fopenmp"}
+        extra["port"] = {"value": port_value, "unit": UNIT, "cores": cores, "kind": "port"}
+        if idm * jdm * nlay / tsec > value:           # the line reports the FASTER of the two CPU arms
+            value, sec, kind = idm * jdm * nlay / tsec, tsec, "reference"
+            impl_note = "the reference text compiled (oracle/_ref), gcc -O2 -fopenmp schedule(static,jblk)"
+    except Exception as e:  # noqa: BLE001
+        extra["reference_text"] = {"skipped": repr(e)[:300]}
+    o.close()
     if not args.no_full_kdm:
         try:
             import psutil
@@ -219,7 +268,8 @@ def run_reference(args):
         except Exception as e:  # noqa: BLE001
             extra["full_kdm_call"] = {"skipped": repr(e)[:200]}
     sample = (f"{nlay} of {kdm} layers of {args.workload} ({idm}x{jdm}) per step, "
-              f"{len(timed)} timed tsadvc calls, C oracle -O2 -fopenmp schedule(static,jblk), {cores} threads")
+              f"{len(timed)} timed tsadvc calls, {impl_note}, {cores} threads; the faster of the port and the compiled "
+              f"reference text (both in extra)")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -230,7 +280,7 @@ def run_reference(args):
                                alg_bytes_per_call(idm // ipr, (jdm + jpr - 1) // jpr, kdm, args.advtyp, args.ntracr)),
         "step_is": f"one tsadvc call over {nlay} of the {kdm} layers (bounded sample; layers are independent): "
                    f"value = {nlay} layers' cells / ms_per_step",
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "extra": extra,
     }

@@ -121,8 +121,9 @@ def _strip_comment(line):
     return "".join(out).rstrip()
 
 
-def load_source(path, defines=(), include_dirs=()):
-    """logical, lower-cased statements of a Fortran file after cpp: list of (label or None, text)"""
+def load_source(path, defines=(), include_dirs=(), keep_omp=False):
+    """logical, lower-cased statements of a Fortran file after cpp: list of (label or None, text).  keep_omp: the
+    `!$OMP` directives come back as statements `$omp ...` (for the C backend, oracle/fortran_to_c.py)"""
     import os
     defined = {d: "" for d in defines}
     macros = {}
@@ -177,7 +178,11 @@ def load_source(path, defines=(), include_dirs=()):
     # comments, continuations (free form: trailing &; the next line may start with &)
     stmts, cur = [], ""
     for ln in out_lines:
-        ln = _strip_comment(ln)
+        omp = re.match(r"^\s*!(\$omp\b.*)$", ln, flags=re.I)
+        if omp and keep_omp:
+            ln = omp.group(1) if not cur else re.sub(r"^\$omp", "", omp.group(1), flags=re.I)
+        else:
+            ln = _strip_comment(ln)
         if not ln.strip():
             continue
         body = ln.strip()

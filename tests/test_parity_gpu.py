@@ -271,6 +271,16 @@ def test_full_size_glb_layers_match_oracle(oracle, advtyp, ntracr):
         dev = ts.download(cabi.F_TRACER, n, ktr=1, k0=k0, nk=nk)
         for k in range(nk):
             assert np.array_equal(dev[k][msk], ref["tracer"][0, n - 1, k][msk])
+    # the same two layers against the COMPILED REFERENCE TEXT itself (oracle/_ref), when this machine has it
+    import copy
+    cbt = copy.deepcopy(cb2)
+    if util.run_compiled_reference_text(cbt, sea, m, n):
+        for fld, name in ((cabi.F_TEMP, "temp"), (cabi.F_SALN, "saln")):
+            dev = ts.download(fld, n, k0=k0, nk=nk)
+            assert np.array_equal(dev[:, msk], getattr(cbt, name)[n - 1][:, msk]), (name, "reference text")
+        if ntracr:
+            dev = ts.download(cabi.F_TRACER, n, ktr=1, k0=k0, nk=nk)
+            assert np.array_equal(dev[:, msk], cbt.tracer[0, n - 1][:, msk]), "tracer vs reference text"
     # remaining layers: properties
     for k in (1, kdm):
         s = ts.download(cabi.F_SALN, n, k0=k, nk=1)[0]
@@ -927,3 +937,26 @@ def test_config1_on_device_reproduces_the_reference_text():
     got, before, launches = _run_host_path(cb, 1, 2)
     assert launches > 0
     assert T.config1_digest(cb, got["temp"], got["saln"]) == _REFTEXT[T.CONFIG1]
+
+
+@pytest.mark.parametrize("itdm,jtdm,kdm,nreg,ntracr,advtyp,extra", CASES + [(90, 64, 2, 2, 1, 2, {}), (90, 61, 3, 4, 1, 2, {"btrmas": True})])
+def test_tsadvc_host_path_matches_the_compiled_reference_text(itdm, jtdm, kdm, nreg, ntracr, advtyp, extra):
+    """the device against the reference text compiled (oracle/_ref), nothing in between: every scheme and driver option
+    of CASES, across the arctic, and advem_fct2c"""
+    import copy
+    m, n = 1, 2
+    if nreg == 2:
+        cfg, sea, g, cb = util.make_arctic_case(itdm, jtdm, kdm, ntracr=ntracr, seed=13, m=m, n=n, advtyp=advtyp, nstep=3, **extra)
+    else:
+        cfg, sea, g, cb = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=13, m=m, n=n, advtyp=advtyp, nstep=3, **extra)
+    cbt = copy.deepcopy(cb)
+    if not util.run_compiled_reference_text(cbt, sea, m, n):
+        pytest.skip("oracle/_ref holds no compiled reference text on this machine")
+    got, before, launches = _run_host_path(cb, m, n)
+    assert launches > 0
+    msk = util.interior_sea(cb)
+    for name in ("temp", "saln", "th3d"):
+        assert np.array_equal(got[name][n - 1][:, msk], getattr(cbt, name)[n - 1][:, msk]), name
+    for q in range(ntracr):
+        assert np.array_equal(got["tracer"][q, n - 1][:, msk], cbt.tracer[q, n - 1][:, msk]), ("tracer", q)
+    assert not np.array_equal(got["saln"][n - 1, 0][msk], before["saln"][n - 1, 0][msk])

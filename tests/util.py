@@ -291,3 +291,33 @@ def run_oracle_cnuity(oracle, cb, sea, st, m, n, isopyc=False, mxlkta=False):
                                          "uflxav", "vflxav", "dpav", "dpmold")}
     ot.close()
     return out
+
+
+def run_compiled_reference_text(cb, sea, m, n, sigver=6):
+    """tsadvc(m,n) of the COMPILED REFERENCE TEXT (oracle/_ref/libref_text_*.so: mod_tsadvc.F90, bigrid.F90 and xctilr of
+    mod_xc_sm.h translated statement by statement to C by oracle/fortran_to_c.py where /root/reference exists) on the
+    host arrays of cb, in place.  False when no library can be had on this machine (then the caller has the oracle only)."""
+    import os, sys
+    root = os.path.join(os.path.dirname(__file__), "..")
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import reference_text as rt
+    import reference_text_c as rc
+    g = cb.geom
+    arctic = g.nreg == 2
+    so = rc.RefTextC.so_path(sigver, arctic)
+    if not rt.available() and not (os.path.exists(so) and os.path.exists(so[:-3] + ".json")):
+        return False
+    try:
+        lib = rc.RefTextC(sigver, arctic)
+    except (OSError, RuntimeError) as e:
+        print("compiled reference text unavailable:", repr(e)[:200])
+        return False
+    nb = g.nbdy
+    env = rt.make_env(g.ii, g.jj, g.kdm)
+    depth = np.zeros((g.nrows, g.ncols))
+    depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea != 0, 100.0, 0.0)
+    lib.run(env, "bigrid", depth, 4 if g.nreg in (3, 4) else 0, *[np.zeros_like(depth) for _ in range(3)])
+    assert env["nreg"] == g.nreg, (env["nreg"], g.nreg)
+    rt.add_cb_arrays(env, cb)
+    lib.run(env, "tsadvc", m, n)
+    return True
