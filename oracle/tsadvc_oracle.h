@@ -18,7 +18,10 @@
  * reference text computes BIT FOR BIT (unfused IEEE double, i.e. a
  * -ffp-contract=off build; tofsig of the 7/9-term fits to 1e-12 because of
  * libm's atan2/cos); tests/golden/from_reference_text.json keeps digests of
- * those runs for machines without /root/reference.  On top: an independent
+ * those runs for machines without /root/reference.  A second backend,
+ * oracle/fortran_to_c.py, compiles the same text to C (oracle/_ref/*.so): equal to
+ * the interpreter on every routine, equal to this restatement at the full
+ * GLBb0.08 horizontal size, and what the GPU tests compare the device with.  On top: an independent
  * second restatement in numpy (oracle/np_restatement.py) that must agree bit
  * for bit, and the invariants the reference relies on.
  * A compiled-reference pin is one `bash fortran/build_ref.sh` away on any
