@@ -14,7 +14,7 @@ the same statements), max/min keep the first argument on a tie like gfortran's i
 multiplies left to right like the interpreter.
 
 Every Fortran name becomes f_<name> (j0, y1, index ... are libm / libc names).  Module variables are C globals set
-from the interpreter's environment (bind()): a scalar is `int` / `double`, an array `double *` / `int64_t *` with its
+from the interpreter's environment (bind()): a scalar is `int` / `double`, an array `double *` / `int32_t *` with its
 lower bounds and extents in f_<name>_lo[] / f_<name>_n[].
 """
 from __future__ import annotations
@@ -335,7 +335,7 @@ class CUnit:
         for a in self.args:
             ct, b, _, _ = self.decl.get(a, ("double", None, None, ""))
             if b is not None:
-                ps.append(f"{'int64_t' if ct == 'int' else 'double'} *f_{a}")
+                ps.append(f"{'int32_t' if ct == 'int' else 'double'} *f_{a}")
             else:
                 ps.append(f"{ct} f_{a}")
         return f"void f_{self.name}({', '.join(ps) or 'void'})"
@@ -347,7 +347,7 @@ class CUnit:
             if self.is_array_dummy(a):
                 ct, b, _, _ = self.decl[a]
                 lo, nn = self.bounds_c(b)
-                self.scope[a] = Arr(f"f_{a}", "int64_t" if ct == "int" else "double", lo, nn)
+                self.scope[a] = Arr(f"f_{a}", "int32_t" if ct == "int" else "double", lo, nn)
         done = set(self.args)
         for _, st in self.body:
             names = []
@@ -387,7 +387,7 @@ class CUnit:
                                                   # after the call (xmin, xmax of tsadvc; like the interpreter)
                 else:
                     lo, nn = self.bounds_c(b)
-                    at_ = "int64_t" if ct == "int" else "double"
+                    at_ = "int32_t" if ct == "int" else "double"
                     size = " * ".join(x for x in nn)
                     self.emit(f"{at_} *f_{n} __attribute__((cleanup(free_))) = calloc(({size}) > 0 ? ({size}) : 1, sizeof({at_}));")
                     self.scope[n] = Arr(f"f_{n}", at_, lo, nn)
@@ -626,7 +626,7 @@ class Generator:
         self.modarr, self.modsc, self.sigs, self.units = {}, {}, {}, []
         for k, v in env.items():
             if isinstance(v, FArray):
-                ct = "int64_t" if v.isint else "double"
+                ct = "int32_t" if v.isint else "double"
                 self.modarr[k] = Arr(f"f_{k}", ct, [f"f_{k}_lo[{d}]" for d in range(v.rank)],
                                      [f"f_{k}_n[{d}]" for d in range(v.rank)])
             elif isinstance(v, bool) or isinstance(v, (int, np.integer)):
@@ -703,7 +703,7 @@ class Library:
             if k not in env:
                 continue
             v = env[k]
-            assert v.a.flags["C_CONTIGUOUS"] and v.a.dtype == (np.int64 if a.ctype == "int64_t" else np.float64), k
+            assert v.a.flags["C_CONTIGUOUS"] and v.a.dtype == (np.int32 if a.ctype == "int32_t" else np.float64), (k, v.a.dtype)
             C.c_void_p.in_dll(self.lib, f"f_{k}").value = v.a.ctypes.data
             lo = (C.c_int * a.rank).in_dll(self.lib, f"f_{k}_lo")
             nn = (C.c_int * a.rank).in_dll(self.lib, f"f_{k}_n")

@@ -21,6 +21,7 @@ import fortran_exec as fx
 
 REF = os.environ.get("HYCOM_REFERENCE", "/root/reference")
 NBDY = 6
+INT = np.int32      # integer and logical arrays are 4 bytes (no -fdefault-integer-8: config/generic-gnu-relo_one)
 
 
 def available():
@@ -61,22 +62,22 @@ def make_env(ii, jj, kdm=1, nreg=-1):
                itest=-99, jtest=-99, jblk=jj, lpipe_advem=False, lconserve=False, flush_lp=1, no_flush=0,
                halo_ps=1, halo_pv=11, halo_qs=2, halo_qv=12, halo_us=3, halo_uv=13, halo_vs=4, halo_vv=14)
     for n in ("ip", "iu", "iv", "iq", "ipim1", "ipip1", "ipjm1", "ipjp1", "ipim1x", "ipip1x", "ipjm1x", "ipjp1x"):
-        env[n] = fx.FArray.zeros(b2, dtype=np.int64)
+        env[n] = fx.FArray.zeros(b2, dtype=INT)
     for n in ("allip", "alliq", "alliu", "alliv"):
-        env[n] = fx.FArray.zeros(((1 - nb, jj + nb),), dtype=np.int64)
+        env[n] = fx.FArray.zeros(((1 - nb, jj + nb),), dtype=INT)
     for p in "pquv":
-        env["is" + p] = fx.FArray.zeros(((1 - nb, jj + nb),), dtype=np.int64)
-        env["js" + p] = fx.FArray.zeros(((1 - nb, ii + nb),), dtype=np.int64)
+        env["is" + p] = fx.FArray.zeros(((1 - nb, jj + nb),), dtype=INT)
+        env["js" + p] = fx.FArray.zeros(((1 - nb, ii + nb),), dtype=INT)
         for f in ("if", "il"):
-            env[f + p] = fx.FArray.zeros(((1 - nb, jj + nb), (1, ms)), dtype=np.int64)
+            env[f + p] = fx.FArray.zeros(((1 - nb, jj + nb), (1, ms)), dtype=INT)
         for f in ("jf", "jl"):
-            env[f + p] = fx.FArray.zeros(((1 - nb, ii + nb), (1, ms)), dtype=np.int64)
+            env[f + p] = fx.FArray.zeros(((1 - nb, ii + nb), (1, ms)), dtype=INT)
     # scratch of mod_tsadvc (:38-64), r_init = NaN so that nothing uninitialised goes unnoticed
     for n in ("fmx", "fmn", "flx", "fly", "fldlo", "fmxlo", "fmnlo", "fax", "fay", "rp", "rm", "flxdiv", "tx1", "ty1",
               "fldao", "fldan", "uloc", "vloc", "hloc", "dtloc", "ucumdt", "vcumdt", "flxcum", "flycum"):
         env[n] = fx.FArray.zeros(b2, fill=np.nan)
-    env["lcalc"] = fx.FArray.zeros(b2, dtype=np.int64)
-    env["mbdy_advtyp"] = fx.FArray(np.array([2, 5, 5, 0, 5], dtype=np.int64), (0,))   # mod_tsadvc.F90:24-29
+    env["lcalc"] = fx.FArray.zeros(b2, dtype=INT)
+    env["mbdy_advtyp"] = fx.FArray(np.array([2, 5, 5, 0, 5], dtype=INT), (0,))   # mod_tsadvc.F90:24-29
     env["xctilr"] = _xctilr_factory(env)
     env["xcmaxr"] = lambda x: x
     env["xcminr"] = lambda x: x
@@ -186,7 +187,7 @@ def add_cb_arrays(env, cb):
         env[name].fill(0.0)
     env["trold"] = fx.FArray.zeros(b2 + ((1, max(cb.ntracr, 1)),), fill=np.nan)
     env["xmin"], env["xmax"] = fx.FArray.zeros(((1, kk),), fill=np.nan), fx.FArray.zeros(((1, kk),), fill=np.nan)
-    trc = np.zeros(max(cb.ntracr, 1), dtype=np.int64)
+    trc = np.zeros(max(cb.ntracr, 1), dtype=INT)
     for q, v in enumerate(list(cb.trcflg)[:cb.ntracr]):
         trc[q] = v
     env["trcflg"] = fx.FArray(trc, (1,))
@@ -281,7 +282,7 @@ def add_cnuity_arrays(env, cb, st, mxlkta=False):
     for name in ("uflux", "vflux", "uflux2", "vflux2", "utotm", "vtotm"):
         env[name].fill(0.0)
     for name in ("masku", "maskv", "iuopn", "ivopn"):
-        env[name] = fx.FArray.zeros(b2, dtype=np.int64)
+        env[name] = fx.FArray.zeros(b2, dtype=INT)
     env["dpmn"] = fx.FArray.zeros(((1 - nb, g.jj + nb),), fill=np.nan)
     env["p"] = fx.FArray.zeros(b2 + ((1, kk + 1),), fill=np.nan)
     env["p"].a[0] = 0.0                                        # p(:,:,1) = 0 always (geopar / inicon)
