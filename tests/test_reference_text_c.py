@@ -183,3 +183,60 @@ def test_compiled_text_equals_oracle_at_glbb008_size(oracle, advtyp, ntracr):
     if ntracr:
         assert np.array_equal(cb.tracer[:, n - 1][..., inner], ref["tracer"][:, n - 1][..., inner])
     assert np.array_equal(env["xmin"].a, ref["xmin"]) and np.array_equal(env["xmax"].a, ref["xmax"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# stage by stage: after tsadvc(m,n) on BASELINE configs[0] (150 x 150 x 22 box) the module
+# scratch of mod_tsadvc.F90:38-51 holds the intermediates of the last advem call - low-order fluxes, extrema,
+# low-order solution, antidiffusive fluxes before and after the limiter, limiter ratios - exactly where the reference
+# has its pipe_compare_sym hooks.  The oracle's scratch must hold the same bits, hence the same zero-flux and sign
+# patterns, at every point the masks define.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("advtyp", [2, 1, 4])
+def test_intermediates_of_config1_equal_the_compiled_reference_text(oracle, advtyp):
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(150, 150, 22, nreg=0, ntracr=0, seed=13, m=m, n=n, advtyp=advtyp, nstep=3)
+    ot = util.oracle_tile_from_cb(oracle, cb, sea)
+    ot.tsadvc(m, n, 1)
+    lib, env = compiled_env(g, sea)
+    rt.add_cb_arrays(env, cb)
+    lib.run(env, "tsadvc", m, n)
+    nb = g.nbdy
+    inner = np.zeros((g.nrows, g.ncols), dtype=bool)
+    inner[nb:nb + g.jj, nb:nb + g.ii] = True
+    P, U, V = inner & (cb.ip != 0), inner & (cb.iu != 0), inner & (cb.iv != 0)
+    stages = [("flx", U), ("fly", V), ("fmx", P), ("fmn", P), ("fldlo", P), ("flxdiv", P), ("rp", P), ("rm", P)]
+    if advtyp in (2, 4):
+        stages += [("fmxlo", P), ("fmnlo", P), ("fax", U), ("fay", V)]
+    else:
+        stages += [("tx1", U), ("ty1", V)]
+    for name, msk in stages:
+        a, b = ot.f64(name), env[name].a
+        assert np.isfinite(b[msk]).all(), name
+        assert np.array_equal(a[msk], b[msk]), name
+        assert np.array_equal(np.signbit(a[msk]), np.signbit(b[msk])), (name, "sign pattern")
+        assert np.array_equal(a[msk] == 0.0, b[msk] == 0.0), (name, "zero pattern")
+    ot.close()
+
+
+def test_compiled_cnuity_equals_oracle_at_glbb008_size(oracle):
+    """cnuity(m,n) with the biharmonic interface-depth diffusion on two layers of the GLBb0.08 horizontal size:
+    compiled reference text == oracle"""
+    m, n, kdm = 1, 2, 2
+    cfg, sea, g, cb = util.make_case(4500, 3298, kdm, nreg=0, seed=23, m=m, n=n, nstep=4)
+    st = util.add_cnuity(cfg, sea, g, cb, m, n, thkdf=0.01, bih=True)
+    got = util.run_oracle_cnuity(oracle, cb, sea, st, m, n)
+    lib, env = compiled_env(g, sea)
+    rt.add_cb_arrays(env, cb)
+    rt.add_cnuity_arrays(env, cb, st)
+    lib.run(env, "cnuity", m, n)
+    nb = g.nbdy
+    inner = util.interior_sea(cb)
+    iu_in, iv_in = np.zeros_like(inner), np.zeros_like(inner)
+    iu_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iu[nb:nb + g.jj, nb:nb + g.ii] != 0
+    iv_in[nb:nb + g.jj, nb:nb + g.ii] = cb.iv[nb:nb + g.jj, nb:nb + g.ii] != 0
+    assert inner.sum() > 13_000_000
+    for name, msk in (("dp", inner), ("dpo", inner), ("uflx", iu_in), ("vflx", iv_in)):
+        assert np.array_equal(got[name][..., msk], st[name][..., msk]), name
+    assert np.array_equal(got["p"][1:][:, inner], env["p"].a[1:][:, inner])
+    assert np.array_equal(got["utotn"][iu_in], env["utotn"].a[iu_in]) and np.array_equal(got["vtotn"][iv_in], env["vtotn"].a[iv_in])
