@@ -449,7 +449,7 @@ def _pow(a, b):
         r = 1 if isinstance(a, int) else 1.0
         for _ in range(abs(b)):
             r = r * a
-        return r if b >= 0 else 1.0 / r
+        return r if b >= 0 else _div(1.0, r)
     return math.pow(a, b)
 
 
