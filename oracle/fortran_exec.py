@@ -847,13 +847,13 @@ class Translator:
         return "\n".join(head + ["    pass"] + inner_src + self.lines) + "\n"
 
 
-def compile_slice(path, unit, first, last, name, env, defines=("RELO",), **kw):
+def compile_slice(path, unit, first, last, name, env, defines=("RELO",), back=0, **kw):
     """a run of statements of `subroutine unit` as a parameterless subroutine `name`: from the first statement that
     matches the regular expression `first` up to (not including) the first later statement that matches `last`.
     For routines whose head cannot be executed (xcspmd: file input, MPI start-up) but whose tail is plain Fortran."""
     stmts = load_source(path, defines)
     _, body, _ = extract_unit(stmts, unit)
-    k0 = next(k for k, (_, st) in enumerate(body) if re.search(first, st))
+    k0 = next(k for k, (_, st) in enumerate(body) if re.search(first, st)) - back     # `back`: enclosing do statements
     k1 = next(k for k, (_, st) in enumerate(body) if k > k0 and re.search(last, st))
     arrays = {k: v.rank for k, v in env.items() if isinstance(v, FArray)}
     t = Translator(name.lower(), [], body[k0:k1], arrays, module_scalars=[k for k, v in env.items() if not isinstance(v, FArray)], **kw)

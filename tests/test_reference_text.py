@@ -557,3 +557,32 @@ def test_multi_tile_xctilr_of_the_reference_text_equals_oracle(oracle, ipr, jpr,
 def fx_array3(a, nb):
     import fortran_exec as fx
     return fx.FArray(a, (1 - nb, 1 - nb, 1))
+
+
+def test_geopar_metrics_of_the_reference_text_equal_oracle(oracle):
+    """geopar.F90:311-340 as written (cell areas, their inverses, the aspect-limited grid spacing factors)"""
+    if not rt.available():
+        pytest.skip("the reference source tree is not on this machine")
+    import fortran_exec as fx
+    cfg, sea, g, cb = util.make_case(30, 24, 1, nreg=0, seed=3)
+    nb = g.nbdy
+    rng = np.random.default_rng(5)
+    shp = (g.nrows, g.ncols)
+    sc = {n: np.ascontiguousarray(8000.0 * (0.2 + rng.random(shp) * np.where(rng.random(shp) < 0.3, 5.0, 1.0)))
+          for n in ("scpx", "scpy", "scux", "scuy", "scvx", "scvy", "scqx", "scqy")}
+    sc["scux"][3, 4] = 0.0                       # the max(.., epsil) guards
+    sc["scpx"][5, 6] = 0.0
+    env = dict(nbdy=nb, ii=g.ii, jj=g.jj, epsil=1.0e-11, aspmax=2.0)
+    for n, a in sc.items():
+        env[n] = fx.FArray(a, (1 - nb, 1 - nb))
+    for n in ("scu2", "scv2", "scp2", "scq2", "scuxi", "scvyi", "scp2i", "scq2i", "aspux", "aspuy", "aspvx", "aspvy", "util1", "depths"):
+        env[n] = fx.FArray(np.zeros(shp), (1 - nb, 1 - nb))
+    fx.compile_slice(os.path.join(rt.REF, "geopar.F90"), "geopar", r"^scu2\(i,j\)=scux\(i,j\)\*scuy\(i,j\)$", r"^if\s*\(ishelf\.eq\.0\)\s*then$",
+                     "metrics", env, back=2)
+    with np.errstate(all="ignore"):
+        env["metrics"]()
+    ot = oracle.tile(g, 0)
+    ot.geopar(sc["scpx"], sc["scpy"], sc["scux"], sc["scuy"], sc["scvx"], sc["scvy"])
+    for n in ("scp2", "scp2i", "aspux", "aspvy"):
+        assert np.array_equal(ot.f64(n), env[n].a), n
+    ot.close()
