@@ -195,8 +195,10 @@ def reference_text_rate(o, calls, threads):
     so = rc.RefTextC.so_path(6, False, True)
     if not rt.available() and not (os.path.exists(so) and os.path.exists(so[:-3] + ".json")):
         raise FileNotFoundError("oracle/_ref holds no compiled reference text (build() makes it where /root/reference exists)")
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     lib = rc.RefTextC(6, False, openmp=True, flags=rc.RefTextC.TIMED_FLAGS)
+    import ctypes
+    # (torchrun exports OMP_NUM_THREADS=1 to its ranks; the directives of the text carry no num_threads clause)
+    ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
     g, cb, sea = o.geom, o.cb, o.sea
     nb = g.nbdy
     env = rt.make_env(g.ii, g.jj, g.kdm)
