@@ -62,8 +62,11 @@ def _tile_env(tiles, t, ipr, jpr, nreg, itdm, jtdm, kdm, mnproc):
 class World:
     """ipr x jpr tiles of one global grid; `tiles` are the product's Geometry objects (hycom-src_b200/geometry.py)"""
 
-    def __init__(self, tiles, ipr, jpr, nreg, itdm, jtdm, kdm, flavour="MPI"):
+    def __init__(self, tiles, ipr, jpr, nreg, itdm, jtdm, kdm, flavour="MPI", envs=None):
+        """envs: environments to build on (reference_text.make_env of every tile, for running bigrid / tsadvc on the
+        tiles: uniform tilings only); their xctilr, xcmaxr, xcminr become the multi-tile ones"""
         self.tiles, self.n = tiles, len(tiles)
+        self.slots = [None] * self.n
         arctic = nreg == 2
         defines = ("RELO", flavour) + (("ARCTIC",) if arctic else ())
         self.envs = []
@@ -73,7 +76,12 @@ class World:
         start = r"^null_tile\s*=\s*-1$" if flavour == "SHMEM" else r"^null_tile\s*=\s*mpi_proc_null$"
         for r, t in enumerate(tiles):
             assert r == (t.mproc - 1) + ipr * (t.nproc - 1)
-            env = _tile_env(tiles, t, ipr, jpr, nreg, itdm, jtdm, kdm, r + 1)
+            env = envs[r] if envs is not None else {}
+            if envs is not None:
+                assert (t.idm, t.jdm) == (t.ii, t.jj), "uniform tiles only"
+                env["xcmaxr"] = (lambda rr: lambda x: self.allreduce(rr, x, max))(r)
+                env["xcminr"] = (lambda rr: lambda x: self.allreduce(rr, x, min))(r)
+            env.update(_tile_env(tiles, t, ipr, jpr, nreg, itdm, jtdm, kdm, r + 1))
             fx.compile_slice(_PATH, "xcspmd", start, r"^call xcsync\(flush_lp\)$", "xcspmd_tables", env, defines=defines,
                              skip_calls=("xcsync", "xcstop", "mpi_comm_split", "mpi_comm_free"))
             env["xcspmd_tables"]()
@@ -87,6 +95,32 @@ class World:
             fx.compile_unit(_PATH, "xctilr", env, defines=defines, skip_calls=("xctmr0", "xctmr1", "mem_stat_add"),
                             callee_ranks=ranks, drop_blocks=(r"allocated",))
             self.envs.append(env)
+
+    def allreduce(self, r, x, op):
+        """xcmaxr / xcminr of a scalar over the tiles"""
+        self.slots[r] = x
+        self.barrier.wait()
+        v = op(self.slots)
+        self.barrier.wait()
+        return v
+
+    def run(self, fn):
+        """fn(rank, env) on every tile, one thread each"""
+        errs = []
+
+        def go(r):
+            try:
+                fn(r, self.envs[r])
+            except BaseException as e:      # noqa: BLE001
+                errs.append((r, e))
+                self.barrier.abort()
+        th = [threading.Thread(target=go, args=(r,)) for r in range(self.n)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0][1]
 
     def _box(self, to, frm, tag):
         with self.lock:

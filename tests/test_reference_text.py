@@ -586,3 +586,55 @@ def test_geopar_metrics_of_the_reference_text_equal_oracle(oracle):
     for n in ("scp2", "scp2i", "aspux", "aspvy"):
         assert np.array_equal(ot.f64(n), env[n].a), n
     ot.close()
+
+
+# the whole path on tiles, in the reference text: bigrid and tsadvc(m,n) of every tile on its own thread, their xctilr
+# the multi-tile text of mod_xc_mp.h, xcmaxr a reduction over the threads - the reference's own tiling invariance
+# (mod_pipe.F90:26-127), and the per-tile results the product's tiles are compared with on the GPU
+@pytest.mark.skipif(not rt.available(), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("ipr,jpr,nreg,advtyp,ntracr", [(2, 2, 0, 2, 1), (2, 1, 1, 1, 0), (2, 1, 3, 4, 0),     # (the f-plane wants jpr = 1: mod_xc_mp.h:2855)
+                                                      (2, 2, 2, 2, 1), (4, 2, 2, 1, 0)])                       # across the arctic
+def test_tsadvc_of_the_reference_text_on_tiles_equals_one_tile(oracle, ipr, jpr, nreg, advtyp, ntracr):
+    import reference_text_mp as rmp
+    pkg, syn = util.pkg, util.syn
+    m, n = 1, 2
+    itdm, jtdm, kdm = (36, 28, 2) if nreg != 2 else (48, 36, 2)
+    if nreg == 2:
+        cfg, sea, g1, cb1 = util.make_arctic_case(itdm, jtdm, kdm, ntracr=ntracr, seed=11, m=m, n=n, advtyp=advtyp, nstep=3)
+        cbs = util.make_arctic_tiles(cfg, sea, cb1, ipr, jpr, m, n, advtyp=advtyp, nstep=3)
+    else:
+        cfg, sea, g1, cb1 = util.make_case(itdm, jtdm, kdm, nreg=nreg, ntracr=ntracr, seed=11, m=m, n=n, advtyp=advtyp, nstep=3)
+    ref = util.run_oracle(oracle, cb1, sea, m, n)                      # one tile, the oracle
+    _run_reference_driver(cb1, sea, g1, m, n)                          # one tile, the reference text (updates cb1)
+    tiles = pkg.partition(itdm, jtdm, kdm, ipr, jpr, nreg)
+    if nreg != 2:
+        cbs = [syn.build_cb_arrays(cfg, g, sea, m, n, advtyp=advtyp, nstep=3) for g in tiles]
+    envs = [rt.make_env(g.ii, g.jj, kdm) for g in tiles]
+    for env, g in zip(envs, tiles):
+        env.update(i0=g.i0, j0=g.j0, itdm=itdm, jtdm=jtdm)
+    world = rmp.World(tiles, ipr, jpr, nreg, itdm, jtdm, kdm, envs=envs)
+    nb = g1.nbdy
+
+    def tile(r, env):
+        g, cb = tiles[r], cbs[r]
+        depth = np.zeros((g.nrows, g.ncols))
+        depth[nb:nb + g.jj, nb:nb + g.ii] = np.where(sea[g.j0:g.j0 + g.jj, g.i0:g.i0 + g.ii] != 0, 100.0, 0.0)
+        rt.run_bigrid(env, depth, mapflg=4 if nreg in (3, 4) else 0)
+        assert env["nreg"] == nreg
+        for name in ("ip", "iu", "iv"):
+            assert np.array_equal(env[name].a[1:-1, 1:-1], getattr(cb, name)[1:-1, 1:-1]), name
+        rt.add_cb_arrays(env, cb)
+        rt.compile_tsadvc(env)
+        rt.run_tsadvc(env, m, n)
+    world.run(tile)
+    for g, cb in zip(tiles, cbs):
+        sea_t = cb.ip[nb:nb + g.jj, nb:nb + g.ii] != 0
+        for name in ("temp", "saln"):
+            loc = getattr(cb, name)[n - 1, :, nb:nb + g.jj, nb:nb + g.ii]
+            for other in (getattr(cb1, name), ref[name]):
+                glb = other[n - 1, :, nb + g.j0:nb + g.j0 + g.jj, nb + g.i0:nb + g.i0 + g.ii]
+                assert np.array_equal(loc[:, sea_t], glb[:, sea_t]), (name, g.mproc, g.nproc)
+        for q in range(ntracr):
+            loc = cb.tracer[q, n - 1, :, nb:nb + g.jj, nb:nb + g.ii]
+            glb = cb1.tracer[q, n - 1, :, nb + g.j0:nb + g.j0 + g.jj, nb + g.i0:nb + g.i0 + g.ii]
+            assert np.array_equal(loc[:, sea_t], glb[:, sea_t]), ("tracer", q)
