@@ -32,28 +32,30 @@ _PATH = os.path.join(REF, "mod_xc_mp.h")
 def _tile_env(tiles, t, ipr, jpr, nreg, itdm, jtdm, kdm, mnproc):
     nb = NBDY
     I = lambda bounds, fill=0: fx.FArray.zeros(bounds, dtype=np.int64, fill=fill)   # noqa: E731
-    env = dict(ipr=ipr, jpr=jpr, ijpr=ipr * jpr, iqr=ipr, jqr=jpr, ijqr=ipr * jpr, nreg=nreg, itdm=itdm, jtdm=jtdm,
+    # (iqr, jqr, ijqr: the compile-time maxima of mod_dimensions.F90 that size the tables, larger than any tiling)
+    iqr, jqr = ipr + 2, jpr + 2
+    env = dict(ipr=ipr, jpr=jpr, ijpr=ipr * jpr, iqr=iqr, jqr=jqr, ijqr=iqr * jqr, nreg=nreg, itdm=itdm, jtdm=jtdm,
                nbdy=nb, kdm=kdm, idm=t.idm, jdm=t.jdm, mnproc=mnproc, npesi=ipr * jpr, lp=6, flush_lp=1, vland=0.0,
                mproc=-1, nproc=-1, null_tile=-99, mp_1st=-1, ixsum=-1, i0=-1, ii=-1, j0=-1, jj=-1,
                m0_top=-1, mm_top=-1, m0_bot=-1, mm_bot=-1)
     for n in ("i0_pe", "ii_pe", "j0_pe", "jj_pe", "i1sum", "iisum"):
-        env[n] = I(((1, ipr), (1, jpr)))
+        env[n] = I(((1, iqr), (1, jqr)))
     for g in tiles:     # what patch.input holds (xcspmd reads ispt = i0+1, iipe, jspt, jjpe)
         env["i0_pe"][g.mproc, g.nproc], env["ii_pe"][g.mproc, g.nproc] = g.i0, g.ii
         env["j0_pe"][g.mproc, g.nproc], env["jj_pe"][g.mproc, g.nproc] = g.j0, g.jj
-    env["idproc"] = I(((0, ipr + 1), (0, jpr + 1)), -77)
-    env["idproc1"] = I(((0, ipr * jpr + 1),), -77)
+    env["idproc"] = I(((0, iqr + 1), (0, jqr + 1)), -77)
+    env["idproc1"] = I(((0, iqr * jqr + 1),), -77)
     env["idhalo"] = I(((1, 2),), -77)
-    env["mpe_1"], env["mpe_e"] = I(((1, jpr),)), I(((1, jpr),))
-    env["mpe_i"], env["npe_j"] = I(((0, itdm + 1), (0, jpr))), I(((0, jtdm + 1),))
+    env["mpe_1"], env["mpe_e"] = I(((1, jqr),)), I(((1, jqr),))
+    env["mpe_i"], env["npe_j"] = I(((0, itdm + 1), (0, jqr))), I(((0, jtdm + 1),))
     for n in ("i0_st", "ii_st", "i0_gt", "ii_gt", "i0_sb", "ii_sb", "i0_gb", "ii_gb"):
-        env[n] = I(((1, ipr),), -77)
+        env[n] = I(((1, iqr),), -77)
     # the symmetric buffers of xctilr (save, allocatable: allocated on the first call)
     env["ai"] = fx.FArray.zeros(((1, t.idm * kdm * nb + 64), (1, 4)), fill=np.nan)
     env["aj"] = fx.FArray.zeros(((1, (t.jdm + 2 * nb) * kdm * nb + 64), (1, 4)), fill=np.nan)
     env["aia"] = fx.FArray.zeros(((1, kdm * nb + 64), (1, 2)), fill=np.nan)
     # MPI flavour: the saved request tables with the values their `data` statements give them, constants of mpif.h
-    env["mpireqa"], env["mpireqb"] = I(((1, 4 * ipr),), -1), I(((1, 4),), -1)
+    env["mpireqa"], env["mpireqb"] = I(((1, 4 * iqr),), -1), I(((1, 4),), -1)
     env.update(nreqa=0, klmold=0, klnold=0, mhlold=0, nhlold=0, ityold=0, ilold=0, jlold=0, mpierr=0,
                mpi_proc_null=-2, mpi_comm_hycom=0, mpi_real8=8, mpi_statuses_ignore=0, group_1st_in_row=0)
     return env

@@ -271,6 +271,20 @@ def test_exchange_schedule_matches_oracle_world_xctilr(oracle, ipr, jpr, nreg):
     for t, g in enumerate(tiles):
         for q in range(len(itypes)):
             assert np.array_equal(got[t][q], ref[t][q], equal_nan=True), (g.mproc, g.nproc, itypes[q])
+    # ... and exactly like the reference's own multi-tile xctilr, executed as written (mod_xc_mp.h in its MPI flavour,
+    # one thread per tile: oracle/reference_text_mp.py), where the reference tree is on this machine and the tiling is
+    # one the reference admits (a domain periodic in latitude wants jpr = 1)
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import reference_text as rt
+    if rt.available() and not (nreg == 3 and jpr > 1):
+        import reference_text_mp as rmp
+        world = rmp.World(tiles, ipr, jpr, nreg, itdm, jtdm, kk)
+        txt = tile_arrays()
+        for q, it in enumerate(itypes):
+            world.xctilr([txt[t][q] for t in range(len(tiles))], 1, kk, 5, 5, it)
+        for t, g in enumerate(tiles):
+            for q in range(len(itypes)):
+                assert np.array_equal(got[t][q], txt[t][q], equal_nan=True), (g.mproc, g.nproc, itypes[q], "reference text")
 
 
 def test_periodic_shift_invariance(oracle):
