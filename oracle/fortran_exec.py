@@ -66,7 +66,7 @@ class FArray:
             self.a[tuple(i - l for i, l in zip(reversed(idx), reversed(self.lo)))] = v
 
     def fill(self, v):
-        self.a[...] = v
+        self.a[...] = v.a if isinstance(v, FArray) else v
 
     def section(self, idx):
         """numpy view of a(lo:hi, :, k, ...): `idx` holds ints (the dimension is dropped) or (lo, hi) pairs with
@@ -174,6 +174,14 @@ def load_source(path, defines=(), include_dirs=(), keep_omp=False):
             continue
         if not active():
             continue
+        mi = re.match(r"^\s*include\s+['\"]([^'\"]+)['\"]\s*(!.*)?$", ln, flags=re.I)
+        if mi and not mi.group(1).lower().startswith("mpif"):       # the Fortran include line (stmt_fns.h in the shim)
+            for dd in (os.path.dirname(path),) + tuple(include_dirs):
+                f = os.path.join(dd, mi.group(1))
+                if os.path.exists(f):
+                    raw[i:i] = open(f, errors="replace").read().split("\n")
+                    break
+            continue
         out_lines.append(ln)
     # comments, continuations (free form: trailing &; the next line may start with &)
     stmts, cur = [], ""
@@ -255,7 +263,7 @@ _TOK = re.compile(r"""\s*(?:
     (?P<str>'') |
     (?P<num>(?:\d+\.(?!(?:and|or|not|eq|ne|lt|le|gt|ge|eqv|neqv|true|false)\.)\d*|\.\d+|\d+)(?:[ed][+-]?\d+)?(?:_\w+)?) |
     (?P<dotop>\.(?:and|or|not|eq|ne|lt|le|gt|ge|true|false|eqv|neqv)\.) |
-    (?P<name>[a-z_]\w*) |
+    (?P<name>[a-z_]\w*(?:%[a-z_]\w*)*) |
     (?P<op>\*\*|==|/=|<=|>=|//|[-+*/(),<>:=])
 )""", re.X)
 
@@ -264,13 +272,15 @@ _INTRINSIC = {
     "min0": "_min", "abs": "abs", "dabs": "abs", "iabs": "abs", "mod": "_mod", "sign": "_sign", "sqrt": "_sqrt",
     "dsqrt": "_sqrt", "real": "float", "float": "float", "dble": "float", "int": "_int", "nint": "_nint",
     "exp": "_exp", "log": "_log", "alog": "_log", "atan2": "_atan2", "cos": "_cos", "sin": "_sin", "atan": "_atan",
-    "tan": "_tan", "acos": "_acos", "asin": "_asin", "minval": "_minval", "maxval": "_maxval",
+    "tan": "_tan", "acos": "_acos", "asin": "_asin", "minval": "_minval", "maxval": "_maxval", "merge": "_merge", "transfer": "_transfer",
 }
 _REL = {".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", "==": "==", "/=": "!=",
         "<": "<", "<=": "<=", ">": ">", ">=": ">="}
 
 
 def _pyname(n):
+    if "%" in n:                                   # a component of a derived-type variable: an attribute
+        return ".".join(_pyname(x) for x in n.split("%"))
     return n + "_" if keyword.iskeyword(n) or n in ("print", "len", "id", "type", "sum", "all", "any") else n
 
 
@@ -414,7 +424,7 @@ class ExprParser:
             if self.peek()[1] == "(":
                 self.take()
                 a = self.args()
-                if v in self.arrays:
+                if v in self.arrays or "%" in v:
                     if any(isinstance(x, tuple) for x in a):
                         parts = [f"({x[1]}, {x[2]})" if isinstance(x, tuple) else x for x in a]
                         return f"{_pyname(v)}.section(({', '.join(parts)},))"
@@ -491,6 +501,16 @@ def _frange(a, b, c=1):
     return range(a, b + 1, c) if c > 0 else range(a, b - 1, c)
 
 
+def _merge(t, f, mask):
+    return t if mask else f
+
+
+def _transfer(src, mold):
+    """transfer(source, mold) between arrays: the bytes of `src` seen with the type of `mold`"""
+    b = np.ascontiguousarray(src.a).view(np.uint8).reshape(-1)
+    return FArray(b.view(mold.a.dtype)[:mold.a.size].copy(), mold.lo)
+
+
 def _dummy(a, bounds):
     if not isinstance(a, FArray) or a.rank != len(bounds):
         return a
@@ -505,7 +525,7 @@ class FortranStop(Exception):
     pass
 
 
-RUNTIME = dict(np=np, _dummy=_dummy, _minval=lambda a: float(np.min(a)), _maxval=lambda a: float(np.max(a)), _div=_div, _pow=_pow, _max=_max, _min=_min, _mod=_mod, _sign=_sign, _int=_int, _nint=_nint,
+RUNTIME = dict(np=np, _dummy=_dummy, _merge=_merge, _transfer=_transfer, _minval=lambda a: float(np.min(a)), _maxval=lambda a: float(np.max(a)), _div=_div, _pow=_pow, _max=_max, _min=_min, _mod=_mod, _sign=_sign, _int=_int, _nint=_nint,
                _frange=_frange, _sqrt=math.sqrt, _exp=math.exp, _log=math.log, _atan2=math.atan2, _cos=math.cos,
                _sin=math.sin, _atan=math.atan, _tan=math.tan, _acos=math.acos, _asin=math.asin, FArray=FArray,
                FortranStop=FortranStop)
@@ -587,6 +607,27 @@ class Translator:
             raise NotImplementedError(st)
         if _IO.match(st) or st in ("continue",):
             self.emit("pass")
+            return
+        m = re.match(r"^type\s*\(\s*(\w+)\s*\)\s*(?:,[^:]*)?::(.*)$", st)
+        if m and m.group(1) != "c_ptr":               # a variable of a derived type: the harness builds it (_newtype)
+            for n in _split_top(m.group(2)):
+                self.emit(f"{_pyname(n.strip())} = _newtype('{m.group(1)}')")
+            return
+        m = re.match(r"^character\b.*::\s*(\w+)\s*\((\w+)\)$", st)
+        if m:                                          # character(kind=c_char) :: id(128): bytes
+            self.arr[m.group(1)] = 1
+            self.emit(f"{_pyname(m.group(1))} = FArray.zeros(((1, {self.ex(m.group(2))}),), dtype=np.uint8)")
+            return
+        m = re.match(r"^allocate\s*\((.*)\)$", st)
+        if m:
+            for ent in _split_top(m.group(1)):
+                me = re.match(r"^(\w+)\s*\((.*)\)$", ent)
+                bb = []
+                for b in _split_top(me.group(2)):
+                    lo, hi = (b.split(":") + [None])[:2] if ":" in b else ("1", b)
+                    bb.append(f"({self.ex(lo)}, {self.ex(hi)})")
+                self.assigned.add(me.group(1))
+                self.emit(f"{_pyname(me.group(1))} = FArray.zeros(({', '.join(bb)},))")
             return
         m = re.match(r"^(real|integer|logical|double\s*precision)\b(.*?)::(.*)$", st)
         if ((m and "parameter" in m.group(2)) or re.match(r"^parameter\s*\(", st)) and getattr(self, "params_done", False):
@@ -698,10 +739,10 @@ class Translator:
         if eq < 0:
             raise NotImplementedError(st)
         lhs, rhs = st[:eq].strip(), st[eq + 1:].strip()
-        m = re.match(r"^(\w+)\s*\((.*)\)$", lhs)
+        m = re.match(r"^([\w%]+)\s*\((.*)\)$", lhs)
         if m:
             n, idx = m.group(1), _split_top(m.group(2))
-            if n not in self.arr:
+            if n not in self.arr and "%" not in n:
                 if all(re.match(r"^[a-z_]\w*$", i) for i in idx):   # a statement function: name(dummies) = expression
                     self.funcs.add(n)
                     self.emit(f"def {_pyname(n)}({', '.join(_pyname(i) for i in idx)}):")
@@ -864,10 +905,10 @@ def compile_slice(path, unit, first, last, name, env, defines=("RELO",), back=0,
     return src
 
 
-def compile_unit(path, name, env, defines=("RELO",), extra_arrays=None, **kw):
+def compile_unit(path, name, env, defines=("RELO",), extra_arrays=None, include_dirs=(), **kw):
     """translate `subroutine name` of the file and define it in `env` (a dict that holds the module variables:
     FArray objects and scalars); returns the Python source (for inspection)"""
-    stmts = load_source(path, defines)
+    stmts = load_source(path, defines, include_dirs)
     args, body, internals = extract_unit(stmts, name)
     arrays = {k: v.rank for k, v in env.items() if isinstance(v, FArray)}
     arrays.update(extra_arrays or {})
