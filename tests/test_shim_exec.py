@@ -189,3 +189,35 @@ def test_shim_with_diffusion_uploads_theta_once(oracle):
         assert np.array_equal(getattr(cb, name)[n - 1][..., inner], getattr(ref_cb, name)[n - 1][..., inner]), name
     env["tsadvc"](n, m)
     assert len([c for c in lib.calls if isinstance(c, tuple)]) == 1
+
+
+def test_shim_attaches_the_communicator_on_several_tiles(oracle):
+    """ipr*jpr > 1: tile 1 draws the 128-byte id, it travels through mod_xc's own broadcast xcastr as 16 reals
+    (transfer there and back) and every tile hands it to hycom_tsadvc_comm_init"""
+    cfg, sea, g, cb = util.make_case(20, 16, 1, seed=3)
+    cb.sigver = 6
+    env = _shim_env(cb, sea, g)
+    lib = StandIn(env, oracle, cb, sea)
+    lib.install()
+    env.update(ipr=2, jpr=1)
+    seen = {}
+
+    def unique_id(id_):
+        assert id_.a.shape == (128,) and id_.a.dtype == np.uint8
+        id_.a[:] = (np.arange(128) * 7 + 3) % 251
+        seen["drawn"] = id_.a.copy()
+        return 0
+
+    def xcastr(a, root):
+        assert a.a.shape == (16,) and a.a.dtype == np.float64 and root == 1
+        seen["cast"] = a.a.copy()
+
+    def comm_init(h, id_):
+        assert h is env["handle"]
+        seen["init"] = id_.a.copy()
+        return 0
+    env.update(hycom_tsadvc_comm_unique_id=unique_id, xcastr=xcastr, hycom_tsadvc_comm_init=comm_init)
+    _compile_shim(env, 6)
+    env["tsadvc"](1, 2)
+    assert np.array_equal(seen["init"], seen["drawn"]) and seen["cast"].view(np.uint8).tolist() == seen["drawn"].tolist()
+    assert lib.calls[:2] == ["create", "set_static"] and lib.calls[-1] == "step"
