@@ -301,8 +301,8 @@ class ExprParser:
     """Fortran expression -> Python source.  `arrays`: names indexed with [] (everything else followed by '(' is a
     call); `rank`: rank of known arrays (for array-element actual arguments)"""
 
-    def __init__(self, toks, arrays, funcs=()):
-        self.t, self.p, self.arrays, self.funcs = toks, 0, arrays, funcs
+    def __init__(self, toks, arrays, funcs=(), callee=None):
+        self.t, self.p, self.arrays, self.funcs, self.callee = toks, 0, arrays, funcs, callee or {}
 
     def peek(self):
         return self.t[self.p] if self.p < len(self.t) else (None, None)
@@ -431,13 +431,19 @@ class ExprParser:
                     return f"{_pyname(v)}[{', '.join(a)}]" if len(a) > 1 else f"{_pyname(v)}[{a[0]}]"
                 if v in _INTRINSIC and v not in self.funcs:
                     return f"{_INTRINSIC[v]}({', '.join(a)})"
+                if v in self.callee:       # a function with array dummies: an array-element actual is the array from there on
+                    ranks = self.callee[v]
+                    for k, x in enumerate(a):
+                        me = re.match(r"^(\w+)\[(.*)\]$", x) if isinstance(x, str) else None
+                        if me and k < len(ranks) and ranks[k]:
+                            a[k] = f"{me.group(1)}.from_element(({me.group(2)},), {ranks[k]})"
                 return f"{_pyname(v)}({', '.join(a)})"
             return _pyname(v)
         raise SyntaxError(f"unexpected {v!r} in {self.t}")
 
 
-def expr(s, arrays, funcs=()):
-    p = ExprParser(tokenize(s), arrays, funcs)
+def expr(s, arrays, funcs=(), callee=None):
+    p = ExprParser(tokenize(s), arrays, funcs, callee)
     e = p.parse()
     if p.p != len(p.t):
         raise SyntaxError(f"trailing tokens in {s!r}")
@@ -591,7 +597,7 @@ class Translator:
         self.lines.append("    " * self.ind + s)
 
     def ex(self, s):
-        return expr(s, self.arr, self.funcs)
+        return expr(s, self.arr, self.funcs, self.callee)
 
     def stmt(self, st):
         m = re.match(r"^if\s*\((.*)\)\s*go\s*to\s*(\d+)$", st)

@@ -221,3 +221,60 @@ def test_shim_attaches_the_communicator_on_several_tiles(oracle):
     env["tsadvc"](1, 2)
     assert np.array_equal(seen["init"], seen["drawn"]) and seen["cast"].view(np.uint8).tolist() == seen["drawn"].tolist()
     assert lib.calls[:2] == ["create", "set_static"] and lib.calls[-1] == "step"
+
+
+def test_shim_with_mellor_yamada_fields_fills_and_reads_their_mirrors(oracle):
+    """mxlmy: q2, q2l (0:kk+1, both slots) are not arguments of hycom_tsadvc_step; the shim uploads both slots before
+    the call (fields 9, 10: kdm+2 slabs from element (1-nbdy,1-nbdy,0,t)) and downloads slot n after it"""
+    m, n = 1, 2
+    cfg, sea, g, cb = util.make_case(26, 22, 3, nreg=0, ntracr=0, seed=11, m=m, n=n, advtyp=2, nstep=3)
+    util.add_q2(cfg, sea, g, cb, m, n)
+    cb.sigver = 6
+    ref_cb = copy.deepcopy(cb)
+    T._run_reference_driver(ref_cb, sea, g, m, n, 6)
+    env = _shim_env(cb, sea, g)
+    lib = StandIn(env, oracle, cb, sea)
+    lib.install()
+    mirrors = {}
+
+    def addr(a):
+        return a.__array_interface__["data"][0]
+
+    def upload(h, field, ktr, tlev, k0, nk, host):
+        name = {9: "q2", 10: "q2l"}[field]
+        assert (ktr, k0, nk) == (0, 1, g.kdm + 2) and addr(host.a) == addr(env[name].a[tlev - 1])      # from layer 0 of slot tlev
+        mirrors[(field, tlev)] = host.a[:nk * g.nrows * g.ncols].copy()
+        lib.calls.append(("upload", field, tlev))
+        return 0
+    real_step = lib.step
+
+    def step(*a):
+        assert sorted(mirrors) == [(9, 1), (9, 2), (10, 1), (10, 2)]        # all four slabs are up before the call
+        before = (cb.q2.copy(), cb.q2l.copy())
+        rc = real_step(*a)
+        ref = util.run_oracle(oracle, lib_cb_before, sea, m, n)
+        mirrors[(9, n)], mirrors[(10, n)] = ref["q2"][n - 1].reshape(-1).copy(), ref["q2l"][n - 1].reshape(-1).copy()
+        assert np.array_equal(cb.q2, before[0], equal_nan=True) and np.array_equal(cb.q2l, before[1], equal_nan=True)
+        return rc
+
+    def download(h, field, ktr, tlev, k0, nk, host):
+        name = {9: "q2", 10: "q2l"}[field]
+        assert tlev == n and (ktr, k0, nk) == (0, 1, g.kdm + 2) and addr(host.a) == addr(env[name].a[tlev - 1])
+        host.a[:nk * g.nrows * g.ncols] = mirrors[(field, tlev)]
+        lib.calls.append(("download", field, tlev))
+        return 0
+    lib_cb_before = copy.deepcopy(cb)
+    env.update(hycom_tsadvc_upload=upload, hycom_tsadvc_step=step, hycom_tsadvc_download=download)
+    kw = dict(defines=("RELO",) + rt._EOS_DEFINES[6], include_dirs=(rt.REF,), skip_calls=rt._SKIP, extra_arrays={"xmin": 1, "xmax": 1},
+              callee_ranks={"hycom_tsadvc_upload": (None,) * 6 + (1,), "hycom_tsadvc_download": (None,) * 6 + (1,)})
+    fx.compile_unit(SHIM, "b200_stop", env, **kw)
+    fx.compile_unit(SHIM, "tsadvc", env, **kw)
+    env["tsadvc"](m, n)
+    order = [c for c in lib.calls if isinstance(c, tuple) or c == "step"]
+    assert order[:4] == [("upload", 9, 1), ("upload", 10, 1), ("upload", 9, 2), ("upload", 10, 2)] and order[4] == "step"
+    assert order[5:] == [("download", 9, n), ("download", 10, n)]
+    inner = util.interior_sea(cb)
+    for name in ("q2", "q2l"):
+        assert np.array_equal(getattr(cb, name)[n - 1, 1:-1][..., inner], getattr(ref_cb, name)[n - 1, 1:-1][..., inner]), name
+    for name in ("temp", "saln"):
+        assert np.array_equal(getattr(cb, name)[n - 1][..., inner], getattr(ref_cb, name)[n - 1][..., inner]), name
