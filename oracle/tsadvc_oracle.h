@@ -9,7 +9,7 @@
  * PARITY PINNED AGAINST THE REFERENCE'S SOURCE TEXT, not against a reference
  * binary: the reference ships no golden vectors, no tests and no input decks,
  * and no Fortran compiler exists in this image or on the GPU boxes, so there is
- * no oracle/_ref.  Instead oracle/fortran_exec.py translates the Fortran of
+ * no gfortran-built oracle/_ref.  Instead oracle/fortran_exec.py translates the Fortran of
  * /root/reference (bigrid.F90, xctilr of mod_xc_sm.h and - on threads - of
  * mod_xc_mp.h incl. ARCTIC, mod_tsadvc.F90
  * with stmt_fns.h, mod_asselin.F90, cnuity.F90) statement by statement into
